@@ -1,0 +1,188 @@
+/* qsb200.h -- plain-C boundary of the B200 many-chain MCMC engine (libqsb200.so).
+ *
+ * This header is what quicksand's Terra host code loads with terralib.includec (the
+ * reference's own FFI mechanism: qs/lib/ad.t:3, qs/lib/random.t:2-7, qs/lib/util.t:45-61,
+ * qs/mcmc.t:12-17).  It is plain C: fixed-width integers, plain pointers and sizes,
+ * opaque handles, no C++ or torch types.  Every entry point returns 0 on success and a
+ * non-zero code on failure (message through qsb_last_error()); nothing aborts or throws
+ * across the boundary -- the Terra shim (qs/b200.t) turns a non-zero return into the
+ * reference's print + abort behaviour (qs/lib/std.t:35-43).
+ *
+ * The boundary sits at the *method* level of the reference,
+ *     method(program) -> terra(samples: &S.Vector(SampleType(program)))   (qs/infer.t:57-69,
+ *                                                                          qs/mcmc.t:45,95-103)
+ * and not at the per-iteration kernel:next level (qs/mcmc.t:63): one FFI call per chain
+ * per iteration would forfeit every fusion the device path depends on.
+ *
+ * Threading: one host thread per sampler (the reference is single-threaded with
+ * process-global state: qs/trace.t:452-454, qs/lib/ad.t:9,19).  Memory: the library never
+ * allocates memory the caller frees and never frees caller memory (qs/infer.t:127
+ * "Caller is responsible for the memory of the returned vector").
+ */
+#ifndef QSB200_H
+#define QSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSB_VERSION 100
+
+/* ---- model families: fixed-structure continuous programs.
+ * A quicksand program of one of these shapes (all choices {struc=false}) is described by a
+ * POD descriptor; anything else (structural choices, discrete ERPs) is rejected on the
+ * Terra side at qs.MCMC(...)(program) time. */
+enum {
+  QSB_FAM_INDEP = 1,         /* K independent ERPs with constant params   (test/testsuite.t:621-691, 719-730) */
+  QSB_FAM_GAUSS_PREC = 2,    /* x_i ~ gaussian(0,1); factor(-0.5 x'Ax)     (config c2) */
+  QSB_FAM_LOGISTIC = 3,      /* theta_j ~ gaussian(0,s); flip.observe(y_i, 1/(1+exp(-x_i.theta)))  (config c3) */
+  QSB_FAM_EIGHT_SCHOOLS = 4, /* mu, logtau, theta_j ~ gaussian(mu, exp(logtau)); gaussian.observe(y_j, theta_j, sigma_j) (c4) */
+  QSB_FAM_FUNNEL = 5         /* v ~ gaussian(0,3); x_i ~ gaussian(0, exp(v/2))  (config c5) */
+};
+
+/* ERP kinds with their bounding transforms as bound in qs/erpdefs.t:
+ * gaussian -> Bounds.None (46-57), gamma -> Lower(0) (61-69), beta -> LowerUpper(0,1) (92-100),
+ * uniform -> LowerUpper(lo,hi) (28-36). */
+enum { QSB_ERP_GAUSSIAN = 0, QSB_ERP_GAMMA = 1, QSB_ERP_BETA = 2, QSB_ERP_UNIFORM = 3 };
+
+/* transition kernels: qs/hmc.t:57-66, qs/drift.t:63-73, qs/harm.t:16-22 */
+enum { QSB_KERNEL_HMC = 1, QSB_KERNEL_DRIFT = 2, QSB_KERNEL_HARM = 3 };
+
+typedef struct qsb_model qsb_model;       /* opaque; owns device copies of the model data */
+typedef struct qsb_sampler qsb_sampler;   /* opaque; owns the SoA chain state in HBM */
+
+/* All pointers are HOST pointers, read during qsb_model_create and not retained. */
+typedef struct {
+  int32_t family;          /* QSB_FAM_* */
+  int32_t dim;             /* number of real components n (unconstrained dimension) */
+  int32_t nobs;            /* LOGISTIC: N rows;  EIGHT_SCHOOLS: J (dim = J+2);  otherwise 0 */
+  int32_t ret_mode;        /* INDEP: 0 = return sum(values)/ret_div (scalar), 1 = return the value vector */
+  double ret_div;
+  double prior_sigma;      /* LOGISTIC: prior standard deviation */
+  const int32_t* erp_kind; /* INDEP [dim] */
+  const double* erp_p0;    /* INDEP [dim]  first ERP parameter  (mu / shape / a / lo) */
+  const double* erp_p1;    /* INDEP [dim]  second ERP parameter (sigma / scale / b / hi) */
+  const double* A;         /* GAUSS_PREC [dim*dim] row-major */
+  const double* X;         /* LOGISTIC [nobs*dim] row-major */
+  const uint8_t* ybin;     /* LOGISTIC [nobs] 0/1 */
+  const double* y;         /* EIGHT_SCHOOLS [nobs] */
+  const double* sigma;     /* EIGHT_SCHOOLS [nobs] */
+} qsb_model_desc;
+
+/* One transition kernel; nspecs > 1 means MixtureKernel(kernels, weights) (qs/mcmc.t:199-291). */
+typedef struct {
+  int32_t kind;        /* QSB_KERNEL_* */
+  int32_t doAdapt;     /* doStepSizeAdapt (hmc.t:61-62) / doScaleAdapt (drift.t:66-67, harm.t:19-20) */
+  double stepSize;     /* HMC: stepSize (hmc.t:59) */
+  uint64_t numSteps;   /* HMC: numSteps (hmc.t:60) */
+  double scale;        /* Drift / HARM: scale (drift.t:65, harm.t:18) */
+  double weight;       /* mixture weight; ignored when nspecs == 1 */
+} qsb_kernel_spec;
+
+enum {
+  QSB_FLAG_MOMENTS = 1u,     /* accumulate per-chain running moments of the kept samples (for split-Rhat) */
+  QSB_FLAG_RECORD = 2u,      /* keep a per-iteration record (state, accept, dH, step, kernel index) -- parity tests */
+  QSB_FLAG_RECORD_LEAP = 4u  /* additionally record the position after every leapfrog step (single HMC kernel) */
+};
+
+typedef struct {
+  uint64_t seed;           /* Philox key; the sub-stream of a draw is (seed, global chain id, iteration, slot) */
+  uint32_t chain_begin;    /* global id of this sampler's first chain (multi-GPU shards: rank * numchains) */
+  uint32_t numchains;      /* chains owned by this sampler; numchains = 1 reproduces the reference's single chain */
+  uint32_t sample_chains;  /* leading chains whose samples are stored (0 = all) */
+  uint32_t flags;          /* QSB_FLAG_* */
+  int32_t device;          /* CUDA device ordinal (-1 = current) */
+  int32_t reserved;
+  void* stream;            /* cudaStream_t to launch on (NULL = default stream) */
+} qsb_run_config;
+
+typedef struct {
+  uint64_t props_made, props_accepted;    /* KernelPropStats summed over chains and sub-kernels (mcmc.t:116-125) */
+  uint64_t sub_made[8], sub_accepted[8];  /* per sub-kernel of a mixture (mcmc.t:256-273) */
+  uint64_t grad_evals;                    /* log-density gradient evaluations (= leapfrog steps + re-gathers) */
+  uint64_t leapfrog_steps;                /* HMCKernel:step calls inside :next, all chains */
+  uint64_t iterations;                    /* MCMC iterations done so far (per chain) */
+  uint64_t kernel_launches;               /* CUDA kernels launched by this sampler so far */
+  double seconds;                         /* device time of the last qsb_sampler_run / advance (CUDA events) */
+} qsb_stats;
+
+int qsb_version(void);
+const char* qsb_last_error(void);
+
+/* ---- models */
+int qsb_model_create(const qsb_model_desc* desc, int32_t device, qsb_model** out);
+int qsb_model_destroy(qsb_model* m);
+int qsb_model_dim(const qsb_model* m);      /* n: real components          (trace.t:830-905) */
+int qsb_model_retdim(const qsb_model* m);   /* length of the return value  (infer.t:47-49)   */
+
+/* ---- samplers: replaces TraceType.salloc():init(true) + KernelType.salloc():init() (mcmc.t:55-56) */
+int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspecs,
+                       const qsb_run_config* cfg, qsb_sampler** out);
+int qsb_sampler_destroy(qsb_sampler* s);
+
+/* Rejection-free forward-sampling initialisation of every chain (trace.t:592-624, erp.t:567-572). */
+int qsb_sampler_init(qsb_sampler* s);
+/* Explicit initial values, ERP option {init=...} (erp.t:57-61, 677-679): x is HOST [numchains][dim],
+ * unconstrained coordinates.  Also used by tests to re-synchronise with the oracle. */
+int qsb_sampler_set_state(qsb_sampler* s, const double* x);
+int qsb_sampler_get_state(qsb_sampler* s, double* x);   /* HOST [numchains][dim], unconstrained */
+
+/* doMCMC (mcmc.t:50-90): iters = burnin + nsamps*lag; iteration i is kept iff i >= burnin and
+ * i % lag == 0.  Restarts the iteration counter at 0 and discards previously kept samples. */
+int qsb_sampler_run(qsb_sampler* s, uint64_t nsamps, uint64_t burnin, uint64_t lag);
+/* Continue the same run by `iters` more iterations (iteration counter keeps counting); every
+ * iteration with (i >= burnin and i % lag == 0) under the parameters of qsb_sampler_begin is kept. */
+int qsb_sampler_begin(qsb_sampler* s, uint64_t max_samples, uint64_t burnin, uint64_t lag, uint64_t numiters);
+int qsb_sampler_advance(qsb_sampler* s, uint64_t iters);
+uint64_t qsb_sampler_num_samples(const qsb_sampler* s);
+
+/* Copy kept samples into caller-owned memory laid out like S.Vector(Sample(T))._data:
+ * element = { double value[retdim]; double logprob; double loglikelihood; }  (infer.t:13-18),
+ * element (c - chain_begin_local) * (sample_end - sample_begin) + (k - sample_begin) at dst + that * stride.
+ * stride_bytes >= (retdim+2)*8.  Chains are sampler-local indices. */
+int qsb_sampler_fetch_samples(qsb_sampler* s, uint32_t chain_begin, uint32_t chain_end,
+                              uint64_t sample_begin, uint64_t sample_end, void* dst, size_t stride_bytes);
+/* Only the values, as a dense HOST array [chain][sample][retdim] (no logprob fields). */
+int qsb_sampler_fetch_values(qsb_sampler* s, uint32_t chain_begin, uint32_t chain_end,
+                             uint64_t sample_begin, uint64_t sample_end, double* dst);
+
+int qsb_sampler_stats(qsb_sampler* s, qsb_stats* out);
+
+/* Cross-chain sufficient statistics of the kept samples, for split-Rhat / pooled moments / ESS.
+ * dst receives, per return-value dimension j (retdim of them), 8 doubles:
+ *   [0] number of half-chains m   [1] draws per half-chain n
+ *   [2] sum over half-chains of the half-chain mean      [3] sum of (half-chain mean)^2
+ *   [4] sum of the half-chain sample variances (n-1)     [5] sum of all draws   [6] sum of all draws^2  [7] reserved
+ * followed (if maxlag > 0) by retdim*(maxlag+1) doubles: sum over chains of the lag-t autocovariance
+ * numerators sum_i (x_i - m_c)(x_{i+t} - m_c), t = 0..maxlag, m_c = the chain's mean.
+ * These are plain sums, so shards on different GPUs combine with one all-reduce(sum).
+ * If dst_is_device != 0, dst is a device pointer on the sampler's device (e.g. a torch tensor
+ * handed to NCCL); otherwise a host pointer. */
+int qsb_sampler_diagnostics(qsb_sampler* s, int32_t maxlag, double* dst, int32_t dst_is_device);
+
+/* Per-iteration record (QSB_FLAG_RECORD): HOST arrays, any may be NULL.
+ *   state [numchains][iters][dim]   accept, kidx [numchains][iters] (int32)   dh, step [numchains][iters]
+ *   leap  [numchains][iters][numSteps][dim]  (QSB_FLAG_RECORD_LEAP) */
+int qsb_sampler_fetch_record(qsb_sampler* s, double* state, int32_t* accept, double* dh, double* step,
+                             int32_t* kidx, double* leap);
+
+/* ---- test hooks (parity with the CPU oracle) */
+/* log-density and gradient of the model at n points x (HOST [n][dim], unconstrained), evaluated by the
+ * device functions the kernels use: lp_dual (with log-Jacobians, what HMC sees: erp.t:623-640), its
+ * gradient grad [n][dim], and lp_float (what Drift/HARM see: no Jacobian, erp.t:361). */
+int qsb_logp_grad(qsb_model* m, const double* x, int32_t n, double* lp_dual, double* grad, double* lp_float);
+/* Device density functions, same selector as the oracle: 1 uniform(x,lo,hi) 2 gaussian(x,mu,sigma)
+ * 3 gamma(x,k,theta) 4 beta(x,a,b) 9 log_gamma(x) 0 bernoulli(val,p); n tuples of 3 doubles. */
+int qsb_logprob(int32_t which, const double* args, int32_t n, double* out);
+/* The injected uniform stream (replaces qs/lib/random.t:5,11) and the Leva Gaussian sampler on it
+ * (qs/distrib.t:61-74), evaluated on the device. */
+int qsb_uniforms(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t slot, int32_t n, double* out);
+int qsb_gaussians(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t slot0, int32_t n, double mu, double sigma, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSB200_H */

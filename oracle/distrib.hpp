@@ -72,7 +72,10 @@ template <class real> inline real log_gamma(real xx) {
 
 // ---- gamma (distrib.t:109-135): Marsaglia-Tsang
 inline double gamma_sample(double shape, double scale) {
-  if (shape < 1.0) return gamma_sample(1.0 + shape, scale) * std::pow(random_(), 1.0 / shape);
+  if (shape < 1.0) {   // left operand first (Terra emits operands in source order); C++ leaves the order unspecified
+    double g = gamma_sample(1.0 + shape, scale);
+    return g * std::pow(random_(), 1.0 / shape);
+  }
   double x, v, u;
   double d = shape - 1.0 / 3.0;
   double c = 1.0 / std::sqrt(9.0 * d);

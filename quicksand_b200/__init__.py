@@ -1,0 +1,13 @@
+"""quicksand_b200 -- B200-native many-chain MCMC engine behind quicksand's infer/MCMC/kernel API.
+
+The compute lives in ``libqsb200.so`` (hand-written CUDA for sm_100a behind the plain-C ABI of
+``include/qsb200.h``); this package is the host-side mirror of the reference's interface for the
+hot path.  There is no CPU fallback: without the built library every compute call raises.
+"""
+from . import programs
+from .api import (Autocorrelation, DriftKernel, Expectation, HARMKernel, HMCKernel, MCMC, MixtureKernel,
+                  Sampler, Samples, SampleVector, infer)
+from .programs import Program
+
+__all__ = ["programs", "Program", "infer", "MCMC", "HMCKernel", "DriftKernel", "HARMKernel", "MixtureKernel",
+           "Samples", "Expectation", "Autocorrelation", "Sampler", "SampleVector"]

@@ -1,0 +1,314 @@
+"""Host-side mirror of the reference's inference interface for the hot path:
+
+    qs.infer(program, query, method)                               qs/infer.t:59-70
+    qs.MCMC(kernel, {numsamps, burnin, lag, verbose})              qs/mcmc.t:36-105
+    qs.HMCKernel{stepSize, numSteps, doStepSizeAdapt}              qs/hmc.t:57-66
+    qs.DriftKernel{scale, doScaleAdapt, lexicalScaleSharing}       qs/drift.t:63-73
+    qs.HARMKernel{scale, doScaleAdapt}                             qs/harm.t:16-22
+    qs.MixtureKernel(kernels, weights)                             qs/mcmc.t:199-291
+    qs.Samples / qs.Expectation / qs.Autocorrelation               qs/infer.t:128-136, 146-187, 213-264
+
+Same names, same parameter meaning, same defaults, same error behaviour (the reference aborts with a
+message; Python raises with the same message).  New optional MCMC params: ``numchains`` (default 1 =
+the reference's single chain, identical sample shape), ``seed``, ``device``, ``chain_begin``.
+Everything numeric happens in libqsb200.so (CUDA); this module only marshals descriptors.
+"""
+import ctypes as C
+import sys
+import time
+
+import numpy as np
+
+from . import _lib as L
+from .programs import Program
+
+
+# ---------------------------------------------------------------------------------------------
+class KernelSpecs:
+    """What a kernel constructor yields: the reference returns ``function(TraceType) -> struct``;
+    here the spec list the B200 driver reads."""
+
+    def __init__(self, specs, names):
+        self.specs, self.names = specs, names
+
+
+def HMCKernel(params=None, **kw):
+    p = dict(params or {}); p.update(kw)
+    unknown = set(p) - {"stepSize", "numSteps", "doStepSizeAdapt"}
+    if unknown:
+        raise TypeError("HMCKernel: unknown params %s" % sorted(unknown))
+    adapt = p.get("doStepSizeAdapt", True)                     # hmc.t:61-62
+    s = L.KernelSpec(L.KERNEL_HMC, int(bool(adapt)), float(p.get("stepSize", 1.0)), int(p.get("numSteps", 1)), 1.0, 1.0)
+    return KernelSpecs([s], ["HMCKernel"])
+
+
+def DriftKernel(params=None, **kw):
+    p = dict(params or {}); p.update(kw)
+    unknown = set(p) - {"scale", "doScaleAdapt", "lexicalScaleSharing"}
+    if unknown:
+        raise TypeError("DriftKernel: unknown params %s" % sorted(unknown))
+    if p.get("lexicalScaleSharing", False):
+        raise NotImplementedError("DriftKernel: lexicalScaleSharing is a next-row item (SURVEY.md 8f-4)")
+    adapt = p.get("doScaleAdapt", True)                        # drift.t:66-67
+    s = L.KernelSpec(L.KERNEL_DRIFT, int(bool(adapt)), 1.0, 1, float(p.get("scale", 1.0)), 1.0)
+    return KernelSpecs([s], ["DriftKernel"])
+
+
+def HARMKernel(params=None, **kw):
+    p = dict(params or {}); p.update(kw)
+    unknown = set(p) - {"scale", "doScaleAdapt"}
+    if unknown:
+        raise TypeError("HARMKernel: unknown params %s" % sorted(unknown))
+    adapt = p.get("doScaleAdapt", True)                        # harm.t:19-20
+    s = L.KernelSpec(L.KERNEL_HARM, int(bool(adapt)), 1.0, 1, float(p.get("scale", 1.0)), 1.0)
+    return KernelSpecs([s], ["HARMKernel"])
+
+
+def MixtureKernel(kernels, weights):
+    assert len(kernels) == len(weights), "MixtureKernel: number of kernels must equal number of weights"   # mcmc.t:200-201
+    specs, names = [], []
+    for k, w in zip(kernels, weights):
+        if len(k.specs) != 1:
+            raise NotImplementedError("MixtureKernel: nested mixtures are not supported")
+        s = k.specs[0]
+        specs.append(L.KernelSpec(s.kind, s.doAdapt, s.stepSize, s.numSteps, s.scale, float(w)))
+        names.append(k.names[0])
+    return KernelSpecs(specs, names)
+
+
+# ---------------------------------------------------------------------------------------------
+class Sampler:
+    """One ``qsb_sampler``: the SoA state of ``numchains`` chains of one program under one kernel,
+    resident in HBM.  Thin wrapper over the C ABI; used by MCMC(), the tests and bench.py."""
+
+    def __init__(self, program, kernel, numchains=1, seed=0, device=-1, chain_begin=0, sample_chains=0,
+                 flags=0, stream=None, mapping=0):
+        assert isinstance(program, Program), "MCMC: expected a qs.program"      # progmod.assertIsProgram (mcmc.t:46)
+        self.program, self.kernel = program, kernel
+        self.numchains = int(numchains)
+        self.sample_chains = int(sample_chains) if sample_chains else self.numchains
+        self.retdim, self.dim = program.retdim, program.dim
+        arr = (L.KernelSpec * len(kernel.specs))(*kernel.specs)
+        cfg = L.RunConfig(int(seed), int(chain_begin), self.numchains, int(sample_chains), int(flags), int(device), int(mapping),
+                          C.c_void_p(stream) if stream else None)
+        self.h = C.c_void_p()
+        self.flags = flags
+        self._numiters = 0
+        L.check(L.lib().qsb_sampler_create(program.model(device), arr, len(kernel.specs), C.byref(cfg), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            L.lib().qsb_sampler_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self):
+        L.check(L.lib().qsb_sampler_init(self.h))
+
+    def set_state(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.numchains, self.dim)
+        L.check(L.lib().qsb_sampler_set_state(self.h, x.ctypes.data_as(L.dp)))
+
+    def get_state(self):
+        x = np.empty((self.numchains, self.dim))
+        L.check(L.lib().qsb_sampler_get_state(self.h, x.ctypes.data_as(L.dp)))
+        return x
+
+    def run(self, nsamps, burnin=0, lag=1):
+        self._numiters = burnin + nsamps * lag
+        L.check(L.lib().qsb_sampler_run(self.h, nsamps, burnin, lag))
+
+    def begin(self, max_samples, burnin=0, lag=1, numiters=0):
+        self._numiters = numiters
+        L.check(L.lib().qsb_sampler_begin(self.h, max_samples, burnin, lag, numiters))
+
+    def advance(self, iters):
+        L.check(L.lib().qsb_sampler_advance(self.h, iters))
+
+    def num_samples(self):
+        return int(L.lib().qsb_sampler_num_samples(self.h))
+
+    def sample_dtype(self):
+        """C layout of Sample(T) = { T value; double logprob; double loglikelihood } (infer.t:13-18)."""
+        return np.dtype([("value", np.float64, (self.retdim,)), ("logprob", np.float64), ("loglikelihood", np.float64)])
+
+    def fetch_samples(self, chain_begin=0, chain_end=None, sample_begin=0, sample_end=None, out=None):
+        chain_end = self.sample_chains if chain_end is None else chain_end
+        sample_end = self.num_samples() if sample_end is None else sample_end
+        dt = self.sample_dtype()
+        if out is None:
+            out = np.empty((chain_end - chain_begin, sample_end - sample_begin), dtype=dt)
+        L.check(L.lib().qsb_sampler_fetch_samples(self.h, chain_begin, chain_end, sample_begin, sample_end,
+                                                  out.ctypes.data_as(C.c_void_p), dt.itemsize))
+        return out
+
+    def fetch_values(self, chain_begin=0, chain_end=None, sample_begin=0, sample_end=None, out=None):
+        chain_end = self.sample_chains if chain_end is None else chain_end
+        sample_end = self.num_samples() if sample_end is None else sample_end
+        if out is None:
+            out = np.empty((chain_end - chain_begin, sample_end - sample_begin, self.retdim))
+        L.check(L.lib().qsb_sampler_fetch_values(self.h, chain_begin, chain_end, sample_begin, sample_end, out.ctypes.data_as(L.dp)))
+        return out
+
+    def stats(self):
+        st = L.Stats()
+        L.check(L.lib().qsb_sampler_stats(self.h, C.byref(st)))
+        n = len(self.kernel.specs)
+        return dict(props_made=st.props_made, props_accepted=st.props_accepted, sub_made=list(st.sub_made)[:n],
+                    sub_accepted=list(st.sub_accepted)[:n], grad_evals=st.grad_evals, leapfrog_steps=st.leapfrog_steps,
+                    iterations=st.iterations, kernel_launches=st.kernel_launches, seconds=st.seconds)
+
+    def diagnostics_raw(self, maxlag=0, out_ptr=None):
+        """Sufficient statistics (see qsb_sampler_diagnostics).  ``out_ptr``: device pointer (e.g. a torch
+        tensor's data_ptr()) to write into for a following NCCL all-reduce; otherwise a numpy array."""
+        n = self.retdim * 8 + (self.retdim * (maxlag + 1) if maxlag > 0 else 0)
+        if out_ptr is not None:
+            L.check(L.lib().qsb_sampler_diagnostics(self.h, maxlag, C.c_void_p(out_ptr), 1))
+            return None
+        out = np.empty(n)
+        L.check(L.lib().qsb_sampler_diagnostics(self.h, maxlag, out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+    def fetch_record(self, leap=False):
+        T, Cn, d = self._numiters, self.numchains, self.dim
+        state = np.zeros((Cn, T, d)); acc = np.zeros((Cn, T), dtype=np.int32); dh = np.zeros((Cn, T)); step = np.zeros((Cn, T))
+        nsub = len(self.kernel.specs)
+        kidx = np.zeros((Cn, T), dtype=np.int32) if nsub > 1 else None
+        lf = np.zeros((Cn, T, int(self.kernel.specs[0].numSteps), d)) if leap else None
+        L.check(L.lib().qsb_sampler_fetch_record(
+            self.h, state.ctypes.data_as(L.dp), acc.ctypes.data_as(L.ip), dh.ctypes.data_as(L.dp), step.ctypes.data_as(L.dp),
+            kidx.ctypes.data_as(L.ip) if kidx is not None else None, lf.ctypes.data_as(L.dp) if lf is not None else None))
+        return dict(state=state, accept=acc, dH=dh, step=step, kidx=kidx, leapfrog=lf)
+
+
+# ---------------------------------------------------------------------------------------------
+class SampleVector:
+    """The filled ``S.Vector(Sample(T))`` (qs/infer.t:12-36; qs/lib/std.t:219-351): ``data`` is a
+    structured array [numchains][nsamps] of {value[retdim], logprob, loglikelihood}.  With
+    numchains == 1 it is indexable like the reference's single vector of samples."""
+
+    def __init__(self, data):
+        self.data = data
+
+    def size(self):
+        return self.data.shape[1]
+
+    @property
+    def value(self):
+        return self.data["value"]
+
+    @property
+    def logprob(self):
+        return self.data["logprob"]
+
+    def __len__(self):
+        return self.data.shape[1]
+
+    def __getitem__(self, i):
+        return self.data[0, i]
+
+
+def MCMC(kernel, params=None, **kw):
+    """``MCMC(kernel, params)`` -> ``function(program)`` -> ``run(samples)`` (qs/mcmc.t:36-105)."""
+    p = dict(params or {}); p.update(kw)
+    numsamps = int(p.get("numsamps", 1000))       # mcmc.t:38
+    burnin = int(p.get("burnin", 0))              # mcmc.t:39
+    lag = int(p.get("lag", 1))                    # mcmc.t:40 (the code's default, not the comment's)
+    verbose = p.get("verbose", False)
+    numchains = int(p.get("numchains", 1))
+    seed = int(p.get("seed", 0))
+    device = int(p.get("device", -1))
+    chain_begin = int(p.get("chain_begin", 0))
+
+    def method(program):
+        assert isinstance(program, Program), "MCMC: argument is not a qs.program"
+
+        def doMCMC(samples=None):
+            out = sys.stdout if verbose is True else (verbose or None)
+            s = Sampler(program, kernel, numchains=numchains, seed=seed, device=device, chain_begin=chain_begin)
+            try:
+                s.init()
+                t0 = time.time()
+                s.run(numsamps, burnin, lag)
+                data = s.fetch_samples()
+                if out:   # mcmc.t:73-89, same line formats
+                    st = s.stats()
+                    pm, pa = st["props_made"], st["props_accepted"]
+                    out.write("Acceptance Ratio: %u/%u (%g%%)\n" % (pa, pm, 100.0 * pa / max(pm, 1)))
+                    if len(kernel.specs) > 1:   # MixtureKernel:printStats (mcmc.t:256-273)
+                        for name, m_, a_ in zip(kernel.names, st["sub_made"], st["sub_accepted"]):
+                            out.write("   %s Acceptance Ratio: %u/%u (%g%%)\n" % (name, a_, m_, 100.0 * a_ / max(m_, 1)))
+                    out.write("Time: %g\n" % (time.time() - t0))
+            finally:
+                s.close()
+            vec = SampleVector(data)
+            if samples is not None:
+                samples.data = data
+            return vec
+        return doMCMC
+    return method
+
+
+# ---- queries (qs/infer.t:128-294, the ones the hot path feeds)
+def Samples():
+    return lambda program: (lambda samples: samples)
+
+
+def Expectation(doVariance=False):
+    """infer.t:146-187, per chain: the mean starts at value[0] and the weights are summed from i=1,
+    so for MCMC samples (loglikelihood = 0) mean = sum(v)/(N-1); variance divides by N.  Returns
+    [numchains][retdim] (and [numchains]); squeezed to the reference's shape when numchains == 1."""
+    def query(program):
+        def run(samples):
+            v = samples.value                                  # [C][N][retdim]
+            w = np.exp(samples.data["loglikelihood"])          # [C][N]
+            totalw = w[:, 1:].sum(axis=1)
+            m = (v[:, 0, :] + (w[:, 1:, None] * v[:, 1:, :]).sum(axis=1)) / totalw[:, None]
+            if v.shape[2] == 1:
+                m_out = m[:, 0]
+            else:
+                m_out = m
+            if not doVariance:
+                return m_out[0] if v.shape[0] == 1 else m_out
+            diff = v - m[:, None, :]
+            var = (diff * diff).sum(axis=2).sum(axis=1) / v.shape[1]
+            return (m_out[0], var[0]) if v.shape[0] == 1 else (m_out, var)
+        return run
+    return query
+
+
+def Autocorrelation(mean=None, variance=None):
+    """infer.t:213-264, per chain."""
+    def query(program):
+        def run(samples):
+            v = samples.value
+            Cn, N, _ = v.shape
+            if mean is None or variance is None:
+                m, var = Expectation(True)(program)(SampleVector(samples.data))
+                m = np.reshape(m, (Cn, -1)); var = np.reshape(var, (Cn,))
+            else:
+                m = np.broadcast_to(np.reshape(mean, (1, -1)), (Cn, v.shape[2])); var = np.full(Cn, variance)
+            diff = v - m[:, None, :]
+            ac = np.zeros((Cn, N))
+            for t in range(N):
+                n = N - t
+                ac[:, t] = (diff[:, :n, :] * diff[:, t:, :]).sum(axis=(1, 2)) / (n * var)
+            return ac[0] if Cn == 1 else ac
+        return run
+    return query
+
+
+def infer(program, query, method):
+    """qs/infer.t:59-70: returns a function; calling it runs ``method`` and applies ``query``."""
+    methodfn = method(program)
+    queryfn = query(program)
+
+    def run():
+        samples = methodfn()
+        return queryfn(samples)
+    return run

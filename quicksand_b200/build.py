@@ -1,0 +1,73 @@
+"""Build libqsb200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m quicksand_b200.build [--force]
+
+Each translation unit is compiled to an object in parallel, then linked with ``nvcc -shared``.
+The library links only the CUDA runtime: no torch, no Python -- Terra loads it directly.
+"""
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libqsb200.so")
+SOURCES = ["capi.cu", "glm_hmc.cu", "engine_f1.cu", "engine_f2.cu", "engine_f4.cu", "engine_f5.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if p and (os.path.isabs(p) and os.path.exists(p) or not os.path.isabs(p)):
+            return p
+    return "nvcc"
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(HERE, "..", "include", "qsb200.h"))
+    jobs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or _stale(o, [s] + headers):
+            jobs.append((s, o))
+
+    def compile_one(job):
+        s, o = job
+        r = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
+        with open(o + ".log", "w") as f:
+            f.write(r.stdout + r.stderr)
+        return s, r.returncode, r.stdout + r.stderr
+
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for s, rc, out in ex.map(compile_one, jobs):
+                if rc != 0:
+                    sys.stderr.write(out)
+                    raise RuntimeError("nvcc failed on %s" % s)
+                if verbose:
+                    print("compiled", os.path.basename(s))
+    objs = [os.path.join(OBJ, src.replace(".cu", ".o")) for src in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        r = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,701 @@
+// C-ABI of libqsb200.so (include/qsb200.h): host-side sampler objects over the chain-parallel
+// engine (engine.cuh) and the GLM tensor-core path (glm_hmc.cu).  Plain CUDA runtime; no torch.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/qsb200.h"
+#include "engine.cuh"
+#include "glm_hmc.cuh"
+
+namespace qsb {
+extern const EngineVariant g_variants_f1[]; extern const int g_nvariants_f1;
+extern const EngineVariant g_variants_f2[]; extern const int g_nvariants_f2;
+extern const EngineVariant g_variants_f4[]; extern const int g_nvariants_f4;
+extern const EngineVariant g_variants_f5[]; extern const int g_nvariants_f5;
+}  // namespace qsb
+
+using namespace qsb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(100 + (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct DevArena {
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  template <class T> cudaError_t alloc(T** p, size_t n, bool zero = true) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(*p);
+    bytes += n * sizeof(T);
+    if (zero) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+  }
+  void release() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); }
+};
+
+struct qsb_model {
+  qsb_model_desc desc;
+  int device = 0;
+  int retdim = 0;
+  std::vector<double> A;      // GAUSS_PREC host copy
+  ModelDev dev;
+  DevArena arena;
+  GlmModel glm;               // LOGISTIC
+};
+
+struct qsb_sampler {
+  qsb_model* m = nullptr;
+  qsb_run_config cfg;
+  std::vector<qsb_kernel_spec> specs;
+  EngineParams P;
+  const EngineVariant* var = nullptr;
+  GlmSampler* glm = nullptr;
+  DevArena arena;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint64_t iter = 0, burnin = 0, lag = 1, max_samples = 0, numiters = 0;
+  uint64_t launches = 0;
+  double seconds = 0.0;
+  bool inited = false;
+  uint64_t rec_iters = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+__global__ void precompute_obs_kernel(const double* sigma, double* cy, double* s2, int n) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) { double s = sigma[j]; cy[j] = 1.8378770664093453 + 2.0 * log(s); s2[j] = s * s; }
+}
+
+// device sample layout -> AoS Sample elements { value[retdim], logprob, loglikelihood } (infer.t:13-18)
+__global__ void gather_samples_kernel(const double* samples, const double* samp_lp, int G, uint32_t SC, int retdim,
+                                      uint32_t c0, uint32_t nc, uint64_t s0, uint64_t ns, double* out, size_t stride_d, int with_lp) {
+  size_t total = (size_t)nc * ns * (retdim + (with_lp ? 2 : 0));
+  int w = retdim + (with_lp ? 2 : 0);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(t % w);
+    size_t r = t / w;
+    uint64_t k = s0 + r % ns;
+    uint32_t c = c0 + (uint32_t)(r / ns);
+    double v;
+    if (j < retdim) v = samples[G == 1 ? ((size_t)k * retdim + j) * SC + c : ((size_t)k * SC + c) * retdim + j];
+    else if (j == retdim) v = samp_lp[(size_t)k * SC + c];
+    else v = 0.0;   // loglikelihood = 0 (mcmc.t:70)
+    out[r * stride_d + j] = v;
+  }
+}
+
+// per-(chain, dim) statistics of kept draws -> per-dim sums (see qsb_sampler_diagnostics in qsb200.h)
+__global__ void diagnostics_kernel(const double* samples, int G, uint32_t SC, int retdim, uint64_t n, int maxlag, double* out) {
+  size_t total = (size_t)SC * retdim;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t c; int j;
+  if (G == 1) { c = (uint32_t)(t % SC); j = (int)(t / SC); } else { j = (int)(t % retdim); c = (uint32_t)(t / retdim); }
+  auto at = [&](uint64_t k) { return samples[G == 1 ? ((size_t)k * retdim + j) * SC + c : ((size_t)k * SC + c) * retdim + j]; };
+  const uint64_t h = n / 2;
+  double* o = out + (size_t)j * 8;
+  double sum_all = 0.0, sq_all = 0.0;
+  for (int half = 0; half < 2; ++half) {
+    if (h < 2) break;
+    uint64_t b = half * h;
+    double s = 0.0;
+    for (uint64_t k = b; k < b + h; ++k) s += at(k);
+    double mean = s / (double)h, m2 = 0.0;
+    for (uint64_t k = b; k < b + h; ++k) { double dlt = at(k) - mean; m2 += dlt * dlt; }
+    atomicAdd(&o[2], mean); atomicAdd(&o[3], mean * mean); atomicAdd(&o[4], m2 / (double)(h - 1));
+  }
+  for (uint64_t k = 0; k < n; ++k) { double v = at(k); sum_all += v; sq_all += v * v; }
+  atomicAdd(&o[5], sum_all); atomicAdd(&o[6], sq_all);
+  if (maxlag > 0 && n > 1) {
+    double mean = sum_all / (double)n;
+    double* ac = out + (size_t)retdim * 8 + (size_t)j * (maxlag + 1);
+    for (int lagv = 0; lagv <= maxlag && (uint64_t)lagv < n; ++lagv) {
+      double s = 0.0;
+      for (uint64_t k = 0; k + lagv < n; ++k) s += (at(k) - mean) * (at(k + lagv) - mean);
+      atomicAdd(&ac[lagv], s);
+    }
+  }
+}
+__global__ void diagnostics_header_kernel(double* out, int retdim, double m, double n) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < retdim) { out[(size_t)j * 8 + 0] = m; out[(size_t)j * 8 + 1] = n; }
+}
+
+__global__ void uniforms_kernel(RngKey key, uint32_t chain, uint32_t iter, uint32_t slot, int n, double* out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    SubStream s(key, chain, iter, slot);
+    for (int i = 0; i < n; ++i) out[i] = s.random();
+  }
+}
+__global__ void gaussians_kernel(RngKey key, uint32_t chain, uint32_t iter, uint32_t slot0, int n, double mu, double sigma, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = gaussian_sample(key, chain, iter, slot0 + (uint32_t)i, mu, sigma);
+}
+__global__ void logprob_kernel(int which, const double* a, int n, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* v = a + 3 * (size_t)i;
+  double r;
+  switch (which) {
+    case 0: r = bernoulli_lp(v[0] != 0.0, v[1]); break;
+    case 1: r = uniform_lp(v[0], v[1], v[2]); break;
+    case 2: r = gaussian_lp(v[0], v[1], v[2]); break;
+    case 3: r = gamma_lp(v[0], v[1], v[2]); break;
+    case 4: r = beta_lp(v[0], v[1], v[2]); break;
+    case 9: r = log_gamma5(v[0]); break;
+    default: r = nan(""); break;
+  }
+  out[i] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+static const EngineVariant* pick_variant(int family, int d, int mapping, std::string& why) {
+  const EngineVariant* tab = nullptr; int n = 0;
+  switch (family) {
+    case QSB_FAM_INDEP: tab = g_variants_f1; n = g_nvariants_f1; break;
+    case QSB_FAM_GAUSS_PREC: tab = g_variants_f2; n = g_nvariants_f2; break;
+    case QSB_FAM_EIGHT_SCHOOLS: tab = g_variants_f4; n = g_nvariants_f4; break;
+    case QSB_FAM_FUNNEL: tab = g_variants_f5; n = g_nvariants_f5; break;
+    default: why = "family has no chain-parallel engine variant"; return nullptr;
+  }
+  const EngineVariant* best = nullptr;
+  for (int i = 0; i < n; ++i) {
+    const EngineVariant& v = tab[i];
+    if (mapping != 0 && v.G != mapping) continue;
+    if ((long)v.G * v.npl < d) continue;
+    if (!best || (long)v.G * v.npl < (long)best->G * best->npl) best = &v;
+  }
+  if (!best) why = "no engine variant for dim=" + std::to_string(d) + " (family " + std::to_string(family) + ", mapping " + std::to_string(mapping) + ")";
+  return best;
+}
+
+template <class T> static cudaError_t fill(T* p, size_t n, T v, cudaStream_t st) {
+  std::vector<T> h(n, v);
+  return cudaMemcpyAsync(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, st) == cudaSuccess ? cudaStreamSynchronize(st) : cudaGetLastError();
+}
+
+extern "C" {
+
+int qsb_version(void) { return QSB_VERSION; }
+const char* qsb_last_error(void) { return g_err.c_str(); }
+
+int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
+  if (!d || !out) return fail(1, "qsb_model_create: null argument");
+  *out = nullptr;
+  if (d->dim <= 0) return fail(2, "qsb_model_create: dim must be positive");
+  if (device >= 0) CU(cudaSetDevice(device)); else CU(cudaGetDevice(&device));
+  qsb_model* m = new qsb_model();
+  m->desc = *d; m->device = device;
+  memset(&m->dev, 0, sizeof(m->dev));
+  m->dev.family = d->family; m->dev.dim = d->dim; m->dev.nobs = d->nobs; m->dev.ret_mode = d->ret_mode;
+  m->dev.ret_div = d->ret_div; m->dev.prior_sigma = d->prior_sigma;
+  m->retdim = d->dim;
+  auto bail = [&](int code, const std::string& msg) { m->arena.release(); delete m; return fail(code, msg); };
+  switch (d->family) {
+    case QSB_FAM_INDEP: {
+      if (!d->erp_kind || !d->erp_p0 || !d->erp_p1) return bail(3, "INDEP: erp_kind/erp_p0/erp_p1 required");
+      for (int i = 0; i < d->dim; ++i) if (d->erp_kind[i] < 0 || d->erp_kind[i] > 3) return bail(3, "INDEP: unsupported ERP kind (continuous gaussian/gamma/beta/uniform only)");
+      int* k; double *p0, *p1;
+      if (m->arena.alloc(&k, d->dim) || m->arena.alloc(&p0, d->dim) || m->arena.alloc(&p1, d->dim)) return bail(4, "cudaMalloc failed");
+      cudaMemcpy(k, d->erp_kind, sizeof(int) * d->dim, cudaMemcpyHostToDevice);
+      cudaMemcpy(p0, d->erp_p0, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
+      cudaMemcpy(p1, d->erp_p1, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
+      m->dev.erp_kind = k; m->dev.p0 = p0; m->dev.p1 = p1;
+      if (d->ret_mode == 0) m->retdim = 1;
+      break;
+    }
+    case QSB_FAM_GAUSS_PREC: {
+      if (!d->A) return bail(3, "GAUSS_PREC: A required");
+      if (d->dim > 16) return bail(3, "GAUSS_PREC: dim <= 16 supported (thread-per-chain register path)");
+      m->A.assign(d->A, d->A + (size_t)d->dim * d->dim);
+      break;
+    }
+    case QSB_FAM_LOGISTIC: {
+      if (!d->X || !d->ybin || d->nobs <= 0) return bail(3, "LOGISTIC: X, ybin, nobs required");
+      std::string why;
+      if (glm_model_create(&m->glm, d->X, d->ybin, d->nobs, d->dim, d->prior_sigma, why)) return bail(5, "LOGISTIC: " + why);
+      break;
+    }
+    case QSB_FAM_EIGHT_SCHOOLS: {
+      if (!d->y || !d->sigma || d->nobs <= 0 || d->dim != d->nobs + 2) return bail(3, "EIGHT_SCHOOLS: y, sigma required and dim == nobs + 2");
+      double *y, *sg, *cy, *s2;
+      if (m->arena.alloc(&y, d->nobs) || m->arena.alloc(&sg, d->nobs) || m->arena.alloc(&cy, d->nobs) || m->arena.alloc(&s2, d->nobs)) return bail(4, "cudaMalloc failed");
+      cudaMemcpy(y, d->y, sizeof(double) * d->nobs, cudaMemcpyHostToDevice);
+      cudaMemcpy(sg, d->sigma, sizeof(double) * d->nobs, cudaMemcpyHostToDevice);
+      precompute_obs_kernel<<<(d->nobs + 127) / 128, 128>>>(sg, cy, s2, d->nobs);
+      if (cudaDeviceSynchronize() != cudaSuccess) return bail(6, "precompute_obs_kernel failed");
+      m->dev.y = y; m->dev.cy = cy; m->dev.s2 = s2;
+      break;
+    }
+    case QSB_FAM_FUNNEL: break;
+    default: return bail(2, "qsb_model_create: unknown family");
+  }
+  *out = m;
+  return 0;
+}
+
+int qsb_model_destroy(qsb_model* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  glm_model_destroy(&m->glm);
+  m->arena.release();
+  delete m;
+  return 0;
+}
+int qsb_model_dim(const qsb_model* m) { return m ? m->desc.dim : -1; }
+int qsb_model_retdim(const qsb_model* m) { return m ? m->retdim : -1; }
+
+static void free_run_buffers(qsb_sampler* s) {
+  EngineParams& P = s->P;
+  for (double** p : {&P.samples, &P.samp_lp, &P.rec_state, &P.rec_dh, &P.rec_step, &P.rec_leap}) if (*p) { cudaFree(*p); *p = nullptr; }
+  for (int** p : {&P.rec_accept, &P.rec_kidx}) if (*p) { cudaFree(*p); *p = nullptr; }
+  s->rec_iters = 0; P.rec_iters = 0;
+}
+
+static int alloc_engine_state(qsb_sampler* s) {
+  EngineParams& P = s->P;
+  const size_t C = P.C, d = P.d, ns = P.nsub;
+  DevArena& a = s->arena;
+  bool has_hmc = false, has_drift = false, has_harm = false;
+  for (auto& k : s->specs) { has_hmc |= k.kind == QSB_KERNEL_HMC; has_drift |= k.kind == QSB_KERNEL_DRIFT; has_harm |= k.kind == QSB_KERNEL_HARM; }
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(a.alloc(&P.x, C * d)); A(a.alloc(&P.lp, C)); A(a.alloc(&P.flags, C));
+  A(a.alloc(&P.eps, C));   // also the lp_float output of the logp_grad test hook
+  A(a.alloc(&P.g, C * d));
+  if (has_hmc) {
+    A(a.alloc(&P.da_gbar, C)); A(a.alloc(&P.da_xbar, C)); A(a.alloc(&P.da_x0, C)); A(a.alloc(&P.da_lastx, C)); A(a.alloc(&P.da_gamma, C));
+    A(a.alloc(&P.da_k, C));
+  }
+  if (has_drift) { A(a.alloc(&P.dr_mean, C * d)); A(a.alloc(&P.dr_m2, C * d)); A(a.alloc(&P.dr_s0, C)); A(a.alloc(&P.dr_mult, C)); A(a.alloc(&P.dr_n, C)); }
+  if (has_harm) A(a.alloc(&P.ha_scale, C));
+  A(a.alloc(&P.made, ns * C)); A(a.alloc(&P.acc, ns * C));
+  A(a.alloc(&P.counters, 4)); A(a.alloc(&P.status, 1));
+  if (e != cudaSuccess) return fail(4, std::string("cudaMalloc (chain state): ") + cudaGetErrorString(e));
+  return 0;
+}
+
+static int reset_kernel_state(qsb_sampler* s) {
+  EngineParams& P = s->P;
+  const size_t C = P.C, d = P.d;
+  cudaStream_t st = s->stream;
+  CU(cudaMemsetAsync(P.flags, 0, C, st));
+  CU(cudaMemsetAsync(P.made, 0, sizeof(unsigned long long) * P.nsub * C, st));
+  CU(cudaMemsetAsync(P.acc, 0, sizeof(unsigned long long) * P.nsub * C, st));
+  CU(cudaMemsetAsync(P.counters, 0, sizeof(unsigned long long) * 4, st));
+  CU(cudaMemsetAsync(P.status, 0, sizeof(int), st));
+  for (int k = 0; k < P.nsub; ++k) {
+    if (P.kind[k] == K_HMC) {
+      CU(fill(P.eps, C, P.stepSize0[k], st));
+      CU(cudaMemsetAsync(P.da_gbar, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_xbar, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_x0, 0, 8 * C, st));
+      CU(cudaMemsetAsync(P.da_lastx, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_gamma, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_k, 0, 4 * C, st));
+    } else if (P.kind[k] == K_DRIFT) {
+      CU(fill(P.dr_s0, C, P.scale0[k], st)); CU(fill(P.dr_mult, C, 1.0, st));
+      CU(cudaMemsetAsync(P.dr_n, 0, 4 * C, st)); CU(cudaMemsetAsync(P.dr_mean, 0, 8 * C * d, st)); CU(cudaMemsetAsync(P.dr_m2, 0, 8 * C * d, st));
+    } else if (P.kind[k] == K_HARM) {
+      CU(fill(P.ha_scale, C, P.scale0[k], st));
+    }
+  }
+  return 0;
+}
+
+int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspecs, const qsb_run_config* cfg, qsb_sampler** out) {
+  if (!m || !specs || !cfg || !out) return fail(1, "qsb_sampler_create: null argument");
+  *out = nullptr;
+  if (nspecs < 1 || nspecs > MAX_SUB) return fail(2, "qsb_sampler_create: 1..8 kernels");
+  if (cfg->numchains == 0) return fail(2, "qsb_sampler_create: numchains must be positive");
+  int nh = 0, nd = 0, nr = 0;
+  for (int i = 0; i < nspecs; ++i) {
+    switch (specs[i].kind) {
+      case QSB_KERNEL_HMC: ++nh; if (specs[i].numSteps < 1 || specs[i].numSteps > 0xFFFFFFFFull) return fail(2, "HMC: numSteps out of range"); break;
+      case QSB_KERNEL_DRIFT: ++nd; break;
+      case QSB_KERNEL_HARM: ++nr; break;
+      default: return fail(2, "qsb_sampler_create: unknown kernel kind");
+    }
+  }
+  if (nh > 1 || nd > 1 || nr > 1) return fail(2, "qsb_sampler_create: at most one kernel of each kind per mixture");
+  CU(cudaSetDevice(m->device));
+  qsb_sampler* s = new qsb_sampler();
+  s->m = m; s->cfg = *cfg; s->specs.assign(specs, specs + nspecs);
+  s->stream = (cudaStream_t)cfg->stream;
+  if (s->cfg.sample_chains == 0 || s->cfg.sample_chains > cfg->numchains) s->cfg.sample_chains = cfg->numchains;
+  auto bail = [&](int code, const std::string& msg) { s->arena.release(); if (s->glm) glm_sampler_destroy(s->glm); delete s; return fail(code, msg); };
+  if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(4, "cudaEventCreate failed");
+  if (m->desc.family == QSB_FAM_LOGISTIC) {
+    if (nspecs != 1 || specs[0].kind != QSB_KERNEL_HMC) return bail(2, "LOGISTIC: the tensor-core path implements HMCKernel only");
+    std::string why;
+    s->glm = glm_sampler_create(&m->glm, specs[0].stepSize, (uint32_t)specs[0].numSteps, specs[0].doAdapt != 0, cfg->seed, cfg->chain_begin,
+                                cfg->numchains, s->cfg.sample_chains, cfg->flags, (void*)s->stream, why);
+    if (!s->glm) return bail(5, "LOGISTIC: " + why);
+    *out = s;
+    return 0;
+  }
+  EngineParams& P = s->P;
+  memset(&P, 0, sizeof(P));
+  P.m = m->dev;
+  P.key = RngKey{(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
+  P.chain_begin = cfg->chain_begin; P.C = cfg->numchains; P.d = m->desc.dim; P.retdim = m->retdim;
+  P.nsub = nspecs;
+  for (int i = 0; i < nspecs; ++i) {
+    P.kind[i] = specs[i].kind; P.doAdapt[i] = specs[i].doAdapt; P.stepSize0[i] = specs[i].stepSize;
+    P.numSteps[i] = (uint32_t)specs[i].numSteps; P.scale0[i] = specs[i].scale; P.weight[i] = specs[i].weight;
+  }
+  P.sample_chains = s->cfg.sample_chains;
+  P.lag = 1;
+  std::string why;
+  s->var = pick_variant(m->desc.family, P.d, cfg->reserved, why);
+  if (!s->var) return bail(2, why);
+  if (m->desc.family == QSB_FAM_GAUSS_PREC) {
+    const int d = P.d, npl = s->var->npl;
+    for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) P.Sc[i * npl + j] = m->A[(size_t)i * d + j] + m->A[(size_t)j * d + i];
+  }
+  if (int rc = alloc_engine_state(s)) { std::string e = g_err; return bail(rc, e); }
+  if (int rc = reset_kernel_state(s)) { std::string e = g_err; return bail(rc, e); }
+  *out = s;
+  return 0;
+}
+
+int qsb_sampler_destroy(qsb_sampler* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->m->device);
+  cudaStreamSynchronize(s->stream);
+  if (s->glm) glm_sampler_destroy(s->glm);
+  else free_run_buffers(s);
+  s->arena.release();
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+  return 0;
+}
+
+static int check_status(qsb_sampler* s) {
+  int st = 0;
+  CU(cudaMemcpyAsync(&st, s->P.status, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (st & ERR_NAN_SEARCH) return fail(20, "HMC step size search failed because logprob became NaN");                                  // hmc.t:361-365
+  if (st & ERR_SEARCH_INF) return fail(21, "HMC step size search diverged to infinity (Is your probability distribution flat?)");        // hmc.t:381-384
+  if (st & ERR_SEARCH_ZERO) return fail(22, "HMC step size search collapsed to zero (Is your probability distribution discontinuous?)"); // hmc.t:385-388
+  return 0;
+}
+
+int qsb_sampler_init(qsb_sampler* s) {
+  if (!s) return fail(1, "null sampler");
+  CU(cudaSetDevice(s->m->device));
+  if (s->glm) { std::string why; if (glm_sampler_init(s->glm, why)) return fail(5, why); s->inited = true; s->iter = 0; return 0; }
+  if (int rc = reset_kernel_state(s)) return rc;
+  s->var->init(s->P, s->stream); ++s->launches;
+  CU(cudaGetLastError());
+  s->inited = true; s->iter = 0;
+  return 0;
+}
+
+int qsb_sampler_set_state(qsb_sampler* s, const double* x) {
+  if (!s || !x) return fail(1, "null argument");
+  CU(cudaSetDevice(s->m->device));
+  if (s->glm) { std::string why; if (glm_sampler_set_state(s->glm, x, why)) return fail(5, why); s->inited = true; s->iter = 0; return 0; }
+  EngineParams& P = s->P;
+  const size_t C = P.C, d = P.d;
+  std::vector<double> h(C * d);
+  if (s->var->G == 1) { for (size_t c = 0; c < C; ++c) for (size_t i = 0; i < d; ++i) h[i * C + c] = x[c * d + i]; }
+  else std::copy(x, x + C * d, h.begin());
+  if (int rc = reset_kernel_state(s)) return rc;
+  CU(cudaMemcpyAsync(P.x, h.data(), sizeof(double) * C * d, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  s->var->rescore(P, s->stream); ++s->launches;
+  CU(cudaGetLastError());
+  s->inited = true; s->iter = 0;
+  return 0;
+}
+
+int qsb_sampler_get_state(qsb_sampler* s, double* x) {
+  if (!s || !x) return fail(1, "null argument");
+  CU(cudaSetDevice(s->m->device));
+  if (s->glm) { std::string why; if (glm_sampler_get_state(s->glm, x, why)) return fail(5, why); return 0; }
+  EngineParams& P = s->P;
+  const size_t C = P.C, d = P.d;
+  std::vector<double> h(C * d);
+  CU(cudaMemcpyAsync(h.data(), P.x, sizeof(double) * C * d, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (s->var->G == 1) { for (size_t c = 0; c < C; ++c) for (size_t i = 0; i < d; ++i) x[c * d + i] = h[i * C + c]; }
+  else std::copy(h.begin(), h.end(), x);
+  return 0;
+}
+
+int qsb_sampler_begin(qsb_sampler* s, uint64_t max_samples, uint64_t burnin, uint64_t lag, uint64_t numiters) {
+  if (!s) return fail(1, "null sampler");
+  if (lag == 0) return fail(2, "lag must be >= 1");
+  CU(cudaSetDevice(s->m->device));
+  if (!s->inited) if (int rc = qsb_sampler_init(s)) return rc;
+  s->iter = 0; s->burnin = burnin; s->lag = lag; s->max_samples = max_samples; s->numiters = numiters;
+  if (s->glm) { std::string why; if (glm_sampler_begin(s->glm, max_samples, burnin, lag, numiters, why)) return fail(5, why); return 0; }
+  EngineParams& P = s->P;
+  // (re)allocate the sample and record buffers of this run; the chain state persists
+  free_run_buffers(s);
+  P.max_samples = max_samples; P.burnin = burnin; P.lag = lag;
+  if (max_samples > 0) {
+    CU(cudaMalloc((void**)&P.samples, sizeof(double) * max_samples * P.sample_chains * P.retdim));
+    CU(cudaMalloc((void**)&P.samp_lp, sizeof(double) * max_samples * P.sample_chains));
+  }
+  if (s->cfg.flags & QSB_FLAG_RECORD) {
+    if (numiters == 0) return fail(2, "QSB_FLAG_RECORD needs numiters");
+    const size_t C = P.C, d = P.d;
+    s->rec_iters = numiters; P.rec_iters = numiters;
+    CU(cudaMalloc((void**)&P.rec_state, sizeof(double) * C * numiters * d));
+    CU(cudaMalloc((void**)&P.rec_dh, sizeof(double) * C * numiters));
+    CU(cudaMalloc((void**)&P.rec_step, sizeof(double) * C * numiters));
+    CU(cudaMalloc((void**)&P.rec_accept, sizeof(int) * C * numiters));
+    CU(cudaMemset(P.rec_state, 0, sizeof(double) * C * numiters * d));
+    if (P.nsub > 1) CU(cudaMalloc((void**)&P.rec_kidx, sizeof(int) * C * numiters));
+    if ((s->cfg.flags & QSB_FLAG_RECORD_LEAP) && P.nsub == 1 && P.kind[0] == K_HMC) {
+      CU(cudaMalloc((void**)&P.rec_leap, sizeof(double) * C * numiters * P.numSteps[0] * d));
+      CU(cudaMemset(P.rec_leap, 0, sizeof(double) * C * numiters * P.numSteps[0] * d));
+    }
+  }
+  return 0;
+}
+
+int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
+  if (!s) return fail(1, "null sampler");
+  if (iters == 0) return 0;
+  CU(cudaSetDevice(s->m->device));
+  if (s->iter + iters >= QSB_ITER_SEARCH) return fail(2, "iteration counter would overflow the Philox iteration word");
+  if (s->glm) {
+    std::string why;
+    if (glm_sampler_advance(s->glm, iters, why)) return fail(5, why);
+    s->iter += iters;
+    return 0;
+  }
+  EngineParams& P = s->P;
+  if (s->rec_iters && s->iter + iters > s->rec_iters) return fail(2, "record buffer holds numiters iterations only");
+  P.it_begin = s->iter; P.n_iters = iters;
+  CU(cudaEventRecord(s->ev0, s->stream));
+  {
+    // the kernel indexes record rows by (it - it_begin); shift the bases so rows are absolute iterations
+    EngineParams R = P;
+    if (R.rec_state) {
+      const size_t d = R.d, off = s->iter;
+      R.rec_state += off * d; R.rec_dh += off; R.rec_step += off; R.rec_accept += off;
+      if (R.rec_kidx) R.rec_kidx += off;
+      if (R.rec_leap) R.rec_leap += off * R.numSteps[0] * d;
+    }
+    s->var->advance(R, s->stream);
+  }
+  ++s->launches;
+  CU(cudaEventRecord(s->ev1, s->stream));
+  CU(cudaGetLastError());
+  s->iter += iters;
+  return 0;
+}
+
+int qsb_sampler_run(qsb_sampler* s, uint64_t nsamps, uint64_t burnin, uint64_t lag) {
+  if (!s) return fail(1, "null sampler");
+  if (lag == 0) return fail(2, "lag must be >= 1");
+  const uint64_t iters = burnin + nsamps * lag;   // mcmc.t:53
+  if (int rc = qsb_sampler_begin(s, nsamps + 1, burnin, lag, iters)) return rc;
+  if (int rc = qsb_sampler_advance(s, iters)) return rc;
+  CU(cudaStreamSynchronize(s->stream));
+  if (!s->glm) if (int rc = check_status(s)) return rc;
+  return 0;
+}
+
+uint64_t qsb_sampler_num_samples(const qsb_sampler* s) {
+  if (!s) return 0;
+  // iterations i in [0, iter) with i >= burnin and i % lag == 0
+  if (s->iter == 0) return 0;
+  const uint64_t last = (s->iter - 1) / s->lag;                  // largest multiple index below iter
+  const uint64_t first = (s->burnin + s->lag - 1) / s->lag;      // first kept multiple index
+  uint64_t n = last >= first ? last - first + 1 : 0;
+  return std::min(n, s->max_samples);
+}
+
+static int fetch_common(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, uint64_t s1, void* dst, size_t stride_bytes, int with_lp) {
+  if (!s || !dst) return fail(1, "null argument");
+  CU(cudaSetDevice(s->m->device));
+  const double *samples, *samp_lp; int G; uint32_t SC; int retdim;
+  if (s->glm) glm_sampler_sample_view(s->glm, &samples, &samp_lp, &G, &SC, &retdim);
+  else { samples = s->P.samples; samp_lp = s->P.samp_lp; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }
+  const uint64_t have = qsb_sampler_num_samples(s);
+  if (c1 > SC || c0 > c1 || s1 > have || s0 > s1) return fail(2, "fetch: chain/sample range out of bounds (chains stored: " + std::to_string(SC) + ", samples kept: " + std::to_string(have) + ")");
+  const int w = retdim + (with_lp ? 2 : 0);
+  if (stride_bytes < (size_t)w * 8 || stride_bytes % 8) return fail(2, "fetch: stride must be a multiple of 8 and >= element size");
+  const uint64_t ns = s1 - s0;
+  if (ns == 0 || c1 == c0) return 0;
+  const size_t stride_d = stride_bytes / 8;
+  // staged through a device buffer, at most ~256 MiB at a time
+  uint32_t chunk = (uint32_t)std::max<size_t>(1, (256u << 20) / (ns * stride_bytes));
+  chunk = std::min<uint32_t>(chunk, c1 - c0);
+  double* stage = nullptr;
+  CU(cudaMalloc((void**)&stage, (size_t)chunk * ns * stride_bytes));
+  int rc = 0;
+  for (uint32_t c = c0; c < c1 && !rc; c += chunk) {
+    uint32_t nc = std::min<uint32_t>(chunk, c1 - c);
+    size_t total = (size_t)nc * ns * w;
+    unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+    gather_samples_kernel<<<grid, 256, 0, s->stream>>>(samples, samp_lp, G, SC, retdim, c, nc, s0, ns, stage, stride_d, with_lp);
+    ++s->launches;
+    cudaError_t e = cudaMemcpyAsync((char*)dst + (size_t)(c - c0) * ns * stride_bytes, stage, (size_t)nc * ns * stride_bytes, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) rc = fail(100 + (int)e, std::string("fetch: ") + cudaGetErrorString(e));
+  }
+  cudaFree(stage);
+  return rc;
+}
+
+int qsb_sampler_fetch_samples(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, uint64_t s1, void* dst, size_t stride_bytes) {
+  return fetch_common(s, c0, c1, s0, s1, dst, stride_bytes, 1);
+}
+int qsb_sampler_fetch_values(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, uint64_t s1, double* dst) {
+  if (!s) return fail(1, "null sampler");
+  int retdim = s->glm ? s->m->retdim : s->P.retdim;
+  return fetch_common(s, c0, c1, s0, s1, dst, (size_t)retdim * 8, 0);
+}
+
+int qsb_sampler_stats(qsb_sampler* s, qsb_stats* out) {
+  if (!s || !out) return fail(1, "null argument");
+  CU(cudaSetDevice(s->m->device));
+  memset(out, 0, sizeof(*out));
+  CU(cudaStreamSynchronize(s->stream));
+  if (s->glm) {
+    std::string why;
+    if (glm_sampler_stats(s->glm, &out->props_made, &out->props_accepted, &out->grad_evals, &out->leapfrog_steps, &out->kernel_launches, &out->seconds, why)) return fail(5, why);
+    out->sub_made[0] = out->props_made; out->sub_accepted[0] = out->props_accepted;
+    out->iterations = s->iter;
+    return 0;
+  }
+  EngineParams& P = s->P;
+  const size_t C = P.C;
+  std::vector<unsigned long long> made(P.nsub * C), acc(P.nsub * C);
+  unsigned long long counters[4];
+  CU(cudaMemcpy(made.data(), P.made, 8 * made.size(), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(acc.data(), P.acc, 8 * acc.size(), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(counters, P.counters, 32, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < P.nsub; ++k) for (size_t c = 0; c < C; ++c) {
+    out->sub_made[k] += made[k * C + c]; out->sub_accepted[k] += acc[k * C + c];
+  }
+  for (int k = 0; k < P.nsub; ++k) { out->props_made += out->sub_made[k]; out->props_accepted += out->sub_accepted[k]; }
+  out->grad_evals = counters[0]; out->leapfrog_steps = counters[1];
+  out->iterations = s->iter; out->kernel_launches = s->launches;
+  float ms = 0.f;
+  if (s->launches && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) out->seconds = ms * 1e-3;
+  return 0;
+}
+
+int qsb_sampler_diagnostics(qsb_sampler* s, int32_t maxlag, double* dst, int32_t dst_is_device) {
+  if (!s || !dst) return fail(1, "null argument");
+  if (maxlag < 0) return fail(2, "maxlag must be >= 0");
+  CU(cudaSetDevice(s->m->device));
+  const double *samples, *samp_lp; int G; uint32_t SC; int retdim;
+  if (s->glm) glm_sampler_sample_view(s->glm, &samples, &samp_lp, &G, &SC, &retdim);
+  else { samples = s->P.samples; samp_lp = s->P.samp_lp; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }
+  const uint64_t n = qsb_sampler_num_samples(s);
+  const size_t len = (size_t)retdim * 8 + (maxlag > 0 ? (size_t)retdim * (maxlag + 1) : 0);
+  double* out = dst;
+  if (!dst_is_device) CU(cudaMalloc((void**)&out, len * 8));
+  CU(cudaMemsetAsync(out, 0, len * 8, s->stream));
+  if (n >= 2 && samples) {
+    size_t total = (size_t)SC * retdim;
+    diagnostics_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s->stream>>>(samples, G, SC, retdim, n, maxlag, out);
+    diagnostics_header_kernel<<<(retdim + 127) / 128, 128, 0, s->stream>>>(out, retdim, (n / 2 >= 2) ? 2.0 * SC : 0.0, (double)(n / 2));
+    s->launches += 2;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && !dst_is_device) e = cudaMemcpyAsync(dst, out, len * 8, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  if (!dst_is_device) cudaFree(out);
+  if (e != cudaSuccess) return fail(100 + (int)e, std::string("diagnostics: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int qsb_sampler_fetch_record(qsb_sampler* s, double* state, int32_t* accept, double* dh, double* step, int32_t* kidx, double* leap) {
+  if (!s) return fail(1, "null sampler");
+  CU(cudaSetDevice(s->m->device));
+  if (s->glm) { std::string why; if (glm_sampler_fetch_record(s->glm, state, accept, dh, step, leap, why)) return fail(5, why); return 0; }
+  EngineParams& P = s->P;
+  if (!P.rec_state) return fail(2, "sampler was not created with QSB_FLAG_RECORD");
+  CU(cudaStreamSynchronize(s->stream));
+  const size_t C = P.C, d = P.d, T = s->rec_iters;
+  if (state) CU(cudaMemcpy(state, P.rec_state, 8 * C * T * d, cudaMemcpyDeviceToHost));
+  if (accept) CU(cudaMemcpy(accept, P.rec_accept, 4 * C * T, cudaMemcpyDeviceToHost));
+  if (dh) CU(cudaMemcpy(dh, P.rec_dh, 8 * C * T, cudaMemcpyDeviceToHost));
+  if (step) CU(cudaMemcpy(step, P.rec_step, 8 * C * T, cudaMemcpyDeviceToHost));
+  if (kidx) { if (!P.rec_kidx) return fail(2, "kernel index is recorded for mixtures only"); CU(cudaMemcpy(kidx, P.rec_kidx, 4 * C * T, cudaMemcpyDeviceToHost)); }
+  if (leap) { if (!P.rec_leap) return fail(2, "leapfrog positions need QSB_FLAG_RECORD_LEAP and a single HMC kernel"); CU(cudaMemcpy(leap, P.rec_leap, 8 * C * T * P.numSteps[0] * d, cudaMemcpyDeviceToHost)); }
+  return 0;
+}
+
+// ---- test hooks
+int qsb_logp_grad(qsb_model* m, const double* x, int32_t n, double* lp_dual, double* grad, double* lp_float) {
+  if (!m || !x || n <= 0) return fail(1, "bad argument");
+  CU(cudaSetDevice(m->device));
+  if (m->desc.family == QSB_FAM_LOGISTIC) {
+    std::string why;
+    if (glm_logp_grad(&m->glm, x, n, lp_dual, grad, lp_float, why)) return fail(5, why);
+    return 0;
+  }
+  qsb_kernel_spec spec = {QSB_KERNEL_HMC, 0, 1.0, 1, 1.0, 1.0};
+  qsb_run_config cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.numchains = (uint32_t)n; cfg.device = m->device;
+  const char* env = getenv("QSB_TEST_MAPPING");
+  if (env) cfg.reserved = atoi(env);
+  qsb_sampler* s = nullptr;
+  if (int rc = qsb_sampler_create(m, &spec, 1, &cfg, &s)) return rc;
+  int rc = qsb_sampler_set_state(s, x);
+  if (!rc) {
+    s->var->logp_grad(s->P, s->stream);
+    const size_t C = n, d = m->desc.dim;
+    std::vector<double> g(C * d);
+    cudaError_t e = cudaMemcpy(g.data(), s->P.g, 8 * C * d, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && lp_dual) e = cudaMemcpy(lp_dual, s->P.lp, 8 * C, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && lp_float) e = cudaMemcpy(lp_float, s->P.eps, 8 * C, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(100 + (int)e, cudaGetErrorString(e));
+    else if (grad) {
+      if (s->var->G == 1) { for (size_t c = 0; c < C; ++c) for (size_t i = 0; i < d; ++i) grad[c * d + i] = g[i * C + c]; }
+      else std::copy(g.begin(), g.end(), grad);
+    }
+  }
+  qsb_sampler_destroy(s);
+  return rc;
+}
+
+int qsb_logprob(int32_t which, const double* args, int32_t n, double* out) {
+  if (!args || !out || n <= 0) return fail(1, "bad argument");
+  double *da = nullptr, *dout = nullptr;
+  CU(cudaMalloc((void**)&da, 24 * (size_t)n)); CU(cudaMalloc((void**)&dout, 8 * (size_t)n));
+  cudaMemcpy(da, args, 24 * (size_t)n, cudaMemcpyHostToDevice);
+  logprob_kernel<<<(n + 127) / 128, 128>>>(which, da, n, dout);
+  cudaError_t e = cudaMemcpy(out, dout, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(da); cudaFree(dout);
+  if (e != cudaSuccess) return fail(100 + (int)e, cudaGetErrorString(e));
+  return 0;
+}
+
+int qsb_uniforms(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t slot, int32_t n, double* out) {
+  if (!out || n <= 0) return fail(1, "bad argument");
+  double* d = nullptr;
+  CU(cudaMalloc((void**)&d, 8 * (size_t)n));
+  uniforms_kernel<<<1, 1>>>(RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)}, chain, iter, slot, n, d);
+  cudaError_t e = cudaMemcpy(out, d, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(100 + (int)e, cudaGetErrorString(e));
+  return 0;
+}
+
+int qsb_gaussians(uint64_t seed, uint32_t chain, uint32_t iter, uint32_t slot0, int32_t n, double mu, double sigma, double* out) {
+  if (!out || n <= 0) return fail(1, "bad argument");
+  double* d = nullptr;
+  CU(cudaMalloc((void**)&d, 8 * (size_t)n));
+  gaussians_kernel<<<(n + 127) / 128, 128>>>(RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)}, chain, iter, slot0, n, mu, sigma, d);
+  cudaError_t e = cudaMemcpy(out, d, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(100 + (int)e, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,636 @@
+// Chain-parallel MCMC engine: the fused per-chain transition kernels that replace the reference's
+// doMCMC loop (qs/mcmc.t:50-90) with its HMC (qs/hmc.t), drift (qs/drift.t), HARM (qs/harm.t) and
+// mixture (qs/mcmc.t:199-291) kernels, for many independent chains at once.
+//
+// Mapping.  A chain is owned by a *group* of G lanes: G = 1 (thread per chain, small n: the whole
+// state of a transition lives in registers) or G = 32 (warp per chain, n up to 1024: lane l owns
+// components l, l+32, ...; reductions are warp shuffles; all global accesses are coalesced over
+// the components of one chain).  The same source serves both: lane-local arrays of NPL elements,
+// element e <-> component e*G + lane.
+//
+// Data layout in HBM (flat structure-of-arrays, fp64; replaces the per-chain trace of
+// qs/trace.t:523-540 and the kernels' S.Vector members, hmc.t:82-101, drift.t:87-98, harm.t:30-41):
+//   x, g          unconstrained positions / cached gradient:  G=1: [n][C] (chain-minor),  G=32: [C][n]
+//   lp            [C] currTrace.logprob
+//   eps, da_*     [C] HMC step size + DualAverage state        (hmc.t:14-48)
+//   dr_mean,dr_m2 like x: RunningVar per component; dr_n, dr_s0, dr_mult [C]   (drift.t:15-50, 274-300)
+//   ha_scale      [C]                                           (harm.t:30-41)
+//   made, acc     [nsub][C] KernelPropStats                     (mcmc.t:116-125)
+// The drift kernel's per-component `scale` is not stored: it is recomputed from (dr_m2, dr_n) with
+// the operations of RunningVar:getStdDev, which is what drift.t:288-298 assigns each iteration.
+#pragma once
+#include <cstdint>
+#include "distrib.cuh"
+#include "philox.cuh"
+
+namespace qsb {
+
+enum { FAM_INDEP = 1, FAM_GAUSS_PREC = 2, FAM_LOGISTIC = 3, FAM_EIGHT_SCHOOLS = 4, FAM_FUNNEL = 5 };
+enum { K_HMC = 1, K_DRIFT = 2, K_HARM = 3 };
+enum { FLAG_HMC_INIT = 1, FLAG_GRAD_VALID = 2 };
+enum { ERR_NAN_SEARCH = 1, ERR_SEARCH_INF = 2, ERR_SEARCH_ZERO = 4 };
+static constexpr int MAX_SUB = 8;
+
+struct ModelDev {
+  int family, dim, nobs, ret_mode;
+  double ret_div, prior_sigma;
+  const int* erp_kind; const double* p0; const double* p1;   // INDEP
+  // EIGHT_SCHOOLS observations, precomputed once per model with the same device operations the
+  // per-term logprob would use (bit-identical): cy = 1.8378770664093453 + 2*log(sigma), s2 = sigma*sigma
+  const double* y; const double* cy; const double* s2;
+};
+
+struct EngineParams {
+  ModelDev m;
+  RngKey key;
+  uint32_t chain_begin, C;
+  int d, retdim;
+  int nsub;
+  int kind[MAX_SUB], doAdapt[MAX_SUB];
+  double stepSize0[MAX_SUB], scale0[MAX_SUB], weight[MAX_SUB];
+  uint32_t numSteps[MAX_SUB];
+  double Sc[16 * 16];               // GAUSS_PREC: A + A^T padded to stride NPL, read from the constant bank
+  // chain state
+  double *x, *g, *lp;
+  uint8_t* flags;
+  double *eps, *da_gbar, *da_xbar, *da_x0, *da_lastx, *da_gamma;
+  uint32_t* da_k;
+  double *dr_mean, *dr_m2, *dr_s0, *dr_mult;
+  uint32_t* dr_n;
+  double* ha_scale;
+  unsigned long long *made, *acc;   // [nsub][C]
+  unsigned long long* counters;     // [0] gradient evaluations, [1] leapfrog steps (inside :next)
+  int* status;                      // sticky error bits
+  // run window
+  uint64_t it_begin, n_iters, burnin, lag;
+  // kept samples
+  double *samples, *samp_lp;
+  uint32_t sample_chains;
+  uint64_t max_samples;
+  // per-iteration record (parity tests)
+  double *rec_state, *rec_dh, *rec_step, *rec_leap;
+  int *rec_accept, *rec_kidx;
+  uint64_t rec_iters;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <int G> struct Grp {
+  static __device__ __forceinline__ int lane() { return G == 1 ? 0 : (int)(threadIdx.x & 31u); }
+  static __device__ __forceinline__ double sum(double v) {
+    if (G == 32) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;
+  }
+  static __device__ __forceinline__ double bcast(double v, int src) {
+    if (G == 32) return __shfl_sync(0xffffffffu, v, src);
+    return v;
+  }
+};
+
+template <int G> __device__ __forceinline__ size_t vidx(const EngineParams& P, int i, uint32_t c) {
+  return G == 1 ? (size_t)i * P.C + c : (size_t)c * P.d + i;
+}
+
+#define QSB_FOR_E _Pragma("unroll") for (int e = 0; e < NPL; ++e)
+
+// One ERP site of a dual trace: prior logprob of the constrained value, log-Jacobian, and
+// d(logprob + logJ)/dx  (erp.t:623-640).  Not inlined: the INDEP family is not a throughput path
+// and the four-way kind switch would otherwise be replicated at every unrolled component.
+static __device__ __noinline__ void erp_eval(int kind, double x, double p0, double p1, double& lpy, double& lj, double& g) {
+  double dydx, dlpdy, dlj;
+  double y = erp_fwd(kind, x, p0, p1, &dydx);
+  lpy = erp_prior_lp(kind, y, p0, p1, &dlpdy);
+  lj = erp_logjac(kind, x, p0, p1, &dlj);
+  g = dlpdy * dydx + dlj;
+}
+static __device__ __noinline__ double erp_fwd_noinline(int kind, double x, double p0, double p1) { return erp_fwd(kind, x, p0, p1, nullptr); }
+
+// ---------------------------------------------------------------------------------------------
+// Model log-densities.  Returns the dual-trace logprob (with log-Jacobians: what HMC's traceUpdate
+// sees, hmc.t:325-342 + erp.t:623-640); lp_float is the float-trace logprob (no Jacobian: what
+// Drift/HARM and the very first HMC Hamiltonian see, erp.t:361).  Inactive elements (component
+// index >= dim) carry x = 0 and must not contribute.
+template <int FAM, int G, int NPL, bool GRAD>
+__device__ __forceinline__ double model_eval(const EngineParams& P, int lane, const double (&x)[NPL], double (&g)[NPL], double& lp_float) {
+  const ModelDev& m = P.m;
+  const int d = m.dim;
+  if (FAM == FAM_INDEP) {
+    double lpd = 0.0, lpf = 0.0;
+    QSB_FOR_E {
+      int i = e * G + lane;
+      if (i < d) {
+        double lpy, lj, gi;
+        erp_eval(m.erp_kind[i], x[e], m.p0[i], m.p1[i], lpy, lj, gi);
+        lpf += lpy;
+        lpd += lpy + lj;
+        if (GRAD) g[e] = gi;
+      } else if (GRAD) g[e] = 0.0;
+    }
+    lp_float = Grp<G>::sum(lpf);
+    return Grp<G>::sum(lpd);
+  } else if (FAM == FAM_GAUSS_PREC) {
+    // log p = sum_i gaussian_lp(x_i;0,1) + factor(-0.5 x'Ax),  x'Ax = 0.5 x'(A+A')x ;  G == 1 only
+    double lp = 0.0, q = 0.0;
+    QSB_FOR_E {
+      if (e < d) {
+        double sx = 0.0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) if (j < d) sx += P.Sc[(e * NPL + j) & 255] * x[j];
+        q += x[e] * sx;
+        lp += gaussian_lp(x[e], 0.0, 1.0);
+        if (GRAD) g[e] = -x[e] - 0.5 * sx;
+      } else if (GRAD) g[e] = 0.0;
+    }
+    lp += -0.5 * (0.5 * q);
+    lp_float = lp;
+    return lp;
+  } else if (FAM == FAM_EIGHT_SCHOOLS) {
+    // components: 0 mu, 1 logtau, 2+j theta_j
+    double x0 = 0.0, x1 = 0.0;
+    if (G == 1) { x0 = x[0]; x1 = NPL > 1 ? x[NPL > 1 ? 1 : 0] : 0.0; }
+    else { x0 = Grp<G>::bcast(x[0], 0); x1 = Grp<G>::bcast(x[0], 1); }
+    const double mu = x0, lt = x1;
+    const double tau = exp(lt);
+    const double tau2 = tau * tau;
+    const double c_th = 1.8378770664093453 + 2.0 * log(tau);
+    double lp = 0.0, gmu = 0.0, glt = 0.0;
+    QSB_FOR_E {
+      int i = e * G + lane;
+      if (i >= 2 && i < d) {
+        int j = i - 2;
+        double yj = m.y[j], s2 = m.s2[j];
+        double th = x[e];
+        double r = th - mu;
+        double r2t = r * r / tau2;
+        double ry = yj - th;
+        lp += -.5 * (c_th + r2t);
+        lp += -.5 * (m.cy[j] + ry * ry / s2);
+        if (GRAD) {
+          double rt = r / tau2;
+          g[e] = -rt + ry / s2;
+          gmu += rt;
+          glt += -1.0 + r2t;
+        }
+      } else if (GRAD) g[e] = 0.0;
+    }
+    lp = Grp<G>::sum(lp);
+    lp += gaussian_lp(mu, 0.0, 5.0) + gaussian_lp(lt, 0.0, 1.0);
+    if (GRAD) {
+      gmu = Grp<G>::sum(gmu);
+      glt = Grp<G>::sum(glt);
+      QSB_FOR_E {
+        int i = e * G + lane;
+        if (i == 0) g[e] = -mu / 25.0 + gmu;
+        if (i == 1) g[e] = -lt + glt;
+      }
+    }
+    lp_float = lp;
+    return lp;
+  } else {  // FAM_FUNNEL: component 0 = v, i >= 1: x_i ~ gaussian(0, exp(v/2))
+    const double v = Grp<G>::bcast(x[0], 0);
+    const double s = exp(v / 2.0);
+    const double s2 = s * s;
+    const double c_x = 1.8378770664093453 + 2.0 * log(s);
+    double lp = 0.0, gv = 0.0;
+    QSB_FOR_E {
+      int i = e * G + lane;
+      if (i >= 1 && i < d) {
+        double xi = x[e];
+        double q = xi * xi / s2;
+        lp += -.5 * (c_x + q);
+        if (GRAD) { g[e] = -xi / s2; gv += -0.5 + 0.5 * q; }
+      } else if (GRAD) g[e] = 0.0;
+    }
+    lp = Grp<G>::sum(lp);
+    lp += gaussian_lp(v, 0.0, 3.0);
+    if (GRAD) {
+      gv = Grp<G>::sum(gv);
+      QSB_FOR_E { if (e * G + lane == 0) g[e] = -v / 9.0 + gv; }
+    }
+    lp_float = lp;
+    return lp;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int FAM, int G, int NPL> struct Chain {
+  const EngineParams& P;
+  const uint32_t c;       // local chain index
+  const uint32_t gc;      // global chain id (Philox counter word)
+  const int lane;
+  const int d;
+  __device__ __forceinline__ Chain(const EngineParams& P_, uint32_t c_)
+      : P(P_), c(c_), gc(P_.chain_begin + c_), lane(Grp<G>::lane()), d(P_.d) {}
+
+  __device__ __forceinline__ void load(const double* base, double (&v)[NPL]) const {
+    QSB_FOR_E { int i = e * G + lane; v[e] = i < d ? base[vidx<G>(P, i, c)] : 0.0; }
+  }
+  __device__ __forceinline__ void store(double* base, const double (&v)[NPL]) const {
+    QSB_FOR_E { int i = e * G + lane; if (i < d) base[vidx<G>(P, i, c)] = v[e]; }
+  }
+  __device__ __forceinline__ bool leader() const { return lane == 0; }
+  __device__ __forceinline__ void count(int which, unsigned long long n) const {
+    if (leader()) atomicAdd(&P.counters[which], n);
+  }
+
+  // ---- sampleMomenta + kinetic energy (hmc.t:289-305), invMasses == 1
+  __device__ __forceinline__ void sample_momenta(uint32_t iter, double (&p)[NPL]) const {
+    QSB_FOR_E {
+      int i = e * G + lane;
+      p[e] = i < d ? gaussian_std(P.key, gc, iter, (uint32_t)i) * 1.0 : 0.0;
+    }
+  }
+  __device__ __forceinline__ double kinetic(const double (&p)[NPL]) const {
+    double k = 0.0;
+    QSB_FOR_E k += p[e] * p[e] * 1.0;
+    return -0.5 * Grp<G>::sum(k);
+  }
+  // ---- HMCKernel:step (hmc.t:307-323): two separate half-kicks, reference operation order
+  __device__ __forceinline__ double leapfrog(double eps, double (&xs)[NPL], double (&gs)[NPL], double (&p)[NPL]) const {
+    const double he = 0.5 * eps;
+    QSB_FOR_E p[e] = p[e] + he * gs[e];
+    QSB_FOR_E xs[e] = xs[e] + eps * p[e] * 1.0;
+    double lpf;
+    double lp = model_eval<FAM, G, NPL, true>(P, lane, xs, gs, lpf);
+    QSB_FOR_E p[e] = p[e] + he * gs[e];
+    return lp;
+  }
+
+  // ---- DualAverage:update + adaptStepSize (hmc.t:38-48, 394-402)
+  __device__ __forceinline__ double adapt_step_size(double dH, double target) const {
+    double EdH = exp(dH);
+    if (EdH > 1.0) EdH = 1.0;
+    if (!(EdH == EdH)) EdH = 0.0;
+    double gr = target - EdH;
+    uint32_t k = P.da_k[c] + 1;
+    double avgeta = 1.0 / (double)(k + 10);
+    double xbar_avgeta = pow((double)k, -0.75);
+    double muk = 0.5 * sqrt((double)k) / P.da_gamma[c];
+    double gbar = avgeta * gr + (1 - avgeta) * P.da_gbar[c];
+    double lastx = P.da_x0[c] - muk * gbar;
+    double xbar = xbar_avgeta * lastx + (1 - xbar_avgeta) * P.da_xbar[c];
+    if (leader()) { P.da_k[c] = k; P.da_gbar[c] = gbar; P.da_lastx[c] = lastx; P.da_xbar[c] = xbar; }
+    return exp(lastx);
+  }
+
+  // ---- searchForInitialStepSize (hmc.t:345-391).  x, g are the current position / gradient in HBM.
+  __device__ __forceinline__ double search_step_size(double eps, double dual_lp, double (&xs)[NPL], double (&gs)[NPL], double (&p)[NPL]) const {
+    uint32_t probe = 0;
+    const double LOG_HALF = log(0.5);
+    load(P.x, xs); load(P.g, gs);
+    sample_momenta(QSB_ITER_SEARCH + probe++, p);
+    double prevlp = dual_lp;
+    double lp = leapfrog(eps, xs, gs, p);
+    double H = lp - prevlp;
+    prevlp = lp;
+    int direction = H > LOG_HALF ? 1 : -1;
+    unsigned long long evals = 1;
+    while (true) {
+      load(P.x, xs); load(P.g, gs);
+      sample_momenta(QSB_ITER_SEARCH + probe++, p);
+      lp = leapfrog(eps, xs, gs, p);
+      ++evals;
+      H = lp - prevlp;      // hmc.t:357: dualTrace.logprob is the previous probe's value
+      prevlp = lp;
+      if (!(lp == lp)) { if (leader()) atomicOr(P.status, ERR_NAN_SEARCH); break; }
+      if (direction == 1 && H <= LOG_HALF) break;
+      else if (direction == -1 && H >= LOG_HALF) break;
+      else if (direction == 1) eps = eps * 2.0;
+      else eps = eps * 0.5;
+      if (eps > 1e300) { if (leader()) atomicOr(P.status, ERR_SEARCH_INF); break; }
+      if (eps == 0) { if (leader()) atomicOr(P.status, ERR_SEARCH_ZERO); break; }
+    }
+    count(0, evals);
+    return eps;
+  }
+
+  // ---- HMCKernel:next (hmc.t:134-186)
+  __device__ __forceinline__ bool hmc_next(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    double xs[NPL], gs[NPL], p[NPL];
+    const bool adapting = P.doAdapt[k] != 0;
+    const uint32_t L = P.numSteps[k];
+    const double target = L == 1 ? 0.574 : 0.65;
+    if (leader()) P.made[(size_t)k * P.C + c] += 1;
+    uint8_t fl = P.flags[c];
+    double eps = P.eps[c];
+    // checkForChanges (hmc.t:188-287)
+    if (!(fl & FLAG_GRAD_VALID)) {
+      load(P.x, xs);
+      double lpf;
+      double dual_lp = model_eval<FAM, G, NPL, true>(P, lane, xs, gs, lpf);
+      store(P.g, gs);
+      count(0, 1);
+      if (!(fl & FLAG_HMC_INIT) && adapting) {
+        if (G == 32) __syncwarp();
+        eps = search_step_size(eps, dual_lp, xs, gs, p);
+        if (leader()) {   // adapter:reinit(stepSize, adaptRate) (hmc.t:261)
+          P.da_k[c] = 0; P.da_x0[c] = eps; P.da_lastx[c] = eps; P.da_gbar[c] = 0.0; P.da_xbar[c] = 0.0; P.da_gamma[c] = 0.05;
+        }
+        if (G == 32) __syncwarp();
+      }
+      fl |= FLAG_HMC_INIT | FLAG_GRAD_VALID;
+    }
+    load(P.x, xs); load(P.g, gs);
+    sample_momenta(iter, p);
+    const double lp_cur = P.lp[c];
+    const double H = kinetic(p) + lp_cur;
+    double newlp = 0.0;
+    rec_step = eps;
+    for (uint32_t s = 0; s < L; ++s) {
+      newlp = leapfrog(eps, xs, gs, p);
+      if (P.rec_leap) {
+        size_t base = (((size_t)c * P.rec_iters + (iter - P.it_begin)) * L + s) * d;
+        QSB_FOR_E { int i = e * G + lane; if (i < d) P.rec_leap[base + i] = xs[e]; }
+      }
+    }
+    count(0, L); count(1, L);
+    const double H_new = kinetic(p) + newlp;
+    const double dH = H_new - H;
+    rec_dh = dH;
+    if (adapting) eps = adapt_step_size(dH, target);
+    const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
+    const bool accept = log(u) < dH;
+    if (accept) {
+      store(P.x, xs); store(P.g, gs);
+      if (leader()) { P.acc[(size_t)k * P.C + c] += 1; P.lp[c] = newlp; }
+    }
+    if (leader()) { P.eps[c] = eps; P.flags[c] = fl; }
+    return accept;
+  }
+
+  // ---- DriftKernel:next + adapt (drift.t:133-172, 274-300), lexicalScaleSharing = false
+  __device__ __forceinline__ bool drift_next(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    double x[NPL], xp[NPL];
+    const bool adapting = P.doAdapt[k] != 0;
+    const size_t kc = (size_t)k * P.C + c;
+    unsigned long long made = P.made[kc] + 1, acc = P.acc[kc];
+    const uint32_t n_rv = P.dr_n[c];
+    const double s0 = P.dr_s0[c], mult = P.dr_mult[c];
+    load(P.x, x);
+    // proposal x'_i = gaussian.sample(x_i, scale_i)
+    QSB_FOR_E {
+      int i = e * G + lane;
+      if (i < d) {
+        double sc = s0;
+        if (n_rv > 100) {   // scale = varEst:getStdDev() [* 0.99]  (drift.t:288-298)
+          sc = sqrt(P.dr_m2[vidx<G>(P, i, c)] / (double)(n_rv - 1));
+          if (mult != 1.0) sc = sc * mult;
+        }
+        xp[e] = gaussian_sample(P.key, gc, iter, (uint32_t)i, x[e], sc);
+      } else xp[e] = 0.0;
+    }
+    rec_step = s0;
+    double lpf, gdummy[NPL];
+    model_eval<FAM, G, NPL, false>(P, lane, xp, gdummy, lpf);
+    const double lp_cur = P.lp[c];
+    const double thresh = lpf - lp_cur;
+    rec_dh = thresh;
+    const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
+    const bool accept = log(u) < thresh;
+    if (accept) {
+      acc += 1;
+      store(P.x, xp);
+      QSB_FOR_E x[e] = xp[e];
+      if (leader()) { P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID; }
+    }
+    if (adapting) {
+      const double ratio = (double)acc / (double)made;
+      uint32_t n_new = n_rv;
+      if (ratio >= 0.05 && acc > 5) {   // RunningVar:update with the current state (drift.t:26-37)
+        n_new = n_rv + 1;
+        QSB_FOR_E {
+          int i = e * G + lane;
+          if (i < d) {
+            size_t ix = vidx<G>(P, i, c);
+            if (n_new == 1) { P.dr_mean[ix] = x[e]; P.dr_m2[ix] = 0.0; }
+            else {
+              double mean = P.dr_mean[ix];
+              double newmean = mean + (x[e] - mean) / (double)n_new;
+              P.dr_m2[ix] = P.dr_m2[ix] + (x[e] - mean) * (x[e] - newmean);
+              P.dr_mean[ix] = newmean;
+            }
+          }
+        }
+      }
+      if (leader()) {
+        const bool shrink = ratio < 0.05 && acc > 5;
+        P.dr_n[c] = n_new;
+        if (n_new > 100) P.dr_mult[c] = shrink ? 0.99 : 1.0;
+        else if (shrink) P.dr_s0[c] = s0 * 0.99;
+      }
+    }
+    if (leader()) { P.made[kc] = made; P.acc[kc] = acc; }
+    return accept;
+  }
+
+  // ---- HARMKernel:next (harm.t:60-113)
+  __device__ __forceinline__ bool harm_next(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    double x[NPL], xp[NPL];
+    const bool adapting = P.doAdapt[k] != 0;
+    const size_t kc = (size_t)k * P.C + c;
+    load(P.x, x);
+    double nrm = 0.0;
+    QSB_FOR_E {
+      int i = e * G + lane;
+      xp[e] = i < d ? gaussian_std(P.key, gc, iter, (uint32_t)i) : 0.0;
+      nrm += xp[e] * xp[e];
+    }
+    nrm = sqrt(Grp<G>::sum(nrm));
+    const double hscale = P.ha_scale[c];
+    rec_step = hscale;
+    const double step = uniform_at(P.key, gc, iter, (uint32_t)d) * hscale;
+    QSB_FOR_E {
+      int i = e * G + lane;
+      xp[e] = i < d ? x[e] + (step * (xp[e] / nrm)) : 0.0;
+    }
+    double lpf, gdummy[NPL];
+    model_eval<FAM, G, NPL, false>(P, lane, xp, gdummy, lpf);
+    double t = 0.234;
+    if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
+    const double thresh = lpf - P.lp[c];
+    rec_dh = thresh;
+    const double u = uniform_at(P.key, gc, iter, (uint32_t)d + 1u);
+    const bool accept = log(u) < thresh;
+    double ns = hscale;
+    if (accept) {
+      store(P.x, xp);
+      if (adapting) ns = hscale + (hscale / (t * (1.0 - t))) * (1.0 - t) / (double)(iter + 1u);
+    } else {
+      if (adapting) ns = fabs(hscale - (hscale / (t * (1.0 - t))) * t / (double)(iter + 1u));
+    }
+    if (leader()) {
+      P.made[kc] += 1;
+      if (accept) { P.acc[kc] += 1; P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID; }
+      P.ha_scale[c] = ns;
+    }
+    return accept;
+  }
+
+  // ---- one iteration of doMCMC's loop body (mcmc.t:57-72)
+  __device__ __forceinline__ void iterate(uint64_t it) const {
+    const uint32_t iter = (uint32_t)it;
+    int k = 0;
+    if (P.nsub > 1) {   // MixtureKernel:next (mcmc.t:275-287) + categorical_array.sample (distrib.t:281-292)
+      double sum = 0.0;
+      for (int j = 0; j < P.nsub; ++j) sum = sum + P.weight[j];
+      double xr = uniform_at(P.key, gc, iter, QSB_SLOT_MIXTURE) * sum;
+      double pa = 0.0;
+      int result = 0;
+      do { pa = pa + P.weight[result]; result = result + 1; } while (!(pa > xr || result == P.nsub));
+      k = result - 1;
+    }
+    double rdh = 0.0, rstep = 0.0;
+    bool accept;
+    const int kind = P.kind[k];
+    if (kind == K_HMC) accept = hmc_next(k, iter, rdh, rstep);
+    else if (kind == K_DRIFT) accept = drift_next(k, iter, rdh, rstep);
+    else accept = harm_next(k, iter, rdh, rstep);
+    if (G == 32) __syncwarp();
+    const bool keep = it >= P.burnin && (it % P.lag) == 0 && c < P.sample_chains && P.samples != nullptr;
+    if (keep || P.rec_state) {
+      double x[NPL];
+      load(P.x, x);
+      if (P.rec_state) {
+        size_t r = (size_t)c * P.rec_iters + (it - P.it_begin);
+        QSB_FOR_E { int i = e * G + lane; if (i < d) P.rec_state[r * d + i] = x[e]; }
+        if (leader()) {
+          P.rec_accept[r] = accept ? 1 : 0; P.rec_dh[r] = rdh; P.rec_step[r] = rstep;
+          if (P.rec_kidx) P.rec_kidx[r] = k;
+        }
+      }
+      if (keep) {
+        const uint64_t sidx = it / P.lag - (P.burnin + P.lag - 1) / P.lag;
+        if (sidx < P.max_samples) {
+          const uint32_t SC = P.sample_chains;
+          if (FAM == FAM_INDEP) {
+            double sum = 0.0;
+            QSB_FOR_E {
+              int i = e * G + lane;
+              if (i < d) {
+                double y = erp_fwd_noinline(P.m.erp_kind[i], x[e], P.m.p0[i], P.m.p1[i]);
+                if (P.m.ret_mode == 0) sum += y;
+                else P.samples[G == 1 ? ((size_t)sidx * P.retdim + i) * SC + c : ((size_t)sidx * SC + c) * P.retdim + i] = y;
+              }
+            }
+            if (P.m.ret_mode == 0) {
+              sum = Grp<G>::sum(sum);
+              if (leader()) P.samples[(size_t)sidx * SC + c] = sum / P.m.ret_div;
+            }
+          } else {
+            QSB_FOR_E {
+              int i = e * G + lane;
+              if (i < d) P.samples[G == 1 ? ((size_t)sidx * P.retdim + i) * SC + c : ((size_t)sidx * SC + c) * P.retdim + i] = x[e];
+            }
+          }
+          if (leader()) P.samp_lp[(size_t)sidx * SC + c] = P.lp[c];
+        }
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernels
+template <int FAM, int G, int NPL>
+__global__ void __launch_bounds__(G == 1 ? 128 : 256) advance_kernel(const __grid_constant__ EngineParams P) {
+  const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
+  if (grp >= P.C) return;
+  Chain<FAM, G, NPL> ch(P, grp);
+  for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.iterate(it);
+}
+
+// Forward-sampling initialisation (trace.t:592-624: update(true) creates every choice by sampling it,
+// erp.t:567-572) followed by the kernels' first gather of unconstrained components (erp.t:519-522).
+// The ERPs of a chain are sampled in program order; ERP i reads sub-stream (chain, ITER_INIT, i).
+template <int FAM, int G, int NPL>
+__global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_constant__ EngineParams P) {
+  const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
+  if (grp >= P.C) return;
+  Chain<FAM, G, NPL> ch(P, grp);
+  const int lane = ch.lane, d = P.d;
+  double x[NPL];
+  double lp0 = 0.0;
+  if (FAM == FAM_INDEP) {
+    double lp = 0.0;
+    QSB_FOR_E {
+      int i = e * G + lane;
+      x[e] = 0.0;
+      if (i < d) {
+        int kind = P.m.erp_kind[i];
+        double p0 = P.m.p0[i], p1 = P.m.p1[i];
+        SubStream s(P.key, ch.gc, QSB_ITER_INIT, (uint32_t)i);
+        double y = erp_sample_seq(kind, s, p0, p1);
+        lp += erp_prior_lp(kind, y, p0, p1, nullptr);   // float trace: logprob of the sampled value itself
+        x[e] = erp_inv(kind, y, p0, p1);
+      }
+    }
+    lp0 = Grp<G>::sum(lp);
+  } else {
+    if (FAM == FAM_GAUSS_PREC) {
+      QSB_FOR_E { int i = e * G + lane; x[e] = i < d ? gaussian_sample(P.key, ch.gc, QSB_ITER_INIT, (uint32_t)i, 0.0, 1.0) : 0.0; }
+    } else if (FAM == FAM_EIGHT_SCHOOLS) {
+      double mu = gaussian_sample(P.key, ch.gc, QSB_ITER_INIT, 0u, 0.0, 5.0);
+      double lt = gaussian_sample(P.key, ch.gc, QSB_ITER_INIT, 1u, 0.0, 1.0);
+      double tau = exp(lt);
+      QSB_FOR_E {
+        int i = e * G + lane;
+        x[e] = 0.0;
+        if (i == 0) x[e] = mu;
+        else if (i == 1) x[e] = lt;
+        else if (i < d) x[e] = gaussian_sample(P.key, ch.gc, QSB_ITER_INIT, (uint32_t)i, mu, tau);
+      }
+    } else {
+      double v = gaussian_sample(P.key, ch.gc, QSB_ITER_INIT, 0u, 0.0, 3.0);
+      double s = exp(v / 2.0);
+      QSB_FOR_E {
+        int i = e * G + lane;
+        x[e] = 0.0;
+        if (i == 0) x[e] = v;
+        else if (i < d) x[e] = gaussian_sample(P.key, ch.gc, QSB_ITER_INIT, (uint32_t)i, 0.0, s);
+      }
+    }
+    double g[NPL], lpf;
+    model_eval<FAM, G, NPL, false>(P, lane, x, g, lpf);
+    lp0 = lpf;
+  }
+  ch.store(P.x, x);
+  if (ch.leader()) P.lp[grp] = lp0;
+}
+
+// lp of an explicitly set state (qsb_sampler_set_state)
+template <int FAM, int G, int NPL>
+__global__ void __launch_bounds__(G == 1 ? 128 : 256) rescore_kernel(const __grid_constant__ EngineParams P) {
+  const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
+  if (grp >= P.C) return;
+  Chain<FAM, G, NPL> ch(P, grp);
+  double x[NPL], g[NPL], lpf;
+  ch.load(P.x, x);
+  model_eval<FAM, G, NPL, false>(P, ch.lane, x, g, lpf);
+  if (ch.leader()) P.lp[grp] = lpf;
+}
+
+// test hook: lp_dual, gradient and lp_float at the states in P.x; gradient to P.g, lp_dual to P.lp, lp_float to P.eps
+template <int FAM, int G, int NPL>
+__global__ void __launch_bounds__(G == 1 ? 128 : 256) logp_grad_kernel(const __grid_constant__ EngineParams P) {
+  const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
+  if (grp >= P.C) return;
+  Chain<FAM, G, NPL> ch(P, grp);
+  double x[NPL], g[NPL], lpf;
+  ch.load(P.x, x);
+  double lpd = model_eval<FAM, G, NPL, true>(P, ch.lane, x, g, lpf);
+  ch.store(P.g, g);
+  if (ch.leader()) { P.lp[grp] = lpd; P.eps[grp] = lpf; }
+}
+
+// host-side launcher table entry
+struct EngineVariant {
+  int family, G, npl;
+  void (*advance)(const EngineParams&, void* stream);
+  void (*init)(const EngineParams&, void* stream);
+  void (*rescore)(const EngineParams&, void* stream);
+  void (*logp_grad)(const EngineParams&, void* stream);
+};
+
+}  // namespace qsb

@@ -1,0 +1,706 @@
+// Bernoulli-logit GLM under HMC (config c3): theta_j ~ gaussian(0, s), flip.observe(y_i, 1/(1+exp(-x_i.theta))).
+//
+// What the reference does per gradient (qs/hmc.t:325-342): re-run the whole program on tape-AD numbers --
+// N*d multiply-adds each allocating a node -- then sweep the tape backwards (qs/lib/ad.t:679-708).
+// Here one gradient of ALL chains is a pair of dense fp64 contractions on the tensor cores (DMMA,
+// mma.sync.m8n8k4.f64) fused around the sigmoid:
+//     Z = X Theta  (N x C),   R = y - 1/(1+exp(-Z)),   G = X^T R  (d x C),   lp = sum log(y ? p : 1-p)
+// Z and R never leave registers.  Orientation: chains are the M dimension of both MMAs
+// (Z^T = Theta^T X^T, G^T = R^T X), so the accumulator fragment of the first MMA *is* the A fragment
+// of the second (thread (g,t) holds chain g, two observation rows) -- no shuffles, no shared-memory
+// round trip.  The k-index <-> dimension map of the first MMA and the k-index <-> row map of the
+// second are chosen so that every thread only ever touches the 2*NJ dimensions it owns
+// (dims 8J+2t, 8J+2t+1 of chain g) and all shared-memory fragment loads are bank-conflict free.
+//
+// X (N x d, row stride S) is streamed from L2 through shared memory by one producer thread with TMA
+// bulk copies (cp.async.bulk + mbarrier complete_tx) into a STAGES-deep ring; the 8 consumer warps of a
+// CTA (64 chains) all read the same staged rows, so each row block is fetched once per 64 chains.
+// The grid is (chain tiles) x (row splits): row splits give full waves on 148 SMs for any chain
+// count; their partial gradients are summed in a fixed order by the vector kernel (deterministic).
+//
+// The leapfrog updates, momenta, Hamiltonians, accept/reject, dual averaging and sample collection
+// are the warp-per-chain vector kernels below (qs/hmc.t:134-186, 289-323, 394-402).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/qsb200.h"
+#include "distrib.cuh"
+#include "glm_hmc.cuh"
+#include "philox.cuh"
+
+namespace qsb {
+
+static constexpr int MB = 32;          // observation rows per pipeline stage
+static constexpr int NT = MB / 8;      // 8-row n-tiles per stage
+static constexpr int STAGES = 4;
+static constexpr int CW = 8;           // consumer warps per CTA
+static constexpr int CB = CW * 8;      // chains per CTA
+static constexpr int GRAD_THREADS = (CW + 1) * 32;
+
+struct GradParams {
+  const double* Xp; const double* yv;
+  int S, d, nj, nblocks, ksplit, ntiles;
+  uint32_t C; int Dp;
+  const double* theta;     // [C][Dp]
+  double* partG;           // [ksplit][C][Dp]
+  double* partLp;          // [ksplit][C]
+  int want_lp;
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// smem: per stage [MB*S + 8 doubles X (8 = zeroed over-read pad)] [MB doubles y]; then 2*STAGES mbarriers
+__host__ __device__ inline size_t stage_doubles(int S) { return (size_t)MB * S + 8 + MB; }
+
+template <int NJ>
+__global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_constant__ GradParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  const size_t SD = stage_doubles(P.S);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + SD * STAGES);
+  uint64_t* empty = full + STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % P.ntiles, split = blockIdx.x / P.ntiles;
+  const int b0 = (int)(((long)split * P.nblocks) / P.ksplit), b1 = (int)(((long)(split + 1) * P.nblocks) / P.ksplit);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < STAGES * 8) sm[SD * (threadIdx.x >> 3) + (size_t)MB * P.S + (threadIdx.x & 7)] = 0.0;   // over-read pads
+  __syncthreads();
+
+  if (warp == CW) {
+    // ---- producer: TMA bulk copies of whole row blocks (contiguous in HBM: Xp is stored with stride S)
+    if (lane == 0) {
+      const uint32_t bytesX = (uint32_t)(MB * P.S * sizeof(double)), bytesY = (uint32_t)(MB * sizeof(double));
+      for (int b = b0; b < b1; ++b) {
+        const int it = b - b0, st = it % STAGES, round = it / STAGES;
+        mbar_wait(&empty[st], (uint32_t)((round & 1) ^ 1));
+        mbar_expect_tx(&full[st], bytesX + bytesY);
+        double* dst = sm + SD * st;
+        bulk_g2s(dst, P.Xp + (size_t)b * MB * P.S, bytesX, &full[st]);
+        bulk_g2s(dst + (size_t)MB * P.S + 8, P.yv + (size_t)b * MB, bytesY, &full[st]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: warp w owns chains tile*CB + 8w .. +7; thread (gid, tig) owns dims 8J+2tig+{0,1} of chain gid
+  const int gid = lane >> 2, tig = lane & 3;
+  const uint32_t chain = (uint32_t)tile * CB + warp * 8 + gid;
+  const bool valid = chain < P.C;
+  const int S = P.S, nj = P.nj;
+  // row permutation inside an 8-row tile (see header): rho = [0,2,1,3,6,4,7,5]
+  const uint32_t RHO = 0x57463120u;
+  const int rho_g = (RHO >> (4 * gid)) & 7, rho_t0 = (RHO >> (8 * tig)) & 7, rho_t1 = (RHO >> (8 * tig + 4)) & 7;
+
+  double th[NJ][2], G[NJ][2];
+#pragma unroll
+  for (int J = 0; J < NJ; ++J) {
+    th[J][0] = th[J][1] = 0.0; G[J][0] = G[J][1] = 0.0;
+    if (J < nj && valid) {
+      double2 v = *reinterpret_cast<const double2*>(P.theta + (size_t)chain * P.Dp + 8 * J + 2 * tig);
+      th[J][0] = v.x; th[J][1] = v.y;
+    }
+  }
+  double lpacc = 0.0;
+  const int offA = rho_g * S + 2 * tig;                 // phase 1 B fragment: X[rho(gid)][8J + 2tig .. +1]
+  const int offB0 = rho_t0 * S + gid, offB1 = rho_t1 * S + gid;   // phase 2 B fragment: X[rho(2tig+e)][8J + gid]
+
+  for (int b = b0; b < b1; ++b) {
+    const int it = b - b0, st = it % STAGES, round = it / STAGES;
+    mbar_wait(&full[st], (uint32_t)(round & 1));
+    const double* Xs = sm + SD * st;
+    const double* ys = Xs + (size_t)MB * S + 8;
+    // phase 1: Z^T tile = Theta^T X^T
+    double acc[NT][2];
+#pragma unroll
+    for (int T = 0; T < NT; ++T) acc[T][0] = acc[T][1] = 0.0;
+#pragma unroll
+    for (int J = 0; J < NJ; ++J) {
+      if (J < nj) {
+#pragma unroll
+        for (int T = 0; T < NT; ++T) {
+          const double2 xv = *reinterpret_cast<const double2*>(Xs + T * 8 * S + offA + 8 * J);
+          dmma(acc[T], th[J][0], xv.x);
+          dmma(acc[T], th[J][1], xv.y);
+        }
+      }
+    }
+    // sigmoid epilogue in registers: r = y - p  (d/dz of log(y ? p : 1-p) with p = 1/(1+exp(-z)))
+#pragma unroll
+    for (int T = 0; T < NT; ++T) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double y = ys[T * 8 + (e ? rho_t1 : rho_t0)];
+        const double pr = 1.0 / (1.0 + exp(-acc[T][e]));
+        if (P.want_lp && y <= 1.0) lpacc += log(y != 0.0 ? pr : 1.0 - pr);   // distrib.t:17-25 on the naive sigmoid
+        acc[T][e] = y - pr;
+      }
+    }
+    // phase 2: G^T += R^T X
+#pragma unroll
+    for (int T = 0; T < NT; ++T) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double* xb = Xs + T * 8 * S + (e ? offB1 : offB0);
+#pragma unroll
+        for (int J = 0; J < NJ; ++J)
+          if (J < nj) dmma(G[J], acc[T][e], xb[8 * J]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+
+  if (valid) {
+    double* out = P.partG + ((size_t)split * P.C + chain) * P.Dp + 2 * tig;
+#pragma unroll
+    for (int J = 0; J < NJ; ++J)
+      if (J < nj) *reinterpret_cast<double2*>(out + 8 * J) = make_double2(G[J][0], G[J][1]);
+  }
+  if (P.want_lp) {
+    lpacc += __shfl_xor_sync(0xffffffffu, lpacc, 1);
+    lpacc += __shfl_xor_sync(0xffffffffu, lpacc, 2);
+    if (valid && tig == 0) P.partLp[(size_t)split * P.C + chain] = lpacc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vector kernels: one warp per chain, lanes over dimensions.
+enum { V_INIT_SAMPLE = 0, V_FINISH_EVAL = 1, V_TRANS_FIRST = 2, V_TRANS_MID = 3, V_TRANS_LAST = 4, V_PROBE_FIRST = 5, V_PROBE_LAST = 6 };
+
+struct VecParams {
+  RngKey key; uint32_t chain_begin, C; int d, Dp, ksplit;
+  double prior_sigma;
+  double *x, *g, *xs, *gs, *p;                 // [C][Dp]
+  const double* partG; const double* partLp;
+  double *lp, *H0, *eps, *prevlp;
+  double *da_gbar, *da_xbar, *da_x0, *da_lastx, *da_gamma; uint32_t* da_k;
+  int *direction, *done; int* n_active;
+  unsigned long long *made, *acc;
+  int* status;
+  uint32_t iter, L, step, probe;
+  int adapting;
+  double stepSize0;
+  // samples / record
+  double *samples, *samp_lp; uint32_t SC; uint64_t sidx; int keep;
+  double *rec_state, *rec_dh, *rec_step, *rec_leap; int* rec_accept; uint64_t rec_iters, rec_row;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// gradient and (optionally) log-density of the chain at xs from the partial sums of the GEMM kernel
+__device__ __forceinline__ double finish_grad(const VecParams& P, uint32_t c, int i, double th) {
+  double gl = 0.0;
+  for (int r = 0; r < P.ksplit; ++r) gl += P.partG[((size_t)r * P.C + c) * P.Dp + i];
+  return gaussian_dlp_dx(th, 0.0, P.prior_sigma) + gl;
+}
+__device__ __forceinline__ double finish_lp(const VecParams& P, uint32_t c, int lane, const double* pos) {
+  double lpp = 0.0;
+  for (int i = lane; i < P.d; i += 32) lpp += gaussian_lp(pos[i], 0.0, P.prior_sigma);
+  lpp = warp_sum(lpp);
+  double ll = 0.0;
+  for (int r = 0; r < P.ksplit; ++r) ll += P.partLp[(size_t)r * P.C + c];
+  return lpp + ll;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ VecParams P) {
+  const uint32_t c = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (c >= P.C) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t gc = P.chain_begin + c;
+  const int d = P.d;
+  const size_t base = (size_t)c * P.Dp;
+  double* x = P.x + base; double* g = P.g + base; double* xs = P.xs + base; double* gs = P.gs + base; double* p = P.p + base;
+
+  if (MODE == V_INIT_SAMPLE) {
+    // forward sample theta_j ~ gaussian(0, sigma) in program order (trace.t:612-623); lp follows from the first evaluation
+    for (int i = lane; i < P.Dp; i += 32) {
+      double v = i < d ? gaussian_sample(P.key, gc, QSB_ITER_INIT, (uint32_t)i, 0.0, P.prior_sigma) : 0.0;
+      x[i] = v; xs[i] = v; g[i] = 0.0; gs[i] = 0.0; p[i] = 0.0;
+    }
+    return;
+  }
+  if (MODE == V_FINISH_EVAL) {
+    // lp and gradient at x (= xs) after an evaluation outside a trajectory: initial trace logprob and
+    // the gradient HMCKernel:checkForChanges computes on its first call (hmc.t:254)
+    for (int i = lane; i < d; i += 32) g[i] = finish_grad(P, c, i, x[i]);
+    double lp = finish_lp(P, c, lane, x);
+    if (lane == 0) { P.lp[c] = lp; P.prevlp[c] = lp; }
+    return;
+  }
+  const double eps = P.eps[c];
+  const double he = 0.5 * eps;
+  if (MODE == V_TRANS_FIRST || MODE == V_PROBE_FIRST) {
+    if (MODE == V_PROBE_FIRST && P.done[c]) return;
+    // sampleMomenta, initial Hamiltonian, first half-kick and drift (hmc.t:140-149, 307-315)
+    const uint32_t it = MODE == V_PROBE_FIRST ? QSB_ITER_SEARCH + P.probe : P.iter;
+    double kin = 0.0;
+    for (int i = lane; i < d; i += 32) {
+      double m = gaussian_std(P.key, gc, it, (uint32_t)i) * 1.0;
+      kin += m * m * 1.0;
+      m = m + he * g[i];
+      double pos = x[i] + eps * m * 1.0;
+      p[i] = m; xs[i] = pos;
+    }
+    if (MODE == V_TRANS_FIRST) {
+      kin = -0.5 * warp_sum(kin);
+      if (lane == 0) { P.H0[c] = kin + P.lp[c]; P.made[c] += 1; }
+    }
+    return;
+  }
+  if (MODE == V_TRANS_MID) {
+    // finish leapfrog step `step` (second half-kick), start the next one (hmc.t:307-323)
+    for (int i = lane; i < d; i += 32) {
+      double pos = xs[i];
+      double gn = finish_grad(P, c, i, pos);
+      double m = p[i] + he * gn;
+      if (P.rec_leap) P.rec_leap[(((size_t)c * P.rec_iters + P.rec_row) * P.L + P.step) * d + i] = pos;
+      m = m + he * gn;
+      p[i] = m; xs[i] = pos + eps * m * 1.0;
+    }
+    return;
+  }
+  if (MODE == V_PROBE_LAST) {
+    if (P.done[c]) return;
+    // searchForInitialStepSize bookkeeping (hmc.t:345-391); the momentum half-kick is irrelevant to it
+    double lp = finish_lp(P, c, lane, xs);
+    if (lane == 0) {
+      const double LOG_HALF = log(0.5);
+      double H = lp - P.prevlp[c];
+      P.prevlp[c] = lp;
+      double e2 = eps;
+      int done = 0;
+      if (P.probe == 0) P.direction[c] = H > LOG_HALF ? 1 : -1;
+      else {
+        int dir = P.direction[c];
+        if (!(lp == lp)) { atomicOr(P.status, 1); done = 1; }
+        else if (dir == 1 && H <= LOG_HALF) done = 1;
+        else if (dir == -1 && H >= LOG_HALF) done = 1;
+        else if (dir == 1) e2 = eps * 2.0;
+        else e2 = eps * 0.5;
+        if (!done && e2 > 1e300) { atomicOr(P.status, 2); done = 1; }
+        if (!done && e2 == 0) { atomicOr(P.status, 4); done = 1; }
+      }
+      P.eps[c] = e2;
+      if (done) {
+        P.done[c] = 1;
+        // adapter:reinit(stepSize, adaptRate) (hmc.t:261)
+        P.da_k[c] = 0; P.da_x0[c] = e2; P.da_lastx[c] = e2; P.da_gbar[c] = 0.0; P.da_xbar[c] = 0.0; P.da_gamma[c] = 0.05;
+      } else atomicAdd(P.n_active, 1);
+    }
+    return;
+  }
+  // ---- V_TRANS_LAST: last half-kick, final Hamiltonian, adaptation, accept/reject, sample (hmc.t:150-186)
+  double kin = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    double pos = xs[i];
+    double gn = finish_grad(P, c, i, pos);
+    double m = p[i] + he * gn;
+    if (P.rec_leap) P.rec_leap[(((size_t)c * P.rec_iters + P.rec_row) * P.L + P.step) * d + i] = pos;
+    gs[i] = gn; p[i] = m;
+    kin += m * m * 1.0;
+  }
+  const double newlp = finish_lp(P, c, lane, xs);
+  const double H_new = -0.5 * warp_sum(kin) + newlp;
+  const double dH = H_new - P.H0[c];
+  double eps_new = eps;
+  if (P.adapting) {   // adaptStepSize + DualAverage:update (hmc.t:38-48, 394-402)
+    double EdH = exp(dH);
+    if (EdH > 1.0) EdH = 1.0;
+    if (!(EdH == EdH)) EdH = 0.0;
+    const double target = P.L == 1 ? 0.574 : 0.65;
+    double gr = target - EdH;
+    uint32_t k = P.da_k[c] + 1;
+    double avgeta = 1.0 / (double)(k + 10);
+    double xbar_avgeta = pow((double)k, -0.75);
+    double muk = 0.5 * sqrt((double)k) / P.da_gamma[c];
+    double gbar = avgeta * gr + (1 - avgeta) * P.da_gbar[c];
+    double lastx = P.da_x0[c] - muk * gbar;
+    double xbar = xbar_avgeta * lastx + (1 - xbar_avgeta) * P.da_xbar[c];
+    __syncwarp();
+    if (lane == 0) { P.da_k[c] = k; P.da_gbar[c] = gbar; P.da_lastx[c] = lastx; P.da_xbar[c] = xbar; }
+    eps_new = exp(lastx);
+  }
+  const double u = uniform_at(P.key, gc, P.iter, (uint32_t)d);
+  const bool accept = log(u) < dH;
+  __syncwarp();
+  if (accept) {
+    for (int i = lane; i < d; i += 32) { x[i] = xs[i]; g[i] = gs[i]; }
+    if (lane == 0) { P.acc[c] += 1; P.lp[c] = newlp; }
+  }
+  if (lane == 0) P.eps[c] = eps_new;
+  __syncwarp();
+  if (P.rec_state) {
+    size_t r = (size_t)c * P.rec_iters + P.rec_row;
+    for (int i = lane; i < d; i += 32) P.rec_state[r * d + i] = x[i];
+    if (lane == 0) { P.rec_accept[r] = accept ? 1 : 0; P.rec_dh[r] = dH; P.rec_step[r] = eps; }
+  }
+  if (P.keep && c < P.SC) {
+    for (int i = lane; i < d; i += 32) P.samples[((size_t)P.sidx * P.SC + c) * d + i] = x[i];
+    if (lane == 0) P.samp_lp[(size_t)P.sidx * P.SC + c] = accept ? newlp : P.lp[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct GlmSampler {
+  GlmModel* m = nullptr;
+  cudaStream_t stream = nullptr;
+  VecParams V;
+  GradParams Gp;
+  std::vector<void*> bufs;
+  uint32_t L = 1; bool adapting = true; double stepSize0 = 1.0;
+  uint32_t flags = 0;
+  bool searched = false;
+  uint64_t iter = 0, burnin = 0, lag = 1, max_samples = 0, rec_iters = 0;
+  uint64_t grad_evals = 0, leapfrogs = 0, launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int nj_inst = 0;
+  size_t smem = 0;
+};
+
+static int pick_ksplit(int ntiles, int nblocks, int nsm) {
+  int best = 1; double beste = 0.0;
+  const int kmax = std::max(1, nblocks / 12);
+  for (int k = 1; k <= kmax; ++k) {
+    long ctas = (long)ntiles * k;
+    long waves = (ctas + nsm - 1) / nsm;
+    double eff = (double)ctas / (double)(waves * nsm);
+    // per-CTA prologue/epilogue costs roughly one row block of time
+    eff *= (double)(nblocks / k) / (double)(nblocks / k + 1.5);
+    if (eff > beste * 1.005) { beste = eff; best = k; }
+  }
+  return best;
+}
+
+template <int NJ> static cudaError_t launch_grad_t(const GradParams& P, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  glm_grad_kernel<NJ><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
+  return cudaGetLastError();
+}
+static cudaError_t launch_grad(int nj_inst, const GradParams& P, size_t smem, cudaStream_t st) {
+  switch (nj_inst) {
+    case 2: return launch_grad_t<2>(P, smem, st);
+    case 4: return launch_grad_t<4>(P, smem, st);
+    case 13: return launch_grad_t<13>(P, smem, st);
+    case 16: return launch_grad_t<16>(P, smem, st);
+  }
+  return cudaErrorInvalidValue;
+}
+static int pick_nj_inst(int nj) { for (int c : {2, 4, 13, 16}) if (nj <= c) return c; return 0; }
+
+int glm_model_create(GlmModel* m, const double* X, const uint8_t* y, int N, int d, double prior_sigma, std::string& why) {
+  if (d > 128) { why = "dim <= 128 supported by the tensor-core GLM path"; return 1; }
+  m->N = N; m->d = d; m->prior_sigma = prior_sigma;
+  m->Dp = 8 * ((d + 7) / 8);
+  int S = d; while (S % 8 != 4) ++S;
+  m->S = S;
+  m->Npad = MB * ((N + MB - 1) / MB);
+  std::vector<double> Xp((size_t)m->Npad * S, 0.0), yv(m->Npad, 2.0);
+  for (int i = 0; i < N; ++i) {
+    memcpy(&Xp[(size_t)i * S], X + (size_t)i * d, sizeof(double) * d);
+    yv[i] = y[i] ? 1.0 : 0.0;
+  }
+  if (cudaMalloc((void**)&m->Xp, Xp.size() * 8) != cudaSuccess || cudaMalloc((void**)&m->yv, yv.size() * 8) != cudaSuccess) { why = "cudaMalloc failed"; return 2; }
+  cudaMemcpy(m->Xp, Xp.data(), Xp.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(m->yv, yv.data(), yv.size() * 8, cudaMemcpyHostToDevice);
+  return 0;
+}
+void glm_model_destroy(GlmModel* m) {
+  if (m->Xp) cudaFree(m->Xp);
+  if (m->yv) cudaFree(m->yv);
+  m->Xp = m->yv = nullptr;
+}
+
+template <class T> static bool dalloc(GlmSampler* s, T** p, size_t n) {
+  *p = nullptr;
+  if (cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return false;
+  cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T));
+  s->bufs.push_back(*p);
+  return true;
+}
+
+static void glm_free_run_buffers(GlmSampler* s) {
+  VecParams& V = s->V;
+  for (double** p : {&V.samples, &V.samp_lp, &V.rec_state, &V.rec_dh, &V.rec_step, &V.rec_leap}) if (*p) { cudaFree(*p); *p = nullptr; }
+  if (V.rec_accept) { cudaFree(V.rec_accept); V.rec_accept = nullptr; }
+  s->rec_iters = 0; V.rec_iters = 0;
+}
+
+GlmSampler* glm_sampler_create(GlmModel* m, double stepSize, uint32_t numSteps, bool adapt, uint64_t seed, uint32_t chain_begin,
+                               uint32_t numchains, uint32_t sample_chains, uint32_t flags, void* stream, std::string& why) {
+  GlmSampler* s = new GlmSampler();
+  s->m = m; s->stream = (cudaStream_t)stream; s->L = numSteps; s->adapting = adapt; s->stepSize0 = stepSize; s->flags = flags;
+  memset(&s->V, 0, sizeof(s->V)); memset(&s->Gp, 0, sizeof(s->Gp));
+  VecParams& V = s->V; GradParams& G = s->Gp;
+  const size_t C = numchains, Dp = m->Dp;
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  G.Xp = m->Xp; G.yv = m->yv; G.S = m->S; G.d = m->d; G.nj = m->Dp / 8; G.nblocks = m->Npad / MB;
+  G.ntiles = (int)((C + CB - 1) / CB); G.ksplit = pick_ksplit(G.ntiles, G.nblocks, nsm);
+  G.C = numchains; G.Dp = m->Dp;
+  s->nj_inst = pick_nj_inst(G.nj);
+  s->smem = stage_doubles(m->S) * STAGES * 8 + 2 * STAGES * 8;
+  V.key = RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)}; V.chain_begin = chain_begin; V.C = numchains; V.d = m->d; V.Dp = m->Dp;
+  V.ksplit = G.ksplit; V.prior_sigma = m->prior_sigma; V.L = numSteps; V.adapting = adapt ? 1 : 0; V.stepSize0 = stepSize; V.SC = sample_chains;
+  bool ok = dalloc(s, &V.x, C * Dp) && dalloc(s, &V.g, C * Dp) && dalloc(s, &V.xs, C * Dp) && dalloc(s, &V.gs, C * Dp) && dalloc(s, &V.p, C * Dp);
+  double *partG = nullptr, *partLp = nullptr;
+  ok = ok && dalloc(s, &partG, (size_t)G.ksplit * C * Dp) && dalloc(s, &partLp, (size_t)G.ksplit * C);
+  ok = ok && dalloc(s, &V.lp, C) && dalloc(s, &V.H0, C) && dalloc(s, &V.eps, C) && dalloc(s, &V.prevlp, C);
+  ok = ok && dalloc(s, &V.da_gbar, C) && dalloc(s, &V.da_xbar, C) && dalloc(s, &V.da_x0, C) && dalloc(s, &V.da_lastx, C) && dalloc(s, &V.da_gamma, C) && dalloc(s, &V.da_k, C);
+  ok = ok && dalloc(s, &V.direction, C) && dalloc(s, &V.done, C) && dalloc(s, &V.n_active, 1) && dalloc(s, &V.made, C) && dalloc(s, &V.acc, C) && dalloc(s, &V.status, 1);
+  ok = ok && cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+  if (!ok || !s->nj_inst) { why = !s->nj_inst ? "unsupported dim" : "cudaMalloc failed"; glm_sampler_destroy(s); return nullptr; }
+  G.partG = partG; G.partLp = partLp; V.partG = partG; V.partLp = partLp;
+  G.theta = V.xs;
+  return s;
+}
+
+void glm_sampler_destroy(GlmSampler* s) {
+  if (!s) return;
+  cudaStreamSynchronize(s->stream);
+  glm_free_run_buffers(s);
+  for (void* p : s->bufs) cudaFree(p);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+}
+
+#define GCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { why = std::string(#call) + ": " + cudaGetErrorString(e_); return 100 + (int)e_; } } while (0)
+
+template <int MODE> static cudaError_t launch_vec(GlmSampler* s, const VecParams& V) {
+  glm_vec_kernel<MODE><<<(unsigned)(((size_t)V.C * 32 + 255) / 256), 256, 0, s->stream>>>(V);
+  ++s->launches;
+  return cudaGetLastError();
+}
+static cudaError_t run_grad(GlmSampler* s, const double* theta, int want_lp) {
+  GradParams G = s->Gp;
+  G.theta = theta; G.want_lp = want_lp;
+  ++s->launches; ++s->grad_evals;
+  return launch_grad(s->nj_inst, G, s->smem, s->stream);
+}
+
+static int reset_chain_state(GlmSampler* s, std::string& why) {
+  VecParams& V = s->V;
+  const size_t C = V.C;
+  std::vector<double> e(C, s->stepSize0);
+  GCU(cudaMemcpyAsync(V.eps, e.data(), 8 * C, cudaMemcpyHostToDevice, s->stream));
+  GCU(cudaStreamSynchronize(s->stream));
+  for (double* p : {V.da_gbar, V.da_xbar, V.da_x0, V.da_lastx, V.da_gamma}) GCU(cudaMemsetAsync(p, 0, 8 * C, s->stream));
+  GCU(cudaMemsetAsync(V.da_k, 0, 4 * C, s->stream));
+  GCU(cudaMemsetAsync(V.done, 0, 4 * C, s->stream)); GCU(cudaMemsetAsync(V.direction, 0, 4 * C, s->stream));
+  GCU(cudaMemsetAsync(V.made, 0, 8 * C, s->stream)); GCU(cudaMemsetAsync(V.acc, 0, 8 * C, s->stream));
+  GCU(cudaMemsetAsync(V.status, 0, 4, s->stream));
+  s->searched = false; s->iter = 0; s->grad_evals = 0; s->leapfrogs = 0;
+  return 0;
+}
+
+// lp and gradient at x: the trace's initial logprob (trace.t:612-623) and HMC's first gradient (hmc.t:254)
+static int eval_at_x(GlmSampler* s, std::string& why) {
+  GCU(run_grad(s, s->V.x, 1));
+  GCU(launch_vec<V_FINISH_EVAL>(s, s->V));
+  return 0;
+}
+
+int glm_sampler_init(GlmSampler* s, std::string& why) {
+  if (int rc = reset_chain_state(s, why)) return rc;
+  GCU(launch_vec<V_INIT_SAMPLE>(s, s->V));
+  return eval_at_x(s, why);
+}
+
+int glm_sampler_set_state(GlmSampler* s, const double* x, std::string& why) {
+  if (int rc = reset_chain_state(s, why)) return rc;
+  const VecParams& V = s->V;
+  std::vector<double> h((size_t)V.C * V.Dp, 0.0);
+  for (size_t c = 0; c < V.C; ++c) memcpy(&h[c * V.Dp], x + c * V.d, 8 * V.d);
+  GCU(cudaMemcpyAsync(V.x, h.data(), 8 * h.size(), cudaMemcpyHostToDevice, s->stream));
+  GCU(cudaMemcpyAsync(V.xs, h.data(), 8 * h.size(), cudaMemcpyHostToDevice, s->stream));
+  GCU(cudaStreamSynchronize(s->stream));
+  return eval_at_x(s, why);
+}
+
+int glm_sampler_get_state(GlmSampler* s, double* x, std::string& why) {
+  const VecParams& V = s->V;
+  std::vector<double> h((size_t)V.C * V.Dp);
+  GCU(cudaMemcpyAsync(h.data(), V.x, 8 * h.size(), cudaMemcpyDeviceToHost, s->stream));
+  GCU(cudaStreamSynchronize(s->stream));
+  for (size_t c = 0; c < V.C; ++c) memcpy(x + c * V.d, &h[c * V.Dp], 8 * V.d);
+  return 0;
+}
+
+int glm_sampler_begin(GlmSampler* s, uint64_t max_samples, uint64_t burnin, uint64_t lag, uint64_t numiters, std::string& why) {
+  VecParams& V = s->V;
+  glm_free_run_buffers(s);
+  s->iter = 0; s->burnin = burnin; s->lag = lag; s->max_samples = max_samples;
+  if (max_samples > 0) {
+    GCU(cudaMalloc((void**)&V.samples, 8 * max_samples * V.SC * V.d));
+    GCU(cudaMalloc((void**)&V.samp_lp, 8 * max_samples * V.SC));
+  }
+  if (s->flags & QSB_FLAG_RECORD) {
+    if (numiters == 0) { why = "QSB_FLAG_RECORD needs numiters"; return 2; }
+    const size_t C = V.C, d = V.d;
+    s->rec_iters = numiters; V.rec_iters = numiters;
+    GCU(cudaMalloc((void**)&V.rec_state, 8 * C * numiters * d));
+    GCU(cudaMalloc((void**)&V.rec_dh, 8 * C * numiters));
+    GCU(cudaMalloc((void**)&V.rec_step, 8 * C * numiters));
+    GCU(cudaMalloc((void**)&V.rec_accept, 4 * C * numiters));
+    if (s->flags & QSB_FLAG_RECORD_LEAP) {
+      GCU(cudaMalloc((void**)&V.rec_leap, 8 * C * numiters * s->L * d));
+      GCU(cudaMemset(V.rec_leap, 0, 8 * C * numiters * s->L * d));
+    }
+  }
+  return 0;
+}
+
+// searchForInitialStepSize (hmc.t:345-391): every probe is one leapfrog step of all chains still searching;
+// the host only loops until no chain is left (one 4-byte read per probe; initialisation only)
+static int step_size_search(GlmSampler* s, std::string& why) {
+  VecParams V = s->V;
+  for (uint32_t probe = 0; probe < 4096; ++probe) {
+    V.probe = probe;
+    GCU(cudaMemsetAsync(V.n_active, 0, 4, s->stream));
+    GCU(launch_vec<V_PROBE_FIRST>(s, V));
+    GCU(run_grad(s, V.xs, 1));
+    GCU(launch_vec<V_PROBE_LAST>(s, V));
+    int n_active = 0;
+    GCU(cudaMemcpyAsync(&n_active, V.n_active, 4, cudaMemcpyDeviceToHost, s->stream));
+    GCU(cudaStreamSynchronize(s->stream));
+    if (n_active == 0) break;
+  }
+  int st = 0;
+  GCU(cudaMemcpy(&st, V.status, 4, cudaMemcpyDeviceToHost));
+  if (st & 1) { why = "HMC step size search failed because logprob became NaN"; return 20; }
+  if (st & 2) { why = "HMC step size search diverged to infinity (Is your probability distribution flat?)"; return 21; }
+  if (st & 4) { why = "HMC step size search collapsed to zero (Is your probability distribution discontinuous?)"; return 22; }
+  return 0;
+}
+
+int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
+  if (s->rec_iters && s->iter + iters > s->rec_iters) { why = "record buffer holds numiters iterations only"; return 2; }
+  if (!s->searched) {
+    ++s->grad_evals;   // the reference's first traceUpdate (hmc.t:254); its value was computed with the initial logprob
+    if (s->adapting) if (int rc = step_size_search(s, why)) return rc;
+    s->searched = true;
+  }
+  GCU(cudaEventRecord(s->ev0, s->stream));
+  for (uint64_t k = 0; k < iters; ++k) {
+    const uint64_t it = s->iter + k;
+    VecParams V = s->V;
+    V.iter = (uint32_t)it; V.rec_row = it;
+    GCU(launch_vec<V_TRANS_FIRST>(s, V));
+    for (uint32_t st = 0; st < s->L; ++st) {
+      const bool last = st + 1 == s->L;
+      V.step = st;
+      GCU(run_grad(s, V.xs, last ? 1 : 0));
+      if (!last) GCU(launch_vec<V_TRANS_MID>(s, V));
+      else {
+        V.keep = (it >= s->burnin && it % s->lag == 0 && V.samples) ? 1 : 0;
+        V.sidx = it / s->lag - (s->burnin + s->lag - 1) / s->lag;
+        if (V.sidx >= s->max_samples) V.keep = 0;
+        GCU(launch_vec<V_TRANS_LAST>(s, V));
+      }
+    }
+    s->leapfrogs += s->L;
+  }
+  GCU(cudaEventRecord(s->ev1, s->stream));
+  s->iter += iters;
+  return 0;
+}
+
+void glm_sampler_sample_view(GlmSampler* s, const double** samples, const double** samp_lp, int* G, uint32_t* SC, int* retdim) {
+  *samples = s->V.samples; *samp_lp = s->V.samp_lp; *G = 32; *SC = s->V.SC; *retdim = s->V.d;
+}
+
+int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* grad_evals, uint64_t* leapfrogs, uint64_t* launches,
+                      double* seconds, std::string& why) {
+  const VecParams& V = s->V;
+  std::vector<unsigned long long> m(V.C), a(V.C);
+  GCU(cudaStreamSynchronize(s->stream));
+  GCU(cudaMemcpy(m.data(), V.made, 8 * V.C, cudaMemcpyDeviceToHost));
+  GCU(cudaMemcpy(a.data(), V.acc, 8 * V.C, cudaMemcpyDeviceToHost));
+  *made = 0; *acc = 0;
+  for (size_t c = 0; c < V.C; ++c) { *made += m[c]; *acc += a[c]; }
+  *grad_evals = s->grad_evals * V.C; *leapfrogs = s->leapfrogs * V.C; *launches = s->launches;
+  float ms = 0.f;
+  *seconds = (s->iter && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) ? ms * 1e-3 : 0.0;
+  return 0;
+}
+
+int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, double* dh, double* step, double* leap, std::string& why) {
+  const VecParams& V = s->V;
+  if (!V.rec_state) { why = "sampler was not created with QSB_FLAG_RECORD"; return 2; }
+  GCU(cudaStreamSynchronize(s->stream));
+  const size_t C = V.C, d = V.d, T = s->rec_iters;
+  if (state) GCU(cudaMemcpy(state, V.rec_state, 8 * C * T * d, cudaMemcpyDeviceToHost));
+  if (accept) GCU(cudaMemcpy(accept, V.rec_accept, 4 * C * T, cudaMemcpyDeviceToHost));
+  if (dh) GCU(cudaMemcpy(dh, V.rec_dh, 8 * C * T, cudaMemcpyDeviceToHost));
+  if (step) GCU(cudaMemcpy(step, V.rec_step, 8 * C * T, cudaMemcpyDeviceToHost));
+  if (leap) { if (!V.rec_leap) { why = "leapfrog positions need QSB_FLAG_RECORD_LEAP"; return 2; } GCU(cudaMemcpy(leap, V.rec_leap, 8 * C * T * s->L * d, cudaMemcpyDeviceToHost)); }
+  return 0;
+}
+
+int glm_logp_grad(GlmModel* m, const double* x, int n, double* lp_dual, double* grad, double* lp_float, std::string& why) {
+  GlmSampler* s = glm_sampler_create(m, 1.0, 1, false, 0, 0, (uint32_t)n, (uint32_t)n, 0, nullptr, why);
+  if (!s) return 5;
+  int rc = glm_sampler_set_state(s, x, why);
+  if (!rc) {
+    const VecParams& V = s->V;
+    std::vector<double> g((size_t)n * V.Dp), lp(n);
+    cudaError_t e = cudaMemcpy(g.data(), V.g, 8 * g.size(), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(lp.data(), V.lp, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { why = cudaGetErrorString(e); rc = 100 + (int)e; }
+    else {
+      for (int c = 0; c < n; ++c) {
+        if (grad) memcpy(grad + (size_t)c * V.d, &g[(size_t)c * V.Dp], 8 * V.d);
+        if (lp_dual) lp_dual[c] = lp[c];
+        if (lp_float) lp_float[c] = lp[c];
+      }
+    }
+  }
+  glm_sampler_destroy(s);
+  return rc;
+}
+
+}  // namespace qsb

@@ -1,0 +1,38 @@
+// Host interface of the Bernoulli-logit GLM path (config c3: Bayesian logistic regression under HMC).
+// Implemented in glm_hmc.cu; used by capi.cu only.
+#pragma once
+#include <cstdint>
+#include <string>
+
+namespace qsb {
+
+struct GlmModel {
+  int N = 0, d = 0;        // observations, regression dimension
+  int Npad = 0;            // rows padded to a whole number of row blocks
+  int S = 0;               // row stride of the staged X in doubles (>= d, S % 8 == 4: conflict-free fragment loads)
+  int Dp = 0;              // d padded to a multiple of 8 (DMMA n-tiles)
+  double prior_sigma = 0;
+  double* Xp = nullptr;    // HBM [Npad][S], zero padded
+  double* yv = nullptr;    // HBM [Npad]: 0.0 / 1.0, 2.0 marks a padding row
+};
+
+struct GlmSampler;
+
+int glm_model_create(GlmModel* m, const double* X, const uint8_t* y, int N, int d, double prior_sigma, std::string& why);
+void glm_model_destroy(GlmModel* m);
+
+GlmSampler* glm_sampler_create(GlmModel* m, double stepSize, uint32_t numSteps, bool adapt, uint64_t seed, uint32_t chain_begin,
+                               uint32_t numchains, uint32_t sample_chains, uint32_t flags, void* stream, std::string& why);
+void glm_sampler_destroy(GlmSampler* s);
+int glm_sampler_init(GlmSampler* s, std::string& why);
+int glm_sampler_set_state(GlmSampler* s, const double* x, std::string& why);
+int glm_sampler_get_state(GlmSampler* s, double* x, std::string& why);
+int glm_sampler_begin(GlmSampler* s, uint64_t max_samples, uint64_t burnin, uint64_t lag, uint64_t numiters, std::string& why);
+int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why);
+void glm_sampler_sample_view(GlmSampler* s, const double** samples, const double** samp_lp, int* G, uint32_t* SC, int* retdim);
+int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* grad_evals, uint64_t* leapfrogs, uint64_t* launches,
+                      double* seconds, std::string& why);
+int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, double* dh, double* step, double* leap, std::string& why);
+int glm_logp_grad(GlmModel* m, const double* x, int n, double* lp_dual, double* grad, double* lp_float, std::string& why);
+
+}  // namespace qsb

@@ -1,0 +1,145 @@
+"""Fixed-structure continuous programs: the model-family descriptors that stand for a
+``qs.program`` on the device.  Each function mirrors how a quicksand user
+writes the program (ERP calls with {struc=false}, qs.factor, erp.observe) and returns a
+:class:`Program` holding the POD descriptor the C ABI reads."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _dp(a):
+    return a.ctypes.data_as(L.dp)
+
+
+class Program:
+    """Host-side stand-in for a compiled ``qs.program`` (qs/progmodule.t:58-70)."""
+
+    def __init__(self, family, dim, **arrays):
+        self.family, self.dim = family, dim
+        self.nobs = arrays.pop("nobs", 0)
+        self.ret_mode = arrays.pop("ret_mode", 1)
+        self.ret_div = arrays.pop("ret_div", 1.0)
+        self.prior_sigma = arrays.pop("prior_sigma", 0.0)
+        self.arrays = arrays          # keeps the numpy buffers alive
+        self._models = {}
+
+    @property
+    def retdim(self):
+        return 1 if (self.family == L.FAM_INDEP and self.ret_mode == 0) else self.dim
+
+    def desc(self):
+        d = L.ModelDesc()
+        d.family, d.dim, d.nobs, d.ret_mode = self.family, self.dim, self.nobs, self.ret_mode
+        d.ret_div, d.prior_sigma = self.ret_div, self.prior_sigma
+        a = self.arrays
+        if "erp_kind" in a:
+            d.erp_kind = a["erp_kind"].ctypes.data_as(L.ip); d.erp_p0 = _dp(a["erp_p0"]); d.erp_p1 = _dp(a["erp_p1"])
+        if "A" in a:
+            d.A = _dp(a["A"])
+        if "X" in a:
+            d.X = _dp(a["X"]); d.ybin = a["ybin"].ctypes.data_as(C.POINTER(C.c_uint8))
+        if "y" in a:
+            d.y = _dp(a["y"]); d.sigma = _dp(a["sigma"])
+        return d
+
+    def model(self, device=-1):
+        """Device-resident model handle (uploads the model data once per device)."""
+        if device not in self._models:
+            h = C.c_void_p()
+            L.check(L.lib().qsb_model_create(C.byref(self.desc()), device, C.byref(h)))
+            self._models[device] = h
+        return self._models[device]
+
+    def upload(self, device=-1):
+        """Force a fresh host->device upload of the model data (used by the end-to-end benchmark)."""
+        self.release(device)
+        return self.model(device)
+
+    def release(self, device=None):
+        for dev in list(self._models) if device is None else [device]:
+            h = self._models.pop(dev, None)
+            if h is not None:
+                L.lib().qsb_model_destroy(h)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def logp_grad(self, x, device=-1):
+        """Test hook: (lp_dual, grad, lp_float) at unconstrained points x [n][dim]."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        n = x.shape[0]
+        lpd, lpf, g = np.empty(n), np.empty(n), np.empty_like(x)
+        L.check(L.lib().qsb_logp_grad(self.model(device), _dp(x), n, _dp(lpd), _dp(g), _dp(lpf)))
+        return lpd, g, lpf
+
+
+_KIND = {"gaussian": L.ERP_GAUSSIAN, "gamma": L.ERP_GAMMA, "beta": L.ERP_BETA, "uniform": L.ERP_UNIFORM}
+
+
+def indep(erps, ret="sum", ret_div=1.0):
+    """K independent ERPs with constant parameters, e.g. ``[("gamma", 2.0, 2.0)]`` with ret_div=10 for
+    ``return qs.gamma(2.0, 2.0, {struc=false})/10.0`` (test/testsuite.t:657-673)."""
+    kinds = np.array([_KIND[k] if isinstance(k, str) else int(k) for k, _, _ in erps], dtype=np.int32)
+    p0 = np.array([a for _, a, _ in erps], dtype=np.float64)
+    p1 = np.array([b for _, _, b in erps], dtype=np.float64)
+    return Program(L.FAM_INDEP, len(erps), erp_kind=kinds, erp_p0=p0, erp_p1=p1,
+                   ret_mode=0 if ret == "sum" else 1, ret_div=float(ret_div))
+
+
+def gauss_prec(A):
+    """x_i ~ qs.gaussian(0,1,{struc=false}), i<d; qs.factor(-0.5 x'Ax).  log p = -0.5 x'(I+A)x + c."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    return Program(L.FAM_GAUSS_PREC, A.shape[0], A=A)
+
+
+def logistic(X, y, prior_sigma=2.5):
+    """theta_j ~ qs.gaussian(0, prior_sigma); qs.flip.observe(y_i, 1/(1+exp(-x_i . theta)))."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.uint8)
+    return Program(L.FAM_LOGISTIC, X.shape[1], X=X, ybin=y, nobs=X.shape[0], prior_sigma=float(prior_sigma))
+
+
+def eight_schools(y, sigma):
+    """mu ~ gaussian(0,5); logtau ~ gaussian(0,1); theta_j ~ gaussian(mu, exp(logtau));
+    qs.gaussian.observe(y_j, theta_j, sigma_j).  Components [mu, logtau, theta_0..theta_{J-1}]."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    s = np.ascontiguousarray(sigma, dtype=np.float64)
+    return Program(L.FAM_EIGHT_SCHOOLS, len(y) + 2, y=y, sigma=s, nobs=len(y))
+
+
+def funnel(d):
+    """v ~ gaussian(0,3); x_i ~ gaussian(0, exp(v/2)), i<d-1.  Components [v, x_0..x_{d-2}]."""
+    return Program(L.FAM_FUNNEL, int(d))
+
+
+# ---- synthetic data of BASELINE.json's configs; numpy Philox streams, fixed seeds
+def _rng(seed):
+    return np.random.Generator(np.random.Philox(seed))
+
+
+def c2_correlated_gaussian(d=10, rho=0.9):
+    i = np.arange(d)
+    Sigma = rho ** np.abs(i[:, None] - i[None, :])
+    P = np.linalg.inv(Sigma)
+    return gauss_prec(P - np.eye(d)), Sigma
+
+
+def c3_logistic_data(N=10000, d=100):
+    X = _rng(1).standard_normal((N, d)) / np.sqrt(d)
+    theta = _rng(2).standard_normal(d)
+    p = 1.0 / (1.0 + np.exp(-(X @ theta)))
+    y = (_rng(3).random(N) < p).astype(np.uint8)
+    return X, y, theta
+
+
+def c4_eight_schools_data(J=1000):
+    r = _rng(4)
+    sigma = r.uniform(8.0, 18.0, J)
+    theta = 4.0 + 3.0 * r.standard_normal(J)
+    y = theta + sigma * r.standard_normal(J)
+    return y, sigma

@@ -1,0 +1,90 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol include/qsb200.h declares
+(no compute calls: there is no GPU here), the product has no route into the oracle, and the host-side
+mirror of the reference interface keeps the reference's names, defaults and error behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "qsb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qsb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(qs):
+    from quicksand_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libqsb200.so does not export %s" % name
+    assert sorted(_lib.PROTOTYPES) == declared
+    assert lib.qsb_version() == 100
+
+
+def test_header_is_plain_c(tmp_path):
+    """terralib.includec needs a header a C compiler accepts."""
+    import subprocess
+    c = tmp_path / "t.c"
+    c.write_text('#include "qsb200.h"\nint main(void){ qsb_run_config c; c.seed = 1; return (int)c.seed - 1 + (QSB_VERSION != 100); }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(c), "-o",
+                    str(tmp_path / "t.o")], check=True)
+
+
+def test_product_never_touches_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use oracle/."""
+    pkg = os.path.join(ROOT, "quicksand_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".t")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), (dirpath, f)
+                assert "libqsoracle" not in text and "oracle/" not in text, (dirpath, f)
+
+
+def test_kernel_constructor_defaults_match_reference(qs):
+    from quicksand_b200 import _lib as L
+    h = qs.HMCKernel().specs[0]        # hmc.t:57-66
+    assert (h.kind, h.stepSize, h.numSteps, h.doAdapt) == (L.KERNEL_HMC, 1.0, 1, 1)
+    h = qs.HMCKernel({"numSteps": 10, "doStepSizeAdapt": False}).specs[0]
+    assert (h.numSteps, h.doAdapt) == (10, 0)
+    d = qs.DriftKernel().specs[0]      # drift.t:63-73
+    assert (d.kind, d.scale, d.doAdapt) == (L.KERNEL_DRIFT, 1.0, 1)
+    r = qs.HARMKernel(scale=2.0).specs[0]   # harm.t:16-22
+    assert (r.kind, r.scale, r.doAdapt) == (L.KERNEL_HARM, 2.0, 1)
+    m = qs.MixtureKernel([qs.HARMKernel(), qs.HMCKernel(numSteps=16)], [0.5, 0.5])
+    assert [s.kind for s in m.specs] == [L.KERNEL_HARM, L.KERNEL_HMC] and [s.weight for s in m.specs] == [0.5, 0.5]
+    with pytest.raises(AssertionError):   # mcmc.t:200-201
+        qs.MixtureKernel([qs.HARMKernel()], [0.5, 0.5])
+    with pytest.raises(TypeError):
+        qs.HMCKernel(stepsize=1.0)
+
+
+def test_expectation_query_matches_reference_quirk(qs, oracle):
+    """infer.t:146-187 on a hand-made S.Vector(Sample): same numbers as the oracle's restatement."""
+    rng = np.random.default_rng(0)
+    dt = np.dtype([("value", np.float64, (3,)), ("logprob", np.float64), ("loglikelihood", np.float64)])
+    data = np.zeros((2, 17), dtype=dt)
+    data["value"] = rng.normal(size=(2, 17, 3))
+    vec = qs.SampleVector(data)
+    m, v = qs.Expectation(True)(None)(vec)
+    for c in range(2):
+        mo, vo = oracle.expectation(data["value"][c], do_variance=True)
+        assert np.allclose(m[c], mo, rtol=0, atol=1e-14) and abs(v[c] - vo) < 1e-13
+    ac = qs.Autocorrelation()(None)(vec)
+    assert np.allclose(ac[0], oracle.autocorrelation(data["value"][0]), atol=1e-12)
+
+
+def test_no_gpu_means_loud_failure(qs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from quicksand_b200 import _lib
+    with pytest.raises(_lib.QsbError):
+        qs.programs.funnel(8).model()

@@ -1,0 +1,148 @@
+"""GPU parity tests proper: the CUDA engine, called through the C ABI, against the CPU oracle on the
+same seeded inputs and the same injected Philox stream (north_star: per-step leapfrog positions
+within 1e-10 relative in fp64, accept/reject decisions identical on >= 99.9 % of steps)."""
+import numpy as np
+import pytest
+
+import parity as P
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def test_rng_stream_bit_exact(qs, oracle):
+    from quicksand_b200 import _lib as L
+    import ctypes as C
+    for seed, chain, it, slot in [(0, 0, 0, 0), (20261019, 65535, 17, 9), (2**63 + 5, 2**31, oracle.ITER_INIT, 3),
+                                  (7, 1, oracle.ITER_SEARCH + 2, oracle.SLOT_MIXTURE)]:
+        out = np.empty(64)
+        L.check(L.lib().qsb_uniforms(seed, chain, it, slot, 64, out.ctypes.data_as(L.dp)))
+        ref = oracle.uniforms(seed, chain, it, slot, 64)
+        assert np.array_equal(out, ref)
+        g = np.empty(4096)
+        L.check(L.lib().qsb_gaussians(seed, chain, it, 0, 4096, 0.3, 1.7, g.ctypes.data_as(L.dp)))
+        gref = oracle.gaussians(seed, chain, it, 0, 4096, 0.3, 1.7)
+        assert np.array_equal(g, gref), np.abs(g - gref).max()   # Leva sampler: un-contracted arithmetic => bit-exact
+
+
+def test_device_densities_against_reference_goldens(qs):
+    """The known-answer values of test/testsuite.t:159-170 (tolerance 1e-8, testsuite.t:34) on the device functions."""
+    from quicksand_b200 import _lib as L
+    import json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "testsuite_logprob_goldens.json")))
+    for g in gold["cases"]:
+        if g["which"] not in (0, 1, 2, 3, 4):
+            continue
+        a = np.array((g["args"] + [0.0, 0.0, 0.0])[:3], dtype=np.float64)
+        out = np.empty(1)
+        L.check(L.lib().qsb_logprob(g["which"], a.ctypes.data_as(L.dp), 1, out.ctypes.data_as(L.dp)))
+        assert abs(out[0] - g["value"]) <= 1e-8, (g, out[0])
+
+
+def _programs(qs):
+    rng = np.random.default_rng(5)
+    progs = {}
+    progs["gaussian1"] = qs.programs.indep([("gaussian", 0.1, 0.5)])
+    progs["gamma1"] = qs.programs.indep([("gamma", 2.0, 2.0)], ret_div=10.0)
+    progs["beta1"] = qs.programs.indep([("beta", 2.0, 5.0)])
+    progs["uniform1"] = qs.programs.indep([("uniform", 0.1, 0.4)])
+    progs["gauss10"] = qs.programs.indep([("gaussian", 0.1, 0.5)] * 10, ret_div=10.0)
+    progs["mixed10"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("gamma", 2.0, 2.0), ("beta", 2.0, 5.0), ("uniform", -1.0, 3.0),
+                                           ("gamma", 0.7, 1.5)] * 2, ret="vector")
+    progs["c2"] = qs.programs.c2_correlated_gaussian()[0]
+    J = 11
+    progs["schools13"] = qs.programs.eight_schools(rng.normal(4, 10, J), rng.uniform(8, 18, J))
+    J = 60
+    progs["schools62"] = qs.programs.eight_schools(rng.normal(4, 10, J), rng.uniform(8, 18, J))
+    progs["funnel12"] = qs.programs.funnel(12)
+    progs["funnel70"] = qs.programs.funnel(70)
+    X = rng.standard_normal((333, 20)) / np.sqrt(20)
+    y = (rng.random(333) < 0.5).astype(np.uint8)
+    progs["logistic20"] = qs.programs.logistic(X, y, 2.5)
+    return progs
+
+
+@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "c2", "schools13", "schools62",
+                                  "funnel12", "funnel70", "logistic20"])
+def test_logp_and_gradient_match_tape_ad(qs, oracle, name):
+    """Closed-form device gradients vs the oracle's tape AD (qs/lib/ad.t) on random unconstrained points."""
+    prog = _programs(qs)[name]
+    op = P.oracle_program(prog)
+    rng = np.random.default_rng(11)
+    x = rng.normal(0, 1.0, (37, prog.dim))
+    lpd, g, lpf = prog.logp_grad(x)
+    for c in range(x.shape[0]):
+        lpd_o, g_o, lpf_o = op.logp_grad(x[c])
+        assert P.relerr(lpd[c], lpd_o) <= 1e-12, (name, c, lpd[c], lpd_o)
+        assert P.relerr(lpf[c], lpf_o) <= 1e-12, (name, c, lpf[c], lpf_o)
+        assert P.relerr(g[c], g_o).max() <= 1e-11, (name, c, np.abs(g[c] - g_o).max())
+
+
+HMC_CASES = [
+    ("gaussian1", dict(numSteps=1), 0), ("gaussian1", dict(numSteps=10), 0),
+    ("gamma1", dict(numSteps=10), 0), ("beta1", dict(numSteps=10), 0), ("uniform1", dict(numSteps=1), 0),
+    ("gauss10", dict(numSteps=10), 0), ("mixed10", dict(numSteps=5), 0), ("mixed10", dict(numSteps=5), 32),
+    ("c2", dict(numSteps=16, stepSize=0.15, doStepSizeAdapt=False), 0), ("c2", dict(numSteps=16), 0),
+    ("schools13", dict(numSteps=8), 1), ("schools13", dict(numSteps=8), 32), ("schools62", dict(numSteps=8), 0),
+    ("funnel12", dict(numSteps=16), 1), ("funnel12", dict(numSteps=16), 32), ("funnel70", dict(numSteps=16), 0),
+    ("logistic20", dict(numSteps=20), 0), ("logistic20", dict(numSteps=7, stepSize=0.05, doStepSizeAdapt=False), 0),
+]
+
+
+@pytest.mark.parametrize("name,kp,mapping", HMC_CASES)
+def test_hmc_per_step_parity(qs, oracle, name, kp, mapping):
+    prog = _programs(qs)[name]
+    gpu, cpu = P.run_both(prog, qs.HMCKernel(kp), chains=96, iters=30, seed=20261019, leap=True, mapping=mapping)
+    P.compare(gpu, cpu, TOL, leap=True, what="HMC %s %s map%d" % (name, kp, mapping))
+    assert P.relerr(gpu["step"], cpu["step"]).max() <= 1e-9
+    assert P.relerr(gpu["samples"], cpu["samples"]).max() <= 1e-9 or (gpu["accept"] != cpu["accept"]).any()
+
+
+@pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0),
+                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0)])
+def test_drift_per_step_parity(qs, oracle, name, mapping):
+    prog = _programs(qs)[name]
+    gpu, cpu = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=64, iters=400, seed=99, mapping=mapping)
+    P.compare(gpu, cpu, TOL, what="Drift %s map%d" % (name, mapping))
+
+
+@pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("gaussian1", 0), ("c2", 0), ("schools13", 32), ("schools62", 0),
+                                          ("funnel12", 1), ("funnel70", 0)])
+def test_harm_per_step_parity(qs, oracle, name, mapping):
+    prog = _programs(qs)[name]
+    gpu, cpu = P.run_both(prog, qs.HARMKernel(), chains=64, iters=300, seed=5, mapping=mapping)
+    P.compare(gpu, cpu, TOL, what="HARM %s map%d" % (name, mapping))
+    assert P.relerr(gpu["step"], cpu["step"]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name,mapping", [("funnel12", 1), ("funnel70", 0), ("gauss10", 0), ("schools13", 32)])
+def test_mixture_harm_hmc_parity(qs, oracle, name, mapping):
+    """config c5's kernel: MixtureKernel({HARMKernel{}, HMCKernel{numSteps=L}}, {0.5, 0.5}) (mcmc.t:199-291)."""
+    prog = _programs(qs)[name]
+    k = qs.MixtureKernel([qs.HARMKernel(), qs.HMCKernel(numSteps=16)], [0.5, 0.5])
+    gpu, cpu = P.run_both(prog, k, chains=64, iters=60, seed=31, mapping=mapping)
+    assert np.array_equal(gpu["kidx"], cpu["kidx"])
+    P.compare(gpu, cpu, TOL, what="Mixture %s map%d" % (name, mapping))
+
+
+def test_three_way_mixture_and_lag(qs, oracle):
+    prog = _programs(qs)["gauss10"]
+    k = qs.MixtureKernel([qs.DriftKernel(), qs.HARMKernel(), qs.HMCKernel(numSteps=3)], [0.2, 0.3, 0.5])
+    gpu, cpu = P.run_both(prog, k, chains=32, iters=10 + 20 * 3, seed=8, burnin=10, lag=3)
+    assert np.array_equal(gpu["kidx"], cpu["kidx"])
+    P.compare(gpu, cpu, TOL, what="3-way mixture")
+    assert gpu["samples"].shape == cpu["samples"].shape == (32, 20, 1)
+    same = (gpu["accept"] == cpu["accept"]).all(axis=1)
+    assert P.relerr(gpu["samples"][same], cpu["samples"][same]).max() <= 1e-9
+    assert P.relerr(gpu["logprobs"][same], cpu["logprobs"][same]).max() <= 1e-9
+
+
+def test_chain_ids_are_partition_invariant(qs):
+    """Philox key = global chain id: chains [32,64) run as a shard equal chains 32..63 of the full run, bit for bit
+    (the multi-GPU invariance the chain sharding relies on)."""
+    prog = _programs(qs)["funnel12"]
+    k = qs.HMCKernel(numSteps=4)
+    full = qs.Sampler(prog, k, numchains=64, seed=3); full.init(); full.run(20)
+    part = qs.Sampler(prog, k, numchains=32, seed=3, chain_begin=32); part.init(); part.run(20)
+    a = full.fetch_values(); b = part.fetch_values()
+    assert np.array_equal(a[32:], b)
