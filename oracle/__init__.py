@@ -20,7 +20,17 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = None
+_LIBS = {}
+_ACTIVE = "strict"
+_SO = {"strict": "libqsoracle.so", "fma": "libqsoracle_fma.so"}
+
+
+def use(variant):
+    """Select the oracle build new Programs are created in: "strict" (no FMA contraction, the oracle
+    proper) or "fma" (contracted; a control for chaotic trajectories, see the Makefile)."""
+    global _ACTIVE
+    assert variant in _SO
+    _ACTIVE = variant
 
 HMC, DRIFT, HARM = 1, 2, 3
 ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM = 0, 1, 2, 3
@@ -41,18 +51,18 @@ class Stats(C.Structure):
 
 def build(force=False):
     """Compile the restatement with g++ (Makefile in this directory)."""
-    so = os.path.join(_HERE, "libqsoracle.so")
-    if force or not os.path.exists(so) or any(
+    sos = [os.path.join(_HERE, f) for f in _SO.values()]
+    if force or any(not os.path.exists(so) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(so)
-            for f in os.listdir(_HERE) if f.endswith((".hpp", ".cpp"))):
+            for f in os.listdir(_HERE) if f.endswith((".hpp", ".cpp"))) for so in sos):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
-    return so
+    return sos[0]
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        so = os.path.join(_HERE, "libqsoracle.so")
+def lib(variant=None):
+    variant = variant or _ACTIVE
+    if variant not in _LIBS:
+        so = os.path.join(_HERE, _SO[variant])
         if not os.path.exists(so):
             build()
         L = C.CDLL(so)
@@ -81,8 +91,8 @@ def lib():
         L.qso_logp_grad.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp]
         L.qso_expectation.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, dp]
         L.qso_autocorrelation.argtypes = [dp, C.c_int, C.c_int, dp]
-        _LIB = L
-    return _LIB
+        _LIBS[variant] = L
+    return _LIBS[variant]
 
 
 def _dp(a):
@@ -131,12 +141,13 @@ class Program:
     def __init__(self, handle, keep=()):
         self.h = C.c_void_p(handle)
         self._keep = keep
-        self.retdim = lib().qso_program_retdim(self.h)
-        self.dim = lib().qso_program_dim(self.h)
+        self._lib = lib()          # the build this program's code lives in
+        self.retdim = self._lib.qso_program_retdim(self.h)
+        self.dim = self._lib.qso_program_dim(self.h)
 
     def __del__(self):
         try:
-            lib().qso_program_free(self.h)
+            self._lib.qso_program_free(self.h)
         except Exception:
             pass
 
@@ -172,7 +183,7 @@ class Program:
         x = np.ascontiguousarray(x, dtype=np.float64)
         g = np.empty_like(x)
         lpd, lpf = C.c_double(), C.c_double()
-        rc = lib().qso_logp_grad(self.h, _dp(x), len(x), C.byref(lpd), _dp(g), C.byref(lpf))
+        rc = self._lib.qso_logp_grad(self.h, _dp(x), len(x), C.byref(lpd), _dp(g), C.byref(lpf))
         if rc:
             raise ValueError("dimension mismatch")
         return lpd.value, g, lpf.value
@@ -203,7 +214,7 @@ def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, r
             lf = np.zeros((nchains, iters, specs[0].numSteps, n))
         out.update(state=st, accept=ac, dH=dh, step=ss, kidx=ki, leapfrog=lf, init=init)
     stats = Stats()
-    rc = lib().qso_run(program.h, arr, len(specs), seed, chain_begin, nchains, nsamps, burnin, lag,
+    rc = program._lib.qso_run(program.h, arr, len(specs), seed, chain_begin, nchains, nsamps, burnin, lag,
                        _dp(samples), _dp(logprobs), _dp(st), _ip(ac), _dp(dh), _dp(ss), _ip(ki), _dp(lf), _dp(init),
                        C.byref(stats))
     if rc:
