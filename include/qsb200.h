@@ -85,7 +85,8 @@ typedef struct {
 enum {
   QSB_FLAG_MOMENTS = 1u,     /* accumulate per-chain running moments of the kept samples (for split-Rhat) */
   QSB_FLAG_RECORD = 2u,      /* keep a per-iteration record (state, accept, dH, step, kernel index) -- parity tests */
-  QSB_FLAG_RECORD_LEAP = 4u  /* additionally record the position after every leapfrog step (single HMC kernel) */
+  QSB_FLAG_RECORD_LEAP = 4u, /* additionally record the position after every leapfrog step (single HMC kernel) */
+  QSB_FLAG_TIME_KERNEL = 8u  /* bracket every launch of the dominant kernel with CUDA events (roofline measurement) */
 };
 
 typedef struct {
@@ -115,6 +116,9 @@ const char* qsb_last_error(void);
 /* ---- models */
 int qsb_model_create(const qsb_model_desc* desc, int32_t device, qsb_model** out);
 int qsb_model_destroy(qsb_model* m);
+/* Refresh the observation data of an existing model in place from HOST buffers (same shapes as at creation;
+ * LOGISTIC: X, ybin; EIGHT_SCHOOLS: y, sigma).  Asynchronous on `stream` when the buffers are pinned. */
+int qsb_model_update_data(qsb_model* m, const qsb_model_desc* desc, void* stream);
 int qsb_model_dim(const qsb_model* m);      /* n: real components          (trace.t:830-905) */
 int qsb_model_retdim(const qsb_model* m);   /* length of the return value  (infer.t:47-49)   */
 
@@ -150,12 +154,18 @@ int qsb_sampler_fetch_values(qsb_sampler* s, uint32_t chain_begin, uint32_t chai
                              uint64_t sample_begin, uint64_t sample_end, double* dst);
 
 int qsb_sampler_stats(qsb_sampler* s, qsb_stats* out);
+/* QSB_FLAG_TIME_KERNEL: summed device time and launch count of the dominant kernel (the log-density/gradient
+ * contraction for LOGISTIC, the fused transition kernel otherwise) since the last call; resets the counters. */
+int qsb_sampler_kernel_time(qsb_sampler* s, double* seconds, uint64_t* launches);
 
 /* Cross-chain sufficient statistics of the kept samples, for split-Rhat / pooled moments / ESS.
- * dst receives, per return-value dimension j (retdim of them), 8 doubles:
- *   [0] number of half-chains m   [1] draws per half-chain n
- *   [2] sum over half-chains of the half-chain mean      [3] sum of (half-chain mean)^2
- *   [4] sum of the half-chain sample variances (n-1)     [5] sum of all draws   [6] sum of all draws^2  [7] reserved
+ * dst receives, per return-value dimension j (retdim of them), 12 doubles:
+ *   [0] number of half-chains   [1] draws per half-chain
+ *   [2] sum over half-chains of the half-chain mean   [3] sum of (half-chain mean)^2
+ *   [4] sum of the half-chain sample variances (n-1 denominators)
+ *   [5] sum of all draws   [6] sum of all draws^2
+ *   [7] number of chains M   [8] draws per chain N
+ *   [9] sum over chains of the chain mean   [10] sum of (chain mean)^2   [11] sum of the chain sample variances (N-1)
  * followed (if maxlag > 0) by retdim*(maxlag+1) doubles: sum over chains of the lag-t autocovariance
  * numerators sum_i (x_i - m_c)(x_{i+t} - m_c), t = 0..maxlag, m_c = the chain's mean.
  * These are plain sums, so shards on different GPUs combine with one all-reduce(sum).

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libqsb200.so")
 FAM_INDEP, FAM_GAUSS_PREC, FAM_LOGISTIC, FAM_EIGHT_SCHOOLS, FAM_FUNNEL = 1, 2, 3, 4, 5
 ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM = 0, 1, 2, 3
 KERNEL_HMC, KERNEL_DRIFT, KERNEL_HARM = 1, 2, 3
-FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP = 1, 2, 4
+FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL = 1, 2, 4, 8
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -49,6 +49,7 @@ PROTOTYPES = {
     "qsb_last_error": (C.c_char_p, []),
     "qsb_model_create": (C.c_int, [C.POINTER(ModelDesc), C.c_int32, C.POINTER(C.c_void_p)]),
     "qsb_model_destroy": (C.c_int, [C.c_void_p]),
+    "qsb_model_update_data": (C.c_int, [C.c_void_p, C.POINTER(ModelDesc), C.c_void_p]),
     "qsb_model_dim": (C.c_int, [C.c_void_p]),
     "qsb_model_retdim": (C.c_int, [C.c_void_p]),
     "qsb_sampler_create": (C.c_int, [C.c_void_p, C.POINTER(KernelSpec), C.c_int32, C.POINTER(RunConfig), C.POINTER(C.c_void_p)]),
@@ -63,6 +64,7 @@ PROTOTYPES = {
     "qsb_sampler_fetch_samples": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
     "qsb_sampler_fetch_values": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, dp]),
     "qsb_sampler_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "qsb_sampler_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "qsb_sampler_diagnostics": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "qsb_sampler_fetch_record": (C.c_int, [C.c_void_p, dp, ip, dp, dp, ip, dp]),
     "qsb_logp_grad": (C.c_int, [C.c_void_p, dp, C.c_int32, dp, dp, dp]),

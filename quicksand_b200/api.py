@@ -163,10 +163,16 @@ class Sampler:
                     sub_accepted=list(st.sub_accepted)[:n], grad_evals=st.grad_evals, leapfrog_steps=st.leapfrog_steps,
                     iterations=st.iterations, kernel_launches=st.kernel_launches, seconds=st.seconds)
 
+    def kernel_time(self):
+        """(seconds, launches) of the dominant kernel since the last call (needs FLAG_TIME_KERNEL)."""
+        sec, n = C.c_double(), C.c_uint64()
+        L.check(L.lib().qsb_sampler_kernel_time(self.h, C.byref(sec), C.byref(n)))
+        return sec.value, n.value
+
     def diagnostics_raw(self, maxlag=0, out_ptr=None):
         """Sufficient statistics (see qsb_sampler_diagnostics).  ``out_ptr``: device pointer (e.g. a torch
         tensor's data_ptr()) to write into for a following NCCL all-reduce; otherwise a numpy array."""
-        n = self.retdim * 8 + (self.retdim * (maxlag + 1) if maxlag > 0 else 0)
+        n = self.retdim * 12 + (self.retdim * (maxlag + 1) if maxlag > 0 else 0)
         if out_ptr is not None:
             L.check(L.lib().qsb_sampler_diagnostics(self.h, maxlag, C.c_void_p(out_ptr), 1))
             return None

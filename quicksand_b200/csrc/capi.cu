@@ -48,6 +48,7 @@ struct qsb_model {
   ModelDev dev;
   DevArena arena;
   GlmModel glm;               // LOGISTIC
+  double* sigma_dev = nullptr; // EIGHT_SCHOOLS
 };
 
 struct qsb_sampler {
@@ -65,6 +66,8 @@ struct qsb_sampler {
   double seconds = 0.0;
   bool inited = false;
   uint64_t rec_iters = 0;
+  double t_accum = 0.0; uint64_t t_launches = 0;   // QSB_FLAG_TIME_KERNEL
+  bool ev_pending = false;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -100,7 +103,7 @@ __global__ void diagnostics_kernel(const double* samples, int G, uint32_t SC, in
   if (G == 1) { c = (uint32_t)(t % SC); j = (int)(t / SC); } else { j = (int)(t % retdim); c = (uint32_t)(t / retdim); }
   auto at = [&](uint64_t k) { return samples[G == 1 ? ((size_t)k * retdim + j) * SC + c : ((size_t)k * SC + c) * retdim + j]; };
   const uint64_t h = n / 2;
-  double* o = out + (size_t)j * 8;
+  double* o = out + (size_t)j * 12;
   double sum_all = 0.0, sq_all = 0.0;
   for (int half = 0; half < 2; ++half) {
     if (h < 2) break;
@@ -113,9 +116,14 @@ __global__ void diagnostics_kernel(const double* samples, int G, uint32_t SC, in
   }
   for (uint64_t k = 0; k < n; ++k) { double v = at(k); sum_all += v; sq_all += v * v; }
   atomicAdd(&o[5], sum_all); atomicAdd(&o[6], sq_all);
+  {
+    double mean = sum_all / (double)n, m2 = 0.0;
+    for (uint64_t k = 0; k < n; ++k) { double dlt = at(k) - mean; m2 += dlt * dlt; }
+    atomicAdd(&o[9], mean); atomicAdd(&o[10], mean * mean); atomicAdd(&o[11], m2 / (double)(n - 1));
+  }
   if (maxlag > 0 && n > 1) {
     double mean = sum_all / (double)n;
-    double* ac = out + (size_t)retdim * 8 + (size_t)j * (maxlag + 1);
+    double* ac = out + (size_t)retdim * 12 + (size_t)j * (maxlag + 1);
     for (int lagv = 0; lagv <= maxlag && (uint64_t)lagv < n; ++lagv) {
       double s = 0.0;
       for (uint64_t k = 0; k + lagv < n; ++k) s += (at(k) - mean) * (at(k + lagv) - mean);
@@ -123,9 +131,9 @@ __global__ void diagnostics_kernel(const double* samples, int G, uint32_t SC, in
     }
   }
 }
-__global__ void diagnostics_header_kernel(double* out, int retdim, double m, double n) {
+__global__ void diagnostics_header_kernel(double* out, int retdim, double mh, double nh, double M, double N) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < retdim) { out[(size_t)j * 8 + 0] = m; out[(size_t)j * 8 + 1] = n; }
+  if (j < retdim) { double* o = out + (size_t)j * 12; o[0] = mh; o[1] = nh; o[7] = M; o[8] = N; }
 }
 
 __global__ void uniforms_kernel(RngKey key, uint32_t chain, uint32_t iter, uint32_t slot, int n, double* out) {
@@ -231,7 +239,7 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
       cudaMemcpy(sg, d->sigma, sizeof(double) * d->nobs, cudaMemcpyHostToDevice);
       precompute_obs_kernel<<<(d->nobs + 127) / 128, 128>>>(sg, cy, s2, d->nobs);
       if (cudaDeviceSynchronize() != cudaSuccess) return bail(6, "precompute_obs_kernel failed");
-      m->dev.y = y; m->dev.cy = cy; m->dev.s2 = s2;
+      m->dev.y = y; m->dev.cy = cy; m->dev.s2 = s2; m->sigma_dev = sg;
       break;
     }
     case QSB_FAM_FUNNEL: break;
@@ -239,6 +247,28 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
   }
   *out = m;
   return 0;
+}
+
+int qsb_model_update_data(qsb_model* m, const qsb_model_desc* d, void* stream) {
+  if (!m || !d) return fail(1, "null argument");
+  if (d->family != m->desc.family || d->dim != m->desc.dim || d->nobs != m->desc.nobs) return fail(2, "qsb_model_update_data: shape mismatch");
+  CU(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->family == QSB_FAM_LOGISTIC) {
+    if (!d->X || !d->ybin) return fail(3, "LOGISTIC: X, ybin required");
+    std::string why;
+    if (glm_model_update(&m->glm, d->X, d->ybin, stream, why)) return fail(5, "LOGISTIC: " + why);
+    return 0;
+  }
+  if (d->family == QSB_FAM_EIGHT_SCHOOLS) {
+    if (!d->y || !d->sigma) return fail(3, "EIGHT_SCHOOLS: y, sigma required");
+    CU(cudaMemcpyAsync((void*)m->dev.y, d->y, sizeof(double) * d->nobs, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync((void*)m->sigma_dev, d->sigma, sizeof(double) * d->nobs, cudaMemcpyHostToDevice, st));
+    precompute_obs_kernel<<<(d->nobs + 127) / 128, 128, 0, st>>>(m->sigma_dev, (double*)m->dev.cy, (double*)m->dev.s2, d->nobs);
+    CU(cudaGetLastError());
+    return 0;
+  }
+  return fail(2, "qsb_model_update_data: family has no observation data");
 }
 
 int qsb_model_destroy(qsb_model* m) {
@@ -474,6 +504,12 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
   }
   EngineParams& P = s->P;
   if (s->rec_iters && s->iter + iters > s->rec_iters) return fail(2, "record buffer holds numiters iterations only");
+  if ((s->cfg.flags & QSB_FLAG_TIME_KERNEL) && s->ev_pending) {   // fold the previous launch's time before reusing the events
+    float ms = 0.f;
+    CU(cudaEventSynchronize(s->ev1));
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) { s->t_accum += ms * 1e-3; ++s->t_launches; }
+    s->ev_pending = false;
+  }
   P.it_begin = s->iter; P.n_iters = iters;
   CU(cudaEventRecord(s->ev0, s->stream));
   {
@@ -490,6 +526,7 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
   ++s->launches;
   CU(cudaEventRecord(s->ev1, s->stream));
   CU(cudaGetLastError());
+  s->ev_pending = true;
   s->iter += iters;
   return 0;
 }
@@ -587,6 +624,21 @@ int qsb_sampler_stats(qsb_sampler* s, qsb_stats* out) {
   return 0;
 }
 
+int qsb_sampler_kernel_time(qsb_sampler* s, double* seconds, uint64_t* launches) {
+  if (!s || !seconds || !launches) return fail(1, "null argument");
+  CU(cudaSetDevice(s->m->device));
+  if (s->glm) { std::string why; if (glm_sampler_kernel_time(s->glm, seconds, launches, why)) return fail(5, why); return 0; }
+  CU(cudaStreamSynchronize(s->stream));
+  if (s->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) { s->t_accum += ms * 1e-3; ++s->t_launches; }
+    s->ev_pending = false;
+  }
+  *seconds = s->t_accum; *launches = s->t_launches;
+  s->t_accum = 0.0; s->t_launches = 0;
+  return 0;
+}
+
 int qsb_sampler_diagnostics(qsb_sampler* s, int32_t maxlag, double* dst, int32_t dst_is_device) {
   if (!s || !dst) return fail(1, "null argument");
   if (maxlag < 0) return fail(2, "maxlag must be >= 0");
@@ -595,14 +647,14 @@ int qsb_sampler_diagnostics(qsb_sampler* s, int32_t maxlag, double* dst, int32_t
   if (s->glm) glm_sampler_sample_view(s->glm, &samples, &samp_lp, &G, &SC, &retdim);
   else { samples = s->P.samples; samp_lp = s->P.samp_lp; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }
   const uint64_t n = qsb_sampler_num_samples(s);
-  const size_t len = (size_t)retdim * 8 + (maxlag > 0 ? (size_t)retdim * (maxlag + 1) : 0);
+  const size_t len = (size_t)retdim * 12 + (maxlag > 0 ? (size_t)retdim * (maxlag + 1) : 0);
   double* out = dst;
   if (!dst_is_device) CU(cudaMalloc((void**)&out, len * 8));
   CU(cudaMemsetAsync(out, 0, len * 8, s->stream));
   if (n >= 2 && samples) {
     size_t total = (size_t)SC * retdim;
     diagnostics_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s->stream>>>(samples, G, SC, retdim, n, maxlag, out);
-    diagnostics_header_kernel<<<(retdim + 127) / 128, 128, 0, s->stream>>>(out, retdim, (n / 2 >= 2) ? 2.0 * SC : 0.0, (double)(n / 2));
+    diagnostics_header_kernel<<<(retdim + 127) / 128, 128, 0, s->stream>>>(out, retdim, (n / 2 >= 2) ? 2.0 * SC : 0.0, (double)(n / 2), (double)SC, (double)n);
     s->launches += 2;
   }
   cudaError_t e = cudaGetLastError();

@@ -393,6 +393,10 @@ struct GlmSampler {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int nj_inst = 0;
   size_t smem = 0;
+  // QSB_FLAG_TIME_KERNEL: event pairs around the gradient-contraction launches
+  std::vector<cudaEvent_t> tev;
+  size_t tev_used = 0;
+  double t_accum = 0.0; uint64_t t_launches = 0;
 };
 
 static int pick_ksplit(int ntiles, int nblocks, int nsm) {
@@ -445,6 +449,19 @@ int glm_model_create(GlmModel* m, const double* X, const uint8_t* y, int N, int 
   if (cudaMalloc((void**)&m->Xp, Xp.size() * 8) != cudaSuccess || cudaMalloc((void**)&m->yv, yv.size() * 8) != cudaSuccess) { why = "cudaMalloc failed"; return 2; }
   cudaMemcpy(m->Xp, Xp.data(), Xp.size() * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(m->yv, yv.data(), yv.size() * 8, cudaMemcpyHostToDevice);
+  return 0;
+}
+int glm_model_update(GlmModel* m, const double* X, const uint8_t* y, void* stream, std::string& why) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (m->S == m->d) e = cudaMemcpyAsync(m->Xp, X, (size_t)m->N * m->d * 8, cudaMemcpyHostToDevice, st);
+  else e = cudaMemcpy2DAsync(m->Xp, (size_t)m->S * 8, X, (size_t)m->d * 8, (size_t)m->d * 8, m->N, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { why = cudaGetErrorString(e); return 100 + (int)e; }
+  if (m->ystage.size() != (size_t)m->N) m->ystage.resize(m->N);
+  for (int i = 0; i < m->N; ++i) m->ystage[i] = y[i] ? 1.0 : 0.0;
+  e = cudaMemcpyAsync(m->yv, m->ystage.data(), (size_t)m->N * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // ystage is reused by the next call
+  if (e != cudaSuccess) { why = cudaGetErrorString(e); return 100 + (int)e; }
   return 0;
 }
 void glm_model_destroy(GlmModel* m) {
@@ -503,12 +520,23 @@ void glm_sampler_destroy(GlmSampler* s) {
   cudaStreamSynchronize(s->stream);
   glm_free_run_buffers(s);
   for (void* p : s->bufs) cudaFree(p);
+  for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
 }
 
 #define GCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { why = std::string(#call) + ": " + cudaGetErrorString(e_); return 100 + (int)e_; } } while (0)
+
+static void glm_collect_times(GlmSampler* s) {
+  if (!s->tev_used) return;
+  cudaStreamSynchronize(s->stream);
+  for (size_t i = 0; i + 1 < s->tev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->tev[i], s->tev[i + 1]) == cudaSuccess) { s->t_accum += ms * 1e-3; ++s->t_launches; }
+  }
+  s->tev_used = 0;
+}
 
 template <int MODE> static cudaError_t launch_vec(GlmSampler* s, const VecParams& V) {
   glm_vec_kernel<MODE><<<(unsigned)(((size_t)V.C * 32 + 255) / 256), 256, 0, s->stream>>>(V);
@@ -519,7 +547,16 @@ static cudaError_t run_grad(GlmSampler* s, const double* theta, int want_lp) {
   GradParams G = s->Gp;
   G.theta = theta; G.want_lp = want_lp;
   ++s->launches; ++s->grad_evals;
-  return launch_grad(s->nj_inst, G, s->smem, s->stream);
+  if (!(s->flags & QSB_FLAG_TIME_KERNEL)) return launch_grad(s->nj_inst, G, s->smem, s->stream);
+  if (s->tev_used + 2 > s->tev.size()) {
+    if (s->tev.size() >= 8192) { glm_collect_times(s); }
+    else for (int i = 0; i < 512; ++i) { cudaEvent_t e; cudaEventCreate(&e); s->tev.push_back(e); }
+  }
+  cudaEventRecord(s->tev[s->tev_used], s->stream);
+  cudaError_t r = launch_grad(s->nj_inst, G, s->smem, s->stream);
+  cudaEventRecord(s->tev[s->tev_used + 1], s->stream);
+  s->tev_used += 2;
+  return r;
 }
 
 static int reset_chain_state(GlmSampler* s, std::string& why) {
@@ -678,6 +715,13 @@ int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, doub
   if (dh) GCU(cudaMemcpy(dh, V.rec_dh, 8 * C * T, cudaMemcpyDeviceToHost));
   if (step) GCU(cudaMemcpy(step, V.rec_step, 8 * C * T, cudaMemcpyDeviceToHost));
   if (leap) { if (!V.rec_leap) { why = "leapfrog positions need QSB_FLAG_RECORD_LEAP"; return 2; } GCU(cudaMemcpy(leap, V.rec_leap, 8 * C * T * s->L * d, cudaMemcpyDeviceToHost)); }
+  return 0;
+}
+
+int glm_sampler_kernel_time(GlmSampler* s, double* seconds, uint64_t* launches, std::string& why) {
+  glm_collect_times(s);
+  *seconds = s->t_accum; *launches = s->t_launches;
+  s->t_accum = 0.0; s->t_launches = 0;
   return 0;
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <vector>
 
 namespace qsb {
 
@@ -14,12 +15,14 @@ struct GlmModel {
   double prior_sigma = 0;
   double* Xp = nullptr;    // HBM [Npad][S], zero padded
   double* yv = nullptr;    // HBM [Npad]: 0.0 / 1.0, 2.0 marks a padding row
+  std::vector<double> ystage;   // host staging of y as doubles (qsb_model_update_data)
 };
 
 struct GlmSampler;
 
 int glm_model_create(GlmModel* m, const double* X, const uint8_t* y, int N, int d, double prior_sigma, std::string& why);
 void glm_model_destroy(GlmModel* m);
+int glm_model_update(GlmModel* m, const double* X, const uint8_t* y, void* stream, std::string& why);
 
 GlmSampler* glm_sampler_create(GlmModel* m, double stepSize, uint32_t numSteps, bool adapt, uint64_t seed, uint32_t chain_begin,
                                uint32_t numchains, uint32_t sample_chains, uint32_t flags, void* stream, std::string& why);
@@ -33,6 +36,7 @@ void glm_sampler_sample_view(GlmSampler* s, const double** samples, const double
 int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* grad_evals, uint64_t* leapfrogs, uint64_t* launches,
                       double* seconds, std::string& why);
 int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, double* dh, double* step, double* leap, std::string& why);
+int glm_sampler_kernel_time(GlmSampler* s, double* seconds, uint64_t* launches, std::string& why);
 int glm_logp_grad(GlmModel* m, const double* x, int n, double* lp_dual, double* grad, double* lp_float, std::string& why);
 
 }  // namespace qsb

@@ -1,0 +1,82 @@
+"""Cross-chain convergence diagnostics from the plain-sum sufficient statistics of
+``qsb_sampler_diagnostics`` (include/qsb200.h): pooled moments, split-R-hat, and ESS with Geyer's
+initial-monotone-sequence truncation on the chain-averaged autocovariance (Stan-style, not
+rank-normalised).  The reference has none of these (its only related code is Autocorrelation,
+qs/infer.t:213-264); they are the new statistics north_star asks for.  Because the inputs are sums
+over chains, shards on different GPUs combine with ONE all-reduce(sum) -- the only collective of
+the whole path."""
+import numpy as np
+
+HDR = 12
+
+
+def unpack(raw, retdim, maxlag, nshards=1):
+    raw = np.asarray(raw, dtype=np.float64)
+    hdr = raw[:retdim * HDR].reshape(retdim, HDR).copy()
+    hdr[:, 1] /= nshards      # draws per half-chain and per chain are constants, not sums
+    hdr[:, 8] /= nshards
+    acov = raw[retdim * HDR:].reshape(retdim, maxlag + 1) if maxlag > 0 else None
+    return hdr, acov
+
+
+def summarize(raw, retdim, maxlag=0, nshards=1):
+    """dict(mean, var, rhat, ess, tau) per return-value dimension; `raw` may be the all-reduced sum of `nshards` shards."""
+    hdr, acov = unpack(raw, retdim, maxlag, nshards)
+    mh, nh = hdr[:, 0], hdr[:, 1]
+    M, N = hdr[:, 7], hdr[:, 8]
+    tot = M * N
+    mean = hdr[:, 5] / tot
+    var = hdr[:, 6] / tot - mean * mean
+    out = dict(mean=mean, var=var, chains=M, draws=N)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        # split-R-hat over the 2M half-chains
+        Bn = (hdr[:, 3] - hdr[:, 2] ** 2 / mh) / (mh - 1.0)       # variance of the half-chain means = B/n
+        W = hdr[:, 4] / mh
+        varplus = (nh - 1.0) / nh * W + Bn
+        out["rhat"] = np.sqrt(varplus / W)
+        if acov is not None:
+            Bn_f = (hdr[:, 10] - hdr[:, 9] ** 2 / M) / np.maximum(M - 1.0, 1.0)
+            W_f = hdr[:, 11] / M
+            vp = (N - 1.0) / N * W_f + Bn_f
+            acov_mean = acov / (M[:, None] * N[:, None])          # chain-averaged, biased (1/N) autocovariance
+            rho = 1.0 - (W_f[:, None] - acov_mean) / vp[:, None]
+            rho[:, 0] = 1.0
+            tau = np.empty(retdim)
+            for j in range(retdim):
+                tau[j] = _geyer_tau(rho[j])
+            out["tau"] = tau
+            out["ess"] = tot / tau
+    return out
+
+
+def _geyer_tau(rho):
+    """tau = -1 + 2 * sum of the initial positive, monotone sequence of pair sums P_k = rho_2k + rho_2k+1."""
+    T = len(rho)
+    s = 0.0
+    prev = np.inf
+    k = 0
+    while 2 * k + 1 < T:
+        P = rho[2 * k] + rho[2 * k + 1]
+        if not (P > 0.0):
+            break
+        P = min(P, prev)
+        s += P
+        prev = P
+        k += 1
+    tau = -1.0 + 2.0 * s
+    return tau if tau > 1e-3 else 1e-3
+
+
+def ess_numpy(draws, maxlag):
+    """Reference implementation on raw draws [chains][N] for one dimension (used by the tests)."""
+    M, N = draws.shape
+    means = draws.mean(axis=1)
+    W = draws.var(axis=1, ddof=1).mean()
+    Bn = means.var(ddof=1) if M > 1 else 0.0
+    vp = (N - 1.0) / N * W + Bn
+    d = draws - means[:, None]
+    rho = np.ones(maxlag + 1)
+    for t in range(1, maxlag + 1):
+        ac = (d[:, :N - t] * d[:, t:]).sum(axis=1).mean() / N
+        rho[t] = 1.0 - (W - ac) / vp
+    return M * N / _geyer_tau(rho)

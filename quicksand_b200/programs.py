@@ -52,6 +52,13 @@ class Program:
             self._models[device] = h
         return self._models[device]
 
+    def update_data(self, device=-1, stream=None, **arrays):
+        """Refresh the observation data of the device-resident model from host arrays (same shapes)."""
+        for k, v in arrays.items():
+            assert k in self.arrays and v.shape == self.arrays[k].shape and v.dtype == self.arrays[k].dtype
+            self.arrays[k] = v
+        L.check(L.lib().qsb_model_update_data(self.model(device), C.byref(self.desc()), C.c_void_p(stream) if stream else None))
+
     def upload(self, device=-1):
         """Force a fresh host->device upload of the model data (used by the end-to-end benchmark)."""
         self.release(device)
