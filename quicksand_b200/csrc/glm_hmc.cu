@@ -37,9 +37,9 @@ namespace qsb {
 static constexpr int MB = 32;          // observation rows per pipeline stage
 static constexpr int NT = MB / 8;      // 8-row n-tiles per stage
 static constexpr int STAGES = 4;
-static constexpr int CW = 8;           // consumer warps per CTA
+static constexpr int CW = 12;          // warps per CTA (3 per SM sub-partition: 16384 regs / 3 / 32 = 170 -> 168 regs/thread)
 static constexpr int CB = CW * 8;      // chains per CTA
-static constexpr int GRAD_THREADS = (CW + 1) * 32;
+static constexpr int GRAD_THREADS = CW * 32;
 
 struct GradParams {
   const double* Xp; const double* yv;
@@ -62,6 +62,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive; true iff this arrival was the last one pending, i.e. it completed the phase
+__device__ __forceinline__ bool mbar_arrive_last(uint64_t* bar) {
+  uint32_t pending;
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%1];\n mbarrier.pending_count.b64 %0, st;\n}"
+               : "=r"(pending) : "r"(smem_u32(bar)) : "memory");
+  return pending == 1u;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -74,6 +81,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  // volatile: keeps the issue order written below (independent accumulators back to back), nothing else
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
@@ -81,7 +89,45 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // smem: per stage [MB*S + 8 doubles X (8 = zeroed over-read pad)] [MB doubles y]; then 2*STAGES mbarriers
 __host__ __device__ inline size_t stage_doubles(int S) { return (size_t)MB * S + 8 + MB; }
 
-template <int NJ>
+// exp(-z) and 1/(1+exp(-z)) without branches: the library exp()/division carry slow-path branches that cost
+// issue slots and reconvergence stalls inside the MMA pipeline (ncu: profiles/r01_c3_grad_v1).  Accurate to
+// ~2 ulp (range reduction with a split ln2, degree-13 polynomial, exponent scaling, reciprocal by MUFU seed
+// + two Newton steps); saturates exactly like the naive form for |z| > 708.
+__device__ __forceinline__ double sigmoid_fast(double z) {
+  double t = fmin(fmax(-z, -708.0), 708.0);
+  const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest-integer by addition
+  double kd = fma(t, 1.4426950408889634, SHIFT);
+  int k = __double2loint(kd);
+  kd -= SHIFT;
+  double r = fma(kd, -6.93147180369123816490e-01, t);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821613e-10;           // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);         // 1/12!
+  q = fma(q, r, 2.505210838544172e-08);        // 1/11!
+  q = fma(q, r, 2.755731922398589e-07);        // 1/10!
+  q = fma(q, r, 2.7557319223985893e-06);       // 1/9!
+  q = fma(q, r, 2.48015873015873e-05);         // 1/8!
+  q = fma(q, r, 1.984126984126984e-04);        // 1/7!
+  q = fma(q, r, 1.388888888888889e-03);        // 1/6!
+  q = fma(q, r, 8.333333333333333e-03);        // 1/5!
+  q = fma(q, r, 4.1666666666666664e-02);       // 1/4!
+  q = fma(q, r, 1.6666666666666666e-01);       // 1/3!
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  double e = __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));   // q * 2^k, result stays normal
+  double d = 1.0 + e;
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double err = fma(-d, y, 1.0);
+  y = fma(y, err, y);
+  err = fma(-d, y, 1.0);
+  y = fma(y, err, y);
+  return y;
+}
+
+// FULL: every one of the NJ dimension tiles is live (nj == NJ), so the tile loops carry no predicates.
+template <int NJ, bool FULL>
 __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_constant__ GradParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
@@ -99,27 +145,26 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   if (threadIdx.x < STAGES * 8) sm[SD * (threadIdx.x >> 3) + (size_t)MB * P.S + (threadIdx.x & 7)] = 0.0;   // over-read pads
   __syncthreads();
 
-  if (warp == CW) {
-    // ---- producer: TMA bulk copies of whole row blocks (contiguous in HBM: Xp is stored with stride S)
-    if (lane == 0) {
-      const uint32_t bytesX = (uint32_t)(MB * P.S * sizeof(double)), bytesY = (uint32_t)(MB * sizeof(double));
-      for (int b = b0; b < b1; ++b) {
-        const int it = b - b0, st = it % STAGES, round = it / STAGES;
-        mbar_wait(&empty[st], (uint32_t)((round & 1) ^ 1));
-        mbar_expect_tx(&full[st], bytesX + bytesY);
-        double* dst = sm + SD * st;
-        bulk_g2s(dst, P.Xp + (size_t)b * MB * P.S, bytesX, &full[st]);
-        bulk_g2s(dst + (size_t)MB * P.S + 8, P.yv + (size_t)b * MB, bytesY, &full[st]);
-      }
-    }
-    return;
-  }
+  // ---- no dedicated producer warp (it would take a third of one sub-partition's register file): thread 0 starts
+  // the ring; afterwards the warp whose release of a stage is the LAST one pending re-arms it with the next row
+  // block (TMA bulk copies of whole row blocks: contiguous in HBM because Xp is stored with stride S)
+  const uint32_t bytesX = (uint32_t)(MB * P.S * sizeof(double)), bytesY = (uint32_t)(MB * sizeof(double));
+  auto issue_load = [&](int b) {
+    const int st = (b - b0) % STAGES;
+    mbar_expect_tx(&full[st], bytesX + bytesY);
+    double* dst = sm + SD * st;
+    bulk_g2s(dst, P.Xp + (size_t)b * MB * P.S, bytesX, &full[st]);
+    bulk_g2s(dst + (size_t)MB * P.S + 8, P.yv + (size_t)b * MB, bytesY, &full[st]);
+  };
+  if (threadIdx.x == 0)
+    for (int b = b0; b < b1 && b < b0 + STAGES; ++b) issue_load(b);
 
   // ---- consumers: warp w owns chains tile*CB + 8w .. +7; thread (gid, tig) owns dims 8J+2tig+{0,1} of chain gid
   const int gid = lane >> 2, tig = lane & 3;
   const uint32_t chain = (uint32_t)tile * CB + warp * 8 + gid;
   const bool valid = chain < P.C;
-  const int S = P.S, nj = P.nj;
+  const int S = P.S;
+  const int nj = FULL ? NJ : P.nj;
   // row permutation inside an 8-row tile (see header): rho = [0,2,1,3,6,4,7,5]
   const uint32_t RHO = 0x57463120u;
   const int rho_g = (RHO >> (4 * gid)) & 7, rho_t0 = (RHO >> (8 * tig)) & 7, rho_t1 = (RHO >> (8 * tig + 4)) & 7;
@@ -128,7 +173,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
 #pragma unroll
   for (int J = 0; J < NJ; ++J) {
     th[J][0] = th[J][1] = 0.0; G[J][0] = G[J][1] = 0.0;
-    if (J < nj && valid) {
+    if ((FULL || J < nj) && valid) {
       double2 v = *reinterpret_cast<const double2*>(P.theta + (size_t)chain * P.Dp + 8 * J + 2 * tig);
       th[J][0] = v.x; th[J][1] = v.y;
     }
@@ -136,37 +181,60 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   double lpacc = 0.0;
   const int offA = rho_g * S + 2 * tig;                 // phase 1 B fragment: X[rho(gid)][8J + 2tig .. +1]
   const int offB0 = rho_t0 * S + gid, offB1 = rho_t1 * S + gid;   // phase 2 B fragment: X[rho(2tig+e)][8J + gid]
+  const bool want_lp = P.want_lp != 0;
 
-  for (int b = b0; b < b1; ++b) {
-    const int it = b - b0, st = it % STAGES, round = it / STAGES;
-    mbar_wait(&full[st], (uint32_t)(round & 1));
-    const double* Xs = sm + SD * st;
-    const double* ys = Xs + (size_t)MB * S + 8;
-    // phase 1: Z^T tile = Theta^T X^T
-    double acc[NT][2];
+  // Software pipeline over row blocks: while the sigmoid epilogue of block b runs on the FP64 ALU path, the first
+  // contraction (Z^T = Theta^T X^T) of block b+1 is already feeding the tensor pipe; then the second contraction
+  // (G^T += R^T X) of block b.  acc holds Z of the block whose epilogue is due, nxt the one being accumulated.
+  double acc[NT][2], nxt[NT][2];
+  auto phase1_tile = [&](const double* Xs, int J, double (&a)[NT][2]) {
+    double2 xv[NT];
+#pragma unroll
+    for (int T = 0; T < NT; ++T) xv[T] = *reinterpret_cast<const double2*>(Xs + T * 8 * S + offA + 8 * J);
+#pragma unroll
+    for (int T = 0; T < NT; ++T) dmma(a[T], th[J][0], xv[T].x);   // NT independent accumulators back to back,
+#pragma unroll
+    for (int T = 0; T < NT; ++T) dmma(a[T], th[J][1], xv[T].y);   // then the dependent second k-step of each
+  };
+  auto epilogue_elem = [&](const double* ys, int T, int e) {
+    const double y = ys[T * 8 + (e ? rho_t1 : rho_t0)];
+    if (want_lp) {
+      const double pr = 1.0 / (1.0 + exp(-acc[T][e]));
+      if (y <= 1.0) lpacc += log(y != 0.0 ? pr : 1.0 - pr);   // distrib.t:17-25 on the naive sigmoid
+      acc[T][e] = y - pr;
+    } else {
+      acc[T][e] = y - sigmoid_fast(acc[T][e]);
+    }
+  };
+
+  if (b0 < b1) {
+    mbar_wait(&full[0], 0u);
 #pragma unroll
     for (int T = 0; T < NT; ++T) acc[T][0] = acc[T][1] = 0.0;
 #pragma unroll
-    for (int J = 0; J < NJ; ++J) {
-      if (J < nj) {
+    for (int J = 0; J < NJ; ++J) if (FULL || J < nj) phase1_tile(sm, J, acc);
+  }
+  for (int b = b0; b < b1; ++b) {
+    const int it = b - b0, st = it % STAGES;
+    const double* Xs = sm + SD * st;
+    const double* ys = Xs + (size_t)MB * S + 8;
+    const bool has_next = b + 1 < b1;
+    if (has_next) {
+      const int it2 = it + 1, st2 = it2 % STAGES;
+      mbar_wait(&full[st2], (uint32_t)((it2 / STAGES) & 1));
+      const double* Xn = sm + SD * st2;
 #pragma unroll
-        for (int T = 0; T < NT; ++T) {
-          const double2 xv = *reinterpret_cast<const double2*>(Xs + T * 8 * S + offA + 8 * J);
-          dmma(acc[T], th[J][0], xv.x);
-          dmma(acc[T], th[J][1], xv.y);
-        }
+      for (int T = 0; T < NT; ++T) nxt[T][0] = nxt[T][1] = 0.0;
+#pragma unroll
+      for (int J = 0; J < NJ; ++J) {
+        if (FULL || J < nj) phase1_tile(Xn, J, nxt);
+        if (J < 2 * NT) epilogue_elem(ys, J >> 1, J & 1);      // NJ >= 2*NT interleaves all; otherwise the rest follows
       }
-    }
-    // sigmoid epilogue in registers: r = y - p  (d/dz of log(y ? p : 1-p) with p = 1/(1+exp(-z)))
 #pragma unroll
-    for (int T = 0; T < NT; ++T) {
+      for (int q = NJ; q < 2 * NT; ++q) epilogue_elem(ys, q >> 1, q & 1);
+    } else {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const double y = ys[T * 8 + (e ? rho_t1 : rho_t0)];
-        const double pr = 1.0 / (1.0 + exp(-acc[T][e]));
-        if (P.want_lp && y <= 1.0) lpacc += log(y != 0.0 ? pr : 1.0 - pr);   // distrib.t:17-25 on the naive sigmoid
-        acc[T][e] = y - pr;
-      }
+      for (int q = 0; q < 2 * NT; ++q) epilogue_elem(ys, q >> 1, q & 1);
     }
     // phase 2: G^T += R^T X
 #pragma unroll
@@ -176,20 +244,27 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
         const double* xb = Xs + T * 8 * S + (e ? offB1 : offB0);
 #pragma unroll
         for (int J = 0; J < NJ; ++J)
-          if (J < nj) dmma(G[J], acc[T][e], xb[8 * J]);
+          if (FULL || J < nj) dmma(G[J], acc[T][e], xb[8 * J]);
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
+    if (lane == 0) {
+      if (mbar_arrive_last(&empty[st])) {           // every warp is done with this stage: refill it
+        mbar_wait(&empty[st], (uint32_t)((it / STAGES) & 1));   // acquire the other warps' releases (already complete)
+        if (b + STAGES < b1) issue_load(b + STAGES);
+      }
+    }
+#pragma unroll
+    for (int T = 0; T < NT; ++T) { acc[T][0] = nxt[T][0]; acc[T][1] = nxt[T][1]; }
   }
 
   if (valid) {
     double* out = P.partG + ((size_t)split * P.C + chain) * P.Dp + 2 * tig;
 #pragma unroll
     for (int J = 0; J < NJ; ++J)
-      if (J < nj) *reinterpret_cast<double2*>(out + 8 * J) = make_double2(G[J][0], G[J][1]);
+      if (FULL || J < nj) *reinterpret_cast<double2*>(out + 8 * J) = make_double2(G[J][0], G[J][1]);
   }
-  if (P.want_lp) {
+  if (want_lp) {
     lpacc += __shfl_xor_sync(0xffffffffu, lpacc, 1);
     lpacc += __shfl_xor_sync(0xffffffffu, lpacc, 2);
     if (valid && tig == 0) P.partLp[(size_t)split * P.C + chain] = lpacc;
@@ -413,15 +488,18 @@ static int pick_ksplit(int ntiles, int nblocks, int nsm) {
   return best;
 }
 
-template <int NJ> static cudaError_t launch_grad_t(const GradParams& P, size_t smem, cudaStream_t st) {
+template <int NJ, bool FULL> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  glm_grad_kernel<NJ><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
+  glm_grad_kernel<NJ, FULL><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
   return cudaGetLastError();
+}
+template <int NJ> static cudaError_t launch_grad_t(const GradParams& P, size_t smem, cudaStream_t st) {
+  return P.nj == NJ ? launch_grad_tf<NJ, true>(P, smem, st) : launch_grad_tf<NJ, false>(P, smem, st);
 }
 static cudaError_t launch_grad(int nj_inst, const GradParams& P, size_t smem, cudaStream_t st) {
   switch (nj_inst) {
