@@ -51,8 +51,8 @@ def workload(name, chains=None):
                     unit_per_iter=16, unit="leapfrog steps/s", arrays={}, flops_per_unit=290.0, bound="fp64", peak=FP64_DFMA_PEAK_TFLOPS)
     if name == "c4":
         y, sigma = qs.programs.c4_eight_schools_data(1000)
-        return dict(name="c4", prog=qs.programs.eight_schools(y, sigma), kernel=qs.DriftKernel(), L=1, chains=chains or 131072,
-                    desc="hierarchical 8-schools-style J=1000 (d=1002), drift RW-Metropolis with scale adaptation, fp64",
+        return dict(name="c4", prog=qs.programs.eight_schools(y, sigma), kernel=qs.DriftKernel(scale=0.02), L=1, chains=chains or 131072,
+                    desc="hierarchical 8-schools-style J=1000 (d=1002), drift RW-Metropolis scale=0.02 with scale adaptation, fp64",
                     unit_per_iter=1, unit="proposals/s", arrays=dict(y=y, sigma=sigma), bytes_per_unit=40.0 * 1002, bound="hbm")
     if name == "c5":
         return dict(name="c5", prog=qs.programs.funnel(1000), kernel=qs.MixtureKernel([qs.HARMKernel(), qs.HMCKernel(numSteps=16)], [0.5, 0.5]),

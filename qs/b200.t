@@ -1,0 +1,183 @@
+-- qs/b200.t -- the Terra side of the B200 many-chain MCMC engine.
+--
+-- Drop-in for the hot path of qs/mcmc.t: `qs.b200.MCMC(kernel, params)` has the signature and the
+-- return shape of `qs.MCMC(kernel, params)` (qs/mcmc.t:36-105): it returns `function(program)` which
+-- returns `terra(samples: &S.Vector(infer.SampleType(program)))`.  The kernel constructors
+-- `qs.b200.HMCKernel{...}`, `DriftKernel{...}`, `HARMKernel{...}`, `MixtureKernel(kernels, weights)` take the
+-- parameter tables of qs/hmc.t:52-66, qs/drift.t:55-73, qs/harm.t:12-22, qs/mcmc.t:199-203 and yield a
+-- POD spec the CUDA library reads, instead of a `function(TraceType) -> struct`.
+--
+-- The library is reached the way the reference reaches C: terralib.includec on a plain-C header
+-- (qs/lib/ad.t:3, qs/lib/random.t:2-7, qs/lib/util.t:45-61).  A non-zero return becomes the reference's
+-- print + abort (S.assert, qs/lib/std.t:35-43).
+--
+-- NOTE: this image has no Terra compiler, so this file is shipped un-run; the same ABI is exercised from
+-- Python (quicksand_b200/_lib.py) and C (tests/test_abi.py::test_header_is_plain_c).  INTEGRATION.md shows
+-- the two-line change to qs/init.t that registers it.
+
+local S = require("qs.lib.std")
+local qs = require("qs.globals")
+local infer = require("qs.infer")
+local progmod = require("qs.progmodule")
+
+local libdir = os.getenv("QSB200_LIB_DIR") or "."
+terralib.linklibrary(libdir .. "/libqsb200.so")
+local B = terralib.includec("qsb200.h", {"-I", os.getenv("QSB200_INCLUDE_DIR") or "include"})
+
+local C = terralib.includecstring [[
+#include <stdio.h>
+#include <stdlib.h>
+]]
+
+-- S.assert-style failure: message, then abort (qs/lib/std.t:35-43)
+local check = macro(function(rc)
+	return quote
+		if rc ~= 0 then
+			C.printf("qsb200: %s\n", B.qsb_last_error())
+			C.abort()
+		end
+	end
+end)
+
+-- ---------------------------------------------------------------------------------------------
+-- Kernel constructors: same tables, same defaults as the reference.
+local function kernelSpec(kind, doAdapt, stepSize, numSteps, scale)
+	return { specs = { {kind=kind, doAdapt=doAdapt and 1 or 0, stepSize=stepSize, numSteps=numSteps, scale=scale, weight=1.0} } }
+end
+
+local function HMCKernel(params)            -- qs/hmc.t:57-66
+	params = params or {}
+	local doStepSizeAdapt = true
+	if params.doStepSizeAdapt ~= nil then doStepSizeAdapt = params.doStepSizeAdapt end
+	return kernelSpec(B.QSB_KERNEL_HMC, doStepSizeAdapt, params.stepSize or 1.0, params.numSteps or 1, 1.0)
+end
+
+local function DriftKernel(params)          -- qs/drift.t:63-73
+	params = params or {}
+	local doScaleAdapt = true
+	if params.doScaleAdapt ~= nil then doScaleAdapt = params.doScaleAdapt end
+	assert(not params.lexicalScaleSharing, "qs.b200.DriftKernel: lexicalScaleSharing is not implemented on the device yet")
+	return kernelSpec(B.QSB_KERNEL_DRIFT, doScaleAdapt, 1.0, 1, params.scale or 1.0)
+end
+
+local function HARMKernel(params)           -- qs/harm.t:16-22
+	params = params or {}
+	local doScaleAdapt = true
+	if params.doScaleAdapt ~= nil then doScaleAdapt = params.doScaleAdapt end
+	return kernelSpec(B.QSB_KERNEL_HARM, doScaleAdapt, 1.0, 1, params.scale or 1.0)
+end
+
+local function MixtureKernel(kernels, weights)   -- qs/mcmc.t:199-203
+	assert(#kernels == #weights, "MixtureKernel: number of kernels must equal number of weights")
+	local specs = {}
+	for i,k in ipairs(kernels) do
+		assert(#k.specs == 1, "qs.b200.MixtureKernel: nested mixtures are not supported")
+		local s = {}
+		for key,v in pairs(k.specs[1]) do s[key] = v end
+		s.weight = weights[i]
+		specs[#specs+1] = s
+	end
+	return { specs = specs }
+end
+
+-- ---------------------------------------------------------------------------------------------
+-- Model descriptors.  The device path runs a closed set of fixed-structure families; a qs.program is tagged with
+-- the descriptor of its family:  qs.b200.describe(program, {family=..., dim=..., ...}).  Pointers in the table are
+-- Terra globals / constant arrays owned by the caller.
+local descriptors = {}
+local function describe(program, desc)
+	progmod.assertIsProgram(program, "qs.b200.describe")
+	descriptors[program] = desc
+	return program
+end
+
+-- ---------------------------------------------------------------------------------------------
+-- qs.b200.MCMC: the replacement of doMCMC (qs/mcmc.t:45-103).
+local function MCMC(kernel, params)
+	params = params or {}
+	local _numsamps = params.numsamps or 1000      -- mcmc.t:38
+	local _burnin = params.burnin or 0             -- mcmc.t:39
+	local _lag = params.lag or 1                   -- mcmc.t:40
+	local _numchains = params.numchains or 1       -- new: 1 = the reference's single chain, identical sample shape
+	local _seed = params.seed or 0
+	local _device = params.device or -1
+	local _verbose = params.verbose and true or false
+	local nspecs = #kernel.specs
+
+	return function(program)
+		progmod.assertIsProgram(program, "MCMC")
+		local desc = descriptors[program]
+		if not desc then
+			error("qs.b200.MCMC: program has no device descriptor (structural or discrete programs stay on qs.MCMC)")
+		end
+		local SampleT = infer.SampleType(program)
+
+		return terra(samples: &S.Vector(SampleT))
+			var d : B.qsb_model_desc
+			d.family = [desc.family]; d.dim = [desc.dim]; d.nobs = [desc.nobs or 0]
+			d.ret_mode = [desc.ret_mode or 1]; d.ret_div = [desc.ret_div or 1.0]; d.prior_sigma = [desc.prior_sigma or 0.0]
+			d.erp_kind = [desc.erp_kind or `nil]; d.erp_p0 = [desc.erp_p0 or `nil]; d.erp_p1 = [desc.erp_p1 or `nil]
+			d.A = [desc.A or `nil]; d.X = [desc.X or `nil]; d.ybin = [desc.ybin or `nil]
+			d.y = [desc.y or `nil]; d.sigma = [desc.sigma or `nil]
+			var model : &B.qsb_model = nil
+			check(B.qsb_model_create(&d, [_device], &model))
+
+			var specs : B.qsb_kernel_spec[ nspecs ]
+			escape
+				for i,s in ipairs(kernel.specs) do
+					emit quote
+						specs[ [i-1] ].kind = [s.kind]; specs[ [i-1] ].doAdapt = [s.doAdapt]
+						specs[ [i-1] ].stepSize = [s.stepSize]; specs[ [i-1] ].numSteps = [s.numSteps]
+						specs[ [i-1] ].scale = [s.scale]; specs[ [i-1] ].weight = [s.weight]
+					end
+				end
+			end
+			var cfg : B.qsb_run_config
+			cfg.seed = [_seed]; cfg.chain_begin = 0; cfg.numchains = [_numchains]; cfg.sample_chains = 0
+			cfg.flags = 0; cfg.device = [_device]; cfg.reserved = 0; cfg.stream = nil
+			var sampler : &B.qsb_sampler = nil
+			check(B.qsb_sampler_create(model, specs, nspecs, &cfg, &sampler))
+			check(B.qsb_sampler_init(sampler))                                  -- TraceType.salloc():init(true), mcmc.t:55
+			check(B.qsb_sampler_run(sampler, [_numsamps], [_burnin], [_lag]))   -- the for i=0,iters loop, mcmc.t:57-72
+
+			-- Caller owns the vector (qs/infer.t:127): it is resized here and the library writes Sample structs
+			-- {value, logprob, loglikelihood} (infer.t:13-18) straight into its storage, chain after chain.
+			var n = B.qsb_sampler_num_samples(sampler)
+			samples:resize(n * [_numchains])
+			check(B.qsb_sampler_fetch_samples(sampler, 0, [_numchains], 0, n, [&opaque](samples:get(0)), sizeof(SampleT)))
+
+			escape
+				if _verbose then
+					emit quote
+						var st : B.qsb_stats
+						check(B.qsb_sampler_stats(sampler, &st))
+						-- same line formats as mcmc.t:81,88
+						C.printf("Acceptance Ratio: %u/%u (%g%%)\n", st.props_accepted, st.props_made,
+							100.0*double(st.props_accepted)/st.props_made)
+						C.printf("Time: %g\n", st.seconds)
+					end
+				end
+			end
+			check(B.qsb_sampler_destroy(sampler))
+			check(B.qsb_model_destroy(model))
+		end
+	end
+end
+
+return
+{
+	exports =
+	{
+		b200 =
+		{
+			MCMC = MCMC,
+			HMCKernel = HMCKernel,
+			DriftKernel = DriftKernel,
+			HARMKernel = HARMKernel,
+			MixtureKernel = MixtureKernel,
+			describe = describe,
+			FAM_INDEP = B.QSB_FAM_INDEP, FAM_GAUSS_PREC = B.QSB_FAM_GAUSS_PREC, FAM_LOGISTIC = B.QSB_FAM_LOGISTIC,
+			FAM_EIGHT_SCHOOLS = B.QSB_FAM_EIGHT_SCHOOLS, FAM_FUNNEL = B.QSB_FAM_FUNNEL
+		}
+	}
+}

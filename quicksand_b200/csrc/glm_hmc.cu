@@ -475,6 +475,7 @@ struct GlmSampler {
 };
 
 static int pick_ksplit(int ntiles, int nblocks, int nsm) {
+  if (const char* env = getenv("QSB_GLM_KSPLIT")) { int k = atoi(env); if (k >= 1 && k <= nblocks) return k; }   // tuning override
   int best = 1; double beste = 0.0;
   const int kmax = std::max(1, nblocks / 12);
   for (int k = 1; k <= kmax; ++k) {
