@@ -195,3 +195,52 @@ def test_chain_ids_are_partition_invariant(qs):
     part = qs.Sampler(prog, k, numchains=32, seed=3, chain_begin=32); part.init(); part.run(20)
     a = full.fetch_values(); b = part.fetch_values()
     assert np.array_equal(a[32:], b)
+
+
+def test_device_diagnostics_match_numpy(qs):
+    """qsb_sampler_diagnostics (device reduction to plain sums) against a numpy evaluation of the fetched draws,
+    for both sample layouts (thread-per-chain and warp-per-chain)."""
+    from quicksand_b200 import diagnostics as D
+    from test_multirank_gloo import raw_from_draws
+    for prog, mapping in [(_programs(qs)["funnel12"], 1), (_programs(qs)["funnel70"], 32)]:
+        s = qs.Sampler(prog, qs.HMCKernel(numSteps=4, stepSize=0.05, doStepSizeAdapt=False), numchains=48, seed=5, mapping=mapping)
+        s.init(); s.run(60, burnin=10, lag=2)
+        draws = s.fetch_values()
+        assert draws.shape == (48, 60, prog.dim)
+        raw = s.diagnostics_raw(maxlag=20)
+        ref = raw_from_draws(draws, 20)
+        assert np.allclose(raw, ref, rtol=1e-9, atol=1e-9), np.abs(raw - ref).max()
+        summ = D.summarize(raw, prog.dim, 20)
+        assert np.all(np.isfinite(summ["ess"])) and np.all(summ["ess"] > 0)
+        st = s.stats()
+        assert st["iterations"] == 130 and st["props_made"] == 48 * 130
+        s.close()
+
+
+def test_sample_struct_layout_and_lag(qs):
+    """fetch_samples fills S.Vector(Sample(T)) elements {value[retdim], logprob, loglikelihood} (infer.t:13-18);
+    iteration i is kept iff i >= burnin and i % lag == 0 (mcmc.t:64)."""
+    prog = _programs(qs)["gauss10"]
+    s = qs.Sampler(prog, qs.DriftKernel(scale=0.2), numchains=8, seed=1, flags=2)
+    s.init(); s.run(7, burnin=5, lag=3)     # iters = 26; kept i = 6, 9, ..., 24 -> 7 samples
+    rec = s.fetch_record()
+    smp = s.fetch_samples()
+    assert smp.shape == (8, 7) and smp.dtype.itemsize == 8 * 3
+    kept = [i for i in range(26) if i >= 5 and i % 3 == 0]
+    assert len(kept) == 7
+    vals = rec["state"][:, kept, :].sum(axis=2) / 10.0
+    assert np.allclose(smp["value"][:, :, 0], vals, rtol=1e-13)
+    assert np.all(smp["loglikelihood"] == 0.0)
+    s.close()
+
+
+def test_error_behaviour(qs):
+    """Unsupported requests fail loudly with a message (the shim turns them into the reference's print + abort)."""
+    from quicksand_b200 import _lib as L
+    with pytest.raises(L.QsbError):
+        qs.Sampler(_programs(qs)["logistic20"], qs.DriftKernel(), numchains=4)
+    with pytest.raises(L.QsbError):
+        qs.Sampler(qs.programs.funnel(5000), qs.HMCKernel(), numchains=4)
+    m = qs.MCMC(qs.HMCKernel(numSteps=3), dict(numsamps=20, numchains=3, seed=2))
+    mean = qs.infer(_programs(qs)["gaussian1"], qs.Expectation(), m)()
+    assert mean.shape == (3,) and np.all(np.isfinite(mean))
