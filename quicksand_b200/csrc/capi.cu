@@ -68,6 +68,7 @@ struct qsb_sampler {
   uint64_t rec_iters = 0;
   double t_accum = 0.0; uint64_t t_launches = 0;   // QSB_FLAG_TIME_KERNEL
   bool ev_pending = false;
+  double* stage = nullptr; size_t stage_bytes = 0;  // device staging of fetch_samples (kept between calls)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -398,6 +399,7 @@ int qsb_sampler_destroy(qsb_sampler* s) {
   cudaStreamSynchronize(s->stream);
   if (s->glm) glm_sampler_destroy(s->glm);
   else free_run_buffers(s);
+  if (s->stage) cudaFree(s->stage);
   s->arena.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -568,8 +570,14 @@ static int fetch_common(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, u
   // staged through a device buffer, at most ~256 MiB at a time
   uint32_t chunk = (uint32_t)std::max<size_t>(1, (256u << 20) / (ns * stride_bytes));
   chunk = std::min<uint32_t>(chunk, c1 - c0);
-  double* stage = nullptr;
-  CU(cudaMalloc((void**)&stage, (size_t)chunk * ns * stride_bytes));
+  const size_t need = (size_t)chunk * ns * stride_bytes;
+  if (s->stage_bytes < need) {
+    if (s->stage) cudaFree(s->stage);
+    s->stage = nullptr; s->stage_bytes = 0;
+    CU(cudaMalloc((void**)&s->stage, need));
+    s->stage_bytes = need;
+  }
+  double* stage = s->stage;
   int rc = 0;
   for (uint32_t c = c0; c < c1 && !rc; c += chunk) {
     uint32_t nc = std::min<uint32_t>(chunk, c1 - c);
@@ -581,7 +589,6 @@ static int fetch_common(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, u
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) rc = fail(100 + (int)e, std::string("fetch: ") + cudaGetErrorString(e));
   }
-  cudaFree(stage);
   return rc;
 }
 

@@ -126,8 +126,49 @@ __device__ __forceinline__ double sigmoid_fast(double z) {
   return y;
 }
 
+// The same computation cut into 22 single-latency steps on a (zr, q, k) state, so that the steps of several
+// elements can be issued round-robin between the tensor-core instructions of the next row block: no step waits on
+// its predecessor and the MMA stream of the warp never stalls behind a 25-deep dependent DFMA chain
+// (ncu profiles/r01_c3_grad_v2: stall_wait 33 % of samples before this change).
+struct SigState { double zr, q; int k; };
+template <int STEP> __device__ __forceinline__ void sigmoid_step(SigState& s, double yv) {
+  constexpr double SHIFT = 6755399441055744.0;
+  if (STEP == 0) s.zr = fmin(fmax(-s.zr, -708.0), 708.0);
+  else if (STEP == 1) s.q = fma(s.zr, 1.4426950408889634, SHIFT);
+  else if (STEP == 2) { s.k = __double2loint(s.q); s.q -= SHIFT; }
+  else if (STEP == 3) s.zr = fma(s.q, -6.93147180369123816490e-01, s.zr);
+  else if (STEP == 4) { s.zr = fma(s.q, -1.90821492927058770002e-10, s.zr); s.q = 1.6059043836821613e-10; }
+  else if (STEP == 5) s.q = fma(s.q, s.zr, 2.08767569878681e-09);
+  else if (STEP == 6) s.q = fma(s.q, s.zr, 2.505210838544172e-08);
+  else if (STEP == 7) s.q = fma(s.q, s.zr, 2.755731922398589e-07);
+  else if (STEP == 8) s.q = fma(s.q, s.zr, 2.7557319223985893e-06);
+  else if (STEP == 9) s.q = fma(s.q, s.zr, 2.48015873015873e-05);
+  else if (STEP == 10) s.q = fma(s.q, s.zr, 1.984126984126984e-04);
+  else if (STEP == 11) s.q = fma(s.q, s.zr, 1.388888888888889e-03);
+  else if (STEP == 12) s.q = fma(s.q, s.zr, 8.333333333333333e-03);
+  else if (STEP == 13) s.q = fma(s.q, s.zr, 4.1666666666666664e-02);
+  else if (STEP == 14) s.q = fma(s.q, s.zr, 1.6666666666666666e-01);
+  else if (STEP == 15) s.q = fma(s.q, s.zr, 0.5);
+  else if (STEP == 16) s.q = fma(s.q, s.zr, 1.0);
+  else if (STEP == 17) s.q = fma(s.q, s.zr, 1.0);
+  else if (STEP == 18) s.q = 1.0 + __hiloint2double(__double2hiint(s.q) + (s.k << 20), __double2loint(s.q));
+  else if (STEP == 19) { asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s.zr) : "d"(s.q)); }
+  else if (STEP == 20) { double err = fma(-s.q, s.zr, 1.0); s.zr = fma(s.zr, err, s.zr); }
+  else if (STEP == 21) { double err = fma(-s.q, s.zr, 1.0); s.zr = fma(s.zr, err, s.zr); }
+  else if (STEP == 22) s.zr = yv - s.zr;
+}
+static constexpr int SIG_STEPS = 23;
+template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps(SigState (&st)[4], const double (&yv)[4]) {
+  if constexpr (S0 < S1 && S0 < SIG_STEPS) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sigmoid_step<S0>(st[i], yv[i]);
+    sigmoid_steps<S0 + 1, S1>(st, yv);
+  }
+}
+
 // FULL: every one of the NJ dimension tiles is live (nj == NJ), so the tile loops carry no predicates.
-template <int NJ, bool FULL>
+// LP: also accumulate the log-likelihood (last leapfrog step of a trajectory, initialisation, step-size probes).
+template <int NJ, bool FULL, bool LP>
 __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_constant__ GradParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
@@ -181,7 +222,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   double lpacc = 0.0;
   const int offA = rho_g * S + 2 * tig;                 // phase 1 B fragment: X[rho(gid)][8J + 2tig .. +1]
   const int offB0 = rho_t0 * S + gid, offB1 = rho_t1 * S + gid;   // phase 2 B fragment: X[rho(2tig+e)][8J + gid]
-  const bool want_lp = P.want_lp != 0;
+  constexpr bool want_lp = LP;
 
   // Software pipeline over row blocks: while the sigmoid epilogue of block b runs on the FP64 ALU path, the first
   // contraction (Z^T = Theta^T X^T) of block b+1 is already feeding the tensor pipe; then the second contraction
@@ -225,13 +266,40 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
       const double* Xn = sm + SD * st2;
 #pragma unroll
       for (int T = 0; T < NT; ++T) nxt[T][0] = nxt[T][1] = 0.0;
+      if constexpr (!LP && NT == 4 && NJ >= 12) {
+        // lock-step sigmoid: elements (T=0,1) advance 4 steps per dimension tile J = 0..5, elements (T=2,3) during J = 6..11
+        SigState sa[4], sb[4];
+        double ya[4], yb[4];
 #pragma unroll
-      for (int J = 0; J < NJ; ++J) {
-        if (FULL || J < nj) phase1_tile(Xn, J, nxt);
-        if (J < 2 * NT) epilogue_elem(ys, J >> 1, J & 1);      // NJ >= 2*NT interleaves all; otherwise the rest follows
+        for (int i = 0; i < 4; ++i) {
+          sa[i].zr = acc[i >> 1][i & 1]; sa[i].q = 0.0; sa[i].k = 0; ya[i] = ys[(i >> 1) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
+          sb[i].zr = acc[2 + (i >> 1)][i & 1]; sb[i].q = 0.0; sb[i].k = 0; yb[i] = ys[(2 + (i >> 1)) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
+        }
+        if (FULL || 0 < nj) phase1_tile(Xn, 0, nxt);  sigmoid_steps<0, 4>(sa, ya);
+        if (FULL || 1 < nj) phase1_tile(Xn, 1, nxt);  sigmoid_steps<4, 8>(sa, ya);
+        if (FULL || 2 < nj) phase1_tile(Xn, 2, nxt);  sigmoid_steps<8, 12>(sa, ya);
+        if (FULL || 3 < nj) phase1_tile(Xn, 3, nxt);  sigmoid_steps<12, 16>(sa, ya);
+        if (FULL || 4 < nj) phase1_tile(Xn, 4, nxt);  sigmoid_steps<16, 20>(sa, ya);
+        if (FULL || 5 < nj) phase1_tile(Xn, 5, nxt);  sigmoid_steps<20, 23>(sa, ya);
+        if (FULL || 6 < nj) phase1_tile(Xn, 6, nxt);  sigmoid_steps<0, 4>(sb, yb);
+        if (FULL || 7 < nj) phase1_tile(Xn, 7, nxt);  sigmoid_steps<4, 8>(sb, yb);
+        if (FULL || 8 < nj) phase1_tile(Xn, 8, nxt);  sigmoid_steps<8, 12>(sb, yb);
+        if (FULL || 9 < nj) phase1_tile(Xn, 9, nxt);  sigmoid_steps<12, 16>(sb, yb);
+        if (FULL || 10 < nj) phase1_tile(Xn, 10, nxt); sigmoid_steps<16, 20>(sb, yb);
+        if (FULL || 11 < nj) phase1_tile(Xn, 11, nxt); sigmoid_steps<20, 23>(sb, yb);
+#pragma unroll
+        for (int J = 12; J < NJ; ++J) if (FULL || J < nj) phase1_tile(Xn, J, nxt);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i >> 1][i & 1] = sa[i].zr; acc[2 + (i >> 1)][i & 1] = sb[i].zr; }
+      } else {
+#pragma unroll
+        for (int J = 0; J < NJ; ++J) {
+          if (FULL || J < nj) phase1_tile(Xn, J, nxt);
+          if (J < 2 * NT) epilogue_elem(ys, J >> 1, J & 1);      // NJ >= 2*NT interleaves all; otherwise the rest follows
+        }
+#pragma unroll
+        for (int q = NJ; q < 2 * NT; ++q) epilogue_elem(ys, q >> 1, q & 1);
       }
-#pragma unroll
-      for (int q = NJ; q < 2 * NT; ++q) epilogue_elem(ys, q >> 1, q & 1);
     } else {
 #pragma unroll
       for (int q = 0; q < 2 * NT; ++q) epilogue_elem(ys, q >> 1, q & 1);
@@ -483,24 +551,25 @@ static int pick_ksplit(int ntiles, int nblocks, int nsm) {
     long waves = (ctas + nsm - 1) / nsm;
     double eff = (double)ctas / (double)(waves * nsm);
     // per-CTA prologue/epilogue costs roughly one row block of time
-    eff *= (double)(nblocks / k) / (double)(nblocks / k + 1.5);
+    eff *= (double)(nblocks / k) / (double)(nblocks / k + 0.75);
     if (eff > beste * 1.005) { beste = eff; best = k; }
   }
   return best;
 }
 
-template <int NJ, bool FULL> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
+template <int NJ, bool FULL, bool LP> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  glm_grad_kernel<NJ, FULL><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
+  glm_grad_kernel<NJ, FULL, LP><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
   return cudaGetLastError();
 }
 template <int NJ> static cudaError_t launch_grad_t(const GradParams& P, size_t smem, cudaStream_t st) {
-  return P.nj == NJ ? launch_grad_tf<NJ, true>(P, smem, st) : launch_grad_tf<NJ, false>(P, smem, st);
+  if (P.nj == NJ) return P.want_lp ? launch_grad_tf<NJ, true, true>(P, smem, st) : launch_grad_tf<NJ, true, false>(P, smem, st);
+  return P.want_lp ? launch_grad_tf<NJ, false, true>(P, smem, st) : launch_grad_tf<NJ, false, false>(P, smem, st);
 }
 static cudaError_t launch_grad(int nj_inst, const GradParams& P, size_t smem, cudaStream_t st) {
   switch (nj_inst) {
