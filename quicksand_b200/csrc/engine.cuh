@@ -112,7 +112,7 @@ static __device__ __noinline__ double erp_fwd_noinline(int kind, double x, doubl
 // sees, hmc.t:325-342 + erp.t:623-640); lp_float is the float-trace logprob (no Jacobian: what
 // Drift/HARM and the very first HMC Hamiltonian see, erp.t:361).  Inactive elements (component
 // index >= dim) carry x = 0 and must not contribute.
-template <int FAM, int G, int NPL, bool GRAD>
+template <int FAM, int G, int NPL, bool GRAD, bool LP = true>
 __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, const double (&x)[NPL], double (&g)[NPL], double& lp_float) {
   const ModelDev& m = P.m;
   const int d = m.dim;
@@ -138,12 +138,11 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
         double sx = 0.0;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) if (j < d) sx += P.Sc[(e * NPL + j) & 255] * x[j];
-        q += x[e] * sx;
-        lp += gaussian_lp(x[e], 0.0, 1.0);
+        if (LP) { q += x[e] * sx; lp += gaussian_lp(x[e], 0.0, 1.0); }
         if (GRAD) g[e] = -x[e] - 0.5 * sx;
       } else if (GRAD) g[e] = 0.0;
     }
-    lp += -0.5 * (0.5 * q);
+    if (LP) lp += -0.5 * (0.5 * q);
     lp_float = lp;
     return lp;
   } else if (FAM == FAM_EIGHT_SCHOOLS) {
@@ -154,7 +153,7 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
     const double mu = x0, lt = x1;
     const double tau = exp(lt);
     const double tau2 = tau * tau;
-    const double c_th = 1.8378770664093453 + 2.0 * log(tau);
+    const double c_th = LP ? 1.8378770664093453 + 2.0 * log(tau) : 0.0;
     double lp = 0.0, gmu = 0.0, glt = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
@@ -165,8 +164,10 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
         double r = th - mu;
         double r2t = r * r / tau2;
         double ry = yj - th;
-        lp += -.5 * (c_th + r2t);
-        lp += -.5 * (m.cy[j] + ry * ry / s2);
+        if (LP) {
+          lp += -.5 * (c_th + r2t);
+          lp += -.5 * (m.cy[j] + ry * ry / s2);
+        }
         if (GRAD) {
           double rt = r / tau2;
           g[e] = -rt + ry / s2;
@@ -175,8 +176,10 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
         }
       } else if (GRAD) g[e] = 0.0;
     }
-    lp = Grp<G>::sum(lp);
-    lp += gaussian_lp(mu, 0.0, 5.0) + gaussian_lp(lt, 0.0, 1.0);
+    if (LP) {
+      lp = Grp<G>::sum(lp);
+      lp += gaussian_lp(mu, 0.0, 5.0) + gaussian_lp(lt, 0.0, 1.0);
+    }
     if (GRAD) {
       gmu = Grp<G>::sum(gmu);
       glt = Grp<G>::sum(glt);
@@ -192,19 +195,21 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
     const double v = Grp<G>::bcast(x[0], 0);
     const double s = exp(v / 2.0);
     const double s2 = s * s;
-    const double c_x = 1.8378770664093453 + 2.0 * log(s);
+    const double c_x = LP ? 1.8378770664093453 + 2.0 * log(s) : 0.0;
     double lp = 0.0, gv = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
       if (i >= 1 && i < d) {
         double xi = x[e];
         double q = xi * xi / s2;
-        lp += -.5 * (c_x + q);
+        if (LP) lp += -.5 * (c_x + q);
         if (GRAD) { g[e] = -xi / s2; gv += -0.5 + 0.5 * q; }
       } else if (GRAD) g[e] = 0.0;
     }
-    lp = Grp<G>::sum(lp);
-    lp += gaussian_lp(v, 0.0, 3.0);
+    if (LP) {
+      lp = Grp<G>::sum(lp);
+      lp += gaussian_lp(v, 0.0, 3.0);
+    }
     if (GRAD) {
       gv = Grp<G>::sum(gv);
       QSB_FOR_E { if (e * G + lane == 0) g[e] = -v / 9.0 + gv; }
@@ -248,12 +253,15 @@ template <int FAM, int G, int NPL> struct Chain {
     return -0.5 * Grp<G>::sum(k);
   }
   // ---- HMCKernel:step (hmc.t:307-323): two separate half-kicks, reference operation order
+  // LPW: also return the log-density at the new position.  Inside a trajectory only the last step's value is used
+  // (hmc.t:150-152 computes and overwrites it every step), so the other steps skip its logs and divisions.
+  template <bool LPW = true>
   __device__ __forceinline__ double leapfrog(double eps, double (&xs)[NPL], double (&gs)[NPL], double (&p)[NPL]) const {
     const double he = 0.5 * eps;
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     QSB_FOR_E xs[e] = xs[e] + eps * p[e] * 1.0;
     double lpf;
-    double lp = model_eval<FAM, G, NPL, true>(P, lane, xs, gs, lpf);
+    double lp = model_eval<FAM, G, NPL, true, LPW>(P, lane, xs, gs, lpf);
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     return lp;
   }
@@ -276,7 +284,8 @@ template <int FAM, int G, int NPL> struct Chain {
   }
 
   // ---- searchForInitialStepSize (hmc.t:345-391).  x, g are the current position / gradient in HBM.
-  __device__ __forceinline__ double search_step_size(double eps, double dual_lp, double (&xs)[NPL], double (&gs)[NPL], double (&p)[NPL]) const {
+  __device__ __noinline__ double search_step_size(double eps, double dual_lp) const {
+    double xs[NPL], gs[NPL], p[NPL];   // own scratch: arrays passed by reference into a call would be forced into local memory
     uint32_t probe = 0;
     const double LOG_HALF = log(0.5);
     load(P.x, xs); load(P.g, gs);
@@ -324,7 +333,7 @@ template <int FAM, int G, int NPL> struct Chain {
       count(0, 1);
       if (!(fl & FLAG_HMC_INIT) && adapting) {
         if (G == 32) __syncwarp();
-        eps = search_step_size(eps, dual_lp, xs, gs, p);
+        eps = search_step_size(eps, dual_lp);
         if (leader()) {   // adapter:reinit(stepSize, adaptRate) (hmc.t:261)
           P.da_k[c] = 0; P.da_x0[c] = eps; P.da_lastx[c] = eps; P.da_gbar[c] = 0.0; P.da_xbar[c] = 0.0; P.da_gamma[c] = 0.05;
         }
@@ -338,10 +347,17 @@ template <int FAM, int G, int NPL> struct Chain {
     const double H = kinetic(p) + lp_cur;
     double newlp = 0.0;
     rec_step = eps;
-    for (uint32_t s = 0; s < L; ++s) {
-      newlp = leapfrog(eps, xs, gs, p);
+    for (uint32_t s = 0; s + 1 < L; ++s) {
+      leapfrog<false>(eps, xs, gs, p);
       if (P.rec_leap) {
         size_t base = (((size_t)c * P.rec_iters + (iter - P.it_begin)) * L + s) * d;
+        QSB_FOR_E { int i = e * G + lane; if (i < d) P.rec_leap[base + i] = xs[e]; }
+      }
+    }
+    {
+      newlp = leapfrog<true>(eps, xs, gs, p);
+      if (P.rec_leap) {
+        size_t base = (((size_t)c * P.rec_iters + (iter - P.it_begin)) * L + (L - 1)) * d;
         QSB_FOR_E { int i = e * G + lane; if (i < d) P.rec_leap[base + i] = xs[e]; }
       }
     }
@@ -534,7 +550,7 @@ template <int FAM, int G, int NPL> struct Chain {
 // ---------------------------------------------------------------------------------------------
 // Kernels
 template <int FAM, int G, int NPL>
-__global__ void __launch_bounds__(G == 1 ? 128 : 256) advance_kernel(const __grid_constant__ EngineParams P) {
+__global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 4 : 1) advance_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
   if (grp >= P.C) return;
   Chain<FAM, G, NPL> ch(P, grp);

@@ -83,7 +83,9 @@ __device__ __forceinline__ double uniform_at(RngKey key, uint32_t chain, uint32_
 // v from uniform(2a+1)).  Returns v/u; the caller forms mu + sigma*v/u in the reference's order.
 // Products and sums of the acceptance test are issued un-contracted (no FMA) so the accept/reject of
 // every attempt, and therefore the draw, is bit-identical to a CPU evaluation of the same expressions.
-__device__ __forceinline__ void leva_vu(RngKey key, uint32_t chain, uint32_t iter, uint32_t slot, double& v_out, double& u_out) {
+// not inlined: called once per component per iteration; inlining the 10-round Philox at every unrolled component
+// multiplied the kernels' code size past the instruction cache
+static __device__ __noinline__ void leva_vu(RngKey key, uint32_t chain, uint32_t iter, uint32_t slot, double& v_out, double& u_out) {
   double u, v;
   for (uint32_t blk = 0;; ++blk) {
     uint32_t w[4];
