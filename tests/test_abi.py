@@ -88,3 +88,20 @@ def test_no_gpu_means_loud_failure(qs):
     from quicksand_b200 import _lib
     with pytest.raises(_lib.QsbError):
         qs.programs.funnel(8).model()
+
+
+def test_cxx_mirror_compiles_links_and_fails_loudly_without_gpu(qs, tmp_path):
+    """include/qsb200.hpp (header-only C++ mirror of the reference interface) against libqsb200.so: the reference's
+    10-gaussian HMC test (testsuite.t:719-730).  Without a GPU the program must exit with the library's error, not fall back."""
+    import subprocess
+    import torch
+    from quicksand_b200 import _lib
+    exe = tmp_path / "example"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cxx", "example.cpp"),
+                    "-o", str(exe), "-L", libdir, "-lqsb200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 2 and "qsb200:" in r.stderr

@@ -345,3 +345,16 @@ def test_correlated_gaussian_moments_and_oracle_agreement(qs, oracle):
         assert abs(d["var"][j] - ov) <= 4 * np.sqrt(m4 / max(d["ess"][j], 100.0) + m4 / oess), (j, d["var"][j], ov)
     emp = np.cov(vals.reshape(-1, 10).T)
     assert np.abs(emp - Sigma).max() < 0.15      # the never-ending adaptation biases the reference algorithm itself
+
+
+def test_cxx_mirror_runs_the_reference_test(qs, tmp_path):
+    """The C++ mirror (include/qsb200.hpp) end to end on the device: the reference's 10-gaussian HMC expectation test."""
+    import os, subprocess
+    from quicksand_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "example"
+    subprocess.run(["g++", "-std=c++17", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cxx", "example.cpp"),
+                    "-o", str(exe), "-L", libdir, "-lqsb200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
