@@ -185,7 +185,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=os.environ.get("QSB_WORKLOAD", "c3"))
@@ -206,7 +206,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         wl0 = workload(args.workload)
-        trans = {"c3": 8, "c2": 4000, "c4": 1500, "c5": 150}[wl0["name"]]
+        trans = {"c3": 16, "c2": 8000, "c4": 3000, "c5": 300}[wl0["name"]]
         s = cpu_sample(args.workload, cores, trans)
         cpu = {"value": cpu_units_per_sec(wl0, s), "unit": wl0["unit"], "cores": cores, "kind": "port",
                "sample": "%d chains (one per core) x %d transitions from initialisation of the CPU restatement of the reference algorithm "

@@ -599,23 +599,31 @@ int glm_model_create(GlmModel* m, const double* X, const uint8_t* y, int N, int 
   cudaMemcpy(m->yv, yv.data(), yv.size() * 8, cudaMemcpyHostToDevice);
   return 0;
 }
+__global__ void ybin_to_double_kernel(const uint8_t* yb, double* yv, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) yv[i] = yb[i] ? 1.0 : 0.0;
+}
+
+// fully asynchronous on `stream` when X and y are pinned: two H2D copies and a conversion kernel, no host sync
 int glm_model_update(GlmModel* m, const double* X, const uint8_t* y, void* stream, std::string& why) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (m->S == m->d) e = cudaMemcpyAsync(m->Xp, X, (size_t)m->N * m->d * 8, cudaMemcpyHostToDevice, st);
   else e = cudaMemcpy2DAsync(m->Xp, (size_t)m->S * 8, X, (size_t)m->d * 8, (size_t)m->d * 8, m->N, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) { why = cudaGetErrorString(e); return 100 + (int)e; }
-  if (m->ystage.size() != (size_t)m->N) m->ystage.resize(m->N);
-  for (int i = 0; i < m->N; ++i) m->ystage[i] = y[i] ? 1.0 : 0.0;
-  e = cudaMemcpyAsync(m->yv, m->ystage.data(), (size_t)m->N * 8, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // ystage is reused by the next call
+  if (!m->ybin_dev && cudaMalloc((void**)&m->ybin_dev, m->N) != cudaSuccess) { why = "cudaMalloc failed"; return 2; }
+  e = cudaMemcpyAsync(m->ybin_dev, y, (size_t)m->N, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { why = cudaGetErrorString(e); return 100 + (int)e; }
+  ybin_to_double_kernel<<<(m->N + 255) / 256, 256, 0, st>>>(m->ybin_dev, m->yv, m->N);
+  e = cudaGetLastError();
   if (e != cudaSuccess) { why = cudaGetErrorString(e); return 100 + (int)e; }
   return 0;
 }
 void glm_model_destroy(GlmModel* m) {
   if (m->Xp) cudaFree(m->Xp);
   if (m->yv) cudaFree(m->yv);
-  m->Xp = m->yv = nullptr;
+  if (m->ybin_dev) cudaFree(m->ybin_dev);
+  m->Xp = m->yv = nullptr; m->ybin_dev = nullptr;
 }
 
 template <class T> static bool dalloc(GlmSampler* s, T** p, size_t n) {

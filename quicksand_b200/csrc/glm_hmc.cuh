@@ -15,7 +15,7 @@ struct GlmModel {
   double prior_sigma = 0;
   double* Xp = nullptr;    // HBM [Npad][S], zero padded
   double* yv = nullptr;    // HBM [Npad]: 0.0 / 1.0, 2.0 marks a padding row
-  std::vector<double> ystage;   // host staging of y as doubles (qsb_model_update_data)
+  uint8_t* ybin_dev = nullptr;  // HBM [N] raw labels, staging of qsb_model_update_data
 };
 
 struct GlmSampler;
