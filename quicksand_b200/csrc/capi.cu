@@ -301,6 +301,7 @@ static int alloc_engine_state(qsb_sampler* s) {
   A(a.alloc(&P.x, C * d)); A(a.alloc(&P.lp, C)); A(a.alloc(&P.flags, C));
   A(a.alloc(&P.eps, C));   // also the lp_float output of the logp_grad test hook
   A(a.alloc(&P.g, C * d));
+  if (has_drift || has_harm) A(a.alloc(&P.xs, C * d));
   if (has_hmc) {
     A(a.alloc(&P.da_gbar, C)); A(a.alloc(&P.da_xbar, C)); A(a.alloc(&P.da_x0, C)); A(a.alloc(&P.da_lastx, C)); A(a.alloc(&P.da_gamma, C));
     A(a.alloc(&P.da_k, C));
@@ -523,7 +524,9 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
       if (R.rec_kidx) R.rec_kidx += off;
       if (R.rec_leap) R.rec_leap += off * R.numSteps[0] * d;
     }
-    s->var->advance(R, s->stream);
+    bool has_hmc = false;
+    for (int k = 0; k < R.nsub; ++k) has_hmc |= R.kind[k] == K_HMC;
+    if (has_hmc) s->var->advance(R, s->stream); else s->var->advance_nohmc(R, s->stream);
   }
   ++s->launches;
   CU(cudaEventRecord(s->ev1, s->stream));

@@ -30,6 +30,9 @@ enum { K_HMC = 1, K_DRIFT = 2, K_HARM = 3 };
 enum { FLAG_HMC_INIT = 1, FLAG_GRAD_VALID = 2 };
 enum { ERR_NAN_SEARCH = 1, ERR_SEARCH_INF = 2, ERR_SEARCH_ZERO = 4 };
 static constexpr int MAX_SUB = 8;
+#ifndef QSB_WARP_BLOCKS
+#define QSB_WARP_BLOCKS 2   // resident 256-thread blocks per SM of the warp-per-chain kernels (register cap 128)
+#endif
 
 struct ModelDev {
   int family, dim, nobs, ret_mode;
@@ -52,6 +55,7 @@ struct EngineParams {
   double Sc[16 * 16];               // GAUSS_PREC: A + A^T padded to stride NPL, read from the constant bank
   // chain state
   double *x, *g, *lp;
+  double* xs;                       // proposal scratch of the streaming Drift / HARM kernels, like x
   uint8_t* flags;
   double *eps, *da_gbar, *da_xbar, *da_x0, *da_lastx, *da_gamma;
   uint32_t* da_k;
@@ -220,6 +224,42 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// The float-trace log-density as a stream over components (what Drift / HARM score: erp.t:361, no Jacobian), for the
+// warp-per-chain kernels: a proposal is generated, scored and parked in HBM component by component, so the kernel holds
+// no per-lane vectors in registers and runs at 3 blocks per SM instead of 1.  The per-lane accumulation order equals
+// model_eval's (components ascending, then the warp butterfly), so both forms give bit-identical sums.
+template <int FAM> struct ModelStream {
+  double g0, g1, a, b;   // component 0 and 1 of the proposal and two derived scalars
+  __device__ __forceinline__ void prep(const EngineParams& P, double x0, double x1) {
+    g0 = x0; g1 = x1; a = 0.0; b = 0.0;
+    if (FAM == FAM_EIGHT_SCHOOLS) { const double tau = exp(x1); a = tau * tau; b = 1.8378770664093453 + 2.0 * log(tau); }
+    if (FAM == FAM_FUNNEL) { const double s = exp(x0 / 2.0); a = s * s; b = 1.8378770664093453 + 2.0 * log(s); }
+  }
+  // adds component i's terms to lp, in model_eval's order
+  __device__ __forceinline__ void term(const EngineParams& P, int i, double xi, double& lp) const {
+    if (FAM == FAM_INDEP) {
+      double lpy, lj, gi;
+      erp_eval(P.m.erp_kind[i], xi, P.m.p0[i], P.m.p1[i], lpy, lj, gi);
+      lp += lpy;
+    } else if (FAM == FAM_EIGHT_SCHOOLS) {
+      if (i >= 2) {
+        const int j = i - 2;
+        const double r = xi - g0, ry = P.m.y[j] - xi;
+        lp += -.5 * (b + r * r / a);
+        lp += -.5 * (P.m.cy[j] + ry * ry / P.m.s2[j]);
+      }
+    } else if (FAM == FAM_FUNNEL) {
+      if (i >= 1) lp += -.5 * (b + xi * xi / a);
+    }
+  }
+  __device__ __forceinline__ double finish(double lp_sum) const {
+    if (FAM == FAM_EIGHT_SCHOOLS) return lp_sum + (gaussian_lp(g0, 0.0, 5.0) + gaussian_lp(g1, 0.0, 1.0));
+    if (FAM == FAM_FUNNEL) return lp_sum + gaussian_lp(g0, 0.0, 3.0);
+    return lp_sum;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 template <int FAM, int G, int NPL> struct Chain {
   const EngineParams& P;
   const uint32_t c;       // local chain index
@@ -240,11 +280,44 @@ template <int FAM, int G, int NPL> struct Chain {
     if (leader()) atomicAdd(&P.counters[which], n);
   }
 
+  // ---- Gaussian draws of one iteration.  Component i of the chain reads sub-stream (chain, iter, slot = i) and
+  // accepts the first Leva pair that passes (distrib.t:66-72).  Doing that in lock step over the components of a
+  // lane would make every component cost the *maximum* attempt count of the 32 lanes of the warp (E ~ 3.6 instead
+  // of 1.37).  Instead every lane walks through ITS OWN components, one attempt per trip, and parks the accepted
+  // pair in its private column of shared memory (column = thread, row = component slot: conflict-free); the
+  // consumer then reads the rows with compile-time indices.  Warp trips ~ max over lanes of the lane's total attempts.
+  static constexpr int HALF = (NPL + 1) / 2;
+  static constexpr int NB = 2 * HALF;                 // shared-memory rows per thread
+  __device__ __forceinline__ double* zcol() const {
+    extern __shared__ double qsb_zbuf[];
+    return qsb_zbuf + threadIdx.x;
+  }
+  // VU = false: row r (component e_begin + r) <- v/u;  VU = true: row r <- v, row HALF + r <- u
+  template <bool VU>
+  __device__ __forceinline__ void gaussian_fill(uint32_t iter, int e_begin, int e_end) const {
+    double* z = zcol();
+    const int stride = blockDim.x;
+    int e = e_begin;
+    uint32_t blk = 0;
+    while (e < e_end && e * G + lane < d) {
+      double v, u;
+      if (leva_attempt(P.key, gc, iter, (uint32_t)(e * G + lane), blk, v, u)) {
+        if (VU) { z[(e - e_begin) * stride] = v; z[(HALF + e - e_begin) * stride] = u; }
+        else z[(e - e_begin) * stride] = v / u;
+        ++e; blk = 0;
+      } else ++blk;
+    }
+    if (G > 1) __syncwarp();
+  }
+
   // ---- sampleMomenta + kinetic energy (hmc.t:289-305), invMasses == 1
   __device__ __forceinline__ void sample_momenta(uint32_t iter, double (&p)[NPL]) const {
+    gaussian_fill<false>(iter, 0, NPL);
+    const double* z = zcol();
+    const int stride = blockDim.x;
     QSB_FOR_E {
       int i = e * G + lane;
-      p[e] = i < d ? gaussian_std(P.key, gc, iter, (uint32_t)i) * 1.0 : 0.0;
+      p[e] = i < d ? z[e * stride] * 1.0 : 0.0;
     }
   }
   __device__ __forceinline__ double kinetic(const double (&p)[NPL]) const {
@@ -385,17 +458,30 @@ template <int FAM, int G, int NPL> struct Chain {
     const uint32_t n_rv = P.dr_n[c];
     const double s0 = P.dr_s0[c], mult = P.dr_mult[c];
     load(P.x, x);
-    // proposal x'_i = gaussian.sample(x_i, scale_i)
-    QSB_FOR_E {
-      int i = e * G + lane;
-      if (i < d) {
-        double sc = s0;
-        if (n_rv > 100) {   // scale = varEst:getStdDev() [* 0.99]  (drift.t:288-298)
-          sc = sqrt(P.dr_m2[vidx<G>(P, i, c)] / (double)(n_rv - 1));
-          if (mult != 1.0) sc = sc * mult;
+    // proposal x'_i = gaussian.sample(x_i, scale_i) = x_i + scale_i*v/u (distrib.t:73), in two passes of HALF components
+    {
+      const double* z = zcol();
+      const int stride = blockDim.x;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        gaussian_fill<true>(iter, h * HALF, h * HALF + HALF < NPL ? h * HALF + HALF : NPL);
+#pragma unroll
+        for (int r = 0; r < HALF; ++r) {
+          const int e = h * HALF + r;
+          if (e < NPL) {
+            int i = e * G + lane;
+            if (i < d) {
+              double sc = s0;
+              if (n_rv > 100) {   // scale = varEst:getStdDev() [* 0.99]  (drift.t:288-298)
+                sc = sqrt(P.dr_m2[vidx<G>(P, i, c)] / (double)(n_rv - 1));
+                if (mult != 1.0) sc = sc * mult;
+              }
+              xp[e] = __dadd_rn(x[e], __dmul_rn(sc, z[r * stride]) / z[(HALF + r) * stride]);
+            } else xp[e] = 0.0;
+          }
         }
-        xp[e] = gaussian_sample(P.key, gc, iter, (uint32_t)i, x[e], sc);
-      } else xp[e] = 0.0;
+        if (G > 1) __syncwarp();
+      }
     }
     rec_step = s0;
     double lpf, gdummy[NPL];
@@ -448,10 +534,15 @@ template <int FAM, int G, int NPL> struct Chain {
     const size_t kc = (size_t)k * P.C + c;
     load(P.x, x);
     double nrm = 0.0;
-    QSB_FOR_E {
-      int i = e * G + lane;
-      xp[e] = i < d ? gaussian_std(P.key, gc, iter, (uint32_t)i) : 0.0;
-      nrm += xp[e] * xp[e];
+    gaussian_fill<false>(iter, 0, NPL);
+    {
+      const double* z = zcol();
+      const int stride = blockDim.x;
+      QSB_FOR_E {
+        int i = e * G + lane;
+        xp[e] = i < d ? z[e * stride] : 0.0;
+        nrm += xp[e] * xp[e];
+      }
     }
     nrm = sqrt(Grp<G>::sum(nrm));
     const double hscale = P.ha_scale[c];
@@ -484,7 +575,131 @@ template <int FAM, int G, int NPL> struct Chain {
     return accept;
   }
 
+  // ---- warp-per-chain streaming forms of the two Metropolis kernels (same operations, no register vectors)
+  __device__ __forceinline__ bool drift_next_stream(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    const bool adapting = P.doAdapt[k] != 0;
+    const size_t kc = (size_t)k * P.C + c;
+    unsigned long long made = P.made[kc] + 1, acc = P.acc[kc];
+    const uint32_t n_rv = P.dr_n[c];
+    const double s0 = P.dr_s0[c], mult = P.dr_mult[c];
+    const double* z = zcol();
+    const int stride = blockDim.x;
+    const int ne = (d + G - 1) / G;                     // component rows of this chain
+    ModelStream<FAM> ms;
+    double lp = 0.0;
+    for (int h = 0; h < 2; ++h) {
+      const int e0 = h * HALF, e1 = min(e0 + HALF, ne);
+      gaussian_fill<true>(iter, e0, e1);
+      for (int e = e0; e < e1; ++e) {
+        const int i = e * G + lane;
+        double xpi = 0.0;
+        if (i < d) {
+          const size_t ix = vidx<G>(P, i, c);
+          double sc = s0;
+          if (n_rv > 100) {   // scale = varEst:getStdDev() [* 0.99]  (drift.t:288-298)
+            sc = sqrt(P.dr_m2[ix] / (double)(n_rv - 1));
+            if (mult != 1.0) sc = sc * mult;
+          }
+          xpi = __dadd_rn(P.x[ix], __dmul_rn(sc, z[(e - e0) * stride]) / z[(HALF + e - e0) * stride]);
+          P.xs[ix] = xpi;
+        }
+        if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
+        if (i < d) ms.term(P, i, xpi, lp);
+      }
+      __syncwarp();
+    }
+    rec_step = s0;
+    const double lpf = ms.finish(Grp<G>::sum(lp));
+    const double thresh = lpf - P.lp[c];
+    rec_dh = thresh;
+    const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
+    const bool accept = log(u) < thresh;
+    if (accept) acc += 1;
+    const double ratio = (double)acc / (double)made;
+    const bool upd = adapting && ratio >= 0.05 && acc > 5;   // RunningVar:update with the current state (drift.t:26-37, 279-284)
+    const uint32_t n_new = upd ? n_rv + 1 : n_rv;
+    if (accept || upd) {
+      for (int e = 0; e < ne; ++e) {
+        const int i = e * G + lane;
+        if (i < d) {
+          const size_t ix = vidx<G>(P, i, c);
+          double cur;
+          if (accept) { cur = P.xs[ix]; P.x[ix] = cur; } else cur = P.x[ix];
+          if (upd) {
+            if (n_new == 1) { P.dr_mean[ix] = cur; P.dr_m2[ix] = 0.0; }
+            else {
+              const double mean = P.dr_mean[ix];
+              const double newmean = mean + (cur - mean) / (double)n_new;
+              P.dr_m2[ix] = P.dr_m2[ix] + (cur - mean) * (cur - newmean);
+              P.dr_mean[ix] = newmean;
+            }
+          }
+        }
+      }
+    }
+    if (leader()) {
+      if (accept) { P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID; }
+      if (adapting) {
+        const bool shrink = ratio < 0.05 && acc > 5;
+        P.dr_n[c] = n_new;
+        if (n_new > 100) P.dr_mult[c] = shrink ? 0.99 : 1.0;
+        else if (shrink) P.dr_s0[c] = s0 * 0.99;
+      }
+      P.made[kc] = made; P.acc[kc] = acc;
+    }
+    return accept;
+  }
+
+  __device__ __forceinline__ bool harm_next_stream(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    const bool adapting = P.doAdapt[k] != 0;
+    const size_t kc = (size_t)k * P.C + c;
+    const double* z = zcol();
+    const int stride = blockDim.x;
+    const int ne = (d + G - 1) / G;
+    gaussian_fill<false>(iter, 0, ne);
+    double nrm = 0.0;
+    for (int e = 0; e < ne; ++e) { if (e * G + lane < d) { const double zi = z[e * stride]; nrm += zi * zi; } }
+    nrm = sqrt(Grp<G>::sum(nrm));
+    const double hscale = P.ha_scale[c];
+    rec_step = hscale;
+    const double step = uniform_at(P.key, gc, iter, (uint32_t)d) * hscale;
+    ModelStream<FAM> ms;
+    double lp = 0.0;
+    for (int e = 0; e < ne; ++e) {
+      const int i = e * G + lane;
+      double xpi = 0.0;
+      if (i < d) {
+        const size_t ix = vidx<G>(P, i, c);
+        xpi = P.x[ix] + (step * (z[e * stride] / nrm));
+        P.xs[ix] = xpi;
+      }
+      if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
+      if (i < d) ms.term(P, i, xpi, lp);
+    }
+    const double lpf = ms.finish(Grp<G>::sum(lp));
+    double t = 0.234;
+    if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
+    const double thresh = lpf - P.lp[c];
+    rec_dh = thresh;
+    const double u = uniform_at(P.key, gc, iter, (uint32_t)d + 1u);
+    const bool accept = log(u) < thresh;
+    double ns = hscale;
+    if (accept) {
+      for (int e = 0; e < ne; ++e) { const int i = e * G + lane; if (i < d) { const size_t ix = vidx<G>(P, i, c); P.x[ix] = P.xs[ix]; } }
+      if (adapting) ns = hscale + (hscale / (t * (1.0 - t))) * (1.0 - t) / (double)(iter + 1u);
+    } else {
+      if (adapting) ns = fabs(hscale - (hscale / (t * (1.0 - t))) * t / (double)(iter + 1u));
+    }
+    if (leader()) {
+      P.made[kc] += 1;
+      if (accept) { P.acc[kc] += 1; P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID; }
+      P.ha_scale[c] = ns;
+    }
+    return accept;
+  }
+
   // ---- one iteration of doMCMC's loop body (mcmc.t:57-72)
+  template <bool HAS_HMC>
   __device__ __forceinline__ void iterate(uint64_t it) const {
     const uint32_t iter = (uint32_t)it;
     int k = 0;
@@ -500,9 +715,10 @@ template <int FAM, int G, int NPL> struct Chain {
     double rdh = 0.0, rstep = 0.0;
     bool accept;
     const int kind = P.kind[k];
-    if (kind == K_HMC) accept = hmc_next(k, iter, rdh, rstep);
-    else if (kind == K_DRIFT) accept = drift_next(k, iter, rdh, rstep);
-    else accept = harm_next(k, iter, rdh, rstep);
+    constexpr bool STREAM = G == 32 && FAM != FAM_GAUSS_PREC;
+    if (HAS_HMC && kind == K_HMC) accept = hmc_next(k, iter, rdh, rstep);
+    else if (kind == K_DRIFT) accept = STREAM ? drift_next_stream(k, iter, rdh, rstep) : drift_next(k, iter, rdh, rstep);
+    else accept = STREAM ? harm_next_stream(k, iter, rdh, rstep) : harm_next(k, iter, rdh, rstep);
     if (G == 32) __syncwarp();
     const bool keep = it >= P.burnin && (it % P.lag) == 0 && c < P.sample_chains && P.samples != nullptr;
     if (keep || P.rec_state) {
@@ -549,12 +765,15 @@ template <int FAM, int G, int NPL> struct Chain {
 
 // ---------------------------------------------------------------------------------------------
 // Kernels
-template <int FAM, int G, int NPL>
-__global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 4 : 1) advance_kernel(const __grid_constant__ EngineParams P) {
+// HAS_HMC = false: the kernel list holds no HMCKernel; the trajectory code (and its register vectors) is not compiled
+// in, which lets the warp-per-chain Drift / HARM kernels run at 3 blocks per SM.
+template <int FAM, int G, int NPL, bool HAS_HMC>
+__global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 4 : (HAS_HMC ? QSB_WARP_BLOCKS : 3))
+advance_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
   if (grp >= P.C) return;
   Chain<FAM, G, NPL> ch(P, grp);
-  for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.iterate(it);
+  for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC>(it);
 }
 
 // Forward-sampling initialisation (trace.t:592-624: update(true) creates every choice by sampling it,
@@ -644,6 +863,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) logp_grad_kernel(const __g
 struct EngineVariant {
   int family, G, npl;
   void (*advance)(const EngineParams&, void* stream);
+  void (*advance_nohmc)(const EngineParams&, void* stream);
   void (*init)(const EngineParams&, void* stream);
   void (*rescore)(const EngineParams&, void* stream);
   void (*logp_grad)(const EngineParams&, void* stream);

@@ -8,11 +8,18 @@ namespace qsb {
 template <int FAM, int G, int NPL> struct VariantImpl {
   static constexpr int TPB = G == 1 ? 128 : 256;
   static unsigned grid(const EngineParams& P) { return (unsigned)(((size_t)P.C * G + TPB - 1) / TPB); }
-  static void advance(const EngineParams& P, void* st) { advance_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
+  static constexpr size_t SMEM = (size_t)Chain<FAM, G, NPL>::NB * TPB * sizeof(double);   // Gaussian staging columns
+  template <bool HAS_HMC> static void advance_t(const EngineParams& P, void* st) {
+    static bool attr = false;
+    if (!attr && SMEM > 48 * 1024) { cudaFuncSetAttribute(advance_kernel<FAM, G, NPL, HAS_HMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); attr = true; }
+    advance_kernel<FAM, G, NPL, HAS_HMC><<<grid(P), TPB, SMEM, (cudaStream_t)st>>>(P);
+  }
+  static void advance(const EngineParams& P, void* st) { advance_t<true>(P, st); }
+  static void advance_nohmc(const EngineParams& P, void* st) { advance_t<false>(P, st); }
   static void init(const EngineParams& P, void* st) { init_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void rescore(const EngineParams& P, void* st) { rescore_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void logp_grad(const EngineParams& P, void* st) { logp_grad_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
-  static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &init, &rescore, &logp_grad}; }
+  static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &advance_nohmc, &init, &rescore, &logp_grad}; }
 };
 
 }  // namespace qsb

@@ -103,6 +103,20 @@ static __device__ __noinline__ void leva_vu(RngKey key, uint32_t chain, uint32_t
   }
   v_out = v; u_out = u;
 }
+// One attempt (= one Philox block) of the same loop: true when the pair (v, u) is accepted.
+static __device__ __noinline__ bool leva_attempt(RngKey key, uint32_t chain, uint32_t iter, uint32_t slot, uint32_t blk, double& v_out, double& u_out) {
+  uint32_t w[4];
+  philox4x32_10(blk, slot, iter, chain, key.k0, key.k1, w);
+  const double u = __dsub_rn(1.0, u53(w[0], w[1]));
+  const double v = __dmul_rn(1.7156, __dsub_rn(u53(w[2], w[3]), 0.5));
+  v_out = v; u_out = u;
+  const double x = __dsub_rn(u, 0.449871);
+  const double y = __dadd_rn(fabs(v), 0.386595);
+  const double q = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, __dsub_rn(__dmul_rn(0.196, y), __dmul_rn(0.25472, x))));
+  if (!(q >= 0.27597)) return true;
+  if (q > 0.27846) return false;
+  return !(__dmul_rn(v, v) > __dmul_rn(__dmul_rn(__dmul_rn(-4.0, u), u), log(u)));
+}
 __device__ __forceinline__ double gaussian_std(RngKey key, uint32_t chain, uint32_t iter, uint32_t slot) {
   double v, u;
   leva_vu(key, chain, iter, slot, v, u);
