@@ -53,7 +53,7 @@ def workload(name, chains=None):
         y, sigma = qs.programs.c4_eight_schools_data(1000)
         return dict(name="c4", prog=qs.programs.eight_schools(y, sigma), kernel=qs.DriftKernel(scale=0.02), L=1, chains=chains or 131072,
                     desc="hierarchical 8-schools-style J=1000 (d=1002), drift RW-Metropolis scale=0.02 with scale adaptation, fp64",
-                    unit_per_iter=1, unit="proposals/s", arrays=dict(y=y, sigma=sigma), bytes_per_unit=40.0 * 1002, bound="hbm")
+                    unit_per_iter=1, unit="proposals/s", arrays=dict(y=y, sigma=sigma), bytes_per_unit=40.0 * 1002, bound="hbm")   # x, mean, m2 read; mean, m2 written
     if name == "c5":
         return dict(name="c5", prog=qs.programs.funnel(1000), kernel=qs.MixtureKernel([qs.HARMKernel(), qs.HMCKernel(numSteps=16)], [0.5, 0.5]),
                     L=16, chains=chains or 32768, desc="1000-D Neal's funnel, MixtureKernel{HARM, HMC L=16} 0.5/0.5, fp64",
@@ -328,7 +328,9 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
         else:
             achieved = wl["flops_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e12
-            roof = {"bound": wl["bound"], "achieved": achieved, "peak": wl["peak"], "unit": "TFLOP/s", "frac": achieved / wl["peak"], "traffic": None,
+            roof = {"bound": wl["bound"], "achieved": achieved, "peak": wl["peak"], "unit": "TFLOP/s", "frac": achieved / wl["peak"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01_c3_grad_v3.ncu-rep)
+                    "traffic": 40.1e6 if (wl["name"] == "c3" and C == 8192) else None,
                     "peak_source": "fp64 peak measured by tools/microbench.cu on this pool (profiles/r01_microbench_b200.json); "
                                    "MEASURED_PEAKS.json has no fp64 entry",
                     "kernel": "glm_grad_kernel" if wl["name"] == "c3" else "advance_kernel",
