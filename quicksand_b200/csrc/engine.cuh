@@ -117,7 +117,8 @@ static __device__ __noinline__ double erp_fwd_noinline(int kind, double x, doubl
 // Drift/HARM and the very first HMC Hamiltonian see, erp.t:361).  Inactive elements (component
 // index >= dim) carry x = 0 and must not contribute.
 template <int FAM, int G, int NPL, bool GRAD, bool LP = true>
-__device__ __forceinline__ double model_eval(const EngineParams& P, int lane, const double (&x)[NPL], double (&g)[NPL], double& lp_float) {
+__device__ __forceinline__ double model_eval(const EngineParams& P, int lane, const double (&x)[NPL], double (&g)[NPL], double& lp_float,
+                                             const double* Ssm = nullptr) {
   const ModelDev& m = P.m;
   const int d = m.dim;
   if (FAM == FAM_INDEP) {
@@ -141,7 +142,7 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
       if (e < d) {
         double sx = 0.0;
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) if (j < d) sx += P.Sc[(e * NPL + j) & 255] * x[j];
+        for (int j = 0; j < NPL; ++j) if (j < d) sx += (Ssm ? Ssm[e * NPL + j] : P.Sc[(e * NPL + j) & 255]) * x[j];
         if (LP) { q += x[e] * sx; lp += gaussian_lp(x[e], 0.0, 1.0); }
         if (GRAD) g[e] = -x[e] - 0.5 * sx;
       } else if (GRAD) g[e] = 0.0;
@@ -266,6 +267,8 @@ template <int FAM, int G, int NPL> struct Chain {
   const uint32_t gc;      // global chain id (Philox counter word)
   const int lane;
   const int d;
+  const double* Ssm = nullptr;                 // GAUSS_PREC: A + A^T staged in shared memory (broadcast LDS, compile-time offsets)
+  mutable unsigned long long cnt[2] = {0, 0};  // gradient evaluations / leapfrog steps of this group, flushed once per launch
   __device__ __forceinline__ Chain(const EngineParams& P_, uint32_t c_)
       : P(P_), c(c_), gc(P_.chain_begin + c_), lane(Grp<G>::lane()), d(P_.d) {}
 
@@ -277,7 +280,17 @@ template <int FAM, int G, int NPL> struct Chain {
   }
   __device__ __forceinline__ bool leader() const { return lane == 0; }
   __device__ __forceinline__ void count(int which, unsigned long long n) const {
-    if (leader()) atomicAdd(&P.counters[which], n);
+    if (leader()) cnt[which] += n;
+  }
+  // one atomic per warp and counter per launch (a per-chain atomic on one address serialised 9 % of the c2 kernel)
+  __device__ __forceinline__ void flush_counts() const {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      unsigned long long v = cnt[w];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31u) == 0 && v) atomicAdd(&P.counters[w], v);
+    }
   }
 
   // ---- Gaussian draws of one iteration.  Component i of the chain reads sub-stream (chain, iter, slot = i) and
@@ -334,7 +347,7 @@ template <int FAM, int G, int NPL> struct Chain {
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     QSB_FOR_E xs[e] = xs[e] + eps * p[e] * 1.0;
     double lpf;
-    double lp = model_eval<FAM, G, NPL, true, LPW>(P, lane, xs, gs, lpf);
+    double lp = model_eval<FAM, G, NPL, true, LPW>(P, lane, xs, gs, lpf, Ssm);
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     return lp;
   }
@@ -401,7 +414,7 @@ template <int FAM, int G, int NPL> struct Chain {
     if (!(fl & FLAG_GRAD_VALID)) {
       load(P.x, xs);
       double lpf;
-      double dual_lp = model_eval<FAM, G, NPL, true>(P, lane, xs, gs, lpf);
+      double dual_lp = model_eval<FAM, G, NPL, true>(P, lane, xs, gs, lpf, Ssm);
       store(P.g, gs);
       count(0, 1);
       if (!(fl & FLAG_HMC_INIT) && adapting) {
@@ -485,7 +498,7 @@ template <int FAM, int G, int NPL> struct Chain {
     }
     rec_step = s0;
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false>(P, lane, xp, gdummy, lpf);
+    model_eval<FAM, G, NPL, false>(P, lane, xp, gdummy, lpf, Ssm);
     const double lp_cur = P.lp[c];
     const double thresh = lpf - lp_cur;
     rec_dh = thresh;
@@ -553,7 +566,7 @@ template <int FAM, int G, int NPL> struct Chain {
       xp[e] = i < d ? x[e] + (step * (xp[e] / nrm)) : 0.0;
     }
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false>(P, lane, xp, gdummy, lpf);
+    model_eval<FAM, G, NPL, false>(P, lane, xp, gdummy, lpf, Ssm);
     double t = 0.234;
     if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
     const double thresh = lpf - P.lp[c];
@@ -771,9 +784,20 @@ template <int FAM, int G, int NPL, bool HAS_HMC>
 __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 4 : (HAS_HMC ? QSB_WARP_BLOCKS : 3))
 advance_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
-  if (grp >= P.C) return;
-  Chain<FAM, G, NPL> ch(P, grp);
-  for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC>(it);
+  const double* Ssm = nullptr;
+  if (FAM == FAM_GAUSS_PREC) {
+    extern __shared__ double qsb_zbuf[];
+    double* sS = qsb_zbuf + (size_t)Chain<FAM, G, NPL>::NB * blockDim.x;   // after the Gaussian staging columns
+    for (int t = threadIdx.x; t < NPL * NPL; t += blockDim.x) sS[t] = P.Sc[t & 255];
+    __syncthreads();
+    Ssm = sS;
+  }
+  const bool active = grp < P.C;               // whole warps: C*G and the block size are multiples of 32 or the tail warp idles
+  Chain<FAM, G, NPL> ch(P, active ? grp : 0);
+  ch.Ssm = Ssm;
+  if (active)
+    for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC>(it);
+  ch.flush_counts();
 }
 
 // Forward-sampling initialisation (trace.t:592-624: update(true) creates every choice by sampling it,

@@ -8,7 +8,7 @@ namespace qsb {
 template <int FAM, int G, int NPL> struct VariantImpl {
   static constexpr int TPB = G == 1 ? 128 : 256;
   static unsigned grid(const EngineParams& P) { return (unsigned)(((size_t)P.C * G + TPB - 1) / TPB); }
-  static constexpr size_t SMEM = (size_t)Chain<FAM, G, NPL>::NB * TPB * sizeof(double);   // Gaussian staging columns
+  static constexpr size_t SMEM = ((size_t)Chain<FAM, G, NPL>::NB * TPB + (FAM == FAM_GAUSS_PREC ? NPL * NPL : 0)) * sizeof(double);   // Gaussian staging columns (+ S)
   template <bool HAS_HMC> static void advance_t(const EngineParams& P, void* st) {
     static bool attr = false;
     if (!attr && SMEM > 48 * 1024) { cudaFuncSetAttribute(advance_kernel<FAM, G, NPL, HAS_HMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); attr = true; }
