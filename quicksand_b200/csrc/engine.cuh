@@ -116,9 +116,10 @@ static __device__ __noinline__ double erp_fwd_noinline(int kind, double x, doubl
 // sees, hmc.t:325-342 + erp.t:623-640); lp_float is the float-trace logprob (no Jacobian: what
 // Drift/HARM and the very first HMC Hamiltonian see, erp.t:361).  Inactive elements (component
 // index >= dim) carry x = 0 and must not contribute.
-template <int FAM, int G, int NPL, bool GRAD, bool LP = true>
-__device__ __forceinline__ double model_eval(const EngineParams& P, int lane, const double (&x)[NPL], double (&g)[NPL], double& lp_float,
-                                             const double* Ssm = nullptr) {
+// SSM: GAUSS_PREC reads A + A^T from the copy advance_kernel staged in shared memory behind the Gaussian columns
+// (the pointer is formed here from the shared array itself so that the loads compile to LDS, not generic LD).
+template <int FAM, int G, int NPL, bool GRAD, bool LP = true, bool SSM = false>
+__device__ __forceinline__ double model_eval(const EngineParams& P, int lane, const double (&x)[NPL], double (&g)[NPL], double& lp_float) {
   const ModelDev& m = P.m;
   const int d = m.dim;
   if (FAM == FAM_INDEP) {
@@ -138,11 +139,18 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
   } else if (FAM == FAM_GAUSS_PREC) {
     // log p = sum_i gaussian_lp(x_i;0,1) + factor(-0.5 x'Ax),  x'Ax = 0.5 x'(A+A')x ;  G == 1 only
     double lp = 0.0, q = 0.0;
+    extern __shared__ double qsb_zbuf[];
+    const double* Ssm = qsb_zbuf + (size_t)(2 * ((NPL + 1) / 2)) * blockDim.x;
     QSB_FOR_E {
       if (e < d) {
         double sx = 0.0;
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) if (j < d) sx += (Ssm ? Ssm[e * NPL + j] : P.Sc[(e * NPL + j) & 255]) * x[j];
+        for (int j = 0; j < NPL; ++j) {
+          if (j < d) {
+            if (SSM) sx += Ssm[e * NPL + j] * x[j];                 // shared memory (advance kernel)
+            else sx += P.Sc[(e * NPL + j) & 255] * x[j];            // kernel parameter (one-off kernels)
+          }
+        }
         if (LP) { q += x[e] * sx; lp += gaussian_lp(x[e], 0.0, 1.0); }
         if (GRAD) g[e] = -x[e] - 0.5 * sx;
       } else if (GRAD) g[e] = 0.0;
@@ -267,7 +275,6 @@ template <int FAM, int G, int NPL> struct Chain {
   const uint32_t gc;      // global chain id (Philox counter word)
   const int lane;
   const int d;
-  const double* Ssm = nullptr;                 // GAUSS_PREC: A + A^T staged in shared memory (broadcast LDS, compile-time offsets)
   mutable unsigned long long cnt[2] = {0, 0};  // gradient evaluations / leapfrog steps of this group, flushed once per launch
   __device__ __forceinline__ Chain(const EngineParams& P_, uint32_t c_)
       : P(P_), c(c_), gc(P_.chain_begin + c_), lane(Grp<G>::lane()), d(P_.d) {}
@@ -347,7 +354,7 @@ template <int FAM, int G, int NPL> struct Chain {
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     QSB_FOR_E xs[e] = xs[e] + eps * p[e] * 1.0;
     double lpf;
-    double lp = model_eval<FAM, G, NPL, true, LPW>(P, lane, xs, gs, lpf, Ssm);
+    double lp = model_eval<FAM, G, NPL, true, LPW, FAM == FAM_GAUSS_PREC>(P, lane, xs, gs, lpf);
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     return lp;
   }
@@ -370,7 +377,7 @@ template <int FAM, int G, int NPL> struct Chain {
   }
 
   // ---- searchForInitialStepSize (hmc.t:345-391).  x, g are the current position / gradient in HBM.
-  __device__ __noinline__ double search_step_size(double eps, double dual_lp) const {
+  __device__ __forceinline__ double search_step_size(double eps, double dual_lp) const {
     double xs[NPL], gs[NPL], p[NPL];   // own scratch: arrays passed by reference into a call would be forced into local memory
     uint32_t probe = 0;
     const double LOG_HALF = log(0.5);
@@ -414,7 +421,7 @@ template <int FAM, int G, int NPL> struct Chain {
     if (!(fl & FLAG_GRAD_VALID)) {
       load(P.x, xs);
       double lpf;
-      double dual_lp = model_eval<FAM, G, NPL, true>(P, lane, xs, gs, lpf, Ssm);
+      double dual_lp = model_eval<FAM, G, NPL, true, true, FAM == FAM_GAUSS_PREC>(P, lane, xs, gs, lpf);
       store(P.g, gs);
       count(0, 1);
       if (!(fl & FLAG_HMC_INIT) && adapting) {
@@ -498,7 +505,7 @@ template <int FAM, int G, int NPL> struct Chain {
     }
     rec_step = s0;
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false>(P, lane, xp, gdummy, lpf, Ssm);
+    model_eval<FAM, G, NPL, false, true, FAM == FAM_GAUSS_PREC>(P, lane, xp, gdummy, lpf);
     const double lp_cur = P.lp[c];
     const double thresh = lpf - lp_cur;
     rec_dh = thresh;
@@ -566,7 +573,7 @@ template <int FAM, int G, int NPL> struct Chain {
       xp[e] = i < d ? x[e] + (step * (xp[e] / nrm)) : 0.0;
     }
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false>(P, lane, xp, gdummy, lpf, Ssm);
+    model_eval<FAM, G, NPL, false, true, FAM == FAM_GAUSS_PREC>(P, lane, xp, gdummy, lpf);
     double t = 0.234;
     if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
     const double thresh = lpf - P.lp[c];
@@ -784,17 +791,14 @@ template <int FAM, int G, int NPL, bool HAS_HMC>
 __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 4 : (HAS_HMC ? QSB_WARP_BLOCKS : 3))
 advance_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
-  const double* Ssm = nullptr;
   if (FAM == FAM_GAUSS_PREC) {
     extern __shared__ double qsb_zbuf[];
     double* sS = qsb_zbuf + (size_t)Chain<FAM, G, NPL>::NB * blockDim.x;   // after the Gaussian staging columns
     for (int t = threadIdx.x; t < NPL * NPL; t += blockDim.x) sS[t] = P.Sc[t & 255];
     __syncthreads();
-    Ssm = sS;
   }
   const bool active = grp < P.C;               // whole warps: C*G and the block size are multiples of 32 or the tail warp idles
   Chain<FAM, G, NPL> ch(P, active ? grp : 0);
-  ch.Ssm = Ssm;
   if (active)
     for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC>(it);
   ch.flush_counts();
