@@ -72,9 +72,9 @@ struct qsb_sampler {
 };
 
 // ---------------------------------------------------------------------------------------------
-__global__ void precompute_obs_kernel(const double* sigma, double* cy, double* s2, int n) {
+__global__ void precompute_obs_kernel(const double* sigma, double* cy, double* s2, double* is2, int n) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) { double s = sigma[j]; cy[j] = 1.8378770664093453 + 2.0 * log(s); s2[j] = s * s; }
+  if (j < n) { double s = sigma[j]; cy[j] = 1.8378770664093453 + 2.0 * log(s); s2[j] = s * s; is2[j] = 1.0 / (s * s); }
 }
 
 // device sample layout -> AoS Sample elements { value[retdim], logprob, loglikelihood } (infer.t:13-18)
@@ -234,13 +234,14 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
     }
     case QSB_FAM_EIGHT_SCHOOLS: {
       if (!d->y || !d->sigma || d->nobs <= 0 || d->dim != d->nobs + 2) return bail(3, "EIGHT_SCHOOLS: y, sigma required and dim == nobs + 2");
-      double *y, *sg, *cy, *s2;
-      if (m->arena.alloc(&y, d->nobs) || m->arena.alloc(&sg, d->nobs) || m->arena.alloc(&cy, d->nobs) || m->arena.alloc(&s2, d->nobs)) return bail(4, "cudaMalloc failed");
+      double *y, *sg, *cy, *s2, *is2;
+      if (m->arena.alloc(&y, d->nobs) || m->arena.alloc(&sg, d->nobs) || m->arena.alloc(&cy, d->nobs) || m->arena.alloc(&s2, d->nobs) ||
+          m->arena.alloc(&is2, d->nobs)) return bail(4, "cudaMalloc failed");
       cudaMemcpy(y, d->y, sizeof(double) * d->nobs, cudaMemcpyHostToDevice);
       cudaMemcpy(sg, d->sigma, sizeof(double) * d->nobs, cudaMemcpyHostToDevice);
-      precompute_obs_kernel<<<(d->nobs + 127) / 128, 128>>>(sg, cy, s2, d->nobs);
+      precompute_obs_kernel<<<(d->nobs + 127) / 128, 128>>>(sg, cy, s2, is2, d->nobs);
       if (cudaDeviceSynchronize() != cudaSuccess) return bail(6, "precompute_obs_kernel failed");
-      m->dev.y = y; m->dev.cy = cy; m->dev.s2 = s2; m->sigma_dev = sg;
+      m->dev.y = y; m->dev.cy = cy; m->dev.s2 = s2; m->dev.is2 = is2; m->sigma_dev = sg;
       break;
     }
     case QSB_FAM_FUNNEL: break;
@@ -265,7 +266,7 @@ int qsb_model_update_data(qsb_model* m, const qsb_model_desc* d, void* stream) {
     if (!d->y || !d->sigma) return fail(3, "EIGHT_SCHOOLS: y, sigma required");
     CU(cudaMemcpyAsync((void*)m->dev.y, d->y, sizeof(double) * d->nobs, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync((void*)m->sigma_dev, d->sigma, sizeof(double) * d->nobs, cudaMemcpyHostToDevice, st));
-    precompute_obs_kernel<<<(d->nobs + 127) / 128, 128, 0, st>>>(m->sigma_dev, (double*)m->dev.cy, (double*)m->dev.s2, d->nobs);
+    precompute_obs_kernel<<<(d->nobs + 127) / 128, 128, 0, st>>>(m->sigma_dev, (double*)m->dev.cy, (double*)m->dev.s2, (double*)m->dev.is2, d->nobs);
     CU(cudaGetLastError());
     return 0;
   }

@@ -40,7 +40,7 @@ struct ModelDev {
   const int* erp_kind; const double* p0; const double* p1;   // INDEP
   // EIGHT_SCHOOLS observations, precomputed once per model with the same device operations the
   // per-term logprob would use (bit-identical): cy = 1.8378770664093453 + 2*log(sigma), s2 = sigma*sigma
-  const double* y; const double* cy; const double* s2;
+  const double* y; const double* cy; const double* s2; const double* is2;   // is2 = 1/s2
 };
 
 struct EngineParams {
@@ -167,25 +167,31 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
     const double tau = exp(lt);
     const double tau2 = tau * tau;
     const double c_th = LP ? 1.8378770664093453 + 2.0 * log(tau) : 0.0;
+    const double inv_tau2 = 1.0 / tau2;
     double lp = 0.0, gmu = 0.0, glt = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
       if (i >= 2 && i < d) {
         int j = i - 2;
-        double yj = m.y[j], s2 = m.s2[j];
         double th = x[e];
         double r = th - mu;
-        double r2t = r * r / tau2;
-        double ry = yj - th;
-        if (LP) {
+        double ry = m.y[j] - th;
+        if (LP) {   // evaluations whose log-density is used: the reference's expressions, division for division
+          double s2 = m.s2[j];
+          double r2t = r * r / tau2;
           lp += -.5 * (c_th + r2t);
           lp += -.5 * (m.cy[j] + ry * ry / s2);
-        }
-        if (GRAD) {
-          double rt = r / tau2;
-          g[e] = -rt + ry / s2;
+          if (GRAD) {
+            double rt = r / tau2;
+            g[e] = -rt + ry / s2;
+            gmu += rt;
+            glt += -1.0 + r2t;
+          }
+        } else if (GRAD) {   // inside a trajectory only the gradient is needed: reciprocals instead of divisions (<= 1 ulp apart)
+          double rt = r * inv_tau2;
+          g[e] = -rt + ry * m.is2[j];
           gmu += rt;
-          glt += -1.0 + r2t;
+          glt += -1.0 + r * rt;
         }
       } else if (GRAD) g[e] = 0.0;
     }
@@ -209,14 +215,20 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
     const double s = exp(v / 2.0);
     const double s2 = s * s;
     const double c_x = LP ? 1.8378770664093453 + 2.0 * log(s) : 0.0;
+    const double inv_s2 = 1.0 / s2;
     double lp = 0.0, gv = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
       if (i >= 1 && i < d) {
         double xi = x[e];
-        double q = xi * xi / s2;
-        if (LP) lp += -.5 * (c_x + q);
-        if (GRAD) { g[e] = -xi / s2; gv += -0.5 + 0.5 * q; }
+        if (LP) {
+          double q = xi * xi / s2;
+          lp += -.5 * (c_x + q);
+          if (GRAD) { g[e] = -xi / s2; gv += -0.5 + 0.5 * q; }
+        } else if (GRAD) {   // inside a trajectory: one reciprocal per evaluation instead of two divisions per component
+          double t = xi * inv_s2;
+          g[e] = -t; gv += -0.5 + 0.5 * (xi * t);
+        }
       } else if (GRAD) g[e] = 0.0;
     }
     if (LP) {
@@ -379,23 +391,18 @@ template <int FAM, int G, int NPL> struct Chain {
   // ---- searchForInitialStepSize (hmc.t:345-391).  x, g are the current position / gradient in HBM.
   __device__ __forceinline__ double search_step_size(double eps, double dual_lp) const {
     double xs[NPL], gs[NPL], p[NPL];   // own scratch: arrays passed by reference into a call would be forced into local memory
-    uint32_t probe = 0;
     const double LOG_HALF = log(0.5);
-    load(P.x, xs); load(P.g, gs);
-    sample_momenta(QSB_ITER_SEARCH + probe++, p);
     double prevlp = dual_lp;
-    double lp = leapfrog(eps, xs, gs, p);
-    double H = lp - prevlp;
-    prevlp = lp;
-    int direction = H > LOG_HALF ? 1 : -1;
-    unsigned long long evals = 1;
-    while (true) {
+    int direction = 0;
+    unsigned long long evals = 0;
+    for (uint32_t probe = 0;; ++probe) {     // one leapfrog call site for the first probe and the doubling/halving loop
       load(P.x, xs); load(P.g, gs);
-      sample_momenta(QSB_ITER_SEARCH + probe++, p);
-      lp = leapfrog(eps, xs, gs, p);
+      sample_momenta(QSB_ITER_SEARCH + probe, p);
+      const double lp = leapfrog(eps, xs, gs, p);
       ++evals;
-      H = lp - prevlp;      // hmc.t:357: dualTrace.logprob is the previous probe's value
+      const double H = lp - prevlp;      // hmc.t:349-351, 357: dualTrace.logprob is the previous probe's value
       prevlp = lp;
+      if (probe == 0) { direction = H > LOG_HALF ? 1 : -1; continue; }
       if (!(lp == lp)) { if (leader()) atomicOr(P.status, ERR_NAN_SEARCH); break; }
       if (direction == 1 && H <= LOG_HALF) break;
       else if (direction == -1 && H >= LOG_HALF) break;
