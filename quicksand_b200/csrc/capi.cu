@@ -302,7 +302,6 @@ static int alloc_engine_state(qsb_sampler* s) {
   A(a.alloc(&P.x, C * d)); A(a.alloc(&P.lp, C)); A(a.alloc(&P.flags, C));
   A(a.alloc(&P.eps, C));   // also the lp_float output of the logp_grad test hook
   A(a.alloc(&P.g, C * d));
-  if (has_drift || has_harm) A(a.alloc(&P.xs, C * d));
   if (has_hmc) {
     A(a.alloc(&P.da_gbar, C)); A(a.alloc(&P.da_xbar, C)); A(a.alloc(&P.da_x0, C)); A(a.alloc(&P.da_lastx, C)); A(a.alloc(&P.da_gamma, C));
     A(a.alloc(&P.da_k, C));

@@ -55,7 +55,6 @@ struct EngineParams {
   double Sc[16 * 16];               // GAUSS_PREC: A + A^T padded to stride NPL, read from the constant bank
   // chain state
   double *x, *g, *lp;
-  double* xs;                       // proposal scratch of the streaming Drift / HARM kernels, like x
   uint8_t* flags;
   double *eps, *da_gbar, *da_xbar, *da_x0, *da_lastx, *da_gamma;
   uint32_t* da_k;
@@ -250,27 +249,32 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
 // no per-lane vectors in registers and runs at 3 blocks per SM instead of 1.  The per-lane accumulation order equals
 // model_eval's (components ascending, then the warp butterfly), so both forms give bit-identical sums.
 template <int FAM> struct ModelStream {
-  double g0, g1, a, b;   // component 0 and 1 of the proposal and two derived scalars
+  double g0, g1, a, b;   // component 0 and 1 of the proposal and two derived scalars (a is a reciprocal)
+  struct Obs { double y, cy, is2; };   // per-component observation data, fetched ahead of use
   __device__ __forceinline__ void prep(const EngineParams& P, double x0, double x1) {
     g0 = x0; g1 = x1; a = 0.0; b = 0.0;
-    if (FAM == FAM_EIGHT_SCHOOLS) { const double tau = exp(x1); a = tau * tau; b = 1.8378770664093453 + 2.0 * log(tau); }
-    if (FAM == FAM_FUNNEL) { const double s = exp(x0 / 2.0); a = s * s; b = 1.8378770664093453 + 2.0 * log(s); }
+    if (FAM == FAM_EIGHT_SCHOOLS) { const double tau = exp(x1); a = 1.0 / (tau * tau); b = 1.8378770664093453 + 2.0 * log(tau); }
+    if (FAM == FAM_FUNNEL) { const double s = exp(x0 / 2.0); a = 1.0 / (s * s); b = 1.8378770664093453 + 2.0 * log(s); }
   }
-  // adds component i's terms to lp, in model_eval's order
-  __device__ __forceinline__ void term(const EngineParams& P, int i, double xi, double& lp) const {
+  __device__ __forceinline__ void fetch(const EngineParams& P, int i, int d, Obs& o) const {
+    o.y = 0.0; o.cy = 0.0; o.is2 = 0.0;
+    if (FAM == FAM_EIGHT_SCHOOLS && i >= 2 && i < d) { o.y = P.m.y[i - 2]; o.cy = P.m.cy[i - 2]; o.is2 = P.m.is2[i - 2]; }
+  }
+  // adds component i's terms to lp, in model_eval's order.  Quotients by chain-level or per-observation constants are
+  // products with their reciprocals here (<= 1 ulp per term from the reference's divisions).
+  __device__ __forceinline__ void term(const EngineParams& P, int i, double xi, const Obs& o, double& lp) const {
     if (FAM == FAM_INDEP) {
       double lpy, lj, gi;
       erp_eval(P.m.erp_kind[i], xi, P.m.p0[i], P.m.p1[i], lpy, lj, gi);
       lp += lpy;
     } else if (FAM == FAM_EIGHT_SCHOOLS) {
       if (i >= 2) {
-        const int j = i - 2;
-        const double r = xi - g0, ry = P.m.y[j] - xi;
-        lp += -.5 * (b + r * r / a);
-        lp += -.5 * (P.m.cy[j] + ry * ry / P.m.s2[j]);
+        const double r = xi - g0, ry = o.y - xi;
+        lp += -.5 * (b + r * r * a);
+        lp += -.5 * (o.cy + ry * ry * o.is2);
       }
     } else if (FAM == FAM_FUNNEL) {
-      if (i >= 1) lp += -.5 * (b + xi * xi / a);
+      if (i >= 1) lp += -.5 * (b + xi * xi * a);
     }
   }
   __device__ __forceinline__ double finish(double lp_sum) const {
@@ -279,6 +283,47 @@ template <int FAM> struct ModelStream {
     return lp_sum;
   }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Standard-normal draws z_j = v/u (distrib.t:64-74 with mu = 0, sigma = 1) of the n components [32*row_begin, 32*row_begin + n)
+// of ONE chain's iteration, by the 32 lanes of the chain's warp.  Component j reads sub-stream (chain, iter, slot = j) and
+// accepts its first Leva pair that passes -- which pair that is does not depend on who evaluates it, so the lanes pull
+// components from a common cursor: every trip of the loop makes 32 attempts for 32 different components and a lane whose
+// attempt passed takes the next unassigned component.  Trips ~ 1.37 n / 32 + a short tail, instead of the maximum over lanes
+// of a lane's own total (1.7 n / 32).  Results go to this warp's columns of the block's staging array: component
+// 32*(row_begin + r) + l -> qsb_zbuf[r * rstride + (warp's first thread) + l], i.e. lane l later reads its own component of row r.
+// One out-of-line copy per kernel (the 10 Philox rounds are inlined in it).
+static __device__ __noinline__ void gaussian_fill_warp(uint32_t k0, uint32_t k1, uint32_t gc, uint32_t iter, int row_begin, int n, int rstride) {
+  extern __shared__ double qsb_zbuf[];
+  double* zw = qsb_zbuf + (threadIdx.x & ~31u);
+  const int lane = (int)(threadIdx.x & 31u);
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t slot0 = (uint32_t)row_begin * 32u;
+  int j = lane, next = 32;
+  uint32_t blk = 0;
+  bool active = j < n;
+  while (__any_sync(0xffffffffu, active)) {
+    bool ok = false;
+    if (active) {
+      uint32_t w[4];
+      philox4x32_10(blk, slot0 + (uint32_t)j, iter, gc, k0, k1, w);
+      const double u = __dsub_rn(1.0, u53(w[0], w[1]));
+      const double v = __dmul_rn(1.7156, __dsub_rn(u53(w[2], w[3]), 0.5));
+      const double x = __dsub_rn(u, 0.449871);
+      const double y = __dadd_rn(fabs(v), 0.386595);
+      const double q = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, __dsub_rn(__dmul_rn(0.196, y), __dmul_rn(0.25472, x))));
+      if (!(q >= 0.27597)) ok = true;
+      else if (q > 0.27846) ok = false;
+      else ok = !(__dmul_rn(v, v) > __dmul_rn(__dmul_rn(__dmul_rn(-4.0, u), u), log(u)));
+      if (ok) zw[(j >> 5) * rstride + (j & 31)] = v / u;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) { j = next + __popc(m & lt); blk = 0; active = j < n; }
+    else ++blk;
+    next += __popc(m);
+  }
+  __syncwarp();
+}
 
 // ---------------------------------------------------------------------------------------------
 template <int FAM, int G, int NPL> struct Chain {
@@ -327,6 +372,11 @@ template <int FAM, int G, int NPL> struct Chain {
   // VU = false: row r (component e_begin + r) <- v/u;  VU = true: row r <- v, row HALF + r <- u
   template <bool VU>
   __device__ __forceinline__ void gaussian_fill(uint32_t iter, int e_begin, int e_end) const {
+    if (G == 32 && !VU) {   // warp per chain: the lanes share the attempts of all components of these rows
+      const int hi = e_end * 32 < d ? e_end * 32 : d;
+      gaussian_fill_warp(P.key.k0, P.key.k1, gc, iter, e_begin, hi - e_begin * 32, (int)blockDim.x);
+      return;
+    }
     double* z = zcol();
     const int stride = blockDim.x;
     int e = e_begin;
@@ -602,7 +652,12 @@ template <int FAM, int G, int NPL> struct Chain {
     return accept;
   }
 
-  // ---- warp-per-chain streaming forms of the two Metropolis kernels (same operations, no register vectors)
+  // ---- warp-per-chain streaming forms of the two Metropolis kernels: no per-lane vectors in registers, the proposal is
+  // never written to HBM (on acceptance it is recomputed from the staged Gaussians with the same operations), global
+  // loads are issued RB rows ahead of their use.  Against the register forms above (and the reference's expression
+  // order) three quotients become products with a reciprocal -- sigma*(v/u) for (sigma*v)/u, m2*(1/(n-1)), (x-mean)*(1/n),
+  // z*(1/norm) -- each within 1 ulp.
+  static constexpr int RB = 4;
   __device__ __forceinline__ bool drift_next_stream(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
     const bool adapting = P.doAdapt[k] != 0;
     const size_t kc = (size_t)k * P.C + c;
@@ -612,28 +667,39 @@ template <int FAM, int G, int NPL> struct Chain {
     const double* z = zcol();
     const int stride = blockDim.x;
     const int ne = (d + G - 1) / G;                     // component rows of this chain
+    const size_t base = (size_t)c * d;
+    const double* __restrict__ xr = P.x + base;
+    const bool use_var = n_rv > 100;                    // scale = varEst:getStdDev() [* 0.99]  (drift.t:288-298)
+    const double inv_nm1 = use_var ? 1.0 / (double)(n_rv - 1) : 0.0;
+    gaussian_fill<false>(iter, 0, ne);
     ModelStream<FAM> ms;
     double lp = 0.0;
-    for (int h = 0; h < 2; ++h) {
-      const int e0 = h * HALF, e1 = min(e0 + HALF, ne);
-      gaussian_fill<true>(iter, e0, e1);
-      for (int e = e0; e < e1; ++e) {
-        const int i = e * G + lane;
-        double xpi = 0.0;
-        if (i < d) {
-          const size_t ix = vidx<G>(P, i, c);
-          double sc = s0;
-          if (n_rv > 100) {   // scale = varEst:getStdDev() [* 0.99]  (drift.t:288-298)
-            sc = sqrt(P.dr_m2[ix] / (double)(n_rv - 1));
-            if (mult != 1.0) sc = sc * mult;
-          }
-          xpi = __dadd_rn(P.x[ix], __dmul_rn(sc, z[(e - e0) * stride]) / z[(HALF + e - e0) * stride]);
-          P.xs[ix] = xpi;
-        }
-        if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
-        if (i < d) ms.term(P, i, xpi, lp);
+    for (int e0 = 0; e0 < ne; e0 += RB) {
+      double xv[RB], mv[RB];
+      typename ModelStream<FAM>::Obs ob[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int i = (e0 + r) * G + lane;
+        const bool ok = i < d;
+        xv[r] = ok ? xr[i] : 0.0;
+        mv[r] = (ok && use_var) ? P.dr_m2[base + i] : 0.0;
+        ms.fetch(P, i, d, ob[r]);
       }
-      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int e = e0 + r;
+        if (e < ne) {
+          const int i = e * G + lane;
+          double xpi = 0.0;
+          if (i < d) {
+            double sc = s0;
+            if (use_var) { sc = sqrt(mv[r] * inv_nm1); if (mult != 1.0) sc = sc * mult; }
+            xpi = __dadd_rn(xv[r], __dmul_rn(sc, z[e * stride]));
+          }
+          if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
+          if (i < d) ms.term(P, i, xpi, ob[r], lp);
+        }
+      }
     }
     rec_step = s0;
     const double lpf = ms.finish(Grp<G>::sum(lp));
@@ -646,24 +712,44 @@ template <int FAM, int G, int NPL> struct Chain {
     const bool upd = adapting && ratio >= 0.05 && acc > 5;   // RunningVar:update with the current state (drift.t:26-37, 279-284)
     const uint32_t n_new = upd ? n_rv + 1 : n_rv;
     if (accept || upd) {
-      for (int e = 0; e < ne; ++e) {
-        const int i = e * G + lane;
-        if (i < d) {
-          const size_t ix = vidx<G>(P, i, c);
-          double cur;
-          if (accept) { cur = P.xs[ix]; P.x[ix] = cur; } else cur = P.x[ix];
-          if (upd) {
-            if (n_new == 1) { P.dr_mean[ix] = cur; P.dr_m2[ix] = 0.0; }
-            else {
-              const double mean = P.dr_mean[ix];
-              const double newmean = mean + (cur - mean) / (double)n_new;
-              P.dr_m2[ix] = P.dr_m2[ix] + (cur - mean) * (cur - newmean);
-              P.dr_mean[ix] = newmean;
+      const double inv_n = 1.0 / (double)n_new;
+      double* __restrict__ xw = P.x + base;
+      for (int e0 = 0; e0 < ne; e0 += RB) {
+        double xv[RB], mv[RB], av[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int i = (e0 + r) * G + lane;
+          const bool ok = i < d;
+          xv[r] = ok ? xw[i] : 0.0;
+          mv[r] = (ok && (use_var || (upd && n_new != 1))) ? P.dr_m2[base + i] : 0.0;
+          av[r] = (ok && upd && n_new != 1) ? P.dr_mean[base + i] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int e = e0 + r;
+          const int i = e * G + lane;
+          if (e < ne && i < d) {
+            double cur = xv[r];
+            if (accept) {   // the accepted proposal, recomputed exactly as it was scored
+              double sc = s0;
+              if (use_var) { sc = sqrt(mv[r] * inv_nm1); if (mult != 1.0) sc = sc * mult; }
+              cur = __dadd_rn(xv[r], __dmul_rn(sc, z[e * stride]));
+              xw[i] = cur;
+            }
+            if (upd) {
+              if (n_new == 1) { P.dr_mean[base + i] = cur; P.dr_m2[base + i] = 0.0; }
+              else {
+                const double mean = av[r];
+                const double newmean = mean + (cur - mean) * inv_n;
+                P.dr_m2[base + i] = mv[r] + (cur - mean) * (cur - newmean);
+                P.dr_mean[base + i] = newmean;
+              }
             }
           }
         }
       }
     }
+    __syncwarp();
     if (leader()) {
       if (accept) { P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID; }
       if (adapting) {
@@ -683,6 +769,8 @@ template <int FAM, int G, int NPL> struct Chain {
     const double* z = zcol();
     const int stride = blockDim.x;
     const int ne = (d + G - 1) / G;
+    const size_t base = (size_t)c * d;
+    double* __restrict__ xw = P.x + base;
     gaussian_fill<false>(iter, 0, ne);
     double nrm = 0.0;
     for (int e = 0; e < ne; ++e) { if (e * G + lane < d) { const double zi = z[e * stride]; nrm += zi * zi; } }
@@ -690,18 +778,29 @@ template <int FAM, int G, int NPL> struct Chain {
     const double hscale = P.ha_scale[c];
     rec_step = hscale;
     const double step = uniform_at(P.key, gc, iter, (uint32_t)d) * hscale;
+    const double sn = step * (1.0 / nrm);      // x' = x + step*(z/norm) (harm.t:78-79) as x + (step/norm)*z
     ModelStream<FAM> ms;
     double lp = 0.0;
-    for (int e = 0; e < ne; ++e) {
-      const int i = e * G + lane;
-      double xpi = 0.0;
-      if (i < d) {
-        const size_t ix = vidx<G>(P, i, c);
-        xpi = P.x[ix] + (step * (z[e * stride] / nrm));
-        P.xs[ix] = xpi;
+    for (int e0 = 0; e0 < ne; e0 += RB) {
+      double xv[RB];
+      typename ModelStream<FAM>::Obs ob[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int i = (e0 + r) * G + lane;
+        xv[r] = i < d ? xw[i] : 0.0;
+        ms.fetch(P, i, d, ob[r]);
       }
-      if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
-      if (i < d) ms.term(P, i, xpi, lp);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int e = e0 + r;
+        if (e < ne) {
+          const int i = e * G + lane;
+          double xpi = 0.0;
+          if (i < d) xpi = fma(sn, z[e * stride], xv[r]);
+          if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
+          if (i < d) ms.term(P, i, xpi, ob[r], lp);
+        }
+      }
     }
     const double lpf = ms.finish(Grp<G>::sum(lp));
     double t = 0.234;
@@ -712,11 +811,18 @@ template <int FAM, int G, int NPL> struct Chain {
     const bool accept = log(u) < thresh;
     double ns = hscale;
     if (accept) {
-      for (int e = 0; e < ne; ++e) { const int i = e * G + lane; if (i < d) { const size_t ix = vidx<G>(P, i, c); P.x[ix] = P.xs[ix]; } }
+      for (int e0 = 0; e0 < ne; e0 += RB) {
+        double xv[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) { const int i = (e0 + r) * G + lane; xv[r] = i < d ? xw[i] : 0.0; }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) { const int e = e0 + r; const int i = e * G + lane; if (e < ne && i < d) xw[i] = fma(sn, z[e * stride], xv[r]); }
+      }
       if (adapting) ns = hscale + (hscale / (t * (1.0 - t))) * (1.0 - t) / (double)(iter + 1u);
     } else {
       if (adapting) ns = fabs(hscale - (hscale / (t * (1.0 - t))) * t / (double)(iter + 1u));
     }
+    __syncwarp();
     if (leader()) {
       P.made[kc] += 1;
       if (accept) { P.acc[kc] += 1; P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID; }
