@@ -30,9 +30,6 @@ enum { K_HMC = 1, K_DRIFT = 2, K_HARM = 3 };
 enum { FLAG_HMC_INIT = 1, FLAG_GRAD_VALID = 2 };
 enum { ERR_NAN_SEARCH = 1, ERR_SEARCH_INF = 2, ERR_SEARCH_ZERO = 4 };
 static constexpr int MAX_SUB = 8;
-#ifndef QSB_WARP_BLOCKS
-#define QSB_WARP_BLOCKS 2   // resident 256-thread blocks per SM of the warp-per-chain kernels (register cap 128)
-#endif
 
 struct ModelDev {
   int family, dim, nobs, ret_mode;
@@ -242,6 +239,47 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
     return lp;
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Gradient of the hierarchical families from chain-level scalars.  For FUNNEL and EIGHT_SCHOOLS every component's
+// gradient is a function of that component, two reduced scalars and (EIGHT_SCHOOLS) its observation, so the
+// warp-per-chain HMC trajectory keeps positions and momenta in registers and NO gradient vector: 2*NPL instead of
+// 3*NPL doubles per lane, which is what lets n = 1000 run without register spills.  Operation for operation the
+// in-trajectory (GRAD && !LP) branch of model_eval.
+template <int FAM> struct GradScalars {
+  double a, b, g0, g1;   // FUNNEL: a = 1/s^2, g0 = d/dv.  EIGHT_SCHOOLS: a = mu, b = 1/tau^2, g0 = d/dmu, g1 = d/dlogtau
+  template <int G, int NPL> __device__ __forceinline__ void reduce(const EngineParams& P, int lane, const double (&x)[NPL]) {
+    const int d = P.m.dim;
+    if (FAM == FAM_FUNNEL) {
+      const double v = Grp<G>::bcast(x[0], 0);
+      const double s = exp(v / 2.0);
+      const double s2 = s * s;
+      a = 1.0 / s2; b = 0.0; g1 = 0.0;
+      double gv = 0.0;
+      QSB_FOR_E { int i = e * G + lane; if (i >= 1 && i < d) { const double t = x[e] * a; gv += -0.5 + 0.5 * (x[e] * t); } }
+      g0 = -v / 9.0 + Grp<G>::sum(gv);
+    } else {
+      const double mu = Grp<G>::bcast(x[0], 0), lt = Grp<G>::bcast(x[0], 1);
+      const double tau = exp(lt);
+      const double tau2 = tau * tau;
+      a = mu; b = 1.0 / tau2;
+      double gmu = 0.0, glt = 0.0;
+      QSB_FOR_E { int i = e * G + lane; if (i >= 2 && i < d) { const double r = x[e] - mu; const double rt = r * b; gmu += rt; glt += -1.0 + r * rt; } }
+      g0 = -mu / 25.0 + Grp<G>::sum(gmu);
+      g1 = -lt + Grp<G>::sum(glt);
+    }
+  }
+  // gradient of component i at value xi
+  __device__ __forceinline__ double elem(const EngineParams& P, int i, double xi) const {
+    const int d = P.m.dim;
+    if (i >= d) return 0.0;
+    if (FAM == FAM_FUNNEL) return i == 0 ? g0 : -(xi * a);
+    if (i == 0) return g0;
+    if (i == 1) return g1;
+    const double rt = (xi - a) * b;
+    return -rt + (P.m.y[i - 2] - xi) * P.m.is2[i - 2];
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // The float-trace log-density as a stream over components (what Drift / HARM score: erp.t:361, no Jacobian), for the
@@ -526,6 +564,105 @@ template <int FAM, int G, int NPL> struct Chain {
     return accept;
   }
 
+  // ---- HMCKernel:next for the warp-per-chain hierarchical families: positions and momenta in registers, the gradient
+  // recomputed from GradScalars at every kick (two kicks per evaluation inside a trajectory, hmc.t:307-323 kept as two
+  // separate half-kicks).  The cached gradient of the reference (hmc.t:82-101) is a function of the cached position, so
+  // it is not stored.
+  static constexpr bool SCALAR_GRAD = G == 32 && (FAM == FAM_FUNNEL || FAM == FAM_EIGHT_SCHOOLS);
+  __device__ __forceinline__ void kick(double he, const GradScalars<FAM>& gs, const double (&x)[NPL], double (&p)[NPL], bool twice) const {
+    QSB_FOR_E {
+      const double g = gs.elem(P, e * G + lane, x[e]);
+      p[e] = p[e] + he * g;
+      if (twice) p[e] = p[e] + he * g;
+    }
+  }
+  __device__ __forceinline__ double lp_only(const double (&x)[NPL]) const {
+    double lpf, gd[NPL];
+    return model_eval<FAM, G, NPL, false, true, false>(P, lane, x, gd, lpf);
+  }
+  __device__ __forceinline__ double search_step_size_warp(double eps, double dual_lp) const {
+    double x[NPL], p[NPL];
+    const double LOG_HALF = log(0.5);
+    double prevlp = dual_lp;
+    int direction = 0;
+    unsigned long long evals = 0;
+    GradScalars<FAM> gs;
+    for (uint32_t probe = 0;; ++probe) {
+      load(P.x, x);
+      sample_momenta(QSB_ITER_SEARCH + probe, p);
+      gs.template reduce<G, NPL>(P, lane, x);
+      kick(0.5 * eps, gs, x, p, false);
+      QSB_FOR_E x[e] = x[e] + eps * p[e] * 1.0;
+      const double lp = lp_only(x);
+      ++evals;
+      const double H = lp - prevlp;      // hmc.t:349-351, 357: dualTrace.logprob is the previous probe's value
+      prevlp = lp;
+      if (probe == 0) { direction = H > LOG_HALF ? 1 : -1; continue; }
+      if (!(lp == lp)) { if (leader()) atomicOr(P.status, ERR_NAN_SEARCH); break; }
+      if (direction == 1 && H <= LOG_HALF) break;
+      else if (direction == -1 && H >= LOG_HALF) break;
+      else if (direction == 1) eps = eps * 2.0;
+      else eps = eps * 0.5;
+      if (eps > 1e300) { if (leader()) atomicOr(P.status, ERR_SEARCH_INF); break; }
+      if (eps == 0) { if (leader()) atomicOr(P.status, ERR_SEARCH_ZERO); break; }
+    }
+    count(0, evals);
+    return eps;
+  }
+  __device__ __forceinline__ bool hmc_next_warp(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    double x[NPL], p[NPL];
+    const bool adapting = P.doAdapt[k] != 0;
+    const uint32_t L = P.numSteps[k];
+    const double target = L == 1 ? 0.574 : 0.65;
+    if (leader()) P.made[(size_t)k * P.C + c] += 1;
+    uint8_t fl = P.flags[c];
+    double eps = P.eps[c];
+    if (!(fl & FLAG_GRAD_VALID)) {   // checkForChanges (hmc.t:188-287): the reference re-evaluates the gradient here
+      count(0, 1);
+      if (!(fl & FLAG_HMC_INIT) && adapting) {
+        load(P.x, x);
+        const double dual_lp = lp_only(x);
+        __syncwarp();
+        eps = search_step_size_warp(eps, dual_lp);
+        if (leader()) {   // adapter:reinit(stepSize, adaptRate) (hmc.t:261)
+          P.da_k[c] = 0; P.da_x0[c] = eps; P.da_lastx[c] = eps; P.da_gbar[c] = 0.0; P.da_xbar[c] = 0.0; P.da_gamma[c] = 0.05;
+        }
+        __syncwarp();
+      }
+      fl |= FLAG_HMC_INIT | FLAG_GRAD_VALID;
+    }
+    load(P.x, x);
+    sample_momenta(iter, p);
+    const double H = kinetic(p) + P.lp[c];
+    rec_step = eps;
+    const double he = 0.5 * eps;
+    GradScalars<FAM> gs;
+    gs.template reduce<G, NPL>(P, lane, x);
+    kick(he, gs, x, p, false);
+    for (uint32_t s = 0; s < L; ++s) {
+      QSB_FOR_E x[e] = x[e] + eps * p[e] * 1.0;
+      gs.template reduce<G, NPL>(P, lane, x);
+      kick(he, gs, x, p, s + 1 < L);
+      if (P.rec_leap) {
+        size_t base = (((size_t)c * P.rec_iters + (iter - P.it_begin)) * L + s) * d;
+        QSB_FOR_E { int i = e * G + lane; if (i < d) P.rec_leap[base + i] = x[e]; }
+      }
+    }
+    const double newlp = lp_only(x);
+    count(0, L); count(1, L);
+    const double dH = (kinetic(p) + newlp) - H;
+    rec_dh = dH;
+    if (adapting) eps = adapt_step_size(dH, target);
+    const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
+    const bool accept = log(u) < dH;
+    if (accept) {
+      store(P.x, x);
+      if (leader()) { P.acc[(size_t)k * P.C + c] += 1; P.lp[c] = newlp; }
+    }
+    if (leader()) { P.eps[c] = eps; P.flags[c] = fl; }
+    return accept;
+  }
+
   // ---- DriftKernel:next + adapt (drift.t:133-172, 274-300), lexicalScaleSharing = false
   __device__ __forceinline__ bool drift_next(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
     double x[NPL], xp[NPL];
@@ -674,17 +811,24 @@ template <int FAM, int G, int NPL> struct Chain {
     gaussian_fill<false>(iter, 0, ne);
     ModelStream<FAM> ms;
     double lp = 0.0;
-    for (int e0 = 0; e0 < ne; e0 += RB) {
-      double xv[RB], mv[RB];
-      typename ModelStream<FAM>::Obs ob[RB];
+    // x and m2 of rows e0+RB.. are requested while rows e0.. are scored (double buffer in registers); the observation
+    // data are model constants shared by every chain (L1 hits) and are read at their use
+    double xn[RB], mn[RB];
+    auto load_rows = [&](int e0) {
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const int i = (e0 + r) * G + lane;
         const bool ok = i < d;
-        xv[r] = ok ? xr[i] : 0.0;
-        mv[r] = (ok && use_var) ? P.dr_m2[base + i] : 0.0;
-        ms.fetch(P, i, d, ob[r]);
+        xn[r] = ok ? xr[i] : 0.0;
+        mn[r] = (ok && use_var) ? P.dr_m2[base + i] : 0.0;
       }
+    };
+    load_rows(0);
+    for (int e0 = 0; e0 < ne; e0 += RB) {
+      double xv[RB], mv[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) { xv[r] = xn[r]; mv[r] = mn[r]; }
+      if (e0 + RB < ne) load_rows(e0 + RB);
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const int e = e0 + r;
@@ -697,7 +841,7 @@ template <int FAM, int G, int NPL> struct Chain {
             xpi = __dadd_rn(xv[r], __dmul_rn(sc, z[e * stride]));
           }
           if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
-          if (i < d) ms.term(P, i, xpi, ob[r], lp);
+          if (i < d) { typename ModelStream<FAM>::Obs ob; ms.fetch(P, i, d, ob); ms.term(P, i, xpi, ob, lp); }
         }
       }
     }
@@ -783,13 +927,8 @@ template <int FAM, int G, int NPL> struct Chain {
     double lp = 0.0;
     for (int e0 = 0; e0 < ne; e0 += RB) {
       double xv[RB];
-      typename ModelStream<FAM>::Obs ob[RB];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const int i = (e0 + r) * G + lane;
-        xv[r] = i < d ? xw[i] : 0.0;
-        ms.fetch(P, i, d, ob[r]);
-      }
+      for (int r = 0; r < RB; ++r) { const int i = (e0 + r) * G + lane; xv[r] = i < d ? xw[i] : 0.0; }
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
         const int e = e0 + r;
@@ -798,7 +937,7 @@ template <int FAM, int G, int NPL> struct Chain {
           double xpi = 0.0;
           if (i < d) xpi = fma(sn, z[e * stride], xv[r]);
           if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
-          if (i < d) ms.term(P, i, xpi, ob[r], lp);
+          if (i < d) { typename ModelStream<FAM>::Obs ob; ms.fetch(P, i, d, ob); ms.term(P, i, xpi, ob, lp); }
         }
       }
     }
@@ -849,7 +988,10 @@ template <int FAM, int G, int NPL> struct Chain {
     bool accept;
     const int kind = P.kind[k];
     constexpr bool STREAM = G == 32 && FAM != FAM_GAUSS_PREC;
-    if (HAS_HMC && kind == K_HMC) accept = hmc_next(k, iter, rdh, rstep);
+    if (HAS_HMC && kind == K_HMC) {
+      if constexpr (SCALAR_GRAD) accept = hmc_next_warp(k, iter, rdh, rstep);
+      else accept = hmc_next(k, iter, rdh, rstep);
+    }
     else if (kind == K_DRIFT) accept = STREAM ? drift_next_stream(k, iter, rdh, rstep) : drift_next(k, iter, rdh, rstep);
     else accept = STREAM ? harm_next_stream(k, iter, rdh, rstep) : harm_next(k, iter, rdh, rstep);
     if (G == 32) __syncwarp();
@@ -901,7 +1043,7 @@ template <int FAM, int G, int NPL> struct Chain {
 // HAS_HMC = false: the kernel list holds no HMCKernel; the trajectory code (and its register vectors) is not compiled
 // in, which lets the warp-per-chain Drift / HARM kernels run at 3 blocks per SM.
 template <int FAM, int G, int NPL, bool HAS_HMC>
-__global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 4 : (HAS_HMC ? QSB_WARP_BLOCKS : 3))
+__global__ void __launch_bounds__(G == 1 || HAS_HMC ? 128 : 256, G == 1 ? 4 : 3)
 advance_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
   if (FAM == FAM_GAUSS_PREC) {

@@ -8,11 +8,12 @@ namespace qsb {
 template <int FAM, int G, int NPL> struct VariantImpl {
   static constexpr int TPB = G == 1 ? 128 : 256;
   static unsigned grid(const EngineParams& P) { return (unsigned)(((size_t)P.C * G + TPB - 1) / TPB); }
-  static constexpr size_t SMEM = ((size_t)Chain<FAM, G, NPL>::NB * TPB + (FAM == FAM_GAUSS_PREC ? NPL * NPL : 0)) * sizeof(double);   // Gaussian staging columns (+ S)
   template <bool HAS_HMC> static void advance_t(const EngineParams& P, void* st) {
+    constexpr int TPBA = (G == 1 || HAS_HMC) ? 128 : 256;   // must equal advance_kernel's launch bounds
+    constexpr size_t SMEM = ((size_t)Chain<FAM, G, NPL>::NB * TPBA + (FAM == FAM_GAUSS_PREC ? NPL * NPL : 0)) * sizeof(double);   // Gaussian staging columns (+ S)
     static bool attr = false;
     if (!attr && SMEM > 48 * 1024) { cudaFuncSetAttribute(advance_kernel<FAM, G, NPL, HAS_HMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); attr = true; }
-    advance_kernel<FAM, G, NPL, HAS_HMC><<<grid(P), TPB, SMEM, (cudaStream_t)st>>>(P);
+    advance_kernel<FAM, G, NPL, HAS_HMC><<<(unsigned)(((size_t)P.C * G + TPBA - 1) / TPBA), TPBA, SMEM, (cudaStream_t)st>>>(P);
   }
   static void advance(const EngineParams& P, void* st) { advance_t<true>(P, st); }
   static void advance_nohmc(const EngineParams& P, void* st) { advance_t<false>(P, st); }
