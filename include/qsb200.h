@@ -143,6 +143,14 @@ int qsb_sampler_begin(qsb_sampler* s, uint64_t max_samples, uint64_t burnin, uin
 int qsb_sampler_advance(qsb_sampler* s, uint64_t iters);
 uint64_t qsb_sampler_num_samples(const qsb_sampler* s);
 
+/* AnnealingKernel(kernel, annealSched) (mcmc.t:297-319): temps is a HOST array, temps[i] = annealSched(i, numiters)
+ * evaluated by the caller for iterations i = 0..n-1 (the schedule is a Terra function on the host side; later
+ * iterations reuse temps[n-1]).  Iteration i sets the trace temperature to temps[i] before the kernel runs
+ * (trace.t:652-655): every log-density evaluated during it is divided by the temperature (trace.t:737-741), cached
+ * values keep the temperature they were computed under, kept samples store logprob * temperature (mcmc.t:69).
+ * n = 0 (or temps = NULL) removes the schedule (temperature 1).  Call between qsb_sampler_init and run/advance. */
+int qsb_sampler_set_temperatures(qsb_sampler* s, const double* temps, uint64_t n);
+
 /* Copy kept samples into caller-owned memory laid out like S.Vector(Sample(T))._data:
  * element = { double value[retdim]; double logprob; double loglikelihood; }  (infer.t:13-18),
  * element (c - chain_begin_local) * (sample_end - sample_begin) + (k - sample_begin) at dst + that * stride.

@@ -88,6 +88,7 @@ def lib(variant=None):
         ip = C.POINTER(C.c_int32)
         L.qso_run.argtypes = [C.c_void_p, C.POINTER(KernelSpec), C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
                               C.c_uint64, C.c_uint64, C.c_uint64, dp, dp, dp, ip, dp, dp, ip, dp, dp, C.POINTER(Stats)]
+        L.qso_set_temperatures.argtypes = [dp, C.c_uint64]
         L.qso_logp_grad.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp]
         L.qso_expectation.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, dp]
         L.qso_autocorrelation.argtypes = [dp, C.c_int, C.c_int, dp]
@@ -193,9 +194,10 @@ def spec(kind, stepSize=1.0, numSteps=1, doAdapt=True, scale=1.0, weight=1.0):
     return KernelSpec(kind, int(bool(doAdapt)), stepSize, numSteps, scale, weight)
 
 
-def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, record=False):
+def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, record=False, temps=None):
     """doMCMC for each chain.  Returns a dict with samples [C][S][retdim], logprobs and, if
-    ``record``, the per-iteration trace (state, accept, dH, step, kernel index, leapfrog positions)."""
+    ``record``, the per-iteration trace (state, accept, dH, step, kernel index, leapfrog positions).
+    ``temps``: AnnealingKernel schedule, temps[i] = annealSched(i, iters) (qs/mcmc.t:297-319)."""
     if isinstance(specs, KernelSpec):
         specs = [specs]
     arr = (KernelSpec * len(specs))(*specs)
@@ -214,9 +216,12 @@ def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, r
             lf = np.zeros((nchains, iters, specs[0].numSteps, n))
         out.update(state=st, accept=ac, dH=dh, step=ss, kidx=ki, leapfrog=lf, init=init)
     stats = Stats()
+    tarr = np.ascontiguousarray(temps, dtype=np.float64) if temps is not None else None
+    program._lib.qso_set_temperatures(_dp(tarr), 0 if tarr is None else len(tarr))
     rc = program._lib.qso_run(program.h, arr, len(specs), seed, chain_begin, nchains, nsamps, burnin, lag,
                        _dp(samples), _dp(logprobs), _dp(st), _ip(ac), _dp(dh), _dp(ss), _ip(ki), _dp(lf), _dp(init),
                        C.byref(stats))
+    program._lib.qso_set_temperatures(None, 0)
     if rc:
         raise RuntimeError("qso_run failed: %d" % rc)
     out["stats"] = {f: getattr(stats, f) for f, _ in Stats._fields_}

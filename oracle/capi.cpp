@@ -112,6 +112,10 @@ void* qso_program_funnel(int d) {
 void qso_program_free(void* p) { delete (Program*)p; }
 int qso_program_retdim(void* p) { return ((Program*)p)->retdim; }
 
+// AnnealingKernel schedule applied by the following qso_run calls of this thread (n = 0: none)
+static thread_local std::vector<double> g_temps;
+void qso_set_temperatures(const double* temps, uint64_t n) { g_temps.clear(); if (temps && n) g_temps.assign(temps, temps + n); }
+
 static Kernel* make_kernel(const qso_kernel_spec* specs, int nspecs) {
   auto one = [](const qso_kernel_spec& s) -> Kernel* {
     switch (s.kind) {
@@ -155,8 +159,11 @@ int qso_run(void* prog, const qso_kernel_spec* specs, int nspecs, uint64_t seed,
   for (uint32_t c = 0; c < nchains; ++c) {
     r.seed = seed; r.chain = chain_begin + c;
     ad::recoverMemory();
-    std::unique_ptr<Kernel> k(make_kernel(specs, nspecs));
-    if (!k) return 2;
+    Kernel* inner = make_kernel(specs, nspecs);
+    if (!inner) return 2;
+    std::unique_ptr<Kernel> k;
+    if (g_temps.empty()) k.reset(inner);
+    else { AnnealingKernel* a = new AnnealingKernel(); a->k.reset(inner); a->temps = g_temps; k.reset(a); }
     Recorder rec;
     recorder() = want_rec ? &rec : nullptr;
     std::vector<Sample> samps;
@@ -185,9 +192,9 @@ int qso_run(void* prog, const qso_kernel_spec* specs, int nspecs, uint64_t seed,
         std::memcpy(rec_leap + (size_t)c * iters * specs[0].numSteps * n, rec.leapfrog_pos.data(), sizeof(double) * rec.leapfrog_pos.size());
     }
     pm += k->proposalsMade(); pa += k->proposalsAccepted();
-    if (nspecs == 1 && specs[0].kind == 1) ge += ((HMCKernel*)k.get())->gradEvals;
+    if (nspecs == 1 && specs[0].kind == 1) ge += ((HMCKernel*)inner)->gradEvals;
     else if (nspecs > 1) {
-      MixtureKernel* m = (MixtureKernel*)k.get();
+      MixtureKernel* m = (MixtureKernel*)inner;
       for (int i = 0; i < nspecs; ++i) if (specs[i].kind == 1) ge += ((HMCKernel*)m->kernels[i].get())->gradEvals;
     }
   }

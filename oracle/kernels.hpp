@@ -383,9 +383,11 @@ struct MixtureKernel : Kernel {
 };
 
 // ------------------------------------------------------------------ qs/mcmc.t:297-319 (next-row f1)
+// annealSched(iter, numiters) is tabulated by the caller: temps[i] = annealSched(i, numiters).
 struct AnnealingKernel : Kernel {
   std::unique_ptr<Kernel> k;
-  double (*annealSched)(uint32_t, uint32_t) = nullptr;
+  std::vector<double> temps;
+  double annealSched(uint32_t iter, uint32_t) const { return temps[iter < temps.size() ? iter : temps.size() - 1]; }
   void next(Trace<double>* currTrace, uint32_t iter, uint32_t numiters) override {
     currTrace->setTemperature(annealSched(iter, numiters));
     k->next(currTrace, iter, numiters);

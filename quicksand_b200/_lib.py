@@ -61,6 +61,7 @@ PROTOTYPES = {
     "qsb_sampler_begin": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "qsb_sampler_advance": (C.c_int, [C.c_void_p, C.c_uint64]),
     "qsb_sampler_num_samples": (C.c_uint64, [C.c_void_p]),
+    "qsb_sampler_set_temperatures": (C.c_int, [C.c_void_p, dp, C.c_uint64]),
     "qsb_sampler_fetch_samples": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
     "qsb_sampler_fetch_values": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, dp]),
     "qsb_sampler_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),

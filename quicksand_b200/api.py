@@ -6,6 +6,7 @@
     qs.DriftKernel{scale, doScaleAdapt, lexicalScaleSharing}       qs/drift.t:63-73
     qs.HARMKernel{scale, doScaleAdapt}                             qs/harm.t:16-22
     qs.MixtureKernel(kernels, weights)                             qs/mcmc.t:199-291
+    qs.AnnealingKernel(kernel, annealSched)                        qs/mcmc.t:297-319
     qs.Samples / qs.Expectation / qs.Autocorrelation               qs/infer.t:128-136, 146-187, 213-264
 
 Same names, same parameter meaning, same defaults, same error behaviour (the reference aborts with a
@@ -28,8 +29,9 @@ class KernelSpecs:
     """What a kernel constructor yields: the reference returns ``function(TraceType) -> struct``;
     here the spec list the B200 driver reads."""
 
-    def __init__(self, specs, names):
+    def __init__(self, specs, names, anneal=None):
         self.specs, self.names = specs, names
+        self.anneal = anneal      # annealSched(iter, numiters) -> temperature, or None
 
 
 def HMCKernel(params=None, **kw):
@@ -70,10 +72,22 @@ def MixtureKernel(kernels, weights):
     for k, w in zip(kernels, weights):
         if len(k.specs) != 1:
             raise NotImplementedError("MixtureKernel: nested mixtures are not supported")
+        if k.anneal is not None:
+            raise NotImplementedError("MixtureKernel: anneal the mixture (AnnealingKernel(MixtureKernel(...))), not its parts")
         s = k.specs[0]
         specs.append(L.KernelSpec(s.kind, s.doAdapt, s.stepSize, s.numSteps, s.scale, float(w)))
         names.append(k.names[0])
     return KernelSpecs(specs, names)
+
+
+def AnnealingKernel(kernel, annealSched):
+    """Simulated annealing on top of another kernel (qs/mcmc.t:297-319): before every iteration the trace
+    temperature is set to ``annealSched(iter, numiters)`` (any callable of two ints returning a float).  The
+    schedule is host code, as in the reference (a Terra function); it is tabulated once per run and handed to
+    the device as an array (``qsb_sampler_set_temperatures``)."""
+    if kernel.anneal is not None:
+        raise NotImplementedError("AnnealingKernel: nested annealing schedules are not supported")
+    return KernelSpecs(kernel.specs, kernel.names, anneal=annealSched)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -119,12 +133,26 @@ class Sampler:
         L.check(L.lib().qsb_sampler_get_state(self.h, x.ctypes.data_as(L.dp)))
         return x
 
+    def set_temperatures(self, temps):
+        """temps[i] = temperature of iteration i (None removes the schedule)."""
+        if temps is None:
+            L.check(L.lib().qsb_sampler_set_temperatures(self.h, None, 0))
+            return
+        t = np.ascontiguousarray(temps, dtype=np.float64)
+        L.check(L.lib().qsb_sampler_set_temperatures(self.h, t.ctypes.data_as(L.dp), len(t)))
+
+    def _tabulate_schedule(self, numiters):
+        if self.kernel.anneal is not None:
+            self.set_temperatures([float(self.kernel.anneal(i, numiters)) for i in range(numiters)])
+
     def run(self, nsamps, burnin=0, lag=1):
         self._numiters = burnin + nsamps * lag
+        self._tabulate_schedule(self._numiters)
         L.check(L.lib().qsb_sampler_run(self.h, nsamps, burnin, lag))
 
     def begin(self, max_samples, burnin=0, lag=1, numiters=0):
         self._numiters = numiters
+        self._tabulate_schedule(numiters)
         L.check(L.lib().qsb_sampler_begin(self.h, max_samples, burnin, lag, numiters))
 
     def advance(self, iters):

@@ -69,6 +69,7 @@ struct qsb_sampler {
   double t_accum = 0.0; uint64_t t_launches = 0;   // QSB_FLAG_TIME_KERNEL
   bool ev_pending = false;
   double* stage = nullptr; size_t stage_bytes = 0;  // device staging of fetch_samples (kept between calls)
+  double* temps_dev = nullptr;                      // AnnealingKernel schedule
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -305,6 +306,7 @@ static int alloc_engine_state(qsb_sampler* s) {
   if (has_hmc) {
     A(a.alloc(&P.da_gbar, C)); A(a.alloc(&P.da_xbar, C)); A(a.alloc(&P.da_x0, C)); A(a.alloc(&P.da_lastx, C)); A(a.alloc(&P.da_gamma, C));
     A(a.alloc(&P.da_k, C));
+    A(a.alloc(&P.hmc_dualT, C)); A(a.alloc(&P.hmc_gT, C));
   }
   if (has_drift) { A(a.alloc(&P.dr_mean, C * d)); A(a.alloc(&P.dr_m2, C * d)); A(a.alloc(&P.dr_s0, C)); A(a.alloc(&P.dr_mult, C)); A(a.alloc(&P.dr_n, C)); }
   if (has_harm) A(a.alloc(&P.ha_scale, C));
@@ -326,6 +328,7 @@ static int reset_kernel_state(qsb_sampler* s) {
   for (int k = 0; k < P.nsub; ++k) {
     if (P.kind[k] == K_HMC) {
       CU(fill(P.eps, C, P.stepSize0[k], st));
+      CU(fill(P.hmc_dualT, C, 1.0, st)); CU(fill(P.hmc_gT, C, 1.0, st));
       CU(cudaMemsetAsync(P.da_gbar, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_xbar, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_x0, 0, 8 * C, st));
       CU(cudaMemsetAsync(P.da_lastx, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_gamma, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_k, 0, 4 * C, st));
     } else if (P.kind[k] == K_DRIFT) {
@@ -401,6 +404,7 @@ int qsb_sampler_destroy(qsb_sampler* s) {
   if (s->glm) glm_sampler_destroy(s->glm);
   else free_run_buffers(s);
   if (s->stage) cudaFree(s->stage);
+  if (s->temps_dev) cudaFree(s->temps_dev);
   s->arena.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -533,6 +537,22 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
   CU(cudaGetLastError());
   s->ev_pending = true;
   s->iter += iters;
+  return 0;
+}
+
+int qsb_sampler_set_temperatures(qsb_sampler* s, const double* temps, uint64_t n) {
+  if (!s) return fail(1, "null sampler");
+  CU(cudaSetDevice(s->m->device));
+  for (uint64_t i = 0; temps && i < n; ++i) if (!(temps[i] > 0.0)) return fail(2, "qsb_sampler_set_temperatures: temperatures must be positive");
+  if (s->glm) { std::string why; if (glm_sampler_set_temperatures(s->glm, temps, temps ? n : 0, why)) return fail(5, why); return 0; }
+  CU(cudaStreamSynchronize(s->stream));
+  if (s->temps_dev) { cudaFree(s->temps_dev); s->temps_dev = nullptr; }
+  s->P.temps = nullptr; s->P.ntemps = 0;
+  if (temps && n) {
+    CU(cudaMalloc((void**)&s->temps_dev, 8 * n));
+    CU(cudaMemcpy(s->temps_dev, temps, 8 * n, cudaMemcpyHostToDevice));
+    s->P.temps = s->temps_dev; s->P.ntemps = n;
+  }
   return 0;
 }
 

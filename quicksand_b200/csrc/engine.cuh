@@ -54,6 +54,7 @@ struct EngineParams {
   double *x, *g, *lp;
   uint8_t* flags;
   double *eps, *da_gbar, *da_xbar, *da_x0, *da_lastx, *da_gamma;
+  double *hmc_dualT, *hmc_gT;       // [C] dualTrace.temperature (hmc.t:266) and the temperature the cached gradient was computed under
   uint32_t* da_k;
   double *dr_mean, *dr_m2, *dr_s0, *dr_mult;
   uint32_t* dr_n;
@@ -63,6 +64,8 @@ struct EngineParams {
   int* status;                      // sticky error bits
   // run window
   uint64_t it_begin, n_iters, burnin, lag;
+  // AnnealingKernel (mcmc.t:297-319): temperature of iteration i = temps[min(i, ntemps-1)]; nullptr = 1
+  const double* temps; uint64_t ntemps;
   // kept samples
   double *samples, *samp_lp;
   uint32_t sample_chains;
@@ -137,19 +140,32 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
     double lp = 0.0, q = 0.0;
     extern __shared__ double qsb_zbuf[];
     const double* Ssm = qsb_zbuf + (size_t)(2 * ((NPL + 1) / 2)) * blockDim.x;
-    QSB_FOR_E {
-      if (e < d) {
+    if (d == NPL) {   // every element live (config c2: n = 10 on the NPL = 10 variant): no per-element predicates
+      QSB_FOR_E {
         double sx = 0.0;
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
-          if (j < d) {
-            if (SSM) sx += Ssm[e * NPL + j] * x[j];                 // shared memory (advance kernel)
-            else sx += P.Sc[(e * NPL + j) & 255] * x[j];            // kernel parameter (one-off kernels)
-          }
+          if (SSM) sx += Ssm[e * NPL + j] * x[j];
+          else sx += P.Sc[(e * NPL + j) & 255] * x[j];
         }
         if (LP) { q += x[e] * sx; lp += gaussian_lp(x[e], 0.0, 1.0); }
         if (GRAD) g[e] = -x[e] - 0.5 * sx;
-      } else if (GRAD) g[e] = 0.0;
+      }
+    } else {
+      QSB_FOR_E {
+        if (e < d) {
+          double sx = 0.0;
+#pragma unroll
+          for (int j = 0; j < NPL; ++j) {
+            if (j < d) {
+              if (SSM) sx += Ssm[e * NPL + j] * x[j];                 // shared memory (advance kernel)
+              else sx += P.Sc[(e * NPL + j) & 255] * x[j];            // kernel parameter (one-off kernels)
+            }
+          }
+          if (LP) { q += x[e] * sx; lp += gaussian_lp(x[e], 0.0, 1.0); }
+          if (GRAD) g[e] = -x[e] - 0.5 * sx;
+        } else if (GRAD) g[e] = 0.0;
+      }
     }
     if (LP) lp += -0.5 * (0.5 * q);
     lp_float = lp;
@@ -371,6 +387,10 @@ template <int FAM, int G, int NPL> struct Chain {
   const int lane;
   const int d;
   mutable unsigned long long cnt[2] = {0, 0};  // gradient evaluations / leapfrog steps of this group, flushed once per launch
+  // currTrace.temperature of this iteration (trace.t:652-655): every log-density evaluated during the iteration is
+  // divided by it (trace.t:737-741) and its gradient multiplied by 1/T (the adjoint of that division, ad.t:405-412);
+  // values cached from earlier iterations (lp, gradient) keep the temperature they were computed under, as in the reference
+  mutable double T = 1.0, invT = 1.0;
   __device__ __forceinline__ Chain(const EngineParams& P_, uint32_t c_)
       : P(P_), c(c_), gc(P_.chain_begin + c_), lane(Grp<G>::lane()), d(P_.d) {}
 
@@ -455,6 +475,7 @@ template <int FAM, int G, int NPL> struct Chain {
     QSB_FOR_E xs[e] = xs[e] + eps * p[e] * 1.0;
     double lpf;
     double lp = model_eval<FAM, G, NPL, true, LPW, FAM == FAM_GAUSS_PREC>(P, lane, xs, gs, lpf);
+    if (T != 1.0) { lp = lp / T; QSB_FOR_E gs[e] = gs[e] * invT; }
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     return lp;
   }
@@ -517,6 +538,12 @@ template <int FAM, int G, int NPL> struct Chain {
       load(P.x, xs);
       double lpf;
       double dual_lp = model_eval<FAM, G, NPL, true, true, FAM == FAM_GAUSS_PREC>(P, lane, xs, gs, lpf);
+      if (P.temps) {
+        // hmc.t:254 runs before hmc.t:266: the re-gathered gradient is taken under the temperature the dual trace was
+        // left with by the previous HMC call (first call: the copy of currTrace's, hmc.t:218 / trace.t:167-173)
+        const double Tg = (fl & FLAG_HMC_INIT) ? P.hmc_dualT[c] : T;
+        if (Tg != 1.0) { const double iTg = 1.0 / Tg; dual_lp = dual_lp / Tg; QSB_FOR_E gs[e] = gs[e] * iTg; }
+      }
       store(P.g, gs);
       count(0, 1);
       if (!(fl & FLAG_HMC_INIT) && adapting) {
@@ -529,6 +556,7 @@ template <int FAM, int G, int NPL> struct Chain {
       }
       fl |= FLAG_HMC_INIT | FLAG_GRAD_VALID;
     }
+    if (P.temps && leader()) P.hmc_dualT[c] = T;   // hmc.t:266
     load(P.x, xs); load(P.g, gs);
     sample_momenta(iter, p);
     const double lp_cur = P.lp[c];
@@ -569,16 +597,18 @@ template <int FAM, int G, int NPL> struct Chain {
   // separate half-kicks).  The cached gradient of the reference (hmc.t:82-101) is a function of the cached position, so
   // it is not stored.
   static constexpr bool SCALAR_GRAD = G == 32 && (FAM == FAM_FUNNEL || FAM == FAM_EIGHT_SCHOOLS);
-  __device__ __forceinline__ void kick(double he, const GradScalars<FAM>& gs, const double (&x)[NPL], double (&p)[NPL], bool twice) const {
+  __device__ __forceinline__ void kick(double he, const GradScalars<FAM>& gs, const double (&x)[NPL], double (&p)[NPL], bool twice, double f) const {
     QSB_FOR_E {
-      const double g = gs.elem(P, e * G + lane, x[e]);
+      double g = gs.elem(P, e * G + lane, x[e]);
+      if (f != 1.0) g = g * f;
       p[e] = p[e] + he * g;
       if (twice) p[e] = p[e] + he * g;
     }
   }
   __device__ __forceinline__ double lp_only(const double (&x)[NPL]) const {
     double lpf, gd[NPL];
-    return model_eval<FAM, G, NPL, false, true, false>(P, lane, x, gd, lpf);
+    const double lp = model_eval<FAM, G, NPL, false, true, false>(P, lane, x, gd, lpf);
+    return T != 1.0 ? lp / T : lp;
   }
   __device__ __forceinline__ double search_step_size_warp(double eps, double dual_lp) const {
     double x[NPL], p[NPL];
@@ -591,7 +621,7 @@ template <int FAM, int G, int NPL> struct Chain {
       load(P.x, x);
       sample_momenta(QSB_ITER_SEARCH + probe, p);
       gs.template reduce<G, NPL>(P, lane, x);
-      kick(0.5 * eps, gs, x, p, false);
+      kick(0.5 * eps, gs, x, p, false, invT);
       QSB_FOR_E x[e] = x[e] + eps * p[e] * 1.0;
       const double lp = lp_only(x);
       ++evals;
@@ -617,6 +647,12 @@ template <int FAM, int G, int NPL> struct Chain {
     if (leader()) P.made[(size_t)k * P.C + c] += 1;
     uint8_t fl = P.flags[c];
     double eps = P.eps[c];
+    double Tg0 = T;     // temperature carried by the reference's cached gradient (first half-kick of this call)
+    if (P.temps) {
+      if (fl & FLAG_GRAD_VALID) Tg0 = P.hmc_gT[c];
+      else if (fl & FLAG_HMC_INIT) Tg0 = P.hmc_dualT[c];   // re-gather under the dual trace's stale temperature (hmc.t:254 before :266)
+    }
+    const double f0 = Tg0 != 1.0 ? 1.0 / Tg0 : 1.0;
     if (!(fl & FLAG_GRAD_VALID)) {   // checkForChanges (hmc.t:188-287): the reference re-evaluates the gradient here
       count(0, 1);
       if (!(fl & FLAG_HMC_INIT) && adapting) {
@@ -638,11 +674,11 @@ template <int FAM, int G, int NPL> struct Chain {
     const double he = 0.5 * eps;
     GradScalars<FAM> gs;
     gs.template reduce<G, NPL>(P, lane, x);
-    kick(he, gs, x, p, false);
+    kick(he, gs, x, p, false, f0);
     for (uint32_t s = 0; s < L; ++s) {
       QSB_FOR_E x[e] = x[e] + eps * p[e] * 1.0;
       gs.template reduce<G, NPL>(P, lane, x);
-      kick(he, gs, x, p, s + 1 < L);
+      kick(he, gs, x, p, s + 1 < L, invT);
       if (P.rec_leap) {
         size_t base = (((size_t)c * P.rec_iters + (iter - P.it_begin)) * L + s) * d;
         QSB_FOR_E { int i = e * G + lane; if (i < d) P.rec_leap[base + i] = x[e]; }
@@ -659,7 +695,10 @@ template <int FAM, int G, int NPL> struct Chain {
       store(P.x, x);
       if (leader()) { P.acc[(size_t)k * P.C + c] += 1; P.lp[c] = newlp; }
     }
-    if (leader()) { P.eps[c] = eps; P.flags[c] = fl; }
+    if (leader()) {
+      P.eps[c] = eps; P.flags[c] = fl;
+      if (P.temps) { P.hmc_dualT[c] = T; P.hmc_gT[c] = accept ? T : Tg0; }
+    }
     return accept;
   }
 
@@ -700,6 +739,7 @@ template <int FAM, int G, int NPL> struct Chain {
     rec_step = s0;
     double lpf, gdummy[NPL];
     model_eval<FAM, G, NPL, false, true, FAM == FAM_GAUSS_PREC>(P, lane, xp, gdummy, lpf);
+    if (T != 1.0) lpf = lpf / T;
     const double lp_cur = P.lp[c];
     const double thresh = lpf - lp_cur;
     rec_dh = thresh;
@@ -768,6 +808,7 @@ template <int FAM, int G, int NPL> struct Chain {
     }
     double lpf, gdummy[NPL];
     model_eval<FAM, G, NPL, false, true, FAM == FAM_GAUSS_PREC>(P, lane, xp, gdummy, lpf);
+    if (T != 1.0) lpf = lpf / T;
     double t = 0.234;
     if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
     const double thresh = lpf - P.lp[c];
@@ -846,7 +887,8 @@ template <int FAM, int G, int NPL> struct Chain {
       }
     }
     rec_step = s0;
-    const double lpf = ms.finish(Grp<G>::sum(lp));
+    double lpf = ms.finish(Grp<G>::sum(lp));
+    if (T != 1.0) lpf = lpf / T;
     const double thresh = lpf - P.lp[c];
     rec_dh = thresh;
     const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
@@ -941,7 +983,8 @@ template <int FAM, int G, int NPL> struct Chain {
         }
       }
     }
-    const double lpf = ms.finish(Grp<G>::sum(lp));
+    double lpf = ms.finish(Grp<G>::sum(lp));
+    if (T != 1.0) lpf = lpf / T;
     double t = 0.234;
     if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
     const double thresh = lpf - P.lp[c];
@@ -974,6 +1017,7 @@ template <int FAM, int G, int NPL> struct Chain {
   template <bool HAS_HMC>
   __device__ __forceinline__ void iterate(uint64_t it) const {
     const uint32_t iter = (uint32_t)it;
+    if (P.temps) { T = P.temps[it < P.ntemps ? it : P.ntemps - 1]; invT = 1.0 / T; }   // AnnealingKernel:next (mcmc.t:308-311)
     int k = 0;
     if (P.nsub > 1) {   // MixtureKernel:next (mcmc.t:275-287) + categorical_array.sample (distrib.t:281-292)
       double sum = 0.0;
@@ -1031,7 +1075,7 @@ template <int FAM, int G, int NPL> struct Chain {
               if (i < d) P.samples[G == 1 ? ((size_t)sidx * P.retdim + i) * SC + c : ((size_t)sidx * SC + c) * P.retdim + i] = x[e];
             }
           }
-          if (leader()) P.samp_lp[(size_t)sidx * SC + c] = P.lp[c];
+          if (leader()) P.samp_lp[(size_t)sidx * SC + c] = P.lp[c] * T;   // mcmc.t:69
         }
       }
     }

@@ -354,6 +354,7 @@ struct VecParams {
   unsigned long long *made, *acc;
   int* status;
   uint32_t iter, L, step, probe;
+  double T, invT;   // trace temperature of this iteration (AnnealingKernel, mcmc.t:297-319; trace.t:737-741)
   int adapting;
   double stepSize0;
   // samples / record
@@ -371,7 +372,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ double finish_grad(const VecParams& P, uint32_t c, int i, double th) {
   double gl = 0.0;
   for (int r = 0; r < P.ksplit; ++r) gl += P.partG[((size_t)r * P.C + c) * P.Dp + i];
-  return gaussian_dlp_dx(th, 0.0, P.prior_sigma) + gl;
+  const double g = gaussian_dlp_dx(th, 0.0, P.prior_sigma) + gl;
+  return P.T != 1.0 ? g * P.invT : g;
 }
 __device__ __forceinline__ double finish_lp(const VecParams& P, uint32_t c, int lane, const double* pos) {
   double lpp = 0.0;
@@ -379,7 +381,7 @@ __device__ __forceinline__ double finish_lp(const VecParams& P, uint32_t c, int 
   lpp = warp_sum(lpp);
   double ll = 0.0;
   for (int r = 0; r < P.ksplit; ++r) ll += P.partLp[(size_t)r * P.C + c];
-  return lpp + ll;
+  return lpp + ll;   // at temperature 1; callers divide
 }
 
 template <int MODE>
@@ -405,7 +407,9 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
     // the gradient HMCKernel:checkForChanges computes on its first call (hmc.t:254)
     for (int i = lane; i < d; i += 32) g[i] = finish_grad(P, c, i, x[i]);
     double lp = finish_lp(P, c, lane, x);
-    if (lane == 0) { P.lp[c] = lp; P.prevlp[c] = lp; }
+    // currTrace.logprob comes from the initialisation at temperature 1 (trace.t:592-624); the dual trace is first
+    // evaluated under the first iteration's temperature (hmc.t:218, 254)
+    if (lane == 0) { P.lp[c] = lp; P.prevlp[c] = P.T != 1.0 ? lp / P.T : lp; }
     return;
   }
   const double eps = P.eps[c];
@@ -444,6 +448,7 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
     if (P.done[c]) return;
     // searchForInitialStepSize bookkeeping (hmc.t:345-391); the momentum half-kick is irrelevant to it
     double lp = finish_lp(P, c, lane, xs);
+    if (P.T != 1.0) lp = lp / P.T;
     if (lane == 0) {
       const double LOG_HALF = log(0.5);
       double H = lp - P.prevlp[c];
@@ -480,7 +485,8 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
     gs[i] = gn; p[i] = m;
     kin += m * m * 1.0;
   }
-  const double newlp = finish_lp(P, c, lane, xs);
+  double newlp = finish_lp(P, c, lane, xs);
+  if (P.T != 1.0) newlp = newlp / P.T;
   const double H_new = -0.5 * warp_sum(kin) + newlp;
   const double dH = H_new - P.H0[c];
   double eps_new = eps;
@@ -517,7 +523,7 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
   }
   if (P.keep && c < P.SC) {
     for (int i = lane; i < d; i += 32) P.samples[((size_t)P.sidx * P.SC + c) * d + i] = x[i];
-    if (lane == 0) P.samp_lp[(size_t)P.sidx * P.SC + c] = accept ? newlp : P.lp[c];
+    if (lane == 0) P.samp_lp[(size_t)P.sidx * P.SC + c] = (accept ? newlp : P.lp[c]) * P.T;   // mcmc.t:69
   }
 }
 
@@ -540,6 +546,7 @@ struct GlmSampler {
   std::vector<cudaEvent_t> tev;
   size_t tev_used = 0;
   double t_accum = 0.0; uint64_t t_launches = 0;
+  std::vector<double> temps;   // AnnealingKernel schedule (host: the launches of an iteration carry its temperature)
 };
 
 static int pick_ksplit(int ntiles, int nblocks, int nsm) {
@@ -657,6 +664,7 @@ GlmSampler* glm_sampler_create(GlmModel* m, double stepSize, uint32_t numSteps, 
   s->nj_inst = pick_nj_inst(G.nj);
   s->smem = stage_doubles(m->S) * STAGES * 8 + 2 * STAGES * 8;
   V.key = RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)}; V.chain_begin = chain_begin; V.C = numchains; V.d = m->d; V.Dp = m->Dp;
+  V.T = 1.0; V.invT = 1.0;
   V.ksplit = G.ksplit; V.prior_sigma = m->prior_sigma; V.L = numSteps; V.adapting = adapt ? 1 : 0; V.stepSize0 = stepSize; V.SC = sample_chains;
   bool ok = dalloc(s, &V.x, C * Dp) && dalloc(s, &V.g, C * Dp) && dalloc(s, &V.xs, C * Dp) && dalloc(s, &V.gs, C * Dp) && dalloc(s, &V.p, C * Dp);
   double *partG = nullptr, *partLp = nullptr;
@@ -789,8 +797,20 @@ int glm_sampler_begin(GlmSampler* s, uint64_t max_samples, uint64_t burnin, uint
 
 // searchForInitialStepSize (hmc.t:345-391): every probe is one leapfrog step of all chains still searching;
 // the host only loops until no chain is left (one 4-byte read per probe; initialisation only)
+static double temp_at(const GlmSampler* s, uint64_t it) {
+  if (s->temps.empty()) return 1.0;
+  return s->temps[it < s->temps.size() ? it : s->temps.size() - 1];
+}
+
+int glm_sampler_set_temperatures(GlmSampler* s, const double* temps, uint64_t n, std::string&) {
+  s->temps.clear();
+  if (temps && n) s->temps.assign(temps, temps + n);
+  return 0;
+}
+
 static int step_size_search(GlmSampler* s, std::string& why) {
   VecParams V = s->V;
+  V.T = temp_at(s, 0); V.invT = 1.0 / V.T;
   for (uint32_t probe = 0; probe < 4096; ++probe) {
     V.probe = probe;
     GCU(cudaMemsetAsync(V.n_active, 0, 4, s->stream));
@@ -813,6 +833,11 @@ static int step_size_search(GlmSampler* s, std::string& why) {
 int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
   if (s->rec_iters && s->iter + iters > s->rec_iters) { why = "record buffer holds numiters iterations only"; return 2; }
   if (!s->searched) {
+    if (temp_at(s, s->iter) != 1.0) {   // first dual-trace evaluation under the first temperature: gradient and search baseline
+      VecParams V0 = s->V;
+      V0.T = temp_at(s, s->iter); V0.invT = 1.0 / V0.T;
+      GCU(launch_vec<V_FINISH_EVAL>(s, V0));
+    }
     ++s->grad_evals;   // the reference's first traceUpdate (hmc.t:254); its value was computed with the initial logprob
     if (s->adapting) if (int rc = step_size_search(s, why)) return rc;
     s->searched = true;
@@ -822,6 +847,7 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
     const uint64_t it = s->iter + k;
     VecParams V = s->V;
     V.iter = (uint32_t)it; V.rec_row = it;
+    V.T = temp_at(s, it); V.invT = 1.0 / V.T;
     GCU(launch_vec<V_TRANS_FIRST>(s, V));
     for (uint32_t st = 0; st < s->L; ++st) {
       const bool last = st + 1 == s->L;

@@ -34,7 +34,7 @@ def run_oracle(program, kernel, chains, iters, seed=1234, chain_begin=0, burnin=
         O.use("strict")
 
 
-def run_both(program, kernel, chains, iters, seed=1234, chain_begin=0, leap=False, mapping=0, burnin=0, lag=1):
+def run_both(program, kernel, chains, iters, seed=1234, chain_begin=0, leap=False, mapping=0, burnin=0, lag=1, temps=None):
     """Returns (gpu, cpu): dicts with state [C][T][n], accept, dH, step, kidx, leapfrog, samples, logprobs, init."""
     nsamps = (iters - burnin) // lag
     assert burnin + nsamps * lag == iters
@@ -42,6 +42,8 @@ def run_both(program, kernel, chains, iters, seed=1234, chain_begin=0, leap=Fals
     s = qs.Sampler(program, kernel, numchains=chains, seed=seed, chain_begin=chain_begin, flags=flags, mapping=mapping)
     s.init()
     init = s.get_state()
+    if temps is not None:
+        s.set_temperatures(temps)
     s.run(nsamps, burnin, lag)
     gpu = s.fetch_record(leap=leap)
     gpu["init"] = init
@@ -50,7 +52,10 @@ def run_both(program, kernel, chains, iters, seed=1234, chain_begin=0, leap=Fals
     gpu["logprobs"] = smp["logprob"]
     gpu["stats"] = s.stats()
     s.close()
-    cpu = O.run(oracle_program(program), oracle_specs(kernel), seed, chains, nsamps, burnin, lag, chain_begin=chain_begin, record=True)
+    if temps is None and kernel.anneal is not None:
+        temps = [float(kernel.anneal(i, iters)) for i in range(iters)]
+    cpu = O.run(oracle_program(program), oracle_specs(kernel), seed, chains, nsamps, burnin, lag, chain_begin=chain_begin, record=True,
+                temps=temps)
     return gpu, cpu
 
 

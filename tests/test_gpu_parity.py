@@ -186,6 +186,53 @@ def test_three_way_mixture_and_lag(qs, oracle):
     assert P.relerr(gpu["logprobs"], cpu["logprobs"]).max() <= 1e-9
 
 
+def _cooling(i, n):
+    """annealSched(iter, numiters): geometric cooling from 4 to 1 over the first 3/4 of the run."""
+    return max(1.0, 4.0 * (0.25 ** (i / (0.75 * n))))
+
+
+ANNEAL = [
+    ("c2", "hmc", 0), ("gauss10", "mix3", 0), ("schools13", "drift", 32), ("schools13", "hmc", 32), ("schools13", "hmc", 1),
+    ("funnel12", "mix", 32), ("funnel12", "mix", 1), ("funnel70", "harm", 0), ("logistic20", "hmc", 0), ("mixed10", "hmc", 32),
+]
+
+
+@pytest.mark.parametrize("name,kind,mapping", ANNEAL)
+def test_annealing_kernel_parity(qs, oracle, name, kind, mapping):
+    """AnnealingKernel(kernel, annealSched) (mcmc.t:297-319): the trace temperature changes every iteration; cached
+    log-densities and gradients keep the temperature they were computed under (hmc.t:144, 254, 266; drift.t:155;
+    harm.t:90), kept samples store logprob * temperature (mcmc.t:69)."""
+    prog = _programs(qs)[name]
+    eps = {"c2": 0.15, "schools13": 0.02, "funnel12": 0.01, "logistic20": 0.05, "mixed10": 0.1, "gauss10": 0.2}.get(name, 0.1)
+    hmc = qs.HMCKernel(numSteps=6, stepSize=eps, doStepSizeAdapt=False)
+    inner = {"hmc": hmc, "drift": qs.DriftKernel(scale=0.3), "harm": qs.HARMKernel(),
+             "mix": qs.MixtureKernel([qs.HARMKernel(), hmc], [0.5, 0.5]),
+             "mix3": qs.MixtureKernel([qs.DriftKernel(), qs.HARMKernel(), hmc], [0.3, 0.3, 0.4])}[kind]
+    k = qs.AnnealingKernel(inner, _cooling)
+    gpu, cpu = P.run_both(prog, k, chains=64, iters=80, seed=77, mapping=mapping, leap=(kind == "hmc"))
+    r = P.compare(gpu, cpu, TOL, leap=(kind == "hmc"), what="Annealing %s %s map%d" % (name, kind, mapping), min_compared=0.9)
+    v = r["valid"]
+    assert P.relerr(gpu["logprobs"], cpu["logprobs"])[v].max() <= 1e-9
+    # the schedule really was applied: an un-annealed run differs
+    plain, _ = P.run_both(prog, inner, chains=8, iters=80, seed=77, mapping=mapping)
+    assert not np.array_equal(plain["state"], gpu["state"][:8])
+
+
+def test_annealing_with_adaptive_hmc_first_iteration(qs, oracle):
+    """The step-size search and the first gradient run under the first iteration's temperature (hmc.t:218, 254-262)."""
+    prog = _programs(qs)["funnel12"]
+    k = qs.AnnealingKernel(qs.HMCKernel(numSteps=2), lambda i, n: 3.0 if i < 5 else 1.0)
+    for mapping in (1, 32):
+        gpu, cpu = P.run_both(prog, k, chains=64, iters=12, seed=78, mapping=mapping, leap=True)
+        assert np.array_equal(gpu["step"][:, 0], cpu["step"][:, 0])
+        P.compare(gpu, cpu, TOL, leap=True, what="Annealing adaptive HMC map%d" % mapping, min_compared=0.5)
+    prog = _programs(qs)["logistic20"]
+    gpu, cpu = P.run_both(prog, k, chains=64, iters=12, seed=79, leap=True)
+    assert np.array_equal(gpu["step"][:, 0], cpu["step"][:, 0])
+    # adaptive HMC on the GLM target leaves the stable region within a few transitions (see HMC_ADAPT): prefix mode
+    P.compare(gpu, cpu, TOL, leap=True, what="Annealing adaptive HMC logistic", min_compared=0.05)
+
+
 def test_chain_ids_are_partition_invariant(qs):
     """Philox key = global chain id: chains [32,64) run as a shard equal chains 32..63 of the full run, bit for bit
     (the multi-GPU invariance the chain sharding relies on)."""
