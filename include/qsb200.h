@@ -46,7 +46,12 @@ enum {
 /* ERP kinds with their bounding transforms as bound in qs/erpdefs.t:
  * gaussian -> Bounds.None (46-57), gamma -> Lower(0) (61-69), beta -> LowerUpper(0,1) (92-100),
  * uniform -> LowerUpper(lo,hi) (28-36). */
-enum { QSB_ERP_GAUSSIAN = 0, QSB_ERP_GAMMA = 1, QSB_ERP_BETA = 2, QSB_ERP_UNIFORM = 3 };
+enum { QSB_ERP_GAUSSIAN = 0, QSB_ERP_GAMMA = 1, QSB_ERP_BETA = 2, QSB_ERP_UNIFORM = 3,
+       /* dirichlet -> Bounds.UnitSimplex (erpdefs.t:179-212, erp.t:200-254): a K-vector choice is K consecutive
+        * components of this kind with erp_p0 = alpha_k and erp_p1 = k (index inside the choice, 0..K-1); component K-1
+        * of the unconstrained vector is the reference's unused stick coordinate.  gammamv / betamv (erpdefs.t:72-88,
+        * 103-125) are host-side reparametrisations of gamma / beta. */
+       QSB_ERP_DIRICHLET = 4 };
 
 /* transition kernels: qs/hmc.t:57-66, qs/drift.t:63-73, qs/harm.t:16-22 */
 enum { QSB_KERNEL_HMC = 1, QSB_KERNEL_DRIFT = 2, QSB_KERNEL_HARM = 3 };
@@ -180,6 +185,27 @@ int qsb_sampler_kernel_time(qsb_sampler* s, double* seconds, uint64_t* launches)
  * If dst_is_device != 0, dst is a device pointer on the sampler's device (e.g. a torch tensor
  * handed to NCCL); otherwise a host pointer. */
 int qsb_sampler_diagnostics(qsb_sampler* s, int32_t maxlag, double* dst, int32_t dst_is_device);
+
+/* ---- queries (qs/infer.t:128-264) evaluated on the device, per chain, over the kept samples of a sampler (no host
+ * round trip of the samples) or over a caller-owned HOST vector of Sample elements laid out as qsb_sampler_fetch_samples
+ * writes it ([nchains][nsamps] elements of stride_bytes).  Chains are sampler-local indices [chain_begin, chain_end).
+ *
+ * Expectation(doVariance) (infer.t:146-187), reference arithmetic: the mean starts at value[0], weights
+ * w_i = exp(loglikelihood_i) are summed from i = 1 (mean = sum(v)/(N-1) for MCMC samples), the variance is
+ * sum_i |value_i - mean|^2 / N.  mean: HOST [nchains][retdim]; var: HOST [nchains] or NULL (doVariance = false). */
+int qsb_query_expectation(qsb_sampler* s, uint32_t chain_begin, uint32_t chain_end, double* mean, double* var);
+int qsb_query_expectation_host(const void* samples, size_t stride_bytes, uint32_t nchains, uint64_t nsamps, int32_t retdim,
+                               double* mean, double* var);
+/* MAP (infer.t:191-206): the first sample of largest logprob.  value: HOST [nchains][retdim]; logprob: HOST [nchains] or NULL. */
+int qsb_query_map(qsb_sampler* s, uint32_t chain_begin, uint32_t chain_end, double* value, double* logprob);
+int qsb_query_map_host(const void* samples, size_t stride_bytes, uint32_t nchains, uint64_t nsamps, int32_t retdim,
+                       double* value, double* logprob);
+/* Autocorrelation(mean, variance) (infer.t:213-264): ac[t] = sum_{i<N-t} (v_i - m).(v_{i+t} - m) / ((N-t) * variance),
+ * t = 0..N-1.  mean: HOST [retdim] shared by all chains, or NULL = each chain's own Expectation(true) (then `variance`
+ * is ignored).  ac: HOST [nchains][nsamps]. */
+int qsb_query_autocorrelation(qsb_sampler* s, uint32_t chain_begin, uint32_t chain_end, const double* mean, double variance, double* ac);
+int qsb_query_autocorrelation_host(const void* samples, size_t stride_bytes, uint32_t nchains, uint64_t nsamps, int32_t retdim,
+                                   const double* mean, double variance, double* ac);
 
 /* Per-iteration record (QSB_FLAG_RECORD): HOST arrays, any may be NULL.
  *   state [numchains][iters][dim]   accept, kidx [numchains][iters] (int32)   dh, step [numchains][iters]

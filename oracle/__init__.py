@@ -33,7 +33,7 @@ def use(variant):
     _ACTIVE = variant
 
 HMC, DRIFT, HARM = 1, 2, 3
-ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM = 0, 1, 2, 3
+ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
 ITER_INIT = 0xFFFFFFFF
 ITER_SEARCH = 0xF0000000
 SLOT_MIXTURE = 0xFFFFFFFF

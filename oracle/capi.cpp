@@ -45,6 +45,7 @@ double qso_logprob(int which, const double* a, int n) {
     case 6: return D::poisson_logprob((int)a[0], a[1]);
     case 7: return D::categorical_logprob((int)a[0], a + 1, n - 1);
     case 8: return D::dirichlet_logprob<double>(a, a + n / 2, n / 2);
+    case 10: { std::vector<double> x(a, a + n); return simplex_lpincr<double>(x); }
     case 9: return D::log_gamma<double>(a[0]);
   }
   return NAN;
@@ -135,7 +136,7 @@ static Kernel* make_kernel(const qso_kernel_spec* specs, int nspecs) {
 int qso_program_dim(void* prog) {
   Rng& r = rng(); r.seed = 0; r.chain = 0; r.at(ITER_INIT, 0);
   Trace<double> t; t.init((Program*)prog, true);
-  return (int)t.choices.size();
+  return (int)t.countRealComps();
 }
 
 // Run chains [chain_begin, chain_begin+nchains) one after the other, like nchains runs of doMCMC.
@@ -172,7 +173,9 @@ int qso_run(void* prog, const qso_kernel_spec* specs, int nspecs, uint64_t seed,
       // replay the initial forward sample to report it (same sub-streams, no side effect on the run)
       r.at(ITER_INIT, 0);
       Trace<double> t; t.init(program, true);
-      for (size_t i = 0; i < t.choices.size(); ++i) rec_init[(size_t)c * t.choices.size() + i] = t.choices[i].getUnboundedValue();
+      std::vector<double> x0;
+      for (auto& rc : t.choices) rc.getUnboundedRealComps(x0);
+      std::memcpy(rec_init + (size_t)c * x0.size(), x0.data(), sizeof(double) * x0.size());
     }
     doMCMC(program, k.get(), samps, nsamps, burnin, lag);
     recorder() = nullptr;
@@ -215,8 +218,8 @@ int qso_logp_grad(void* prog, const double* x, int n, double* lp_dual, double* g
   Rng& r = rng(); r.seed = 0; r.chain = 0; r.at(ITER_INIT, 0);
   ad::recoverMemory();
   Trace<double> t; t.init(program, true);
-  if ((int)t.choices.size() != n) return 1;
-  for (int i = 0; i < n; ++i) t.choices[i].setUnboundedValue(x[i]);
+  if ((int)t.countRealComps() != n) return 1;
+  { std::vector<double> xv(x, x + n); size_t index = 0; for (auto& rc : t.choices) index += rc.setUnboundedRealComps(xv, index); }
   t.update(false);
   if (lp_float) *lp_float = t.logprob;
   HMCKernel k(1.0, 1, false);

@@ -47,7 +47,7 @@ struct Kernel {
   virtual uint64_t proposalsAccepted() { return propsAccepted; }
   virtual void unconstrained_state(Trace<double>* t, std::vector<double>& out) {
     out.clear();
-    for (auto& rc : t->choices) out.push_back(rc.getUnboundedValue());
+    for (auto& rc : t->choices) rc.getUnboundedRealComps(out);
   }
 };
 
@@ -114,7 +114,7 @@ struct HMCKernel : Kernel {
       propsAccepted = propsAccepted + 1;
       std::swap(positions, positions_scratch);
       std::swap(gradient, gradient_scratch);
-      for (size_t i = 0; i < currTrace->choices.size(); ++i) currTrace->choices[i].setUnboundedValue(positions[i]);
+      { size_t index = 0; for (auto& rc : currTrace->choices) index += rc.setUnboundedRealComps(positions, index); }   // hmc.t:170-176
       currTrace->update(false, false);
       currTrace->copyProbabilities(dualTrace);
     }
@@ -129,7 +129,7 @@ struct HMCKernel : Kernel {
       positions.clear();
       size_t numvars = currTrace->countChoices();
       if (numvars == 0) { std::printf("HMC: found 0 non-structural random choices.\n"); std::abort(); }
-      for (size_t i = 0; i < numvars; ++i) positions.push_back(currTrace->choices[i].getUnboundedValue());
+      for (size_t i = 0; i < numvars; ++i) currTrace->choices[i].getUnboundedRealComps(positions);
       size_t newn = positions.size();
       if (newn != oldn) {
         copyFromRealType(dualTrace, *currTrace);
@@ -170,7 +170,7 @@ struct HMCKernel : Kernel {
   double traceUpdate(std::vector<double>& pos, std::vector<double>& grad) {   // hmc.t:325-342
     positions_dual_scratch.clear(); positions_dual_scratch.reserve(pos.size());
     for (size_t i = 0; i < pos.size(); ++i) positions_dual_scratch.push_back(ad::num(pos[i]));
-    for (size_t i = 0; i < dualTrace.choices.size(); ++i) dualTrace.choices[i].setStoredValue(positions_dual_scratch[i]);
+    { size_t index = 0; for (auto& rc : dualTrace.choices) index += rc.setStoredRealComps(positions_dual_scratch, index); }   // hmc.t:329-334
     dualTrace.update(false);
     ad::num duallp = dualTrace.logprob;
     double lp = duallp.val();
@@ -255,7 +255,7 @@ struct DriftKernel : Kernel {
       realcomps_scratch[i] = D::gaussian_sample(realcomps[i], scales[i].scale);
     }
     Trace<double> nextTrace = *currTrace;   // TraceType.salloc():copy(currTrace)
-    for (size_t i = 0; i < nextTrace.choices.size(); ++i) nextTrace.choices[i].setUnboundedValue(realcomps_scratch[i]);
+    { size_t index = 0; for (auto& rc : nextTrace.choices) index += rc.setUnboundedRealComps(realcomps_scratch, index); }
     nextTrace.update(false);
     double acceptThresh = nextTrace.logprob - currTrace->logprob;
     rng().at(iter, (uint32_t)n);
@@ -276,7 +276,7 @@ struct DriftKernel : Kernel {
       realcomps.clear();
       size_t numvars = currTrace->countChoices();
       if (numvars == 0) { std::printf("DriftKernel: found 0 non-structural random choices\n"); std::abort(); }
-      for (size_t i = 0; i < numvars; ++i) realcomps.push_back(currTrace->choices[i].getUnboundedValue());
+      for (size_t i = 0; i < numvars; ++i) currTrace->choices[i].getUnboundedRealComps(realcomps);
       size_t n = realcomps.size();
       realcomps_scratch.assign(n, 0.0);
       for (size_t j = scales.size(); j < n; ++j) { ScaleAdapter s; s.scale = initScale; scales.push_back(s); }
@@ -327,7 +327,7 @@ struct HARMKernel : Kernel {
       realcomps_scratch[i] = realcomps[i] + (scale * direction[i]);
     }
     Trace<double> nextTrace = *currTrace;
-    for (size_t i = 0; i < nextTrace.choices.size(); ++i) nextTrace.choices[i].setUnboundedValue(realcomps_scratch[i]);
+    { size_t index = 0; for (auto& rc : nextTrace.choices) index += rc.setUnboundedRealComps(realcomps_scratch, index); }
     nextTrace.update(false);
     double targetAcceptRatio = 0.234;
     if (n < 5) targetAcceptRatio = lerp_(0.44, 0.234, (n - 1) / 4.0);
@@ -358,7 +358,7 @@ struct HARMKernel : Kernel {
       realcomps.clear();
       size_t numvars = currTrace->countChoices();
       if (numvars == 0) { std::printf("HARMKernel: found 0 non-structural random choices\n"); std::abort(); }
-      for (size_t i = 0; i < numvars; ++i) realcomps.push_back(currTrace->choices[i].getUnboundedValue());
+      for (size_t i = 0; i < numvars; ++i) currTrace->choices[i].getUnboundedRealComps(realcomps);
       realcomps_scratch.assign(realcomps.size(), 0.0);
     }
   }

@@ -27,15 +27,27 @@ struct IndepErps : Program {
   std::vector<double> p0, p1;
   int ret_mode = 0;
   double ret_div = 1.0;
+  // Entries are per real component.  A dirichlet choice of K components is K consecutive entries of kind
+  // ERP_DIRICHLET with p0 = alpha_k and p1 = k (its index inside the choice); it is ONE ERP call site.
   template <class real> void body(Trace<real>& t) {
     size_t K = kind.size();
-    if (ret_mode == 0) {
-      real sum = real(0.0);
-      for (size_t i = 0; i < K; ++i) sum = sum + t.erp(kind[i], real(p0[i]), real(p1[i]));
-      t.returnValue.push_back(sum / ret_div);
-    } else {
-      for (size_t i = 0; i < K; ++i) t.returnValue.push_back(t.erp(kind[i], real(p0[i]), real(p1[i])));
+    real sum = real(0.0);
+    for (size_t i = 0; i < K;) {
+      if (kind[i] == ERP_DIRICHLET) {
+        size_t j = i + 1;
+        while (j < K && kind[j] == ERP_DIRICHLET && p1[j] == (double)(j - i)) ++j;
+        std::vector<real> params;
+        for (size_t m = i; m < j; ++m) params.push_back(real(p0[m]));
+        std::vector<real> v = t.dirichlet(params);
+        for (auto& x : v) { if (ret_mode == 0) sum = sum + x; else t.returnValue.push_back(x); }
+        i = j;
+      } else {
+        real x = t.erp(kind[i], real(p0[i]), real(p1[i]));
+        if (ret_mode == 0) sum = sum + x; else t.returnValue.push_back(x);
+        ++i;
+      }
     }
+    if (ret_mode == 0) t.returnValue.push_back(sum / ret_div);
   }
   QSO_PROGRAM_RUNNERS
 };

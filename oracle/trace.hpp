@@ -28,7 +28,7 @@
 
 namespace qso {
 
-enum ErpKind { ERP_GAUSSIAN = 0, ERP_GAMMA = 1, ERP_BETA = 2, ERP_UNIFORM = 3 };
+enum ErpKind { ERP_GAUSSIAN = 0, ERP_GAMMA = 1, ERP_BETA = 2, ERP_UNIFORM = 3, ERP_DIRICHLET = 4 };
 
 template <class real> struct is_dual : std::false_type {};
 template <> struct is_dual<ad::num> : std::true_type {};
@@ -60,7 +60,80 @@ template <class real, class BT> inline real lowerupper_lpincr(real x, BT lo, BT 
   return tmath::log(hi - lo) - x - 2.0 * tmath::log(1.0 + tmath::exp(-x));
 }
 
+// ---- Bounds.UnitSimplex (erp.t:200-254): stick breaking on a K-vector; component K-1 of x is unused
+template <class real> inline std::vector<real> simplex_fwd(const std::vector<real>& x) {
+  std::vector<real> y(x.size(), real(0.0));
+  int Km1 = (int)x.size() - 1;
+  real sticklen = real(1.0);
+  for (int k = 0; k < Km1; ++k) {
+    real z = logistic<real>(x[k] - tmath::log((double)(Km1 - k)));
+    y[k] = sticklen * z;
+    sticklen = sticklen - y[k];
+  }
+  y[Km1] = sticklen;
+  return y;
+}
+template <class real> inline std::vector<real> simplex_inv(const std::vector<real>& y) {
+  std::vector<real> x(y.size(), real(0.0));   // makeArrayLikeFrom: zeros (erp.t:97-103); x[K-1] stays 0
+  int Km1 = (int)y.size() - 1;
+  real sticklen = y[Km1];
+  for (int k = Km1 - 1; k >= 0; --k) {
+    sticklen = sticklen + y[k];
+    real z = y[k] / sticklen;
+    x[k] = invlogistic<real>(z) + tmath::log((double)(Km1 - k));
+  }
+  return x;
+}
+template <class real> inline real simplex_lpincr(const std::vector<real>& x) {
+  real lp = real(0.0);
+  int Km1 = (int)x.size() - 1;
+  real sticklen = real(1.0);
+  for (int k = 0; k < Km1; ++k) {
+    real z = logistic<real>(x[k] - tmath::log((double)(Km1 - k)));
+    lp = lp + tmath::log(sticklen);
+    lp = lp + tmath::log(z);
+    lp = lp + tmath::log(1.0 - z);
+    sticklen = sticklen - (sticklen * z);
+  }
+  return lp;
+}
+
 template <class real> struct RandomChoice {   // RandomChoiceT, erp.t:286-311
+  // vector-valued choice (dirichlet, erpdefs.t:179-212): value and params are K-vectors
+  std::vector<real> vvalue, vparams;
+  bool is_vector() const { return kind == ERP_DIRICHLET; }
+  std::vector<real> getValueV() { if (applyingBounds) return simplex_fwd<real>(vvalue); return vvalue; }
+  void setValueV(const std::vector<real>& v) { vvalue = applyingBounds ? simplex_inv<real>(v) : v; needsRescore = true; }
+  std::vector<real> getUnboundedValueV() { if (applyingBounds) return vvalue; return simplex_inv<real>(vvalue); }
+  void setUnboundedValueV(const std::vector<real>& v) { vvalue = applyingBounds ? v : simplex_fwd<real>(v); needsRescore = true; }
+  // real-component accessors (erp.t:436-526): how the kernels read and write a choice
+  size_t getUnboundedRealComps(std::vector<real>& comps) {
+    if (is_vector()) { std::vector<real> v = getUnboundedValueV(); comps.insert(comps.end(), v.begin(), v.end()); return v.size(); }
+    comps.push_back(getUnboundedValue()); return 1;
+  }
+  size_t setUnboundedRealComps(const std::vector<real>& comps, size_t start) {
+    if (is_vector()) { std::vector<real> v(comps.begin() + start, comps.begin() + start + vvalue.size()); setUnboundedValueV(v); return v.size(); }
+    setUnboundedValue(comps[start]); return 1;
+  }
+  size_t setStoredRealComps(const std::vector<real>& comps, size_t start) {
+    if (is_vector()) { for (size_t i = 0; i < vvalue.size(); ++i) vvalue[i] = comps[start + i]; needsRescore = true; return vvalue.size(); }
+    setStoredValue(comps[start]); return 1;
+  }
+  size_t ncomps() const { return is_vector() ? vvalue.size() : 1; }
+  void init_vector(const std::vector<real>& params, unsigned lexid_, const std::vector<real>& initval) {   // erp.t:546-563
+    kind = ERP_DIRICHLET; vparams = params;
+    vvalue = applyingBounds ? simplex_inv<real>(initval) : initval;
+    rescore();
+    active = true; lexid = lexid_;
+  }
+  void update_vector(const std::vector<real>& params) {   // erp.t:576-610
+    bool needs = needsRescore;
+    if (is_dual<real>::value) { needs = true; vparams = params; }
+    else for (size_t i = 0; i < params.size(); ++i) if (!(val(vparams[i]) == val(params[i]))) { needs = true; vparams[i] = params[i]; }
+    if (needs) rescore();
+    active = true;
+  }
+
   int kind = ERP_GAUSSIAN;
   real value;        // stored value: constrained in float traces, unconstrained in dual traces
   real param0, param1;
@@ -118,6 +191,13 @@ template <class real> struct RandomChoice {   // RandomChoiceT, erp.t:286-311
   void setStoredValue(real newval) { value = newval; needsRescore = true; }
   // erp.t:623-640
   void rescore() {
+    if (is_vector()) {
+      std::vector<real> v = getValueV();
+      logprob = D::dirichlet_logprob<real>(v.data(), vparams.data(), (int)v.size());
+      if (applyingBounds) logprob = logprob + simplex_lpincr<real>(vvalue);
+      needsRescore = false;
+      return;
+    }
     real val = getValue();
     logprob = prior_logprob(val);
     if (applyingBounds) {
@@ -238,6 +318,27 @@ template <class real> struct Trace {   // RandExecTraceT, trace.t:523-540
     addPrior(rc.logprob);
     return rc.getValue();
   }
+  // vector-valued ERP site (dirichlet): same lookup, K real components
+  std::vector<real> dirichlet(const std::vector<real>& params) {
+    if (creating) {
+      rng().slot = (uint32_t)choices.size(); rng().k = 0;
+      std::vector<double> pv(params.size()), out(params.size());
+      for (size_t i = 0; i < params.size(); ++i) pv[i] = val(params[i]);
+      D::dirichlet_sample(pv.data(), (int)pv.size(), out.data());
+      std::vector<real> iv(out.begin(), out.end());
+      RandomChoice<real> rc;
+      rc.init_vector(params, (unsigned)choices.size(), iv);
+      choices.push_back(rc);
+      RandomChoice<real>& r = choices.back();
+      addPrior(r.logprob);
+      return r.getValueV();
+    }
+    RandomChoice<real>& rc = choices[counter];
+    counter = counter + 1;
+    rc.update_vector(params);
+    addPrior(rc.logprob);
+    return rc.getValueV();
+  }
   real gaussian(real mu, real sigma) { return erp(ERP_GAUSSIAN, mu, sigma); }
   real gamma(real shape, real scale) { return erp(ERP_GAMMA, shape, scale); }
   real beta(real a, real b) { return erp(ERP_BETA, a, b); }
@@ -251,6 +352,7 @@ template <class real> struct Trace {   // RandExecTraceT, trace.t:523-540
 
   // countChoices/getChoice({isStructural=false}) (trace.t:830-905): every choice here is non-structural and scalar
   size_t countChoices() const { return choices.size(); }
+  size_t countRealComps() const { size_t n = 0; for (auto& rc : choices) n += rc.ncomps(); return n; }
 };
 
 // DualTraceType.copyFromRealType(qs.float) (trace.t:167-173; erp.t:531-540)
@@ -262,6 +364,15 @@ inline void copyFromRealType(Trace<ad::num>& self, Trace<double>& other) {
     RandomChoice<ad::num> rc;
     rc.kind = o.kind; rc.param0 = ad::num(o.param0); rc.param1 = ad::num(o.param1);
     rc.logprob = ad::num(o.logprob); rc.active = o.active; rc.lexid = o.lexid;
+    if (o.is_vector()) {
+      for (auto& p : o.vparams) rc.vparams.push_back(ad::num(p));
+      std::vector<double> ov = o.getValueV();
+      std::vector<ad::num> mv;
+      for (double v : ov) mv.push_back(ad::num(v));
+      rc.setValueV(mv);
+      self.choices.push_back(rc);
+      continue;
+    }
     double otherval = o.getValue();
     rc.setValue(ad::num(otherval));
     self.choices.push_back(rc);

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libqsb200.so")
 
 FAM_INDEP, FAM_GAUSS_PREC, FAM_LOGISTIC, FAM_EIGHT_SCHOOLS, FAM_FUNNEL = 1, 2, 3, 4, 5
-ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM = 0, 1, 2, 3
+ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
 KERNEL_HMC, KERNEL_DRIFT, KERNEL_HARM = 1, 2, 3
 FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL = 1, 2, 4, 8
 
@@ -68,6 +68,12 @@ PROTOTYPES = {
     "qsb_sampler_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "qsb_sampler_diagnostics": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "qsb_sampler_fetch_record": (C.c_int, [C.c_void_p, dp, ip, dp, dp, ip, dp]),
+    "qsb_query_expectation": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, dp, dp]),
+    "qsb_query_expectation_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int32, dp, dp]),
+    "qsb_query_map": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, dp, dp]),
+    "qsb_query_map_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int32, dp, dp]),
+    "qsb_query_autocorrelation": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, dp, C.c_double, dp]),
+    "qsb_query_autocorrelation_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int32, dp, C.c_double, dp]),
     "qsb_logp_grad": (C.c_int, [C.c_void_p, dp, C.c_int32, dp, dp, dp]),
     "qsb_logprob": (C.c_int, [C.c_int32, dp, C.c_int32, dp]),
     "qsb_uniforms": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, dp]),

@@ -224,10 +224,13 @@ class Sampler:
 class SampleVector:
     """The filled ``S.Vector(Sample(T))`` (qs/infer.t:12-36; qs/lib/std.t:219-351): ``data`` is a
     structured array [numchains][nsamps] of {value[retdim], logprob, loglikelihood}.  With
-    numchains == 1 it is indexable like the reference's single vector of samples."""
+    numchains == 1 it is indexable like the reference's single vector of samples.  When it was filled by
+    ``MCMC`` it also keeps the sampler whose kept samples it mirrors, so that queries run on the
+    device-resident copy without re-uploading."""
 
-    def __init__(self, data):
+    def __init__(self, data, sampler=None):
         self.data = data
+        self._sampler = sampler
 
     def size(self):
         return self.data.shape[1]
@@ -245,6 +248,16 @@ class SampleVector:
 
     def __getitem__(self, i):
         return self.data[0, i]
+
+    # -- plumbing of the device queries
+    def _shape(self):
+        Cn, N = self.data.shape
+        return Cn, N, self.data.dtype["value"].shape[0]
+
+    def _host_args(self):
+        d = np.ascontiguousarray(self.data)
+        Cn, N, rd = self._shape()
+        return d, (d.ctypes.data_as(C.c_void_p), d.dtype.itemsize, Cn, N, rd)
 
 
 def MCMC(kernel, params=None, **kw):
@@ -278,19 +291,33 @@ def MCMC(kernel, params=None, **kw):
                         for name, m_, a_ in zip(kernel.names, st["sub_made"], st["sub_accepted"]):
                             out.write("   %s Acceptance Ratio: %u/%u (%g%%)\n" % (name, a_, m_, 100.0 * a_ / max(m_, 1)))
                     out.write("Time: %g\n" % (time.time() - t0))
-            finally:
+            except Exception:
                 s.close()
-            vec = SampleVector(data)
+                raise
+            vec = SampleVector(data, sampler=s)     # the sampler (and its device-resident samples) lives as long as the vector
             if samples is not None:
                 samples.data = data
+                samples._sampler = s
             return vec
         return doMCMC
     return method
 
 
-# ---- queries (qs/infer.t:128-294, the ones the hot path feeds)
+# ---- queries (qs/infer.t:128-294, the ones the hot path feeds), evaluated on the device through the C ABI
 def Samples():
     return lambda program: (lambda samples: samples)
+
+
+def _expectation(samples, doVariance):
+    Cn, N, rd = samples._shape()
+    mean = np.empty((Cn, rd)); var = np.empty(Cn) if doVariance else None
+    vp = var.ctypes.data_as(L.dp) if doVariance else None
+    if samples._sampler is not None and samples._sampler.h:
+        L.check(L.lib().qsb_query_expectation(samples._sampler.h, 0, Cn, mean.ctypes.data_as(L.dp), vp))
+    else:
+        keep, args = samples._host_args()
+        L.check(L.lib().qsb_query_expectation_host(*args, mean.ctypes.data_as(L.dp), vp))
+    return mean, var
 
 
 def Expectation(doVariance=False):
@@ -299,39 +326,52 @@ def Expectation(doVariance=False):
     [numchains][retdim] (and [numchains]); squeezed to the reference's shape when numchains == 1."""
     def query(program):
         def run(samples):
-            v = samples.value                                  # [C][N][retdim]
-            w = np.exp(samples.data["loglikelihood"])          # [C][N]
-            totalw = w[:, 1:].sum(axis=1)
-            m = (v[:, 0, :] + (w[:, 1:, None] * v[:, 1:, :]).sum(axis=1)) / totalw[:, None]
-            if v.shape[2] == 1:
-                m_out = m[:, 0]
-            else:
-                m_out = m
+            assert samples.size() > 0                          # S.assert(samples:size() > 0) (infer.t:153)
+            m, var = _expectation(samples, doVariance)
+            m_out = m[:, 0] if m.shape[1] == 1 else m
             if not doVariance:
-                return m_out[0] if v.shape[0] == 1 else m_out
-            diff = v - m[:, None, :]
-            var = (diff * diff).sum(axis=2).sum(axis=1) / v.shape[1]
-            return (m_out[0], var[0]) if v.shape[0] == 1 else (m_out, var)
+                return m_out[0] if m.shape[0] == 1 else m_out
+            return (m_out[0], var[0]) if m.shape[0] == 1 else (m_out, var)
         return run
     return query
 
 
+def MAP(program):
+    """infer.t:191-206, per chain: the value of the first sample with the largest logprob."""
+    def run(samples):
+        assert samples.size() > 0
+        Cn, N, rd = samples._shape()
+        val = np.empty((Cn, rd))
+        if samples._sampler is not None and samples._sampler.h:
+            L.check(L.lib().qsb_query_map(samples._sampler.h, 0, Cn, val.ctypes.data_as(L.dp), None))
+        else:
+            keep, args = samples._host_args()
+            L.check(L.lib().qsb_query_map_host(*args, val.ctypes.data_as(L.dp), None))
+        v = val[:, 0] if rd == 1 else val
+        return v[0] if Cn == 1 else v
+    return run
+
+
 def Autocorrelation(mean=None, variance=None):
     """infer.t:213-264, per chain."""
+    if mean is not None or variance is not None:
+        assert mean is not None and variance is not None, \
+            "Autocorrelation: both mean and variance must be provided if one is provided."     # infer.t:214-217
+
     def query(program):
         def run(samples):
-            v = samples.value
-            Cn, N, _ = v.shape
-            if mean is None or variance is None:
-                m, var = Expectation(True)(program)(SampleVector(samples.data))
-                m = np.reshape(m, (Cn, -1)); var = np.reshape(var, (Cn,))
+            Cn, N, rd = samples._shape()
+            ac = np.empty((Cn, N))
+            mp = None
+            if mean is not None:
+                marr = np.ascontiguousarray(np.broadcast_to(np.reshape(np.asarray(mean, dtype=np.float64), (-1,)), (rd,)))
+                mp = marr.ctypes.data_as(L.dp)
+            v = float(variance) if variance is not None else 0.0
+            if samples._sampler is not None and samples._sampler.h:
+                L.check(L.lib().qsb_query_autocorrelation(samples._sampler.h, 0, Cn, mp, v, ac.ctypes.data_as(L.dp)))
             else:
-                m = np.broadcast_to(np.reshape(mean, (1, -1)), (Cn, v.shape[2])); var = np.full(Cn, variance)
-            diff = v - m[:, None, :]
-            ac = np.zeros((Cn, N))
-            for t in range(N):
-                n = N - t
-                ac[:, t] = (diff[:, :n, :] * diff[:, t:, :]).sum(axis=(1, 2)) / (n * var)
+                keep, args = samples._host_args()
+                L.check(L.lib().qsb_query_autocorrelation_host(*args, mp, v, ac.ctypes.data_as(L.dp)))
             return ac[0] if Cn == 1 else ac
         return run
     return query

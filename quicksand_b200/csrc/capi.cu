@@ -138,6 +138,83 @@ __global__ void diagnostics_header_kernel(double* out, int retdim, double mh, do
   if (j < retdim) { double* o = out + (size_t)j * 12; o[0] = mh; o[1] = nh; o[7] = M; o[8] = N; }
 }
 
+// ---- queries (infer.t:146-264).  View of kept samples: value(k, c, j), logprob(k, c), loglikelihood(k, c)
+struct SampleView {
+  const double* samples; const double* samp_lp; const double* samp_ll;   // samp_ll == nullptr: loglikelihood = 0 (mcmc.t:70)
+  int layout;        // 1: [k][j][c]   32: [k][c][j]   0: AoS host vector staged on the device, element stride `stride` doubles
+  uint32_t SC; int retdim; uint64_t n; size_t stride;
+  __device__ __forceinline__ double value(uint64_t k, uint32_t c, int j) const {
+    if (layout == 1) return samples[((size_t)k * retdim + j) * SC + c];
+    if (layout == 32) return samples[((size_t)k * SC + c) * retdim + j];
+    return samples[((size_t)c * n + k) * stride + j];
+  }
+  __device__ __forceinline__ double logprob(uint64_t k, uint32_t c) const {
+    return layout ? samp_lp[(size_t)k * SC + c] : samples[((size_t)c * n + k) * stride + retdim];
+  }
+  __device__ __forceinline__ double loglik(uint64_t k, uint32_t c) const {
+    return layout ? 0.0 : samples[((size_t)c * n + k) * stride + retdim + 1];
+  }
+};
+
+// Expectation: thread per (chain, dim), samples summed in the reference's order (infer.t:154-165)
+__global__ void expectation_mean_kernel(SampleView V, uint32_t c0, uint32_t nc, double* mean) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= (size_t)nc * V.retdim) return;
+  const uint32_t c = c0 + (uint32_t)(t / V.retdim); const int j = (int)(t % V.retdim);
+  double m = V.value(0, c, j), totalw = 0.0;
+  for (uint64_t i = 1; i < V.n; ++i) {
+    const double w = exp(V.loglik(i, c));
+    totalw = totalw + w;
+    m = m + w * V.value(i, c, j);
+  }
+  mean[t] = m / totalw;
+}
+// variance: warp per chain; per sample the inner product diff.diff over dims (lanes), accumulated in sample order (infer.t:169-176)
+__global__ void expectation_var_kernel(SampleView V, uint32_t c0, uint32_t nc, const double* mean, double* var) {
+  const uint32_t w = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= nc) return;
+  const uint32_t c = c0 + w;
+  double v = 0.0;
+  for (uint64_t i = 0; i < V.n; ++i) {
+    double dd = 0.0;
+    for (int j = lane; j < V.retdim; j += 32) { const double diff = V.value(i, c, j) - mean[(size_t)w * V.retdim + j]; dd = dd + diff * diff; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+    v = v + dd;
+  }
+  if (lane == 0) var[w] = v / (double)V.n;
+}
+// MAP: thread per chain, first strict maximum (infer.t:195-201)
+__global__ void map_kernel(SampleView V, uint32_t c0, uint32_t nc, double* value, double* logprob) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nc) return;
+  const uint32_t c = c0 + w;
+  uint64_t best = 0; double bl = V.logprob(0, c);
+  for (uint64_t i = 1; i < V.n; ++i) { const double l = V.logprob(i, c); if (l > bl) { bl = l; best = i; } }
+  for (int j = 0; j < V.retdim; ++j) value[(size_t)w * V.retdim + j] = V.value(best, c, j);
+  if (logprob) logprob[w] = bl;
+}
+// Autocorrelation: block per chain, thread per lag t; the sum over i and the inner product over dims are sequential
+// like the reference's (infer.t:221-241).  mean: [nc][retdim] (per chain) or [retdim] (shared, per_chain = 0)
+__global__ void autocorrelation_kernel(SampleView V, uint32_t c0, const double* mean, const double* var, double shared_var, int per_chain, double* ac) {
+  const uint32_t w = blockIdx.x;
+  const uint32_t c = c0 + w;
+  const double* m = mean + (per_chain ? (size_t)w * V.retdim : 0);
+  const double v = per_chain ? var[w] : shared_var;
+  for (uint64_t t = threadIdx.x; t < V.n; t += blockDim.x) {
+    double act = 0.0;
+    const uint64_t n = V.n - t;
+    for (uint64_t i = 0; i < n; ++i) {
+      double ip = 0.0;
+      for (int j = 0; j < V.retdim; ++j) ip = ip + (V.value(i, c, j) - m[j]) * (V.value(i + t, c, j) - m[j]);
+      act = act + ip;
+    }
+    if (n > 0) act = act / ((double)n * v);
+    ac[(size_t)w * V.n + t] = act;
+  }
+}
+
 __global__ void uniforms_kernel(RngKey key, uint32_t chain, uint32_t iter, uint32_t slot, int n, double* out) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     SubStream s(key, chain, iter, slot);
@@ -151,6 +228,17 @@ __global__ void gaussians_kernel(RngKey key, uint32_t chain, uint32_t iter, uint
 __global__ void logprob_kernel(int which, const double* a, int n, double* out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (which == 8) {   // dirichlet (distrib.t:352-362) over the n tuples (theta_k, alpha_k, -): one value, in out[0]; others NaN
+    double r = nan("");
+    if (i == 0) {
+      double sum = 0.0;
+      for (int k = 0; k < n; ++k) sum = sum + a[3 * k + 1];
+      r = log_gamma5(sum);
+      for (int k = 0; k < n; ++k) { const double al = a[3 * k + 1]; r = r + (al - 1.0) * log(a[3 * k]); r = r - log_gamma5(al); }
+    }
+    out[i] = r;
+    return;
+  }
   const double* v = a + 3 * (size_t)i;
   double r;
   switch (which) {
@@ -211,9 +299,33 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
   switch (d->family) {
     case QSB_FAM_INDEP: {
       if (!d->erp_kind || !d->erp_p0 || !d->erp_p1) return bail(3, "INDEP: erp_kind/erp_p0/erp_p1 required");
-      for (int i = 0; i < d->dim; ++i) if (d->erp_kind[i] < 0 || d->erp_kind[i] > 3) return bail(3, "INDEP: unsupported ERP kind (continuous gaussian/gamma/beta/uniform only)");
-      int* k; double *p0, *p1;
-      if (m->arena.alloc(&k, d->dim) || m->arena.alloc(&p0, d->dim) || m->arena.alloc(&p1, d->dim)) return bail(4, "cudaMalloc failed");
+      for (int i = 0; i < d->dim; ++i) if (d->erp_kind[i] < 0 || d->erp_kind[i] > 4) return bail(3, "INDEP: unsupported ERP kind (continuous gaussian/gamma/beta/uniform/dirichlet only)");
+      // vector choices: K consecutive components of kind DIRICHLET with erp_p1 = 0, 1, .., K-1
+      std::vector<int> len(d->dim, 1), slot(d->dim, 0);
+      std::vector<double> asum(d->dim, 0.0);
+      int nerp = 0;
+      for (int i = 0; i < d->dim;) {
+        if (d->erp_kind[i] != QSB_ERP_DIRICHLET) { slot[i] = nerp++; ++i; continue; }
+        if (d->erp_p1[i] != 0.0) return bail(3, "INDEP: a dirichlet choice must start with erp_p1 = 0 (component index inside the choice)");
+        int j = i + 1;
+        while (j < d->dim && d->erp_kind[j] == QSB_ERP_DIRICHLET && d->erp_p1[j] == (double)(j - i)) ++j;
+        const int K = j - i;
+        if (K < 2 || K > 32) return bail(3, "INDEP: dirichlet choices of 2..32 components are supported");
+        for (int q = i; q < j; ++q) {
+          if (!(d->erp_p0[q] > 0.0)) return bail(3, "INDEP: dirichlet parameters must be positive");
+          len[q] = K; slot[q] = nerp;
+          for (int r = q + 1; r < j; ++r) asum[q] += d->erp_p0[r];
+        }
+        ++nerp; m->dev.has_vector = 1;
+        i = j;
+      }
+      int *k, *dl, *ds; double *p0, *p1, *da;
+      if (m->arena.alloc(&k, d->dim) || m->arena.alloc(&p0, d->dim) || m->arena.alloc(&p1, d->dim) ||
+          m->arena.alloc(&dl, d->dim) || m->arena.alloc(&ds, d->dim) || m->arena.alloc(&da, d->dim)) return bail(4, "cudaMalloc failed");
+      cudaMemcpy(dl, len.data(), sizeof(int) * d->dim, cudaMemcpyHostToDevice);
+      cudaMemcpy(ds, slot.data(), sizeof(int) * d->dim, cudaMemcpyHostToDevice);
+      cudaMemcpy(da, asum.data(), sizeof(double) * d->dim, cudaMemcpyHostToDevice);
+      m->dev.erp_len = dl; m->dev.erp_slot = ds; m->dev.erp_asum = da;
       cudaMemcpy(k, d->erp_kind, sizeof(int) * d->dim, cudaMemcpyHostToDevice);
       cudaMemcpy(p0, d->erp_p0, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
       cudaMemcpy(p1, d->erp_p1, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
@@ -385,8 +497,9 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   P.sample_chains = s->cfg.sample_chains;
   P.lag = 1;
   std::string why;
-  s->var = pick_variant(m->desc.family, P.d, cfg->reserved, why);
-  if (!s->var) return bail(2, why);
+  s->var = pick_variant(m->desc.family, P.d, m->dev.has_vector ? 1 : cfg->reserved, why);
+  if (!s->var) return bail(2, m->dev.has_vector ? "dirichlet choices run in the thread-per-chain mapping only (" + why + ")" : why);
+  if (m->dev.has_vector && cfg->reserved != 0 && cfg->reserved != 1) return bail(2, "dirichlet choices run in the thread-per-chain mapping only");
   if (m->desc.family == QSB_FAM_GAUSS_PREC) {
     const int d = P.d, npl = s->var->npl;
     for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) P.Sc[i * npl + j] = m->A[(size_t)i * d + j] + m->A[(size_t)j * d + i];
@@ -693,6 +806,122 @@ int qsb_sampler_diagnostics(qsb_sampler* s, int32_t maxlag, double* dst, int32_t
   if (!dst_is_device) cudaFree(out);
   if (e != cudaSuccess) return fail(100 + (int)e, std::string("diagnostics: ") + cudaGetErrorString(e));
   return 0;
+}
+
+// ---- queries
+}  // extern "C"
+
+struct DevTmp {   // scoped device scratch
+  std::vector<void*> p;
+  template <class T> cudaError_t get(T** q, size_t n) { *q = nullptr; cudaError_t e = cudaMalloc((void**)q, std::max<size_t>(n, 1) * sizeof(T)); if (e == cudaSuccess) p.push_back(*q); return e; }
+  ~DevTmp() { for (void* q : p) cudaFree(q); }
+};
+
+static int sampler_view(qsb_sampler* s, uint32_t c0, uint32_t c1, SampleView& V) {
+  if (!s) return fail(1, "null sampler");
+  CU(cudaSetDevice(s->m->device));
+  int G; const double *samples, *samp_lp; uint32_t SC; int retdim;
+  if (s->glm) glm_sampler_sample_view(s->glm, &samples, &samp_lp, &G, &SC, &retdim);
+  else { samples = s->P.samples; samp_lp = s->P.samp_lp; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }
+  const uint64_t n = qsb_sampler_num_samples(s);
+  if (n == 0 || !samples) return fail(2, "query: the sampler holds no samples");   // S.assert(samples:size() > 0) (infer.t:153, 194)
+  if (c1 > SC || c0 >= c1) return fail(2, "query: chain range out of bounds (chains stored: " + std::to_string(SC) + ")");
+  V.samples = samples; V.samp_lp = samp_lp; V.samp_ll = nullptr; V.layout = G == 1 ? 1 : 32; V.SC = SC; V.retdim = retdim; V.n = n; V.stride = 0;
+  return 0;
+}
+static int host_view(const void* samples, size_t stride_bytes, uint32_t nchains, uint64_t nsamps, int32_t retdim, DevTmp& tmp, SampleView& V) {
+  if (!samples || nchains == 0 || retdim <= 0) return fail(1, "query: bad argument");
+  if (nsamps == 0) return fail(2, "query: empty sample vector");
+  if (stride_bytes < (size_t)(retdim + 2) * 8 || stride_bytes % 8) return fail(2, "query: stride must be a multiple of 8 and >= element size");
+  double* d;
+  const size_t bytes = (size_t)nchains * nsamps * stride_bytes;
+  CU(tmp.get(&d, bytes / 8));
+  CU(cudaMemcpy(d, samples, bytes, cudaMemcpyHostToDevice));
+  V.samples = d; V.samp_lp = nullptr; V.samp_ll = nullptr; V.layout = 0; V.SC = nchains; V.retdim = retdim; V.n = nsamps; V.stride = stride_bytes / 8;
+  return 0;
+}
+static int run_expectation(const SampleView& V, uint32_t c0, uint32_t nc, cudaStream_t st, double* mean, double* var, double* mean_dev_out, double* var_dev_out) {
+  DevTmp tmp;
+  double *dm = mean_dev_out, *dv = var_dev_out;
+  if (!dm) CU(tmp.get(&dm, (size_t)nc * V.retdim));
+  if (!dv && (var || var_dev_out)) CU(tmp.get(&dv, nc));
+  const size_t total = (size_t)nc * V.retdim;
+  expectation_mean_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(V, c0, nc, dm);
+  if (dv) expectation_var_kernel<<<(unsigned)(((size_t)nc * 32 + 127) / 128), 128, 0, st>>>(V, c0, nc, dm, dv);
+  CU(cudaGetLastError());
+  if (mean) CU(cudaMemcpyAsync(mean, dm, total * 8, cudaMemcpyDeviceToHost, st));
+  if (var) CU(cudaMemcpyAsync(var, dv, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+static int run_map(const SampleView& V, uint32_t c0, uint32_t nc, cudaStream_t st, double* value, double* logprob) {
+  if (!value) return fail(1, "query: null output");
+  DevTmp tmp;
+  double *dv, *dl;
+  CU(tmp.get(&dv, (size_t)nc * V.retdim)); CU(tmp.get(&dl, nc));
+  map_kernel<<<(nc + 127) / 128, 128, 0, st>>>(V, c0, nc, dv, dl);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(value, dv, (size_t)nc * V.retdim * 8, cudaMemcpyDeviceToHost, st));
+  if (logprob) CU(cudaMemcpyAsync(logprob, dl, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+static int run_autocorrelation(const SampleView& V, uint32_t c0, uint32_t nc, cudaStream_t st, const double* mean, double variance, double* ac) {
+  if (!ac) return fail(1, "query: null output");
+  DevTmp tmp;
+  double *dm, *dv = nullptr, *dac;
+  CU(tmp.get(&dac, (size_t)nc * V.n));
+  if (mean) {
+    CU(tmp.get(&dm, V.retdim));
+    CU(cudaMemcpyAsync(dm, mean, (size_t)V.retdim * 8, cudaMemcpyHostToDevice, st));
+  } else {   // noMeanAndVar (infer.t:244-247): each chain's own Expectation(true)
+    CU(tmp.get(&dm, (size_t)nc * V.retdim)); CU(tmp.get(&dv, nc));
+    if (int rc = run_expectation(V, c0, nc, st, nullptr, nullptr, dm, dv)) return rc;
+  }
+  autocorrelation_kernel<<<nc, 128, 0, st>>>(V, c0, dm, dv, variance, mean ? 0 : 1, dac);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ac, dac, (size_t)nc * V.n * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" {
+
+int qsb_query_expectation(qsb_sampler* s, uint32_t c0, uint32_t c1, double* mean, double* var) {
+  SampleView V;
+  if (int rc = sampler_view(s, c0, c1, V)) return rc;
+  if (!mean) return fail(1, "query: null output");
+  s->launches += var ? 2 : 1;
+  return run_expectation(V, c0, c1 - c0, s->stream, mean, var, nullptr, nullptr);
+}
+int qsb_query_expectation_host(const void* samples, size_t stride_bytes, uint32_t nchains, uint64_t nsamps, int32_t retdim, double* mean, double* var) {
+  DevTmp tmp; SampleView V;
+  if (int rc = host_view(samples, stride_bytes, nchains, nsamps, retdim, tmp, V)) return rc;
+  if (!mean) return fail(1, "query: null output");
+  return run_expectation(V, 0, nchains, nullptr, mean, var, nullptr, nullptr);
+}
+int qsb_query_map(qsb_sampler* s, uint32_t c0, uint32_t c1, double* value, double* logprob) {
+  SampleView V;
+  if (int rc = sampler_view(s, c0, c1, V)) return rc;
+  ++s->launches;
+  return run_map(V, c0, c1 - c0, s->stream, value, logprob);
+}
+int qsb_query_map_host(const void* samples, size_t stride_bytes, uint32_t nchains, uint64_t nsamps, int32_t retdim, double* value, double* logprob) {
+  DevTmp tmp; SampleView V;
+  if (int rc = host_view(samples, stride_bytes, nchains, nsamps, retdim, tmp, V)) return rc;
+  return run_map(V, 0, nchains, nullptr, value, logprob);
+}
+int qsb_query_autocorrelation(qsb_sampler* s, uint32_t c0, uint32_t c1, const double* mean, double variance, double* ac) {
+  SampleView V;
+  if (int rc = sampler_view(s, c0, c1, V)) return rc;
+  s->launches += mean ? 1 : 3;
+  return run_autocorrelation(V, c0, c1 - c0, s->stream, mean, variance, ac);
+}
+int qsb_query_autocorrelation_host(const void* samples, size_t stride_bytes, uint32_t nchains, uint64_t nsamps, int32_t retdim,
+                                   const double* mean, double variance, double* ac) {
+  DevTmp tmp; SampleView V;
+  if (int rc = host_view(samples, stride_bytes, nchains, nsamps, retdim, tmp, V)) return rc;
+  return run_autocorrelation(V, 0, nchains, nullptr, mean, variance, ac);
 }
 
 int qsb_sampler_fetch_record(qsb_sampler* s, double* state, int32_t* accept, double* dh, double* step, int32_t* kidx, double* leap) {

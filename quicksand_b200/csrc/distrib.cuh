@@ -69,7 +69,33 @@ QSB_D double bernoulli_lp(bool val, double p) { return log(val ? p : 1.0 - p); }
 QSB_D double logistic_(double x) { return 1.0 / (1.0 + exp(-x)); }
 QSB_D double invlogistic_(double y) { return -log(1.0 / y - 1.0); }
 
-enum { ERP_GAUSSIAN = 0, ERP_GAMMA = 1, ERP_BETA = 2, ERP_UNIFORM = 3 };
+enum { ERP_GAUSSIAN = 0, ERP_GAMMA = 1, ERP_BETA = 2, ERP_UNIFORM = 3, ERP_DIRICHLET = 4 };
+
+// ---- dirichlet (distrib.t:336-362) under Bounds.UnitSimplex (erp.t:200-254), one component at a time.
+// A K-vector dirichlet choice occupies K consecutive real components; component K-1 of the unconstrained vector is
+// unused by the transform (zero gradient).  The stick-breaking recurrence is carried from component to component:
+//   z_k = logistic(x_k - log(K-1-k)),  y_k = stick*z_k,  stick -= y_k,  y_{K-1} = stick
+//   logJ = sum_{k<K-1} log stick_k + log z_k + log(1-z_k)
+//   lp   = lg5(sum alpha) + sum_k (alpha_k-1) log y_k - lg5(alpha_k)
+// and d(lp + logJ)/dx_k = alpha_k (1-z_k) - z_k * sum_{m>k} alpha_m  (what the tape AD accumulates through the recurrence).
+struct SimplexCarry { double stick, lp, lj; };
+// returns y_k; adds the component's terms to the carry; *g = d(lp+logJ)/dx_k
+QSB_D double dirichlet_component(SimplexCarry& c, int k, int K, double x, double alpha, double asum_after, double* g) {
+  const int Km1 = K - 1;
+  if (k == 0) { c.stick = 1.0; c.lp = log_gamma5(alpha + asum_after); c.lj = 0.0; }
+  double y, gi = 0.0;
+  if (k < Km1) {
+    const double z = logistic_(x - log((double)(Km1 - k)));
+    y = c.stick * z;
+    c.lj = c.lj + log(c.stick); c.lj = c.lj + log(z); c.lj = c.lj + log(1.0 - z);
+    c.stick = c.stick - y;
+    gi = alpha * (1.0 - z) - z * asum_after;
+  } else y = c.stick;
+  c.lp = c.lp + (alpha - 1.0) * log(y);
+  c.lp = c.lp - log_gamma5(alpha);
+  if (g) *g = gi;
+  return y;
+}
 
 // Forward transform x -> y of an ERP kind, with dy/dx as the tape AD would produce it.
 QSB_D double erp_fwd(int kind, double x, double p0, double p1, double* dydx) {

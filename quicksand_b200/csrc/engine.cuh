@@ -35,6 +35,10 @@ struct ModelDev {
   int family, dim, nobs, ret_mode;
   double ret_div, prior_sigma;
   const int* erp_kind; const double* p0; const double* p1;   // INDEP
+  // INDEP, dirichlet components (thread-per-chain mapping only): choice length K, sum of the later alphas of the choice,
+  // and the ERP index of every component (= the Philox slot of its forward sample; equals the component index without vector choices)
+  const int* erp_len; const double* erp_asum; const int* erp_slot;
+  int has_vector;
   // EIGHT_SCHOOLS observations, precomputed once per model with the same device operations the
   // per-term logprob would use (bit-identical): cy = 1.8378770664093453 + 2*log(sigma), s2 = sigma*sigma
   const double* y; const double* cy; const double* s2; const double* is2;   // is2 = 1/s2
@@ -109,6 +113,9 @@ static __device__ __noinline__ void erp_eval(int kind, double x, double p0, doub
   g = dlpdy * dydx + dlj;
 }
 static __device__ __noinline__ double erp_fwd_noinline(int kind, double x, double p0, double p1) { return erp_fwd(kind, x, p0, p1, nullptr); }
+static __device__ __noinline__ double dirichlet_component_noinline(SimplexCarry& c, int k, int K, double x, double alpha, double asum_after, double& g) {
+  return dirichlet_component(c, k, K, x, alpha, asum_after, &g);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Model log-densities.  Returns the dual-trace logprob (with log-Jacobians: what HMC's traceUpdate
@@ -123,14 +130,24 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
   const int d = m.dim;
   if (FAM == FAM_INDEP) {
     double lpd = 0.0, lpf = 0.0;
+    SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
       if (i < d) {
-        double lpy, lj, gi;
-        erp_eval(m.erp_kind[i], x[e], m.p0[i], m.p1[i], lpy, lj, gi);
-        lpf += lpy;
-        lpd += lpy + lj;
-        if (GRAD) g[e] = gi;
+        const int kind = m.erp_kind[i];
+        if (G == 1 && kind == ERP_DIRICHLET) {   // one component of a vector choice; the recurrence is carried in sc
+          double gi;
+          const int k = (int)m.p1[i], K = m.erp_len[i];
+          dirichlet_component_noinline(sc, k, K, x[e], m.p0[i], m.erp_asum[i], gi);
+          if (k == K - 1) { lpf += sc.lp; lpd += sc.lp + sc.lj; }
+          if (GRAD) g[e] = gi;
+        } else {
+          double lpy, lj, gi;
+          erp_eval(kind, x[e], m.p0[i], m.p1[i], lpy, lj, gi);
+          lpf += lpy;
+          lpd += lpy + lj;
+          if (GRAD) g[e] = gi;
+        }
       } else if (GRAD) g[e] = 0.0;
     }
     lp_float = Grp<G>::sum(lpf);
@@ -1057,10 +1074,14 @@ template <int FAM, int G, int NPL> struct Chain {
           const uint32_t SC = P.sample_chains;
           if (FAM == FAM_INDEP) {
             double sum = 0.0;
+            SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
             QSB_FOR_E {
               int i = e * G + lane;
               if (i < d) {
-                double y = erp_fwd_noinline(P.m.erp_kind[i], x[e], P.m.p0[i], P.m.p1[i]);
+                double y, gdummy;
+                if (G == 1 && P.m.erp_kind[i] == ERP_DIRICHLET)
+                  y = dirichlet_component_noinline(sc, (int)P.m.p1[i], P.m.erp_len[i], x[e], P.m.p0[i], P.m.erp_asum[i], gdummy);
+                else y = erp_fwd_noinline(P.m.erp_kind[i], x[e], P.m.p0[i], P.m.p1[i]);
                 if (P.m.ret_mode == 0) sum += y;
                 else P.samples[G == 1 ? ((size_t)sidx * P.retdim + i) * SC + c : ((size_t)sidx * SC + c) * P.retdim + i] = y;
               }
@@ -1116,16 +1137,39 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_c
   double lp0 = 0.0;
   if (FAM == FAM_INDEP) {
     double lp = 0.0;
+    QSB_FOR_E x[e] = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
-      x[e] = 0.0;
       if (i < d) {
         int kind = P.m.erp_kind[i];
         double p0 = P.m.p0[i], p1 = P.m.p1[i];
-        SubStream s(P.key, ch.gc, QSB_ITER_INIT, (uint32_t)i);
-        double y = erp_sample_seq(kind, s, p0, p1);
-        lp += erp_prior_lp(kind, y, p0, p1, nullptr);   // float trace: logprob of the sampled value itself
-        x[e] = erp_inv(kind, y, p0, p1);
+        const uint32_t slot = P.m.erp_slot ? (uint32_t)P.m.erp_slot[i] : (uint32_t)i;   // ERP index (trace.t:948-994 creates choices in program order)
+        if (G == 1 && kind == ERP_DIRICHLET) {
+          if ((int)p1 == 0) {
+            // dirichlet.sample (distrib.t:339-350): K gammas from the choice's sub-stream, normalised; logprob of the
+            // sampled vector (distrib.t:352-362); inverse stick breaking (erp.t:219-233), x[K-1] = 0
+            const int K = P.m.erp_len[i], Km1 = K - 1;
+            SubStream s(P.key, ch.gc, QSB_ITER_INIT, slot);
+            double t[32];
+            double ssum = 0.0, asum = 0.0;
+            for (int k = 0; k < K; ++k) { t[k] = gamma_sample_seq(s, P.m.p0[i + k], 1.0); ssum = ssum + t[k]; asum = asum + P.m.p0[i + k]; }
+            for (int k = 0; k < K; ++k) t[k] = t[k] / ssum;
+            double lpv = log_gamma5(asum);
+            for (int k = 0; k < K; ++k) { const double a = P.m.p0[i + k]; lpv = lpv + (a - 1.0) * log(t[k]); lpv = lpv - log_gamma5(a); }
+            lp += lpv;
+            double sticklen = t[Km1];
+            for (int k = Km1 - 1; k >= 0; --k) {
+              sticklen = sticklen + t[k];
+              const double z = t[k] / sticklen;
+              x[e + k < NPL ? e + k : NPL - 1] = invlogistic_(z) + log((double)(Km1 - k));
+            }
+          }
+        } else {
+          SubStream s(P.key, ch.gc, QSB_ITER_INIT, slot);
+          double y = erp_sample_seq(kind, s, p0, p1);
+          lp += erp_prior_lp(kind, y, p0, p1, nullptr);   // float trace: logprob of the sampled value itself
+          x[e] = erp_inv(kind, y, p0, p1);
+        }
       }
     }
     lp0 = Grp<G>::sum(lp);

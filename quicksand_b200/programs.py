@@ -89,13 +89,32 @@ _KIND = {"gaussian": L.ERP_GAUSSIAN, "gamma": L.ERP_GAMMA, "beta": L.ERP_BETA, "
 
 
 def indep(erps, ret="sum", ret_div=1.0):
-    """K independent ERPs with constant parameters, e.g. ``[("gamma", 2.0, 2.0)]`` with ret_div=10 for
-    ``return qs.gamma(2.0, 2.0, {struc=false})/10.0`` (test/testsuite.t:657-673)."""
-    kinds = np.array([_KIND[k] if isinstance(k, str) else int(k) for k, _, _ in erps], dtype=np.int32)
-    p0 = np.array([a for _, a, _ in erps], dtype=np.float64)
-    p1 = np.array([b for _, _, b in erps], dtype=np.float64)
-    return Program(L.FAM_INDEP, len(erps), erp_kind=kinds, erp_p0=p0, erp_p1=p1,
-                   ret_mode=0 if ret == "sum" else 1, ret_div=float(ret_div))
+    """Independent ERPs with constant parameters, e.g. ``[("gamma", 2.0, 2.0)]`` with ret_div=10 for
+    ``return qs.gamma(2.0, 2.0, {struc=false})/10.0`` (test/testsuite.t:657-673).  Entries:
+
+      ("gaussian", mu, sigma) ("gamma", shape, scale) ("beta", a, b) ("uniform", lo, hi)     erpdefs.t:28-36, 46-69, 92-100
+      ("gammamv", m, v)  -> gamma(m*m/v, v/m)                                                  erpdefs.t:72-80
+      ("betamv", m, v)   -> beta(-m*tmp/v, (m-1)*tmp/v), tmp = m*m - m + v (must be < 0)       erpdefs.t:103-117
+      ("dirichlet", [alpha_0 .. alpha_{K-1}])  one vector-valued choice of K real components   erpdefs.t:179-212
+    """
+    kinds, p0, p1 = [], [], []
+    for e in erps:
+        k = e[0]
+        if k == "dirichlet":
+            alphas = [float(a) for a in e[1]]
+            for j, a in enumerate(alphas):
+                kinds.append(L.ERP_DIRICHLET); p0.append(a); p1.append(float(j))
+            continue
+        a, b = float(e[1]), float(e[2])
+        if k == "gammamv":
+            k, a, b = "gamma", a * a / b, b / a
+        elif k == "betamv":
+            tmp = a * a - a + b
+            assert tmp < 0.0, "betamv: v must be less than m - m^2"          # S.assert(tmp < 0.0) (erpdefs.t:110)
+            k, a, b = "beta", -a * tmp / b, (a - 1) * tmp / b
+        kinds.append(_KIND[k] if isinstance(k, str) else int(k)); p0.append(a); p1.append(b)
+    return Program(L.FAM_INDEP, len(kinds), erp_kind=np.array(kinds, dtype=np.int32), erp_p0=np.array(p0, dtype=np.float64),
+                   erp_p1=np.array(p1, dtype=np.float64), ret_mode=0 if ret == "sum" else 1, ret_div=float(ret_div))
 
 
 def gauss_prec(A):

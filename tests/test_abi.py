@@ -66,21 +66,6 @@ def test_kernel_constructor_defaults_match_reference(qs):
         qs.HMCKernel(stepsize=1.0)
 
 
-def test_expectation_query_matches_reference_quirk(qs, oracle):
-    """infer.t:146-187 on a hand-made S.Vector(Sample): same numbers as the oracle's restatement."""
-    rng = np.random.default_rng(0)
-    dt = np.dtype([("value", np.float64, (3,)), ("logprob", np.float64), ("loglikelihood", np.float64)])
-    data = np.zeros((2, 17), dtype=dt)
-    data["value"] = rng.normal(size=(2, 17, 3))
-    vec = qs.SampleVector(data)
-    m, v = qs.Expectation(True)(None)(vec)
-    for c in range(2):
-        mo, vo = oracle.expectation(data["value"][c], do_variance=True)
-        assert np.allclose(m[c], mo, rtol=0, atol=1e-14) and abs(v[c] - vo) < 1e-13
-    ac = qs.Autocorrelation()(None)(vec)
-    assert np.allclose(ac[0], oracle.autocorrelation(data["value"][0]), atol=1e-12)
-
-
 def test_no_gpu_means_loud_failure(qs):
     import torch
     if torch.cuda.is_available():

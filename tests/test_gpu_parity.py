@@ -31,6 +31,13 @@ def test_device_densities_against_reference_goldens(qs):
     import json, os
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "testsuite_logprob_goldens.json")))
     for g in gold["cases"]:
+        if g["which"] == 8:      # dirichlet (testsuite.t:184-187): K tuples (theta_k, alpha_k, -)
+            K = len(g["args"]) // 2
+            a = np.zeros((K, 3)); a[:, 0] = g["args"][:K]; a[:, 1] = g["args"][K:]
+            out = np.empty(K)
+            L.check(L.lib().qsb_logprob(8, a.ctypes.data_as(L.dp), K, out.ctypes.data_as(L.dp)))
+            assert abs(out[0] - g["value"]) <= 1e-8, (g, out[0])
+            continue
         if g["which"] not in (0, 1, 2, 3, 4):
             continue
         a = np.array((g["args"] + [0.0, 0.0, 0.0])[:3], dtype=np.float64)
@@ -49,6 +56,10 @@ def _programs(qs):
     progs["gauss10"] = qs.programs.indep([("gaussian", 0.1, 0.5)] * 10, ret_div=10.0)
     progs["mixed10"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("gamma", 2.0, 2.0), ("beta", 2.0, 5.0), ("uniform", -1.0, 3.0),
                                            ("gamma", 0.7, 1.5)] * 2, ret="vector")
+    # vector-valued choices (testsuite.t:693-717, 886-897) and the mean/variance parametrisations (erpdefs.t:72-125)
+    progs["dirichlet4"] = qs.programs.indep([("dirichlet", [1.0, 1.0, 1.0, 1.0])], ret="vector")
+    progs["dirmix9"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("dirichlet", [2.0, 3.0, 5.0]), ("gammamv", 4.0, 8.0),
+                                           ("dirichlet", [0.7, 1.5, 1.0]), ("betamv", 0.3, 0.02)], ret="vector")
     progs["c2"] = qs.programs.c2_correlated_gaussian()[0]
     J = 11
     progs["schools13"] = qs.programs.eight_schools(rng.normal(4, 10, J), rng.uniform(8, 18, J))
@@ -62,8 +73,8 @@ def _programs(qs):
     return progs
 
 
-@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "c2", "schools13", "schools62",
-                                  "funnel12", "funnel70", "logistic20"])
+@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "dirichlet4", "dirmix9", "c2",
+                                  "schools13", "schools62", "funnel12", "funnel70", "logistic20"])
 def test_logp_and_gradient_match_tape_ad(qs, oracle, name):
     """Closed-form device gradients vs the oracle's tape AD (qs/lib/ad.t) on random unconstrained points."""
     prog = _programs(qs)[name]
@@ -84,6 +95,7 @@ HMC_FIXED = [
     ("gamma1", dict(numSteps=10, stepSize=0.2), 0, 1.0), ("beta1", dict(numSteps=10, stepSize=0.2), 0, 1.0),
     ("uniform1", dict(numSteps=10, stepSize=0.5), 0, 1.0),
     ("gauss10", dict(numSteps=10, stepSize=0.2), 0, 1.0), ("mixed10", dict(numSteps=5, stepSize=0.1), 0, 1.0),
+    ("dirichlet4", dict(numSteps=10, stepSize=0.2), 0, 1.0), ("dirmix9", dict(numSteps=5, stepSize=0.1), 0, 1.0),
     ("mixed10", dict(numSteps=5, stepSize=0.1), 32, 1.0),
     ("c2", dict(numSteps=16, stepSize=0.15), 0, 1.0),
     ("schools13", dict(numSteps=8, stepSize=0.02), 1, 0.95), ("schools13", dict(numSteps=8, stepSize=0.02), 32, 0.95),
@@ -117,7 +129,7 @@ def test_hmc_fixed_step_per_leapfrog_parity(qs, oracle, name, kp, mapping, min_c
 # between two CPU builds of the oracle that differ only in FMA contraction.
 HMC_ADAPT = [
     ("gaussian1", 1, 0, 0.9), ("gaussian1", 10, 0, 0.5), ("gamma1", 10, 0, 0.5), ("beta1", 1, 0, 0.9), ("uniform1", 10, 0, 0.8),
-    ("gauss10", 10, 0, 0.4), ("mixed10", 5, 32, 0.8), ("c2", 16, 0, 0.4),
+    ("gauss10", 10, 0, 0.4), ("mixed10", 5, 32, 0.8), ("c2", 16, 0, 0.4), ("dirichlet4", 10, 0, 0.4), ("dirmix9", 1, 0, 0.8),
     ("schools13", 1, 32, 0.9), ("schools13", 2, 1, 0.8), ("schools62", 1, 0, 0.9), ("funnel12", 1, 1, 0.9), ("funnel12", 2, 32, 0.8),
     ("funnel70", 1, 0, 0.9), ("logistic20", 1, 0, 0.9), ("logistic20", 2, 0, 0.05),
     ("schools13", 8, 32, 0.05), ("funnel12", 16, 1, 0.03), ("logistic20", 20, 0, 0.01),
@@ -140,7 +152,7 @@ def test_hmc_adaptive_search_and_dual_averaging(qs, oracle, name, L, mapping, mi
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0)])
+                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0)])
 def test_drift_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=64, iters=400, seed=99, mapping=mapping)
@@ -148,7 +160,7 @@ def test_drift_per_step_parity(qs, oracle, name, mapping):
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("gaussian1", 0), ("c2", 0), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0)])
+                                          ("funnel12", 1), ("funnel70", 0), ("dirichlet4", 0)])
 def test_harm_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.HARMKernel(), chains=64, iters=300, seed=5, mapping=mapping)
@@ -279,6 +291,71 @@ def test_sample_struct_layout_and_lag(qs):
     assert np.allclose(smp["value"][:, :, 0], vals, rtol=1e-13)
     assert np.all(smp["loglikelihood"] == 0.0)
     s.close()
+
+
+def test_queries_on_device_match_reference_arithmetic(qs, oracle):
+    """Expectation / Autocorrelation / MAP (infer.t:146-264) run as CUDA kernels: on a hand-made S.Vector(Sample) handed
+    over from the host, and on the device-resident samples of a sampler; both against the oracle's restatement
+    (mean from value[0] with weights summed from i = 1, variance / N)."""
+    rng = np.random.default_rng(0)
+    dt = np.dtype([("value", np.float64, (3,)), ("logprob", np.float64), ("loglikelihood", np.float64)])
+    data = np.zeros((2, 17), dtype=dt)
+    data["value"] = rng.normal(size=(2, 17, 3))
+    data["logprob"] = rng.normal(size=(2, 17))
+    data["logprob"][1, 5] = data["logprob"][1, 9] = 10.0          # tie: MAP keeps the first
+    vec = qs.SampleVector(data)
+    m, v = qs.Expectation(True)(None)(vec)
+    for c in range(2):
+        mo, vo = oracle.expectation(data["value"][c], do_variance=True)
+        assert np.array_equal(m[c], mo) and abs(v[c] - vo) < 1e-14
+    ac = qs.Autocorrelation()(None)(vec)
+    for c in range(2):
+        assert np.allclose(ac[c], oracle.autocorrelation(data["value"][c]), rtol=0, atol=1e-13)
+    ac2 = qs.Autocorrelation([0.0, 0.0, 0.0], 3.0)(None)(vec)
+    v0 = data["value"][0]
+    want = [(v0[:17 - t] * v0[t:]).sum() / ((17 - t) * 3.0) for t in range(17)]
+    assert np.allclose(ac2[0], want, rtol=0, atol=1e-13)
+    mp = qs.MAP(None)(vec)
+    assert np.array_equal(mp[0], data["value"][0, np.argmax(data["logprob"][0])]) and np.array_equal(mp[1], data["value"][1, 5])
+    with pytest.raises(AssertionError):
+        qs.Autocorrelation(mean=0.0)
+    # device-resident: both sample layouts (thread per chain / warp per chain) and the GLM path
+    for name, mapping in (("gauss10", 0), ("mixed10", 32), ("schools13", 32), ("logistic20", 0)):
+        prog = _programs(qs)[name]
+        s = qs.Sampler(prog, qs.HMCKernel(numSteps=3, stepSize=0.05, doStepSizeAdapt=False), numchains=5, seed=4, mapping=mapping)
+        s.init(); s.run(23, burnin=3, lag=2)
+        vec = qs.SampleVector(s.fetch_samples(), sampler=s)
+        host = qs.SampleVector(vec.data)
+        md, vd = qs.Expectation(True)(prog)(vec)
+        mh, vh = qs.Expectation(True)(prog)(host)
+        assert np.array_equal(md, mh) and np.array_equal(vd, vh)
+        vals = vec.value
+        for c in range(5):
+            mo, vo = oracle.expectation(vals[c], do_variance=True)
+            assert np.array_equal(np.reshape(md[c], -1), mo) and abs(vd[c] - vo) <= 1e-13 * max(1.0, abs(vo))
+        assert np.array_equal(qs.Autocorrelation()(prog)(vec), qs.Autocorrelation()(prog)(host))
+        assert np.allclose(qs.Autocorrelation()(prog)(vec)[2], oracle.autocorrelation(vals[2]), rtol=1e-12, atol=1e-13)
+        assert np.array_equal(qs.MAP(prog)(vec), qs.MAP(prog)(host))
+        best = np.argmax(vec.logprob, axis=1)
+        assert np.array_equal(np.reshape(qs.MAP(prog)(vec), (5, -1)), vals[np.arange(5), best])
+        s.close()
+
+
+def test_dirichlet_samples_live_on_the_simplex(qs):
+    """testsuite.t:693-717 'dirichlet array compile and run (HMC)' with many chains: values are a point of the simplex and
+    the pooled mean of Dirichlet(2,3,5) is alpha / sum(alpha).  Long burn-in on purpose: until a chain's first acceptance
+    the reference's Hamiltonian uses the float trace's logprob, which lacks the log-Jacobian (hmc.t:144, 179-180),
+    so chains initialised near the boundary of the simplex stay put for a while and the transient decays slowly."""
+    from quicksand_b200 import _lib as L
+    prog = qs.programs.indep([("dirichlet", [2.0, 3.0, 5.0])], ret="vector")
+    s = qs.Sampler(prog, qs.HMCKernel(numSteps=5, stepSize=0.3, doStepSizeAdapt=False), numchains=2048, seed=3)
+    s.init(); s.run(40, burnin=400)
+    v = s.fetch_values()
+    s.close()
+    assert np.abs(v.sum(axis=2) - 1.0).max() < 1e-12 and v.min() > 0.0
+    assert np.abs(v.mean(axis=(0, 1)) - np.array([0.2, 0.3, 0.5])).max() < 0.01
+    with pytest.raises(L.QsbError):   # vector choices need the thread-per-chain mapping
+        qs.Sampler(prog, qs.HMCKernel(), numchains=4, mapping=32)
 
 
 def test_error_behaviour(qs):

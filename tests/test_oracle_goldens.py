@@ -77,3 +77,43 @@ def test_stream_is_partition_invariant(oracle):
     a = oracle.run(prog, oracle.spec(oracle.HMC, numSteps=4), 7, 4, 10)
     b = oracle.run(prog, oracle.spec(oracle.HMC, numSteps=4), 7, 2, 10, chain_begin=2)
     assert np.array_equal(a["samples"][2:], b["samples"])
+
+
+def test_dirichlet_unit_simplex_restatement(oracle):
+    """erp.t:200-254 + distrib.t:336-362 in the oracle: the dual-trace density is lp(fwd(x)) + logJ(x); its tape-AD gradient
+    equals the closed form alpha_k (1 - z_k) - z_k * sum_{m>k} alpha_m the device uses; component K-1 is inert; a
+    Dirichlet(2,3,5) chain under HMC has mean alpha / sum(alpha)."""
+    alpha = np.array([2.0, 3.0, 5.0])
+    prog = oracle.Program.indep([4, 4, 4], alpha, [0, 1, 2], 1, 1.0)
+    assert prog.dim == 3 and prog.retdim == 3
+    x = np.array([0.3, -0.2, 1.7])
+    lpd, g, lpf = prog.logp_grad(x)
+    z = [1.0 / (1.0 + np.exp(-(x[k] - np.log(2 - k)))) for k in range(2)]
+    want = [alpha[k] * (1 - z[k]) - z[k] * alpha[k + 1:].sum() for k in range(2)] + [0.0]
+    assert np.allclose(g, want, rtol=0, atol=1e-13)
+    y = [z[0], (1 - z[0]) * z[1], (1 - z[0]) * (1 - z[1])]
+    assert abs(lpf - oracle.logprob(8, list(y) + list(alpha))) < 1e-13
+    lj = sum(np.log(s) + np.log(zz) + np.log(1 - zz) for s, zz in zip([1.0, 1 - z[0]], z))
+    assert abs(lpd - (lpf + lj)) < 1e-12
+    out = oracle.run(prog, oracle.spec(oracle.HMC, numSteps=5), 11, 16, 300, 100)
+    s = out["samples"]
+    assert np.abs(s.sum(axis=2) - 1.0).max() < 1e-12
+    assert np.abs(s.mean(axis=(0, 1)) - alpha / alpha.sum()).max() < 0.03
+
+
+def test_annealing_kernel_restatement(oracle):
+    """mcmc.t:297-319: temperature 1 everywhere is the plain kernel; a hot schedule changes the chain and kept samples store
+    logprob * temperature (mcmc.t:69), i.e. the untempered log-density of the kept state when it was scored this iteration."""
+    prog = oracle.Program.funnel(6)
+    sp = oracle.spec(oracle.DRIFT, scale=0.5)
+    a = oracle.run(prog, sp, 5, 3, 40, record=True)
+    b = oracle.run(prog, sp, 5, 3, 40, record=True, temps=[1.0] * 40)
+    c = oracle.run(prog, sp, 5, 3, 40, record=True, temps=[5.0] * 40)
+    assert np.array_equal(a["state"], b["state"]) and np.array_equal(a["logprobs"], b["logprobs"])
+    assert not np.array_equal(a["state"], c["state"])
+    assert c["accept"].mean() > a["accept"].mean()          # a flatter target accepts more
+    # constant temperature: logprob/T * T restores the log-density of the state
+    for ch in range(3):
+        lp = [prog.logp_grad(c["state"][ch, i])[2] for i in range(40)]
+        acc = c["accept"][ch].astype(bool)
+        assert np.allclose(np.array(lp)[acc], c["logprobs"][ch][acc], rtol=1e-12)
