@@ -75,6 +75,10 @@ typedef struct {
   const uint8_t* ybin;     /* LOGISTIC [nobs] 0/1 */
   const double* y;         /* EIGHT_SCHOOLS [nobs] */
   const double* sigma;     /* EIGHT_SCHOOLS [nobs] */
+  const int32_t* erp_lexid;/* INDEP [dim] or NULL: call-site id of each component's choice (erp.t:318-321); choices made by one
+                            * ERP call inside a loop share an id.  NULL = every choice is its own call site.  Only
+                            * DriftKernel{lexicalScaleSharing=true} reads it.  The other families have fixed sites:
+                            * GAUSS_PREC / LOGISTIC one loop; EIGHT_SCHOOLS mu, logtau, theta-loop; FUNNEL v, x-loop. */
 } qsb_model_desc;
 
 /* One transition kernel; nspecs > 1 means MixtureKernel(kernels, weights) (qs/mcmc.t:199-291). */
@@ -85,6 +89,8 @@ typedef struct {
   uint64_t numSteps;   /* HMC: numSteps (hmc.t:60) */
   double scale;        /* Drift / HARM: scale (drift.t:65, harm.t:18) */
   double weight;       /* mixture weight; ignored when nspecs == 1 */
+  int32_t lexicalScaleSharing; /* Drift: choices from one call site share one adapted bandwidth (drift.t:58-60, 71-73, 101-115) */
+  int32_t reserved;
 } qsb_kernel_spec;
 
 enum {

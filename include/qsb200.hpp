@@ -52,11 +52,11 @@ class Program {
 // ---- kernels
 struct Kernel { std::vector<qsb_kernel_spec> specs; };
 struct HMCParams { double stepSize = 1.0; uint64_t numSteps = 1; bool doStepSizeAdapt = true; };
-struct DriftParams { double scale = 1.0; bool doScaleAdapt = true; };
+struct DriftParams { double scale = 1.0; bool doScaleAdapt = true; bool lexicalScaleSharing = false; };
 struct HARMParams { double scale = 1.0; bool doScaleAdapt = true; };
-inline Kernel HMCKernel(HMCParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_HMC, p.doStepSizeAdapt ? 1 : 0, p.stepSize, p.numSteps, 1.0, 1.0}}}; }
-inline Kernel DriftKernel(DriftParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_DRIFT, p.doScaleAdapt ? 1 : 0, 1.0, 1, p.scale, 1.0}}}; }
-inline Kernel HARMKernel(HARMParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_HARM, p.doScaleAdapt ? 1 : 0, 1.0, 1, p.scale, 1.0}}}; }
+inline Kernel HMCKernel(HMCParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_HMC, p.doStepSizeAdapt ? 1 : 0, p.stepSize, p.numSteps, 1.0, 1.0, 0, 0}}}; }
+inline Kernel DriftKernel(DriftParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_DRIFT, p.doScaleAdapt ? 1 : 0, 1.0, 1, p.scale, 1.0, p.lexicalScaleSharing ? 1 : 0, 0}}}; }
+inline Kernel HARMKernel(HARMParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_HARM, p.doScaleAdapt ? 1 : 0, 1.0, 1, p.scale, 1.0, 0, 0}}}; }
 inline Kernel MixtureKernel(const std::vector<Kernel>& kernels, const std::vector<double>& weights) {
   if (kernels.size() != weights.size()) throw Error("MixtureKernel: number of kernels must equal number of weights");   // mcmc.t:200-201
   Kernel k;

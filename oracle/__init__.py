@@ -41,7 +41,8 @@ SLOT_MIXTURE = 0xFFFFFFFF
 
 class KernelSpec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("doAdapt", C.c_int32), ("stepSize", C.c_double),
-                ("numSteps", C.c_uint64), ("scale", C.c_double), ("weight", C.c_double)]
+                ("numSteps", C.c_uint64), ("scale", C.c_double), ("weight", C.c_double),
+                ("lexicalScaleSharing", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -78,6 +79,7 @@ def lib(variant=None):
                   "qso_program_eight_schools", "qso_program_funnel"):
             getattr(L, f).restype = C.c_void_p
         L.qso_program_indep.argtypes = [C.c_int, C.POINTER(C.c_int), dp, dp, C.c_int, C.c_double]
+        L.qso_program_indep_lexids.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.qso_program_gauss_prec.argtypes = [C.c_int, dp]
         L.qso_program_logistic.argtypes = [C.c_int, C.c_int, dp, C.POINTER(C.c_ubyte), C.c_double]
         L.qso_program_eight_schools.argtypes = [C.c_int, dp, dp]
@@ -153,11 +155,15 @@ class Program:
             pass
 
     @staticmethod
-    def indep(kinds, p0, p1, ret_mode=0, ret_div=1.0):
+    def indep(kinds, p0, p1, ret_mode=0, ret_div=1.0, lexids=None):
         k = np.ascontiguousarray(kinds, dtype=np.int32)
         a = np.ascontiguousarray(p0, dtype=np.float64)
         b = np.ascontiguousarray(p1, dtype=np.float64)
-        return Program(lib().qso_program_indep(len(k), k.ctypes.data_as(C.POINTER(C.c_int)), _dp(a), _dp(b), ret_mode, ret_div))
+        h = lib().qso_program_indep(len(k), k.ctypes.data_as(C.POINTER(C.c_int)), _dp(a), _dp(b), ret_mode, ret_div)
+        if lexids is not None:
+            lx = np.ascontiguousarray(lexids, dtype=np.int32)
+            lib().qso_program_indep_lexids(C.c_void_p(h), len(lx), lx.ctypes.data_as(C.POINTER(C.c_int)))
+        return Program(h)
 
     @staticmethod
     def gauss_prec(A):
@@ -190,8 +196,8 @@ class Program:
         return lpd.value, g, lpf.value
 
 
-def spec(kind, stepSize=1.0, numSteps=1, doAdapt=True, scale=1.0, weight=1.0):
-    return KernelSpec(kind, int(bool(doAdapt)), stepSize, numSteps, scale, weight)
+def spec(kind, stepSize=1.0, numSteps=1, doAdapt=True, scale=1.0, weight=1.0, lexicalScaleSharing=False):
+    return KernelSpec(kind, int(bool(doAdapt)), stepSize, numSteps, scale, weight, int(bool(lexicalScaleSharing)), 0)
 
 
 def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, record=False, temps=None):

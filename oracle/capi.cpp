@@ -24,6 +24,7 @@ typedef struct {
   uint64_t numSteps;   // HMC
   double scale;        // Drift / HARM
   double weight;       // MixtureKernel weight (ignored for a single kernel)
+  int32_t lexicalScaleSharing, reserved;   // Drift (drift.t:58-60, 71-73)
 } qso_kernel_spec;
 
 typedef struct {
@@ -90,6 +91,7 @@ void* qso_program_indep(int K, const int* kind, const double* p0, const double* 
   p->ret_mode = ret_mode; p->ret_div = ret_div; p->retdim = ret_mode == 0 ? 1 : K;
   return p;
 }
+void qso_program_indep_lexids(void* prog, int K, const int* lexid) { ((IndepErps*)prog)->lexid.assign(lexid, lexid + K); }
 void* qso_program_gauss_prec(int d, const double* A) {
   GaussPrecision* p = new GaussPrecision();
   p->d = d; p->A.assign(A, A + (size_t)d * d); p->retdim = d;
@@ -121,7 +123,7 @@ static Kernel* make_kernel(const qso_kernel_spec* specs, int nspecs) {
   auto one = [](const qso_kernel_spec& s) -> Kernel* {
     switch (s.kind) {
       case 1: return new HMCKernel(s.stepSize, s.numSteps, s.doAdapt != 0);
-      case 2: return new DriftKernel(s.scale, s.doAdapt != 0);
+      case 2: return new DriftKernel(s.scale, s.doAdapt != 0, s.lexicalScaleSharing != 0);
       case 3: return new HARMKernel(s.scale, s.doAdapt != 0);
     }
     return nullptr;

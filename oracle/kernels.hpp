@@ -234,17 +234,22 @@ struct RunningVar {
 
 inline double lerp_(double a, double b, double t) { return (1.0 - t) * a + t * b; }
 
-// ------------------------------------------------------------------ qs/drift.t:63-300  (lexicalScaleSharing=false)
+// ------------------------------------------------------------------ qs/drift.t:63-300
 struct DriftKernel : Kernel {
   struct ScaleAdapter { double scale; RunningVar varEst; };
   double initScale;
-  std::vector<ScaleAdapter> scales;   // scaleGroups(0)
-  bool adapting;
+  std::vector<std::vector<ScaleAdapter>> scaleGroups;
+  bool adapting, lexicalScaleSharing;
+  std::vector<unsigned> scaleGroupIndexForComp, indexWithinScaleGroupForComp;   // drift.t:101-105
+  ScaleAdapter* getScale(size_t i) {   // drift.t:107-114
+    if (lexicalScaleSharing) return &scaleGroups[scaleGroupIndexForComp[i]][indexWithinScaleGroupForComp[i]];
+    return &scaleGroups[0][i];
+  }
   std::vector<double> realcomps, realcomps_scratch;
   Trace<double>* lastTraceSeen = nullptr;
   int64_t lastNumUpdatesSeen = -1;
 
-  DriftKernel(double scale = 1.0, bool doScaleAdapt = true) { initScale = scale; adapting = doScaleAdapt; }
+  DriftKernel(double scale = 1.0, bool doScaleAdapt = true, bool lexical = false) { initScale = scale; adapting = doScaleAdapt; lexicalScaleSharing = lexical; }
 
   void next(Trace<double>* currTrace, uint32_t iter, uint32_t) override {   // drift.t:133-172
     propsMade = propsMade + 1;
@@ -252,7 +257,7 @@ struct DriftKernel : Kernel {
     size_t n = realcomps.size();
     for (size_t i = 0; i < n; ++i) {
       rng().at(iter, (uint32_t)i);
-      realcomps_scratch[i] = D::gaussian_sample(realcomps[i], scales[i].scale);
+      realcomps_scratch[i] = D::gaussian_sample(realcomps[i], getScale(i)->scale);
     }
     Trace<double> nextTrace = *currTrace;   // TraceType.salloc():copy(currTrace)
     { size_t index = 0; for (auto& rc : nextTrace.choices) index += rc.setUnboundedRealComps(realcomps_scratch, index); }
@@ -276,22 +281,45 @@ struct DriftKernel : Kernel {
       realcomps.clear();
       size_t numvars = currTrace->countChoices();
       if (numvars == 0) { std::printf("DriftKernel: found 0 non-structural random choices\n"); std::abort(); }
-      for (size_t i = 0; i < numvars; ++i) currTrace->choices[i].getUnboundedRealComps(realcomps);
+      std::vector<unsigned> nCompsPerScaleGroup;
+      std::vector<std::pair<unsigned, unsigned>> lexidToGroupIndex;   // HashMap(uint,uint) of drift.t:181
+      if (lexicalScaleSharing) { scaleGroupIndexForComp.clear(); indexWithinScaleGroupForComp.clear(); }
+      else if (scaleGroups.empty()) scaleGroups.emplace_back();
+      for (size_t i = 0; i < numvars; ++i) {
+        RandomChoice<double>& rc = currTrace->choices[i];
+        size_t ncomps = rc.getUnboundedRealComps(realcomps);
+        if (lexicalScaleSharing) {   // drift.t:208-235
+          unsigned lexid = rc.lexid, g = 0;
+          bool found = false;
+          for (auto& kv : lexidToGroupIndex) if (kv.first == lexid) { g = kv.second; found = true; }
+          if (!found) {
+            g = (unsigned)nCompsPerScaleGroup.size();
+            lexidToGroupIndex.emplace_back(lexid, g);
+            nCompsPerScaleGroup.push_back(0);
+            while (scaleGroups.size() < g + 1) scaleGroups.emplace_back();
+          }
+          for (size_t j = 0; j < ncomps; ++j) { scaleGroupIndexForComp.push_back(g); indexWithinScaleGroupForComp.push_back((unsigned)j); }
+          if (ncomps > nCompsPerScaleGroup[g]) nCompsPerScaleGroup[g] = (unsigned)ncomps;
+        }
+      }
       size_t n = realcomps.size();
       realcomps_scratch.assign(n, 0.0);
-      for (size_t j = scales.size(); j < n; ++j) { ScaleAdapter s; s.scale = initScale; scales.push_back(s); }
+      if (!lexicalScaleSharing) nCompsPerScaleGroup.push_back((unsigned)n);
+      for (size_t i = 0; i < nCompsPerScaleGroup.size(); ++i)   // drift.t:262-269
+        for (size_t j = scaleGroups[i].size(); j < nCompsPerScaleGroup[i]; ++j) { ScaleAdapter s; s.scale = initScale; scaleGroups[i].push_back(s); }
     }
   }
   void unconstrained_state(Trace<double>*, std::vector<double>& out) override { out = realcomps; }
   void adapt() {   // drift.t:274-300
     double ratio = (double)propsAccepted / propsMade;
     for (size_t i = 0; i < realcomps.size(); ++i) {
-      if (ratio >= 0.05 && propsAccepted > 5) scales[i].varEst.update(realcomps[i]);
+      if (ratio >= 0.05 && propsAccepted > 5) getScale(i)->varEst.update(realcomps[i]);
     }
-    for (auto& scale : scales) {
-      if (scale.varEst.getN() > 100) scale.scale = scale.varEst.getStdDev();
-      if (ratio < 0.05 && propsAccepted > 5) scale.scale = scale.scale * 0.99;
-    }
+    for (auto& scaleGroup : scaleGroups)
+      for (auto& scale : scaleGroup) {
+        if (scale.varEst.getN() > 100) scale.scale = scale.varEst.getStdDev();
+        if (ratio < 0.05 && propsAccepted > 5) scale.scale = scale.scale * 0.99;
+      }
   }
 };
 

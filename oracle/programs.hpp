@@ -25,6 +25,7 @@ enum Family { FAM_INDEP = 1, FAM_GAUSS_PREC = 2, FAM_LOGISTIC = 3, FAM_EIGHT_SCH
 struct IndepErps : Program {
   std::vector<int> kind;
   std::vector<double> p0, p1;
+  std::vector<int> lexid;   // call-site id per entry (empty: every choice is its own call site)
   int ret_mode = 0;
   double ret_div = 1.0;
   // Entries are per real component.  A dirichlet choice of K components is K consecutive entries of kind
@@ -33,6 +34,7 @@ struct IndepErps : Program {
     size_t K = kind.size();
     real sum = real(0.0);
     for (size_t i = 0; i < K;) {
+      t.site = lexid.empty() ? (unsigned)i : (unsigned)lexid[i];
       if (kind[i] == ERP_DIRICHLET) {
         size_t j = i + 1;
         while (j < K && kind[j] == ERP_DIRICHLET && p1[j] == (double)(j - i)) ++j;
@@ -58,6 +60,7 @@ struct GaussPrecision : Program {
   std::vector<double> A;   // d x d row-major
   template <class real> void body(Trace<real>& t) {
     std::vector<real> x(d);
+    t.site = 0;   // one call site inside the loop
     for (int i = 0; i < d; ++i) x[i] = t.gaussian(real(0.0), real(1.0));
     real q = real(0.0);
     for (int i = 0; i < d; ++i)
@@ -76,6 +79,7 @@ struct Logistic : Program {
   std::vector<unsigned char> y; // N
   template <class real> void body(Trace<real>& t) {
     std::vector<real> theta(d);
+    t.site = 0;
     for (int j = 0; j < d; ++j) theta[j] = t.gaussian(real(0.0), real(prior_sigma));
     for (int i = 0; i < N; ++i) {
       real z = real(0.0);
@@ -95,8 +99,11 @@ struct EightSchools : Program {
   int J = 0;
   std::vector<double> y, sigma;
   template <class real> void body(Trace<real>& t) {
+    t.site = 0;
     real mu = t.gaussian(real(0.0), real(5.0));
+    t.site = 1;
     real logtau = t.gaussian(real(0.0), real(1.0));
+    t.site = 2;   // theta_j: one call site inside the loop
     real tau = tmath::exp(logtau);
     t.returnValue.push_back(mu);
     t.returnValue.push_back(logtau);
@@ -113,7 +120,9 @@ struct EightSchools : Program {
 struct Funnel : Program {
   int d = 0;
   template <class real> void body(Trace<real>& t) {
+    t.site = 0;
     real v = t.gaussian(real(0.0), real(3.0));
+    t.site = 1;   // x_i: one call site inside the loop
     real s = tmath::exp(v / 2.0);
     t.returnValue.push_back(v);
     for (int i = 0; i < d - 1; ++i) t.returnValue.push_back(t.gaussian(real(0.0), s));

@@ -244,6 +244,9 @@ template <class real> struct Trace {   // RandExecTraceT, trace.t:523-540
   std::vector<RandomChoice<real>> choices;   // the flat non-structural choice list (trace.t:314-320)
   size_t counter = 0;
   bool creating = false;
+  // lexical id of the ERP call site being executed (erp.t:674-679 passes a per-call-site id to the constructor;
+  // getLexicalID erp.t:318-321).  A program sets it before each ERP call: calls inside one loop share one id.
+  unsigned site = 0;
   real logprob, loglikelihood;
   double logprob_val = 0.0, loglik_val = 0.0; // val(logprob), val(loglikelihood): kept because dual nodes die with the tape
   double temperature = 1.0;
@@ -306,7 +309,7 @@ template <class real> struct Trace {   // RandExecTraceT, trace.t:523-540
       RandomChoice<real> rc;
       rc.kind = kind;
       double sampled = rc.sample(val(p0), val(p1));
-      rc.init(kind, p0, p1, (unsigned)choices.size(), real(sampled));
+      rc.init(kind, p0, p1, site, real(sampled));
       choices.push_back(rc);
       RandomChoice<real>& r = choices.back();
       addPrior(r.logprob);
@@ -327,7 +330,7 @@ template <class real> struct Trace {   // RandExecTraceT, trace.t:523-540
       D::dirichlet_sample(pv.data(), (int)pv.size(), out.data());
       std::vector<real> iv(out.begin(), out.end());
       RandomChoice<real> rc;
-      rc.init_vector(params, (unsigned)choices.size(), iv);
+      rc.init_vector(params, site, iv);
       choices.push_back(rc);
       RandomChoice<real>& r = choices.back();
       addPrior(r.logprob);

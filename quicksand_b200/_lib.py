@@ -22,12 +22,13 @@ class ModelDesc(C.Structure):
     _fields_ = [("family", C.c_int32), ("dim", C.c_int32), ("nobs", C.c_int32), ("ret_mode", C.c_int32),
                 ("ret_div", C.c_double), ("prior_sigma", C.c_double),
                 ("erp_kind", ip), ("erp_p0", dp), ("erp_p1", dp), ("A", dp), ("X", dp),
-                ("ybin", C.POINTER(C.c_uint8)), ("y", dp), ("sigma", dp)]
+                ("ybin", C.POINTER(C.c_uint8)), ("y", dp), ("sigma", dp), ("erp_lexid", ip)]
 
 
 class KernelSpec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("doAdapt", C.c_int32), ("stepSize", C.c_double),
-                ("numSteps", C.c_uint64), ("scale", C.c_double), ("weight", C.c_double)]
+                ("numSteps", C.c_uint64), ("scale", C.c_double), ("weight", C.c_double),
+                ("lexicalScaleSharing", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RunConfig(C.Structure):

@@ -40,7 +40,7 @@ def HMCKernel(params=None, **kw):
     if unknown:
         raise TypeError("HMCKernel: unknown params %s" % sorted(unknown))
     adapt = p.get("doStepSizeAdapt", True)                     # hmc.t:61-62
-    s = L.KernelSpec(L.KERNEL_HMC, int(bool(adapt)), float(p.get("stepSize", 1.0)), int(p.get("numSteps", 1)), 1.0, 1.0)
+    s = L.KernelSpec(L.KERNEL_HMC, int(bool(adapt)), float(p.get("stepSize", 1.0)), int(p.get("numSteps", 1)), 1.0, 1.0, 0, 0)
     return KernelSpecs([s], ["HMCKernel"])
 
 
@@ -49,10 +49,9 @@ def DriftKernel(params=None, **kw):
     unknown = set(p) - {"scale", "doScaleAdapt", "lexicalScaleSharing"}
     if unknown:
         raise TypeError("DriftKernel: unknown params %s" % sorted(unknown))
-    if p.get("lexicalScaleSharing", False):
-        raise NotImplementedError("DriftKernel: lexicalScaleSharing is a next-row item (SURVEY.md 8f-4)")
     adapt = p.get("doScaleAdapt", True)                        # drift.t:66-67
-    s = L.KernelSpec(L.KERNEL_DRIFT, int(bool(adapt)), 1.0, 1, float(p.get("scale", 1.0)), 1.0)
+    lexical = p.get("lexicalScaleSharing", False)              # drift.t:71-73
+    s = L.KernelSpec(L.KERNEL_DRIFT, int(bool(adapt)), 1.0, 1, float(p.get("scale", 1.0)), 1.0, int(bool(lexical)), 0)
     return KernelSpecs([s], ["DriftKernel"])
 
 
@@ -62,7 +61,7 @@ def HARMKernel(params=None, **kw):
     if unknown:
         raise TypeError("HARMKernel: unknown params %s" % sorted(unknown))
     adapt = p.get("doScaleAdapt", True)                        # harm.t:19-20
-    s = L.KernelSpec(L.KERNEL_HARM, int(bool(adapt)), 1.0, 1, float(p.get("scale", 1.0)), 1.0)
+    s = L.KernelSpec(L.KERNEL_HARM, int(bool(adapt)), 1.0, 1, float(p.get("scale", 1.0)), 1.0, 0, 0)
     return KernelSpecs([s], ["HARMKernel"])
 
 
@@ -75,7 +74,7 @@ def MixtureKernel(kernels, weights):
         if k.anneal is not None:
             raise NotImplementedError("MixtureKernel: anneal the mixture (AnnealingKernel(MixtureKernel(...))), not its parts")
         s = k.specs[0]
-        specs.append(L.KernelSpec(s.kind, s.doAdapt, s.stepSize, s.numSteps, s.scale, float(w)))
+        specs.append(L.KernelSpec(s.kind, s.doAdapt, s.stepSize, s.numSteps, s.scale, float(w), s.lexicalScaleSharing, 0))
         names.append(k.names[0])
     return KernelSpecs(specs, names)
 

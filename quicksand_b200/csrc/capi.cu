@@ -326,6 +326,24 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
       cudaMemcpy(ds, slot.data(), sizeof(int) * d->dim, cudaMemcpyHostToDevice);
       cudaMemcpy(da, asum.data(), sizeof(double) * d->dim, cudaMemcpyHostToDevice);
       m->dev.erp_len = dl; m->dev.erp_slot = ds; m->dev.erp_asum = da;
+      {
+        // DriftKernel lexical scale sharing (drift.t:208-235): adapter of a component = (group of its choice's call site in
+        // order of first appearance, index inside the choice), numbered in order of first appearance
+        std::vector<int> amap(d->dim, 0);
+        std::vector<std::pair<int, int>> seen;   // (lexid, k) -> adapter id = position
+        for (int i = 0; i < d->dim; ++i) {
+          const int lex = d->erp_lexid ? d->erp_lexid[i] : slot[i];
+          const int kk = d->erp_kind[i] == QSB_ERP_DIRICHLET ? (int)d->erp_p1[i] : 0;
+          int a = -1;
+          for (size_t q = 0; q < seen.size(); ++q) if (seen[q].first == lex && seen[q].second == kk) { a = (int)q; break; }
+          if (a < 0) { a = (int)seen.size(); seen.emplace_back(lex, kk); }
+          amap[i] = a;
+        }
+        int* dm;
+        if (m->arena.alloc(&dm, d->dim)) return bail(4, "cudaMalloc failed");
+        cudaMemcpy(dm, amap.data(), sizeof(int) * d->dim, cudaMemcpyHostToDevice);
+        m->dev.lex_map = dm; m->dev.n_adapters = (int)seen.size();
+      }
       cudaMemcpy(k, d->erp_kind, sizeof(int) * d->dim, cudaMemcpyHostToDevice);
       cudaMemcpy(p0, d->erp_p0, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
       cudaMemcpy(p1, d->erp_p1, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
@@ -337,6 +355,7 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
       if (!d->A) return bail(3, "GAUSS_PREC: A required");
       if (d->dim > 16) return bail(3, "GAUSS_PREC: dim <= 16 supported (thread-per-chain register path)");
       m->A.assign(d->A, d->A + (size_t)d->dim * d->dim);
+      m->dev.n_adapters = 1;
       break;
     }
     case QSB_FAM_LOGISTIC: {
@@ -355,9 +374,10 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
       precompute_obs_kernel<<<(d->nobs + 127) / 128, 128>>>(sg, cy, s2, is2, d->nobs);
       if (cudaDeviceSynchronize() != cudaSuccess) return bail(6, "precompute_obs_kernel failed");
       m->dev.y = y; m->dev.cy = cy; m->dev.s2 = s2; m->dev.is2 = is2; m->sigma_dev = sg;
+      m->dev.n_adapters = 3;
       break;
     }
-    case QSB_FAM_FUNNEL: break;
+    case QSB_FAM_FUNNEL: m->dev.n_adapters = 2; break;
     default: return bail(2, "qsb_model_create: unknown family");
   }
   *out = m;
@@ -420,7 +440,11 @@ static int alloc_engine_state(qsb_sampler* s) {
     A(a.alloc(&P.da_k, C));
     A(a.alloc(&P.hmc_dualT, C)); A(a.alloc(&P.hmc_gT, C));
   }
-  if (has_drift) { A(a.alloc(&P.dr_mean, C * d)); A(a.alloc(&P.dr_m2, C * d)); A(a.alloc(&P.dr_s0, C)); A(a.alloc(&P.dr_mult, C)); A(a.alloc(&P.dr_n, C)); }
+  if (has_drift && !P.dr_lexical) { A(a.alloc(&P.dr_mean, C * d)); A(a.alloc(&P.dr_m2, C * d)); A(a.alloc(&P.dr_s0, C)); A(a.alloc(&P.dr_mult, C)); A(a.alloc(&P.dr_n, C)); }
+  if (has_drift && P.dr_lexical) {   // one ScaleAdapter per (call site, index inside the choice) and chain: [adapter][chain]
+    const size_t na = (size_t)P.m.n_adapters;
+    A(a.alloc(&P.ls_scale, na * C)); A(a.alloc(&P.ls_mean, na * C)); A(a.alloc(&P.ls_m2, na * C)); A(a.alloc(&P.ls_n, na * C));
+  }
   if (has_harm) A(a.alloc(&P.ha_scale, C));
   A(a.alloc(&P.made, ns * C)); A(a.alloc(&P.acc, ns * C));
   A(a.alloc(&P.counters, 4)); A(a.alloc(&P.status, 1));
@@ -443,6 +467,10 @@ static int reset_kernel_state(qsb_sampler* s) {
       CU(fill(P.hmc_dualT, C, 1.0, st)); CU(fill(P.hmc_gT, C, 1.0, st));
       CU(cudaMemsetAsync(P.da_gbar, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_xbar, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_x0, 0, 8 * C, st));
       CU(cudaMemsetAsync(P.da_lastx, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_gamma, 0, 8 * C, st)); CU(cudaMemsetAsync(P.da_k, 0, 4 * C, st));
+    } else if (P.kind[k] == K_DRIFT && P.dr_lexical) {
+      const size_t na = (size_t)P.m.n_adapters;
+      CU(fill(P.ls_scale, na * C, P.scale0[k], st));
+      CU(cudaMemsetAsync(P.ls_mean, 0, 8 * na * C, st)); CU(cudaMemsetAsync(P.ls_m2, 0, 8 * na * C, st)); CU(cudaMemsetAsync(P.ls_n, 0, 4 * na * C, st));
     } else if (P.kind[k] == K_DRIFT) {
       CU(fill(P.dr_s0, C, P.scale0[k], st)); CU(fill(P.dr_mult, C, 1.0, st));
       CU(cudaMemsetAsync(P.dr_n, 0, 4 * C, st)); CU(cudaMemsetAsync(P.dr_mean, 0, 8 * C * d, st)); CU(cudaMemsetAsync(P.dr_m2, 0, 8 * C * d, st));
@@ -493,7 +521,9 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   for (int i = 0; i < nspecs; ++i) {
     P.kind[i] = specs[i].kind; P.doAdapt[i] = specs[i].doAdapt; P.stepSize0[i] = specs[i].stepSize;
     P.numSteps[i] = (uint32_t)specs[i].numSteps; P.scale0[i] = specs[i].scale; P.weight[i] = specs[i].weight;
+    if (specs[i].kind == QSB_KERNEL_DRIFT && specs[i].lexicalScaleSharing) P.dr_lexical = 1;
   }
+  if (P.dr_lexical && m->dev.n_adapters > 32) return bail(2, "DriftKernel{lexicalScaleSharing}: at most 32 scale adapters (call site x index inside the choice)");
   P.sample_chains = s->cfg.sample_chains;
   P.lag = 1;
   std::string why;
@@ -643,7 +673,9 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
     }
     bool has_hmc = false;
     for (int k = 0; k < R.nsub; ++k) has_hmc |= R.kind[k] == K_HMC;
-    if (has_hmc) s->var->advance(R, s->stream); else s->var->advance_nohmc(R, s->stream);
+    if (R.dr_lexical) s->var->advance_lex(R, s->stream);
+    else if (has_hmc) s->var->advance(R, s->stream);
+    else s->var->advance_nohmc(R, s->stream);
   }
   ++s->launches;
   CU(cudaEventRecord(s->ev1, s->stream));
@@ -950,7 +982,7 @@ int qsb_logp_grad(qsb_model* m, const double* x, int32_t n, double* lp_dual, dou
     if (glm_logp_grad(&m->glm, x, n, lp_dual, grad, lp_float, why)) return fail(5, why);
     return 0;
   }
-  qsb_kernel_spec spec = {QSB_KERNEL_HMC, 0, 1.0, 1, 1.0, 1.0};
+  qsb_kernel_spec spec = {QSB_KERNEL_HMC, 0, 1.0, 1, 1.0, 1.0, 0, 0};
   qsb_run_config cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.numchains = (uint32_t)n; cfg.device = m->device;
   const char* env = getenv("QSB_TEST_MAPPING");

@@ -39,6 +39,9 @@ struct ModelDev {
   // and the ERP index of every component (= the Philox slot of its forward sample; equals the component index without vector choices)
   const int* erp_len; const double* erp_asum; const int* erp_slot;
   int has_vector;
+  // DriftKernel{lexicalScaleSharing} (drift.t:101-115, 208-235): scale adapter of every component.  INDEP: lex_map;
+  // GAUSS_PREC: one; EIGHT_SCHOOLS: mu, logtau, theta-loop; FUNNEL: v, x-loop
+  const int* lex_map; int n_adapters;
   // EIGHT_SCHOOLS observations, precomputed once per model with the same device operations the
   // per-term logprob would use (bit-identical): cy = 1.8378770664093453 + 2*log(sigma), s2 = sigma*sigma
   const double* y; const double* cy; const double* s2; const double* is2;   // is2 = 1/s2
@@ -62,6 +65,9 @@ struct EngineParams {
   uint32_t* da_k;
   double *dr_mean, *dr_m2, *dr_s0, *dr_mult;
   uint32_t* dr_n;
+  int dr_lexical;                   // lexicalScaleSharing: ScaleAdapter {scale, RunningVar} per adapter and chain, [adapter][C]
+  double *ls_scale, *ls_mean, *ls_m2;
+  uint32_t* ls_n;
   double* ha_scale;
   unsigned long long *made, *acc;   // [nsub][C]
   unsigned long long* counters;     // [0] gradient evaluations, [1] leapfrog steps (inside :next)
@@ -798,6 +804,216 @@ template <int FAM, int G, int NPL> struct Chain {
     return accept;
   }
 
+  // ---- DriftKernel{lexicalScaleSharing = true} (drift.t:101-115, 208-235, 274-300): one ScaleAdapter per call site (and index
+  // inside a vector choice); every component of the site feeds the same RunningVar and is proposed with the same scale.
+  __device__ __forceinline__ int adapter_of(int i) const {
+    if (FAM == FAM_INDEP) return P.m.lex_map[i];
+    if (FAM == FAM_EIGHT_SCHOOLS) return i < 2 ? i : 2;
+    if (FAM == FAM_FUNNEL) return i == 0 ? 0 : 1;
+    return 0;
+  }
+  // scale update of every adapter after the variance updates (drift.t:286-298); lane/thread-serial over adapters
+  __device__ __forceinline__ void lex_rescale(int a, bool shrink) const {
+    const size_t ix = (size_t)a * P.C + c;
+    const uint32_t n = P.ls_n[ix];
+    double sc = P.ls_scale[ix];
+    if (n > 100) sc = sqrt(P.ls_m2[ix] / (double)(n - 1));
+    if (shrink) sc = sc * 0.99;
+    P.ls_scale[ix] = sc;
+  }
+  // thread per chain: the reference's component order, RunningVar:update operation for operation
+  __device__ __forceinline__ bool drift_next_lex(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    double x[NPL], xp[NPL];
+    const bool adapting = P.doAdapt[k] != 0;
+    const size_t kc = (size_t)k * P.C + c;
+    unsigned long long made = P.made[kc] + 1, acc = P.acc[kc];
+    load(P.x, x);
+    {
+      const double* z = zcol();
+      const int stride = blockDim.x;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        gaussian_fill<true>(iter, h * HALF, h * HALF + HALF < NPL ? h * HALF + HALF : NPL);
+#pragma unroll
+        for (int r = 0; r < HALF; ++r) {
+          const int e = h * HALF + r;
+          if (e < NPL) {
+            int i = e * G + lane;
+            if (i < d) {
+              const double sc = P.ls_scale[(size_t)adapter_of(i) * P.C + c];
+              xp[e] = __dadd_rn(x[e], __dmul_rn(sc, z[r * stride]) / z[(HALF + r) * stride]);
+            } else xp[e] = 0.0;
+          }
+        }
+        if (G > 1) __syncwarp();
+      }
+    }
+    rec_step = P.ls_scale[c];
+    double lpf, gdummy[NPL];
+    model_eval<FAM, G, NPL, false, true, FAM == FAM_GAUSS_PREC>(P, lane, xp, gdummy, lpf);
+    if (T != 1.0) lpf = lpf / T;
+    const double thresh = lpf - P.lp[c];
+    rec_dh = thresh;
+    const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
+    const bool accept = log(u) < thresh;
+    if (accept) {
+      acc += 1;
+      store(P.x, xp);
+      QSB_FOR_E x[e] = xp[e];
+      P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID;
+    }
+    if (adapting) {
+      const double ratio = (double)acc / (double)made;
+      if (ratio >= 0.05 && acc > 5) {
+        QSB_FOR_E {
+          const int i = e * G + lane;
+          if (i < d) {   // RunningVar:update (drift.t:26-37)
+            const size_t ix = (size_t)adapter_of(i) * P.C + c;
+            const uint32_t n = P.ls_n[ix] + 1;
+            P.ls_n[ix] = n;
+            if (n == 1) { P.ls_mean[ix] = x[e]; P.ls_m2[ix] = 0.0; }
+            else {
+              const double mean = P.ls_mean[ix];
+              const double newmean = mean + (x[e] - mean) / (double)n;
+              P.ls_m2[ix] = P.ls_m2[ix] + (x[e] - mean) * (x[e] - newmean);
+              P.ls_mean[ix] = newmean;
+            }
+          }
+        }
+      }
+      const bool shrink = ratio < 0.05 && acc > 5;
+      for (int a = 0; a < P.m.n_adapters; ++a) lex_rescale(a, shrink);
+    }
+    P.made[kc] = made; P.acc[kc] = acc;
+    return accept;
+  }
+  // warp per chain: the components of a site are folded into its RunningVar as one batch -- with S1 = sum(x - mean),
+  // S2 = sum (x - mean)^2 over the m components of the site: n' = n + m, mean' = mean + S1/n', M2' = M2 + S2 - S1^2/n'
+  // (the closed form of m successive RunningVar:update calls; equal up to rounding)
+  __device__ __forceinline__ bool drift_next_stream_lex(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    const bool adapting = P.doAdapt[k] != 0;
+    const size_t kc = (size_t)k * P.C + c;
+    unsigned long long made = P.made[kc] + 1, acc = P.acc[kc];
+    const double* z = zcol();
+    const int stride = blockDim.x;
+    const int ne = (d + G - 1) / G;
+    const size_t base = (size_t)c * d;
+    double* __restrict__ xw = P.x + base;
+    const int A = P.m.n_adapters;
+    constexpr bool FEW = FAM != FAM_INDEP;   // at most 3 adapters, chosen by the component index alone
+    double s3[3] = {0.0, 0.0, 0.0};
+    if (FEW) { for (int a = 0; a < 3; ++a) if (a < A) s3[a] = P.ls_scale[(size_t)a * P.C + c]; }
+    auto scale_of = [&](int i) -> double {
+      if (FEW) { const int a = adapter_of(i); return a == 0 ? s3[0] : (a == 1 ? s3[1] : s3[2]); }
+      return P.ls_scale[(size_t)adapter_of(i) * P.C + c];
+    };
+    gaussian_fill<false>(iter, 0, ne);
+    ModelStream<FAM> ms;
+    double lp = 0.0;
+    for (int e0 = 0; e0 < ne; e0 += RB) {
+      double xv[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) { const int i = (e0 + r) * G + lane; xv[r] = i < d ? xw[i] : 0.0; }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int e = e0 + r;
+        if (e < ne) {
+          const int i = e * G + lane;
+          double xpi = 0.0;
+          if (i < d) xpi = __dadd_rn(xv[r], __dmul_rn(scale_of(i), z[e * stride]));
+          if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
+          if (i < d) { typename ModelStream<FAM>::Obs ob; ms.fetch(P, i, d, ob); ms.term(P, i, xpi, ob, lp); }
+        }
+      }
+    }
+    rec_step = FEW ? s3[0] : P.ls_scale[c];
+    double lpf = ms.finish(Grp<G>::sum(lp));
+    if (T != 1.0) lpf = lpf / T;
+    const double thresh = lpf - P.lp[c];
+    rec_dh = thresh;
+    const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
+    const bool accept = log(u) < thresh;
+    if (accept) acc += 1;
+    const double ratio = (double)acc / (double)made;
+    const bool upd = adapting && ratio >= 0.05 && acc > 5;
+    if (accept) {
+      for (int e0 = 0; e0 < ne; e0 += RB) {
+        double xv[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) { const int i = (e0 + r) * G + lane; xv[r] = i < d ? xw[i] : 0.0; }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int e = e0 + r; const int i = e * G + lane;
+          if (e < ne && i < d) xw[i] = __dadd_rn(xv[r], __dmul_rn(scale_of(i), z[e * stride]));
+        }
+      }
+      __syncwarp();
+    }
+    if (upd) {
+      if (FEW) {
+        double mean3[3] = {0.0, 0.0, 0.0}, S1[3] = {0.0, 0.0, 0.0}, S2[3] = {0.0, 0.0, 0.0};
+        int cnt[3] = {0, 0, 0};
+        for (int a = 0; a < 3; ++a) if (a < A) mean3[a] = P.ls_mean[(size_t)a * P.C + c];
+        for (int e0 = 0; e0 < ne; e0 += RB) {
+          double xv[RB];
+#pragma unroll
+          for (int r = 0; r < RB; ++r) { const int i = (e0 + r) * G + lane; xv[r] = i < d ? xw[i] : 0.0; }
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const int e = e0 + r; const int i = e * G + lane;
+            if (e < ne && i < d) {
+              const int a = adapter_of(i);
+#pragma unroll
+              for (int q = 0; q < 3; ++q) if (a == q) { const double dv = xv[r] - mean3[q]; S1[q] += dv; S2[q] += dv * dv; cnt[q] += 1; }
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          S1[q] = Grp<G>::sum(S1[q]); S2[q] = Grp<G>::sum(S2[q]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) cnt[q] += __shfl_xor_sync(0xffffffffu, cnt[q], o);
+          if (lane == q && q < A && cnt[q] > 0) {
+            const size_t ix = (size_t)q * P.C + c;
+            const uint32_t n2 = P.ls_n[ix] + (uint32_t)cnt[q];
+            const double inv = 1.0 / (double)n2;
+            P.ls_n[ix] = n2;
+            P.ls_mean[ix] = mean3[q] + S1[q] * inv;
+            P.ls_m2[ix] = P.ls_m2[ix] + (S2[q] - S1[q] * S1[q] * inv);
+          }
+        }
+      } else {
+        for (int a = 0; a < A; ++a) {
+          const size_t ix = (size_t)a * P.C + c;
+          const double mean = P.ls_mean[ix];
+          double S1 = 0.0, S2 = 0.0; int cnt = 0;
+          for (int e = 0; e < ne; ++e) {
+            const int i = e * G + lane;
+            if (i < d && adapter_of(i) == a) { const double dv = xw[i] - mean; S1 += dv; S2 += dv * dv; cnt += 1; }
+          }
+          S1 = Grp<G>::sum(S1); S2 = Grp<G>::sum(S2);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+          if (leader() && cnt > 0) {
+            const uint32_t n2 = P.ls_n[ix] + (uint32_t)cnt;
+            const double inv = 1.0 / (double)n2;
+            P.ls_n[ix] = n2;
+            P.ls_mean[ix] = mean + S1 * inv;
+            P.ls_m2[ix] = P.ls_m2[ix] + (S2 - S1 * S1 * inv);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (adapting && lane < A) lex_rescale(lane, ratio < 0.05 && acc > 5);
+    __syncwarp();
+    if (leader()) {
+      if (accept) { P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID; }
+      P.made[kc] = made; P.acc[kc] = acc;
+    }
+    return accept;
+  }
+
   // ---- HARMKernel:next (harm.t:60-113)
   __device__ __forceinline__ bool harm_next(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
     double x[NPL], xp[NPL];
@@ -1031,7 +1247,7 @@ template <int FAM, int G, int NPL> struct Chain {
   }
 
   // ---- one iteration of doMCMC's loop body (mcmc.t:57-72)
-  template <bool HAS_HMC>
+  template <bool HAS_HMC, bool LEX>
   __device__ __forceinline__ void iterate(uint64_t it) const {
     const uint32_t iter = (uint32_t)it;
     if (P.temps) { T = P.temps[it < P.ntemps ? it : P.ntemps - 1]; invT = 1.0 / T; }   // AnnealingKernel:next (mcmc.t:308-311)
@@ -1053,7 +1269,15 @@ template <int FAM, int G, int NPL> struct Chain {
       if constexpr (SCALAR_GRAD) accept = hmc_next_warp(k, iter, rdh, rstep);
       else accept = hmc_next(k, iter, rdh, rstep);
     }
-    else if (kind == K_DRIFT) accept = STREAM ? drift_next_stream(k, iter, rdh, rstep) : drift_next(k, iter, rdh, rstep);
+    else if (kind == K_DRIFT) {
+      if constexpr (LEX) {
+        if constexpr (STREAM) accept = drift_next_stream_lex(k, iter, rdh, rstep);
+        else accept = drift_next_lex(k, iter, rdh, rstep);
+      } else {
+        if constexpr (STREAM) accept = drift_next_stream(k, iter, rdh, rstep);
+        else accept = drift_next(k, iter, rdh, rstep);
+      }
+    }
     else accept = STREAM ? harm_next_stream(k, iter, rdh, rstep) : harm_next(k, iter, rdh, rstep);
     if (G == 32) __syncwarp();
     const bool keep = it >= P.burnin && (it % P.lag) == 0 && c < P.sample_chains && P.samples != nullptr;
@@ -1107,7 +1331,8 @@ template <int FAM, int G, int NPL> struct Chain {
 // Kernels
 // HAS_HMC = false: the kernel list holds no HMCKernel; the trajectory code (and its register vectors) is not compiled
 // in, which lets the warp-per-chain Drift / HARM kernels run at 3 blocks per SM.
-template <int FAM, int G, int NPL, bool HAS_HMC>
+// LEX: the DriftKernel shares scales per call site (lexicalScaleSharing); always built with HAS_HMC = true.
+template <int FAM, int G, int NPL, bool HAS_HMC, bool LEX = false>
 __global__ void __launch_bounds__(G == 1 || HAS_HMC ? 128 : 256, G == 1 ? 4 : 3)
 advance_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
@@ -1120,7 +1345,7 @@ advance_kernel(const __grid_constant__ EngineParams P) {
   const bool active = grp < P.C;               // whole warps: C*G and the block size are multiples of 32 or the tail warp idles
   Chain<FAM, G, NPL> ch(P, active ? grp : 0);
   if (active)
-    for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC>(it);
+    for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC, LEX>(it);
   ch.flush_counts();
 }
 
@@ -1235,6 +1460,7 @@ struct EngineVariant {
   int family, G, npl;
   void (*advance)(const EngineParams&, void* stream);
   void (*advance_nohmc)(const EngineParams&, void* stream);
+  void (*advance_lex)(const EngineParams&, void* stream);
   void (*init)(const EngineParams&, void* stream);
   void (*rescore)(const EngineParams&, void* stream);
   void (*logp_grad)(const EngineParams&, void* stream);

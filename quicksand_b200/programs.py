@@ -42,6 +42,8 @@ class Program:
             d.X = _dp(a["X"]); d.ybin = a["ybin"].ctypes.data_as(C.POINTER(C.c_uint8))
         if "y" in a:
             d.y = _dp(a["y"]); d.sigma = _dp(a["sigma"])
+        if "erp_lexid" in a:
+            d.erp_lexid = a["erp_lexid"].ctypes.data_as(L.ip)
         return d
 
     def model(self, device=-1):
@@ -88,7 +90,7 @@ class Program:
 _KIND = {"gaussian": L.ERP_GAUSSIAN, "gamma": L.ERP_GAMMA, "beta": L.ERP_BETA, "uniform": L.ERP_UNIFORM}
 
 
-def indep(erps, ret="sum", ret_div=1.0):
+def indep(erps, ret="sum", ret_div=1.0, lexids=None):
     """Independent ERPs with constant parameters, e.g. ``[("gamma", 2.0, 2.0)]`` with ret_div=10 for
     ``return qs.gamma(2.0, 2.0, {struc=false})/10.0`` (test/testsuite.t:657-673).  Entries:
 
@@ -96,15 +98,19 @@ def indep(erps, ret="sum", ret_div=1.0):
       ("gammamv", m, v)  -> gamma(m*m/v, v/m)                                                  erpdefs.t:72-80
       ("betamv", m, v)   -> beta(-m*tmp/v, (m-1)*tmp/v), tmp = m*m - m + v (must be < 0)       erpdefs.t:103-117
       ("dirichlet", [alpha_0 .. alpha_{K-1}])  one vector-valued choice of K real components   erpdefs.t:179-212
-    """
-    kinds, p0, p1 = [], [], []
-    for e in erps:
+
+    ``lexids[i]``: call-site id of entry i (entries produced by one ERP call inside a loop share an id); only
+    DriftKernel{lexicalScaleSharing=true} looks at it (drift.t:208-235).  Default: every entry is its own call site."""
+    kinds, p0, p1, lex = [], [], [], []
+    for n_e, e in enumerate(erps):
         k = e[0]
+        site = n_e if lexids is None else int(lexids[n_e])
         if k == "dirichlet":
             alphas = [float(a) for a in e[1]]
             for j, a in enumerate(alphas):
-                kinds.append(L.ERP_DIRICHLET); p0.append(a); p1.append(float(j))
+                kinds.append(L.ERP_DIRICHLET); p0.append(a); p1.append(float(j)); lex.append(site)
             continue
+        lex.append(site)
         a, b = float(e[1]), float(e[2])
         if k == "gammamv":
             k, a, b = "gamma", a * a / b, b / a
@@ -113,8 +119,9 @@ def indep(erps, ret="sum", ret_div=1.0):
             assert tmp < 0.0, "betamv: v must be less than m - m^2"          # S.assert(tmp < 0.0) (erpdefs.t:110)
             k, a, b = "beta", -a * tmp / b, (a - 1) * tmp / b
         kinds.append(_KIND[k] if isinstance(k, str) else int(k)); p0.append(a); p1.append(b)
+    extra = {} if lexids is None else {"erp_lexid": np.array(lex, dtype=np.int32)}
     return Program(L.FAM_INDEP, len(kinds), erp_kind=np.array(kinds, dtype=np.int32), erp_p0=np.array(p0, dtype=np.float64),
-                   erp_p1=np.array(p1, dtype=np.float64), ret_mode=0 if ret == "sum" else 1, ret_div=float(ret_div))
+                   erp_p1=np.array(p1, dtype=np.float64), ret_mode=0 if ret == "sum" else 1, ret_div=float(ret_div), **extra)
 
 
 def gauss_prec(A):

@@ -8,14 +8,14 @@ from quicksand_b200 import _lib as L
 
 
 def oracle_specs(kernel):
-    return [O.spec(s.kind, stepSize=s.stepSize, numSteps=int(s.numSteps), doAdapt=bool(s.doAdapt), scale=s.scale, weight=s.weight)
-            for s in kernel.specs]
+    return [O.spec(s.kind, stepSize=s.stepSize, numSteps=int(s.numSteps), doAdapt=bool(s.doAdapt), scale=s.scale, weight=s.weight,
+                   lexicalScaleSharing=bool(s.lexicalScaleSharing)) for s in kernel.specs]
 
 
 def oracle_program(p):
     a = p.arrays
     if p.family == L.FAM_INDEP:
-        return O.Program.indep(a["erp_kind"], a["erp_p0"], a["erp_p1"], p.ret_mode, p.ret_div)
+        return O.Program.indep(a["erp_kind"], a["erp_p0"], a["erp_p1"], p.ret_mode, p.ret_div, lexids=a.get("erp_lexid"))
     if p.family == L.FAM_GAUSS_PREC:
         return O.Program.gauss_prec(a["A"])
     if p.family == L.FAM_LOGISTIC:

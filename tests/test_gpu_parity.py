@@ -60,6 +60,10 @@ def _programs(qs):
     progs["dirichlet4"] = qs.programs.indep([("dirichlet", [1.0, 1.0, 1.0, 1.0])], ret="vector")
     progs["dirmix9"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("dirichlet", [2.0, 3.0, 5.0]), ("gammamv", 4.0, 8.0),
                                            ("dirichlet", [0.7, 1.5, 1.0]), ("betamv", 0.3, 0.02)], ret="vector")
+    # call sites shared by several choices (a loop body), for DriftKernel{lexicalScaleSharing=true} (testsuite.t:846-860)
+    progs["gauss10loop"] = qs.programs.indep([("gaussian", 0.1, 0.5)] * 10, ret_div=10.0, lexids=[0] * 10)
+    progs["sites9"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("dirichlet", [2.0, 3.0, 5.0]), ("gaussian", 1.0, 2.0),
+                                          ("dirichlet", [0.7, 1.5, 1.0]), ("gaussian", -1.0, 0.3)], ret="vector", lexids=[0, 1, 0, 1, 2])
     progs["c2"] = qs.programs.c2_correlated_gaussian()[0]
     J = 11
     progs["schools13"] = qs.programs.eight_schools(rng.normal(4, 10, J), rng.uniform(8, 18, J))
@@ -157,6 +161,24 @@ def test_drift_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=64, iters=400, seed=99, mapping=mapping)
     P.compare(gpu, cpu, TOL, what="Drift %s map%d" % (name, mapping))
+
+
+LEXICAL = [("gauss10loop", 1), ("gauss10loop", 32), ("gauss10", 0), ("sites9", 0), ("c2", 0), ("schools13", 1), ("schools13", 32),
+           ("schools62", 0), ("funnel12", 1), ("funnel12", 32), ("funnel70", 0)]
+
+
+@pytest.mark.parametrize("name,mapping", LEXICAL)
+def test_drift_lexical_scale_sharing_parity(qs, oracle, name, mapping):
+    """DriftKernel{lexicalScaleSharing=true} (drift.t:101-115, 208-235): choices of one call site share a ScaleAdapter.
+    Thread per chain feeds the shared RunningVar in the reference's component order; warp per chain folds a site's
+    components in as one batch (same value up to rounding)."""
+    prog = _programs(qs)[name]
+    k = qs.DriftKernel(scale=0.3, lexicalScaleSharing=True)
+    gpu, cpu = P.run_both(prog, k, chains=64, iters=500, seed=98, mapping=mapping)
+    P.compare(gpu, cpu, TOL, what="Drift lexical %s map%d" % (name, mapping))
+    if name in ("gauss10loop", "schools13", "funnel12"):   # sharing matters: the per-component adapters give another chain
+        plain, _ = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=8, iters=500, seed=98, mapping=mapping)
+        assert not np.array_equal(plain["state"], gpu["state"][:8])
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("gaussian1", 0), ("c2", 0), ("schools13", 32), ("schools62", 0),
@@ -433,12 +455,13 @@ def test_fixed_step_hmc_hits_the_truth(qs, name, mean, var):
     assert d["rhat"][0] < 1.1
 
 
-@pytest.mark.parametrize("kind", ["hmc", "harm", "drift"])
+@pytest.mark.parametrize("kind", ["hmc", "harm", "drift", "drift_lexical"])
 def test_ten_gaussians_truth_on_device(qs, oracle, kind):
-    """testsuite.t:719-730, 776-787, 812-823 with many chains: mean of 10 iid gaussian(0.1, 0.5) -> 0.1 within the
+    """testsuite.t:719-730, 776-787, 812-823, 846-860 with many chains: mean of 10 iid gaussian(0.1, 0.5) -> 0.1 within the
     reference's tolerance, and mean/variance within 3 MCSE of the oracle's."""
-    prog = _programs(qs)["gauss10"]
-    kernel = {"hmc": qs.HMCKernel(numSteps=10), "harm": qs.HARMKernel(), "drift": qs.DriftKernel()}[kind]
+    prog = _programs(qs)["gauss10loop" if kind == "drift_lexical" else "gauss10"]
+    kernel = {"hmc": qs.HMCKernel(numSteps=10), "harm": qs.HARMKernel(), "drift": qs.DriftKernel(),
+              "drift_lexical": qs.DriftKernel(lexicalScaleSharing=True)}[kind]
     burnin, lag = (300, 2) if kind == "hmc" else (1500, 20)
     d, vals = _pooled_moments(qs, prog, kernel, chains=2048, nsamps=100, burnin=burnin, lag=lag)
     assert abs(d["mean"][0] - 0.1) < 0.07

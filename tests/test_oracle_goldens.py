@@ -117,3 +117,9 @@ def test_annealing_kernel_restatement(oracle):
         lp = [prog.logp_grad(c["state"][ch, i])[2] for i in range(40)]
         acc = c["accept"][ch].astype(bool)
         assert np.allclose(np.array(lp)[acc], c["logprobs"][ch][acc], rtol=1e-12)
+
+
+def test_drift_lexical_scale_sharing_truth(oracle):
+    """testsuite.t:846-860: 10 gaussians drawn by one call site, DriftKernel{lexicalScaleSharing=true} -> 0.1."""
+    prog = oracle.Program.indep([0] * 10, [0.1] * 10, [0.5] * 10, 0, 10.0, lexids=[0] * 10)
+    assert _expected_value(oracle, prog, oracle.spec(oracle.DRIFT, lexicalScaleSharing=True), 0.1) <= 0.07
