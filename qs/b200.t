@@ -41,8 +41,9 @@ end)
 
 -- ---------------------------------------------------------------------------------------------
 -- Kernel constructors: same tables, same defaults as the reference.
-local function kernelSpec(kind, doAdapt, stepSize, numSteps, scale)
-	return { specs = { {kind=kind, doAdapt=doAdapt and 1 or 0, stepSize=stepSize, numSteps=numSteps, scale=scale, weight=1.0} } }
+local function kernelSpec(kind, doAdapt, stepSize, numSteps, scale, lexical)
+	return { specs = { {kind=kind, doAdapt=doAdapt and 1 or 0, stepSize=stepSize, numSteps=numSteps, scale=scale, weight=1.0,
+	                    lexicalScaleSharing=lexical and 1 or 0} } }
 end
 
 local function HMCKernel(params)            -- qs/hmc.t:57-66
@@ -56,8 +57,9 @@ local function DriftKernel(params)          -- qs/drift.t:63-73
 	params = params or {}
 	local doScaleAdapt = true
 	if params.doScaleAdapt ~= nil then doScaleAdapt = params.doScaleAdapt end
-	assert(not params.lexicalScaleSharing, "qs.b200.DriftKernel: lexicalScaleSharing is not implemented on the device yet")
-	return kernelSpec(B.QSB_KERNEL_DRIFT, doScaleAdapt, 1.0, 1, params.scale or 1.0)
+	local lexicalScaleSharing = false           -- drift.t:71-73
+	if params.lexicalScaleSharing ~= nil then lexicalScaleSharing = params.lexicalScaleSharing end
+	return kernelSpec(B.QSB_KERNEL_DRIFT, doScaleAdapt, 1.0, 1, params.scale or 1.0, lexicalScaleSharing)
 end
 
 local function HARMKernel(params)           -- qs/harm.t:16-22
@@ -72,12 +74,20 @@ local function MixtureKernel(kernels, weights)   -- qs/mcmc.t:199-203
 	local specs = {}
 	for i,k in ipairs(kernels) do
 		assert(#k.specs == 1, "qs.b200.MixtureKernel: nested mixtures are not supported")
+		assert(not k.annealSched, "qs.b200.MixtureKernel: anneal the mixture, not its parts")
 		local s = {}
 		for key,v in pairs(k.specs[1]) do s[key] = v end
 		s.weight = weights[i]
 		specs[#specs+1] = s
 	end
 	return { specs = specs }
+end
+
+-- qs/mcmc.t:297-319.  annealSched is any Terra function (iter: uint, numiters: uint) -> qs.float; it stays host
+-- code: the run tabulates it once and hands the table to the device (qsb_sampler_set_temperatures).
+local function AnnealingKernel(kernel, annealSched)
+	assert(not kernel.annealSched, "qs.b200.AnnealingKernel: nested schedules are not supported")
+	return { specs = kernel.specs, annealSched = annealSched }
 end
 
 -- ---------------------------------------------------------------------------------------------
@@ -118,7 +128,7 @@ local function MCMC(kernel, params)
 			d.ret_mode = [desc.ret_mode or 1]; d.ret_div = [desc.ret_div or 1.0]; d.prior_sigma = [desc.prior_sigma or 0.0]
 			d.erp_kind = [desc.erp_kind or `nil]; d.erp_p0 = [desc.erp_p0 or `nil]; d.erp_p1 = [desc.erp_p1 or `nil]
 			d.A = [desc.A or `nil]; d.X = [desc.X or `nil]; d.ybin = [desc.ybin or `nil]
-			d.y = [desc.y or `nil]; d.sigma = [desc.sigma or `nil]
+			d.y = [desc.y or `nil]; d.sigma = [desc.sigma or `nil]; d.erp_lexid = [desc.erp_lexid or `nil]
 			var model : &B.qsb_model = nil
 			check(B.qsb_model_create(&d, [_device], &model))
 
@@ -129,6 +139,7 @@ local function MCMC(kernel, params)
 						specs[ [i-1] ].kind = [s.kind]; specs[ [i-1] ].doAdapt = [s.doAdapt]
 						specs[ [i-1] ].stepSize = [s.stepSize]; specs[ [i-1] ].numSteps = [s.numSteps]
 						specs[ [i-1] ].scale = [s.scale]; specs[ [i-1] ].weight = [s.weight]
+						specs[ [i-1] ].lexicalScaleSharing = [s.lexicalScaleSharing or 0]; specs[ [i-1] ].reserved = 0
 					end
 				end
 			end
@@ -138,6 +149,17 @@ local function MCMC(kernel, params)
 			var sampler : &B.qsb_sampler = nil
 			check(B.qsb_sampler_create(model, specs, nspecs, &cfg, &sampler))
 			check(B.qsb_sampler_init(sampler))                                  -- TraceType.salloc():init(true), mcmc.t:55
+			escape
+				if kernel.annealSched then   -- AnnealingKernel:next calls annealSched(iter, numiters) (mcmc.t:308-311)
+					local sched = kernel.annealSched
+					emit quote
+						var iters : uint = [_burnin] + [_numsamps] * [_lag]
+						var temps = [S.Vector(double)].salloc():init()
+						for i=0,iters do temps:insert(sched(i, iters)) end
+						check(B.qsb_sampler_set_temperatures(sampler, temps:get(0), iters))
+					end
+				end
+			end
 			check(B.qsb_sampler_run(sampler, [_numsamps], [_burnin], [_lag]))   -- the for i=0,iters loop, mcmc.t:57-72
 
 			-- Caller owns the vector (qs/infer.t:127): it is resized here and the library writes Sample structs
@@ -175,6 +197,7 @@ return
 			DriftKernel = DriftKernel,
 			HARMKernel = HARMKernel,
 			MixtureKernel = MixtureKernel,
+			AnnealingKernel = AnnealingKernel,
 			describe = describe,
 			FAM_INDEP = B.QSB_FAM_INDEP, FAM_GAUSS_PREC = B.QSB_FAM_GAUSS_PREC, FAM_LOGISTIC = B.QSB_FAM_LOGISTIC,
 			FAM_EIGHT_SCHOOLS = B.QSB_FAM_EIGHT_SCHOOLS, FAM_FUNNEL = B.QSB_FAM_FUNNEL

@@ -119,9 +119,8 @@ __device__ __forceinline__ double sigmoid_fast(double z) {
   double d = 1.0 + e;
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double err = fma(-d, y, 1.0);
-  y = fma(y, err, y);
-  err = fma(-d, y, 1.0);
+  double err = fma(-d, y, 1.0);          // one cubic step: y (1 + e + e^2), 3 x the seed's ~23 bits
+  err = fma(err, err, err);
   y = fma(y, err, y);
   return y;
 }
@@ -153,11 +152,10 @@ template <int STEP> __device__ __forceinline__ void sigmoid_step(SigState& s, do
   else if (STEP == 17) s.q = fma(s.q, s.zr, 1.0);
   else if (STEP == 18) s.q = 1.0 + __hiloint2double(__double2hiint(s.q) + (s.k << 20), __double2loint(s.q));
   else if (STEP == 19) { asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s.zr) : "d"(s.q)); }
-  else if (STEP == 20) { double err = fma(-s.q, s.zr, 1.0); s.zr = fma(s.zr, err, s.zr); }
-  else if (STEP == 21) { double err = fma(-s.q, s.zr, 1.0); s.zr = fma(s.zr, err, s.zr); }
-  else if (STEP == 22) s.zr = yv - s.zr;
+  else if (STEP == 20) { double err = fma(-s.q, s.zr, 1.0); err = fma(err, err, err); s.zr = fma(s.zr, err, s.zr); }   // cubic step
+  else if (STEP == 21) s.zr = yv - s.zr;
 }
-static constexpr int SIG_STEPS = 23;
+static constexpr int SIG_STEPS = 22;
 template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps(SigState (&st)[4], const double (&yv)[4]) {
   if constexpr (S0 < S1 && S0 < SIG_STEPS) {
 #pragma unroll
@@ -168,7 +166,10 @@ template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps(SigState
 
 // FULL: every one of the NJ dimension tiles is live (nj == NJ), so the tile loops carry no predicates.
 // LP: also accumulate the log-likelihood (last leapfrog step of a trajectory, initialisation, step-size probes).
-template <int NJ, bool FULL, bool LP>
+// TRIM: the last dimension tile holds at most 4 real dimensions (d = 100: dims 96..99 of 96..103).  In the first
+// contraction the k <-> dimension map of that tile becomes k-step 0 = dims 8(NJ-1) + tig and its all-padding second
+// k-step is not issued (100 instead of 104 DMMAs per row block); the second contraction is unchanged.
+template <int NJ, bool FULL, bool LP, bool TRIM = false>
 __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_constant__ GradParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
@@ -219,8 +220,11 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
       th[J][0] = v.x; th[J][1] = v.y;
     }
   }
+  double thL = 0.0;                                     // TRIM: theta[8(NJ-1) + tig]
+  if (TRIM && valid) thL = P.theta[(size_t)chain * P.Dp + 8 * (NJ - 1) + tig];
   double lpacc = 0.0;
   const int offA = rho_g * S + 2 * tig;                 // phase 1 B fragment: X[rho(gid)][8J + 2tig .. +1]
+  const int offL = rho_g * S + 8 * (NJ - 1) + tig;      // TRIM: X[rho(gid)][8(NJ-1) + tig]
   const int offB0 = rho_t0 * S + gid, offB1 = rho_t1 * S + gid;   // phase 2 B fragment: X[rho(2tig+e)][8J + gid]
   constexpr bool want_lp = LP;
 
@@ -229,6 +233,14 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   // (G^T += R^T X) of block b.  acc holds Z of the block whose epilogue is due, nxt the one being accumulated.
   double acc[NT][2], nxt[NT][2];
   auto phase1_tile = [&](const double* Xs, int J, double (&a)[NT][2]) {
+    if (TRIM && J == NJ - 1) {
+      double xl[NT];
+#pragma unroll
+      for (int T = 0; T < NT; ++T) xl[T] = Xs[T * 8 * S + offL];
+#pragma unroll
+      for (int T = 0; T < NT; ++T) dmma(a[T], thL, xl[T]);
+      return;
+    }
     double2 xv[NT];
 #pragma unroll
     for (int T = 0; T < NT; ++T) xv[T] = *reinterpret_cast<const double2*>(Xs + T * 8 * S + offA + 8 * J);
@@ -280,13 +292,13 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
         if (FULL || 2 < nj) phase1_tile(Xn, 2, nxt);  sigmoid_steps<8, 12>(sa, ya);
         if (FULL || 3 < nj) phase1_tile(Xn, 3, nxt);  sigmoid_steps<12, 16>(sa, ya);
         if (FULL || 4 < nj) phase1_tile(Xn, 4, nxt);  sigmoid_steps<16, 20>(sa, ya);
-        if (FULL || 5 < nj) phase1_tile(Xn, 5, nxt);  sigmoid_steps<20, 23>(sa, ya);
+        if (FULL || 5 < nj) phase1_tile(Xn, 5, nxt);  sigmoid_steps<20, 22>(sa, ya);
         if (FULL || 6 < nj) phase1_tile(Xn, 6, nxt);  sigmoid_steps<0, 4>(sb, yb);
         if (FULL || 7 < nj) phase1_tile(Xn, 7, nxt);  sigmoid_steps<4, 8>(sb, yb);
         if (FULL || 8 < nj) phase1_tile(Xn, 8, nxt);  sigmoid_steps<8, 12>(sb, yb);
         if (FULL || 9 < nj) phase1_tile(Xn, 9, nxt);  sigmoid_steps<12, 16>(sb, yb);
         if (FULL || 10 < nj) phase1_tile(Xn, 10, nxt); sigmoid_steps<16, 20>(sb, yb);
-        if (FULL || 11 < nj) phase1_tile(Xn, 11, nxt); sigmoid_steps<20, 23>(sb, yb);
+        if (FULL || 11 < nj) phase1_tile(Xn, 11, nxt); sigmoid_steps<20, 22>(sb, yb);
 #pragma unroll
         for (int J = 12; J < NJ; ++J) if (FULL || J < nj) phase1_tile(Xn, J, nxt);
 #pragma unroll
@@ -564,17 +576,21 @@ static int pick_ksplit(int ntiles, int nblocks, int nsm) {
   return best;
 }
 
-template <int NJ, bool FULL, bool LP> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
+template <int NJ, bool FULL, bool LP, bool TRIM = false> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL, LP, TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  glm_grad_kernel<NJ, FULL, LP><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
+  glm_grad_kernel<NJ, FULL, LP, TRIM><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
   return cudaGetLastError();
 }
 template <int NJ> static cudaError_t launch_grad_t(const GradParams& P, size_t smem, cudaStream_t st) {
+  if constexpr (NJ == 13) {   // config c3's shape (d = 100): last tile half empty
+    if (P.nj == NJ && P.d <= 8 * (NJ - 1) + 4)
+      return P.want_lp ? launch_grad_tf<NJ, true, true, true>(P, smem, st) : launch_grad_tf<NJ, true, false, true>(P, smem, st);
+  }
   if (P.nj == NJ) return P.want_lp ? launch_grad_tf<NJ, true, true>(P, smem, st) : launch_grad_tf<NJ, true, false>(P, smem, st);
   return P.want_lp ? launch_grad_tf<NJ, false, true>(P, smem, st) : launch_grad_tf<NJ, false, false>(P, smem, st);
 }
