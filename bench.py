@@ -319,6 +319,13 @@ def main():
         e2e_val = ucnt.item() / (mse.item() * 1e-3)
 
     if rank == 0:
+        if cpu is not None and wl["unit_per_iter"]:
+            # Same algorithm, same random stream: the effective sample size gained per chain-transition is the same on both
+            # sides, so the CPU arm's min-ESS/s is its chain-transitions/s times the ESS per chain-transition measured above
+            # (the CPU sample itself is far too short to estimate an ESS from).
+            ess_per_transition = min_ess / float(C * world * K)
+            cpu["min_ess_per_sec"] = ess_per_transition * cpu["value"] / float(wl["unit_per_iter"])
+            cpu["min_ess_note"] = "CPU chain-transitions/s x min-ESS per chain-transition of the GPU draws (same algorithm and stream)"
         per_launch_units = units_local / max(klaunch, 1)
         if wl["bound"] == "hbm":
             achieved = wl["bytes_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e9
@@ -329,8 +336,8 @@ def main():
         else:
             achieved = wl["flops_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e12
             roof = {"bound": wl["bound"], "achieved": achieved, "peak": wl["peak"], "unit": "TFLOP/s", "frac": achieved / wl["peak"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01_c3_grad_v3.ncu-rep)
-                    "traffic": 40.1e6 if (wl["name"] == "c3" and C == 8192) else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01d_c3_grad.ncu-rep)
+                    "traffic": 40.5e6 if (wl["name"] == "c3" and C == 8192) else None,
                     "peak_source": "fp64 peak measured by tools/microbench.cu on this pool (profiles/r01_microbench_b200.json); "
                                    "MEASURED_PEAKS.json has no fp64 entry",
                     "kernel": "glm_grad_kernel" if wl["name"] == "c3" else "advance_kernel",

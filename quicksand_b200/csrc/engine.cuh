@@ -164,15 +164,21 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
     extern __shared__ double qsb_zbuf[];
     const double* Ssm = qsb_zbuf + (size_t)(2 * ((NPL + 1) / 2)) * blockDim.x;
     if (d == NPL) {   // every element live (config c2: n = 10 on the NPL = 10 variant): no per-element predicates
-      QSB_FOR_E {
-        double sx = 0.0;
+      // column-major sweep: the NPL row sums advance together (NPL independent DFMA chains instead of one chain of NPL
+      // dependent DFMAs per row); S is symmetric, so column j is read as the contiguous row j.  Each row still adds its
+      // terms in ascending j: bit-identical to the row-major form.
+      double sx[NPL];
+      QSB_FOR_E sx[e] = 0.0;
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) {
-          if (SSM) sx += Ssm[e * NPL + j] * x[j];
-          else sx += P.Sc[(e * NPL + j) & 255] * x[j];
+      for (int j = 0; j < NPL; ++j) {
+        QSB_FOR_E {
+          if (SSM) sx[e] += Ssm[j * NPL + e] * x[j];
+          else sx[e] += P.Sc[(j * NPL + e) & 255] * x[j];
         }
-        if (LP) { q += x[e] * sx; lp += gaussian_lp(x[e], 0.0, 1.0); }
-        if (GRAD) g[e] = -x[e] - 0.5 * sx;
+      }
+      QSB_FOR_E {
+        if (LP) { q += x[e] * sx[e]; lp += gaussian_lp(x[e], 0.0, 1.0); }
+        if (GRAD) g[e] = -x[e] - 0.5 * sx[e];
       }
     } else {
       QSB_FOR_E {
