@@ -63,7 +63,8 @@ def workload(name, chains=None):
 
 # ---------------------------------------------------------------------------------------------
 def _oracle_worker(args):
-    """One host core: one chain of the CPU restatement.  Returns (grad_evals, seconds, leapfrogs, draws)."""
+    """One host core: one chain of the CPU restatement.  Returns (grad_evals, seconds, proposals).  The run keeps a
+    single sample (lag = transitions) so that long samples of the 1000-dimensional workloads do not materialise every draw."""
     wl_name, chain, transitions, L = args
     import oracle as O
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -75,9 +76,9 @@ def _oracle_worker(args):
         for s in specs:
             if s.kind == O.HMC:
                 s.numSteps = L
-    out = O.run(prog, specs, SEED, 1, transitions, 0, 1, chain_begin=chain)
+    out = O.run(prog, specs, SEED, 1, 1, 0, transitions, chain_begin=chain)
     st = out["stats"]
-    return st["grad_evals"], st["seconds"], st["props_made"], out["samples"][0]
+    return st["grad_evals"], st["seconds"], st["props_made"]
 
 
 def cpu_sample(wl_name, cores, transitions, L=None):
@@ -92,7 +93,7 @@ def cpu_sample(wl_name, cores, transitions, L=None):
     evals = sum(r[0] for r in res)
     props = sum(r[2] for r in res)
     busy = max(r[1] for r in res)
-    return dict(grad_evals=evals, proposals=props, seconds=busy, wall=wall, draws=np.stack([r[3] for r in res]))
+    return dict(grad_evals=evals, proposals=props, seconds=busy, wall=wall)
 
 
 def cpu_units_per_sec(wl, s):
@@ -206,7 +207,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         wl0 = workload(args.workload)
-        trans = {"c3": 16, "c2": 8000, "c4": 3000, "c5": 300}[wl0["name"]]
+        trans = {"c3": 16, "c2": 100000, "c4": 60000, "c5": 6000}[wl0["name"]]     # ~10-15 s of CPU work per core
         s = cpu_sample(args.workload, cores, trans)
         cpu = {"value": cpu_units_per_sec(wl0, s), "unit": wl0["unit"], "cores": cores, "kind": "port",
                "sample": "%d chains (one per core) x %d transitions from initialisation of the CPU restatement of the reference algorithm "
@@ -327,22 +328,25 @@ def main():
             cpu["min_ess_per_sec"] = ess_per_transition * cpu["value"] / float(wl["unit_per_iter"])
             cpu["min_ess_note"] = "CPU chain-transitions/s x min-ESS per chain-transition of the GPU draws (same algorithm and stream)"
         per_launch_units = units_local / max(klaunch, 1)
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default chain counts, from the
+        # ncu --set full captures summarised in profiles/r01d_*_ncu_metrics.csv
+        traffic = {"c3": (8192, 40.5e6), "c2": (65536, 15.1e6), "c4": (131072, 5.62e9), "c5": (32768, 0.491e9)}[wl["name"]]
+        common = {"traffic": traffic[1] if C == traffic[0] else None,
+                  "kernel": "glm_grad_kernel" if wl["name"] == "c3" else "advance_kernel",
+                  "kernel_ms_per_launch": 1e3 * ktime / max(klaunch, 1), "kernel_launches_timed": klaunch,
+                  "kernel_share_of_step": ktime / t}
         if wl["bound"] == "hbm":
             achieved = wl["bytes_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e9
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
             peak = float(peaks.get("hbm_gbs", 6650.0))
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
         else:
             achieved = wl["flops_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e12
             roof = {"bound": wl["bound"], "achieved": achieved, "peak": wl["peak"], "unit": "TFLOP/s", "frac": achieved / wl["peak"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01d_c3_grad.ncu-rep)
-                    "traffic": 40.5e6 if (wl["name"] == "c3" and C == 8192) else None,
                     "peak_source": "fp64 peak measured by tools/microbench.cu on this pool (profiles/r01_microbench_b200.json); "
-                                   "MEASURED_PEAKS.json has no fp64 entry",
-                    "kernel": "glm_grad_kernel" if wl["name"] == "c3" else "advance_kernel",
-                    "kernel_ms_per_launch": 1e3 * ktime / max(klaunch, 1), "kernel_launches_timed": klaunch,
-                    "kernel_share_of_step": ktime / t}
+                                   "MEASURED_PEAKS.json has no fp64 entry"}
+        roof.update(common)
         line = {
             "metric": "leapfrog steps/sec (all chains)" if wl["name"] != "c4" else "proposals/sec (all chains)",
             "value": value, "unit": wl["unit"], "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t / K,

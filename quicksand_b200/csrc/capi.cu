@@ -67,7 +67,7 @@ struct qsb_sampler {
   bool inited = false;
   uint64_t rec_iters = 0;
   double t_accum = 0.0; uint64_t t_launches = 0;   // QSB_FLAG_TIME_KERNEL
-  bool ev_pending = false;
+  std::vector<cudaEvent_t> tev; size_t tev_used = 0;   // event pairs around the timed launches, folded without stalling the stream
   double* stage = nullptr; size_t stage_bytes = 0;  // device staging of fetch_samples (kept between calls)
   double* temps_dev = nullptr;                      // AnnealingKernel schedule
 };
@@ -548,6 +548,7 @@ int qsb_sampler_destroy(qsb_sampler* s) {
   else free_run_buffers(s);
   if (s->stage) cudaFree(s->stage);
   if (s->temps_dev) cudaFree(s->temps_dev);
+  for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
   s->arena.release();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -641,6 +642,19 @@ int qsb_sampler_begin(qsb_sampler* s, uint64_t max_samples, uint64_t burnin, uin
   return 0;
 }
 
+}  // extern "C"
+static int fold_kernel_times(qsb_sampler* s) {
+  if (!s->tev_used) return 0;
+  CU(cudaStreamSynchronize(s->stream));
+  for (size_t i = 0; i + 1 < s->tev_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->tev[i], s->tev[i + 1]) == cudaSuccess) { s->t_accum += ms * 1e-3; ++s->t_launches; }
+  }
+  s->tev_used = 0;
+  return 0;
+}
+extern "C" {
+
 int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
   if (!s) return fail(1, "null sampler");
   if (iters == 0) return 0;
@@ -654,14 +668,14 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
   }
   EngineParams& P = s->P;
   if (s->rec_iters && s->iter + iters > s->rec_iters) return fail(2, "record buffer holds numiters iterations only");
-  if ((s->cfg.flags & QSB_FLAG_TIME_KERNEL) && s->ev_pending) {   // fold the previous launch's time before reusing the events
-    float ms = 0.f;
-    CU(cudaEventSynchronize(s->ev1));
-    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) { s->t_accum += ms * 1e-3; ++s->t_launches; }
-    s->ev_pending = false;
+  const bool timed = (s->cfg.flags & QSB_FLAG_TIME_KERNEL) != 0;
+  if (timed && s->tev_used + 2 > s->tev.size()) {
+    if (s->tev.size() >= 8192) { if (int rc = fold_kernel_times(s)) return rc; }
+    else for (int i = 0; i < 512; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); s->tev.push_back(e); }
   }
   P.it_begin = s->iter; P.n_iters = iters;
   CU(cudaEventRecord(s->ev0, s->stream));
+  if (timed) CU(cudaEventRecord(s->tev[s->tev_used], s->stream));
   {
     // the kernel indexes record rows by (it - it_begin); shift the bases so rows are absolute iterations
     EngineParams R = P;
@@ -678,9 +692,9 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
     else s->var->advance_nohmc(R, s->stream);
   }
   ++s->launches;
+  if (timed) { CU(cudaEventRecord(s->tev[s->tev_used + 1], s->stream)); s->tev_used += 2; }
   CU(cudaEventRecord(s->ev1, s->stream));
   CU(cudaGetLastError());
-  s->ev_pending = true;
   s->iter += iters;
   return 0;
 }
@@ -803,12 +817,7 @@ int qsb_sampler_kernel_time(qsb_sampler* s, double* seconds, uint64_t* launches)
   if (!s || !seconds || !launches) return fail(1, "null argument");
   CU(cudaSetDevice(s->m->device));
   if (s->glm) { std::string why; if (glm_sampler_kernel_time(s->glm, seconds, launches, why)) return fail(5, why); return 0; }
-  CU(cudaStreamSynchronize(s->stream));
-  if (s->ev_pending) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) { s->t_accum += ms * 1e-3; ++s->t_launches; }
-    s->ev_pending = false;
-  }
+  if (int rc = fold_kernel_times(s)) return rc;
   *seconds = s->t_accum; *launches = s->t_launches;
   s->t_accum = 0.0; s->t_launches = 0;
   return 0;
