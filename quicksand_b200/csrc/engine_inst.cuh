@@ -11,8 +11,13 @@ template <int FAM, int G, int NPL> struct VariantImpl {
   template <bool HAS_HMC, bool LEX = false> static void advance_t(const EngineParams& P, void* st) {
     constexpr int TPBA = (G == 1 || HAS_HMC) ? 128 : 256;   // must equal advance_kernel's launch bounds
     constexpr size_t SMEM = ((size_t)Chain<FAM, G, NPL>::NB * TPBA + (FAM == FAM_GAUSS_PREC ? NPL * NPL : 0)) * sizeof(double);   // Gaussian staging columns (+ S)
-    static bool attr = false;
-    if (!attr && SMEM > 48 * 1024) { cudaFuncSetAttribute(advance_kernel<FAM, G, NPL, HAS_HMC, LEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); attr = true; }
+    static bool attr[64] = {};   // the attribute is per device: a process may drive several (qsb_run_config.device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (SMEM > 48 * 1024 && !attr[dev & 63]) {
+      cudaFuncSetAttribute(advance_kernel<FAM, G, NPL, HAS_HMC, LEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      attr[dev & 63] = true;
+    }
     advance_kernel<FAM, G, NPL, HAS_HMC, LEX><<<(unsigned)(((size_t)P.C * G + TPBA - 1) / TPBA), TPBA, SMEM, (cudaStream_t)st>>>(P);
   }
   static void advance(const EngineParams& P, void* st) { advance_t<true>(P, st); }

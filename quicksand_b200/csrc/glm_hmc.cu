@@ -577,11 +577,13 @@ static int pick_ksplit(int ntiles, int nblocks, int nsm) {
 }
 
 template <int NJ, bool FULL, bool LP, bool TRIM = false> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};   // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL, LP, TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   glm_grad_kernel<NJ, FULL, LP, TRIM><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
   return cudaGetLastError();
