@@ -293,6 +293,29 @@ def test_full_dimension_configs_against_oracle(qs, oracle):
         qs.Sampler(qs.programs.funnel(1025), qs.HARMKernel(), numchains=2)   # beyond the largest variant: loud failure
 
 
+def test_c3_full_shape_gradient_kernel_against_oracle(qs, oracle):
+    """BASELINE config c3 at its full data shape (N = 10 000 rows, d = 100: 13 dimension tiles with the half-empty last
+    tile, 313 row blocks split 12 ways) -- the variant of the tensor-core gradient kernel the benchmark runs -- on a
+    handful of chains against the oracle's tape AD, plus a partial chain tile (chain counts that are not a multiple of 96)."""
+    X, y, _ = qs.programs.c3_logistic_data(10000, 100)
+    prog = qs.programs.logistic(X, y, 2.5)
+    rng = np.random.default_rng(3)
+    x = rng.normal(0, 0.3, (5, 100))
+    lpd, g, lpf = prog.logp_grad(x)
+    op = P.oracle_program(prog)
+    for c in range(5):
+        lpd_o, g_o, lpf_o = op.logp_grad(x[c])
+        assert P.relerr(lpd[c], lpd_o) <= 1e-12 and P.relerr(g[c], g_o).max() <= 1e-11, (c, lpd[c], lpd_o)
+    k = qs.HMCKernel(numSteps=4, stepSize=0.015, doStepSizeAdapt=False)
+    gpu, cpu = P.run_both(prog, k, chains=6, iters=4, seed=20261019, leap=True)
+    P.compare(gpu, cpu, TOL, leap=True, what="c3 full shape HMC")
+    # a chain's result does not depend on the tile it sits in: 200 chains (2 full tiles + a partial one) vs the same ids in shards
+    full = qs.Sampler(prog, k, numchains=200, seed=5); full.init(); full.run(3)
+    tail = qs.Sampler(prog, k, numchains=10, seed=5, chain_begin=190); tail.init(); tail.run(3)
+    assert np.array_equal(full.fetch_values()[190:], tail.fetch_values())
+    full.close(); tail.close()
+
+
 def test_chain_ids_are_partition_invariant(qs):
     """Philox key = global chain id: chains [32,64) run as a shard equal chains 32..63 of the full run, bit for bit
     (the multi-GPU invariance the chain sharding relies on)."""
