@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libqsb200.so")
-SOURCES = ["capi.cu", "glm_hmc.cu", "engine_f1.cu", "engine_f2.cu", "engine_f4.cu", "engine_f5.cu"]
+SOURCES = ["capi.cu", "glm_hmc.cu", "engine_f1.cu", "engine_f1w.cu", "engine_f2.cu", "engine_f4.cu", "engine_f5.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -13,6 +13,7 @@
 
 namespace qsb {
 extern const EngineVariant g_variants_f1[]; extern const int g_nvariants_f1;
+extern const EngineVariant g_variants_f1w[]; extern const int g_nvariants_f1w;
 extern const EngineVariant g_variants_f2[]; extern const int g_nvariants_f2;
 extern const EngineVariant g_variants_f4[]; extern const int g_nvariants_f4;
 extern const EngineVariant g_variants_f5[]; extern const int g_nvariants_f5;
@@ -264,12 +265,16 @@ static const EngineVariant* pick_variant(int family, int d, int mapping, std::st
     default: why = "family has no chain-parallel engine variant"; return nullptr;
   }
   const EngineVariant* best = nullptr;
-  for (int i = 0; i < n; ++i) {
-    const EngineVariant& v = tab[i];
-    if (mapping != 0 && v.G != mapping) continue;
-    if ((long)v.G * v.npl < d) continue;
-    if (!best || (long)v.G * v.npl < (long)best->G * best->npl) best = &v;
-  }
+  auto consider = [&](const EngineVariant* t, int cnt) {
+    for (int i = 0; i < cnt; ++i) {
+      const EngineVariant& v = t[i];
+      if (mapping != 0 && v.G != mapping) continue;
+      if ((long)v.G * v.npl < d) continue;
+      if (!best || (long)v.G * v.npl < (long)best->G * best->npl) best = &v;
+    }
+  };
+  consider(tab, n);
+  if (family == QSB_FAM_INDEP) consider(g_variants_f1w, g_nvariants_f1w);
   if (!best) why = "no engine variant for dim=" + std::to_string(d) + " (family " + std::to_string(family) + ", mapping " + std::to_string(mapping) + ")";
   return best;
 }

@@ -60,6 +60,8 @@ def _programs(qs):
     progs["dirichlet4"] = qs.programs.indep([("dirichlet", [1.0, 1.0, 1.0, 1.0])], ret="vector")
     progs["dirmix9"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("dirichlet", [2.0, 3.0, 5.0]), ("gammamv", 4.0, 8.0),
                                            ("dirichlet", [0.7, 1.5, 1.0]), ("betamv", 0.3, 0.02)], ret="vector")
+    progs["wide24"] = qs.programs.indep([("dirichlet", [1.5] * 8), ("gaussian", 0.0, 1.0), ("gamma", 3.0, 0.5), ("dirichlet", [0.8, 1.0, 2.0, 3.0, 1.2, 0.9]),
+                                          ("beta", 2.0, 2.0), ("uniform", -2.0, 2.0)] + [("gaussian", 1.0, 0.2)] * 6, ret="vector")
     # call sites shared by several choices (a loop body), for DriftKernel{lexicalScaleSharing=true} (testsuite.t:846-860)
     progs["gauss10loop"] = qs.programs.indep([("gaussian", 0.1, 0.5)] * 10, ret_div=10.0, lexids=[0] * 10)
     progs["sites9"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("dirichlet", [2.0, 3.0, 5.0]), ("gaussian", 1.0, 2.0),
@@ -77,7 +79,7 @@ def _programs(qs):
     return progs
 
 
-@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "dirichlet4", "dirmix9", "c2",
+@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "dirichlet4", "dirmix9", "wide24", "c2",
                                   "schools13", "schools62", "funnel12", "funnel70", "logistic20"])
 def test_logp_and_gradient_match_tape_ad(qs, oracle, name):
     """Closed-form device gradients vs the oracle's tape AD (qs/lib/ad.t) on random unconstrained points."""
@@ -100,6 +102,7 @@ HMC_FIXED = [
     ("uniform1", dict(numSteps=10, stepSize=0.5), 0, 1.0),
     ("gauss10", dict(numSteps=10, stepSize=0.2), 0, 1.0), ("mixed10", dict(numSteps=5, stepSize=0.1), 0, 1.0),
     ("dirichlet4", dict(numSteps=10, stepSize=0.2), 0, 1.0), ("dirmix9", dict(numSteps=5, stepSize=0.1), 0, 1.0),
+    ("wide24", dict(numSteps=5, stepSize=0.05), 0, 1.0),
     ("mixed10", dict(numSteps=5, stepSize=0.1), 32, 1.0),
     ("c2", dict(numSteps=16, stepSize=0.15), 0, 1.0),
     ("schools13", dict(numSteps=8, stepSize=0.02), 1, 0.95), ("schools13", dict(numSteps=8, stepSize=0.02), 32, 0.95),
@@ -156,7 +159,7 @@ def test_hmc_adaptive_search_and_dual_averaging(qs, oracle, name, L, mapping, mi
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0)])
+                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0)])
 def test_drift_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=64, iters=400, seed=99, mapping=mapping)
