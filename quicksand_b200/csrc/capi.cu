@@ -509,10 +509,11 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   auto bail = [&](int code, const std::string& msg) { s->arena.release(); if (s->glm) glm_sampler_destroy(s->glm); delete s; return fail(code, msg); };
   if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(4, "cudaEventCreate failed");
   if (m->desc.family == QSB_FAM_LOGISTIC) {
-    if (nspecs != 1 || specs[0].kind != QSB_KERNEL_HMC) return bail(2, "LOGISTIC: the tensor-core path implements HMCKernel only");
+    if (nspecs != 1) return bail(2, "LOGISTIC: the tensor-core path runs a single kernel (HMC, Drift or HARM), not a mixture");
+    if (specs[0].kind == QSB_KERNEL_DRIFT && specs[0].lexicalScaleSharing) return bail(2, "LOGISTIC: DriftKernel{lexicalScaleSharing} is not implemented on the tensor-core path");
     std::string why;
-    s->glm = glm_sampler_create(&m->glm, specs[0].stepSize, (uint32_t)specs[0].numSteps, specs[0].doAdapt != 0, cfg->seed, cfg->chain_begin,
-                                cfg->numchains, s->cfg.sample_chains, cfg->flags, (void*)s->stream, why);
+    s->glm = glm_sampler_create(&m->glm, specs[0].kind, specs[0].stepSize, (uint32_t)specs[0].numSteps, specs[0].scale, specs[0].doAdapt != 0,
+                                cfg->seed, cfg->chain_begin, cfg->numchains, s->cfg.sample_chains, cfg->flags, (void*)s->stream, why);
     if (!s->glm) return bail(5, "LOGISTIC: " + why);
     *out = s;
     return 0;

@@ -49,6 +49,7 @@ struct GradParams {
   double* partG;           // [ksplit][C][Dp]
   double* partLp;          // [ksplit][C]
   int want_lp;
+  int want_grad;           // 0: only the first contraction and the log-likelihood (Drift / HARM score a proposal, no gradient)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
       for (int q = 0; q < 2 * NT; ++q) epilogue_elem(ys, q >> 1, q & 1);
     }
     // phase 2: G^T += R^T X
+    if (P.want_grad)
 #pragma unroll
     for (int T = 0; T < NT; ++T) {
 #pragma unroll
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
     for (int T = 0; T < NT; ++T) { acc[T][0] = nxt[T][0]; acc[T][1] = nxt[T][1]; }
   }
 
-  if (valid) {
+  if (valid && P.want_grad) {
     double* out = P.partG + ((size_t)split * P.C + chain) * P.Dp + 2 * tig;
 #pragma unroll
     for (int J = 0; J < NJ; ++J)
@@ -353,7 +355,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
 
 // ---------------------------------------------------------------------------------------------
 // Vector kernels: one warp per chain, lanes over dimensions.
-enum { V_INIT_SAMPLE = 0, V_FINISH_EVAL = 1, V_TRANS_FIRST = 2, V_TRANS_MID = 3, V_TRANS_LAST = 4, V_PROBE_FIRST = 5, V_PROBE_LAST = 6 };
+enum { V_INIT_SAMPLE = 0, V_FINISH_EVAL = 1, V_TRANS_FIRST = 2, V_TRANS_MID = 3, V_TRANS_LAST = 4, V_PROBE_FIRST = 5, V_PROBE_LAST = 6,
+       V_MH_PROPOSE = 7, V_MH_ACCEPT = 8 };
 
 struct VecParams {
   RngKey key; uint32_t chain_begin, C; int d, Dp, ksplit;
@@ -367,6 +370,9 @@ struct VecParams {
   int* status;
   uint32_t iter, L, step, probe;
   double T, invT;   // trace temperature of this iteration (AnnealingKernel, mcmc.t:297-319; trace.t:737-741)
+  int kind;         // 1 HMC, 2 Drift, 3 HARM
+  double *dr_mean, *dr_m2, *dr_s0, *dr_mult; uint32_t* dr_n;   // Drift: RunningVar per component [C][Dp] + per-chain n, scale, shrink factor
+  double* ha_scale;                                            // HARM: [C]
   int adapting;
   double stepSize0;
   // samples / record
@@ -422,6 +428,94 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
     // currTrace.logprob comes from the initialisation at temperature 1 (trace.t:592-624); the dual trace is first
     // evaluated under the first iteration's temperature (hmc.t:218, 254)
     if (lane == 0) { P.lp[c] = lp; P.prevlp[c] = P.T != 1.0 ? lp / P.T : lp; }
+    return;
+  }
+  if (MODE == V_MH_PROPOSE) {
+    // DriftKernel:next / HARMKernel:next proposals (drift.t:140-142; harm.t:67-79), reference operation order
+    if (P.kind == 2) {
+      const uint32_t n_rv = P.dr_n[c];
+      const double s0 = P.dr_s0[c], mult = P.dr_mult[c];
+      for (int i = lane; i < d; i += 32) {
+        double sc = s0;
+        if (n_rv > 100) { sc = sqrt(P.dr_m2[base + i] / (double)(n_rv - 1)); if (mult != 1.0) sc = sc * mult; }   // drift.t:288-298
+        xs[i] = gaussian_sample(P.key, gc, P.iter, (uint32_t)i, x[i], sc);
+      }
+    } else {
+      double zz[4] = {0.0, 0.0, 0.0, 0.0};
+      double nrm = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < d) { zz[q] = gaussian_std(P.key, gc, P.iter, (uint32_t)i); nrm += zz[q] * zz[q]; } }
+      nrm = sqrt(warp_sum(nrm));
+      const double step = uniform_at(P.key, gc, P.iter, (uint32_t)d) * P.ha_scale[c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const int i = lane + 32 * q; if (i < d) xs[i] = x[i] + (step * (zz[q] / nrm)); }
+    }
+    if (lane == 0) P.made[c] += 1;
+    return;
+  }
+  if (MODE == V_MH_ACCEPT) {
+    // accept / reject against the cached log-density, adaptation, sample (drift.t:155-167, 274-300; harm.t:90-108)
+    double lpn = finish_lp(P, c, lane, xs);
+    if (P.T != 1.0) lpn = lpn / P.T;
+    const double thresh = lpn - P.lp[c];
+    const double u = uniform_at(P.key, gc, P.iter, (uint32_t)d + (P.kind == 3 ? 1u : 0u));
+    const bool accept = log(u) < thresh;
+    double step_rec = 0.0;
+    __syncwarp();
+    if (accept) for (int i = lane; i < d; i += 32) x[i] = xs[i];
+    const unsigned long long acc = P.acc[c] + (accept ? 1ull : 0ull), made = P.made[c];
+    if (P.kind == 2) {
+      const uint32_t n_rv = P.dr_n[c];
+      const double s0 = P.dr_s0[c];
+      step_rec = s0;
+      if (P.adapting) {
+        const double ratio = (double)acc / (double)made;
+        uint32_t n_new = n_rv;
+        if (ratio >= 0.05 && acc > 5) {   // RunningVar:update with the current state (drift.t:26-37)
+          n_new = n_rv + 1;
+          for (int i = lane; i < d; i += 32) {
+            const double cur = accept ? xs[i] : x[i];
+            if (n_new == 1) { P.dr_mean[base + i] = cur; P.dr_m2[base + i] = 0.0; }
+            else {
+              const double mean = P.dr_mean[base + i];
+              const double newmean = mean + (cur - mean) / (double)n_new;
+              P.dr_m2[base + i] = P.dr_m2[base + i] + (cur - mean) * (cur - newmean);
+              P.dr_mean[base + i] = newmean;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          const bool shrink = ratio < 0.05 && acc > 5;
+          P.dr_n[c] = n_new;
+          if (n_new > 100) P.dr_mult[c] = shrink ? 0.99 : 1.0;
+          else if (shrink) P.dr_s0[c] = s0 * 0.99;
+        }
+      }
+    } else {
+      const double hscale = P.ha_scale[c];
+      step_rec = hscale;
+      double t = 0.234;
+      if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
+      double ns = hscale;
+      if (P.adapting) {
+        if (accept) ns = hscale + (hscale / (t * (1.0 - t))) * (1.0 - t) / (double)(P.iter + 1u);
+        else ns = fabs(hscale - (hscale / (t * (1.0 - t))) * t / (double)(P.iter + 1u));
+      }
+      if (lane == 0) P.ha_scale[c] = ns;
+    }
+    const double lp_keep = accept ? lpn : P.lp[c];
+    __syncwarp();
+    if (lane == 0) { P.acc[c] = acc; if (accept) P.lp[c] = lpn; }
+    if (P.rec_state) {
+      size_t r = (size_t)c * P.rec_iters + P.rec_row;
+      for (int i = lane; i < d; i += 32) P.rec_state[r * d + i] = x[i];
+      if (lane == 0) { P.rec_accept[r] = accept ? 1 : 0; P.rec_dh[r] = thresh; P.rec_step[r] = step_rec; }
+    }
+    if (P.keep && c < P.SC) {
+      for (int i = lane; i < d; i += 32) P.samples[((size_t)P.sidx * P.SC + c) * d + i] = x[i];
+      if (lane == 0) P.samp_lp[(size_t)P.sidx * P.SC + c] = lp_keep * P.T;   // mcmc.t:69
+    }
     return;
   }
   const double eps = P.eps[c];
@@ -547,6 +641,7 @@ struct GlmSampler {
   GradParams Gp;
   std::vector<void*> bufs;
   uint32_t L = 1; bool adapting = true; double stepSize0 = 1.0;
+  int kind = 1; double scale0 = 1.0;
   uint32_t flags = 0;
   bool searched = false;
   uint64_t iter = 0, burnin = 0, lag = 1, max_samples = 0, rec_iters = 0;
@@ -666,10 +761,11 @@ static void glm_free_run_buffers(GlmSampler* s) {
   s->rec_iters = 0; V.rec_iters = 0;
 }
 
-GlmSampler* glm_sampler_create(GlmModel* m, double stepSize, uint32_t numSteps, bool adapt, uint64_t seed, uint32_t chain_begin,
-                               uint32_t numchains, uint32_t sample_chains, uint32_t flags, void* stream, std::string& why) {
+GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t numSteps, double scale, bool adapt, uint64_t seed,
+                               uint32_t chain_begin, uint32_t numchains, uint32_t sample_chains, uint32_t flags, void* stream, std::string& why) {
   GlmSampler* s = new GlmSampler();
   s->m = m; s->stream = (cudaStream_t)stream; s->L = numSteps; s->adapting = adapt; s->stepSize0 = stepSize; s->flags = flags;
+  s->kind = kind; s->scale0 = scale;
   memset(&s->V, 0, sizeof(s->V)); memset(&s->Gp, 0, sizeof(s->Gp));
   VecParams& V = s->V; GradParams& G = s->Gp;
   const size_t C = numchains, Dp = m->Dp;
@@ -690,6 +786,9 @@ GlmSampler* glm_sampler_create(GlmModel* m, double stepSize, uint32_t numSteps, 
   ok = ok && dalloc(s, &V.lp, C) && dalloc(s, &V.H0, C) && dalloc(s, &V.eps, C) && dalloc(s, &V.prevlp, C);
   ok = ok && dalloc(s, &V.da_gbar, C) && dalloc(s, &V.da_xbar, C) && dalloc(s, &V.da_x0, C) && dalloc(s, &V.da_lastx, C) && dalloc(s, &V.da_gamma, C) && dalloc(s, &V.da_k, C);
   ok = ok && dalloc(s, &V.direction, C) && dalloc(s, &V.done, C) && dalloc(s, &V.n_active, 1) && dalloc(s, &V.made, C) && dalloc(s, &V.acc, C) && dalloc(s, &V.status, 1);
+  V.kind = kind;
+  if (kind == 2) ok = ok && dalloc(s, &V.dr_mean, C * Dp) && dalloc(s, &V.dr_m2, C * Dp) && dalloc(s, &V.dr_s0, C) && dalloc(s, &V.dr_mult, C) && dalloc(s, &V.dr_n, C);
+  if (kind == 3) ok = ok && dalloc(s, &V.ha_scale, C);
   ok = ok && cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
   if (!ok || !s->nj_inst) { why = !s->nj_inst ? "unsupported dim" : "cudaMalloc failed"; glm_sampler_destroy(s); return nullptr; }
   G.partG = partG; G.partLp = partLp; V.partG = partG; V.partLp = partLp;
@@ -725,9 +824,9 @@ template <int MODE> static cudaError_t launch_vec(GlmSampler* s, const VecParams
   ++s->launches;
   return cudaGetLastError();
 }
-static cudaError_t run_grad(GlmSampler* s, const double* theta, int want_lp) {
+static cudaError_t run_grad(GlmSampler* s, const double* theta, int want_lp, int want_grad = 1) {
   GradParams G = s->Gp;
-  G.theta = theta; G.want_lp = want_lp;
+  G.theta = theta; G.want_lp = want_lp; G.want_grad = want_grad;
   ++s->launches; ++s->grad_evals;
   if (!(s->flags & QSB_FLAG_TIME_KERNEL)) return launch_grad(s->nj_inst, G, s->smem, s->stream);
   if (s->tev_used + 2 > s->tev.size()) {
@@ -752,6 +851,19 @@ static int reset_chain_state(GlmSampler* s, std::string& why) {
   GCU(cudaMemsetAsync(V.done, 0, 4 * C, s->stream)); GCU(cudaMemsetAsync(V.direction, 0, 4 * C, s->stream));
   GCU(cudaMemsetAsync(V.made, 0, 8 * C, s->stream)); GCU(cudaMemsetAsync(V.acc, 0, 8 * C, s->stream));
   GCU(cudaMemsetAsync(V.status, 0, 4, s->stream));
+  if (s->kind == 2) {
+    std::vector<double> sc(C, s->scale0), one(C, 1.0);
+    GCU(cudaMemcpyAsync(V.dr_s0, sc.data(), 8 * C, cudaMemcpyHostToDevice, s->stream));
+    GCU(cudaMemcpyAsync(V.dr_mult, one.data(), 8 * C, cudaMemcpyHostToDevice, s->stream));
+    GCU(cudaStreamSynchronize(s->stream));
+    GCU(cudaMemsetAsync(V.dr_n, 0, 4 * C, s->stream));
+    GCU(cudaMemsetAsync(V.dr_mean, 0, 8 * C * V.Dp, s->stream)); GCU(cudaMemsetAsync(V.dr_m2, 0, 8 * C * V.Dp, s->stream));
+  }
+  if (s->kind == 3) {
+    std::vector<double> sc(C, s->scale0);
+    GCU(cudaMemcpyAsync(V.ha_scale, sc.data(), 8 * C, cudaMemcpyHostToDevice, s->stream));
+    GCU(cudaStreamSynchronize(s->stream));
+  }
   s->searched = false; s->iter = 0; s->grad_evals = 0; s->leapfrogs = 0;
   return 0;
 }
@@ -850,6 +962,25 @@ static int step_size_search(GlmSampler* s, std::string& why) {
 
 int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
   if (s->rec_iters && s->iter + iters > s->rec_iters) { why = "record buffer holds numiters iterations only"; return 2; }
+  if (s->kind != 1) {   // Drift / HARM: propose, score (first contraction + log-likelihood only), accept
+    GCU(cudaEventRecord(s->ev0, s->stream));
+    for (uint64_t k = 0; k < iters; ++k) {
+      const uint64_t it = s->iter + k;
+      VecParams V = s->V;
+      V.iter = (uint32_t)it; V.rec_row = it;
+      V.T = temp_at(s, it); V.invT = 1.0 / V.T;
+      GCU(launch_vec<V_MH_PROPOSE>(s, V));
+      GCU(run_grad(s, V.xs, 1, 0));
+      --s->grad_evals;   // a log-density evaluation, not a gradient
+      V.keep = (it >= s->burnin && it % s->lag == 0 && V.samples) ? 1 : 0;
+      V.sidx = it / s->lag - (s->burnin + s->lag - 1) / s->lag;
+      if (V.sidx >= s->max_samples) V.keep = 0;
+      GCU(launch_vec<V_MH_ACCEPT>(s, V));
+    }
+    GCU(cudaEventRecord(s->ev1, s->stream));
+    s->iter += iters;
+    return 0;
+  }
   if (!s->searched) {
     if (temp_at(s, s->iter) != 1.0) {   // first dual-trace evaluation under the first temperature: gradient and search baseline
       VecParams V0 = s->V;
@@ -926,7 +1057,7 @@ int glm_sampler_kernel_time(GlmSampler* s, double* seconds, uint64_t* launches, 
 }
 
 int glm_logp_grad(GlmModel* m, const double* x, int n, double* lp_dual, double* grad, double* lp_float, std::string& why) {
-  GlmSampler* s = glm_sampler_create(m, 1.0, 1, false, 0, 0, (uint32_t)n, (uint32_t)n, 0, nullptr, why);
+  GlmSampler* s = glm_sampler_create(m, 1, 1.0, 1, 1.0, false, 0, 0, (uint32_t)n, (uint32_t)n, 0, nullptr, why);
   if (!s) return 5;
   int rc = glm_sampler_set_state(s, x, why);
   if (!rc) {

@@ -24,8 +24,9 @@ int glm_model_create(GlmModel* m, const double* X, const uint8_t* y, int N, int 
 void glm_model_destroy(GlmModel* m);
 int glm_model_update(GlmModel* m, const double* X, const uint8_t* y, void* stream, std::string& why);
 
-GlmSampler* glm_sampler_create(GlmModel* m, double stepSize, uint32_t numSteps, bool adapt, uint64_t seed, uint32_t chain_begin,
-                               uint32_t numchains, uint32_t sample_chains, uint32_t flags, void* stream, std::string& why);
+// kind: 1 HMC (stepSize, numSteps), 2 Drift (scale), 3 HARM (scale) -- QSB_KERNEL_*
+GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t numSteps, double scale, bool adapt, uint64_t seed,
+                               uint32_t chain_begin, uint32_t numchains, uint32_t sample_chains, uint32_t flags, void* stream, std::string& why);
 void glm_sampler_destroy(GlmSampler* s);
 int glm_sampler_init(GlmSampler* s, std::string& why);
 int glm_sampler_set_state(GlmSampler* s, const double* x, std::string& why);

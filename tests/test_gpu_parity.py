@@ -159,7 +159,7 @@ def test_hmc_adaptive_search_and_dual_averaging(qs, oracle, name, L, mapping, mi
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0)])
+                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0), ("logistic20", 0)])
 def test_drift_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=64, iters=400, seed=99, mapping=mapping)
@@ -185,7 +185,7 @@ def test_drift_lexical_scale_sharing_parity(qs, oracle, name, mapping):
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("gaussian1", 0), ("c2", 0), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0), ("dirichlet4", 0)])
+                                          ("funnel12", 1), ("funnel70", 0), ("dirichlet4", 0), ("logistic20", 0)])
 def test_harm_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.HARMKernel(), chains=64, iters=300, seed=5, mapping=mapping)
@@ -229,6 +229,7 @@ def _cooling(i, n):
 
 
 ANNEAL = [
+    ("logistic20", "drift", 0), ("logistic20", "harm", 0),
     ("c2", "hmc", 0), ("gauss10", "mix3", 0), ("schools13", "drift", 32), ("schools13", "hmc", 32), ("schools13", "hmc", 1),
     ("funnel12", "mix", 32), ("funnel12", "mix", 1), ("funnel70", "harm", 0), ("logistic20", "hmc", 0), ("mixed10", "hmc", 32),
 ]
@@ -435,8 +436,8 @@ def test_dirichlet_samples_live_on_the_simplex(qs):
 def test_error_behaviour(qs):
     """Unsupported requests fail loudly with a message (the shim turns them into the reference's print + abort)."""
     from quicksand_b200 import _lib as L
-    with pytest.raises(L.QsbError):
-        qs.Sampler(_programs(qs)["logistic20"], qs.DriftKernel(), numchains=4)
+    with pytest.raises(L.QsbError):   # the tensor-core GLM path runs one kernel, not a mixture
+        qs.Sampler(_programs(qs)["logistic20"], qs.MixtureKernel([qs.DriftKernel(), qs.HARMKernel()], [0.5, 0.5]), numchains=4)
     with pytest.raises(L.QsbError):
         qs.Sampler(qs.programs.funnel(5000), qs.HMCKernel(), numchains=4)
     m = qs.MCMC(qs.HMCKernel(numSteps=3), dict(numsamps=20, numchains=3, seed=2))
