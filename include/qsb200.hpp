@@ -4,11 +4,12 @@
 //   qs::infer(program, query, method)                         qs/infer.t:59-70
 //   qs::MCMC(kernel, {numsamps, burnin, lag, verbose})        qs/mcmc.t:36-105   (+ numchains, seed, device)
 //   qs::HMCKernel{stepSize, numSteps, doStepSizeAdapt}        qs/hmc.t:57-66
-//   qs::DriftKernel{scale, doScaleAdapt}                      qs/drift.t:63-73
+//   qs::DriftKernel{scale, doScaleAdapt, lexicalScaleSharing} qs/drift.t:63-73
 //   qs::HARMKernel{scale, doScaleAdapt}                       qs/harm.t:16-22
 //   qs::MixtureKernel({kernels}, {weights})                   qs/mcmc.t:199-291
+//   qs::AnnealingKernel(kernel, annealSched)                  qs/mcmc.t:297-319
 //   qs::Sample { value[retdim], logprob, loglikelihood }      qs/infer.t:12-18
-//   qs::Expectation(samples)                                  qs/infer.t:146-187 (mean starts at value[0], weights from i=1)
+//   qs::Expectation / qs::MAP / qs::Autocorrelation           qs/infer.t:146-264 (device queries over the sample vector)
 //
 // Errors: the reference prints a message and aborts (qs/lib/std.t:35-43); here a qs::Error is thrown with the message.
 #pragma once
@@ -50,7 +51,10 @@ class Program {
 };
 
 // ---- kernels
-struct Kernel { std::vector<qsb_kernel_spec> specs; };
+struct Kernel {
+  std::vector<qsb_kernel_spec> specs;
+  std::function<double(uint32_t, uint32_t)> annealSched;   // AnnealingKernel: temperature of (iter, numiters); empty = none
+};
 struct HMCParams { double stepSize = 1.0; uint64_t numSteps = 1; bool doStepSizeAdapt = true; };
 struct DriftParams { double scale = 1.0; bool doScaleAdapt = true; bool lexicalScaleSharing = false; };
 struct HARMParams { double scale = 1.0; bool doScaleAdapt = true; };
@@ -62,9 +66,16 @@ inline Kernel MixtureKernel(const std::vector<Kernel>& kernels, const std::vecto
   Kernel k;
   for (size_t i = 0; i < kernels.size(); ++i) {
     if (kernels[i].specs.size() != 1) throw Error("MixtureKernel: nested mixtures are not supported");
+    if (kernels[i].annealSched) throw Error("MixtureKernel: anneal the mixture, not its parts");
     qsb_kernel_spec s = kernels[i].specs[0]; s.weight = weights[i]; k.specs.push_back(s);
   }
   return k;
+}
+// AnnealingKernel(kernel, annealSched) (mcmc.t:297-319): the schedule stays host code and is tabulated once per run
+inline Kernel AnnealingKernel(Kernel kernel, std::function<double(uint32_t, uint32_t)> annealSched) {
+  if (kernel.annealSched) throw Error("AnnealingKernel: nested schedules are not supported");
+  kernel.annealSched = std::move(annealSched);
+  return kernel;
 }
 
 // ---- samples: contiguous storage laid out like S.Vector(Sample(T))._data, [chain][sample]{value[retdim], logprob, loglikelihood}
@@ -90,6 +101,12 @@ inline Method MCMC(Kernel kernel, MCMCParams p = {}) {
     try {
       check(qsb_sampler_create(model, kernel.specs.data(), (int32_t)kernel.specs.size(), &cfg, &s));
       check(qsb_sampler_init(s));
+      if (kernel.annealSched) {
+        const uint64_t iters = p.burnin + p.numsamps * p.lag;
+        std::vector<double> temps(iters);
+        for (uint64_t i = 0; i < iters; ++i) temps[i] = kernel.annealSched((uint32_t)i, (uint32_t)iters);
+        check(qsb_sampler_set_temperatures(s, temps.data(), iters));
+      }
       check(qsb_sampler_run(s, p.numsamps, p.burnin, p.lag));
       samples.retdim = program.retdim(); samples.numchains = p.numchains; samples.numsamps = qsb_sampler_num_samples(s);
       samples.data.resize(samples.size() * samples.stride());
@@ -105,16 +122,26 @@ inline Method MCMC(Kernel kernel, MCMCParams p = {}) {
   };
 }
 
-// Expectation (infer.t:146-187) of chain `chain`: mean starts at value[0], weights exp(loglikelihood) summed from i = 1
-inline std::vector<double> Expectation(const SampleVector& v, uint32_t chain = 0) {
-  std::vector<double> m(v.value(chain, 0), v.value(chain, 0) + v.retdim);
-  double totalw = 0.0;
-  for (uint64_t i = 1; i < v.numsamps; ++i) {
-    double w = std::exp(v.loglikelihood(chain, i)); totalw += w;
-    for (int j = 0; j < v.retdim; ++j) m[j] += w * v.value(chain, i)[j];
-  }
-  for (double& x : m) x /= totalw;
+// Queries (infer.t:146-264), evaluated by the library's CUDA kernels over the caller-owned sample vector.
+// Expectation: [numchains][retdim] means (mean starts at value[0], weights exp(loglikelihood) summed from i = 1) and,
+// if `variance` is given, the per-chain variances (sum |v - mean|^2 / N).
+inline std::vector<double> Expectation(const SampleVector& v, std::vector<double>* variance = nullptr) {
+  std::vector<double> m((size_t)v.numchains * v.retdim);
+  if (variance) variance->resize(v.numchains);
+  check(qsb_query_expectation_host(v.data.data(), v.stride() * sizeof(double), v.numchains, v.numsamps, v.retdim, m.data(),
+                                   variance ? variance->data() : nullptr));
   return m;
+}
+inline std::vector<double> MAP(const SampleVector& v) {   // [numchains][retdim]
+  std::vector<double> val((size_t)v.numchains * v.retdim);
+  check(qsb_query_map_host(v.data.data(), v.stride() * sizeof(double), v.numchains, v.numsamps, v.retdim, val.data(), nullptr));
+  return val;
+}
+inline std::vector<double> Autocorrelation(const SampleVector& v, const std::vector<double>* mean = nullptr, double variance = 0.0) {   // [numchains][numsamps]
+  std::vector<double> ac((size_t)v.numchains * v.numsamps);
+  check(qsb_query_autocorrelation_host(v.data.data(), v.stride() * sizeof(double), v.numchains, v.numsamps, v.retdim,
+                                       mean ? mean->data() : nullptr, variance, ac.data()));
+  return ac;
 }
 
 // infer(program, query, method) (infer.t:59-70)

@@ -9,7 +9,7 @@ int main() {
   qs::HMCParams hp; hp.numSteps = 10;
   qs::MCMCParams mp; mp.numsamps = 150; mp.lag = 20; mp.numchains = 256; mp.seed = 1;
   try {
-    auto run = qs::infer(prog, [](const qs::SampleVector& s) { double m = 0; for (uint32_t c = 0; c < s.numchains; ++c) m += qs::Expectation(s, c)[0]; return m / s.numchains; },
+    auto run = qs::infer(prog, [](const qs::SampleVector& s) { double m = 0; for (double e : qs::Expectation(s)) m += e; return m / s.numchains; },
                          qs::MCMC(qs::HMCKernel(hp), mp));
     double est = run();
     std::printf("estimate %.4f (truth 0.1)\n", est);
