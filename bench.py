@@ -282,8 +282,9 @@ def main():
     if world > 1:
         dist.all_reduce(raw)
     diag = D.summarize(raw.cpu().numpy(), retdim, maxlag, nshards=world)
-    min_ess = float(np.nanmin(diag["ess"]))
-    rhat_max = float(np.nanmax(diag["rhat"]))
+    # too few timed draws for an autocovariance (K < 3): no ESS rather than a made-up one
+    min_ess = float(np.nanmin(diag["ess"])) if "ess" in diag and np.isfinite(diag["ess"]).any() else None
+    rhat_max = float(np.nanmax(diag["rhat"])) if np.isfinite(diag["rhat"]).any() else None
 
     # ---- end to end through the host-facing API with HOST buffers: every step uploads the observation data from pinned
     # host memory, runs one transition of all chains and reads that step's draws back into pinned host memory
@@ -324,8 +325,8 @@ def main():
             # Same algorithm, same random stream: the effective sample size gained per chain-transition is the same on both
             # sides, so the CPU arm's min-ESS/s is its chain-transitions/s times the ESS per chain-transition measured above
             # (the CPU sample itself is far too short to estimate an ESS from).
-            ess_per_transition = min_ess / float(C * world * K)
-            cpu["min_ess_per_sec"] = ess_per_transition * cpu["value"] / float(wl["unit_per_iter"])
+            ess_per_transition = (min_ess or 0.0) / float(C * world * K)
+            cpu["min_ess_per_sec"] = ess_per_transition * cpu["value"] / float(wl["unit_per_iter"]) if min_ess else None
             cpu["min_ess_note"] = "CPU chain-transitions/s x min-ESS per chain-transition of the GPU draws (same algorithm and stream)"
         per_launch_units = units_local / max(klaunch, 1)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default chain counts, from the
@@ -354,7 +355,7 @@ def main():
             "config": {"workload": "%s: %s" % (wl["name"], wl["desc"]), "chains_per_gpu": C, "chains_total": C * world,
                        "burnin_transitions": B, "l2": "working set (chain state + partial sums) larger than L2; inputs change every step",
                        "seed": SEED},
-            "secondary": {"metric": "min-ESS/sec", "value": min_ess / t, "unit": "effective samples/s", "min_ess": min_ess,
+            "secondary": {"metric": "min-ESS/sec", "value": (min_ess / t) if min_ess else None, "unit": "effective samples/s", "min_ess": min_ess,
                           "draws_per_chain": K, "max_split_rhat": rhat_max, "maxlag": maxlag,
                           "accept_rate": cnt[1].item() / max(cnt[2].item(), 1.0)},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
