@@ -1075,54 +1075,63 @@ template <int FAM, int G, int NPL> struct Chain {
   // order) three quotients become products with a reciprocal -- sigma*(v/u) for (sigma*v)/u, m2*(1/(n-1)), (x-mean)*(1/n),
   // z*(1/norm) -- each within 1 ulp.
   static constexpr int RB = 4;
+  // Addressing: every array of the chain is walked through a per-lane pointer advanced once per RB rows, so that an
+  // element is reached with an immediate offset (row r of the chunk = +32*r doubles) and no per-element index arithmetic;
+  // TPB (= blockDim.x, the row stride of the Gaussian staging array) is a compile-time constant for the same reason.
+  template <int TPB>
   __device__ __forceinline__ bool drift_next_stream(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
     const bool adapting = P.doAdapt[k] != 0;
     const size_t kc = (size_t)k * P.C + c;
     unsigned long long made = P.made[kc] + 1, acc = P.acc[kc];
     const uint32_t n_rv = P.dr_n[c];
     const double s0 = P.dr_s0[c], mult = P.dr_mult[c];
-    const double* z = zcol();
-    const int stride = blockDim.x;
     const int ne = (d + G - 1) / G;                     // component rows of this chain
-    const size_t base = (size_t)c * d;
-    const double* __restrict__ xr = P.x + base;
+    const size_t base = (size_t)c * d + lane;
     const bool use_var = n_rv > 100;                    // scale = varEst:getStdDev() [* 0.99]  (drift.t:288-298)
     const double inv_nm1 = use_var ? 1.0 / (double)(n_rv - 1) : 0.0;
     gaussian_fill<false>(iter, 0, ne);
     ModelStream<FAM> ms;
     double lp = 0.0;
-    // x and m2 of rows e0+RB.. are requested while rows e0.. are scored (double buffer in registers); the observation
-    // data are model constants shared by every chain (L1 hits) and are read at their use
-    double xn[RB], mn[RB];
-    auto load_rows = [&](int e0) {
+    {
+      // x and m2 of rows e0+RB.. are requested while rows e0.. are scored (double buffer in registers); the observation
+      // data are model constants shared by every chain (L1 hits) and are read at their use
+      const double* __restrict__ xl = P.x + base;
+      const double* __restrict__ ml = P.dr_m2 + base;
+      const double* zl = zcol();
+      int i0 = lane;                                   // component index of row e0 for this lane
+      double xn[RB], mn[RB];
 #pragma unroll
       for (int r = 0; r < RB; ++r) {
-        const int i = (e0 + r) * G + lane;
-        const bool ok = i < d;
-        xn[r] = ok ? xr[i] : 0.0;
-        mn[r] = (ok && use_var) ? P.dr_m2[base + i] : 0.0;
+        const bool ok = i0 + 32 * r < d;
+        xn[r] = ok ? xl[32 * r] : 0.0;
+        mn[r] = (ok && use_var) ? ml[32 * r] : 0.0;
       }
-    };
-    load_rows(0);
-    for (int e0 = 0; e0 < ne; e0 += RB) {
-      double xv[RB], mv[RB];
+      for (int e0 = 0; e0 < ne; e0 += RB) {
+        double xv[RB], mv[RB];
 #pragma unroll
-      for (int r = 0; r < RB; ++r) { xv[r] = xn[r]; mv[r] = mn[r]; }
-      if (e0 + RB < ne) load_rows(e0 + RB);
+        for (int r = 0; r < RB; ++r) { xv[r] = xn[r]; mv[r] = mn[r]; }
+        xl += 32 * RB; ml += 32 * RB;
+        if (e0 + RB < ne) {
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const int e = e0 + r;
-        if (e < ne) {
-          const int i = e * G + lane;
+          for (int r = 0; r < RB; ++r) {
+            const bool ok = i0 + 32 * (RB + r) < d;
+            xn[r] = ok ? xl[32 * r] : 0.0;
+            mn[r] = (ok && use_var) ? ml[32 * r] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int i = i0 + 32 * r;
           double xpi = 0.0;
           if (i < d) {
             double sc = s0;
             if (use_var) { sc = sqrt(mv[r] * inv_nm1); if (mult != 1.0) sc = sc * mult; }
-            xpi = __dadd_rn(xv[r], __dmul_rn(sc, z[e * stride]));
+            xpi = __dadd_rn(xv[r], __dmul_rn(sc, zl[r * TPB]));
           }
-          if (e == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
+          if (e0 == 0 && r == 0) ms.prep(P, Grp<G>::bcast(xpi, 0), Grp<G>::bcast(xpi, 1));
           if (i < d) { typename ModelStream<FAM>::Obs ob; ms.fetch(P, i, d, ob); ms.term(P, i, xpi, ob, lp); }
         }
+        i0 += 32 * RB; zl += RB * TPB;
       }
     }
     rec_step = s0;
@@ -1138,40 +1147,43 @@ template <int FAM, int G, int NPL> struct Chain {
     const uint32_t n_new = upd ? n_rv + 1 : n_rv;
     if (accept || upd) {
       const double inv_n = 1.0 / (double)n_new;
-      double* __restrict__ xw = P.x + base;
+      double* __restrict__ xl = P.x + base;
+      double* __restrict__ ml = P.dr_m2 + base;
+      double* __restrict__ al = P.dr_mean + base;
+      const double* zl = zcol();
+      const bool need_m2 = use_var || (upd && n_new != 1), need_mean = upd && n_new != 1;
+      int i0 = lane;
       for (int e0 = 0; e0 < ne; e0 += RB) {
         double xv[RB], mv[RB], av[RB];
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
-          const int i = (e0 + r) * G + lane;
-          const bool ok = i < d;
-          xv[r] = ok ? xw[i] : 0.0;
-          mv[r] = (ok && (use_var || (upd && n_new != 1))) ? P.dr_m2[base + i] : 0.0;
-          av[r] = (ok && upd && n_new != 1) ? P.dr_mean[base + i] : 0.0;
+          const bool ok = i0 + 32 * r < d;
+          xv[r] = ok ? xl[32 * r] : 0.0;
+          mv[r] = (ok && need_m2) ? ml[32 * r] : 0.0;
+          av[r] = (ok && need_mean) ? al[32 * r] : 0.0;
         }
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
-          const int e = e0 + r;
-          const int i = e * G + lane;
-          if (e < ne && i < d) {
+          if (i0 + 32 * r < d) {
             double cur = xv[r];
             if (accept) {   // the accepted proposal, recomputed exactly as it was scored
               double sc = s0;
               if (use_var) { sc = sqrt(mv[r] * inv_nm1); if (mult != 1.0) sc = sc * mult; }
-              cur = __dadd_rn(xv[r], __dmul_rn(sc, z[e * stride]));
-              xw[i] = cur;
+              cur = __dadd_rn(xv[r], __dmul_rn(sc, zl[r * TPB]));
+              xl[32 * r] = cur;
             }
             if (upd) {
-              if (n_new == 1) { P.dr_mean[base + i] = cur; P.dr_m2[base + i] = 0.0; }
+              if (n_new == 1) { al[32 * r] = cur; ml[32 * r] = 0.0; }
               else {
                 const double mean = av[r];
                 const double newmean = mean + (cur - mean) * inv_n;
-                P.dr_m2[base + i] = mv[r] + (cur - mean) * (cur - newmean);
-                P.dr_mean[base + i] = newmean;
+                ml[32 * r] = mv[r] + (cur - mean) * (cur - newmean);
+                al[32 * r] = newmean;
               }
             }
           }
         }
+        i0 += 32 * RB; xl += 32 * RB; ml += 32 * RB; al += 32 * RB; zl += RB * TPB;
       }
     }
     __syncwarp();
@@ -1280,7 +1292,7 @@ template <int FAM, int G, int NPL> struct Chain {
         if constexpr (STREAM) accept = drift_next_stream_lex(k, iter, rdh, rstep);
         else accept = drift_next_lex(k, iter, rdh, rstep);
       } else {
-        if constexpr (STREAM) accept = drift_next_stream(k, iter, rdh, rstep);
+        if constexpr (STREAM) accept = drift_next_stream<(G == 1 || HAS_HMC) ? 128 : 256>(k, iter, rdh, rstep);
         else accept = drift_next(k, iter, rdh, rstep);
       }
     }
