@@ -694,6 +694,7 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
     bool has_hmc = false;
     for (int k = 0; k < R.nsub; ++k) has_hmc |= R.kind[k] == K_HMC;
     if (R.dr_lexical) s->var->advance_lex(R, s->stream);
+    else if (R.nsub == 1 && R.kind[0] == K_DRIFT) s->var->advance_drift(R, s->stream);
     else if (has_hmc) s->var->advance(R, s->stream);
     else s->var->advance_nohmc(R, s->stream);
   }

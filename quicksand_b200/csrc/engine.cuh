@@ -1265,7 +1265,7 @@ template <int FAM, int G, int NPL> struct Chain {
   }
 
   // ---- one iteration of doMCMC's loop body (mcmc.t:57-72)
-  template <bool HAS_HMC, bool LEX>
+  template <bool HAS_HMC, bool LEX, bool DRIFT_ONLY>
   __device__ __forceinline__ void iterate(uint64_t it) const {
     const uint32_t iter = (uint32_t)it;
     if (P.temps) { T = P.temps[it < P.ntemps ? it : P.ntemps - 1]; invT = 1.0 / T; }   // AnnealingKernel:next (mcmc.t:308-311)
@@ -1287,7 +1287,7 @@ template <int FAM, int G, int NPL> struct Chain {
       if constexpr (SCALAR_GRAD) accept = hmc_next_warp(k, iter, rdh, rstep);
       else accept = hmc_next(k, iter, rdh, rstep);
     }
-    else if (kind == K_DRIFT) {
+    else if (DRIFT_ONLY || kind == K_DRIFT) {
       if constexpr (LEX) {
         if constexpr (STREAM) accept = drift_next_stream_lex(k, iter, rdh, rstep);
         else accept = drift_next_lex(k, iter, rdh, rstep);
@@ -1350,7 +1350,8 @@ template <int FAM, int G, int NPL> struct Chain {
 // HAS_HMC = false: the kernel list holds no HMCKernel; the trajectory code (and its register vectors) is not compiled
 // in, which lets the warp-per-chain Drift / HARM kernels run at 3 blocks per SM.
 // LEX: the DriftKernel shares scales per call site (lexicalScaleSharing); always built with HAS_HMC = true.
-template <int FAM, int G, int NPL, bool HAS_HMC, bool LEX = false>
+// DRIFT_ONLY: a single DriftKernel (config c4): no HARM code in the kernel, so the register allocator serves one path.
+template <int FAM, int G, int NPL, bool HAS_HMC, bool LEX = false, bool DRIFT_ONLY = false>
 __global__ void __launch_bounds__(G == 1 || HAS_HMC ? 128 : 256, G == 1 ? 4 : 3)
 advance_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
@@ -1363,7 +1364,7 @@ advance_kernel(const __grid_constant__ EngineParams P) {
   const bool active = grp < P.C;               // whole warps: C*G and the block size are multiples of 32 or the tail warp idles
   Chain<FAM, G, NPL> ch(P, active ? grp : 0);
   if (active)
-    for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC, LEX>(it);
+    for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC, LEX, DRIFT_ONLY>(it);
   ch.flush_counts();
 }
 
@@ -1479,6 +1480,7 @@ struct EngineVariant {
   void (*advance)(const EngineParams&, void* stream);
   void (*advance_nohmc)(const EngineParams&, void* stream);
   void (*advance_lex)(const EngineParams&, void* stream);
+  void (*advance_drift)(const EngineParams&, void* stream);
   void (*init)(const EngineParams&, void* stream);
   void (*rescore)(const EngineParams&, void* stream);
   void (*logp_grad)(const EngineParams&, void* stream);

@@ -8,25 +8,26 @@ namespace qsb {
 template <int FAM, int G, int NPL> struct VariantImpl {
   static constexpr int TPB = G == 1 ? 128 : 256;
   static unsigned grid(const EngineParams& P) { return (unsigned)(((size_t)P.C * G + TPB - 1) / TPB); }
-  template <bool HAS_HMC, bool LEX = false> static void advance_t(const EngineParams& P, void* st) {
+  template <bool HAS_HMC, bool LEX = false, bool DRIFT_ONLY = false> static void advance_t(const EngineParams& P, void* st) {
     constexpr int TPBA = (G == 1 || HAS_HMC) ? 128 : 256;   // must equal advance_kernel's launch bounds
     constexpr size_t SMEM = ((size_t)Chain<FAM, G, NPL>::NB * TPBA + (FAM == FAM_GAUSS_PREC ? NPL * NPL : 0)) * sizeof(double);   // Gaussian staging columns (+ S)
     static bool attr[64] = {};   // the attribute is per device: a process may drive several (qsb_run_config.device)
     int dev = 0;
     cudaGetDevice(&dev);
     if (SMEM > 48 * 1024 && !attr[dev & 63]) {
-      cudaFuncSetAttribute(advance_kernel<FAM, G, NPL, HAS_HMC, LEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+      cudaFuncSetAttribute(advance_kernel<FAM, G, NPL, HAS_HMC, LEX, DRIFT_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
       attr[dev & 63] = true;
     }
-    advance_kernel<FAM, G, NPL, HAS_HMC, LEX><<<(unsigned)(((size_t)P.C * G + TPBA - 1) / TPBA), TPBA, SMEM, (cudaStream_t)st>>>(P);
+    advance_kernel<FAM, G, NPL, HAS_HMC, LEX, DRIFT_ONLY><<<(unsigned)(((size_t)P.C * G + TPBA - 1) / TPBA), TPBA, SMEM, (cudaStream_t)st>>>(P);
   }
   static void advance(const EngineParams& P, void* st) { advance_t<true>(P, st); }
   static void advance_nohmc(const EngineParams& P, void* st) { advance_t<false>(P, st); }
   static void advance_lex(const EngineParams& P, void* st) { advance_t<true, true>(P, st); }
+  static void advance_drift(const EngineParams& P, void* st) { advance_t<false, false, true>(P, st); }
   static void init(const EngineParams& P, void* st) { init_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void rescore(const EngineParams& P, void* st) { rescore_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void logp_grad(const EngineParams& P, void* st) { logp_grad_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
-  static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &advance_nohmc, &advance_lex, &init, &rescore, &logp_grad}; }
+  static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &advance_nohmc, &advance_lex, &advance_drift, &init, &rescore, &logp_grad}; }
 };
 
 }  // namespace qsb
