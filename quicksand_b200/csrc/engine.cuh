@@ -300,9 +300,16 @@ template <int FAM> struct GradScalars {
       const double s = exp(v / 2.0);
       const double s2 = s * s;
       a = 1.0 / s2; b = 0.0; g1 = 0.0;
-      double gv = 0.0;
-      QSB_FOR_E { int i = e * G + lane; if (i >= 1 && i < d) { const double t = x[e] * a; gv += -0.5 + 0.5 * (x[e] * t); } }
-      g0 = -v / 9.0 + Grp<G>::sum(gv);
+      // sum_i (-0.5 + 0.5 x_i^2/s^2) = 0.5 * sum_i x_i (x_i/s^2) - 0.5 (d-1): no per-element predicate (elements past the
+      // last component hold x = 0; component 0 is masked once) and four independent accumulators per lane
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      QSB_FOR_E {
+        double xe = x[e];
+        if (e == 0) xe = lane == 0 ? 0.0 : xe;
+        acc[e & 3] = fma(xe, xe * a, acc[e & 3]);
+      }
+      const double su = Grp<G>::sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+      g0 = -v / 9.0 + (0.5 * su - 0.5 * (double)(d - 1));
     } else {
       const double mu = Grp<G>::bcast(x[0], 0), lt = Grp<G>::bcast(x[0], 1);
       const double tau = exp(lt);
@@ -317,8 +324,8 @@ template <int FAM> struct GradScalars {
   // gradient of component i at value xi
   __device__ __forceinline__ double elem(const EngineParams& P, int i, double xi) const {
     const int d = P.m.dim;
+    if (FAM == FAM_FUNNEL) return i == 0 ? g0 : -(xi * a);   // elements past the last component hold x = 0: gradient -0
     if (i >= d) return 0.0;
-    if (FAM == FAM_FUNNEL) return i == 0 ? g0 : -(xi * a);
     if (i == 0) return g0;
     if (i == 1) return g1;
     const double rt = (xi - a) * b;
