@@ -383,12 +383,16 @@ template <int FAM> struct ModelStream {
 // of a lane's own total (1.7 n / 32).  Results go to this warp's columns of the block's staging array: component
 // 32*(row_begin + r) + l -> qsb_zbuf[r * rstride + (warp's first thread) + l], i.e. lane l later reads its own component of row r.
 // One out-of-line copy per kernel (the 10 Philox rounds are inlined in it).
+// LANE_CHAINS (thread per chain): the 32 lanes of the warp own 32 consecutive chains (gc = the chain of lane 0); work item
+// j is component row_begin + (j >> 5) of chain gc + (j & 31) and lands in the same place of the staging array, so the warp
+// shares the attempts of its 32 chains the same way.  Needs all 32 lanes of the warp at the call.
+template <bool LANE_CHAINS>
 static __device__ __noinline__ void gaussian_fill_warp(uint32_t k0, uint32_t k1, uint32_t gc, uint32_t iter, int row_begin, int n, int rstride) {
   extern __shared__ double qsb_zbuf[];
   double* zw = qsb_zbuf + (threadIdx.x & ~31u);
   const int lane = (int)(threadIdx.x & 31u);
   const unsigned lt = (1u << lane) - 1u;
-  const uint32_t slot0 = (uint32_t)row_begin * 32u;
+  const uint32_t slot0 = LANE_CHAINS ? (uint32_t)row_begin : (uint32_t)row_begin * 32u;
   int j = lane, next = 32;
   uint32_t blk = 0;
   bool active = j < n;
@@ -396,7 +400,8 @@ static __device__ __noinline__ void gaussian_fill_warp(uint32_t k0, uint32_t k1,
     bool ok = false;
     if (active) {
       uint32_t w[4];
-      philox4x32_10(blk, slot0 + (uint32_t)j, iter, gc, k0, k1, w);
+      if (LANE_CHAINS) philox4x32_10(blk, slot0 + ((uint32_t)j >> 5), iter, gc + ((uint32_t)j & 31u), k0, k1, w);
+      else philox4x32_10(blk, slot0 + (uint32_t)j, iter, gc, k0, k1, w);
       const double u = __dsub_rn(1.0, u53(w[0], w[1]));
       const double v = __dmul_rn(1.7156, __dsub_rn(u53(w[2], w[3]), 0.5));
       const double x = __dsub_rn(u, 0.449871);
@@ -468,7 +473,14 @@ template <int FAM, int G, int NPL> struct Chain {
   __device__ __forceinline__ void gaussian_fill(uint32_t iter, int e_begin, int e_end) const {
     if (G == 32 && !VU) {   // warp per chain: the lanes share the attempts of all components of these rows
       const int hi = e_end * 32 < d ? e_end * 32 : d;
-      gaussian_fill_warp(P.key.k0, P.key.k1, gc, iter, e_begin, hi - e_begin * 32, (int)blockDim.x);
+      gaussian_fill_warp<false>(P.key.k0, P.key.k1, gc, iter, e_begin, hi - e_begin * 32, (int)blockDim.x);
+      return;
+    }
+    if (G == 1 && !VU && P.nsub == 1 && __activemask() == 0xffffffffu) {
+      // thread per chain, a single kernel (every lane of the warp is at this call) and a full warp: the 32 chains share
+      // their attempts.  Partial tail warps and mixtures (lanes in different sub-kernels) take the per-lane loop below.
+      const int hi = e_end < d ? e_end : d;
+      gaussian_fill_warp<true>(P.key.k0, P.key.k1, gc - (uint32_t)(threadIdx.x & 31u), iter, e_begin, (hi - e_begin) * 32, (int)blockDim.x);
       return;
     }
     double* z = zcol();
