@@ -536,12 +536,12 @@ template <int FAM, int G, int NPL> struct Chain {
     double gr = target - EdH;
     uint32_t k = P.da_k[c] + 1;
     double avgeta = 1.0 / (double)(k + 10);
-    double xbar_avgeta = pow((double)k, -0.75);
     double muk = 0.5 * sqrt((double)k) / P.da_gamma[c];
     double gbar = avgeta * gr + (1 - avgeta) * P.da_gbar[c];
     double lastx = P.da_x0[c] - muk * gbar;
-    double xbar = xbar_avgeta * lastx + (1 - xbar_avgeta) * P.da_xbar[c];
-    if (leader()) { P.da_k[c] = k; P.da_gbar[c] = gbar; P.da_lastx[c] = lastx; P.da_xbar[c] = xbar; }
+    // DualAverage.xbar (hmc.t:44-46: xbar = k^-0.75 * lastx + (1 - k^-0.75) * xbar) is written by the reference but never
+    // read: not computed here -- it would cost a pow() per transition for a value nothing observes
+    if (leader()) { P.da_k[c] = k; P.da_gbar[c] = gbar; P.da_lastx[c] = lastx; }
     return exp(lastx);
   }
 

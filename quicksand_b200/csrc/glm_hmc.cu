@@ -604,13 +604,12 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
     double gr = target - EdH;
     uint32_t k = P.da_k[c] + 1;
     double avgeta = 1.0 / (double)(k + 10);
-    double xbar_avgeta = pow((double)k, -0.75);
     double muk = 0.5 * sqrt((double)k) / P.da_gamma[c];
     double gbar = avgeta * gr + (1 - avgeta) * P.da_gbar[c];
     double lastx = P.da_x0[c] - muk * gbar;
-    double xbar = xbar_avgeta * lastx + (1 - xbar_avgeta) * P.da_xbar[c];
+    // DualAverage.xbar (hmc.t:44-46) is written by the reference but never read: not computed
     __syncwarp();
-    if (lane == 0) { P.da_k[c] = k; P.da_gbar[c] = gbar; P.da_lastx[c] = lastx; P.da_xbar[c] = xbar; }
+    if (lane == 0) { P.da_k[c] = k; P.da_gbar[c] = gbar; P.da_lastx[c] = lastx; }
     eps_new = exp(lastx);
   }
   const double u = uniform_at(P.key, gc, P.iter, (uint32_t)d);
