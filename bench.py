@@ -330,8 +330,8 @@ def main():
             cpu["min_ess_note"] = "CPU chain-transitions/s x min-ESS per chain-transition of the GPU draws (same algorithm and stream)"
         per_launch_units = units_local / max(klaunch, 1)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default chain counts, from the
-        # ncu --set full captures summarised in profiles/r01d_*_ncu_metrics.csv
-        traffic = {"c3": (8192, 40.5e6), "c2": (65536, 15.1e6), "c4": (131072, 5.62e9), "c5": (32768, 0.491e9)}[wl["name"]]
+        # ncu --set full captures summarised in profiles/r01h_*_ncu_metrics.csv
+        traffic = {"c3": (8192, 42.2e6), "c2": (65536, 14.6e6), "c4": (131072, 5.46e9), "c5": (32768, 0.533e9)}[wl["name"]]
         common = {"traffic": traffic[1] if C == traffic[0] else None,
                   "kernel": "glm_grad_kernel" if wl["name"] == "c3" else "advance_kernel",
                   "kernel_ms_per_launch": 1e3 * ktime / max(klaunch, 1), "kernel_launches_timed": klaunch,
