@@ -53,8 +53,10 @@ enum { QSB_ERP_GAUSSIAN = 0, QSB_ERP_GAMMA = 1, QSB_ERP_BETA = 2, QSB_ERP_UNIFOR
         * 103-125) are host-side reparametrisations of gamma / beta. */
        QSB_ERP_DIRICHLET = 4 };
 
-/* transition kernels: qs/hmc.t:57-66, qs/drift.t:63-73, qs/harm.t:16-22 */
-enum { QSB_KERNEL_HMC = 1, QSB_KERNEL_DRIFT = 2, QSB_KERNEL_HARM = 3 };
+/* transition kernels: qs/hmc.t:57-66, qs/drift.t:63-73, qs/harm.t:16-22; TRACEMH = TraceMHKernel{doStruct=false}
+ * (qs/mcmc.t:134-193): one random choice per iteration, gaussian ERPs drift with their own sigma (erpdefs.t:46-57), the
+ * others resample from their prior (erp.t:18-38); the structural half of that kernel is out of scope. */
+enum { QSB_KERNEL_HMC = 1, QSB_KERNEL_DRIFT = 2, QSB_KERNEL_HARM = 3, QSB_KERNEL_TRACEMH = 4 };
 
 typedef struct qsb_model qsb_model;       /* opaque; owns device copies of the model data */
 typedef struct qsb_sampler qsb_sampler;   /* opaque; owns the SoA chain state in HBM */

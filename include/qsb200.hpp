@@ -60,6 +60,8 @@ struct DriftParams { double scale = 1.0; bool doScaleAdapt = true; bool lexicalS
 struct HARMParams { double scale = 1.0; bool doScaleAdapt = true; };
 inline Kernel HMCKernel(HMCParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_HMC, p.doStepSizeAdapt ? 1 : 0, p.stepSize, p.numSteps, 1.0, 1.0, 0, 0}}}; }
 inline Kernel DriftKernel(DriftParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_DRIFT, p.doScaleAdapt ? 1 : 0, 1.0, 1, p.scale, 1.0, p.lexicalScaleSharing ? 1 : 0, 0}}}; }
+// TraceMHKernel{doStruct=false} (mcmc.t:134-193): fixed-structure programs have non-structural choices only
+inline Kernel TraceMHKernel() { return Kernel{{qsb_kernel_spec{QSB_KERNEL_TRACEMH, 0, 1.0, 1, 1.0, 1.0, 0, 0}}, {}}; }
 inline Kernel HARMKernel(HARMParams p = {}) { return Kernel{{qsb_kernel_spec{QSB_KERNEL_HARM, p.doScaleAdapt ? 1 : 0, 1.0, 1, p.scale, 1.0, 0, 0}}}; }
 inline Kernel MixtureKernel(const std::vector<Kernel>& kernels, const std::vector<double>& weights) {
   if (kernels.size() != weights.size()) throw Error("MixtureKernel: number of kernels must equal number of weights");   // mcmc.t:200-201

@@ -32,7 +32,7 @@ def use(variant):
     assert variant in _SO
     _ACTIVE = variant
 
-HMC, DRIFT, HARM = 1, 2, 3
+HMC, DRIFT, HARM, TRACEMH = 1, 2, 3, 4
 ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
 ITER_INIT = 0xFFFFFFFF
 ITER_SEARCH = 0xF0000000

@@ -125,6 +125,7 @@ static Kernel* make_kernel(const qso_kernel_spec* specs, int nspecs) {
       case 1: return new HMCKernel(s.stepSize, s.numSteps, s.doAdapt != 0);
       case 2: return new DriftKernel(s.scale, s.doAdapt != 0, s.lexicalScaleSharing != 0);
       case 3: return new HARMKernel(s.scale, s.doAdapt != 0);
+      case 4: return new TraceMHKernel();
     }
     return nullptr;
   };

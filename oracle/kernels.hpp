@@ -392,6 +392,33 @@ struct HARMKernel : Kernel {
   }
 };
 
+// ------------------------------------------------------------------ qs/mcmc.t:134-193, {doStruct=false}: every choice of a
+// fixed-structure program is non-structural, so the filter keeps them all and no dimension-jumping terms arise
+struct TraceMHKernel : Kernel {
+  void next(Trace<double>* currTrace, uint32_t iter, uint32_t) override {
+    propsMade = propsMade + 1;
+    Trace<double> nextTrace = *currTrace;
+    size_t numchoices = nextTrace.countChoices();
+    if (numchoices == 0) { std::printf("TraceMHKernel: found 0 random choices satisfying doStruct=false and doNonstruct=true\n"); std::abort(); }
+    rng().at(iter, SLOT_MH_INDEX);
+    size_t randindex = (size_t)(random_() * numchoices);
+    RandomChoice<double>& rc = nextTrace.choices[randindex];
+    rng().at(iter, SLOT_MH_PROPOSAL);
+    std::pair<double, double> pl = rc.proposal();
+    double fwdPropLP = pl.first, rvsPropLP = pl.second;
+    nextTrace.update(false);
+    double acceptThresh = (nextTrace.logprob - currTrace->logprob) + rvsPropLP - fwdPropLP;
+    rng().at(iter, SLOT_MH_ACCEPT);
+    bool accept = nextTrace.conditionsSatisfied && std::log(random_()) < acceptThresh;
+    Recorder* rec = recorder();
+    if (rec) { rec->dH.push_back(acceptThresh); rec->accepted.push_back(accept ? 1 : 0); rec->stepsize.push_back((double)randindex); }
+    if (accept) {
+      propsAccepted = propsAccepted + 1;
+      std::swap(*currTrace, nextTrace);
+    }
+  }
+};
+
 // ------------------------------------------------------------------ qs/mcmc.t:199-291
 struct MixtureKernel : Kernel {
   std::vector<std::unique_ptr<Kernel>> kernels;

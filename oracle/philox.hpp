@@ -34,6 +34,8 @@ namespace qso {
 static const uint32_t ITER_INIT = 0xFFFFFFFFu;
 static const uint32_t ITER_SEARCH = 0xF0000000u;
 static const uint32_t SLOT_MIXTURE = 0xFFFFFFFFu;
+// TraceMHKernel (qs/mcmc.t:134-193): which choice, the proposal's sampler (a sequential sub-stream), the accept test
+static const uint32_t SLOT_MH_INDEX = 0xFFFFFFFEu, SLOT_MH_PROPOSAL = 0xFFFFFFFDu, SLOT_MH_ACCEPT = 0xFFFFFFFCu;
 
 inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];

@@ -182,6 +182,36 @@ template <class real> struct RandomChoice {   // RandomChoiceT, erp.t:286-311
       default: return D::gaussian_sample(p0, p1);
     }
   }
+  // RandomChoiceT:proposal (erp.t:643-657): the gaussian ERP drifts around the current value with its own sigma
+  // (erpdefs.t:46-57); every other ERP resamples from its prior (makeDefaultProposal, erp.t:18-38).  Float traces only
+  // (TraceMH never runs on a dual trace).  Returns {fwdlp, rvslp}.
+  std::pair<double, double> proposal() {
+    static_assert(true, "");
+    double fwdlp, rvslp;
+    if (is_vector()) {
+      std::vector<real> cur = getValueV();
+      std::vector<double> pv(vparams.size()), out(vparams.size()), cv(vparams.size());
+      for (size_t i = 0; i < pv.size(); ++i) { pv[i] = val(vparams[i]); cv[i] = val(cur[i]); }
+      D::dirichlet_sample(pv.data(), (int)pv.size(), out.data());
+      fwdlp = D::dirichlet_logprob<double>(out.data(), pv.data(), (int)pv.size());
+      rvslp = D::dirichlet_logprob<double>(cv.data(), pv.data(), (int)pv.size());
+      setValueV(std::vector<real>(out.begin(), out.end()));
+      return {fwdlp, rvslp};
+    }
+    double currval = val(getValue()), p0 = val(param0), p1 = val(param1), newval;
+    if (kind == ERP_GAUSSIAN) {
+      newval = D::gaussian_sample(currval, p1);
+      fwdlp = D::gaussian_logprob<double>(newval, currval, p1);
+      rvslp = D::gaussian_logprob<double>(currval, newval, p1);
+    } else {
+      newval = sample(p0, p1);
+      RandomChoice<double> tmp; tmp.kind = kind; tmp.param0 = p0; tmp.param1 = p1;
+      fwdlp = tmp.prior_logprob(newval);
+      rvslp = tmp.prior_logprob(currval);
+    }
+    setValue(real(newval));
+    return {fwdlp, rvslp};
+  }
   // erp.t:369-429
   real getValue() { if (applyingBounds) return fwd(value); return value; }
   void setValue(real newval) { if (applyingBounds) newval = inv(newval); value = newval; needsRescore = true; }

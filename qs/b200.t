@@ -69,6 +69,12 @@ local function HARMKernel(params)           -- qs/harm.t:16-22
 	return kernelSpec(B.QSB_KERNEL_HARM, doScaleAdapt, 1.0, 1, params.scale or 1.0)
 end
 
+local function TraceMHKernel(params)        -- qs/mcmc.t:134-193; fixed-structure programs: the non-structural half only
+	params = params or {}
+	assert(params.doStruct == false, "qs.b200.TraceMHKernel: pass {doStruct=false} (structural choices stay on qs.MCMC)")
+	return kernelSpec(B.QSB_KERNEL_TRACEMH, false, 1.0, 1, 1.0)
+end
+
 local function MixtureKernel(kernels, weights)   -- qs/mcmc.t:199-203
 	assert(#kernels == #weights, "MixtureKernel: number of kernels must equal number of weights")
 	local specs = {}
@@ -196,6 +202,7 @@ return
 			HMCKernel = HMCKernel,
 			DriftKernel = DriftKernel,
 			HARMKernel = HARMKernel,
+			TraceMHKernel = TraceMHKernel,
 			MixtureKernel = MixtureKernel,
 			AnnealingKernel = AnnealingKernel,
 			describe = describe,

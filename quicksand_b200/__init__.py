@@ -5,9 +5,9 @@ The compute lives in ``libqsb200.so`` (hand-written CUDA for sm_100a behind the 
 hot path.  There is no CPU fallback: without the built library every compute call raises.
 """
 from . import programs
-from .api import (AnnealingKernel, Autocorrelation, DriftKernel, Expectation, HARMKernel, HMCKernel, MAP, MCMC, MixtureKernel,
+from .api import (AnnealingKernel, TraceMHKernel, Autocorrelation, DriftKernel, Expectation, HARMKernel, HMCKernel, MAP, MCMC, MixtureKernel,
                   Sampler, Samples, SampleVector, infer)
 from .programs import Program
 
 __all__ = ["programs", "Program", "infer", "MCMC", "HMCKernel", "DriftKernel", "HARMKernel", "MixtureKernel",
-           "AnnealingKernel", "Samples", "MAP", "Expectation", "Autocorrelation", "Sampler", "SampleVector"]
+           "AnnealingKernel", "TraceMHKernel", "Samples", "MAP", "Expectation", "Autocorrelation", "Sampler", "SampleVector"]

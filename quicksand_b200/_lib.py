@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libqsb200.so")
 
 FAM_INDEP, FAM_GAUSS_PREC, FAM_LOGISTIC, FAM_EIGHT_SCHOOLS, FAM_FUNNEL = 1, 2, 3, 4, 5
 ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
-KERNEL_HMC, KERNEL_DRIFT, KERNEL_HARM = 1, 2, 3
+KERNEL_HMC, KERNEL_DRIFT, KERNEL_HARM, KERNEL_TRACEMH = 1, 2, 3, 4
 FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL = 1, 2, 4, 8
 
 dp = C.POINTER(C.c_double)

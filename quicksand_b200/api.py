@@ -5,6 +5,7 @@
     qs.HMCKernel{stepSize, numSteps, doStepSizeAdapt}              qs/hmc.t:57-66
     qs.DriftKernel{scale, doScaleAdapt, lexicalScaleSharing}       qs/drift.t:63-73
     qs.HARMKernel{scale, doScaleAdapt}                             qs/harm.t:16-22
+    qs.TraceMHKernel{doStruct=false}                               qs/mcmc.t:134-193 (the non-structural half)
     qs.MixtureKernel(kernels, weights)                             qs/mcmc.t:199-291
     qs.AnnealingKernel(kernel, annealSched)                        qs/mcmc.t:297-319
     qs.Samples / qs.Expectation / qs.Autocorrelation               qs/infer.t:128-136, 146-187, 213-264
@@ -63,6 +64,21 @@ def HARMKernel(params=None, **kw):
     adapt = p.get("doScaleAdapt", True)                        # harm.t:19-20
     s = L.KernelSpec(L.KERNEL_HARM, int(bool(adapt)), 1.0, 1, float(p.get("scale", 1.0)), 1.0, 0, 0)
     return KernelSpecs([s], ["HARMKernel"])
+
+
+def TraceMHKernel(params=None, **kw):
+    """qs/mcmc.t:134-193.  Fixed-structure programs have no structural choices, so only ``doStruct=false`` (re-propose one
+    random non-structural choice per iteration) exists on the device; the default ``doStruct=true`` is refused."""
+    p = dict(params or {}); p.update(kw)
+    unknown = set(p) - {"doStruct", "doNonstruct"}
+    if unknown:
+        raise TypeError("TraceMHKernel: unknown params %s" % sorted(unknown))
+    doStruct, doNonstruct = p.get("doStruct", True), p.get("doNonstruct", True)
+    assert doStruct or doNonstruct, "TraceMHKernel: cannot set both 'doStruct' and 'doNonstruct' to false"   # mcmc.t:139
+    if doStruct:
+        raise NotImplementedError("TraceMHKernel: structural choices are out of scope of the device path; pass doStruct=False")
+    s = L.KernelSpec(L.KERNEL_TRACEMH, 0, 1.0, 1, 1.0, 1.0, 0, 0)
+    return KernelSpecs([s], ["TraceMHKernel"])
 
 
 def MixtureKernel(kernels, weights):

@@ -348,6 +348,13 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
         if (m->arena.alloc(&dm, d->dim)) return bail(4, "cudaMalloc failed");
         cudaMemcpy(dm, amap.data(), sizeof(int) * d->dim, cudaMemcpyHostToDevice);
         m->dev.lex_map = dm; m->dev.n_adapters = (int)seen.size();
+        // TraceMHKernel picks among the random choices (a vector choice is one): first component of each
+        std::vector<int> first;
+        for (int i = 0; i < d->dim; ++i) if (i == 0 || slot[i] != slot[i - 1]) first.push_back(i);
+        int* df;
+        if (m->arena.alloc(&df, first.size())) return bail(4, "cudaMalloc failed");
+        cudaMemcpy(df, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice);
+        m->dev.erp_first = df; m->dev.n_choices = (int)first.size();
       }
       cudaMemcpy(k, d->erp_kind, sizeof(int) * d->dim, cudaMemcpyHostToDevice);
       cudaMemcpy(p0, d->erp_p0, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
@@ -360,7 +367,7 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
       if (!d->A) return bail(3, "GAUSS_PREC: A required");
       if (d->dim > 16) return bail(3, "GAUSS_PREC: dim <= 16 supported (thread-per-chain register path)");
       m->A.assign(d->A, d->A + (size_t)d->dim * d->dim);
-      m->dev.n_adapters = 1;
+      m->dev.n_adapters = 1; m->dev.n_choices = d->dim;
       break;
     }
     case QSB_FAM_LOGISTIC: {
@@ -379,10 +386,10 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
       precompute_obs_kernel<<<(d->nobs + 127) / 128, 128>>>(sg, cy, s2, is2, d->nobs);
       if (cudaDeviceSynchronize() != cudaSuccess) return bail(6, "precompute_obs_kernel failed");
       m->dev.y = y; m->dev.cy = cy; m->dev.s2 = s2; m->dev.is2 = is2; m->sigma_dev = sg;
-      m->dev.n_adapters = 3;
+      m->dev.n_adapters = 3; m->dev.n_choices = d->dim;
       break;
     }
-    case QSB_FAM_FUNNEL: m->dev.n_adapters = 2; break;
+    case QSB_FAM_FUNNEL: m->dev.n_adapters = 2; m->dev.n_choices = d->dim; break;
     default: return bail(2, "qsb_model_create: unknown family");
   }
   *out = m;
@@ -491,16 +498,17 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   *out = nullptr;
   if (nspecs < 1 || nspecs > MAX_SUB) return fail(2, "qsb_sampler_create: 1..8 kernels");
   if (cfg->numchains == 0) return fail(2, "qsb_sampler_create: numchains must be positive");
-  int nh = 0, nd = 0, nr = 0;
+  int nh = 0, nd = 0, nr = 0, nm = 0;
   for (int i = 0; i < nspecs; ++i) {
     switch (specs[i].kind) {
       case QSB_KERNEL_HMC: ++nh; if (specs[i].numSteps < 1 || specs[i].numSteps > 0xFFFFFFFFull) return fail(2, "HMC: numSteps out of range"); break;
       case QSB_KERNEL_DRIFT: ++nd; break;
       case QSB_KERNEL_HARM: ++nr; break;
+      case QSB_KERNEL_TRACEMH: ++nm; break;
       default: return fail(2, "qsb_sampler_create: unknown kernel kind");
     }
   }
-  if (nh > 1 || nd > 1 || nr > 1) return fail(2, "qsb_sampler_create: at most one kernel of each kind per mixture");
+  if (nh > 1 || nd > 1 || nr > 1 || nm > 1) return fail(2, "qsb_sampler_create: at most one kernel of each kind per mixture");
   CU(cudaSetDevice(m->device));
   qsb_sampler* s = new qsb_sampler();
   s->m = m; s->cfg = *cfg; s->specs.assign(specs, specs + nspecs);
@@ -509,7 +517,7 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   auto bail = [&](int code, const std::string& msg) { s->arena.release(); if (s->glm) glm_sampler_destroy(s->glm); delete s; return fail(code, msg); };
   if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) return bail(4, "cudaEventCreate failed");
   if (m->desc.family == QSB_FAM_LOGISTIC) {
-    if (nspecs != 1) return bail(2, "LOGISTIC: the tensor-core path runs a single kernel (HMC, Drift or HARM), not a mixture");
+    if (nspecs != 1 || specs[0].kind == QSB_KERNEL_TRACEMH) return bail(2, "LOGISTIC: the tensor-core path runs a single kernel (HMC, Drift or HARM), not a mixture or TraceMH");
     if (specs[0].kind == QSB_KERNEL_DRIFT && specs[0].lexicalScaleSharing) return bail(2, "LOGISTIC: DriftKernel{lexicalScaleSharing} is not implemented on the tensor-core path");
     std::string why;
     s->glm = glm_sampler_create(&m->glm, specs[0].kind, specs[0].stepSize, (uint32_t)specs[0].numSteps, specs[0].scale, specs[0].doAdapt != 0,
@@ -693,7 +701,9 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
     }
     bool has_hmc = false;
     for (int k = 0; k < R.nsub; ++k) has_hmc |= R.kind[k] == K_HMC;
-    if (R.dr_lexical) s->var->advance_lex(R, s->stream);
+    bool has_mh = false;
+    for (int k = 0; k < R.nsub; ++k) has_mh |= R.kind[k] == K_TRACEMH;
+    if (R.dr_lexical || has_mh) s->var->advance_lex(R, s->stream);   // the general kernel
     else if (R.nsub == 1 && R.kind[0] == K_DRIFT) s->var->advance_drift(R, s->stream);
     else if (has_hmc) s->var->advance(R, s->stream);
     else s->var->advance_nohmc(R, s->stream);

@@ -26,7 +26,7 @@
 namespace qsb {
 
 enum { FAM_INDEP = 1, FAM_GAUSS_PREC = 2, FAM_LOGISTIC = 3, FAM_EIGHT_SCHOOLS = 4, FAM_FUNNEL = 5 };
-enum { K_HMC = 1, K_DRIFT = 2, K_HARM = 3 };
+enum { K_HMC = 1, K_DRIFT = 2, K_HARM = 3, K_TRACEMH = 4 };
 enum { FLAG_HMC_INIT = 1, FLAG_GRAD_VALID = 2 };
 enum { ERR_NAN_SEARCH = 1, ERR_SEARCH_INF = 2, ERR_SEARCH_ZERO = 4 };
 static constexpr int MAX_SUB = 8;
@@ -42,6 +42,8 @@ struct ModelDev {
   // DriftKernel{lexicalScaleSharing} (drift.t:101-115, 208-235): scale adapter of every component.  INDEP: lex_map;
   // GAUSS_PREC: one; EIGHT_SCHOOLS: mu, logtau, theta-loop; FUNNEL: v, x-loop
   const int* lex_map; int n_adapters;
+  // TraceMHKernel: the random choices of the program (INDEP: first component of every choice; elsewhere one per component)
+  const int* erp_first; int n_choices;
   // EIGHT_SCHOOLS observations, precomputed once per model with the same device operations the
   // per-term logprob would use (bit-identical): cy = 1.8378770664093453 + 2*log(sigma), s2 = sigma*sigma
   const double* y; const double* cy; const double* s2; const double* is2;   // is2 = 1/s2
@@ -1039,6 +1041,95 @@ template <int FAM, int G, int NPL> struct Chain {
     return accept;
   }
 
+  // ---- TraceMHKernel:next with {doStruct=false} (mcmc.t:134-193): one random choice is re-proposed -- a gaussian ERP
+  // drifts around its current value with its own sigma (erpdefs.t:46-57), every other ERP resamples from its prior
+  // (erp.t:18-38) -- the whole program is rescored (float trace: no Jacobian), accept on (lp' - lp) + rvs - fwd.
+  // Every lane of a chain's group computes the (chain-uniform) proposal itself.
+  __device__ __forceinline__ void choice_params(int j, const double (&x)[NPL], int& kind, double& p0, double& p1) const {
+    kind = ERP_GAUSSIAN; p0 = 0.0; p1 = 1.0;
+    if (FAM == FAM_INDEP) { kind = P.m.erp_kind[j]; p0 = P.m.p0[j]; p1 = P.m.p1[j]; }
+    else if (FAM == FAM_EIGHT_SCHOOLS) {
+      if (j == 0) p1 = 5.0;
+      else if (j >= 2) { p0 = Grp<G>::bcast(x[0], 0); p1 = exp(G == 1 ? x[NPL > 1 ? 1 : 0] : Grp<G>::bcast(x[0], 1)); }
+    } else if (FAM == FAM_FUNNEL) {
+      if (j == 0) p1 = 3.0; else p1 = exp(Grp<G>::bcast(x[0], 0) / 2.0);
+    }
+  }
+  __device__ __forceinline__ double component(const double (&x)[NPL], int j) const {   // x_j, known to every lane of the group
+    double v = 0.0;
+    QSB_FOR_E { if (e * G + lane == j) v = x[e]; }
+    return Grp<G>::sum(v);
+  }
+  __device__ __forceinline__ bool tracemh_next(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
+    double x[NPL];
+    const size_t kc = (size_t)k * P.C + c;
+    load(P.x, x);
+    const int nch = P.m.n_choices;
+    const int r = (int)(uniform_at(P.key, gc, iter, QSB_SLOT_MH_INDEX) * (double)nch);   // random()*numchoices, truncated (mcmc.t:171-172)
+    rec_step = (double)r;
+    const int j0 = FAM == FAM_INDEP ? P.m.erp_first[r] : r;
+    SubStream s(P.key, gc, iter, QSB_SLOT_MH_PROPOSAL);
+    double fwdlp, rvslp;
+    int kind; double p0, p1;
+    choice_params(j0, x, kind, p0, p1);
+    if (G == 1 && FAM == FAM_INDEP && kind == ERP_DIRICHLET) {
+      // vector choice: K gammas from the proposal sub-stream, normalised (distrib.t:339-350); current value by stick
+      // breaking, new unconstrained coordinates by its inverse (erp.t:205-233)
+      const int K = P.m.erp_len[j0], Km1 = K - 1;
+      double t[32], cur[32], alpha[32];
+      double ssum = 0.0, asum = 0.0, stick = 1.0;
+      for (int q = 0; q < K; ++q) {
+        alpha[q] = P.m.p0[j0 + q];
+        const double xq = component(x, j0 + q);
+        if (q < Km1) { const double z = logistic_(xq - log((double)(Km1 - q))); cur[q] = stick * z; stick = stick - cur[q]; } else cur[q] = stick;
+        t[q] = gamma_sample_seq(s, alpha[q], 1.0); ssum = ssum + t[q]; asum = asum + alpha[q];
+      }
+      for (int q = 0; q < K; ++q) t[q] = t[q] / ssum;
+      fwdlp = log_gamma5(asum); rvslp = fwdlp;
+      for (int q = 0; q < K; ++q) {
+        fwdlp = fwdlp + (alpha[q] - 1.0) * log(t[q]); fwdlp = fwdlp - log_gamma5(alpha[q]);
+        rvslp = rvslp + (alpha[q] - 1.0) * log(cur[q]); rvslp = rvslp - log_gamma5(alpha[q]);
+      }
+      double sticklen = t[Km1];
+      QSB_FOR_E { if (e == j0 + Km1) x[e] = 0.0; }
+      for (int q = Km1 - 1; q >= 0; --q) {
+        sticklen = sticklen + t[q];
+        const double xn = invlogistic_(t[q] / sticklen) + log((double)(Km1 - q));
+        QSB_FOR_E { if (e == j0 + q) x[e] = xn; }
+      }
+    } else {
+      const double cur_x = component(x, j0);
+      const double cur_v = erp_fwd_noinline(kind, cur_x, p0, p1);
+      double new_v, new_x;
+      if (kind == ERP_GAUSSIAN) {
+        new_v = gaussian_sample_seq(s, cur_v, p1);
+        fwdlp = gaussian_lp(new_v, cur_v, p1);
+        rvslp = gaussian_lp(cur_v, new_v, p1);
+        new_x = new_v;
+      } else {
+        new_v = erp_sample_seq(kind, s, p0, p1);
+        fwdlp = erp_prior_lp(kind, new_v, p0, p1, nullptr);
+        rvslp = erp_prior_lp(kind, cur_v, p0, p1, nullptr);
+        new_x = erp_inv(kind, new_v, p0, p1);
+      }
+      QSB_FOR_E { if (e * G + lane == j0) x[e] = new_x; }
+    }
+    double lpf, gdummy[NPL];
+    model_eval<FAM, G, NPL, false, true, false>(P, lane, x, gdummy, lpf);
+    if (T != 1.0) lpf = lpf / T;
+    const double thresh = (lpf - P.lp[c]) + rvslp - fwdlp;
+    rec_dh = thresh;
+    const double u = uniform_at(P.key, gc, iter, QSB_SLOT_MH_ACCEPT);
+    const bool accept = log(u) < thresh;
+    if (accept) store(P.x, x);
+    if (G == 32) __syncwarp();
+    if (leader()) {
+      P.made[kc] += 1;
+      if (accept) { P.acc[kc] += 1; P.lp[c] = lpf; P.flags[c] = P.flags[c] & ~FLAG_GRAD_VALID; }
+    }
+    return accept;
+  }
+
   // ---- HARMKernel:next (harm.t:60-113)
   __device__ __forceinline__ bool harm_next(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
     double x[NPL], xp[NPL];
@@ -1306,8 +1397,9 @@ template <int FAM, int G, int NPL> struct Chain {
       if constexpr (SCALAR_GRAD) accept = hmc_next_warp(k, iter, rdh, rstep);
       else accept = hmc_next(k, iter, rdh, rstep);
     }
+    else if (LEX && kind == K_TRACEMH) accept = tracemh_next(k, iter, rdh, rstep);
     else if (DRIFT_ONLY || kind == K_DRIFT) {
-      if constexpr (LEX) {
+      if (LEX && P.dr_lexical) {
         if constexpr (STREAM) accept = drift_next_stream_lex(k, iter, rdh, rstep);
         else accept = drift_next_lex(k, iter, rdh, rstep);
       } else {
@@ -1368,7 +1460,8 @@ template <int FAM, int G, int NPL> struct Chain {
 // Kernels
 // HAS_HMC = false: the kernel list holds no HMCKernel; the trajectory code (and its register vectors) is not compiled
 // in, which lets the warp-per-chain Drift / HARM kernels run at 3 blocks per SM.
-// LEX: the DriftKernel shares scales per call site (lexicalScaleSharing); always built with HAS_HMC = true.
+// LEX: the general kernel -- everything above plus DriftKernel{lexicalScaleSharing} and TraceMHKernel; always built with
+// HAS_HMC = true.  The specialised kernels do not carry that code, so their register allocation is not bent by it.
 // DRIFT_ONLY: a single DriftKernel (config c4): no HARM code in the kernel, so the register allocator serves one path.
 template <int FAM, int G, int NPL, bool HAS_HMC, bool LEX = false, bool DRIFT_ONLY = false>
 __global__ void __launch_bounds__(G == 1 || HAS_HMC ? 128 : 256, G == 1 ? 4 : 3)

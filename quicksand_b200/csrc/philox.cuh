@@ -23,6 +23,8 @@ namespace qsb {
 static constexpr uint32_t QSB_ITER_INIT = 0xFFFFFFFFu;
 static constexpr uint32_t QSB_ITER_SEARCH = 0xF0000000u;
 static constexpr uint32_t QSB_SLOT_MIXTURE = 0xFFFFFFFFu;
+// TraceMHKernel (qs/mcmc.t:134-193): which choice, the proposal's sampler (a sequential sub-stream), the accept test
+static constexpr uint32_t QSB_SLOT_MH_INDEX = 0xFFFFFFFEu, QSB_SLOT_MH_PROPOSAL = 0xFFFFFFFDu, QSB_SLOT_MH_ACCEPT = 0xFFFFFFFCu;
 
 struct RngKey { uint32_t k0, k1; };
 

@@ -193,6 +193,47 @@ def test_harm_per_step_parity(qs, oracle, name, mapping):
     assert P.relerr(gpu["step"], cpu["step"]).max() <= 1e-9
 
 
+TRACEMH = [("gaussian1", 0), ("gamma1", 0), ("beta1", 0), ("uniform1", 0), ("gauss10", 0), ("mixed10", 0), ("mixed10", 32), ("dirichlet4", 0),
+           ("dirmix9", 0), ("wide24", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0), ("funnel12", 1), ("funnel12", 32),
+           ("funnel70", 0)]
+
+
+@pytest.mark.parametrize("name,mapping", TRACEMH)
+def test_tracemh_nonstructural_parity(qs, oracle, name, mapping):
+    """TraceMHKernel{doStruct=false} (mcmc.t:134-193): which choice, the proposal (gaussian drift with the ERP's own sigma,
+    prior resampling for the other ERPs incl. vector choices), the forward/reverse proposal terms and the accept decision."""
+    prog = _programs(qs)[name]
+    gpu, cpu = P.run_both(prog, qs.TraceMHKernel(doStruct=False), chains=64, iters=300, seed=41, mapping=mapping)
+    assert np.array_equal(gpu["step"], cpu["step"])            # the chosen choice index of every iteration
+    P.compare(gpu, cpu, TOL, what="TraceMH %s map%d" % (name, mapping))
+    assert gpu["accept"].mean() > 0          # (resampling a lone ERP from its prior is always accepted)
+
+
+def test_tracemh_in_mixtures_and_truth(qs, oracle):
+    """The reference's most common kernel shape: MixtureKernel({TraceMHKernel, HMCKernel}) (testsuite.t:732-751 on a
+    structural program; here its fixed-structure counterpart), per step against the oracle, and the expectation truths of
+    the continuous ERPs under TraceMH alone (testsuite.t:192-266 protocol: 150 samples x lag 20, tolerance 0.07)."""
+    prog = _programs(qs)["mixed10"]
+    k = qs.MixtureKernel([qs.TraceMHKernel(doStruct=False), qs.HMCKernel(numSteps=3, stepSize=0.05, doStepSizeAdapt=False),
+                          qs.DriftKernel(scale=0.2)], [0.5, 0.25, 0.25])
+    gpu, cpu = P.run_both(prog, k, chains=64, iters=200, seed=42)
+    assert np.array_equal(gpu["kidx"], cpu["kidx"])
+    P.compare(gpu, cpu, TOL, what="Mixture TraceMH+HMC+Drift mixed10", min_compared=0.9)
+    k = qs.AnnealingKernel(qs.TraceMHKernel(doStruct=False), _cooling)
+    gpu, cpu = P.run_both(_programs(qs)["funnel12"], k, chains=32, iters=100, seed=43, mapping=32)
+    P.compare(gpu, cpu, TOL, what="Annealed TraceMH funnel12")
+    for name, truth in (("gaussian1", 0.1), ("gamma1", 0.4), ("beta1", 2.0 / 7.0), ("uniform1", 0.25)):
+        m = qs.MCMC(qs.TraceMHKernel(doStruct=False), dict(numsamps=150, lag=20, numchains=512, seed=9))
+        est = qs.infer(_programs(qs)[name], qs.Expectation(), m)()
+        assert abs(np.mean(est) - truth) < 0.02, (name, np.mean(est))
+        assert np.mean(np.abs(est - truth) <= 0.07) > 0.5
+    with pytest.raises(NotImplementedError):
+        qs.TraceMHKernel()                  # the default (structural) form is not a device kernel
+    from quicksand_b200 import _lib as L
+    with pytest.raises(L.QsbError):
+        qs.Sampler(_programs(qs)["logistic20"], qs.TraceMHKernel(doStruct=False), numchains=4)
+
+
 @pytest.mark.parametrize("name,mapping,eps", [("funnel12", 1, 0.01), ("funnel70", 0, 0.01), ("gauss10", 0, 0.2), ("schools13", 32, 0.02)])
 def test_mixture_harm_hmc_parity(qs, oracle, name, mapping, eps):
     """config c5's kernel: MixtureKernel({HARMKernel{}, HMCKernel{numSteps=L}}, {0.5, 0.5}) (mcmc.t:199-291)."""

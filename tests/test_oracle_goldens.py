@@ -123,3 +123,10 @@ def test_drift_lexical_scale_sharing_truth(oracle):
     """testsuite.t:846-860: 10 gaussians drawn by one call site, DriftKernel{lexicalScaleSharing=true} -> 0.1."""
     prog = oracle.Program.indep([0] * 10, [0.1] * 10, [0.5] * 10, 0, 10.0, lexids=[0] * 10)
     assert _expected_value(oracle, prog, oracle.spec(oracle.DRIFT, lexicalScaleSharing=True), 0.1) <= 0.07
+
+
+@pytest.mark.parametrize("name,erp,div,truth", HMC_TRUTHS, ids=[t[0] for t in HMC_TRUTHS])
+def test_tracemh_expectation_truths(oracle, name, erp, div, truth):
+    """testsuite.t:192-266 (multiMethodExpectedValueTest, the MCMC leg with TraceMHKernel) on the continuous ERPs."""
+    prog = oracle.Program.indep([erp[0]], [erp[1]], [erp[2]], 0, div)
+    assert _expected_value(oracle, prog, oracle.spec(oracle.TRACEMH), truth) <= 0.07
