@@ -81,6 +81,9 @@ typedef struct {
                             * ERP call inside a loop share an id.  NULL = every choice is its own call site.  Only
                             * DriftKernel{lexicalScaleSharing=true} reads it.  The other families have fixed sites:
                             * GAUSS_PREC / LOGISTIC one loop; EIGHT_SCHOOLS mu, logtau, theta-loop; FUNNEL v, x-loop. */
+  const double* erp_fmu;   /* INDEP [dim] or NULL: a Gaussian factor on the value of scalar choice i right after it,          */
+  const double* erp_fsigma;/*   qs.factor(gaussian.logprob(v_i, fmu_i, fsigma_i)) == qs.gaussian.observe(v_i, fmu_i, fsigma_i)
+                            *   (trace.t:1099-1107; erp.t:687-696; testsuite.t:394-442).  fsigma_i <= 0: no factor.            */
 } qsb_model_desc;
 
 /* One transition kernel; nspecs > 1 means MixtureKernel(kernels, weights) (qs/mcmc.t:199-291). */

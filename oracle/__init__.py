@@ -80,6 +80,7 @@ def lib(variant=None):
             getattr(L, f).restype = C.c_void_p
         L.qso_program_indep.argtypes = [C.c_int, C.POINTER(C.c_int), dp, dp, C.c_int, C.c_double]
         L.qso_program_indep_lexids.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.qso_program_indep_factors.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.qso_program_gauss_prec.argtypes = [C.c_int, dp]
         L.qso_program_logistic.argtypes = [C.c_int, C.c_int, dp, C.POINTER(C.c_ubyte), C.c_double]
         L.qso_program_eight_schools.argtypes = [C.c_int, dp, dp]
@@ -155,7 +156,7 @@ class Program:
             pass
 
     @staticmethod
-    def indep(kinds, p0, p1, ret_mode=0, ret_div=1.0, lexids=None):
+    def indep(kinds, p0, p1, ret_mode=0, ret_div=1.0, lexids=None, fmu=None, fsigma=None):
         k = np.ascontiguousarray(kinds, dtype=np.int32)
         a = np.ascontiguousarray(p0, dtype=np.float64)
         b = np.ascontiguousarray(p1, dtype=np.float64)
@@ -163,6 +164,9 @@ class Program:
         if lexids is not None:
             lx = np.ascontiguousarray(lexids, dtype=np.int32)
             lib().qso_program_indep_lexids(C.c_void_p(h), len(lx), lx.ctypes.data_as(C.POINTER(C.c_int)))
+        if fsigma is not None:
+            fm = np.ascontiguousarray(fmu, dtype=np.float64); fs = np.ascontiguousarray(fsigma, dtype=np.float64)
+            lib().qso_program_indep_factors(C.c_void_p(h), len(fs), _dp(fm), _dp(fs))
         return Program(h)
 
     @staticmethod

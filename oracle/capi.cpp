@@ -92,6 +92,9 @@ void* qso_program_indep(int K, const int* kind, const double* p0, const double* 
   return p;
 }
 void qso_program_indep_lexids(void* prog, int K, const int* lexid) { ((IndepErps*)prog)->lexid.assign(lexid, lexid + K); }
+void qso_program_indep_factors(void* prog, int K, const double* fmu, const double* fsigma) {
+  ((IndepErps*)prog)->fmu.assign(fmu, fmu + K); ((IndepErps*)prog)->fsigma.assign(fsigma, fsigma + K);
+}
 void* qso_program_gauss_prec(int d, const double* A) {
   GaussPrecision* p = new GaussPrecision();
   p->d = d; p->A.assign(A, A + (size_t)d * d); p->retdim = d;

@@ -26,6 +26,7 @@ struct IndepErps : Program {
   std::vector<int> kind;
   std::vector<double> p0, p1;
   std::vector<int> lexid;   // call-site id per entry (empty: every choice is its own call site)
+  std::vector<double> fmu, fsigma;   // optional qs.factor(gaussian.logprob(value_i, fmu_i, fsigma_i)) after scalar choice i (fsigma <= 0: none)
   int ret_mode = 0;
   double ret_div = 1.0;
   // Entries are per real component.  A dirichlet choice of K components is K consecutive entries of kind
@@ -45,6 +46,7 @@ struct IndepErps : Program {
         i = j;
       } else {
         real x = t.erp(kind[i], real(p0[i]), real(p1[i]));
+        if (!fsigma.empty() && fsigma[i] > 0.0) t.factor(D::gaussian_logprob<real>(x, real(fmu[i]), real(fsigma[i])));   // testsuite.t:394-442
         if (ret_mode == 0) sum = sum + x; else t.returnValue.push_back(x);
         ++i;
       }

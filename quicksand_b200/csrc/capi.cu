@@ -360,6 +360,15 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
       cudaMemcpy(p0, d->erp_p0, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
       cudaMemcpy(p1, d->erp_p1, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
       m->dev.erp_kind = k; m->dev.p0 = p0; m->dev.p1 = p1;
+      if (d->erp_fsigma) {
+        if (!d->erp_fmu) return bail(3, "INDEP: erp_fmu is required with erp_fsigma");
+        for (int i = 0; i < d->dim; ++i) if (d->erp_fsigma[i] > 0.0 && d->erp_kind[i] == QSB_ERP_DIRICHLET) return bail(3, "INDEP: factors on the components of a dirichlet choice are not supported");
+        double *fm, *fs;
+        if (m->arena.alloc(&fm, d->dim) || m->arena.alloc(&fs, d->dim)) return bail(4, "cudaMalloc failed");
+        cudaMemcpy(fm, d->erp_fmu, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
+        cudaMemcpy(fs, d->erp_fsigma, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
+        m->dev.fmu = fm; m->dev.fsigma = fs;
+      }
       if (d->ret_mode == 0) m->retdim = 1;
       break;
     }

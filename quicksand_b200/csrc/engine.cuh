@@ -35,6 +35,9 @@ struct ModelDev {
   int family, dim, nobs, ret_mode;
   double ret_div, prior_sigma;
   const int* erp_kind; const double* p0; const double* p1;   // INDEP
+  // INDEP: optional Gaussian factor on the value of a scalar choice, qs.factor(gaussian.logprob(value, fmu, fsigma)) ==
+  // qs.gaussian.observe(value, fmu, fsigma) (trace.t:1099-1107; erp.t:687-696; testsuite.t:394-442); fsigma <= 0: none
+  const double* fmu; const double* fsigma;
   // INDEP, dirichlet components (thread-per-chain mapping only): choice length K, sum of the later alphas of the choice,
   // and the ERP index of every component (= the Philox slot of its forward sample; equals the component index without vector choices)
   const int* erp_len; const double* erp_asum; const int* erp_slot;
@@ -113,10 +116,14 @@ template <int G> __device__ __forceinline__ size_t vidx(const EngineParams& P, i
 // One ERP site of a dual trace: prior logprob of the constrained value, log-Jacobian, and
 // d(logprob + logJ)/dx  (erp.t:623-640).  Not inlined: the INDEP family is not a throughput path
 // and the four-way kind switch would otherwise be replicated at every unrolled component.
-static __device__ __noinline__ void erp_eval(int kind, double x, double p0, double p1, double& lpy, double& lj, double& g) {
+static __device__ __noinline__ void erp_eval(int kind, double x, double p0, double p1, double fmu, double fsigma, double& lpy, double& lj, double& g) {
   double dydx, dlpdy, dlj;
   double y = erp_fwd(kind, x, p0, p1, &dydx);
   lpy = erp_prior_lp(kind, y, p0, p1, &dlpdy);
+  if (fsigma > 0.0) {   // the factor statement that follows the choice: likelihood term on the constrained value
+    lpy = lpy + gaussian_lp(y, fmu, fsigma);
+    dlpdy = dlpdy + gaussian_dlp_dx(y, fmu, fsigma);
+  }
   lj = erp_logjac(kind, x, p0, p1, &dlj);
   g = dlpdy * dydx + dlj;
 }
@@ -151,7 +158,7 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
           if (GRAD) g[e] = gi;
         } else {
           double lpy, lj, gi;
-          erp_eval(kind, x[e], m.p0[i], m.p1[i], lpy, lj, gi);
+          erp_eval(kind, x[e], m.p0[i], m.p1[i], m.fsigma ? m.fmu[i] : 0.0, m.fsigma ? m.fsigma[i] : 0.0, lpy, lj, gi);
           lpf += lpy;
           lpd += lpy + lj;
           if (GRAD) g[e] = gi;
@@ -357,7 +364,7 @@ template <int FAM> struct ModelStream {
   __device__ __forceinline__ void term(const EngineParams& P, int i, double xi, const Obs& o, double& lp) const {
     if (FAM == FAM_INDEP) {
       double lpy, lj, gi;
-      erp_eval(P.m.erp_kind[i], xi, P.m.p0[i], P.m.p1[i], lpy, lj, gi);
+      erp_eval(P.m.erp_kind[i], xi, P.m.p0[i], P.m.p1[i], P.m.fsigma ? P.m.fmu[i] : 0.0, P.m.fsigma ? P.m.fsigma[i] : 0.0, lpy, lj, gi);
       lp += lpy;
     } else if (FAM == FAM_EIGHT_SCHOOLS) {
       if (i >= 2) {
@@ -1524,6 +1531,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_c
           SubStream s(P.key, ch.gc, QSB_ITER_INIT, slot);
           double y = erp_sample_seq(kind, s, p0, p1);
           lp += erp_prior_lp(kind, y, p0, p1, nullptr);   // float trace: logprob of the sampled value itself
+          if (P.m.fsigma && P.m.fsigma[i] > 0.0) lp += gaussian_lp(y, P.m.fmu[i], P.m.fsigma[i]);   // and the factor that follows it
           x[e] = erp_inv(kind, y, p0, p1);
         }
       }

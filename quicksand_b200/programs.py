@@ -44,6 +44,8 @@ class Program:
             d.y = _dp(a["y"]); d.sigma = _dp(a["sigma"])
         if "erp_lexid" in a:
             d.erp_lexid = a["erp_lexid"].ctypes.data_as(L.ip)
+        if "erp_fsigma" in a:
+            d.erp_fmu = _dp(a["erp_fmu"]); d.erp_fsigma = _dp(a["erp_fsigma"])
         return d
 
     def model(self, device=-1):
@@ -90,7 +92,7 @@ class Program:
 _KIND = {"gaussian": L.ERP_GAUSSIAN, "gamma": L.ERP_GAMMA, "beta": L.ERP_BETA, "uniform": L.ERP_UNIFORM}
 
 
-def indep(erps, ret="sum", ret_div=1.0, lexids=None):
+def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
     """Independent ERPs with constant parameters, e.g. ``[("gamma", 2.0, 2.0)]`` with ret_div=10 for
     ``return qs.gamma(2.0, 2.0, {struc=false})/10.0`` (test/testsuite.t:657-673).  Entries:
 
@@ -99,18 +101,24 @@ def indep(erps, ret="sum", ret_div=1.0, lexids=None):
       ("betamv", m, v)   -> beta(-m*tmp/v, (m-1)*tmp/v), tmp = m*m - m + v (must be < 0)       erpdefs.t:103-117
       ("dirichlet", [alpha_0 .. alpha_{K-1}])  one vector-valued choice of K real components   erpdefs.t:179-212
 
+    ``factors[i]``: ``None`` or ``(mu, sigma)``: the statement ``qs.factor(gaussian.logprob(value_i, mu, sigma))`` (equally
+    ``qs.gaussian.observe(value_i, mu, sigma)``) right after scalar choice i (test/testsuite.t:394-442).
+
     ``lexids[i]``: call-site id of entry i (entries produced by one ERP call inside a loop share an id); only
     DriftKernel{lexicalScaleSharing=true} looks at it (drift.t:208-235).  Default: every entry is its own call site."""
-    kinds, p0, p1, lex = [], [], [], []
+    kinds, p0, p1, lex, fmu, fsig = [], [], [], [], [], []
     for n_e, e in enumerate(erps):
         k = e[0]
         site = n_e if lexids is None else int(lexids[n_e])
+        fac = None if factors is None else factors[n_e]
         if k == "dirichlet":
+            assert fac is None, "factors on a dirichlet choice are not supported"
             alphas = [float(a) for a in e[1]]
             for j, a in enumerate(alphas):
-                kinds.append(L.ERP_DIRICHLET); p0.append(a); p1.append(float(j)); lex.append(site)
+                kinds.append(L.ERP_DIRICHLET); p0.append(a); p1.append(float(j)); lex.append(site); fmu.append(0.0); fsig.append(0.0)
             continue
         lex.append(site)
+        fmu.append(0.0 if fac is None else float(fac[0])); fsig.append(0.0 if fac is None else float(fac[1]))
         a, b = float(e[1]), float(e[2])
         if k == "gammamv":
             k, a, b = "gamma", a * a / b, b / a
@@ -120,6 +128,8 @@ def indep(erps, ret="sum", ret_div=1.0, lexids=None):
             k, a, b = "beta", -a * tmp / b, (a - 1) * tmp / b
         kinds.append(_KIND[k] if isinstance(k, str) else int(k)); p0.append(a); p1.append(b)
     extra = {} if lexids is None else {"erp_lexid": np.array(lex, dtype=np.int32)}
+    if factors is not None:
+        extra.update(erp_fmu=np.array(fmu, dtype=np.float64), erp_fsigma=np.array(fsig, dtype=np.float64))
     return Program(L.FAM_INDEP, len(kinds), erp_kind=np.array(kinds, dtype=np.int32), erp_p0=np.array(p0, dtype=np.float64),
                    erp_p1=np.array(p1, dtype=np.float64), ret_mode=0 if ret == "sum" else 1, ret_div=float(ret_div), **extra)
 

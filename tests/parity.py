@@ -15,7 +15,8 @@ def oracle_specs(kernel):
 def oracle_program(p):
     a = p.arrays
     if p.family == L.FAM_INDEP:
-        return O.Program.indep(a["erp_kind"], a["erp_p0"], a["erp_p1"], p.ret_mode, p.ret_div, lexids=a.get("erp_lexid"))
+        return O.Program.indep(a["erp_kind"], a["erp_p0"], a["erp_p1"], p.ret_mode, p.ret_div, lexids=a.get("erp_lexid"),
+                               fmu=a.get("erp_fmu"), fsigma=a.get("erp_fsigma"))
     if p.family == L.FAM_GAUSS_PREC:
         return O.Program.gauss_prec(a["A"])
     if p.family == L.FAM_LOGISTIC:

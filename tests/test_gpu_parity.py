@@ -60,6 +60,11 @@ def _programs(qs):
     progs["dirichlet4"] = qs.programs.indep([("dirichlet", [1.0, 1.0, 1.0, 1.0])], ret="vector")
     progs["dirmix9"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("dirichlet", [2.0, 3.0, 5.0]), ("gammamv", 4.0, 8.0),
                                            ("dirichlet", [0.7, 1.5, 1.0]), ("betamv", 0.3, 0.02)], ret="vector")
+    # qs.factor / erp.observe statements on the value of a choice (testsuite.t:394-442: uniform(-1,1) with a gaussian(0.3, 0.1) factor)
+    progs["factor1"] = qs.programs.indep([("uniform", -1.0, 1.0)], factors=[(0.3, 0.1)])
+    progs["factor6"] = qs.programs.indep([("uniform", -1.0, 1.0), ("gaussian", 0.0, 2.0), ("gamma", 2.0, 2.0), ("beta", 2.0, 5.0), ("gaussian", 1.0, 1.0),
+                                           ("gammamv", 3.0, 2.0)], ret="vector",
+                                          factors=[(0.3, 0.1), (1.0, 0.5), (3.0, 1.0), None, (0.5, 0.7), (2.5, 0.4)])
     progs["wide24"] = qs.programs.indep([("dirichlet", [1.5] * 8), ("gaussian", 0.0, 1.0), ("gamma", 3.0, 0.5), ("dirichlet", [0.8, 1.0, 2.0, 3.0, 1.2, 0.9]),
                                           ("beta", 2.0, 2.0), ("uniform", -2.0, 2.0)] + [("gaussian", 1.0, 0.2)] * 6, ret="vector")
     # call sites shared by several choices (a loop body), for DriftKernel{lexicalScaleSharing=true} (testsuite.t:846-860)
@@ -79,7 +84,7 @@ def _programs(qs):
     return progs
 
 
-@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "dirichlet4", "dirmix9", "wide24", "c2",
+@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "dirichlet4", "dirmix9", "wide24", "factor1", "factor6", "c2",
                                   "schools13", "schools62", "funnel12", "funnel70", "logistic20"])
 def test_logp_and_gradient_match_tape_ad(qs, oracle, name):
     """Closed-form device gradients vs the oracle's tape AD (qs/lib/ad.t) on random unconstrained points."""
@@ -103,6 +108,7 @@ HMC_FIXED = [
     ("gauss10", dict(numSteps=10, stepSize=0.2), 0, 1.0), ("mixed10", dict(numSteps=5, stepSize=0.1), 0, 1.0),
     ("dirichlet4", dict(numSteps=10, stepSize=0.2), 0, 1.0), ("dirmix9", dict(numSteps=5, stepSize=0.1), 0, 1.0),
     ("wide24", dict(numSteps=5, stepSize=0.05), 0, 1.0),
+    ("factor1", dict(numSteps=10, stepSize=0.05), 0, 1.0), ("factor6", dict(numSteps=5, stepSize=0.05), 0, 1.0), ("factor6", dict(numSteps=5, stepSize=0.05), 32, 1.0),
     ("mixed10", dict(numSteps=5, stepSize=0.1), 32, 1.0),
     ("c2", dict(numSteps=16, stepSize=0.15), 0, 1.0),
     ("schools13", dict(numSteps=8, stepSize=0.02), 1, 0.95), ("schools13", dict(numSteps=8, stepSize=0.02), 32, 0.95),
@@ -159,7 +165,7 @@ def test_hmc_adaptive_search_and_dual_averaging(qs, oracle, name, L, mapping, mi
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0), ("logistic20", 0)])
+                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0), ("logistic20", 0), ("factor6", 0), ("factor6", 32)])
 def test_drift_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=64, iters=400, seed=99, mapping=mapping)
@@ -193,7 +199,7 @@ def test_harm_per_step_parity(qs, oracle, name, mapping):
     assert P.relerr(gpu["step"], cpu["step"]).max() <= 1e-9
 
 
-TRACEMH = [("gaussian1", 0), ("gamma1", 0), ("beta1", 0), ("uniform1", 0), ("gauss10", 0), ("mixed10", 0), ("mixed10", 32), ("dirichlet4", 0),
+TRACEMH = [("factor1", 0), ("factor6", 0), ("factor6", 32), ("gaussian1", 0), ("gamma1", 0), ("beta1", 0), ("uniform1", 0), ("gauss10", 0), ("mixed10", 0), ("mixed10", 32), ("dirichlet4", 0),
            ("dirmix9", 0), ("wide24", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0), ("funnel12", 1), ("funnel12", 32),
            ("funnel70", 0)]
 
@@ -227,6 +233,11 @@ def test_tracemh_in_mixtures_and_truth(qs, oracle):
         est = qs.infer(_programs(qs)[name], qs.Expectation(), m)()
         assert abs(np.mean(est) - truth) < 0.02, (name, np.mean(est))
         assert np.mean(np.abs(est - truth) <= 0.07) > 0.5
+    # testsuite.t:394-442 "factor / observe expectation (mcmc)": uniform(-1, 1) with a gaussian(0.3, 0.1) factor -> 0.3
+    for kern in (qs.TraceMHKernel(doStruct=False), qs.HMCKernel(numSteps=10)):
+        m = qs.MCMC(kern, dict(numsamps=150, lag=20, numchains=512, seed=10))
+        est = qs.infer(_programs(qs)["factor1"], qs.Expectation(), m)()
+        assert abs(np.mean(est) - 0.3) < 0.02 and np.mean(np.abs(est - 0.3) <= 0.07) > 0.9, np.mean(est)
     with pytest.raises(NotImplementedError):
         qs.TraceMHKernel()                  # the default (structural) form is not a device kernel
     from quicksand_b200 import _lib as L

@@ -130,3 +130,12 @@ def test_tracemh_expectation_truths(oracle, name, erp, div, truth):
     """testsuite.t:192-266 (multiMethodExpectedValueTest, the MCMC leg with TraceMHKernel) on the continuous ERPs."""
     prog = oracle.Program.indep([erp[0]], [erp[1]], [erp[2]], 0, div)
     assert _expected_value(oracle, prog, oracle.spec(oracle.TRACEMH), truth) <= 0.07
+
+
+@pytest.mark.parametrize("kind", ["tracemh", "hmc"])
+def test_factor_and_observe_expectation(oracle, kind):
+    """testsuite.t:394-442 "factor expectation (mcmc)" / "observe expectation (mcmc)": x ~ uniform(-1, 1) with
+    qs.factor(gaussian.logprob(x, 0.3, 0.1)) == qs.gaussian.observe(x, 0.3, 0.1) -> 0.3 (the reference runs it under TraceMH)."""
+    prog = oracle.Program.indep([3], [-1.0], [1.0], 0, 1.0, fmu=[0.3], fsigma=[0.1])
+    spec = oracle.spec(oracle.TRACEMH) if kind == "tracemh" else oracle.spec(oracle.HMC, numSteps=10)
+    assert _expected_value(oracle, prog, spec, 0.3) <= 0.07
