@@ -485,6 +485,23 @@ def test_dirichlet_samples_live_on_the_simplex(qs):
         qs.Sampler(prog, qs.HMCKernel(), numchains=4, mapping=32)
 
 
+def test_reference_compile_and_run_programs(qs, oracle):
+    """The reference's compile-and-run tests on the hot path, through the mirrored interface with their own parameters
+    (numsamps = 150): "dirichlet array compile and run (HMC)" (testsuite.t:693-702, HMCKernel() defaults) and "drift vector
+    compile and run (lexical state sharing)" (testsuite.t:886-897: two dirichlet choices from two call sites)."""
+    prog = qs.programs.indep([("dirichlet", [1.0, 1.0, 1.0, 1.0])], ret="vector")
+    samples = qs.infer(prog, qs.Samples(), qs.MCMC(qs.HMCKernel(), dict(numsamps=150, numchains=4, seed=1)))()
+    v = samples.value
+    assert v.shape == (4, 150, 4) and np.all(np.isfinite(v)) and np.abs(v.sum(axis=2) - 1.0).max() < 1e-12 and v.min() > 0.0
+    prog = qs.programs.indep([("dirichlet", [1.0, 1.0, 1.0, 1.0]), ("dirichlet", [1.0, 1.0, 1.0, 1.0])], ret="vector", lexids=[0, 1])
+    k = qs.DriftKernel(lexicalScaleSharing=True)
+    samples = qs.infer(prog, qs.Samples(), qs.MCMC(k, dict(numsamps=150, numchains=4, seed=1)))()
+    v = samples.value
+    assert v.shape == (4, 150, 8) and np.all(np.isfinite(v)) and np.abs(v[:, :, :4].sum(axis=2) - 1.0).max() < 1e-12
+    gpu, cpu = P.run_both(prog, k, chains=16, iters=150, seed=1)
+    P.compare(gpu, cpu, TOL, what="two dirichlets, drift with lexical scale sharing")
+
+
 def test_error_behaviour(qs):
     """Unsupported requests fail loudly with a message (the shim turns them into the reference's print + abort)."""
     from quicksand_b200 import _lib as L
