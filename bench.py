@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=os.environ.get("QSB_WORKLOAD", "c3"))
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
+    ap.add_argument("--scaling", default=os.environ.get("QSB_SCALING", "weak"), choices=["weak", "strong"],
+                    help="weak (default): the configuration's chain count per GPU; strong: that chain count in total, sharded over the GPUs")
     ap.add_argument("--burnin", type=int, default=None, help="untimed adaptation transitions before the warm-up steps")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -225,6 +227,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = workload(args.workload, args.chains)
     prog, kernel, C = wl["prog"], wl["kernel"], wl["chains"]
+    if args.scaling == "strong":
+        C = max(C // world, 1)            # BASELINE's chain count in total (c3: 8 192 = 8 x 1 024), block partition over the ranks
     B = args.burnin if args.burnin is not None else {"c3": 150, "c2": 300, "c4": 300, "c5": 100}[wl["name"]]
     Ke = args.e2e_steps if args.e2e_steps is not None else min(K, 10)
     stream = torch.cuda.current_stream().cuda_stream
@@ -331,7 +335,7 @@ def main():
         per_launch_units = units_local / max(klaunch, 1)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default chain counts, from the
         # ncu --set full captures summarised in profiles/r01h_*_ncu_metrics.csv
-        traffic = {"c3": (8192, 42.2e6), "c2": (65536, 14.6e6), "c4": (131072, 5.46e9), "c5": (32768, 0.533e9)}[wl["name"]]
+        traffic = {"c3": (8192, 42.2e6), "c2": (65536, 14.6e6), "c4": (131072, 5.46e9), "c5": (32768, 0.533e9)}[wl["name"]]   # (chains per GPU, bytes)
         common = {"traffic": traffic[1] if C == traffic[0] else None,
                   "kernel": "glm_grad_kernel" if wl["name"] == "c3" else "advance_kernel",
                   "kernel_ms_per_launch": 1e3 * ktime / max(klaunch, 1), "kernel_launches_timed": klaunch,
@@ -351,7 +355,7 @@ def main():
         line = {
             "metric": "leapfrog steps/sec (all chains)" if wl["name"] != "c4" else "proposals/sec (all chains)",
             "value": value, "unit": wl["unit"], "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (wl["name"], wl["desc"]), "chains_per_gpu": C, "chains_total": C * world,
                        "burnin_transitions": B, "l2": "working set (chain state + partial sums) larger than L2; inputs change every step",
                        "seed": SEED},
