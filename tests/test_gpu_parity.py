@@ -372,6 +372,22 @@ def test_c3_full_shape_gradient_kernel_against_oracle(qs, oracle):
     full.close(); tail.close()
 
 
+def test_shared_and_per_lane_gaussian_fill_agree(qs, oracle):
+    """Thread-per-chain kernels draw the Gaussians of a full warp's 32 chains cooperatively and those of a partial tail warp
+    (or of a mixture, where lanes sit in different sub-kernels) lane by lane; a chain's draws must not depend on which:
+    40 chains = one full warp + a tail of 8, against the oracle and against the same chain ids run as a lone partial warp."""
+    prog = _programs(qs)["c2"]
+    k = qs.HMCKernel(numSteps=4, stepSize=0.15, doStepSizeAdapt=False)
+    gpu, cpu = P.run_both(prog, k, chains=40, iters=30, seed=12, leap=True)
+    P.compare(gpu, cpu, TOL, leap=True, what="HMC c2, 40 chains")
+    a = qs.Sampler(prog, k, numchains=40, seed=12); a.init(); a.run(30)
+    b = qs.Sampler(prog, k, numchains=8, seed=12, chain_begin=5); b.init(); b.run(30)      # chains 5..12 of the full warp, as a partial warp
+    assert np.array_equal(a.fetch_values()[5:13], b.fetch_values())
+    a.close(); b.close()
+    gpu, cpu = P.run_both(_programs(qs)["gauss10"], qs.HARMKernel(), chains=40, iters=100, seed=13)
+    P.compare(gpu, cpu, TOL, what="HARM gauss10, 40 chains")
+
+
 def test_chain_ids_are_partition_invariant(qs):
     """Philox key = global chain id: chains [32,64) run as a shard equal chains 32..63 of the full run, bit for bit
     (the multi-GPU invariance the chain sharding relies on)."""
