@@ -250,11 +250,20 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
 #pragma unroll
     for (int T = 0; T < NT; ++T) dmma(a[T], th[J][1], xv[T].y);   // then the dependent second k-step of each
   };
+  // Log-likelihood of a row block: sum_i log w_i with w_i = (y_i ? p_i : 1 - p_i) (distrib.t:17-25 on the naive sigmoid) is
+  // taken as ONE log of the product of the block's eight w_i per thread -- seven library logs fewer per block, and the
+  // product's rounding (8 ulp) is smaller than that of a sum of eight logs.  Factors below 1e-30 (a hopelessly misfit
+  // observation) are added as their own log so that the product cannot underflow.
+  double wprod = 1.0;
+  auto lik_factor = [&](double w) {
+    if (w < 1e-30) lpacc += log(w); else wprod *= w;
+  };
+  auto lik_flush = [&]() { lpacc += log(wprod); wprod = 1.0; };
   auto epilogue_elem = [&](const double* ys, int T, int e) {
     const double y = ys[T * 8 + (e ? rho_t1 : rho_t0)];
     if (want_lp) {
       const double pr = 1.0 / (1.0 + exp(-acc[T][e]));
-      if (y <= 1.0) lpacc += log(y != 0.0 ? pr : 1.0 - pr);   // distrib.t:17-25 on the naive sigmoid
+      if (y <= 1.0) lik_factor(y != 0.0 ? pr : 1.0 - pr);
       acc[T][e] = y - pr;
     } else {
       acc[T][e] = y - sigmoid_fast(acc[T][e]);
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
       const double* Xn = sm + SD * st2;
 #pragma unroll
       for (int T = 0; T < NT; ++T) nxt[T][0] = nxt[T][1] = 0.0;
-      if constexpr (!LP && NT == 4 && NJ >= 12) {
+      if constexpr (NT == 4 && NJ >= 12) {
         // lock-step sigmoid: elements (T=0,1) advance 4 steps per dimension tile J = 0..5, elements (T=2,3) during J = 6..11
         SigState sa[4], sb[4];
         double ya[4], yb[4];
@@ -304,6 +313,16 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
         for (int J = 12; J < NJ; ++J) if (FULL || J < nj) phase1_tile(Xn, J, nxt);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { acc[i >> 1][i & 1] = sa[i].zr; acc[2 + (i >> 1)][i & 1] = sb[i].zr; }
+        if (want_lp) {
+          // from the residual r = y - p of the lock-step sigmoid: y = 1: p = 1 - r; y = 0: 1 - p = 1 + r; i.e. w = 1 - |r|
+          // (equal to the naive form up to the rounding of 1 - p).  Padding rows carry y = 2.
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (ya[i] <= 1.0) lik_factor(1.0 - fabs(sa[i].zr));
+            if (yb[i] <= 1.0) lik_factor(1.0 - fabs(sb[i].zr));
+          }
+          lik_flush();
+        }
       } else {
 #pragma unroll
         for (int J = 0; J < NJ; ++J) {
@@ -312,10 +331,12 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
         }
 #pragma unroll
         for (int q = NJ; q < 2 * NT; ++q) epilogue_elem(ys, q >> 1, q & 1);
+        if (want_lp) lik_flush();
       }
     } else {
 #pragma unroll
       for (int q = 0; q < 2 * NT; ++q) epilogue_elem(ys, q >> 1, q & 1);
+      if (want_lp) lik_flush();
     }
     // phase 2: G^T += R^T X
     if (P.want_grad)
