@@ -13,8 +13,9 @@
 // (dims 8J+2t, 8J+2t+1 of chain g) and all shared-memory fragment loads are bank-conflict free.
 //
 // X (N x d, row stride S) is streamed from L2 through shared memory by one producer thread with TMA
-// bulk copies (cp.async.bulk + mbarrier complete_tx) into a STAGES-deep ring; the 8 consumer warps of a
-// CTA (64 chains) all read the same staged rows, so each row block is fetched once per 64 chains.
+// bulk copies (cp.async.bulk + mbarrier complete_tx) into a ring of 2..4 stages; the 16 consumer warps of a
+// CTA (128 chains) all read the same staged rows, so each row block is fetched once per 128 chains; the chain tile's Theta
+// sits in shared memory next to the ring (conflict-free LDS.128 rows), not in registers.
 // The grid is (chain tiles) x (row splits): row splits give full waves on 148 SMs for any chain
 // count; their partial gradients are summed in a fixed order by the vector kernel (deterministic).
 //
@@ -36,8 +37,14 @@ namespace qsb {
 
 static constexpr int MB = 32;          // observation rows per pipeline stage
 static constexpr int NT = MB / 8;      // 8-row n-tiles per stage
-static constexpr int STAGES = 4;
-static constexpr int CW = 12;          // warps per CTA (3 per SM sub-partition: 16384 regs / 3 / 32 = 170 -> 168 regs/thread)
+static constexpr int STAGES = 4;        // deepest ring; a sampler uses 2..4 stages (GradParams::stages), whatever fits 227 KB
+#ifndef QSB_GLM_CW
+#define QSB_GLM_CW 16
+#endif
+// warps per CTA.  12: Theta of the chain tile in registers (3 warps per SM sub-partition at 168 registers).  16: Theta in
+// shared memory (the ring leaves 124 KB unused), 4 warps per sub-partition at 128 registers.
+static constexpr int CW = QSB_GLM_CW;
+static constexpr bool THETA_SMEM = CW == 16;
 static constexpr int CB = CW * 8;      // chains per CTA
 static constexpr int GRAD_THREADS = CW * 32;
 
@@ -49,6 +56,7 @@ struct GradParams {
   double* partG;           // [ksplit][C][Dp]
   double* partLp;          // [ksplit][C]
   int want_lp;
+  int stages;              // depth of the X ring in shared memory (2..STAGES)
   int want_grad;           // 0: only the first contraction and the log-likelihood (Drift / HARM score a proposal, no gradient)
 };
 
@@ -89,6 +97,9 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 
 // smem: per stage [MB*S + 8 doubles X (8 = zeroed over-read pad)] [MB doubles y]; then 2*STAGES mbarriers
 __host__ __device__ inline size_t stage_doubles(int S) { return (size_t)MB * S + 8 + MB; }
+// row stride of the Theta tile in shared memory: == 8 mod 16 doubles, so that the LDS.128 of a quarter warp (two chains x
+// four dimension pairs) hits 32 distinct banks
+__host__ __device__ inline int theta_stride(int Dp) { return ((Dp / 8) & 1) ? Dp : Dp + 8; }
 
 // exp(-z) and 1/(1+exp(-z)) without branches: the library exp()/division carry slow-path branches that cost
 // issue slots and reconvergence stalls inside the MMA pipeline (ncu: profiles/r01_c3_grad_v1).  Accurate to
@@ -175,17 +186,27 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   const size_t SD = stage_doubles(P.S);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + SD * STAGES);
+  const int NST = P.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + SD * NST);
   uint64_t* empty = full + STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x % P.ntiles, split = blockIdx.x / P.ntiles;
   const int b0 = (int)(((long)split * P.nblocks) / P.ksplit), b1 = (int)(((long)(split + 1) * P.nblocks) / P.ksplit);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < STAGES * 8) sm[SD * (threadIdx.x >> 3) + (size_t)MB * P.S + (threadIdx.x & 7)] = 0.0;   // over-read pads
+  if ((int)threadIdx.x < NST * 8) sm[SD * (threadIdx.x >> 3) + (size_t)MB * P.S + (threadIdx.x & 7)] = 0.0;   // over-read pads
+  if (THETA_SMEM) {   // the chain tile's Theta, [CB][theta_stride]; rows of chains past the end are zero
+    double* sT = sm + SD * NST + 2 * STAGES;
+    const int Dp = P.Dp, stride = theta_stride(Dp);
+    for (int idx = threadIdx.x; idx < CB * Dp; idx += GRAD_THREADS) {
+      const int ch = idx / Dp, j = idx - ch * Dp;
+      const uint32_t gch = (uint32_t)tile * CB + ch;
+      sT[(size_t)ch * stride + j] = gch < P.C ? P.theta[(size_t)gch * Dp + j] : 0.0;
+    }
+  }
   __syncthreads();
 
   // ---- no dedicated producer warp (it would take a third of one sub-partition's register file): thread 0 starts
@@ -193,14 +214,14 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   // block (TMA bulk copies of whole row blocks: contiguous in HBM because Xp is stored with stride S)
   const uint32_t bytesX = (uint32_t)(MB * P.S * sizeof(double)), bytesY = (uint32_t)(MB * sizeof(double));
   auto issue_load = [&](int b) {
-    const int st = (b - b0) % STAGES;
+    const int st = (b - b0) % NST;
     mbar_expect_tx(&full[st], bytesX + bytesY);
     double* dst = sm + SD * st;
     bulk_g2s(dst, P.Xp + (size_t)b * MB * P.S, bytesX, &full[st]);
     bulk_g2s(dst + (size_t)MB * P.S + 8, P.yv + (size_t)b * MB, bytesY, &full[st]);
   };
   if (threadIdx.x == 0)
-    for (int b = b0; b < b1 && b < b0 + STAGES; ++b) issue_load(b);
+    for (int b = b0; b < b1 && b < b0 + NST; ++b) issue_load(b);
 
   // ---- consumers: warp w owns chains tile*CB + 8w .. +7; thread (gid, tig) owns dims 8J+2tig+{0,1} of chain gid
   const int gid = lane >> 2, tig = lane & 3;
@@ -212,13 +233,18 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   const uint32_t RHO = 0x57463120u;
   const int rho_g = (RHO >> (4 * gid)) & 7, rho_t0 = (RHO >> (8 * tig)) & 7, rho_t1 = (RHO >> (8 * tig + 4)) & 7;
 
-  double th[NJ][2], G[NJ][2];
+  double th[THETA_SMEM ? 1 : NJ][2], G[NJ][2];
+  const int STH = theta_stride(P.Dp);
+  const double* sTh = sm + SD * NST + 2 * STAGES + (size_t)(warp * 8 + gid) * STH + 2 * tig;   // THETA_SMEM: this thread's Theta row
 #pragma unroll
   for (int J = 0; J < NJ; ++J) {
-    th[J][0] = th[J][1] = 0.0; G[J][0] = G[J][1] = 0.0;
-    if ((FULL || J < nj) && valid) {
-      double2 v = *reinterpret_cast<const double2*>(P.theta + (size_t)chain * P.Dp + 8 * J + 2 * tig);
-      th[J][0] = v.x; th[J][1] = v.y;
+    G[J][0] = G[J][1] = 0.0;
+    if (!THETA_SMEM) {
+      th[J % (THETA_SMEM ? 1 : NJ)][0] = th[J % (THETA_SMEM ? 1 : NJ)][1] = 0.0;
+      if ((FULL || J < nj) && valid) {
+        double2 v = *reinterpret_cast<const double2*>(P.theta + (size_t)chain * P.Dp + 8 * J + 2 * tig);
+        th[J % (THETA_SMEM ? 1 : NJ)][0] = v.x; th[J % (THETA_SMEM ? 1 : NJ)][1] = v.y;
+      }
     }
   }
   double thL = 0.0;                                     // TRIM: theta[8(NJ-1) + tig]
@@ -245,10 +271,13 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
     double2 xv[NT];
 #pragma unroll
     for (int T = 0; T < NT; ++T) xv[T] = *reinterpret_cast<const double2*>(Xs + T * 8 * S + offA + 8 * J);
+    double t0, t1;
+    if (THETA_SMEM) { const double2 tv = *reinterpret_cast<const double2*>(sTh + 8 * J); t0 = tv.x; t1 = tv.y; }
+    else { t0 = th[J % (THETA_SMEM ? 1 : NJ)][0]; t1 = th[J % (THETA_SMEM ? 1 : NJ)][1]; }
 #pragma unroll
-    for (int T = 0; T < NT; ++T) dmma(a[T], th[J][0], xv[T].x);   // NT independent accumulators back to back,
+    for (int T = 0; T < NT; ++T) dmma(a[T], t0, xv[T].x);   // NT independent accumulators back to back,
 #pragma unroll
-    for (int T = 0; T < NT; ++T) dmma(a[T], th[J][1], xv[T].y);   // then the dependent second k-step of each
+    for (int T = 0; T < NT; ++T) dmma(a[T], t1, xv[T].y);   // then the dependent second k-step of each
   };
   // Log-likelihood of a row block: sum_i log w_i with w_i = (y_i ? p_i : 1 - p_i) (distrib.t:17-25 on the naive sigmoid) is
   // taken as ONE log of the product of the block's eight w_i per thread -- seven library logs fewer per block, and the
@@ -278,13 +307,13 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
     for (int J = 0; J < NJ; ++J) if (FULL || J < nj) phase1_tile(sm, J, acc);
   }
   for (int b = b0; b < b1; ++b) {
-    const int it = b - b0, st = it % STAGES;
+    const int it = b - b0, st = it % NST;
     const double* Xs = sm + SD * st;
     const double* ys = Xs + (size_t)MB * S + 8;
     const bool has_next = b + 1 < b1;
     if (has_next) {
-      const int it2 = it + 1, st2 = it2 % STAGES;
-      mbar_wait(&full[st2], (uint32_t)((it2 / STAGES) & 1));
+      const int it2 = it + 1, st2 = it2 % NST;
+      mbar_wait(&full[st2], (uint32_t)((it2 / NST) & 1));
       const double* Xn = sm + SD * st2;
 #pragma unroll
       for (int T = 0; T < NT; ++T) nxt[T][0] = nxt[T][1] = 0.0;
@@ -353,8 +382,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
     __syncwarp();
     if (lane == 0) {
       if (mbar_arrive_last(&empty[st])) {           // every warp is done with this stage: refill it
-        mbar_wait(&empty[st], (uint32_t)((it / STAGES) & 1));   // acquire the other warps' releases (already complete)
-        if (b + STAGES < b1) issue_load(b + STAGES);
+        mbar_wait(&empty[st], (uint32_t)((it / NST) & 1));   // acquire the other warps' releases (already complete)
+        if (b + NST < b1) issue_load(b + NST);
       }
     }
 #pragma unroll
@@ -696,7 +725,7 @@ template <int NJ, bool FULL, bool LP, bool TRIM = false> static cudaError_t laun
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL, LP, TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL, LP, TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
@@ -796,7 +825,11 @@ GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t 
   G.ntiles = (int)((C + CB - 1) / CB); G.ksplit = pick_ksplit(G.ntiles, G.nblocks, nsm);
   G.C = numchains; G.Dp = m->Dp;
   s->nj_inst = pick_nj_inst(G.nj);
-  s->smem = stage_doubles(m->S) * STAGES * 8 + 2 * STAGES * 8;
+  G.stages = STAGES;
+  auto smem_for = [&](int nst) { return stage_doubles(m->S) * nst * 8 + 2 * STAGES * 8 + (THETA_SMEM ? (size_t)CB * theta_stride(m->Dp) * 8 : 0); };
+  while (G.stages > 2 && smem_for(G.stages) > 227 * 1024) --G.stages;      // d = 128: the Theta tile leaves room for a 2-deep ring
+  s->smem = smem_for(G.stages);
+  if (s->smem > 227 * 1024) { why = "shared memory of the gradient kernel exceeds 227 KB for this dimension"; delete s; return nullptr; }
   V.key = RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)}; V.chain_begin = chain_begin; V.C = numchains; V.d = m->d; V.Dp = m->Dp;
   V.T = 1.0; V.invT = 1.0;
   V.ksplit = G.ksplit; V.prior_sigma = m->prior_sigma; V.L = numSteps; V.adapting = adapt ? 1 : 0; V.stepSize0 = stepSize; V.SC = sample_chains;

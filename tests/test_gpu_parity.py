@@ -388,6 +388,25 @@ def test_shared_and_per_lane_gaussian_fill_agree(qs, oracle):
     P.compare(gpu, cpu, TOL, what="HARM gauss10, 40 chains")
 
 
+@pytest.mark.parametrize("d,N", [(128, 700), (104, 333), (97, 257), (57, 100), (8, 40), (3, 33)])
+def test_glm_kernel_dimension_edges_against_oracle(qs, oracle, d, N):
+    """The tensor-core gradient kernel at the edges of its shapes: the largest dimension (d = 128: the Theta tile leaves room for
+    a 2-deep ring only), full and partly filled dimension tiles with and without the trimmed last tile, row counts that are
+    not a multiple of the 32-row block."""
+    rng = np.random.default_rng(d)
+    X = rng.standard_normal((N, d)) / np.sqrt(d)
+    y = (rng.random(N) < 0.5).astype(np.uint8)
+    prog = qs.programs.logistic(X, y, 2.5)
+    op = P.oracle_program(prog)
+    x = rng.normal(0, 0.5, (3, d))
+    lpd, g, lpf = prog.logp_grad(x)
+    for c in range(3):
+        lpd_o, g_o, lpf_o = op.logp_grad(x[c])
+        assert P.relerr(lpd[c], lpd_o) <= 1e-12 and P.relerr(g[c], g_o).max() <= 1e-11, (d, c)
+    gpu, cpu = P.run_both(prog, qs.HMCKernel(numSteps=3, stepSize=0.05, doStepSizeAdapt=False), chains=5, iters=4, seed=d, leap=True)
+    P.compare(gpu, cpu, TOL, leap=True, what="GLM d=%d N=%d" % (d, N))
+
+
 def test_chain_ids_are_partition_invariant(qs):
     """Philox key = global chain id: chains [32,64) run as a shard equal chains 32..63 of the full run, bit for bit
     (the multi-GPU invariance the chain sharding relies on)."""
