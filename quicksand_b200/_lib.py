@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqsb200.so")
+LIB_PATH = os.environ.get("QSB200_LIB") or os.path.join(HERE, "libqsb200.so")   # QSB200_LIB: another build of the same ABI (A/B measurements)
 
 FAM_INDEP, FAM_GAUSS_PREC, FAM_LOGISTIC, FAM_EIGHT_SCHOOLS, FAM_FUNNEL = 1, 2, 3, 4, 5
 ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4

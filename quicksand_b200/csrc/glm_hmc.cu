@@ -39,12 +39,17 @@ static constexpr int MB = 32;          // observation rows per pipeline stage
 static constexpr int NT = MB / 8;      // 8-row n-tiles per stage
 static constexpr int STAGES = 4;        // deepest ring; a sampler uses 2..4 stages (GradParams::stages), whatever fits 227 KB
 #ifndef QSB_GLM_CW
-#define QSB_GLM_CW 16
+#define QSB_GLM_CW 12
 #endif
-// warps per CTA.  12: Theta of the chain tile in registers (3 warps per SM sub-partition at 168 registers).  16: Theta in
-// shared memory (the ring leaves 124 KB unused), 4 warps per sub-partition at 128 registers.
+// warps per CTA.  12 (default): Theta of the chain tile in registers (3 warps per SM sub-partition at 168 registers).
+// 16: Theta in shared memory (the ring leaves 124 KB unused), 4 warps per sub-partition at 128 registers -- 1 % slower in
+// a same-box A/B (1.183 vs 1.171 ms per launch on c3), as are 12 warps with Theta in shared memory (1.181 ms); 10 and 14
+// warps leave sub-partitions unevenly loaded (1.41 / 1.35 ms).  Kept selectable for other shapes.
 static constexpr int CW = QSB_GLM_CW;
-static constexpr bool THETA_SMEM = CW == 16;
+#ifndef QSB_GLM_THETA_SMEM
+#define QSB_GLM_THETA_SMEM (QSB_GLM_CW == 16)
+#endif
+static constexpr bool THETA_SMEM = QSB_GLM_THETA_SMEM;
 static constexpr int CB = CW * 8;      // chains per CTA
 static constexpr int GRAD_THREADS = CW * 32;
 
