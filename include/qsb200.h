@@ -84,6 +84,16 @@ typedef struct {
   const double* erp_fmu;   /* INDEP [dim] or NULL: a Gaussian factor on the value of scalar choice i right after it,          */
   const double* erp_fsigma;/*   qs.factor(gaussian.logprob(v_i, fmu_i, fsigma_i)) == qs.gaussian.observe(v_i, fmu_i, fsigma_i)
                             *   (trace.t:1099-1107; erp.t:687-696; testsuite.t:394-442).  fsigma_i <= 0: no factor.            */
+  /* Latent ERP parameters (INDEP, all three NULL = every parameter constant).  Parameter q (0/1) of scalar choice i is
+   *   f( erp_p{q}[i] + erp_pcoef[2i+q] * value_j ),  j = erp_pref[2i+q] < i an earlier scalar choice (-1: constant),
+   *   f = identity (erp_ptf[2i+q] = 0) or exp (1)
+   * -- the parameter expressions of a program such as  mu = gaussian(0,1); x = gaussian(mu, exp(logtau)).  The reference
+   * re-evaluates them on every run and hands them to RandomChoiceT:update (trace.t:948-994, erp.t:576-610); in a dual trace the
+   * tape differentiates the log-density with respect to them, including d/dk of the 5-coefficient log-gamma (distrib.t:84-106).
+   * gaussian, gamma and beta choices only (a uniform's parameters are its bounds); thread-per-chain mapping (dim <= 32). */
+  const int32_t* erp_pref;  /* [2*dim] */
+  const double* erp_pcoef;  /* [2*dim] */
+  const int32_t* erp_ptf;   /* [2*dim] or NULL (all identity) */
 } qsb_model_desc;
 
 /* One transition kernel; nspecs > 1 means MixtureKernel(kernels, weights) (qs/mcmc.t:199-291). */

@@ -81,6 +81,7 @@ def lib(variant=None):
         L.qso_program_indep.argtypes = [C.c_int, C.POINTER(C.c_int), dp, dp, C.c_int, C.c_double]
         L.qso_program_indep_lexids.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.qso_program_indep_factors.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.qso_program_indep_latent.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), dp, C.POINTER(C.c_int)]
         L.qso_program_gauss_prec.argtypes = [C.c_int, dp]
         L.qso_program_logistic.argtypes = [C.c_int, C.c_int, dp, C.POINTER(C.c_ubyte), C.c_double]
         L.qso_program_eight_schools.argtypes = [C.c_int, dp, dp]
@@ -156,7 +157,7 @@ class Program:
             pass
 
     @staticmethod
-    def indep(kinds, p0, p1, ret_mode=0, ret_div=1.0, lexids=None, fmu=None, fsigma=None):
+    def indep(kinds, p0, p1, ret_mode=0, ret_div=1.0, lexids=None, fmu=None, fsigma=None, pref=None, pcoef=None, ptf=None):
         k = np.ascontiguousarray(kinds, dtype=np.int32)
         a = np.ascontiguousarray(p0, dtype=np.float64)
         b = np.ascontiguousarray(p1, dtype=np.float64)
@@ -167,6 +168,11 @@ class Program:
         if fsigma is not None:
             fm = np.ascontiguousarray(fmu, dtype=np.float64); fs = np.ascontiguousarray(fsigma, dtype=np.float64)
             lib().qso_program_indep_factors(C.c_void_p(h), len(fs), _dp(fm), _dp(fs))
+        if pref is not None:
+            r = np.ascontiguousarray(pref, dtype=np.int32).ravel(); cb = np.ascontiguousarray(pcoef, dtype=np.float64).ravel()
+            tf = np.ascontiguousarray(ptf if ptf is not None else np.zeros(len(r)), dtype=np.int32).ravel()
+            ip = C.POINTER(C.c_int)
+            lib().qso_program_indep_latent(C.c_void_p(h), len(k), r.ctypes.data_as(ip), _dp(cb), tf.ctypes.data_as(ip))
         return Program(h)
 
     @staticmethod

@@ -95,6 +95,10 @@ void qso_program_indep_lexids(void* prog, int K, const int* lexid) { ((IndepErps
 void qso_program_indep_factors(void* prog, int K, const double* fmu, const double* fsigma) {
   ((IndepErps*)prog)->fmu.assign(fmu, fmu + K); ((IndepErps*)prog)->fsigma.assign(fsigma, fsigma + K);
 }
+void qso_program_indep_latent(void* prog, int K, const int* ref, const double* b, const int* tf) {
+  IndepErps* p = (IndepErps*)prog;
+  p->lat_ref.assign(ref, ref + 2 * K); p->lat_b.assign(b, b + 2 * K); p->lat_tf.assign(tf, tf + 2 * K);
+}
 void* qso_program_gauss_prec(int d, const double* A) {
   GaussPrecision* p = new GaussPrecision();
   p->d = d; p->A.assign(A, A + (size_t)d * d); p->retdim = d;

@@ -27,6 +27,13 @@ struct IndepErps : Program {
   std::vector<double> p0, p1;
   std::vector<int> lexid;   // call-site id per entry (empty: every choice is its own call site)
   std::vector<double> fmu, fsigma;   // optional qs.factor(gaussian.logprob(value_i, fmu_i, fsigma_i)) after scalar choice i (fsigma <= 0: none)
+  // latent parameters: parameter q of scalar entry i is f(p_q[i] + lat_b[2i+q] * value of the earlier scalar entry
+  // lat_ref[2i+q]) with f = identity (lat_tf = 0) or exp (1); lat_ref < 0: the constant p_q[i].  Empty: all constant.
+  // This is what a program like  mu = gaussian(0,1); x = gaussian(mu, exp(logtau))  does: the parameter expression is
+  // re-evaluated on every run (trace.t:948-994 passes the current parameters to RandomChoiceT:update, erp.t:576-610), and in
+  // a dual trace the tape differentiates the log-density with respect to it.
+  std::vector<int> lat_ref, lat_tf;
+  std::vector<double> lat_b;
   int ret_mode = 0;
   double ret_div = 1.0;
   // Entries are per real component.  A dirichlet choice of K components is K consecutive entries of kind
@@ -34,6 +41,13 @@ struct IndepErps : Program {
   template <class real> void body(Trace<real>& t) {
     size_t K = kind.size();
     real sum = real(0.0);
+    std::vector<real> vals(K, real(0.0));
+    auto par = [&](int q, size_t i) -> real {
+      real a = real(q ? p1[i] : p0[i]);
+      if (lat_ref.empty() || lat_ref[2 * i + q] < 0) return a;
+      real z = a + lat_b[2 * i + q] * vals[(size_t)lat_ref[2 * i + q]];
+      return lat_tf[2 * i + q] ? tmath::exp(z) : z;
+    };
     for (size_t i = 0; i < K;) {
       t.site = lexid.empty() ? (unsigned)i : (unsigned)lexid[i];
       if (kind[i] == ERP_DIRICHLET) {
@@ -45,7 +59,8 @@ struct IndepErps : Program {
         for (auto& x : v) { if (ret_mode == 0) sum = sum + x; else t.returnValue.push_back(x); }
         i = j;
       } else {
-        real x = t.erp(kind[i], real(p0[i]), real(p1[i]));
+        real x = t.erp(kind[i], par(0, i), par(1, i));
+        vals[i] = x;
         if (!fsigma.empty() && fsigma[i] > 0.0) t.factor(D::gaussian_logprob<real>(x, real(fmu[i]), real(fsigma[i])));   // testsuite.t:394-442
         if (ret_mode == 0) sum = sum + x; else t.returnValue.push_back(x);
         ++i;

@@ -135,6 +135,8 @@ local function MCMC(kernel, params)
 			d.erp_kind = [desc.erp_kind or `nil]; d.erp_p0 = [desc.erp_p0 or `nil]; d.erp_p1 = [desc.erp_p1 or `nil]
 			d.A = [desc.A or `nil]; d.X = [desc.X or `nil]; d.ybin = [desc.ybin or `nil]
 			d.y = [desc.y or `nil]; d.sigma = [desc.sigma or `nil]; d.erp_lexid = [desc.erp_lexid or `nil]
+			d.erp_fmu = [desc.erp_fmu or `nil]; d.erp_fsigma = [desc.erp_fsigma or `nil]
+			d.erp_pref = [desc.erp_pref or `nil]; d.erp_pcoef = [desc.erp_pcoef or `nil]; d.erp_ptf = [desc.erp_ptf or `nil]
 			var model : &B.qsb_model = nil
 			check(B.qsb_model_create(&d, [_device], &model))
 

@@ -22,7 +22,8 @@ class ModelDesc(C.Structure):
     _fields_ = [("family", C.c_int32), ("dim", C.c_int32), ("nobs", C.c_int32), ("ret_mode", C.c_int32),
                 ("ret_div", C.c_double), ("prior_sigma", C.c_double),
                 ("erp_kind", ip), ("erp_p0", dp), ("erp_p1", dp), ("A", dp), ("X", dp),
-                ("ybin", C.POINTER(C.c_uint8)), ("y", dp), ("sigma", dp), ("erp_lexid", ip), ("erp_fmu", dp), ("erp_fsigma", dp)]
+                ("ybin", C.POINTER(C.c_uint8)), ("y", dp), ("sigma", dp), ("erp_lexid", ip), ("erp_fmu", dp), ("erp_fsigma", dp),
+                ("erp_pref", ip), ("erp_pcoef", dp), ("erp_ptf", ip)]
 
 
 class KernelSpec(C.Structure):

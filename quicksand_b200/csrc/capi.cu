@@ -369,6 +369,32 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
         cudaMemcpy(fs, d->erp_fsigma, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
         m->dev.fmu = fm; m->dev.fsigma = fs;
       }
+      if (d->erp_pref) {
+        if (!d->erp_pcoef) return bail(3, "INDEP: erp_pcoef is required with erp_pref");
+        if (d->dim > 32) return bail(3, "INDEP: latent parameters run in the thread-per-chain mapping (dim <= 32)");
+        std::vector<int> tf(2 * (size_t)d->dim, 0);
+        bool any = false;
+        for (int i = 0; i < d->dim; ++i)
+          for (int q = 0; q < 2; ++q) {
+            const int r = d->erp_pref[2 * i + q];
+            if (d->erp_ptf) tf[2 * i + q] = d->erp_ptf[2 * i + q] ? 1 : 0;
+            if (r < 0) continue;
+            any = true;
+            if (r >= i) return bail(3, "INDEP: a latent parameter must refer to an earlier choice");
+            if (d->erp_kind[r] == QSB_ERP_DIRICHLET) return bail(3, "INDEP: a latent parameter must refer to a scalar choice");
+            if (d->erp_kind[i] == QSB_ERP_UNIFORM || d->erp_kind[i] == QSB_ERP_DIRICHLET)
+              return bail(3, "INDEP: latent parameters are supported on gaussian, gamma and beta choices");
+          }
+        if (any) {
+          int *lr, *lt; double* lb;
+          if (m->arena.alloc(&lr, 2 * (size_t)d->dim) || m->arena.alloc(&lt, 2 * (size_t)d->dim) || m->arena.alloc(&lb, 2 * (size_t)d->dim)) return bail(4, "cudaMalloc failed");
+          cudaMemcpy(lr, d->erp_pref, sizeof(int) * 2 * d->dim, cudaMemcpyHostToDevice);
+          cudaMemcpy(lt, tf.data(), sizeof(int) * 2 * d->dim, cudaMemcpyHostToDevice);
+          cudaMemcpy(lb, d->erp_pcoef, sizeof(double) * 2 * d->dim, cudaMemcpyHostToDevice);
+          m->dev.lat_ref = lr; m->dev.lat_tf = lt; m->dev.lat_b = lb;
+          m->dev.has_vector = 1;   // same consequence as a vector choice: thread-per-chain mapping only
+        }
+      }
       if (d->ret_mode == 0) m->retdim = 1;
       break;
     }
@@ -551,8 +577,8 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   P.lag = 1;
   std::string why;
   s->var = pick_variant(m->desc.family, P.d, m->dev.has_vector ? 1 : cfg->reserved, why);
-  if (!s->var) return bail(2, m->dev.has_vector ? "dirichlet choices run in the thread-per-chain mapping only (" + why + ")" : why);
-  if (m->dev.has_vector && cfg->reserved != 0 && cfg->reserved != 1) return bail(2, "dirichlet choices run in the thread-per-chain mapping only");
+  if (!s->var) return bail(2, m->dev.has_vector ? "dirichlet choices and latent parameters run in the thread-per-chain mapping only (" + why + ")" : why);
+  if (m->dev.has_vector && cfg->reserved != 0 && cfg->reserved != 1) return bail(2, "dirichlet choices and latent parameters run in the thread-per-chain mapping only");
   if (m->desc.family == QSB_FAM_GAUSS_PREC) {
     const int d = P.d, npl = s->var->npl;
     for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) P.Sc[i * npl + j] = m->A[(size_t)i * d + j] + m->A[(size_t)j * d + i];

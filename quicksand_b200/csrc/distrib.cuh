@@ -41,6 +41,16 @@ QSB_D double log_gamma5(double xx) {
   return -tmp + log(2.5066282746310005 * ser);
 }
 
+// d/dz of log_gamma5 as the reference's tape differentiates it (not the true digamma: they differ by ~2.6e-8 on [1,2])
+QSB_D double digamma5(double xx) {
+  const double cof[5] = {76.18009172947146, -86.50532032941677, 24.01409824083091, -1.231739572450155, 0.1208650973866179e-2};
+  const double t = (xx - 1.0) + 5.5;
+  double ser = 1.000000000190015, dser = 0.0, x = xx - 1.0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { x = x + 1.0; ser = ser + cof[j] / x; dser = dser - cof[j] / (x * x); }
+  return log(t) + ((xx - 1.0) + 0.5) / t - 1.0 + dser / ser;
+}
+
 // ---- gamma (distrib.t:130-133)
 QSB_D double gamma_lp(double x, double shape, double scale) {
   if (x <= 0.0) return -QSB_INF;
@@ -157,6 +167,29 @@ QSB_D double erp_prior_lp(int kind, double y, double p0, double p1, double* dlpd
     case ERP_BETA: if (dlpdy) *dlpdy = beta_dlp_dx(y, p0, p1); return beta_lp(y, p0, p1);
     case ERP_UNIFORM: if (dlpdy) *dlpdy = 0.0; return uniform_lp(y, p0, p1);
     default: if (dlpdy) *dlpdy = gaussian_dlp_dx(y, p0, p1); return gaussian_lp(y, p0, p1);
+  }
+}
+
+// d(prior logprob)/d(parameters) of a scalar ERP at value y: what the tape accumulates into the parameter expressions of
+// a choice whose parameters depend on earlier choices
+QSB_D void erp_dlp_dparams(int kind, double y, double p0, double p1, double& d0, double& d1) {
+  switch (kind) {
+    case ERP_GAMMA:    // (k-1) ln y - y/theta - lg5(k) - k ln theta
+      d0 = log(y) - digamma5(p0) - log(p1);
+      d1 = y / (p1 * p1) - p0 / p1;
+      break;
+    case ERP_BETA: {   // (a-1) ln y + (b-1) ln(1-y) - lg5(a) - lg5(b) + lg5(a+b)
+      const double dab = digamma5(p0 + p1);
+      d0 = log(y) - digamma5(p0) + dab;
+      d1 = log(1.0 - y) - digamma5(p1) + dab;
+      break;
+    }
+    case ERP_UNIFORM: d0 = 1.0 / (p1 - p0); d1 = -1.0 / (p1 - p0); break;
+    default: {         // -.5 (c + 2 ln sigma + (y-mu)^2 / sigma^2)
+      const double r = y - p0, s2 = p1 * p1;
+      d0 = r / s2;
+      d1 = -1.0 / p1 + r * r / (s2 * p1);
+    }
   }
 }
 

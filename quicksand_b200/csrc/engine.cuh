@@ -42,6 +42,9 @@ struct ModelDev {
   // and the ERP index of every component (= the Philox slot of its forward sample; equals the component index without vector choices)
   const int* erp_len; const double* erp_asum; const int* erp_slot;
   int has_vector;
+  // INDEP, latent parameters (thread-per-chain mapping only): parameter q of choice i = f(p_q[i] + lat_b[2i+q] * value of
+  // choice lat_ref[2i+q]) with f = identity / exp (lat_tf); lat_ref < 0: constant; lat_ref == nullptr: none in the program
+  const int* lat_ref; const double* lat_b; const int* lat_tf;
   // DriftKernel{lexicalScaleSharing} (drift.t:101-115, 208-235): scale adapter of every component.  INDEP: lex_map;
   // GAUSS_PREC: one; EIGHT_SCHOOLS: mu, logtau, theta-loop; FUNNEL: v, x-loop
   const int* lex_map; int n_adapters;
@@ -127,9 +130,59 @@ static __device__ __noinline__ void erp_eval(int kind, double x, double p0, doub
   lj = erp_logjac(kind, x, p0, p1, &dlj);
   g = dlpdy * dydx + dlj;
 }
+// Parameter q of choice i of a program with latent parameters, given the value yj of the choice it depends on.
+static __device__ __noinline__ void latent_param(const ModelDev& m, int i, int q, double yj, double& p, double& dpdy) {
+  const double b = m.lat_b[2 * i + q];
+  const double a = (q ? m.p1[i] : m.p0[i]) + b * yj;
+  if (m.lat_tf[2 * i + q]) { p = exp(a); dpdy = b * p; } else { p = a; dpdy = b; }
+}
 static __device__ __noinline__ double erp_fwd_noinline(int kind, double x, double p0, double p1) { return erp_fwd(kind, x, p0, p1, nullptr); }
 static __device__ __noinline__ double dirichlet_component_noinline(SimplexCarry& c, int k, int K, double x, double alpha, double asum_after, double& g) {
   return dirichlet_component(c, k, K, x, alpha, asum_after, &g);
+}
+
+// INDEP program with latent parameters, one thread per chain, rolled loops over local arrays (not a throughput path).
+// Forward in program order: value, resolved parameters, log-density terms and the adjoint each term sends to the values
+// its parameters were computed from; then g_i = (dlp_i/dy_i + adjoint_i) dy_i/dx_i + dlogJ_i/dx_i  -- the reverse sweep of
+// the reference's tape (ad.t) over  sum_i [lp_i(y_i; p(y_parents)) + logJ_i(x_i)]  (erp.t:623-640).
+static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const double* x, double* g, double* lp_float, bool grad) {
+  const int d = m.dim;
+  double yv[32], yb[32], A[32], B[32];
+  double lpd = 0.0, lpf = 0.0;
+  SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
+  for (int i = 0; i < d; ++i) { yb[i] = 0.0; yv[i] = 0.0; }
+  for (int i = 0; i < d; ++i) {
+    const int kind = m.erp_kind[i];
+    if (kind == ERP_DIRICHLET) {
+      double gi;
+      const int k = (int)m.p1[i], K = m.erp_len[i];
+      dirichlet_component_noinline(sc, k, K, x[i], m.p0[i], m.erp_asum[i], gi);
+      if (k == K - 1) { lpf += sc.lp; lpd += sc.lp + sc.lj; }
+      A[i] = 0.0; B[i] = 0.0; g[i] = gi;
+      continue;
+    }
+    double p0 = m.p0[i], p1 = m.p1[i], dp0 = 0.0, dp1 = 0.0;
+    const int r0 = m.lat_ref[2 * i], r1 = m.lat_ref[2 * i + 1];
+    if (r0 >= 0) latent_param(m, i, 0, yv[r0], p0, dp0);
+    if (r1 >= 0) latent_param(m, i, 1, yv[r1], p1, dp1);
+    double dydx, dlpdy, dlj;
+    const double y = erp_fwd(kind, x[i], p0, p1, &dydx);
+    yv[i] = y;
+    double lpy = erp_prior_lp(kind, y, p0, p1, &dlpdy);
+    if (grad && (r0 >= 0 || r1 >= 0)) {
+      double d0, d1;
+      erp_dlp_dparams(kind, y, p0, p1, d0, d1);
+      if (r0 >= 0) yb[r0] += d0 * dp0;
+      if (r1 >= 0) yb[r1] += d1 * dp1;
+    }
+    if (m.fsigma && m.fsigma[i] > 0.0) { lpy = lpy + gaussian_lp(y, m.fmu[i], m.fsigma[i]); dlpdy = dlpdy + gaussian_dlp_dx(y, m.fmu[i], m.fsigma[i]); }
+    const double lj = erp_logjac(kind, x[i], p0, p1, &dlj);
+    lpf += lpy; lpd += lpy + lj;
+    A[i] = dlpdy; B[i] = dydx; g[i] = dlj;
+  }
+  if (grad) for (int i = 0; i < d; ++i) g[i] = (A[i] + yb[i]) * B[i] + g[i];
+  *lp_float = lpf;
+  return lpd;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -144,6 +197,13 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
   const ModelDev& m = P.m;
   const int d = m.dim;
   if (FAM == FAM_INDEP) {
+    if (G == 1 && NPL <= 32 && m.lat_ref) {   // latent parameters: the general (slow) evaluator on local copies
+      double xl[NPL], gl[NPL];
+      QSB_FOR_E { xl[e] = x[e]; gl[e] = 0.0; }
+      const double lpd = indep_latent_eval(m, xl, gl, &lp_float, GRAD);
+      if (GRAD) { QSB_FOR_E g[e] = e < d ? gl[e] : 0.0; }
+      return lpd;
+    }
     double lpd = 0.0, lpf = 0.0;
     SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
     QSB_FOR_E {
@@ -1054,8 +1114,20 @@ template <int FAM, int G, int NPL> struct Chain {
   // Every lane of a chain's group computes the (chain-uniform) proposal itself.
   __device__ __forceinline__ void choice_params(int j, const double (&x)[NPL], int& kind, double& p0, double& p1) const {
     kind = ERP_GAUSSIAN; p0 = 0.0; p1 = 1.0;
-    if (FAM == FAM_INDEP) { kind = P.m.erp_kind[j]; p0 = P.m.p0[j]; p1 = P.m.p1[j]; }
-    else if (FAM == FAM_EIGHT_SCHOOLS) {
+    if (FAM == FAM_INDEP) {
+      kind = P.m.erp_kind[j]; p0 = P.m.p0[j]; p1 = P.m.p1[j];
+      if (G == 1 && P.m.lat_ref) {   // current parameters from the current values of the choices they depend on
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+          const int r = P.m.lat_ref[2 * j + q];
+          if (r >= 0) {
+            const double yr = erp_fwd_noinline(P.m.erp_kind[r], component(x, r), P.m.p0[r], P.m.p1[r]);
+            double dp;
+            latent_param(P.m, j, q, yr, q ? p1 : p0, dp);
+          }
+        }
+      }
+    } else if (FAM == FAM_EIGHT_SCHOOLS) {
       if (j == 0) p1 = 5.0;
       else if (j >= 2) { p0 = Grp<G>::bcast(x[0], 0); p1 = exp(G == 1 ? x[NPL > 1 ? 1 : 0] : Grp<G>::bcast(x[0], 1)); }
     } else if (FAM == FAM_FUNNEL) {
@@ -1500,12 +1572,19 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_c
   double lp0 = 0.0;
   if (FAM == FAM_INDEP) {
     double lp = 0.0;
+    double yv[G == 1 ? NPL : 1];   // sampled values (programs with latent parameters: later choices read them)
     QSB_FOR_E x[e] = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
       if (i < d) {
         int kind = P.m.erp_kind[i];
         double p0 = P.m.p0[i], p1 = P.m.p1[i];
+        if (G == 1 && P.m.lat_ref) {
+          double dp;
+          const int r0 = P.m.lat_ref[2 * i], r1 = P.m.lat_ref[2 * i + 1];
+          if (r0 >= 0) latent_param(P.m, i, 0, yv[r0 < NPL ? r0 : 0], p0, dp);
+          if (r1 >= 0) latent_param(P.m, i, 1, yv[r1 < NPL ? r1 : 0], p1, dp);
+        }
         const uint32_t slot = P.m.erp_slot ? (uint32_t)P.m.erp_slot[i] : (uint32_t)i;   // ERP index (trace.t:948-994 creates choices in program order)
         if (G == 1 && kind == ERP_DIRICHLET) {
           if ((int)p1 == 0) {
@@ -1533,6 +1612,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_c
           lp += erp_prior_lp(kind, y, p0, p1, nullptr);   // float trace: logprob of the sampled value itself
           if (P.m.fsigma && P.m.fsigma[i] > 0.0) lp += gaussian_lp(y, P.m.fmu[i], P.m.fsigma[i]);   // and the factor that follows it
           x[e] = erp_inv(kind, y, p0, p1);
+          if (G == 1) yv[e] = y;
         }
       }
     }

@@ -46,6 +46,8 @@ class Program:
             d.erp_lexid = a["erp_lexid"].ctypes.data_as(L.ip)
         if "erp_fsigma" in a:
             d.erp_fmu = _dp(a["erp_fmu"]); d.erp_fsigma = _dp(a["erp_fsigma"])
+        if "erp_pref" in a:
+            d.erp_pref = a["erp_pref"].ctypes.data_as(L.ip); d.erp_pcoef = _dp(a["erp_pcoef"]); d.erp_ptf = a["erp_ptf"].ctypes.data_as(L.ip)
         return d
 
     def model(self, device=-1):
@@ -92,8 +94,17 @@ class Program:
 _KIND = {"gaussian": L.ERP_GAUSSIAN, "gamma": L.ERP_GAMMA, "beta": L.ERP_BETA, "uniform": L.ERP_UNIFORM}
 
 
+class latent:
+    """A parameter of an ``indep`` entry that depends on the value of an earlier scalar entry: ``f(a + b * value[entry])``
+    with f = identity or exp -- e.g. ``[("gaussian", 0, 1), ("gaussian", latent(0), 1.0)]`` for
+    ``mu = qs.gaussian(0,1); x = qs.gaussian(mu, 1)`` and ``latent(1, b=0.5, exp=True)`` for ``exp(v/2)``."""
+
+    def __init__(self, entry, a=0.0, b=1.0, exp=False):
+        self.entry, self.a, self.b, self.exp = int(entry), float(a), float(b), bool(exp)
+
+
 def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
-    """Independent ERPs with constant parameters, e.g. ``[("gamma", 2.0, 2.0)]`` with ret_div=10 for
+    """ERPs in program order with constant parameters (or ``latent`` ones, see above), e.g. ``[("gamma", 2.0, 2.0)]`` with ret_div=10 for
     ``return qs.gamma(2.0, 2.0, {struc=false})/10.0`` (test/testsuite.t:657-673).  Entries:
 
       ("gaussian", mu, sigma) ("gamma", shape, scale) ("beta", a, b) ("uniform", lo, hi)     erpdefs.t:28-36, 46-69, 92-100
@@ -107,8 +118,10 @@ def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
     ``lexids[i]``: call-site id of entry i (entries produced by one ERP call inside a loop share an id); only
     DriftKernel{lexicalScaleSharing=true} looks at it (drift.t:208-235).  Default: every entry is its own call site."""
     kinds, p0, p1, lex, fmu, fsig = [], [], [], [], [], []
+    pref, pcoef, ptf, comp_of_entry = [], [], [], []
     for n_e, e in enumerate(erps):
         k = e[0]
+        comp_of_entry.append(len(kinds))
         site = n_e if lexids is None else int(lexids[n_e])
         fac = None if factors is None else factors[n_e]
         if k == "dirichlet":
@@ -116,10 +129,18 @@ def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
             alphas = [float(a) for a in e[1]]
             for j, a in enumerate(alphas):
                 kinds.append(L.ERP_DIRICHLET); p0.append(a); p1.append(float(j)); lex.append(site); fmu.append(0.0); fsig.append(0.0)
+                pref += [-1, -1]; pcoef += [0.0, 0.0]; ptf += [0, 0]
             continue
         lex.append(site)
         fmu.append(0.0 if fac is None else float(fac[0])); fsig.append(0.0 if fac is None else float(fac[1]))
-        a, b = float(e[1]), float(e[2])
+        for q in (1, 2):
+            if isinstance(e[q], latent):
+                assert k in ("gaussian", "gamma", "beta"), "latent parameters: gaussian, gamma and beta choices"
+                assert 0 <= e[q].entry < n_e and erps[e[q].entry][0] != "dirichlet", "a latent parameter refers to an earlier scalar entry"
+                pref.append(comp_of_entry[e[q].entry]); pcoef.append(e[q].b); ptf.append(1 if e[q].exp else 0)
+            else:
+                pref.append(-1); pcoef.append(0.0); ptf.append(0)
+        a, b = (x.a if isinstance(x, latent) else float(x) for x in (e[1], e[2]))
         if k == "gammamv":
             k, a, b = "gamma", a * a / b, b / a
         elif k == "betamv":
@@ -130,6 +151,8 @@ def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
     extra = {} if lexids is None else {"erp_lexid": np.array(lex, dtype=np.int32)}
     if factors is not None:
         extra.update(erp_fmu=np.array(fmu, dtype=np.float64), erp_fsigma=np.array(fsig, dtype=np.float64))
+    if any(r >= 0 for r in pref):
+        extra.update(erp_pref=np.array(pref, dtype=np.int32), erp_pcoef=np.array(pcoef, dtype=np.float64), erp_ptf=np.array(ptf, dtype=np.int32))
     return Program(L.FAM_INDEP, len(kinds), erp_kind=np.array(kinds, dtype=np.int32), erp_p0=np.array(p0, dtype=np.float64),
                    erp_p1=np.array(p1, dtype=np.float64), ret_mode=0 if ret == "sum" else 1, ret_div=float(ret_div), **extra)
 

@@ -71,6 +71,17 @@ def _programs(qs):
     progs["gauss10loop"] = qs.programs.indep([("gaussian", 0.1, 0.5)] * 10, ret_div=10.0, lexids=[0] * 10)
     progs["sites9"] = qs.programs.indep([("gaussian", 0.1, 0.5), ("dirichlet", [2.0, 3.0, 5.0]), ("gaussian", 1.0, 2.0),
                                           ("dirichlet", [0.7, 1.5, 1.0]), ("gaussian", -1.0, 0.3)], ret="vector", lexids=[0, 1, 0, 1, 2])
+    # latent parameters: parameters of a choice computed from earlier choices (hierarchical programs written with plain ERPs)
+    lat = qs.programs.latent
+    progs["hier4"] = qs.programs.indep([("gaussian", 1.0, 0.5), ("gaussian", 0.0, 0.5), ("gaussian", lat(0), lat(1, b=0.5, exp=True)),
+                                         ("gaussian", lat(2, a=0.5, b=2.0), 1.0)], ret="vector")
+    progs["hier12"] = qs.programs.indep([("gaussian", 1.0, 0.5), ("gaussian", 0.0, 0.5), ("gaussian", lat(0), lat(1, b=0.5, exp=True)),
+                                          ("gaussian", lat(2, a=0.5, b=2.0), 1.0), ("gamma", 3.0, 1.0), ("gamma", 2.0, 0.5), ("gamma", lat(4), lat(5)),
+                                          ("gamma", 2.5, 1.0), ("gaussian", 0.7, 0.3), ("beta", lat(7), lat(8, exp=True)), ("uniform", -1.0, 1.0),
+                                          ("gaussian", lat(10, b=3.0), lat(6, a=0.2))], ret="vector",
+                                         factors=[None] * 9 + [(0.4, 0.2), None, (0.5, 1.0)])
+    progs["hierdir9"] = qs.programs.indep([("gamma", 3.0, 1.0), ("dirichlet", [2.0, 3.0, 5.0]), ("gamma", lat(0), 2.0), ("gaussian", 0.0, 1.0),
+                                            ("dirichlet", [0.7, 1.5, 1.0]), ("gaussian", lat(3), lat(2, a=0.1))], ret="vector")
     progs["c2"] = qs.programs.c2_correlated_gaussian()[0]
     J = 11
     progs["schools13"] = qs.programs.eight_schools(rng.normal(4, 10, J), rng.uniform(8, 18, J))
@@ -84,7 +95,7 @@ def _programs(qs):
     return progs
 
 
-@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "dirichlet4", "dirmix9", "wide24", "factor1", "factor6", "c2",
+@pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "dirichlet4", "dirmix9", "wide24", "factor1", "factor6", "hier4", "hier12", "hierdir9", "c2",
                                   "schools13", "schools62", "funnel12", "funnel70", "logistic20"])
 def test_logp_and_gradient_match_tape_ad(qs, oracle, name):
     """Closed-form device gradients vs the oracle's tape AD (qs/lib/ad.t) on random unconstrained points."""
@@ -110,6 +121,7 @@ HMC_FIXED = [
     ("wide24", dict(numSteps=5, stepSize=0.05), 0, 1.0),
     ("factor1", dict(numSteps=10, stepSize=0.05), 0, 1.0), ("factor6", dict(numSteps=5, stepSize=0.05), 0, 1.0), ("factor6", dict(numSteps=5, stepSize=0.05), 32, 1.0),
     ("mixed10", dict(numSteps=5, stepSize=0.1), 32, 1.0),
+    ("hier4", dict(numSteps=10, stepSize=0.05), 0, 1.0), ("hier12", dict(numSteps=5, stepSize=0.02), 0, 0.9), ("hierdir9", dict(numSteps=5, stepSize=0.03), 0, 0.9),
     ("c2", dict(numSteps=16, stepSize=0.15), 0, 1.0),
     ("schools13", dict(numSteps=8, stepSize=0.02), 1, 0.95), ("schools13", dict(numSteps=8, stepSize=0.02), 32, 0.95),
     ("schools62", dict(numSteps=8, stepSize=0.02), 0, 0.95),
@@ -144,7 +156,7 @@ HMC_ADAPT = [
     ("gaussian1", 1, 0, 0.9), ("gaussian1", 10, 0, 0.5), ("gamma1", 10, 0, 0.5), ("beta1", 1, 0, 0.9), ("uniform1", 10, 0, 0.8),
     ("gauss10", 10, 0, 0.4), ("mixed10", 5, 32, 0.8), ("c2", 16, 0, 0.4), ("dirichlet4", 10, 0, 0.4), ("dirmix9", 1, 0, 0.8),
     ("schools13", 1, 32, 0.9), ("schools13", 2, 1, 0.8), ("schools62", 1, 0, 0.9), ("funnel12", 1, 1, 0.9), ("funnel12", 2, 32, 0.8),
-    ("funnel70", 1, 0, 0.9), ("logistic20", 1, 0, 0.9), ("logistic20", 2, 0, 0.05),
+    ("funnel70", 1, 0, 0.9), ("logistic20", 1, 0, 0.9), ("logistic20", 2, 0, 0.05), ("hier4", 1, 0, 0.8), ("hier12", 2, 0, 0.3),
     ("schools13", 8, 32, 0.05), ("funnel12", 16, 1, 0.03), ("logistic20", 20, 0, 0.01),
 ]
 
@@ -165,14 +177,15 @@ def test_hmc_adaptive_search_and_dual_averaging(qs, oracle, name, L, mapping, mi
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0), ("logistic20", 0), ("factor6", 0), ("factor6", 32)])
+                                          ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0), ("logistic20", 0), ("factor6", 0), ("factor6", 32),
+                                          ("hier4", 0), ("hier12", 0), ("hierdir9", 0)])
 def test_drift_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=64, iters=400, seed=99, mapping=mapping)
     P.compare(gpu, cpu, TOL, what="Drift %s map%d" % (name, mapping))
 
 
-LEXICAL = [("gauss10loop", 1), ("gauss10loop", 32), ("gauss10", 0), ("sites9", 0), ("c2", 0), ("schools13", 1), ("schools13", 32),
+LEXICAL = [("gauss10loop", 1), ("gauss10loop", 32), ("gauss10", 0), ("sites9", 0), ("hier12", 0), ("c2", 0), ("schools13", 1), ("schools13", 32),
            ("schools62", 0), ("funnel12", 1), ("funnel12", 32), ("funnel70", 0)]
 
 
@@ -191,7 +204,7 @@ def test_drift_lexical_scale_sharing_parity(qs, oracle, name, mapping):
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("gaussian1", 0), ("c2", 0), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0), ("dirichlet4", 0), ("logistic20", 0)])
+                                          ("funnel12", 1), ("funnel70", 0), ("dirichlet4", 0), ("logistic20", 0), ("hier4", 0), ("hier12", 0)])
 def test_harm_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.HARMKernel(), chains=64, iters=300, seed=5, mapping=mapping)
@@ -199,7 +212,7 @@ def test_harm_per_step_parity(qs, oracle, name, mapping):
     assert P.relerr(gpu["step"], cpu["step"]).max() <= 1e-9
 
 
-TRACEMH = [("factor1", 0), ("factor6", 0), ("factor6", 32), ("gaussian1", 0), ("gamma1", 0), ("beta1", 0), ("uniform1", 0), ("gauss10", 0), ("mixed10", 0), ("mixed10", 32), ("dirichlet4", 0),
+TRACEMH = [("hier4", 0), ("hier12", 0), ("hierdir9", 0), ("factor1", 0), ("factor6", 0), ("factor6", 32), ("gaussian1", 0), ("gamma1", 0), ("beta1", 0), ("uniform1", 0), ("gauss10", 0), ("mixed10", 0), ("mixed10", 32), ("dirichlet4", 0),
            ("dirmix9", 0), ("wide24", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0), ("funnel12", 1), ("funnel12", 32),
            ("funnel70", 0)]
 
@@ -662,3 +675,35 @@ def test_cxx_mirror_runs_the_reference_test(qs, tmp_path):
                     "-o", str(exe), "-L", libdir, "-lqsb200", "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("kind", ["hmc", "tracemh"])
+def test_latent_parameter_truths_on_device(qs, kind):
+    """Hierarchical programs written with plain ERPs whose parameters are earlier choices:
+    mu ~ gaussian(1, 0.5); x ~ gaussian(0.5 + 2 mu, 1) -> E[x] = 2.5, Var[x] = 1 + 4 * 0.25 = 2;
+    k ~ gamma(3, 1); y ~ gamma(k, 2) -> E[y] = 6 (latent shape: the gradient runs through the 5-coefficient log-gamma)."""
+    lat = qs.programs.latent
+    k = qs.HMCKernel(numSteps=10) if kind == "hmc" else qs.TraceMHKernel(doStruct=False)
+    g = qs.programs.indep([("gaussian", 1.0, 0.5), ("gaussian", lat(0, a=0.5, b=2.0), 1.0)], ret="vector")
+    d, vals = _pooled_moments(qs, g, k, chains=2048, nsamps=150, burnin=300, lag=2)
+    assert abs(d["mean"][1] - 2.5) < 0.07 and abs(d["mean"][0] - 1.0) < 0.07, d["mean"]
+    assert abs(d["var"][1] - 2.0) < 0.2, d["var"]
+    y = qs.programs.indep([("gamma", 3.0, 1.0), ("gamma", lat(0), 2.0)], ret="vector")
+    d, vals = _pooled_moments(qs, y, k, chains=2048, nsamps=150, burnin=300, lag=2)
+    assert abs(d["mean"][0] - 3.0) < 0.15 and abs(d["mean"][1] - 6.0) < 0.35, d["mean"]
+
+
+def test_latent_parameter_descriptor_errors(qs):
+    from quicksand_b200 import _lib as L
+    lat = qs.programs.latent
+    p = qs.programs.indep([("gaussian", 0.0, 1.0), ("gaussian", lat(0), 1.0)], ret="vector")
+    p.arrays["erp_pref"][0] = 1                       # choice 0 depending on the later choice 1
+    with pytest.raises(L.QsbError):
+        p.model()
+    p = qs.programs.indep([("gaussian", 0.0, 1.0), ("gaussian", lat(0), 1.0)], ret="vector")
+    p.arrays["erp_kind"][1] = L.ERP_UNIFORM          # a uniform's parameters are its bounds: not supported as latent
+    with pytest.raises(L.QsbError):
+        p.model()
+    p = qs.programs.indep([("gaussian", 0.0, 1.0)] + [("gaussian", lat(0), 1.0)] * 40, ret="vector")   # 41 components: no thread-per-chain variant
+    with pytest.raises(L.QsbError):
+        qs.Sampler(p, qs.HMCKernel(), numchains=4)

@@ -139,3 +139,72 @@ def test_factor_and_observe_expectation(oracle, kind):
     prog = oracle.Program.indep([3], [-1.0], [1.0], 0, 1.0, fmu=[0.3], fsigma=[0.1])
     spec = oracle.spec(oracle.TRACEMH) if kind == "tracemh" else oracle.spec(oracle.HMC, numSteps=10)
     assert _expected_value(oracle, prog, spec, 0.3) <= 0.07
+
+
+# ---- latent ERP parameters: parameters of a choice computed from earlier choices, differentiated by the tape
+def _hier10(oracle):
+    """mu, logs ~ gaussian; x ~ gaussian(mu, exp(logs/2)); z ~ gaussian(0.5 + 2x, 1); k, th ~ gamma; y ~ gamma(k, th);
+    a ~ gamma; lb ~ gaussian; w ~ beta(a, exp(lb))."""
+    kinds = [0, 0, 0, 0, 1, 1, 1, 1, 0, 2]
+    p0 = [1.0, 0.0, 0.0, 0.5, 3.0, 2.0, 0.0, 2.5, 0.7, 0.0]
+    p1 = [0.5, 0.5, 0.0, 1.0, 1.0, 0.5, 0.0, 1.0, 0.3, 0.0]
+    pref = [-1, -1, -1, -1, 0, 1, 2, -1, -1, -1, -1, -1, 4, 5, -1, -1, -1, -1, 7, 8]
+    pcoef = [0, 0, 0, 0, 1.0, 0.5, 2.0, 0, 0, 0, 0, 0, 1.0, 1.0, 0, 0, 0, 0, 1.0, 1.0]
+    ptf = [0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]
+    return oracle.Program.indep(kinds, p0, p1, 1, 1.0, pref=pref, pcoef=pcoef, ptf=ptf)
+
+
+def test_latent_parameter_gradient_matches_finite_differences(oracle):
+    prog = _hier10(oracle)
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        x = rng.normal(0, 0.7, 10)
+        _, g, _ = prog.logp_grad(x)
+        h = 1e-6
+        gn = np.array([(prog.logp_grad(x + h * np.eye(10)[i])[0] - prog.logp_grad(x - h * np.eye(10)[i])[0]) / (2 * h) for i in range(10)])
+        assert np.abs(g - gn).max() <= 1e-7 * max(1.0, np.abs(g).max())
+
+
+def _lg5_digamma(z):
+    """d/dz of the reference's 5-coefficient log-gamma (distrib.t:84-106), SURVEY Appendix A."""
+    cof = [76.18009172947146, -86.50532032941677, 24.01409824083091, -1.231739572450155, 0.1208650973866179e-2]
+    t = z + 4.5
+    ser = 1.000000000190015 + sum(c / (z + j) for j, c in enumerate(cof))
+    dser = -sum(c / (z + j) ** 2 for j, c in enumerate(cof))
+    return np.log(t) + (z - 0.5) / t - 1.0 + dser / ser
+
+
+def test_latent_shape_gradient_is_the_derivative_of_the_5_coefficient_log_gamma(oracle):
+    """k ~ gamma(3, 1); y ~ gamma(k, 2): d/dx0 of the dual-trace log-density with k = exp(x0) is
+    [ (3-1)/k - 1 + ln y - psi5(k) - ln 2 ] k + 1, psi5 the derivative of the reference's own log-gamma -- not the true
+    digamma, which differs from it by ~1e-8 (a 1e-10 parity gate sees that)."""
+    from scipy.special import digamma
+    prog = oracle.Program.indep([1, 1], [3.0, 0.0], [1.0, 2.0], 1, 1.0, pref=[-1, -1, 0, -1], pcoef=[0, 0, 1.0, 0], ptf=[0, 0, 0, 0])
+    worst_true = 0.0
+    for x0, x1 in [(0.3, 0.2), (-0.5, 1.0), (1.1, -0.4)]:
+        _, g, _ = prog.logp_grad(np.array([x0, x1]))
+        k, y = np.exp(x0), np.exp(x1)
+        want = (2.0 / k - 1.0 + np.log(y) - _lg5_digamma(k) - np.log(2.0)) * k + 1.0
+        assert abs(g[0] - want) <= 1e-12 * max(1.0, abs(want)), (g[0], want)
+        worst_true = max(worst_true, abs(g[0] - ((2.0 / k - 1.0 + np.log(y) - digamma(k) - np.log(2.0)) * k + 1.0)))
+    assert worst_true > 1e-10
+
+
+@pytest.mark.parametrize("kind", ["hmc", "drift", "tracemh"])
+def test_latent_parameter_expectations(oracle, kind):
+    """mu ~ gaussian(1, 0.5); x ~ gaussian(0.5 + 2 mu, 1): E[x] = 2.5.   k ~ gamma(3, 1); y ~ gamma(k, 2)/10: E = 0.6."""
+    spec = {"hmc": oracle.spec(oracle.HMC, numSteps=10), "drift": oracle.spec(oracle.DRIFT), "tracemh": oracle.spec(oracle.TRACEMH)}[kind]
+    g = oracle.Program.indep([0, 0], [1.0, 0.5], [0.5, 1.0], 1, 1.0, pref=[-1, -1, 0, -1], pcoef=[0, 0, 2.0, 0], ptf=[0, 0, 0, 0])
+    errs = []
+    for r in range(5):
+        out = oracle.run(g, spec, 300 + r, 1, 150, 0, 20)
+        errs.append(abs(out["samples"][0][:, 1].mean() - 2.5))
+    assert np.mean(errs) <= 0.2, errs
+    if kind == "drift":   # Drift scores bounded choices without the log-Jacobian (SURVEY Q2): biased on a gamma by design of the reference
+        return
+    y = oracle.Program.indep([1, 1], [3.0, 0.0], [1.0, 2.0], 1, 1.0, pref=[-1, -1, 0, -1], pcoef=[0, 0, 1.0, 0], ptf=[0, 0, 0, 0])
+    errs = []
+    for r in range(5):
+        out = oracle.run(y, spec, 400 + r, 1, 150, 0, 20)
+        errs.append(abs(out["samples"][0][:, 1].mean() / 10.0 - 0.6))
+    assert np.mean(errs) <= 0.12, errs
