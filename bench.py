@@ -155,6 +155,12 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        # a timed region shorter than nvidia-smi's start-up (c2: 3 ms) leaves no sample: take the first one right after it
+        late = False
+        t_end = time.time() + 2.0
+        while os.path.getsize(self.f.name) == 0 and time.time() < t_end:
+            late = True
+            time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -180,6 +186,8 @@ class ClockSampler:
             pass
         if sm:
             out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            if late:
+                out["when"] = "first sample after the timed region (region shorter than the sampler's start-up)"
         return out
 
 
@@ -334,8 +342,8 @@ def main():
             cpu["min_ess_note"] = "CPU chain-transitions/s x min-ESS per chain-transition of the GPU draws (same algorithm and stream)"
         per_launch_units = units_local / max(klaunch, 1)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default chain counts, from the
-        # ncu --set full captures summarised in profiles/r01h_*_ncu_metrics.csv
-        traffic = {"c3": (8192, 42.2e6), "c2": (65536, 14.6e6), "c4": (131072, 5.46e9), "c5": (32768, 0.533e9)}[wl["name"]]   # (chains per GPU, bytes)
+        # ncu --set full captures summarised in profiles/r01j_c3_grad_ncu_metrics.csv and profiles/r01i_c{2,4,5}_adv_ncu_metrics.csv
+        traffic = {"c3": (8192, 40.0e6), "c2": (65536, 14.6e6), "c4": (131072, 5.46e9), "c5": (32768, 0.533e9)}[wl["name"]]   # (chains per GPU, bytes)
         common = {"traffic": traffic[1] if C == traffic[0] else None,
                   "kernel": "glm_grad_kernel" if wl["name"] == "c3" else "advance_kernel",
                   "kernel_ms_per_launch": 1e3 * ktime / max(klaunch, 1), "kernel_launches_timed": klaunch,

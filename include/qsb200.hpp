@@ -44,6 +44,12 @@ class Program {
     qsb_model_desc m{}; m.family = QSB_FAM_INDEP; m.dim = K; m.erp_kind = kind; m.erp_p0 = p0; m.erp_p1 = p1;
     m.ret_mode = return_sum ? 0 : 1; m.ret_div = ret_div; return Program(m);
   }
+  // optional parts of an INDEP descriptor (arrays stay owned by the caller, like every pointer of qsb_model_desc)
+  Program& LexicalIds(const int32_t* lexid) { desc_.erp_lexid = lexid; return *this; }                       // erp.t:318-321
+  Program& Factors(const double* fmu, const double* fsigma) { desc_.erp_fmu = fmu; desc_.erp_fsigma = fsigma; return *this; }   // trace.t:1099-1107
+  Program& LatentParams(const int32_t* pref, const double* pcoef, const int32_t* ptf = nullptr) {           // erp.t:576-610
+    desc_.erp_pref = pref; desc_.erp_pcoef = pcoef; desc_.erp_ptf = ptf; return *this;
+  }
   const qsb_model_desc& desc() const { return desc_; }
   int retdim() const { return desc_.family == QSB_FAM_INDEP && desc_.ret_mode == 0 ? 1 : desc_.dim; }
  private:

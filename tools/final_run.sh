@@ -15,5 +15,5 @@ $cmd > gpurun_out/plain_c3.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_c3_launches.csv $cmd > gpurun_out/ncu_c3_list.log 2>&1
 $cmd > gpurun_out/plain_c3b.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:glm_grad_kernel -s 60 -c 2 -f -o gpurun_out/${tag}_c3_grad $cmd > gpurun_out/ncu_c3_full.log 2>&1
-bash tools/profile_adv.sh $tag c4 c5 c2
+[ "${SKIP_ADV:-0}" = 1 ] || bash tools/profile_adv.sh $tag c4 c5 c2
 tail -n 3 gpurun_out/pytest_gpu.log gpurun_out/smoke.log
