@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=os.environ.get("QSB_WORKLOAD", "c3"))
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU")
+    ap.add_argument("--balanced", action="store_true",
+                    help="c3: QSB_FLAG_BALANCED (one equal run of row blocks per SM in the gradient kernel; draws then depend on the chain tile in the last bits)")
     ap.add_argument("--scaling", default=os.environ.get("QSB_SCALING", "weak"), choices=["weak", "strong"],
                     help="weak (default): the configuration's chain count per GPU; strong: that chain count in total, sharded over the GPUs")
     ap.add_argument("--burnin", type=int, default=None, help="untimed adaptation transitions before the warm-up steps")
@@ -240,7 +242,7 @@ def main():
     B = args.burnin if args.burnin is not None else {"c3": 150, "c2": 300, "c4": 300, "c5": 100}[wl["name"]]
     Ke = args.e2e_steps if args.e2e_steps is not None else min(K, 10)
     stream = torch.cuda.current_stream().cuda_stream
-    sampler = qs.Sampler(prog, kernel, numchains=C, seed=SEED, device=local, chain_begin=rank * C, flags=L.FLAG_TIME_KERNEL,
+    sampler = qs.Sampler(prog, kernel, numchains=C, seed=SEED, device=local, chain_begin=rank * C, flags=L.FLAG_TIME_KERNEL | (L.FLAG_BALANCED if args.balanced else 0),
                          stream=stream, sample_chains=min(C, 16384))
     sampler.init()
     sampler.begin(K + Ke, burnin=B + W, lag=1, numiters=B + W + K + Ke)
@@ -366,7 +368,7 @@ def main():
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (wl["name"], wl["desc"]), "chains_per_gpu": C, "chains_total": C * world,
                        "burnin_transitions": B, "l2": "working set (chain state + partial sums) larger than L2; inputs change every step",
-                       "seed": SEED},
+                       "seed": SEED, **({"glm_decomposition": "balanced (QSB_FLAG_BALANCED)"} if args.balanced else {})},
             "secondary": {"metric": "min-ESS/sec", "value": (min_ess / t) if min_ess else None, "unit": "effective samples/s", "min_ess": min_ess,
                           "draws_per_chain": K, "max_split_rhat": rhat_max, "maxlag": maxlag,
                           "accept_rate": cnt[1].item() / max(cnt[2].item(), 1.0)},

@@ -112,7 +112,11 @@ enum {
   QSB_FLAG_MOMENTS = 1u,     /* accumulate per-chain running moments of the kept samples (for split-Rhat) */
   QSB_FLAG_RECORD = 2u,      /* keep a per-iteration record (state, accept, dH, step, kernel index) -- parity tests */
   QSB_FLAG_RECORD_LEAP = 4u, /* additionally record the position after every leapfrog step (single HMC kernel) */
-  QSB_FLAG_TIME_KERNEL = 8u  /* bracket every launch of the dominant kernel with CUDA events (roofline measurement) */
+  QSB_FLAG_TIME_KERNEL = 8u, /* bracket every launch of the dominant kernel with CUDA events (roofline measurement) */
+  QSB_FLAG_BALANCED = 16u    /* LOGISTIC: cut the gradient kernel's work into one equal run of row blocks per SM instead of the
+                              * (chain tile x row split) grid: ~2 % faster on c3, more on small shards; a chain's draws then depend, in
+                              * the last bits, on the tile it sits in (default off: draws are bit-identical for any chain partition
+                              * of equal shard size) */
 };
 
 typedef struct {

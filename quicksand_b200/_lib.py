@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("QSB200_LIB") or os.path.join(HERE, "libqsb200.so")   
 FAM_INDEP, FAM_GAUSS_PREC, FAM_LOGISTIC, FAM_EIGHT_SCHOOLS, FAM_FUNNEL = 1, 2, 3, 4, 5
 ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
 KERNEL_HMC, KERNEL_DRIFT, KERNEL_HARM, KERNEL_TRACEMH = 1, 2, 3, 4
-FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL = 1, 2, 4, 8
+FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL, FLAG_BALANCED = 1, 2, 4, 8, 16
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)

@@ -37,6 +37,7 @@ namespace qsb {
 
 static constexpr int MB = 32;          // observation rows per pipeline stage
 static constexpr int NT = MB / 8;      // 8-row n-tiles per stage
+static constexpr int BAR_DOUBLES = 2 * 4 + 2;   // behind the ring: full[STAGES], empty[STAGES] mbarriers and the stream-K cursor
 static constexpr int STAGES = 4;        // deepest ring; a sampler uses 2..4 stages (GradParams::stages), whatever fits 227 KB
 #ifndef QSB_GLM_CW
 #define QSB_GLM_CW 12
@@ -56,6 +57,7 @@ static constexpr int GRAD_THREADS = CW * 32;
 struct GradParams {
   const double* Xp; const double* yv;
   int S, d, nj, nblocks, ksplit, ntiles;
+  int sk_U;                // > 0: balanced ("stream-K") decomposition, see glm_grad_kernel; 0: grid = chain tiles x row splits
   uint32_t C; int Dp;
   const double* theta;     // [C][Dp]
   double* partG;           // [ksplit][C][Dp]
@@ -69,6 +71,9 @@ struct GradParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -186,7 +191,8 @@ template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps(SigState
 // TRIM: the last dimension tile holds at most 4 real dimensions (d = 100: dims 96..99 of 96..103).  In the first
 // contraction the k <-> dimension map of that tile becomes k-step 0 = dims 8(NJ-1) + tig and its all-padding second
 // k-step is not issued (100 instead of 104 DMMAs per row block); the second contraction is unchanged.
-template <int NJ, bool FULL, bool LP, bool TRIM = false>
+// SK: the balanced decomposition below (GradParams::sk_U > 0) instead of the (chain tile, row split) grid.
+template <int NJ, bool FULL, bool LP, bool TRIM = false, bool SK = false>
 __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_constant__ GradParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
@@ -195,8 +201,26 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + SD * NST);
   uint64_t* empty = full + STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x % P.ntiles, split = blockIdx.x / P.ntiles;
-  const int b0 = (int)(((long)split * P.nblocks) / P.ksplit), b1 = (int)(((long)(split + 1) * P.nblocks) / P.ksplit);
+  // Work decomposition.  sk_U == 0: CTA = (chain tile, row split), grid = ntiles x ksplit.  sk_U > 0: the ntiles x nblocks
+  // row-block units, tile-major, are cut into equal runs of sk_U units, one run per CTA (grid ~ number of SMs: one full
+  // wave for any chain count); a run that crosses a tile boundary is worked off as two (or more) segments, and a tile's
+  // segments land in consecutive partial-sum slots (slot = CTA index - index of the first CTA that touches the tile).
+  int& sk_su = *reinterpret_cast<int*>(empty + STAGES);    // first unit of the CTA's next segment (kept out of the register file)
+  if (SK) {
+    if (threadIdx.x == 0) sk_su = (int)blockIdx.x * P.sk_U;   // (ntiles x nblocks < 2^31: checked at creation)
+    __syncthreads();
+  }
+  for (;;) {
+  int tile, split, b0, b1;
+  if (SK) {
+    const int su = sk_su, su_end = min(((int)blockIdx.x + 1) * P.sk_U, P.ntiles * P.nblocks);
+    tile = su / P.nblocks; b0 = su - tile * P.nblocks;
+    b1 = min(P.nblocks, b0 + (su_end - su));
+    split = (int)blockIdx.x - (tile * P.nblocks) / P.sk_U;
+  } else {
+    tile = blockIdx.x % P.ntiles; split = blockIdx.x / P.ntiles;
+    b0 = (int)(((long)split * P.nblocks) / P.ksplit); b1 = (int)(((long)(split + 1) * P.nblocks) / P.ksplit);
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
@@ -204,7 +228,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   }
   if ((int)threadIdx.x < NST * 8) sm[SD * (threadIdx.x >> 3) + (size_t)MB * P.S + (threadIdx.x & 7)] = 0.0;   // over-read pads
   if (THETA_SMEM) {   // the chain tile's Theta, [CB][theta_stride]; rows of chains past the end are zero
-    double* sT = sm + SD * NST + 2 * STAGES;
+    double* sT = sm + SD * NST + BAR_DOUBLES;
     const int Dp = P.Dp, stride = theta_stride(Dp);
     for (int idx = threadIdx.x; idx < CB * Dp; idx += GRAD_THREADS) {
       const int ch = idx / Dp, j = idx - ch * Dp;
@@ -240,7 +264,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
 
   double th[THETA_SMEM ? 1 : NJ][2], G[NJ][2];
   const int STH = theta_stride(P.Dp);
-  const double* sTh = sm + SD * NST + 2 * STAGES + (size_t)(warp * 8 + gid) * STH + 2 * tig;   // THETA_SMEM: this thread's Theta row
+  const double* sTh = sm + SD * NST + BAR_DOUBLES + (size_t)(warp * 8 + gid) * STH + 2 * tig;   // THETA_SMEM: this thread's Theta row
 #pragma unroll
   for (int J = 0; J < NJ; ++J) {
     G[J][0] = G[J][1] = 0.0;
@@ -406,6 +430,16 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
     lpacc += __shfl_xor_sync(0xffffffffu, lpacc, 2);
     if (valid && tig == 0) P.partLp[(size_t)split * P.C + chain] = lpacc;
   }
+  if (!SK) break;
+  __syncthreads();                       // next segment of this CTA's run: the ring starts over
+  const int su_next = tile * P.nblocks + b1;
+  if (su_next >= min(((int)blockIdx.x + 1) * P.sk_U, P.ntiles * P.nblocks)) break;
+  if (threadIdx.x == 0) {
+    sk_su = su_next;
+    for (int s = 0; s < NST; ++s) { mbar_inval(&full[s]); mbar_inval(&empty[s]); }
+  }
+  __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -415,6 +449,7 @@ enum { V_INIT_SAMPLE = 0, V_FINISH_EVAL = 1, V_TRANS_FIRST = 2, V_TRANS_MID = 3,
 
 struct VecParams {
   RngKey key; uint32_t chain_begin, C; int d, Dp, ksplit;
+  int sk_U, sk_nblocks, sk_CB;   // stream-K decomposition of the gradient kernel (sk_U > 0): partial-sum slots per chain tile vary
   double prior_sigma;
   double *x, *g, *xs, *gs, *p;                 // [C][Dp]
   const double* partG; const double* partLp;
@@ -441,10 +476,20 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// number of partial sums the stream-K gradient kernel left for chain c (its tile's segments)
+__device__ __forceinline__ int n_partials_sk(const VecParams& P, uint32_t c) {
+  const long t0 = (long)(c / (uint32_t)P.sk_CB) * P.sk_nblocks;
+  return (int)((t0 + P.sk_nblocks - 1) / P.sk_U - t0 / P.sk_U) + 1;
+}
 // gradient and (optionally) log-density of the chain at xs from the partial sums of the GEMM kernel
 __device__ __forceinline__ double finish_grad(const VecParams& P, uint32_t c, int i, double th) {
   double gl = 0.0;
-  for (int r = 0; r < P.ksplit; ++r) gl += P.partG[((size_t)r * P.C + c) * P.Dp + i];
+  if (!P.sk_U) {
+    for (int r = 0; r < P.ksplit; ++r) gl += P.partG[((size_t)r * P.C + c) * P.Dp + i];
+  } else {
+    const int np = n_partials_sk(P, c);
+    for (int r = 0; r < np; ++r) gl += P.partG[((size_t)r * P.C + c) * P.Dp + i];
+  }
   const double g = gaussian_dlp_dx(th, 0.0, P.prior_sigma) + gl;
   return P.T != 1.0 ? g * P.invT : g;
 }
@@ -453,7 +498,12 @@ __device__ __forceinline__ double finish_lp(const VecParams& P, uint32_t c, int 
   for (int i = lane; i < P.d; i += 32) lpp += gaussian_lp(pos[i], 0.0, P.prior_sigma);
   lpp = warp_sum(lpp);
   double ll = 0.0;
-  for (int r = 0; r < P.ksplit; ++r) ll += P.partLp[(size_t)r * P.C + c];
+  if (!P.sk_U) {
+    for (int r = 0; r < P.ksplit; ++r) ll += P.partLp[(size_t)r * P.C + c];
+  } else {
+    const int np = n_partials_sk(P, c);
+    for (int r = 0; r < np; ++r) ll += P.partLp[(size_t)r * P.C + c];
+  }
   return lpp + ll;   // at temperature 1; callers divide
 }
 
@@ -725,16 +775,18 @@ static int pick_ksplit(int ntiles, int nblocks, int nsm) {
   return best;
 }
 
-template <int NJ, bool FULL, bool LP, bool TRIM = false> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
+template <int NJ, bool FULL, bool LP, bool TRIM = false, bool SK = false> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
+  if constexpr (!SK) { if (P.sk_U) return launch_grad_tf<NJ, FULL, LP, TRIM, true>(P, smem, st); }
   static bool attr_set[64] = {};   // per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL, LP, TRIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(glm_grad_kernel<NJ, FULL, LP, TRIM, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
-  glm_grad_kernel<NJ, FULL, LP, TRIM><<<P.ntiles * P.ksplit, GRAD_THREADS, smem, st>>>(P);
+  const int grid = P.sk_U ? (int)(((long)P.ntiles * P.nblocks + P.sk_U - 1) / P.sk_U) : P.ntiles * P.ksplit;
+  glm_grad_kernel<NJ, FULL, LP, TRIM, SK><<<grid, GRAD_THREADS, smem, st>>>(P);
   return cudaGetLastError();
 }
 template <int NJ> static cudaError_t launch_grad_t(const GradParams& P, size_t smem, cudaStream_t st) {
@@ -829,14 +881,24 @@ GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t 
   G.Xp = m->Xp; G.yv = m->yv; G.S = m->S; G.d = m->d; G.nj = m->Dp / 8; G.nblocks = m->Npad / MB;
   G.ntiles = (int)((C + CB - 1) / CB); G.ksplit = pick_ksplit(G.ntiles, G.nblocks, nsm);
   G.C = numchains; G.Dp = m->Dp;
+  G.sk_U = 0;
+  const char* env_sk = getenv("QSB_GLM_STREAMK");   // tuning override of QSB_FLAG_BALANCED (0 / 1)
+  if (env_sk ? atoi(env_sk) > 0 : (flags & QSB_FLAG_BALANCED) != 0) {
+    const long total = (long)G.ntiles * G.nblocks;
+    if (total < (1L << 30)) {   // one run of row-block units per SM, at least 12 row blocks per run (prologue/epilogue cost ~0.75 of one)
+      G.sk_U = (int)std::max(12L, (total + nsm - 1) / nsm);
+      G.ksplit = (G.nblocks + G.sk_U - 1) / G.sk_U + 1;   // most partial-sum slots a tile can have
+    }
+  }
   s->nj_inst = pick_nj_inst(G.nj);
   G.stages = STAGES;
-  auto smem_for = [&](int nst) { return stage_doubles(m->S) * nst * 8 + 2 * STAGES * 8 + (THETA_SMEM ? (size_t)CB * theta_stride(m->Dp) * 8 : 0); };
+  auto smem_for = [&](int nst) { return stage_doubles(m->S) * nst * 8 + BAR_DOUBLES * 8 + (THETA_SMEM ? (size_t)CB * theta_stride(m->Dp) * 8 : 0); };
   while (G.stages > 2 && smem_for(G.stages) > 227 * 1024) --G.stages;      // d = 128: the Theta tile leaves room for a 2-deep ring
   s->smem = smem_for(G.stages);
   if (s->smem > 227 * 1024) { why = "shared memory of the gradient kernel exceeds 227 KB for this dimension"; delete s; return nullptr; }
   V.key = RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)}; V.chain_begin = chain_begin; V.C = numchains; V.d = m->d; V.Dp = m->Dp;
   V.T = 1.0; V.invT = 1.0;
+  V.sk_U = G.sk_U; V.sk_nblocks = G.nblocks; V.sk_CB = CB;
   V.ksplit = G.ksplit; V.prior_sigma = m->prior_sigma; V.L = numSteps; V.adapting = adapt ? 1 : 0; V.stepSize0 = stepSize; V.SC = sample_chains;
   bool ok = dalloc(s, &V.x, C * Dp) && dalloc(s, &V.g, C * Dp) && dalloc(s, &V.xs, C * Dp) && dalloc(s, &V.gs, C * Dp) && dalloc(s, &V.p, C * Dp);
   double *partG = nullptr, *partLp = nullptr;

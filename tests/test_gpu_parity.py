@@ -707,3 +707,35 @@ def test_latent_parameter_descriptor_errors(qs):
     p = qs.programs.indep([("gaussian", 0.0, 1.0)] + [("gaussian", lat(0), 1.0)] * 40, ret="vector")   # 41 components: no thread-per-chain variant
     with pytest.raises(L.QsbError):
         qs.Sampler(p, qs.HMCKernel(), numchains=4)
+
+
+def test_glm_stream_k_decomposition_parity(qs, oracle, monkeypatch):
+    """QSB_GLM_STREAMK=1: the gradient kernel's balanced decomposition (equal runs of row-block units per SM, runs crossing
+    chain-tile boundaries, a varying number of partial sums per tile) against the oracle and against the default
+    (chain tile x row split) grid.  The two group a chain's row blocks differently: equal to rounding, not bit for bit --
+    which is why the default keeps the grid whose grouping does not depend on the tile a chain sits in."""
+    rng = np.random.default_rng(7)
+    N, d = 10000, 100
+    X = rng.standard_normal((N, d)) / np.sqrt(d)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-X @ rng.normal(0, 1, d)))).astype(np.uint8)
+    big = qs.programs.logistic(X, y, 2.5)
+    k = qs.HMCKernel(numSteps=4, stepSize=0.015, doStepSizeAdapt=False)
+    ref = qs.Sampler(big, k, numchains=300, seed=5); ref.init(); ref.run(3)
+    ref_vals = ref.fetch_values(); ref.close()
+    monkeypatch.setenv("QSB_GLM_STREAMK", "1")
+    gpu, cpu = P.run_both(big, k, chains=6, iters=4, seed=20261019, leap=True)
+    P.compare(gpu, cpu, TOL, leap=True, what="c3 full shape HMC, stream-K")
+    sk = qs.Sampler(big, k, numchains=300, seed=5); sk.init(); sk.run(3)     # 4 chain tiles: runs cross tile boundaries
+    sk_vals = sk.fetch_values(); sk.close()
+    assert P.relerr(sk_vals, ref_vals).max() <= 1e-10
+    monkeypatch.delenv("QSB_GLM_STREAMK")
+    from quicksand_b200 import _lib as L
+    fl = qs.Sampler(big, k, numchains=300, seed=5, flags=L.FLAG_BALANCED); fl.init(); fl.run(3)       # the public switch: QSB_FLAG_BALANCED
+    assert np.array_equal(fl.fetch_values(), sk_vals) and not np.array_equal(sk_vals, ref_vals)
+    fl.close()
+    monkeypatch.setenv("QSB_GLM_STREAMK", "1")
+    small = _programs(qs)["logistic20"]
+    for kern, iters, minc in [(qs.HMCKernel(numSteps=7, stepSize=0.1, doStepSizeAdapt=False), 20, 1.0), (qs.DriftKernel(scale=0.3), 100, 1.0),
+                              (qs.HARMKernel(), 60, 1.0), (qs.HMCKernel(numSteps=1), 15, 0.8)]:
+        gpu, cpu = P.run_both(small, kern, chains=200, iters=iters, seed=3)      # 200 chains of 333 rows: 3 tiles x 11 row blocks in runs of 12
+        P.compare(gpu, cpu, TOL, what="logistic20 stream-K %d" % kern.specs[0].kind, min_compared=minc)
