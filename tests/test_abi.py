@@ -90,3 +90,32 @@ def test_cxx_mirror_compiles_links_and_fails_loudly_without_gpu(qs, tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
     else:
         assert r.returncode == 2 and "qsb200:" in r.stderr
+
+
+def test_indep_descriptor_layout(qs):
+    """Host logic of qs.programs.indep: entries -> per-component descriptor arrays (vector choices expand to K components,
+    gammamv / betamv reparametrise, latent parameters refer to COMPONENT indices and must point backwards), and the ctypes
+    mirror of qsb_model_desc has the header's field order."""
+    from quicksand_b200 import _lib as L
+    lat = qs.programs.latent
+    p = qs.programs.indep([("gamma", 3.0, 1.0), ("dirichlet", [2.0, 3.0, 5.0]), ("gamma", lat(0), 2.0), ("gammamv", 4.0, 8.0),
+                           ("gaussian", lat(3, a=0.5, b=2.0), lat(2, a=0.1, exp=True))], ret="vector", lexids=[0, 1, 0, 2, 3],
+                          factors=[None, None, (1.0, 0.5), None, None])
+    a = p.arrays
+    assert p.dim == 7 and p.retdim == 7
+    assert list(a["erp_kind"]) == [L.ERP_GAMMA] + [L.ERP_DIRICHLET] * 3 + [L.ERP_GAMMA, L.ERP_GAMMA, L.ERP_GAUSSIAN]
+    assert list(a["erp_p1"][1:4]) == [0.0, 1.0, 2.0]                       # index inside the vector choice
+    assert a["erp_p0"][5] == 4.0 * 4.0 / 8.0 and a["erp_p1"][5] == 8.0 / 4.0   # gammamv(m, v) -> gamma(m*m/v, v/m)
+    assert list(a["erp_lexid"]) == [0, 1, 1, 1, 0, 2, 3]
+    assert list(a["erp_pref"]) == [-1, -1, -1, -1, -1, -1, -1, -1, 0, -1, -1, -1, 5, 4]   # entry 3 -> component 5, entry 2 -> component 4
+    assert list(a["erp_ptf"]) == [0] * 13 + [1] and a["erp_pcoef"][12] == 2.0 and a["erp_p0"][6] == 0.5 and a["erp_p1"][6] == 0.1
+    assert a["erp_fsigma"][4] == 0.5 and a["erp_fmu"][4] == 1.0 and a["erp_fsigma"][0] == 0.0
+    with pytest.raises(AssertionError):
+        qs.programs.indep([("gaussian", lat(0), 1.0)])                      # a parameter cannot read its own (or a later) choice
+    with pytest.raises(AssertionError):
+        qs.programs.indep([("gaussian", 0.0, 1.0), ("uniform", lat(0), 2.0)])   # a uniform's parameters are its bounds
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "qsb200.h")).read()
+    body = hdr[hdr.index("typedef struct {", hdr.index("All pointers are HOST pointers")):hdr.index("} qsb_model_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"(\w+)\s*;", body)
+    assert names == [f[0] for f in L.ModelDesc._fields_], (names, [f[0] for f in L.ModelDesc._fields_])
