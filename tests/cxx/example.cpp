@@ -13,6 +13,15 @@ int main() {
                          qs::MCMC(qs::HMCKernel(hp), mp));
     double est = run();
     std::printf("estimate %.4f (truth 0.1)\n", est);
-    return std::fabs(est - 0.1) <= 0.07 ? 0 : 1;
+    if (!(std::fabs(est - 0.1) <= 0.07)) return 1;
+    // a parameter that reads an earlier choice:  mu = gaussian(1, 0.5); x = gaussian(0.5 + 2 mu, 1); return mu + x  ->  3.5
+    std::vector<int32_t> k2(2, QSB_ERP_GAUSSIAN), pref = {-1, -1, 0, -1};
+    std::vector<double> p0 = {1.0, 0.5}, p1 = {0.5, 1.0}, pcoef = {0.0, 0.0, 2.0, 0.0};
+    qs::Program hier = qs::Program::Indep(k2.data(), p0.data(), p1.data(), 2, true, 1.0).LatentParams(pref.data(), pcoef.data());
+    auto run2 = qs::infer(hier, [](const qs::SampleVector& s) { double m = 0; for (double e : qs::Expectation(s)) m += e; return m / s.numchains; },
+                          qs::MCMC(qs::HMCKernel(hp), mp));
+    double est2 = run2();
+    std::printf("estimate %.4f (truth 3.5)\n", est2);
+    return std::fabs(est2 - 3.5) <= 0.15 ? 0 : 1;
   } catch (const qs::Error& e) { std::fprintf(stderr, "%s\n", e.what()); return 2; }
 }
