@@ -371,7 +371,6 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
       }
       if (d->erp_pref) {
         if (!d->erp_pcoef) return bail(3, "INDEP: erp_pcoef is required with erp_pref");
-        if (d->dim > 32) return bail(3, "INDEP: latent parameters run in the thread-per-chain mapping (dim <= 32)");
         std::vector<int> tf(2 * (size_t)d->dim, 0);
         bool any = false;
         for (int i = 0; i < d->dim; ++i)
@@ -385,6 +384,7 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
             if (d->erp_kind[i] == QSB_ERP_UNIFORM || d->erp_kind[i] == QSB_ERP_DIRICHLET)
               return bail(3, "INDEP: latent parameters are supported on gaussian, gamma and beta choices");
           }
+        if (any && d->dim > 32) return bail(3, "INDEP: latent parameters run in the thread-per-chain mapping (dim <= 32)");
         if (any) {
           int *lr, *lt; double* lb;
           if (m->arena.alloc(&lr, 2 * (size_t)d->dim) || m->arena.alloc(&lt, 2 * (size_t)d->dim) || m->arena.alloc(&lb, 2 * (size_t)d->dim)) return bail(4, "cudaMalloc failed");
