@@ -739,3 +739,23 @@ def test_glm_stream_k_decomposition_parity(qs, oracle, monkeypatch):
                               (qs.HARMKernel(), 60, 1.0), (qs.HMCKernel(numSteps=1), 15, 0.8)]:
         gpu, cpu = P.run_both(small, kern, chains=200, iters=iters, seed=3)      # 200 chains of 333 rows: 3 tiles x 11 row blocks in runs of 12
         P.compare(gpu, cpu, TOL, what="logistic20 stream-K %d" % kern.specs[0].kind, min_compared=minc)
+
+
+def test_single_chain_reference_protocol(qs, oracle):
+    """Config c1: with numchains = 1 (the default) qs.MCMC is the reference's single chain.  The reference's own protocol --
+    150 samples x lag 20, 5 runs, mean absolute error <= 0.07 (testsuite.t:84-141) -- on its HMC programs (testsuite.t:621-691,
+    719-730), and that one chain is the oracle's chain step for step."""
+    for name, truth in [("gaussian1", 0.1), ("gauss10", 0.1), ("gamma1", 0.4), ("beta1", 2.0 / 7.0)]:
+        prog = _programs(qs)[name]
+        errs = []
+        for r in range(5):
+            m = qs.MCMC(qs.HMCKernel(numSteps=10), dict(numsamps=150, lag=20, seed=100 + r))
+            est = qs.infer(prog, qs.Expectation(), m)()
+            assert np.size(est) == 1                       # one chain: the reference's scalar, not a per-chain vector
+            errs.append(abs(float(np.ravel(est)[0]) - truth))
+        assert np.mean(errs) <= 0.07, (name, errs)
+    k = qs.HMCKernel(numSteps=10, stepSize=0.2, doStepSizeAdapt=False)
+    gpu, cpu = P.run_both(_programs(qs)["gauss10"], k, chains=1, iters=200, seed=100, leap=True)
+    P.compare(gpu, cpu, TOL, leap=True, what="single chain HMC gauss10")
+    gpu, cpu = P.run_both(_programs(qs)["funnel12"], qs.MixtureKernel([qs.HARMKernel(), qs.DriftKernel(scale=0.3)], [0.5, 0.5]), chains=1, iters=300, seed=101)
+    P.compare(gpu, cpu, TOL, what="single chain HARM+Drift funnel12")
