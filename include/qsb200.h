@@ -142,6 +142,9 @@ typedef struct {
 
 int qsb_version(void);
 const char* qsb_last_error(void);
+/* SHA-256 (hex) over the CUDA sources and this header the loaded binary was compiled from (quicksand_b200/build.py
+ * passes it in at compile time): ties a measured library to a source tree. */
+const char* qsb_source_hash(void);
 
 /* ---- models */
 int qsb_model_create(const qsb_model_desc* desc, int32_t device, qsb_model** out);
@@ -187,6 +190,13 @@ int qsb_sampler_set_temperatures(qsb_sampler* s, const double* temps, uint64_t n
  * stride_bytes >= (retdim+2)*8.  Chains are sampler-local indices. */
 int qsb_sampler_fetch_samples(qsb_sampler* s, uint32_t chain_begin, uint32_t chain_end,
                               uint64_t sample_begin, uint64_t sample_end, void* dst, size_t stride_bytes);
+/* The same without blocking the host: the transposing gather is queued on the sampler's stream, the device-to-host copy
+ * on a second stream of the library (two staging buffers alternate), so the copy of one step's draws overlaps the
+ * transitions queued after it.  dst should be page-locked (the caller pins it; Terra: cudaHostRegister on Vector._data)
+ * and must stay untouched until qsb_sampler_fetch_sync returns. */
+int qsb_sampler_fetch_samples_async(qsb_sampler* s, uint32_t chain_begin, uint32_t chain_end,
+                                    uint64_t sample_begin, uint64_t sample_end, void* dst, size_t stride_bytes);
+int qsb_sampler_fetch_sync(qsb_sampler* s);
 /* Only the values, as a dense HOST array [chain][sample][retdim] (no logprob fields). */
 int qsb_sampler_fetch_values(qsb_sampler* s, uint32_t chain_begin, uint32_t chain_end,
                              uint64_t sample_begin, uint64_t sample_end, double* dst);
@@ -238,7 +248,64 @@ int qsb_query_autocorrelation_host(const void* samples, size_t stride_bytes, uin
 int qsb_sampler_fetch_record(qsb_sampler* s, double* state, int32_t* accept, double* dh, double* step,
                              int32_t* kidx, double* leap);
 
+/* ---- multi-GPU (SURVEY.md 8b Threading, 8e): chains are block-partitioned over the devices of ONE box; a chain's random
+ * stream is keyed by its GLOBAL id, so the partition does not change its draws.  There is no data-path collective; the only
+ * exchange is the all-reduce(sum) of the diagnostics' sufficient statistics, done by the library over its own NCCL
+ * communicator (NVLink / NVSwitch).  The reference is single-threaded (qs/trace.t:452-454), so two shapes are offered:
+ *
+ * (1) qsb_group: ONE host thread drives several devices -- what a Terra process calls.  qs.MCMC(kernel, {numchains=,
+ *     devices={0,1,..}}) maps onto it (qs/mcmc.t:36-43 parameter table + the new `devices`).  Every call fans out to one
+ *     sampler per device (asynchronous launches on per-device streams) and joins; results are indexed by global chain.
+ * (2) qsb_comm: one process per device (torchrun / MPI style); each process owns a qsb_sampler with chain_begin = its
+ *     offset and joins a communicator through a 128-byte id created by rank 0 and distributed by the caller. */
+typedef struct qsb_group qsb_group;
+typedef struct qsb_comm qsb_comm;
+#define QSB_COMM_ID_BYTES 128
+
+/* cfg->numchains = TOTAL chains, cfg->chain_begin = global id of the first; cfg->device / cfg->stream are ignored (each
+ * shard runs on its own stream of its device).  devices[i] may repeat (several shards on one device: used by tests on a
+ * single-GPU box; the reduction then runs as a device kernel instead of NCCL).  desc as for qsb_model_create: the model
+ * data are replicated on every device. */
+int qsb_group_create(const qsb_model_desc* desc, const qsb_kernel_spec* specs, int32_t nspecs, const qsb_run_config* cfg,
+                     const int32_t* devices, int32_t ndevices, qsb_group** out);
+int qsb_group_destroy(qsb_group* g);
+int32_t qsb_group_size(const qsb_group* g);
+qsb_sampler* qsb_group_sampler(qsb_group* g, int32_t shard);      /* borrowed; shard i owns a contiguous block of chains */
+int qsb_group_init(qsb_group* g);
+int qsb_group_run(qsb_group* g, uint64_t nsamps, uint64_t burnin, uint64_t lag);
+int qsb_group_begin(qsb_group* g, uint64_t max_samples, uint64_t burnin, uint64_t lag, uint64_t numiters);
+int qsb_group_advance(qsb_group* g, uint64_t iters);
+int qsb_group_sync(qsb_group* g);                                  /* wait for every device */
+/* chains are indices into the group's [0, numchains) */
+int qsb_group_fetch_samples(qsb_group* g, uint32_t chain_begin, uint32_t chain_end, uint64_t sample_begin, uint64_t sample_end,
+                            void* dst, size_t stride_bytes);
+int qsb_group_stats(qsb_group* g, qsb_stats* out);                 /* counters summed over shards, seconds = max */
+/* qsb_sampler_diagnostics of every shard, all-reduced (NCCL ncclSum over the group's communicator): dst is HOST */
+int qsb_group_diagnostics(qsb_group* g, int32_t maxlag, double* dst);
+
+int qsb_comm_unique_id(uint8_t id[QSB_COMM_ID_BYTES]);            /* rank 0; hand the bytes to the other ranks */
+int qsb_comm_create(const uint8_t id[QSB_COMM_ID_BYTES], int32_t rank, int32_t nranks, int32_t device, qsb_comm** out);
+int qsb_comm_destroy(qsb_comm* c);
+/* in-place sum over ranks of n doubles in DEVICE memory, on `stream` of the communicator's device */
+int qsb_comm_allreduce_sum(qsb_comm* c, double* buf, size_t n, void* stream);
+/* qsb_sampler_diagnostics of this rank's shard followed by the all-reduce; dst is HOST, identical on every rank */
+int qsb_sampler_diagnostics_allreduce(qsb_sampler* s, qsb_comm* c, int32_t maxlag, double* dst);
+
+/* ---- measurement support */
+/* FP64 peak of the device the caller runs on, measured in-process in about `seconds` of device time: which = 0 dependent
+ * chains of DFMA in registers, 1 mma.sync.m8n8k4.f64 (DMMA).  Returns TFLOP/s in *tflops (roofline denominators of
+ * bench.py: MEASURED_PEAKS.json carries no fp64 figure). */
+int qsb_measure_fp64_peak(int32_t which, double seconds, int32_t device, double* tflops);
+
 /* ---- test hooks (parity with the CPU oracle) */
+/* Teacher-forced leapfrog: exactly one HMCKernel:step (qs/hmc.t:307-323) of n independent injected states, taken with the
+ * device functions the transition kernels use (LOGISTIC: the tensor-core gradient kernel).  HOST arrays: x, p [n][dim]
+ * unconstrained positions / momenta, eps [n] step sizes, g [n][dim] the cached gradient at x (NULL: recomputed at x).
+ * last != 0 runs the variant a trajectory uses on its last step and returns the log-density at x' in lp_out [n];
+ * last == 0 the interior-step variant (lp_out = 0).  x_out, p_out, g_out [n][dim]: position, momentum and gradient after
+ * the step.  Replaying the oracle's recorded states through this makes every leapfrog step of an adaptive run comparable. */
+int qsb_debug_leapfrog(qsb_model* m, int32_t n, const double* x, const double* p, const double* g, const double* eps, int32_t last,
+                       double* x_out, double* p_out, double* g_out, double* lp_out);
 /* log-density and gradient of the model at n points x (HOST [n][dim], unconstrained), evaluated by the
  * device functions the kernels use: lp_dual (with log-Jacobians, what HMC sees: erp.t:623-640), its
  * gradient grad [n][dim], and lp_float (what Drift/HARM see: no Jacobian, erp.t:361). */

@@ -93,6 +93,7 @@ def lib(variant=None):
         L.qso_run.argtypes = [C.c_void_p, C.POINTER(KernelSpec), C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
                               C.c_uint64, C.c_uint64, C.c_uint64, dp, dp, dp, ip, dp, dp, ip, dp, dp, C.POINTER(Stats)]
         L.qso_set_temperatures.argtypes = [dp, C.c_uint64]
+        L.qso_set_traj_record.argtypes = [dp] * 7
         L.qso_logp_grad.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp]
         L.qso_expectation.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, dp]
         L.qso_autocorrelation.argtypes = [dp, C.c_int, C.c_int, dp]
@@ -210,10 +211,12 @@ def spec(kind, stepSize=1.0, numSteps=1, doAdapt=True, scale=1.0, weight=1.0, le
     return KernelSpec(kind, int(bool(doAdapt)), stepSize, numSteps, scale, weight, int(bool(lexicalScaleSharing)), 0)
 
 
-def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, record=False, temps=None):
+def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, record=False, temps=None, traj=False):
     """doMCMC for each chain.  Returns a dict with samples [C][S][retdim], logprobs and, if
     ``record``, the per-iteration trace (state, accept, dH, step, kernel index, leapfrog positions).
-    ``temps``: AnnealingKernel schedule, temps[i] = annealSched(i, iters) (qs/mcmc.t:297-319)."""
+    ``temps``: AnnealingKernel schedule, temps[i] = annealSched(i, iters) (qs/mcmc.t:297-319).
+    ``traj`` (single HMC kernel, with ``record``): additionally the state entering every trajectory (x0, g0, p0, lp0)
+    and the momenta / gradient / log-density after every leapfrog step -- what a teacher-forced replay needs."""
     if isinstance(specs, KernelSpec):
         specs = [specs]
     arr = (KernelSpec * len(specs))(*specs)
@@ -231,6 +234,16 @@ def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, r
         elif specs[0].kind == HMC:
             lf = np.zeros((nchains, iters, specs[0].numSteps, n))
         out.update(state=st, accept=ac, dH=dh, step=ss, kidx=ki, leapfrog=lf, init=init)
+    tr = None
+    if traj:
+        assert record and len(specs) == 1 and specs[0].kind == HMC
+        Ls = int(specs[0].numSteps)
+        tr = dict(x0=np.zeros((nchains, iters, n)), g0=np.zeros((nchains, iters, n)), p0=np.zeros((nchains, iters, n)),
+                  lp0=np.zeros((nchains, iters)), leap_mom=np.zeros((nchains, iters, Ls, n)), leap_grad=np.zeros((nchains, iters, Ls, n)),
+                  leap_lp=np.zeros((nchains, iters, Ls)))
+        program._lib.qso_set_traj_record(_dp(tr["x0"]), _dp(tr["g0"]), _dp(tr["p0"]), _dp(tr["lp0"]), _dp(tr["leap_mom"]),
+                                         _dp(tr["leap_grad"]), _dp(tr["leap_lp"]))
+        out.update(tr)
     stats = Stats()
     tarr = np.ascontiguousarray(temps, dtype=np.float64) if temps is not None else None
     program._lib.qso_set_temperatures(_dp(tarr), 0 if tarr is None else len(tarr))
@@ -238,6 +251,8 @@ def run(program, specs, seed, nchains, nsamps, burnin=0, lag=1, chain_begin=0, r
                        _dp(samples), _dp(logprobs), _dp(st), _ip(ac), _dp(dh), _dp(ss), _ip(ki), _dp(lf), _dp(init),
                        C.byref(stats))
     program._lib.qso_set_temperatures(None, 0)
+    if traj:
+        program._lib.qso_set_traj_record(None, None, None, None, None, None, None)
     if rc:
         raise RuntimeError("qso_run failed: %d" % rc)
     out["stats"] = {f: getattr(stats, f) for f, _ in Stats._fields_}

@@ -126,6 +126,14 @@ int qso_program_retdim(void* p) { return ((Program*)p)->retdim; }
 static thread_local std::vector<double> g_temps;
 void qso_set_temperatures(const double* temps, uint64_t n) { g_temps.clear(); if (temps && n) g_temps.assign(temps, temps + n); }
 
+// Teacher-forcing record of a single HMC kernel, filled by the following qso_run call of this thread (all NULL: off).
+//   x0, g0, p0 [nchains][iters][n]   lp0 [nchains][iters]   (state entering each trajectory: positions, cached gradient,
+//   sampled momenta, currTrace.logprob)      leap_mom, leap_grad [nchains][iters][L][n]   leap_lp [nchains][iters][L]
+static thread_local double *g_tx0 = nullptr, *g_tg0 = nullptr, *g_tp0 = nullptr, *g_tlp0 = nullptr, *g_tmom = nullptr, *g_tgrad = nullptr, *g_tlp = nullptr;
+void qso_set_traj_record(double* x0, double* g0, double* p0, double* lp0, double* leap_mom, double* leap_grad, double* leap_lp) {
+  g_tx0 = x0; g_tg0 = g0; g_tp0 = p0; g_tlp0 = lp0; g_tmom = leap_mom; g_tgrad = leap_grad; g_tlp = leap_lp;
+}
+
 static Kernel* make_kernel(const qso_kernel_spec* specs, int nspecs) {
   auto one = [](const qso_kernel_spec& s) -> Kernel* {
     switch (s.kind) {
@@ -176,7 +184,9 @@ int qso_run(void* prog, const qso_kernel_spec* specs, int nspecs, uint64_t seed,
     if (g_temps.empty()) k.reset(inner);
     else { AnnealingKernel* a = new AnnealingKernel(); a->k.reset(inner); a->temps = g_temps; k.reset(a); }
     Recorder rec;
-    recorder() = want_rec ? &rec : nullptr;
+    const bool want_traj = g_tx0 && nspecs == 1 && specs[0].kind == 1;
+    rec.want_traj = want_traj;
+    recorder() = (want_rec || want_traj) ? &rec : nullptr;
     std::vector<Sample> samps;
     samps.reserve(nsamps);
     if (rec_init) {
@@ -203,6 +213,16 @@ int qso_run(void* prog, const qso_kernel_spec* specs, int nspecs, uint64_t seed,
       if (rec_kidx) for (size_t i = 0; i < rec.kernel_index.size(); ++i) rec_kidx[(size_t)c * iters + i] = rec.kernel_index[i];
       if (rec_leap && nspecs == 1 && specs[0].kind == 1)
         std::memcpy(rec_leap + (size_t)c * iters * specs[0].numSteps * n, rec.leapfrog_pos.data(), sizeof(double) * rec.leapfrog_pos.size());
+    }
+    if (want_traj) {
+      const size_t n = iters ? rec.traj_x0.size() / iters : 0, L = specs[0].numSteps;
+      std::memcpy(g_tx0 + (size_t)c * iters * n, rec.traj_x0.data(), sizeof(double) * rec.traj_x0.size());
+      if (g_tg0) std::memcpy(g_tg0 + (size_t)c * iters * n, rec.traj_g0.data(), sizeof(double) * rec.traj_g0.size());
+      if (g_tp0) std::memcpy(g_tp0 + (size_t)c * iters * n, rec.traj_p0.data(), sizeof(double) * rec.traj_p0.size());
+      if (g_tlp0) std::memcpy(g_tlp0 + (size_t)c * iters, rec.traj_lp0.data(), sizeof(double) * rec.traj_lp0.size());
+      if (g_tmom) std::memcpy(g_tmom + (size_t)c * iters * L * n, rec.leapfrog_mom.data(), sizeof(double) * rec.leapfrog_mom.size());
+      if (g_tgrad) std::memcpy(g_tgrad + (size_t)c * iters * L * n, rec.leapfrog_grad.data(), sizeof(double) * rec.leapfrog_grad.size());
+      if (g_tlp) std::memcpy(g_tlp + (size_t)c * iters * L, rec.leapfrog_lp.data(), sizeof(double) * rec.leapfrog_lp.size());
     }
     pm += k->proposalsMade(); pa += k->proposalsAccepted();
     if (nspecs == 1 && specs[0].kind == 1) ge += ((HMCKernel*)inner)->gradEvals;

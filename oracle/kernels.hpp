@@ -35,6 +35,11 @@ struct Recorder {
   std::vector<double> stepsize;       // HMC stepSize / HARM scale used for the proposal of this iteration
   std::vector<int> kernel_index;      // mixture: which sub-kernel ran
   std::vector<double> state;          // unconstrained state after each iteration
+  // teacher-forcing record of HMCKernel:next (tests replay every leapfrog step of a trajectory on the device from these):
+  bool want_traj = false;
+  std::vector<double> traj_x0, traj_g0, traj_p0;   // per HMC iteration: positions, cached gradient, sampled momenta  [n] each
+  std::vector<double> traj_lp0;                    // per HMC iteration: currTrace.logprob entering the Hamiltonian
+  std::vector<double> leapfrog_mom, leapfrog_grad; // after every HMCKernel:step: momenta, gradient at the new position [n] each
   bool in_next = false;
 };
 inline Recorder*& recorder() { static thread_local Recorder* r = nullptr; return r; }
@@ -103,6 +108,12 @@ struct HMCKernel : Kernel {
     gradient_scratch = gradient;
     Recorder* rec = recorder();
     if (rec) { rec->in_next = true; rec->stepsize.push_back(stepSize); }
+    if (rec && rec->want_traj) {
+      rec->traj_x0.insert(rec->traj_x0.end(), positions.begin(), positions.end());
+      rec->traj_g0.insert(rec->traj_g0.end(), gradient.begin(), gradient.end());
+      rec->traj_p0.insert(rec->traj_p0.end(), momenta.begin(), momenta.end());
+      rec->traj_lp0.push_back(currTrace->logprob);
+    }
     for (uint64_t i = 0; i < numSteps; ++i) newlp = step(positions_scratch, gradient_scratch);
     if (rec) rec->in_next = false;
     double H_new = hamiltonian(newlp);
@@ -164,7 +175,13 @@ struct HMCKernel : Kernel {
     double lp = traceUpdate(pos, grad);
     for (size_t i = 0; i < momenta.size(); ++i) momenta[i] = momenta[i] + 0.5 * stepSize * grad[i];
     Recorder* rec = recorder();
-    if (rec && rec->in_next) { rec->leapfrog_pos.insert(rec->leapfrog_pos.end(), pos.begin(), pos.end()); rec->leapfrog_lp.push_back(lp); }
+    if (rec && rec->in_next) {
+      rec->leapfrog_pos.insert(rec->leapfrog_pos.end(), pos.begin(), pos.end()); rec->leapfrog_lp.push_back(lp);
+      if (rec->want_traj) {
+        rec->leapfrog_mom.insert(rec->leapfrog_mom.end(), momenta.begin(), momenta.end());
+        rec->leapfrog_grad.insert(rec->leapfrog_grad.end(), grad.begin(), grad.end());
+      }
+    }
     return lp;
   }
   double traceUpdate(std::vector<double>& pos, std::vector<double>& grad) {   // hmc.t:325-342

@@ -6,8 +6,8 @@ hot path.  There is no CPU fallback: without the built library every compute cal
 """
 from . import programs
 from .api import (AnnealingKernel, TraceMHKernel, Autocorrelation, DriftKernel, Expectation, HARMKernel, HMCKernel, MAP, MCMC, MixtureKernel,
-                  Sampler, Samples, SampleVector, infer)
+                  Sampler, Group, Comm, Samples, SampleVector, infer, measure_fp64_peak, source_hash)
 from .programs import Program
 
 __all__ = ["programs", "Program", "infer", "MCMC", "HMCKernel", "DriftKernel", "HARMKernel", "MixtureKernel",
-           "AnnealingKernel", "TraceMHKernel", "Samples", "MAP", "Expectation", "Autocorrelation", "Sampler", "SampleVector"]
+           "AnnealingKernel", "TraceMHKernel", "Samples", "MAP", "Expectation", "Autocorrelation", "Sampler", "Group", "Comm", "SampleVector", "measure_fp64_peak", "source_hash"]

@@ -14,6 +14,7 @@ ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
 KERNEL_HMC, KERNEL_DRIFT, KERNEL_HARM, KERNEL_TRACEMH = 1, 2, 3, 4
 FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL, FLAG_BALANCED = 1, 2, 4, 8, 16
 
+COMM_ID_BYTES = 128
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
 
@@ -49,6 +50,7 @@ class Stats(C.Structure):
 PROTOTYPES = {
     "qsb_version": (C.c_int, []),
     "qsb_last_error": (C.c_char_p, []),
+    "qsb_source_hash": (C.c_char_p, []),
     "qsb_model_create": (C.c_int, [C.POINTER(ModelDesc), C.c_int32, C.POINTER(C.c_void_p)]),
     "qsb_model_destroy": (C.c_int, [C.c_void_p]),
     "qsb_model_update_data": (C.c_int, [C.c_void_p, C.POINTER(ModelDesc), C.c_void_p]),
@@ -65,6 +67,8 @@ PROTOTYPES = {
     "qsb_sampler_num_samples": (C.c_uint64, [C.c_void_p]),
     "qsb_sampler_set_temperatures": (C.c_int, [C.c_void_p, dp, C.c_uint64]),
     "qsb_sampler_fetch_samples": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "qsb_sampler_fetch_samples_async": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "qsb_sampler_fetch_sync": (C.c_int, [C.c_void_p]),
     "qsb_sampler_fetch_values": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, dp]),
     "qsb_sampler_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "qsb_sampler_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -76,6 +80,25 @@ PROTOTYPES = {
     "qsb_query_map_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int32, dp, dp]),
     "qsb_query_autocorrelation": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, dp, C.c_double, dp]),
     "qsb_query_autocorrelation_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int32, dp, C.c_double, dp]),
+    "qsb_group_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(KernelSpec), C.c_int32, C.POINTER(RunConfig), ip, C.c_int32, C.POINTER(C.c_void_p)]),
+    "qsb_group_destroy": (C.c_int, [C.c_void_p]),
+    "qsb_group_size": (C.c_int32, [C.c_void_p]),
+    "qsb_group_sampler": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "qsb_group_init": (C.c_int, [C.c_void_p]),
+    "qsb_group_run": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "qsb_group_begin": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "qsb_group_advance": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "qsb_group_sync": (C.c_int, [C.c_void_p]),
+    "qsb_group_fetch_samples": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "qsb_group_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "qsb_group_diagnostics": (C.c_int, [C.c_void_p, C.c_int32, dp]),
+    "qsb_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "qsb_comm_create": (C.c_int, [C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "qsb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "qsb_comm_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "qsb_sampler_diagnostics_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, dp]),
+    "qsb_measure_fp64_peak": (C.c_int, [C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_double)]),
+    "qsb_debug_leapfrog": (C.c_int, [C.c_void_p, C.c_int32, dp, dp, dp, dp, C.c_int32, dp, dp, dp, dp]),
     "qsb_logp_grad": (C.c_int, [C.c_void_p, dp, C.c_int32, dp, dp, dp]),
     "qsb_logprob": (C.c_int, [C.c_int32, dp, C.c_int32, dp]),
     "qsb_uniforms": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, dp]),

@@ -190,6 +190,15 @@ class Sampler:
                                                   out.ctypes.data_as(C.c_void_p), dt.itemsize))
         return out
 
+    def fetch_samples_async(self, chain_begin, chain_end, sample_begin, sample_end, out):
+        """Queue the copy of kept samples into the (pinned) structured array ``out`` without waiting; ``fetch_sync`` waits."""
+        dt = self.sample_dtype()
+        L.check(L.lib().qsb_sampler_fetch_samples_async(self.h, chain_begin, chain_end, sample_begin, sample_end,
+                                                        out.ctypes.data_as(C.c_void_p), dt.itemsize))
+
+    def fetch_sync(self):
+        L.check(L.lib().qsb_sampler_fetch_sync(self.h))
+
     def fetch_values(self, chain_begin=0, chain_end=None, sample_begin=0, sample_end=None, out=None):
         chain_end = self.sample_chains if chain_end is None else chain_end
         sample_end = self.num_samples() if sample_end is None else sample_end
@@ -233,6 +242,139 @@ class Sampler:
             self.h, state.ctypes.data_as(L.dp), acc.ctypes.data_as(L.ip), dh.ctypes.data_as(L.dp), step.ctypes.data_as(L.dp),
             kidx.ctypes.data_as(L.ip) if kidx is not None else None, lf.ctypes.data_as(L.dp) if lf is not None else None))
         return dict(state=state, accept=acc, dH=dh, step=step, kidx=kidx, leapfrog=lf)
+
+
+# ---------------------------------------------------------------------------------------------
+class Group:
+    """One ``qsb_group``: the chains of one program block-partitioned over several devices of one box, driven from this
+    (single) host thread; the library owns one stream per device and the NCCL communicator its diagnostics all-reduce
+    runs on.  Same surface as :class:`Sampler`; chain indices are global within the group."""
+
+    def __init__(self, program, kernel, devices, numchains=1, seed=0, chain_begin=0, sample_chains=0, flags=0):
+        assert isinstance(program, Program), "MCMC: expected a qs.program"
+        self.program, self.kernel = program, kernel
+        self.devices = [int(d) for d in devices]
+        self.numchains = int(numchains)
+        self.retdim, self.dim = program.retdim, program.dim
+        arr = (L.KernelSpec * len(kernel.specs))(*kernel.specs)
+        cfg = L.RunConfig(int(seed), int(chain_begin), self.numchains, int(sample_chains), int(flags), -1, 0, None)
+        dev = (C.c_int32 * len(self.devices))(*self.devices)
+        self.h = C.c_void_p()
+        desc = program.desc()
+        L.check(L.lib().qsb_group_create(C.byref(desc), arr, len(kernel.specs), C.byref(cfg), dev, len(self.devices), C.byref(self.h)))
+        self._numiters = 0
+        self._nsamps = 0
+
+    def close(self):
+        if self.h:
+            L.lib().qsb_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return int(L.lib().qsb_group_size(self.h))
+
+    def init(self):
+        L.check(L.lib().qsb_group_init(self.h))
+
+    def _tabulate_schedule(self, numiters):
+        if self.kernel.anneal is not None:
+            t = np.ascontiguousarray([float(self.kernel.anneal(i, numiters)) for i in range(numiters)], dtype=np.float64)
+            for i in range(self.size()):
+                L.check(L.lib().qsb_sampler_set_temperatures(L.lib().qsb_group_sampler(self.h, i), t.ctypes.data_as(L.dp), len(t)))
+
+    def run(self, nsamps, burnin=0, lag=1):
+        self._numiters = burnin + nsamps * lag
+        self._nsamps = nsamps
+        self._tabulate_schedule(self._numiters)
+        L.check(L.lib().qsb_group_run(self.h, nsamps, burnin, lag))
+
+    def begin(self, max_samples, burnin=0, lag=1, numiters=0):
+        self._numiters = numiters
+        self._tabulate_schedule(numiters)
+        L.check(L.lib().qsb_group_begin(self.h, max_samples, burnin, lag, numiters))
+
+    def advance(self, iters):
+        L.check(L.lib().qsb_group_advance(self.h, iters))
+
+    def sync(self):
+        L.check(L.lib().qsb_group_sync(self.h))
+
+    def num_samples(self):
+        return int(L.lib().qsb_sampler_num_samples(L.lib().qsb_group_sampler(self.h, 0)))
+
+    def sample_dtype(self):
+        return np.dtype([("value", np.float64, (self.retdim,)), ("logprob", np.float64), ("loglikelihood", np.float64)])
+
+    def fetch_samples(self, chain_begin=0, chain_end=None, sample_begin=0, sample_end=None, out=None):
+        chain_end = self.numchains if chain_end is None else chain_end
+        sample_end = self.num_samples() if sample_end is None else sample_end
+        dt = self.sample_dtype()
+        if out is None:
+            out = np.empty((chain_end - chain_begin, sample_end - sample_begin), dtype=dt)
+        L.check(L.lib().qsb_group_fetch_samples(self.h, chain_begin, chain_end, sample_begin, sample_end,
+                                                out.ctypes.data_as(C.c_void_p), dt.itemsize))
+        return out
+
+    def stats(self):
+        st = L.Stats()
+        L.check(L.lib().qsb_group_stats(self.h, C.byref(st)))
+        n = len(self.kernel.specs)
+        return dict(props_made=st.props_made, props_accepted=st.props_accepted, sub_made=list(st.sub_made)[:n],
+                    sub_accepted=list(st.sub_accepted)[:n], grad_evals=st.grad_evals, leapfrog_steps=st.leapfrog_steps,
+                    iterations=st.iterations, kernel_launches=st.kernel_launches, seconds=st.seconds)
+
+    def diagnostics_raw(self, maxlag=0):
+        """The sufficient statistics of qsb_sampler_diagnostics summed over the shards (NCCL all-reduce inside the library)."""
+        out = np.empty(self.retdim * 12 + (self.retdim * (maxlag + 1) if maxlag > 0 else 0))
+        L.check(L.lib().qsb_group_diagnostics(self.h, maxlag, out.ctypes.data_as(L.dp)))
+        return out
+
+
+class Comm:
+    """One rank of a multi-process job (one process per device): the library's own NCCL communicator.  ``uid`` is the
+    128-byte id rank 0 obtains from :meth:`unique_id` and the launcher distributes to the other ranks."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * L.COMM_ID_BYTES)()
+        L.check(L.lib().qsb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, uid, rank, nranks, device=-1):
+        buf = (C.c_uint8 * L.COMM_ID_BYTES).from_buffer_copy(uid)
+        self.h = C.c_void_p()
+        self.rank, self.nranks = rank, nranks
+        L.check(L.lib().qsb_comm_create(buf, rank, nranks, device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            L.lib().qsb_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def allreduce_sum(self, dev_ptr, n, stream=None):
+        L.check(L.lib().qsb_comm_allreduce_sum(self.h, C.c_void_p(dev_ptr), n, C.c_void_p(stream) if stream else None))
+
+    def diagnostics_raw(self, sampler, maxlag=0):
+        out = np.empty(sampler.retdim * 12 + (sampler.retdim * (maxlag + 1) if maxlag > 0 else 0))
+        L.check(L.lib().qsb_sampler_diagnostics_allreduce(sampler.h, self.h, maxlag, out.ctypes.data_as(L.dp)))
+        return out
+
+
+def measure_fp64_peak(which="dmma", seconds=0.3, device=-1):
+    """TFLOP/s of dependent DFMA chains ("dfma") or mma.sync.m8n8k4.f64 ("dmma") on this device, measured now."""
+    v = C.c_double()
+    L.check(L.lib().qsb_measure_fp64_peak(1 if which == "dmma" else 0, float(seconds), int(device), C.byref(v)))
+    return v.value
+
+
+def source_hash():
+    return L.lib().qsb_source_hash().decode()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -286,13 +428,17 @@ def MCMC(kernel, params=None, **kw):
     seed = int(p.get("seed", 0))
     device = int(p.get("device", -1))
     chain_begin = int(p.get("chain_begin", 0))
+    devices = p.get("devices", None)              # new: chains block-partitioned over these devices (one host thread, qsb_group)
 
     def method(program):
         assert isinstance(program, Program), "MCMC: argument is not a qs.program"
 
         def doMCMC(samples=None):
             out = sys.stdout if verbose is True else (verbose or None)
-            s = Sampler(program, kernel, numchains=numchains, seed=seed, device=device, chain_begin=chain_begin)
+            if devices is not None and len(devices) > 0:
+                s = Group(program, kernel, devices, numchains=numchains, seed=seed, chain_begin=chain_begin)
+            else:
+                s = Sampler(program, kernel, numchains=numchains, seed=seed, device=device, chain_begin=chain_begin)
             try:
                 s.init()
                 t0 = time.time()
@@ -309,10 +455,19 @@ def MCMC(kernel, params=None, **kw):
             except Exception:
                 s.close()
                 raise
-            vec = SampleVector(data, sampler=s)     # the sampler (and its device-resident samples) lives as long as the vector
+            dev_resident = s if isinstance(s, Sampler) else None    # queries on a group's samples go through the host copy
+            if dev_resident is None:
+                s.close()
+            vec = SampleVector(data, sampler=dev_resident)     # the sampler (and its device-resident samples) lives as long as the vector
             if samples is not None:
-                samples.data = data
-                samples._sampler = s
+                # the reference appends to the caller's vector (samples:insert(), mcmc.t:65); so do we
+                if samples.data is not None and samples.data.size and samples.data.shape[0] == data.shape[0] \
+                        and samples.data.dtype == data.dtype:
+                    samples.data = np.concatenate([samples.data, data], axis=1)
+                    samples._sampler = None            # the device copy holds this run's samples only
+                else:
+                    samples.data = data
+                    samples._sampler = dev_resident
             return vec
         return doMCMC
     return method

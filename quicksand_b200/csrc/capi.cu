@@ -63,6 +63,7 @@ struct qsb_sampler {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   uint64_t iter = 0, burnin = 0, lag = 1, max_samples = 0, numiters = 0;
+  uint64_t iter_base = 0;   // iterations of earlier runs on this chain state: the Philox iteration word keeps counting across qsb_sampler_begin
   uint64_t launches = 0;
   double seconds = 0.0;
   bool inited = false;
@@ -71,6 +72,12 @@ struct qsb_sampler {
   std::vector<cudaEvent_t> tev; size_t tev_used = 0;   // event pairs around the timed launches, folded without stalling the stream
   double* stage = nullptr; size_t stage_bytes = 0;  // device staging of fetch_samples (kept between calls)
   double* temps_dev = nullptr;                      // AnnealingKernel schedule
+  // qsb_sampler_fetch_samples_async: two staging buffers alternate; the gather runs on the compute stream, the D2H copy
+  // on a copy stream, so the copy of one step's draws overlaps the next step's transition
+  cudaStream_t copy_stream = nullptr;
+  double* astage[2] = {nullptr, nullptr}; size_t astage_bytes[2] = {0, 0};
+  cudaEvent_t gathered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+  int aflip = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -288,6 +295,14 @@ extern "C" {
 
 int qsb_version(void) { return QSB_VERSION; }
 const char* qsb_last_error(void) { return g_err.c_str(); }
+#ifndef QSB_SOURCE_HASH
+#define QSB_SOURCE_HASH "unknown"
+#endif
+const char* qsb_source_hash(void) { return QSB_SOURCE_HASH; }
+// internal (multi.cu): not part of include/qsb200.h
+void qsb_set_error_(const char* msg) { g_err = msg ? msg : ""; }
+int qsb_sampler_retdim_(qsb_sampler* s) { return s ? s->m->retdim : -1; }
+void* qsb_sampler_stream_(qsb_sampler* s) { return s ? (void*)s->stream : nullptr; }
 
 int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
   if (!d || !out) return fail(1, "qsb_model_create: null argument");
@@ -596,6 +611,8 @@ int qsb_sampler_destroy(qsb_sampler* s) {
   if (s->glm) glm_sampler_destroy(s->glm);
   else free_run_buffers(s);
   if (s->stage) cudaFree(s->stage);
+  if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+  for (int k = 0; k < 2; ++k) { if (s->astage[k]) cudaFree(s->astage[k]); if (s->gathered[k]) cudaEventDestroy(s->gathered[k]); if (s->copied[k]) cudaEventDestroy(s->copied[k]); }
   if (s->temps_dev) cudaFree(s->temps_dev);
   for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
   s->arena.release();
@@ -618,18 +635,18 @@ static int check_status(qsb_sampler* s) {
 int qsb_sampler_init(qsb_sampler* s) {
   if (!s) return fail(1, "null sampler");
   CU(cudaSetDevice(s->m->device));
-  if (s->glm) { std::string why; if (glm_sampler_init(s->glm, why)) return fail(5, why); s->inited = true; s->iter = 0; return 0; }
+  if (s->glm) { std::string why; if (glm_sampler_init(s->glm, why)) return fail(5, why); s->inited = true; s->iter = 0; s->iter_base = 0; return 0; }
   if (int rc = reset_kernel_state(s)) return rc;
   s->var->init(s->P, s->stream); ++s->launches;
   CU(cudaGetLastError());
-  s->inited = true; s->iter = 0;
+  s->inited = true; s->iter = 0; s->iter_base = 0;
   return 0;
 }
 
 int qsb_sampler_set_state(qsb_sampler* s, const double* x) {
   if (!s || !x) return fail(1, "null argument");
   CU(cudaSetDevice(s->m->device));
-  if (s->glm) { std::string why; if (glm_sampler_set_state(s->glm, x, why)) return fail(5, why); s->inited = true; s->iter = 0; return 0; }
+  if (s->glm) { std::string why; if (glm_sampler_set_state(s->glm, x, why)) return fail(5, why); s->inited = true; s->iter = 0; s->iter_base = 0; return 0; }
   EngineParams& P = s->P;
   const size_t C = P.C, d = P.d;
   std::vector<double> h(C * d);
@@ -640,7 +657,7 @@ int qsb_sampler_set_state(qsb_sampler* s, const double* x) {
   CU(cudaStreamSynchronize(s->stream));
   s->var->rescore(P, s->stream); ++s->launches;
   CU(cudaGetLastError());
-  s->inited = true; s->iter = 0;
+  s->inited = true; s->iter = 0; s->iter_base = 0;
   return 0;
 }
 
@@ -663,6 +680,7 @@ int qsb_sampler_begin(qsb_sampler* s, uint64_t max_samples, uint64_t burnin, uin
   if (lag == 0) return fail(2, "lag must be >= 1");
   CU(cudaSetDevice(s->m->device));
   if (!s->inited) if (int rc = qsb_sampler_init(s)) return rc;
+  s->iter_base += s->iter;   // a further run on the same chain state continues the iteration numbering (fresh random numbers)
   s->iter = 0; s->burnin = burnin; s->lag = lag; s->max_samples = max_samples; s->numiters = numiters;
   if (s->glm) { std::string why; if (glm_sampler_begin(s->glm, max_samples, burnin, lag, numiters, why)) return fail(5, why); return 0; }
   EngineParams& P = s->P;
@@ -708,7 +726,7 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
   if (!s) return fail(1, "null sampler");
   if (iters == 0) return 0;
   CU(cudaSetDevice(s->m->device));
-  if (s->iter + iters >= QSB_ITER_SEARCH) return fail(2, "iteration counter would overflow the Philox iteration word");
+  if (s->iter_base + s->iter + iters >= QSB_ITER_SEARCH) return fail(2, "iteration counter would overflow the Philox iteration word");
   if (s->glm) {
     std::string why;
     if (glm_sampler_advance(s->glm, iters, why)) return fail(5, why);
@@ -722,7 +740,7 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
     if (s->tev.size() >= 8192) { if (int rc = fold_kernel_times(s)) return rc; }
     else for (int i = 0; i < 512; ++i) { cudaEvent_t e; CU(cudaEventCreate(&e)); s->tev.push_back(e); }
   }
-  P.it_begin = s->iter; P.n_iters = iters;
+  P.it_begin = s->iter_base + s->iter; P.n_iters = iters; P.it_origin = s->iter_base;
   CU(cudaEventRecord(s->ev0, s->stream));
   if (timed) CU(cudaEventRecord(s->tev[s->tev_used], s->stream));
   {
@@ -828,6 +846,50 @@ static int fetch_common(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, u
 
 int qsb_sampler_fetch_samples(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, uint64_t s1, void* dst, size_t stride_bytes) {
   return fetch_common(s, c0, c1, s0, s1, dst, stride_bytes, 1);
+}
+int qsb_sampler_fetch_samples_async(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, uint64_t s1, void* dst, size_t stride_bytes) {
+  if (!s || !dst) return fail(1, "null argument");
+  CU(cudaSetDevice(s->m->device));
+  const double *samples, *samp_lp; int G; uint32_t SC; int retdim;
+  if (s->glm) glm_sampler_sample_view(s->glm, &samples, &samp_lp, &G, &SC, &retdim);
+  else { samples = s->P.samples; samp_lp = s->P.samp_lp; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }
+  const uint64_t have = qsb_sampler_num_samples(s);
+  if (c1 > SC || c0 > c1 || s1 > have || s0 > s1) return fail(2, "fetch: chain/sample range out of bounds (chains stored: " + std::to_string(SC) + ", samples kept: " + std::to_string(have) + ")");
+  const int w = retdim + 2;
+  if (stride_bytes < (size_t)w * 8 || stride_bytes % 8) return fail(2, "fetch: stride must be a multiple of 8 and >= element size");
+  const uint64_t ns = s1 - s0; const uint32_t nc = c1 - c0;
+  if (ns == 0 || nc == 0) return 0;
+  const size_t need = (size_t)nc * ns * stride_bytes;
+  if (need > ((size_t)4 << 30)) return fail(2, "fetch_samples_async: at most 4 GiB per call");
+  if (!s->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) { CU(cudaEventCreateWithFlags(&s->gathered[k], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&s->copied[k], cudaEventDisableTiming)); }
+  }
+  const int k = s->aflip; s->aflip ^= 1;
+  if (s->astage_bytes[k] < need) {
+    CU(cudaStreamSynchronize(s->copy_stream));
+    if (s->astage[k]) cudaFree(s->astage[k]);
+    s->astage[k] = nullptr; s->astage_bytes[k] = 0;
+    CU(cudaMalloc((void**)&s->astage[k], need));
+    s->astage_bytes[k] = need;
+  }
+  CU(cudaStreamWaitEvent(s->stream, s->copied[k], 0));      // the copy that last read this staging buffer is done
+  const size_t total = (size_t)nc * ns * w;
+  const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  gather_samples_kernel<<<grid, 256, 0, s->stream>>>(samples, samp_lp, G, SC, retdim, c0, nc, s0, ns, s->astage[k], stride_bytes / 8, 1);
+  ++s->launches;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(s->gathered[k], s->stream));
+  CU(cudaStreamWaitEvent(s->copy_stream, s->gathered[k], 0));
+  CU(cudaMemcpyAsync(dst, s->astage[k], need, cudaMemcpyDeviceToHost, s->copy_stream));
+  CU(cudaEventRecord(s->copied[k], s->copy_stream));
+  return 0;
+}
+int qsb_sampler_fetch_sync(qsb_sampler* s) {
+  if (!s) return fail(1, "null sampler");
+  CU(cudaSetDevice(s->m->device));
+  if (s->copy_stream) CU(cudaStreamSynchronize(s->copy_stream));
+  return 0;
 }
 int qsb_sampler_fetch_values(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, uint64_t s1, double* dst) {
   if (!s) return fail(1, "null sampler");
@@ -1063,6 +1125,66 @@ int qsb_logp_grad(qsb_model* m, const double* x, int32_t n, double* lp_dual, dou
       if (s->var->G == 1) { for (size_t c = 0; c < C; ++c) for (size_t i = 0; i < d; ++i) grad[c * d + i] = g[i * C + c]; }
       else std::copy(g.begin(), g.end(), grad);
     }
+  }
+  qsb_sampler_destroy(s);
+  return rc;
+}
+
+int qsb_debug_leapfrog(qsb_model* m, int32_t n, const double* x, const double* p, const double* g, const double* eps, int32_t last,
+                       double* x_out, double* p_out, double* g_out, double* lp_out) {
+  if (!m || !x || !p || !eps || n <= 0) return fail(1, "bad argument");
+  CU(cudaSetDevice(m->device));
+  if (m->desc.family == QSB_FAM_LOGISTIC) {
+    std::string why;
+    if (glm_debug_leapfrog(&m->glm, n, x, p, g, eps, last, x_out, p_out, g_out, lp_out, why)) return fail(5, why);
+    return 0;
+  }
+  qsb_kernel_spec spec = {QSB_KERNEL_HMC, 0, 1.0, 1, 1.0, 1.0, 0, 0};
+  qsb_run_config cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.numchains = (uint32_t)n; cfg.device = m->device;
+  const char* env = getenv("QSB_TEST_MAPPING");
+  if (env) cfg.reserved = atoi(env);
+  qsb_sampler* s = nullptr;
+  if (int rc = qsb_sampler_create(m, &spec, 1, &cfg, &s)) return rc;
+  int rc = qsb_sampler_set_state(s, x);
+  if (!rc) {
+    const size_t C = n, d = m->desc.dim;
+    const bool tr = s->var->G == 1;   // [n][C] layout
+    DevTmp tmp;
+    double *dp = nullptr, *dg = nullptr, *de = nullptr, *ox = nullptr, *op = nullptr, *og = nullptr, *ol = nullptr;
+    cudaError_t e = tmp.get(&dp, C * d);
+    if (e == cudaSuccess && g) e = tmp.get(&dg, C * d);
+    if (e == cudaSuccess) e = tmp.get(&de, C);
+    if (e == cudaSuccess) e = tmp.get(&ox, C * d);
+    if (e == cudaSuccess) e = tmp.get(&op, C * d);
+    if (e == cudaSuccess) e = tmp.get(&og, C * d);
+    if (e == cudaSuccess) e = tmp.get(&ol, C);
+    std::vector<double> h(C * d);
+    auto up = [&](const double* src, double* dst) {
+      if (tr) { for (size_t c = 0; c < C; ++c) for (size_t i = 0; i < d; ++i) h[i * C + c] = src[c * d + i]; }
+      else std::copy(src, src + C * d, h.begin());
+      return cudaMemcpy(dst, h.data(), 8 * C * d, cudaMemcpyHostToDevice);
+    };
+    auto down = [&](const double* src, double* dst) {
+      cudaError_t e2 = cudaMemcpy(h.data(), src, 8 * C * d, cudaMemcpyDeviceToHost);
+      if (e2 != cudaSuccess) return e2;
+      if (tr) { for (size_t c = 0; c < C; ++c) for (size_t i = 0; i < d; ++i) dst[c * d + i] = h[i * C + c]; }
+      else std::copy(h.begin(), h.end(), dst);
+      return e2;
+    };
+    if (e == cudaSuccess) e = up(p, dp);
+    if (e == cudaSuccess && g) e = up(g, dg);
+    if (e == cudaSuccess) e = cudaMemcpy(de, eps, 8 * C, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      DebugLeap D{dp, dg, de, ox, op, og, ol, last ? 1 : 0};
+      s->var->debug_leap(s->P, D, s->stream);
+      e = cudaStreamSynchronize(s->stream);
+    }
+    if (e == cudaSuccess && x_out) e = down(ox, x_out);
+    if (e == cudaSuccess && p_out) e = down(op, p_out);
+    if (e == cudaSuccess && g_out) e = down(og, g_out);
+    if (e == cudaSuccess && lp_out) e = cudaMemcpy(lp_out, ol, 8 * C, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(100 + (int)e, cudaGetErrorString(e));
   }
   qsb_sampler_destroy(s);
   return rc;

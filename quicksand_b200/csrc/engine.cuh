@@ -80,8 +80,11 @@ struct EngineParams {
   unsigned long long *made, *acc;   // [nsub][C]
   unsigned long long* counters;     // [0] gradient evaluations, [1] leapfrog steps (inside :next)
   int* status;                      // sticky error bits
-  // run window
-  uint64_t it_begin, n_iters, burnin, lag;
+  // run window.  Iterations are numbered continuously over the life of the chain state (the Philox iteration word and
+  // HARM's 1/(iter+1) gain never restart, so a second run on the same sampler does not replay its random numbers);
+  // it_origin = number of the first iteration of the current run: burn-in, lag, sample slots and the temperature
+  // schedule count from it.
+  uint64_t it_begin, n_iters, burnin, lag, it_origin;
   // AnnealingKernel (mcmc.t:297-319): temperature of iteration i = temps[min(i, ntemps-1)]; nullptr = 1
   const double* temps; uint64_t ntemps;
   // kept samples
@@ -610,6 +613,7 @@ template <int FAM, int G, int NPL> struct Chain {
     double lastx = P.da_x0[c] - muk * gbar;
     // DualAverage.xbar (hmc.t:44-46: xbar = k^-0.75 * lastx + (1 - k^-0.75) * xbar) is written by the reference but never
     // read: not computed here -- it would cost a pow() per transition for a value nothing observes
+    if (G == 32) __syncwarp();   // every lane has read the chain's adapter state before the leader overwrites it
     if (leader()) { P.da_k[c] = k; P.da_gbar[c] = gbar; P.da_lastx[c] = lastx; }
     return exp(lastx);
   }
@@ -1457,7 +1461,8 @@ template <int FAM, int G, int NPL> struct Chain {
   template <bool HAS_HMC, bool LEX, bool DRIFT_ONLY>
   __device__ __forceinline__ void iterate(uint64_t it) const {
     const uint32_t iter = (uint32_t)it;
-    if (P.temps) { T = P.temps[it < P.ntemps ? it : P.ntemps - 1]; invT = 1.0 / T; }   // AnnealingKernel:next (mcmc.t:308-311)
+    const uint64_t lit = it - P.it_origin;       // iteration of this run (mcmc.t:57: i = 0 .. iters-1)
+    if (P.temps) { T = P.temps[lit < P.ntemps ? lit : P.ntemps - 1]; invT = 1.0 / T; }   // AnnealingKernel:next (mcmc.t:308-311)
     int k = 0;
     if (P.nsub > 1) {   // MixtureKernel:next (mcmc.t:275-287) + categorical_array.sample (distrib.t:281-292)
       double sum = 0.0;
@@ -1488,7 +1493,7 @@ template <int FAM, int G, int NPL> struct Chain {
     }
     else accept = STREAM ? harm_next_stream(k, iter, rdh, rstep) : harm_next(k, iter, rdh, rstep);
     if (G == 32) __syncwarp();
-    const bool keep = it >= P.burnin && (it % P.lag) == 0 && c < P.sample_chains && P.samples != nullptr;
+    const bool keep = lit >= P.burnin && (lit % P.lag) == 0 && c < P.sample_chains && P.samples != nullptr;
     if (keep || P.rec_state) {
       double x[NPL];
       load(P.x, x);
@@ -1501,7 +1506,7 @@ template <int FAM, int G, int NPL> struct Chain {
         }
       }
       if (keep) {
-        const uint64_t sidx = it / P.lag - (P.burnin + P.lag - 1) / P.lag;
+        const uint64_t sidx = lit / P.lag - (P.burnin + P.lag - 1) / P.lag;
         if (sidx < P.max_samples) {
           const uint32_t SC = P.sample_chains;
           if (FAM == FAM_INDEP) {
@@ -1674,6 +1679,51 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) logp_grad_kernel(const __g
   if (ch.leader()) { P.lp[grp] = lpd; P.eps[grp] = lpf; }
 }
 
+// test hook (qsb_debug_leapfrog): exactly one HMCKernel:step (hmc.t:307-323) from an injected (x, p, eps[, g]) with the
+// device functions the transition kernels use -- Chain::leapfrog for the register form, GradScalars + kick for the
+// scalar-gradient warp form.  `last` selects the variant a trajectory runs on its last step (log-density evaluated with
+// the reference's expressions) or on its interior steps (gradient only).  Arrays are laid out like P.x.
+struct DebugLeap {
+  const double* p; const double* g; const double* eps;   // g == nullptr: gradient recomputed at x
+  double *x_out, *p_out, *g_out, *lp_out;
+  int last;
+};
+template <int FAM, int G, int NPL>
+__global__ void __launch_bounds__(G == 1 ? 128 : 256) debug_leap_kernel(const __grid_constant__ EngineParams P, const DebugLeap D) {
+  const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
+  if (FAM == FAM_GAUSS_PREC) {
+    extern __shared__ double qsb_zbuf[];
+    double* sS = qsb_zbuf + (size_t)Chain<FAM, G, NPL>::NB * blockDim.x;
+    for (int t = threadIdx.x; t < NPL * NPL; t += blockDim.x) sS[t] = P.Sc[t & 255];
+    __syncthreads();
+  }
+  if (grp >= P.C) return;
+  Chain<FAM, G, NPL> ch(P, grp);
+  const int lane = ch.lane;
+  double x[NPL], p[NPL], g[NPL];
+  ch.load(P.x, x); ch.load(D.p, p);
+  const double eps = D.eps[grp];
+  double lp = 0.0;
+  if constexpr (Chain<FAM, G, NPL>::SCALAR_GRAD) {
+    const double he = 0.5 * eps;
+    GradScalars<FAM> gs;
+    gs.template reduce<G, NPL>(P, lane, x);
+    ch.kick(he, gs, x, p, false, 1.0);
+    QSB_FOR_E x[e] = x[e] + eps * p[e] * 1.0;
+    gs.template reduce<G, NPL>(P, lane, x);
+    ch.kick(he, gs, x, p, false, 1.0);
+    QSB_FOR_E g[e] = gs.elem(P, e * G + lane, x[e]);
+    if (D.last) lp = ch.lp_only(x);
+  } else {
+    if (D.g) ch.load(D.g, g);
+    else { double lpf; model_eval<FAM, G, NPL, true, true, FAM == FAM_GAUSS_PREC>(P, lane, x, g, lpf); }
+    if (D.last) lp = ch.template leapfrog<true>(eps, x, g, p);
+    else ch.template leapfrog<false>(eps, x, g, p);
+  }
+  ch.store(D.x_out, x); ch.store(D.p_out, p); ch.store(D.g_out, g);
+  if (ch.leader()) D.lp_out[grp] = lp;
+}
+
 // host-side launcher table entry
 struct EngineVariant {
   int family, G, npl;
@@ -1684,6 +1734,7 @@ struct EngineVariant {
   void (*init)(const EngineParams&, void* stream);
   void (*rescore)(const EngineParams&, void* stream);
   void (*logp_grad)(const EngineParams&, void* stream);
+  void (*debug_leap)(const EngineParams&, const DebugLeap&, void* stream);
 };
 
 }  // namespace qsb

@@ -27,7 +27,11 @@ template <int FAM, int G, int NPL> struct VariantImpl {
   static void init(const EngineParams& P, void* st) { init_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void rescore(const EngineParams& P, void* st) { rescore_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void logp_grad(const EngineParams& P, void* st) { logp_grad_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
-  static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &advance_nohmc, &advance_lex, &advance_drift, &init, &rescore, &logp_grad}; }
+  static void debug_leap(const EngineParams& P, const DebugLeap& D, void* st) {
+    constexpr size_t SMEM = FAM == FAM_GAUSS_PREC ? ((size_t)Chain<FAM, G, NPL>::NB * TPB + NPL * NPL) * sizeof(double) : 0;
+    debug_leap_kernel<FAM, G, NPL><<<grid(P), TPB, SMEM, (cudaStream_t)st>>>(P, D);
+  }
+  static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &advance_nohmc, &advance_lex, &advance_drift, &init, &rescore, &logp_grad, &debug_leap}; }
 };
 
 }  // namespace qsb

@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------
 // Vector kernels: one warp per chain, lanes over dimensions.
 enum { V_INIT_SAMPLE = 0, V_FINISH_EVAL = 1, V_TRANS_FIRST = 2, V_TRANS_MID = 3, V_TRANS_LAST = 4, V_PROBE_FIRST = 5, V_PROBE_LAST = 6,
-       V_MH_PROPOSE = 7, V_MH_ACCEPT = 8 };
+       V_MH_PROPOSE = 7, V_MH_ACCEPT = 8, V_DEBUG_FIRST = 9, V_DEBUG_LAST = 10 };
 
 struct VecParams {
   RngKey key; uint32_t chain_begin, C; int d, Dp, ksplit;
@@ -625,6 +625,22 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
   }
   const double eps = P.eps[c];
   const double he = 0.5 * eps;
+  if (MODE == V_DEBUG_FIRST) {   // qsb_debug_leapfrog: first half-kick and drift of one step from injected (x, p, g, eps)
+    for (int i = lane; i < d; i += 32) {
+      double m = p[i] + he * g[i];
+      double pos = x[i] + eps * m * 1.0;
+      p[i] = m; xs[i] = pos;
+    }
+    return;
+  }
+  if (MODE == V_DEBUG_LAST) {    // ... gradient at the new position, second half-kick; lp when the step is a trajectory's last
+    for (int i = lane; i < d; i += 32) {
+      double gn = finish_grad(P, c, i, xs[i]);
+      gs[i] = gn; p[i] = p[i] + he * gn;
+    }
+    if (P.keep) { double lp = finish_lp(P, c, lane, xs); if (lane == 0) P.lp[c] = lp; }
+    return;
+  }
   if (MODE == V_TRANS_FIRST || MODE == V_PROBE_FIRST) {
     if (MODE == V_PROBE_FIRST && P.done[c]) return;
     // sampleMomenta, initial Hamiltonian, first half-kick and drift (hmc.t:140-149, 307-315)
@@ -749,6 +765,7 @@ struct GlmSampler {
   uint32_t flags = 0;
   bool searched = false;
   uint64_t iter = 0, burnin = 0, lag = 1, max_samples = 0, rec_iters = 0;
+  uint64_t iter_base = 0;   // iterations of earlier runs on this chain state (the Philox iteration word keeps counting across begins)
   uint64_t grad_evals = 0, leapfrogs = 0, launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int nj_inst = 0;
@@ -984,7 +1001,7 @@ static int reset_chain_state(GlmSampler* s, std::string& why) {
     GCU(cudaMemcpyAsync(V.ha_scale, sc.data(), 8 * C, cudaMemcpyHostToDevice, s->stream));
     GCU(cudaStreamSynchronize(s->stream));
   }
-  s->searched = false; s->iter = 0; s->grad_evals = 0; s->leapfrogs = 0;
+  s->searched = false; s->iter = 0; s->iter_base = 0; s->grad_evals = 0; s->leapfrogs = 0;
   return 0;
 }
 
@@ -1024,6 +1041,7 @@ int glm_sampler_get_state(GlmSampler* s, double* x, std::string& why) {
 int glm_sampler_begin(GlmSampler* s, uint64_t max_samples, uint64_t burnin, uint64_t lag, uint64_t numiters, std::string& why) {
   VecParams& V = s->V;
   glm_free_run_buffers(s);
+  s->iter_base += s->iter;
   s->iter = 0; s->burnin = burnin; s->lag = lag; s->max_samples = max_samples;
   if (max_samples > 0) {
     GCU(cudaMalloc((void**)&V.samples, 8 * max_samples * V.SC * V.d));
@@ -1087,7 +1105,7 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
     for (uint64_t k = 0; k < iters; ++k) {
       const uint64_t it = s->iter + k;
       VecParams V = s->V;
-      V.iter = (uint32_t)it; V.rec_row = it;
+      V.iter = (uint32_t)(s->iter_base + it); V.rec_row = it;
       V.T = temp_at(s, it); V.invT = 1.0 / V.T;
       GCU(launch_vec<V_MH_PROPOSE>(s, V));
       GCU(run_grad(s, V.xs, 1, 0));
@@ -1115,7 +1133,7 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
   for (uint64_t k = 0; k < iters; ++k) {
     const uint64_t it = s->iter + k;
     VecParams V = s->V;
-    V.iter = (uint32_t)it; V.rec_row = it;
+    V.iter = (uint32_t)(s->iter_base + it); V.rec_row = it;
     V.T = temp_at(s, it); V.invT = 1.0 / V.T;
     GCU(launch_vec<V_TRANS_FIRST>(s, V));
     for (uint32_t st = 0; st < s->L; ++st) {
@@ -1174,6 +1192,44 @@ int glm_sampler_kernel_time(GlmSampler* s, double* seconds, uint64_t* launches, 
   *seconds = s->t_accum; *launches = s->t_launches;
   s->t_accum = 0.0; s->t_launches = 0;
   return 0;
+}
+
+// Test hook: one HMCKernel:step of n injected states through the product's gradient kernel and vector arithmetic.
+int glm_debug_leapfrog(GlmModel* m, int n, const double* x, const double* p, const double* g, const double* eps, int last,
+                       double* x_out, double* p_out, double* g_out, double* lp_out, std::string& why) {
+  GlmSampler* s = glm_sampler_create(m, 1, 1.0, 1, 1.0, false, 0, 0, (uint32_t)n, (uint32_t)n, 0, nullptr, why);
+  if (!s) return 5;
+  int rc = glm_sampler_set_state(s, x, why);   // also evaluates the gradient at x (used when g == nullptr)
+  auto run = [&]() -> int {
+    VecParams V = s->V;
+    const size_t Dp = V.Dp, d = V.d;
+    std::vector<double> h((size_t)n * Dp, 0.0);
+    auto up = [&](const double* src, double* dst) -> cudaError_t {
+      for (int c = 0; c < n; ++c) memcpy(&h[c * Dp], src + c * d, 8 * d);
+      return cudaMemcpy(dst, h.data(), 8 * h.size(), cudaMemcpyHostToDevice);
+    };
+    GCU(up(p, V.p));
+    if (g) GCU(up(g, V.g));
+    GCU(cudaMemcpy(V.eps, eps, 8 * (size_t)n, cudaMemcpyHostToDevice));
+    GCU(launch_vec<V_DEBUG_FIRST>(s, V));
+    GCU(run_grad(s, V.xs, last ? 1 : 0));
+    V.keep = last ? 1 : 0;
+    GCU(launch_vec<V_DEBUG_LAST>(s, V));
+    GCU(cudaStreamSynchronize(s->stream));
+    auto down = [&](const double* src, double* dst) -> cudaError_t {
+      cudaError_t e = cudaMemcpy(h.data(), src, 8 * h.size(), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) for (int c = 0; c < n; ++c) memcpy(dst + c * d, &h[c * Dp], 8 * d);
+      return e;
+    };
+    if (x_out) GCU(down(V.xs, x_out));
+    if (p_out) GCU(down(V.p, p_out));
+    if (g_out) GCU(down(V.gs, g_out));
+    if (lp_out) GCU(cudaMemcpy(lp_out, V.lp, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  if (!rc) rc = run();
+  glm_sampler_destroy(s);
+  return rc;
 }
 
 int glm_logp_grad(GlmModel* m, const double* x, int n, double* lp_dual, double* grad, double* lp_float, std::string& why) {

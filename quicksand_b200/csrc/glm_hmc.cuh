@@ -39,6 +39,8 @@ int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* gr
                       double* seconds, std::string& why);
 int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, double* dh, double* step, double* leap, std::string& why);
 int glm_sampler_kernel_time(GlmSampler* s, double* seconds, uint64_t* launches, std::string& why);
+int glm_debug_leapfrog(GlmModel* m, int n, const double* x, const double* p, const double* g, const double* eps, int last,
+                       double* x_out, double* p_out, double* g_out, double* lp_out, std::string& why);
 int glm_logp_grad(GlmModel* m, const double* x, int n, double* lp_dual, double* grad, double* lp_float, std::string& why);
 
 }  // namespace qsb

@@ -42,29 +42,35 @@ def summarize(raw, retdim, maxlag=0, nshards=1):
             rho = 1.0 - (W_f[:, None] - acov_mean) / vp[:, None]
             rho[:, 0] = 1.0
             tau = np.empty(retdim)
+            hit = np.zeros(retdim, dtype=bool)
             for j in range(retdim):
-                tau[j] = _geyer_tau(rho[j])
+                tau[j], hit[j] = _geyer_tau(rho[j], with_flag=True)
             out["tau"] = tau
+            out["truncated_at_maxlag"] = hit     # the pair sums were still positive at maxlag: tau (and the ESS) is a bound, not an estimate
             out["ess"] = tot / tau
     return out
 
 
-def _geyer_tau(rho):
-    """tau = -1 + 2 * sum of the initial positive, monotone sequence of pair sums P_k = rho_2k + rho_2k+1."""
+def _geyer_tau(rho, with_flag=False):
+    """tau = -1 + 2 * sum of the initial positive, monotone sequence of pair sums P_k = rho_2k + rho_2k+1.
+    with_flag: also return whether the sequence ran into the end of rho (maxlag) before a non-positive pair sum."""
     T = len(rho)
     s = 0.0
     prev = np.inf
     k = 0
+    stopped = False
     while 2 * k + 1 < T:
         P = rho[2 * k] + rho[2 * k + 1]
         if not (P > 0.0):
+            stopped = True
             break
         P = min(P, prev)
         s += P
         prev = P
         k += 1
     tau = -1.0 + 2.0 * s
-    return tau if tau > 1e-3 else 1e-3
+    tau = tau if tau > 1e-3 else 1e-3
+    return (tau, not stopped) if with_flag else tau
 
 
 def ess_numpy(draws, maxlag):

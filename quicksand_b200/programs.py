@@ -91,6 +91,22 @@ class Program:
         return lpd, g, lpf
 
 
+    def debug_leapfrog(self, x, p, eps, g=None, last=False, device=-1):
+        """Test hook (qsb_debug_leapfrog): one HMCKernel:step of n injected states.  Returns dict(x, p, g, lp)."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
+        n = x.shape[0]
+        eps = np.ascontiguousarray(np.broadcast_to(np.asarray(eps, dtype=np.float64), (n,)))
+        gp = None
+        if g is not None:
+            g = np.ascontiguousarray(np.atleast_2d(g), dtype=np.float64)
+            gp = _dp(g)
+        xo, po, go, lpo = np.empty_like(x), np.empty_like(x), np.empty_like(x), np.empty(n)
+        L.check(L.lib().qsb_debug_leapfrog(self.model(device), n, _dp(x), _dp(p), gp, _dp(eps), int(bool(last)),
+                                           _dp(xo), _dp(po), _dp(go), _dp(lpo)))
+        return dict(x=xo, p=po, g=go, lp=lpo)
+
+
 _KIND = {"gaussian": L.ERP_GAUSSIAN, "gamma": L.ERP_GAMMA, "beta": L.ERP_BETA, "uniform": L.ERP_UNIFORM}
 
 

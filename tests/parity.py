@@ -61,15 +61,30 @@ def run_both(program, kernel, chains, iters, seed=1234, chain_begin=0, leap=Fals
     return gpu, cpu
 
 
-def relerr(a, b):
-    """Relative error against max(|a|, |b|, 1); entries where both sides are non-finite in the same way count as equal."""
+TINY = 1e-300
+
+
+def relerr(a, b, floor=TINY):
+    """TRUE relative error |a - b| / max(|a|, |b|, floor), elementwise; entries where both sides are non-finite in the same
+    way count as equal.  ``floor`` (a scalar or an array broadcastable against a) bounds the scale from below: the default
+    only guards 0/0.  For a *vector* quantity (a chain's position) callers pass ``vector_floor``: components that sit
+    below 1e-3 of the vector's largest are the result of cancellation and are held to 1e-10 of that size instead of to
+    1e-10 of their own -- still a relative gate (it scales with the state), never an absolute one."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     with np.errstate(invalid="ignore", over="ignore"):
-        scale = np.maximum(np.maximum(np.abs(a), np.abs(b)), 1.0)
+        scale = np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
         e = np.abs(a - b) / scale
     both_bad = ~np.isfinite(a) & ~np.isfinite(b)
     e = np.where(both_bad, 0.0, e)
     return np.where(np.isnan(e), np.inf, e)
+
+
+def vector_floor(ref, frac=1e-3):
+    """Per-vector floor for relerr: frac * max_i |ref_i| over the last axis (kept for broadcasting)."""
+    r = np.asarray(ref, dtype=np.float64)
+    with np.errstate(invalid="ignore"):
+        m = np.nanmax(np.where(np.isfinite(r), np.abs(r), 0.0), axis=-1, keepdims=True)
+    return np.maximum(frac * m, TINY)
 
 
 def compare(gpu, cpu, tol=1e-10, min_agree=0.999, leap=False, what="", min_compared=1.0, check=True):
@@ -86,9 +101,9 @@ def compare(gpu, cpu, tol=1e-10, min_agree=0.999, leap=False, what="", min_compa
     and matched, and that accept flips stay below 1 - min_agree of them."""
     acc_g, acc_c = gpu["accept"], cpu["accept"]
     C, T = acc_g.shape
-    e_state_all = relerr(gpu["state"], cpu["state"]).max(axis=2)             # [C][T]
+    e_state_all = relerr(gpu["state"], cpu["state"], vector_floor(cpu["state"])).max(axis=2)             # [C][T]
     if leap:
-        e_leap_all = relerr(gpu["leapfrog"], cpu["leapfrog"]).reshape(C, T, -1).max(axis=2)
+        e_leap_all = relerr(gpu["leapfrog"], cpu["leapfrog"], vector_floor(cpu["leapfrog"])).reshape(C, T, -1).max(axis=2)
     else:
         e_leap_all = np.zeros((C, T))
     flip = acc_g != acc_c
@@ -98,10 +113,12 @@ def compare(gpu, cpu, tol=1e-10, min_agree=0.999, leap=False, what="", min_compa
     compared = int(valid.sum())
     flips = int(sum(1 for c in range(C) if first[c] < T and flip[c, first[c]]))
     agree = 1.0 - flips / max(compared + flips, 1)
-    e_init = relerr(gpu["init"], cpu["init"]).max()
+    e_init = relerr(gpu["init"], cpu["init"], vector_floor(cpu["init"])).max()
     e_state = e_state_all[valid].max() if compared else 0.0
     e_leap = e_leap_all[valid].max() if compared else 0.0
     with np.errstate(invalid="ignore"):
+        # dH is a difference of two Hamiltonians (hundreds to thousands in magnitude for the large models): its error is
+        # relative to them, not to itself; reported, not gated (the accept decisions are what is gated)
         e_dh_all = np.abs(gpu["dH"] - cpu["dH"]) / np.maximum(1.0, np.abs(cpu["dH"]))
     fin = valid & np.isfinite(e_dh_all)
     e_dh = e_dh_all[fin].max() if fin.any() else 0.0
@@ -114,3 +131,88 @@ def compare(gpu, cpu, tol=1e-10, min_agree=0.999, leap=False, what="", min_compa
         assert agree >= min_agree, msg
         assert frac >= min_compared - 1e-12, msg
     return dict(init=e_init, state=e_state, dH=e_dh, leap=e_leap, agree=agree, compared=frac, valid=valid)
+
+
+# ---------------------------------------------------------------------------------------------
+def teacher_forced_hmc(program, kernel, chains, iters, seed=1234, chain_begin=0, tol=1e-10, what="", threads=8):
+    """Teacher-forced parity of EVERY leapfrog step of an HMC run, adaptive or not (north_star: per-step leapfrog positions
+    within 1e-10 relative, accept decisions identical).
+
+    The oracle runs the chains and records, for every trajectory, the state entering it (positions, cached gradient,
+    momenta, log-density, step size) and the positions / momenta / gradient after each HMCKernel:step.  Every one of those
+    steps is then replayed on the device from the ORACLE's input state through qsb_debug_leapfrog -- the device functions
+    the transition kernels use -- and compared with the oracle's output state.  No step is skipped: the chaos of the
+    reference's adaptation transient cannot separate the two sides because each step starts from
+    the same numbers.  The accept decision of every trajectory is re-derived from the device's final (p', lp') and the
+    injected uniform and compared as well."""
+    from concurrent.futures import ThreadPoolExecutor
+    spec = kernel.specs[0]
+    assert len(kernel.specs) == 1 and spec.kind == L.KERNEL_HMC
+    Ls = int(spec.numSteps)
+    n = program.dim
+
+    def one(c):
+        return O.run(oracle_program(program), oracle_specs(kernel), seed, 1, iters, 0, 1, chain_begin=chain_begin + c, record=True, traj=True)
+    with ThreadPoolExecutor(max_workers=min(threads, chains)) as ex:      # ctypes drops the GIL; the oracle's state is thread-local
+        outs = list(ex.map(one, range(chains)))
+    cat = lambda k: np.concatenate([o[k] for o in outs], axis=0)
+    x0, g0, p0, lp0 = cat("x0"), cat("g0"), cat("p0"), cat("lp0")
+    pos, mom, grd, lps = cat("leapfrog"), cat("leap_mom"), cat("leap_grad"), cat("leap_lp")
+    eps, dH, acc = cat("step"), cat("dH"), cat("accept")
+    C, T = eps.shape
+    xin = np.concatenate([x0[:, :, None, :], pos[:, :, :-1, :]], axis=2)      # [C][T][L][n]: state entering step s
+    pin = np.concatenate([p0[:, :, None, :], mom[:, :, :-1, :]], axis=2)
+    gin = np.concatenate([g0[:, :, None, :], grd[:, :, :-1, :]], axis=2)
+    ein = np.broadcast_to(eps[:, :, None], (C, T, Ls))
+    fin = np.isfinite(xin).all(axis=3) & np.isfinite(pin).all(axis=3) & np.isfinite(gin).all(axis=3)   # a diverged trajectory may overflow
+    res = {}
+    worst = dict(x=0.0, p=0.0, g=0.0, lp=0.0)
+    nsteps = 0
+    for last in (False, True):
+        sel = np.zeros((C, T, Ls), dtype=bool)
+        if last:
+            sel[:, :, Ls - 1] = True
+        else:
+            sel[:, :, :Ls - 1] = True
+        sel &= fin
+        if not sel.any():
+            continue
+        r = program.debug_leapfrog(xin[sel], pin[sel], ein[sel], g=gin[sel], last=last)
+        nsteps += int(sel.sum())
+        for key, ref in (("x", pos), ("p", mom), ("g", grd)):
+            e = relerr(r[key], ref[sel], vector_floor(ref[sel]))
+            worst[key] = max(worst[key], float(e.max()))
+        if last:
+            worst["lp"] = float(relerr(r["lp"], lps[sel]).max())
+            res["last_sel"] = sel[:, :, Ls - 1]
+            res["p_last"], res["lp_last"] = r["p"], r["lp"]
+    # accept decisions from the device's own final momentum and log-density, the oracle's H0 and the injected uniform
+    flips = 0
+    ntraj = 0
+    e_dh = 0.0
+    if "last_sel" in res:
+        ls = res["last_sel"]
+        H0 = -0.5 * (p0 * p0).sum(axis=2) + lp0
+        dH_dev = (-0.5 * (res["p_last"] ** 2).sum(axis=1) + res["lp_last"]) - H0[ls]
+        u = np.empty((C, T))
+        one_u = np.empty(1)
+        for c in range(C):
+            for t in range(T):
+                L.check(L.lib().qsb_uniforms(seed, chain_begin + c, t, n, 1, one_u.ctypes.data_as(L.dp)))
+                u[c, t] = one_u[0]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            acc_dev = np.log(u[ls]) < dH_dev
+        flips = int((acc_dev != (acc[ls] != 0)).sum())
+        ntraj = int(ls.sum())
+        with np.errstate(invalid="ignore"):
+            scale = np.maximum(np.maximum(np.abs(H0[ls]), np.abs(dH[ls])), 1.0)     # dH is a difference of Hamiltonians of this size
+            ed = np.abs(dH_dev - dH[ls]) / scale
+        e_dh = float(np.nanmax(np.where(np.isfinite(ed), ed, 0.0))) if ed.size else 0.0
+    msg = "%s teacher-forced: %d leapfrog steps (of %d), x %.2e p %.2e g %.2e lp %.2e; %d trajectories, dH %.2e (rel. to H), accept flips %d; accept rate %.2f, eps range [%.3g, %.3g]" % (
+        what, nsteps, C * T * Ls, worst["x"], worst["p"], worst["g"], worst["lp"], ntraj, e_dh, flips, acc.mean(), eps.min(), eps.max())
+    print(msg)
+    assert nsteps >= 0.98 * C * T * Ls, msg          # (steps whose INPUT already overflowed in the oracle cannot be injected)
+    assert worst["x"] <= tol and worst["p"] <= tol, msg
+    assert worst["g"] <= 10 * tol and worst["lp"] <= tol, msg
+    assert flips == 0, msg
+    return dict(worst=worst, steps=nsteps, flips=flips, accept_rate=float(acc.mean()), eps=eps)

@@ -1,0 +1,97 @@
+"""Multi-GPU behind the C ABI (SURVEY.md 8b Threading / 8e): ``qsb_group`` drives several shards of one chain population
+from one host thread; ``qsb_comm`` is the one-process-per-device shape.  Chains are keyed by their global id, so a sharded
+run must reproduce the unsharded one chain for chain; the diagnostics' sufficient statistics are all-reduced inside the
+library (NCCL when the shards sit on different devices, a device kernel when a test box has a single GPU)."""
+import numpy as np
+import pytest
+
+import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _ndev():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _cases(qs):
+    rng = np.random.default_rng(11)
+    X = rng.standard_normal((200, 12)) / np.sqrt(12)
+    y = (rng.random(200) < 0.5).astype(np.uint8)
+    return [
+        ("funnel mixture", qs.programs.funnel(40), qs.MixtureKernel([qs.HARMKernel(), qs.HMCKernel(numSteps=6)], [0.5, 0.5]), 203),
+        ("c2 HMC", qs.programs.c2_correlated_gaussian(10, 0.9)[0], qs.HMCKernel(numSteps=8), 260),
+        ("schools drift", qs.programs.eight_schools(np.linspace(-3, 9, 30), np.linspace(8, 18, 30)), qs.DriftKernel(scale=0.3), 131),
+        ("logistic HMC (tensor-core path)", qs.programs.logistic(X, y, 2.5), qs.HMCKernel(numSteps=5), 192),
+    ]
+
+
+def _check_group_equals_single(qs, devices):
+    from quicksand_b200 import diagnostics as D
+    for name, prog, kernel, chains in _cases(qs):
+        single = qs.Sampler(prog, kernel, numchains=chains, seed=31, device=devices[0])
+        single.init(); single.run(30, 10, 2)
+        ref = single.fetch_samples()
+        ref_raw = single.diagnostics_raw(maxlag=10)
+        ref_st = single.stats()
+        single.close()
+        g = qs.Group(prog, kernel, devices, numchains=chains, seed=31)
+        assert g.size() == len(devices)
+        g.init(); g.run(30, 10, 2)
+        got = g.fetch_samples()
+        raw = g.diagnostics_raw(maxlag=10)
+        st = g.stats()
+        g.close()
+        assert np.array_equal(got["value"], ref["value"]), name          # chain for chain, bit for bit
+        assert np.array_equal(got["logprob"], ref["logprob"]), name
+        for k in ("props_made", "props_accepted", "leapfrog_steps", "grad_evals"):
+            assert st[k] == ref_st[k], (name, k, st[k], ref_st[k])
+        # sufficient statistics: plain sums accumulated in a different order (atomics, shards)
+        assert P.relerr(raw, ref_raw, 1e-9 * np.abs(ref_raw).max()).max() <= 1e-9, name
+        a, b = D.summarize(raw, prog.retdim, 10), D.summarize(ref_raw, prog.retdim, 10)
+        assert np.allclose(a["rhat"], b["rhat"], rtol=1e-9, equal_nan=True) and np.allclose(a["mean"], b["mean"], rtol=1e-9, atol=1e-12)
+
+
+def test_group_of_two_shards_on_one_device_equals_the_unsharded_run(qs):
+    _check_group_equals_single(qs, [0, 0])
+    _check_group_equals_single(qs, [0, 0, 0])       # uneven block partition (203 = 68 + 68 + 67)
+
+
+@pytest.mark.skipif("_ndev() < 2")
+def test_group_of_two_devices_equals_the_unsharded_run(qs):
+    """One host thread, two B200s, the library's own NCCL communicator."""
+    _check_group_equals_single(qs, [0, 1])
+
+
+def test_group_through_the_mcmc_interface(qs):
+    """qs.MCMC(kernel, {numchains=, devices=}) (qs/mcmc.t:36-43 parameter table + devices) returns the same sample vector."""
+    prog = qs.programs.indep([("gaussian", 0.1, 0.5)] * 10, ret_div=10.0)
+    k = qs.HMCKernel(numSteps=10)
+    a = qs.MCMC(k, numsamps=40, lag=2, numchains=64, seed=3)(prog)()
+    b = qs.MCMC(k, numsamps=40, lag=2, numchains=64, seed=3, devices=[0, 0])(prog)()
+    assert np.array_equal(a.value, b.value) and np.array_equal(a.logprob, b.logprob)
+    m = qs.Expectation()(prog)(b)           # queries run on the host copy of a group's samples
+    assert m.shape == (64,)
+
+
+def test_comm_single_rank_allreduce_is_identity(qs):
+    """qsb_comm with one rank: the NCCL communicator is created and the all-reduced diagnostics equal the local ones."""
+    prog = qs.programs.funnel(12)
+    s = qs.Sampler(prog, qs.HARMKernel(), numchains=64, seed=2)
+    s.init(); s.run(20)
+    c = qs.Comm(qs.Comm.unique_id(), 0, 1)
+    a = c.diagnostics_raw(s, maxlag=5)
+    b = s.diagnostics_raw(maxlag=5)
+    assert P.relerr(a, b, 1e-9 * np.abs(b).max()).max() <= 1e-9
+    c.close(); s.close()
+
+
+def test_measured_fp64_peak_is_plausible(qs):
+    dmma, dfma = qs.measure_fp64_peak("dmma", 0.1), qs.measure_fp64_peak("dfma", 0.1)
+    assert 20.0 < dmma < 60.0 and 20.0 < dfma < 60.0, (dmma, dfma)
+
+
+def test_library_is_built_from_this_tree(qs):
+    from quicksand_b200 import build
+    assert qs.source_hash() == build.source_hash()
