@@ -244,8 +244,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=os.environ.get("QSB_WORKLOAD", "c3"))
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU (weak) / in total (strong)")
-    ap.add_argument("--balanced", action="store_true",
-                    help="c3: QSB_FLAG_BALANCED (one equal run of row blocks per SM in the gradient kernel; draws then depend on the chain tile in the last bits)")
+    ap.add_argument("--balanced", action="store_true", help="(no-op: the balanced decomposition of the c3 gradient kernel is the default since round 2)")
+    ap.add_argument("--invariant", action="store_true",
+                    help="c3: QSB_FLAG_INVARIANT (the fixed chain-tile x 12-row-split grid: draws bit-identical for any chain partition; slower on small shards)")
+    ap.add_argument("--roofline-steps", type=int, default=None, help="steps of the separate pass that times every launch of the dominant kernel")
     ap.add_argument("--scaling", default=os.environ.get("QSB_SCALING"), choices=["weak", "strong"],
                     help="strong: the configuration's chain count in total, sharded over the GPUs (default for c3 = BASELINE's 8 192 chains "
                          "at 1/2/4/8 GPUs); weak: that count per GPU (default for c2, c4, c5)")
@@ -305,7 +307,7 @@ def main():
 
     def make_sampler(chains, begin):
         return qs.Sampler(prog, kernel, numchains=chains, seed=SEED, device=local, chain_begin=begin,
-                          flags=L.FLAG_TIME_KERNEL | (L.FLAG_BALANCED if args.balanced else 0), stream=stream, sample_chains=min(chains, SCn))
+                          flags=(L.FLAG_INVARIANT if args.invariant else 0), stream=stream, sample_chains=min(chains, SCn))
 
     def barrier():
         if world > 1:
@@ -337,18 +339,17 @@ def main():
     sampler.init()
     n_keep = K + Ke + (Kd + dlag - 1) // dlag
     # kept draws: the K timed ones, the Ke end-to-end ones (lag 1), then every dlag-th of the Kd diagnostic ones
-    sampler.begin(K + Ke, burnin=B + W, lag=1, numiters=B + W + K + Ke)
+    Kr_plan = args.roofline_steps if args.roofline_steps is not None else min(K, 10)
+    sampler.begin(K + Ke, burnin=B + W, lag=1, numiters=B + W + K + Ke + Kr_plan)
     sampler.advance(B)                      # adaptation / burn-in (untimed set-up; the reference adapts forever, so do we)
     for _ in range(W):
         sampler.advance(1)                  # warm-up steps
     torch.cuda.synchronize()
     st0 = sampler.stats()
-    sampler.kernel_time()                   # reset the dominant-kernel timer
     clocks = ClockSampler(local) if rank == 0 else None
     time.sleep(0.03)
     t = timed_run(sampler, K, clocks)
     clk = clocks.stop() if clocks else None
-    ktime, klaunch = sampler.kernel_time()
     st1 = sampler.stats()
 
     units_local = units_of(st1, st0)
@@ -403,6 +404,20 @@ def main():
             dist.all_reduce(mse, op=dist.ReduceOp.MAX); dist.all_reduce(ucnt)
         e2e_val = ucnt.item() / (mse.item() * 1e-3)
 
+    # ---- roofline pass: the same transitions with a CUDA-event pair around every launch of the dominant kernel (the event
+    # records sit between the launches of a transition and would suppress their programmatic-dependent-launch overlap, so
+    # the throughput above is measured without them); these steps are not kept and not part of `value`
+    Kr = args.roofline_steps if args.roofline_steps is not None else min(K, 10)
+    ktime, klaunch, t_roof, units_roof = 0.0, 0, 0.0, 0
+    if Kr > 0:
+        sampler.set_kernel_timing(True)
+        sampler.kernel_time()               # reset the dominant-kernel timer
+        r0 = sampler.stats()
+        t_roof = timed_run(sampler, Kr)
+        ktime, klaunch = sampler.kernel_time()
+        units_roof = units_of(sampler.stats(), r0)
+        sampler.set_kernel_timing(False)
+
     # ---- diagnostics: an untimed segment of Kd transitions (every dlag-th kept); sufficient statistics on the device,
     # ONE all-reduce(sum) inside the library (qsb_comm), Geyer ESS on the host
     diag = {}
@@ -445,7 +460,7 @@ def main():
             cpu["note"] = ("throughput of the CPU restatement in the metric's unit; a min-ESS/s of the CPU arm is NOT measured (its sample is far "
                            "too short for an autocovariance) -- with the same algorithm and random stream the ESS per transition is the "
                            "same on both sides, so the min-ESS/s ratio equals the throughput ratio")
-        per_launch_units = units_local / max(klaunch, 1)
+        per_launch_units = units_roof / max(klaunch, 1)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: from the ncu --set full captures under
         # profiles/ (a constant of the kernel at that chain count, not measurable outside a profiler); null at other chain counts
         traffic_tab = {"c3": {8192: 40.0e6}, "c2": {65536: 14.6e6}, "c4": {131072: 5.46e9}, "c5": {32768: 0.533e9}}[wl["name"]]
@@ -459,7 +474,9 @@ def main():
         common = {"traffic": traffic_tab.get(C), "traffic_source": "ncu --set full capture under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                   "kernel": "glm_grad_kernel" if wl["name"] == "c3" else "advance_kernel",
                   "kernel_ms_per_launch": 1e3 * ktime / max(klaunch, 1), "kernel_launches_timed": klaunch,
-                  "kernel_share_of_step": ktime / t}
+                  "kernel_share_of_step": (ktime / t_roof) if t_roof else None,
+                  "timing_pass": "%d extra steps after the timed region with a CUDA-event pair around every launch of the kernel "
+                                 "(%.3f ms per step in that pass vs %.3f ms in the timed region)" % (Kr, 1e3 * t_roof / max(Kr, 1), 1e3 * t / K)}
         if wl["bound"] == "hbm":
             achieved = wl["bytes_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e9
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -480,7 +497,7 @@ def main():
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (wl["name"], wl["desc"]), "chains_per_gpu": C, "chains_total": C * world,
                        "burnin_transitions": B, "l2": "working set (chain state + partial sums) larger than L2; inputs change every step",
-                       "seed": SEED, **({"glm_decomposition": "balanced (QSB_FLAG_BALANCED)"} if args.balanced else {})},
+                       "seed": SEED, **({"glm_decomposition": "invariant grid (QSB_FLAG_INVARIANT)"} if args.invariant else {})},
             "secondary": {"metric": "min-ESS/sec", "unit": "effective samples/s",
                           # ESS per kept draw x kept-draw rate of the timed region; only reported for converged chains
                           "value": (min_ess / (nd * dlag) * K / t * (C * world / chains_diag)) if (min_ess and converged) else None,

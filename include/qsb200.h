@@ -113,10 +113,14 @@ enum {
   QSB_FLAG_RECORD = 2u,      /* keep a per-iteration record (state, accept, dH, step, kernel index) -- parity tests */
   QSB_FLAG_RECORD_LEAP = 4u, /* additionally record the position after every leapfrog step (single HMC kernel) */
   QSB_FLAG_TIME_KERNEL = 8u, /* bracket every launch of the dominant kernel with CUDA events (roofline measurement) */
-  QSB_FLAG_BALANCED = 16u    /* LOGISTIC: cut the gradient kernel's work into one equal run of row blocks per SM instead of the
-                              * (chain tile x row split) grid: ~2 % faster on c3, more on small shards; a chain's draws then depend, in
-                              * the last bits, on the tile it sits in (default off: draws are bit-identical for any chain partition
-                              * of equal shard size) */
+  QSB_FLAG_BALANCED = 16u,   /* LOGISTIC: cut the gradient kernel's work into one equal-cost run of row blocks per SM.  This is the
+                              * DEFAULT since round 2 (the flag is accepted and changes nothing): one full wave for any chain count,
+                              * 2-3 partial sums per chain tile.  A chain's draws then depend, in the last bits, on how many chains
+                              * the sampler holds and where the chain sits (still within 1e-10 per step of any other grouping). */
+  QSB_FLAG_INVARIANT = 32u   /* LOGISTIC: the (chain tile x 12 row splits) grid instead: the grouping of a chain's row blocks into
+                              * partial sums depends on the data shape alone, so a chain's draws are bit-identical for ANY
+                              * partition of the chains over samplers / GPUs (every other family is invariant by construction).
+                              * Costs wave quantisation: ~11 % at 1 024 chains per GPU, <1 % at 8 192. */
 };
 
 typedef struct {
@@ -205,6 +209,10 @@ int qsb_sampler_stats(qsb_sampler* s, qsb_stats* out);
 /* QSB_FLAG_TIME_KERNEL: summed device time and launch count of the dominant kernel (the log-density/gradient
  * contraction for LOGISTIC, the fused transition kernel otherwise) since the last call; resets the counters. */
 int qsb_sampler_kernel_time(qsb_sampler* s, double* seconds, uint64_t* launches);
+/* Switch QSB_FLAG_TIME_KERNEL on / off for the following advances.  (The event pairs sit between the launches of a
+ * transition and suppress the programmatic-dependent-launch overlap of the LOGISTIC path: measure throughput with timing
+ * off and the kernel's own duration in a separate pass with timing on.) */
+int qsb_sampler_set_kernel_timing(qsb_sampler* s, int32_t on);
 
 /* Cross-chain sufficient statistics of the kept samples, for split-Rhat / pooled moments / ESS.
  * dst receives, per return-value dimension j (retdim of them), 12 doubles:
@@ -298,6 +306,11 @@ int qsb_sampler_diagnostics_allreduce(qsb_sampler* s, qsb_comm* c, int32_t maxla
 int qsb_measure_fp64_peak(int32_t which, double seconds, int32_t device, double* tflops);
 
 /* ---- test hooks (parity with the CPU oracle) */
+/* Host-only (no device needed): the balanced decomposition the LOGISTIC gradient kernel would use for `numchains` chains and
+ * `nobs` observations on a device of `nsm` SMs.  start [ncta+1] (row-block units, chain-tile-major), first / np [ntiles];
+ * *ntiles, *nblocks, *ncta receive the sizes; arrays may be NULL to query the sizes (capacity = entries available). */
+int qsb_debug_glm_layout(uint32_t numchains, int32_t nobs, int32_t nsm, int32_t capacity, int32_t* start, int32_t* first, int32_t* np,
+                         int32_t* ntiles, int32_t* nblocks, int32_t* ncta);
 /* Teacher-forced leapfrog: exactly one HMCKernel:step (qs/hmc.t:307-323) of n independent injected states, taken with the
  * device functions the transition kernels use (LOGISTIC: the tensor-core gradient kernel).  HOST arrays: x, p [n][dim]
  * unconstrained positions / momenta, eps [n] step sizes, g [n][dim] the cached gradient at x (NULL: recomputed at x).

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("QSB200_LIB") or os.path.join(HERE, "libqsb200.so")   
 FAM_INDEP, FAM_GAUSS_PREC, FAM_LOGISTIC, FAM_EIGHT_SCHOOLS, FAM_FUNNEL = 1, 2, 3, 4, 5
 ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
 KERNEL_HMC, KERNEL_DRIFT, KERNEL_HARM, KERNEL_TRACEMH = 1, 2, 3, 4
-FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL, FLAG_BALANCED = 1, 2, 4, 8, 16
+FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL, FLAG_BALANCED, FLAG_INVARIANT = 1, 2, 4, 8, 16, 32
 
 COMM_ID_BYTES = 128
 dp = C.POINTER(C.c_double)
@@ -72,6 +72,7 @@ PROTOTYPES = {
     "qsb_sampler_fetch_values": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, dp]),
     "qsb_sampler_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "qsb_sampler_kernel_time": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "qsb_sampler_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "qsb_sampler_diagnostics": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "qsb_sampler_fetch_record": (C.c_int, [C.c_void_p, dp, ip, dp, dp, ip, dp]),
     "qsb_query_expectation": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, dp, dp]),
@@ -99,6 +100,7 @@ PROTOTYPES = {
     "qsb_sampler_diagnostics_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, dp]),
     "qsb_measure_fp64_peak": (C.c_int, [C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_double)]),
     "qsb_debug_leapfrog": (C.c_int, [C.c_void_p, C.c_int32, dp, dp, dp, dp, C.c_int32, dp, dp, dp, dp]),
+    "qsb_debug_glm_layout": (C.c_int, [C.c_uint32, C.c_int32, C.c_int32, C.c_int32, ip, ip, ip, ip, ip, ip]),
     "qsb_logp_grad": (C.c_int, [C.c_void_p, dp, C.c_int32, dp, dp, dp]),
     "qsb_logprob": (C.c_int, [C.c_int32, dp, C.c_int32, dp]),
     "qsb_uniforms": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, dp]),

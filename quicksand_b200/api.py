@@ -215,6 +215,9 @@ class Sampler:
                     sub_accepted=list(st.sub_accepted)[:n], grad_evals=st.grad_evals, leapfrog_steps=st.leapfrog_steps,
                     iterations=st.iterations, kernel_launches=st.kernel_launches, seconds=st.seconds)
 
+    def set_kernel_timing(self, on):
+        L.check(L.lib().qsb_sampler_set_kernel_timing(self.h, int(bool(on))))
+
     def kernel_time(self):
         """(seconds, launches) of the dominant kernel since the last call (needs FLAG_TIME_KERNEL)."""
         sec, n = C.c_double(), C.c_uint64()

@@ -67,6 +67,7 @@ struct qsb_sampler {
   uint64_t launches = 0;
   double seconds = 0.0;
   bool inited = false;
+  bool advanced = false;    // ev0 / ev1 have been recorded at least once
   uint64_t rec_iters = 0;
   double t_accum = 0.0; uint64_t t_launches = 0;   // QSB_FLAG_TIME_KERNEL
   std::vector<cudaEvent_t> tev; size_t tev_used = 0;   // event pairs around the timed launches, folded without stalling the stream
@@ -591,11 +592,15 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   P.sample_chains = s->cfg.sample_chains;
   P.lag = 1;
   std::string why;
-  s->var = pick_variant(m->desc.family, P.d, m->dev.has_vector ? 1 : cfg->reserved, why);
+  int mapping = m->dev.has_vector ? 1 : cfg->reserved;
+  // c2-like shapes: four lanes per chain when the chains fill whole warps (8 per warp) and there are enough of them to matter
+  if (mapping == 0 && m->desc.family == QSB_FAM_GAUSS_PREC && cfg->numchains % 8 == 0 && cfg->numchains >= 2048 && !getenv("QSB_NO_G4")) mapping = 4;
+  if (mapping > 1 && mapping < 32 && cfg->numchains % (32 / mapping) != 0) return bail(2, "a mapping of " + std::to_string(mapping) + " lanes per chain needs a chain count that fills whole warps");
+  s->var = pick_variant(m->desc.family, P.d, mapping, why);
   if (!s->var) return bail(2, m->dev.has_vector ? "dirichlet choices and latent parameters run in the thread-per-chain mapping only (" + why + ")" : why);
   if (m->dev.has_vector && cfg->reserved != 0 && cfg->reserved != 1) return bail(2, "dirichlet choices and latent parameters run in the thread-per-chain mapping only");
   if (m->desc.family == QSB_FAM_GAUSS_PREC) {
-    const int d = P.d, npl = s->var->npl;
+    const int d = P.d, npl = s->var->npl * s->var->G;   // row stride of the staged S = padded dimension
     for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) P.Sc[i * npl + j] = m->A[(size_t)i * d + j] + m->A[(size_t)j * d + i];
   }
   if (int rc = alloc_engine_state(s)) { std::string e = g_err; return bail(rc, e); }
@@ -716,6 +721,7 @@ static int fold_kernel_times(qsb_sampler* s) {
   for (size_t i = 0; i + 1 < s->tev_used; i += 2) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s->tev[i], s->tev[i + 1]) == cudaSuccess) { s->t_accum += ms * 1e-3; ++s->t_launches; }
+    else (void)cudaGetLastError();
   }
   s->tev_used = 0;
   return 0;
@@ -765,7 +771,7 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
   if (timed) { CU(cudaEventRecord(s->tev[s->tev_used + 1], s->stream)); s->tev_used += 2; }
   CU(cudaEventRecord(s->ev1, s->stream));
   CU(cudaGetLastError());
-  s->iter += iters;
+  s->iter += iters; s->advanced = true;
   return 0;
 }
 
@@ -923,7 +929,17 @@ int qsb_sampler_stats(qsb_sampler* s, qsb_stats* out) {
   out->grad_evals = counters[0]; out->leapfrog_steps = counters[1];
   out->iterations = s->iter; out->kernel_launches = s->launches;
   float ms = 0.f;
-  if (s->launches && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) out->seconds = ms * 1e-3;
+  // (events that were never recorded make cudaEventElapsedTime fail AND leave that error pending for the next
+  // cudaGetLastError of this thread: only ask once an advance has recorded them, and clear a failure)
+  if (s->advanced) { if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) out->seconds = ms * 1e-3; else (void)cudaGetLastError(); }
+  return 0;
+}
+
+int qsb_sampler_set_kernel_timing(qsb_sampler* s, int32_t on) {
+  if (!s) return fail(1, "null sampler");
+  CU(cudaSetDevice(s->m->device));
+  if (on) s->cfg.flags |= QSB_FLAG_TIME_KERNEL; else s->cfg.flags &= ~(uint32_t)QSB_FLAG_TIME_KERNEL;
+  if (s->glm) glm_sampler_set_timing(s->glm, on != 0);
   return 0;
 }
 
@@ -1188,6 +1204,20 @@ int qsb_debug_leapfrog(qsb_model* m, int32_t n, const double* x, const double* p
   }
   qsb_sampler_destroy(s);
   return rc;
+}
+
+int qsb_debug_glm_layout(uint32_t numchains, int32_t nobs, int32_t nsm, int32_t capacity, int32_t* start, int32_t* first, int32_t* np,
+                         int32_t* ntiles, int32_t* nblocks, int32_t* ncta) {
+  if (numchains == 0 || nobs <= 0 || nsm <= 0 || !ntiles || !nblocks || !ncta) return fail(1, "bad argument");
+  const int CBt = glm_chains_per_tile(), MBr = glm_rows_per_block();
+  const int nt = (int)((numchains + CBt - 1) / CBt), nb = (nobs + MBr - 1) / MBr;
+  std::vector<int> st, fi, npv;
+  const int nc = glm_layout(nt, nb, numchains, nsm, st, fi, npv);
+  *ntiles = nt; *nblocks = nb; *ncta = nc;
+  if (start) { if (capacity < nc + 1) return fail(2, "capacity"); std::copy(st.begin(), st.end(), start); }
+  if (first) { if (capacity < nt) return fail(2, "capacity"); std::copy(fi.begin(), fi.end(), first); }
+  if (np) { if (capacity < nt) return fail(2, "capacity"); std::copy(npv.begin(), npv.end(), np); }
+  return 0;
 }
 
 int qsb_logprob(int32_t which, const double* args, int32_t n, double* out) {

@@ -98,17 +98,19 @@ struct EngineParams {
 };
 
 // ---------------------------------------------------------------------------------------------
+// G lanes per chain, G a power of two in 1..32: a warp holds 32/G chains side by side.  Reductions are xor butterflies over
+// the low log2(G) lane bits, broadcasts are shuffles of width G.  Every lane of the warp must be at the call (kernels only
+// pick 1 < G < 32 when the chain count fills whole warps).
 template <int G> struct Grp {
-  static __device__ __forceinline__ int lane() { return G == 1 ? 0 : (int)(threadIdx.x & 31u); }
+  static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "lanes per chain: a power of two up to 32");
+  static __device__ __forceinline__ int lane() { return G == 1 ? 0 : (int)(threadIdx.x & (unsigned)(G - 1)); }
   static __device__ __forceinline__ double sum(double v) {
-    if (G == 32) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    }
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   }
   static __device__ __forceinline__ double bcast(double v, int src) {
-    if (G == 32) return __shfl_sync(0xffffffffu, v, src);
+    if (G > 1) return __shfl_sync(0xffffffffu, v, src, G);
     return v;
   }
 };
@@ -235,6 +237,33 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
     double lp = 0.0, q = 0.0;
     extern __shared__ double qsb_zbuf[];
     const double* Ssm = qsb_zbuf + (size_t)(2 * ((NPL + 1) / 2)) * blockDim.x;
+    if (G > 1) {
+      // G lanes per chain: lane l owns rows l, l+G, ..; x_j is broadcast from its owner and every lane advances its own rows'
+      // sums in ascending j (the row sums equal the thread-per-chain form's bit for bit; q and lp are reduced over the lanes)
+      constexpr int DP = G * NPL;                    // padded dimension = row stride of the staged S
+      double sx[NPL];
+      QSB_FOR_E sx[e] = 0.0;
+#pragma unroll
+      for (int j = 0; j < DP; ++j) {
+        const double xj = Grp<G>::bcast(x[j / G], j % G);
+        if (j < d) {
+          QSB_FOR_E {
+            const int i = e * G + lane;
+            if (SSM) sx[e] += Ssm[j * DP + i] * xj;            // S symmetric: column j read as the contiguous row j
+            else sx[e] += P.Sc[(j * DP + i) & 255] * xj;
+          }
+        }
+      }
+      QSB_FOR_E {
+        if (e * G + lane < d) {
+          if (LP) { q += x[e] * sx[e]; lp += gaussian_lp(x[e], 0.0, 1.0); }
+          if (GRAD) g[e] = -x[e] - 0.5 * sx[e];
+        } else if (GRAD) g[e] = 0.0;
+      }
+      if (LP) { q = Grp<G>::sum(q); lp = Grp<G>::sum(lp); lp += -0.5 * (0.5 * q); }
+      lp_float = lp;
+      return lp;
+    }
     if (d == NPL) {   // every element live (config c2: n = 10 on the NPL = 10 variant): no per-element predicates
       // column-major sweep: the NPL row sums advance together (NPL independent DFMA chains instead of one chain of NPL
       // dependent DFMAs per row); S is symmetric, so column j is read as the contiguous row j.  Each row still adds its
@@ -458,13 +487,16 @@ template <int FAM> struct ModelStream {
 // LANE_CHAINS (thread per chain): the 32 lanes of the warp own 32 consecutive chains (gc = the chain of lane 0); work item
 // j is component row_begin + (j >> 5) of chain gc + (j & 31) and lands in the same place of the staging array, so the warp
 // shares the attempts of its 32 chains the same way.  Needs all 32 lanes of the warp at the call.
-template <bool LANE_CHAINS>
+template <int G>
 static __device__ __noinline__ void gaussian_fill_warp(uint32_t k0, uint32_t k1, uint32_t gc, uint32_t iter, int row_begin, int n, int rstride) {
+  // work item j: chain q = j % CPW of the warp's CPW = 32/G chains (gc = the chain of lane 0), component row_begin*G + j / CPW;
+  // it belongs to lane q*G + (component % G), row component / G - row_begin.  n = number of work items.
+  constexpr int CPW = 32 / G;
   extern __shared__ double qsb_zbuf[];
   double* zw = qsb_zbuf + (threadIdx.x & ~31u);
   const int lane = (int)(threadIdx.x & 31u);
   const unsigned lt = (1u << lane) - 1u;
-  const uint32_t slot0 = LANE_CHAINS ? (uint32_t)row_begin : (uint32_t)row_begin * 32u;
+  const uint32_t comp0 = (uint32_t)row_begin * (uint32_t)G;
   int j = lane, next = 32;
   uint32_t blk = 0;
   bool active = j < n;
@@ -472,17 +504,17 @@ static __device__ __noinline__ void gaussian_fill_warp(uint32_t k0, uint32_t k1,
     bool ok = false;
     if (active) {
       uint32_t w[4];
-      if (LANE_CHAINS) philox4x32_10(blk, slot0 + ((uint32_t)j >> 5), iter, gc + ((uint32_t)j & 31u), k0, k1, w);
-      else philox4x32_10(blk, slot0 + (uint32_t)j, iter, gc, k0, k1, w);
+      const uint32_t q = (uint32_t)j % (uint32_t)CPW, ci = (uint32_t)j / (uint32_t)CPW;     // chain in the warp, component - comp0
+      philox4x32_10(blk, comp0 + ci, iter, gc + q, k0, k1, w);
       const double u = __dsub_rn(1.0, u53(w[0], w[1]));
       const double v = __dmul_rn(1.7156, __dsub_rn(u53(w[2], w[3]), 0.5));
       const double x = __dsub_rn(u, 0.449871);
       const double y = __dadd_rn(fabs(v), 0.386595);
-      const double q = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, __dsub_rn(__dmul_rn(0.196, y), __dmul_rn(0.25472, x))));
-      if (!(q >= 0.27597)) ok = true;
-      else if (q > 0.27846) ok = false;
+      const double qq = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, __dsub_rn(__dmul_rn(0.196, y), __dmul_rn(0.25472, x))));
+      if (!(qq >= 0.27597)) ok = true;
+      else if (qq > 0.27846) ok = false;
       else ok = !(__dmul_rn(v, v) > __dmul_rn(__dmul_rn(__dmul_rn(-4.0, u), u), log(u)));
-      if (ok) zw[(j >> 5) * rstride + (j & 31)] = v / u;
+      if (ok) zw[(ci / (uint32_t)G) * rstride + q * (uint32_t)G + (ci % (uint32_t)G)] = v / u;
     }
     const unsigned m = __ballot_sync(0xffffffffu, ok);
     if (ok) { j = next + __popc(m & lt); blk = 0; active = j < n; }
@@ -545,14 +577,14 @@ template <int FAM, int G, int NPL> struct Chain {
   __device__ __forceinline__ void gaussian_fill(uint32_t iter, int e_begin, int e_end) const {
     if (G == 32 && !VU) {   // warp per chain: the lanes share the attempts of all components of these rows
       const int hi = e_end * 32 < d ? e_end * 32 : d;
-      gaussian_fill_warp<false>(P.key.k0, P.key.k1, gc, iter, e_begin, hi - e_begin * 32, (int)blockDim.x);
+      gaussian_fill_warp<32>(P.key.k0, P.key.k1, gc, iter, e_begin, hi - e_begin * 32, (int)blockDim.x);
       return;
     }
-    if (G == 1 && !VU && P.nsub == 1 && __activemask() == 0xffffffffu) {
-      // thread per chain, a single kernel (every lane of the warp is at this call) and a full warp: the 32 chains share
-      // their attempts.  Partial tail warps and mixtures (lanes in different sub-kernels) take the per-lane loop below.
-      const int hi = e_end < d ? e_end : d;
-      gaussian_fill_warp<true>(P.key.k0, P.key.k1, gc - (uint32_t)(threadIdx.x & 31u), iter, e_begin, (hi - e_begin) * 32, (int)blockDim.x);
+    if (G < 32 && !VU && P.nsub == 1 && __activemask() == 0xffffffffu) {
+      // several chains per warp, a single kernel (every lane of the warp is at this call) and a full warp: the 32/G chains
+      // share their attempts.  Partial tail warps and mixtures (lanes in different sub-kernels) take the per-lane loop below.
+      const int hi = e_end * G < d ? e_end * G : d;
+      gaussian_fill_warp<G>(P.key.k0, P.key.k1, gc - (uint32_t)((threadIdx.x & 31u) / (unsigned)G), iter, e_begin, (hi - e_begin * G) * (32 / G), (int)blockDim.x);
       return;
     }
     double* z = zcol();
@@ -1548,13 +1580,13 @@ template <int FAM, int G, int NPL> struct Chain {
 // HAS_HMC = true.  The specialised kernels do not carry that code, so their register allocation is not bent by it.
 // DRIFT_ONLY: a single DriftKernel (config c4): no HARM code in the kernel, so the register allocator serves one path.
 template <int FAM, int G, int NPL, bool HAS_HMC, bool LEX = false, bool DRIFT_ONLY = false>
-__global__ void __launch_bounds__(G == 1 || HAS_HMC ? 128 : 256, G == 1 ? 4 : 3)
+__global__ void __launch_bounds__(G < 32 || HAS_HMC ? 128 : 256, G == 1 ? 4 : (G == 32 ? 3 : 5))
 advance_kernel(const __grid_constant__ EngineParams P) {
   const uint32_t grp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
   if (FAM == FAM_GAUSS_PREC) {
     extern __shared__ double qsb_zbuf[];
     double* sS = qsb_zbuf + (size_t)Chain<FAM, G, NPL>::NB * blockDim.x;   // after the Gaussian staging columns
-    for (int t = threadIdx.x; t < NPL * NPL; t += blockDim.x) sS[t] = P.Sc[t & 255];
+    for (int t = threadIdx.x; t < G * NPL * G * NPL; t += blockDim.x) sS[t] = P.Sc[t & 255];
     __syncthreads();
   }
   const bool active = grp < P.C;               // whole warps: C*G and the block size are multiples of 32 or the tail warp idles
@@ -1694,7 +1726,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) debug_leap_kernel(const __
   if (FAM == FAM_GAUSS_PREC) {
     extern __shared__ double qsb_zbuf[];
     double* sS = qsb_zbuf + (size_t)Chain<FAM, G, NPL>::NB * blockDim.x;
-    for (int t = threadIdx.x; t < NPL * NPL; t += blockDim.x) sS[t] = P.Sc[t & 255];
+    for (int t = threadIdx.x; t < G * NPL * G * NPL; t += blockDim.x) sS[t] = P.Sc[t & 255];
     __syncthreads();
   }
   if (grp >= P.C) return;

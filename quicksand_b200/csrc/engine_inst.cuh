@@ -6,11 +6,11 @@
 namespace qsb {
 
 template <int FAM, int G, int NPL> struct VariantImpl {
-  static constexpr int TPB = G == 1 ? 128 : 256;
+  static constexpr int TPB = G == 1 ? 128 : 256;   // (the one-off kernels; any G > 1 runs them at 256)
   static unsigned grid(const EngineParams& P) { return (unsigned)(((size_t)P.C * G + TPB - 1) / TPB); }
   template <bool HAS_HMC, bool LEX = false, bool DRIFT_ONLY = false> static void advance_t(const EngineParams& P, void* st) {
-    constexpr int TPBA = (G == 1 || HAS_HMC) ? 128 : 256;   // must equal advance_kernel's launch bounds
-    constexpr size_t SMEM = ((size_t)Chain<FAM, G, NPL>::NB * TPBA + (FAM == FAM_GAUSS_PREC ? NPL * NPL : 0)) * sizeof(double);   // Gaussian staging columns (+ S)
+    constexpr int TPBA = (G < 32 || HAS_HMC) ? 128 : 256;   // must equal advance_kernel's launch bounds
+    constexpr size_t SMEM = ((size_t)Chain<FAM, G, NPL>::NB * TPBA + (FAM == FAM_GAUSS_PREC ? G * NPL * G * NPL : 0)) * sizeof(double);   // Gaussian staging columns (+ S)
     static bool attr[64] = {};   // the attribute is per device: a process may drive several (qsb_run_config.device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -28,7 +28,7 @@ template <int FAM, int G, int NPL> struct VariantImpl {
   static void rescore(const EngineParams& P, void* st) { rescore_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void logp_grad(const EngineParams& P, void* st) { logp_grad_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void debug_leap(const EngineParams& P, const DebugLeap& D, void* st) {
-    constexpr size_t SMEM = FAM == FAM_GAUSS_PREC ? ((size_t)Chain<FAM, G, NPL>::NB * TPB + NPL * NPL) * sizeof(double) : 0;
+    constexpr size_t SMEM = FAM == FAM_GAUSS_PREC ? ((size_t)Chain<FAM, G, NPL>::NB * TPB + G * NPL * G * NPL) * sizeof(double) : 0;
     debug_leap_kernel<FAM, G, NPL><<<grid(P), TPB, SMEM, (cudaStream_t)st>>>(P, D);
   }
   static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &advance_nohmc, &advance_lex, &advance_drift, &init, &rescore, &logp_grad, &debug_leap}; }

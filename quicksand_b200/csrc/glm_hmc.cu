@@ -57,7 +57,10 @@ static constexpr int GRAD_THREADS = CW * 32;
 struct GradParams {
   const double* Xp; const double* yv;
   int S, d, nj, nblocks, ksplit, ntiles;
-  int sk_U;                // > 0: balanced ("stream-K") decomposition, see glm_grad_kernel; 0: grid = chain tiles x row splits
+  int sk_U;                // > 0: balanced ("stream-K") decomposition, see glm_grad_kernel (the value is the number of CTAs);
+                           // 0: grid = chain tiles x row splits
+  const int* sk_start;     // [sk_U + 1] first row-block unit (tile-major) of every CTA's run
+  const int* sk_first;     // [ntiles] first CTA whose run touches the tile (partial-sum slot = CTA - that)
   uint32_t C; int Dp;
   const double* theta;     // [C][Dp]
   double* partG;           // [ksplit][C][Dp]
@@ -99,6 +102,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Programmatic dependent launch (PDL): every kernel of a transition is launched with programmatic stream serialization, lets
+// its successor start launching at once (pdl_trigger) and touches nothing its predecessor produces before pdl_wait, which
+// returns when the predecessor grid has completed and its writes are visible.  The ~2-3 us launch gap per kernel boundary
+// (41 boundaries per transition) and the gradient kernel's prologue then overlap the tail of the previous kernel.  Without
+// the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   // volatile: keeps the issue order written below (independent accumulators back to back), nothing else
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -201,33 +212,40 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + SD * NST);
   uint64_t* empty = full + STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  bool pdl_pending = true;      // Theta (and the partial-sum buffers this kernel overwrites) belong to the predecessor until pdl_wait
   // Work decomposition.  sk_U == 0: CTA = (chain tile, row split), grid = ntiles x ksplit.  sk_U > 0: the ntiles x nblocks
-  // row-block units, tile-major, are cut into equal runs of sk_U units, one run per CTA (grid ~ number of SMs: one full
-  // wave for any chain count); a run that crosses a tile boundary is worked off as two (or more) segments, and a tile's
-  // segments land in consecutive partial-sum slots (slot = CTA index - index of the first CTA that touches the tile).
+  // row-block units, tile-major, are cut into sk_U runs of equal COST, one run per CTA (grid = number of SMs: one full
+  // wave for any chain count; a unit of the partially filled last tile costs what its live warps cost -- glm_layout()); a
+  // run that crosses a tile boundary is worked off as two (or more) segments, and a tile's segments land in consecutive
+  // partial-sum slots (slot = CTA index - index of the first CTA that touches the tile).
   int& sk_su = *reinterpret_cast<int*>(empty + STAGES);    // first unit of the CTA's next segment (kept out of the register file)
   if (SK) {
-    if (threadIdx.x == 0) sk_su = (int)blockIdx.x * P.sk_U;   // (ntiles x nblocks < 2^31: checked at creation)
+    if (threadIdx.x == 0) sk_su = P.sk_start[blockIdx.x];   // (ntiles x nblocks < 2^31: checked at creation)
     __syncthreads();
   }
   for (;;) {
   int tile, split, b0, b1;
   if (SK) {
-    const int su = sk_su, su_end = min(((int)blockIdx.x + 1) * P.sk_U, P.ntiles * P.nblocks);
+    const int su = sk_su, su_end = P.sk_start[blockIdx.x + 1];
     tile = su / P.nblocks; b0 = su - tile * P.nblocks;
     b1 = min(P.nblocks, b0 + (su_end - su));
-    split = (int)blockIdx.x - (tile * P.nblocks) / P.sk_U;
+    split = (int)blockIdx.x - P.sk_first[tile];
   } else {
     tile = blockIdx.x % P.ntiles; split = blockIdx.x / P.ntiles;
     b0 = (int)(((long)split * P.nblocks) / P.ksplit); b1 = (int)(((long)(split + 1) * P.nblocks) / P.ksplit);
   }
 
+  // warps whose eight chains all lie past the last chain (the tail of the last tile) do no work at all: the stage-release
+  // barriers count the live warps only, so a 64-chain tile costs its SM sub-partitions 2/3 of a full tile's time
+  const int nvw = min(CW, (int)((P.C - (uint32_t)tile * CB + 7u) / 8u));
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nvw); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if ((int)threadIdx.x < NST * 8) sm[SD * (threadIdx.x >> 3) + (size_t)MB * P.S + (threadIdx.x & 7)] = 0.0;   // over-read pads
   if (THETA_SMEM) {   // the chain tile's Theta, [CB][theta_stride]; rows of chains past the end are zero
+    if (pdl_pending) { pdl_wait(); pdl_pending = false; }
     double* sT = sm + SD * NST + BAR_DOUBLES;
     const int Dp = P.Dp, stride = theta_stride(Dp);
     for (int idx = threadIdx.x; idx < CB * Dp; idx += GRAD_THREADS) {
@@ -252,6 +270,9 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   if (threadIdx.x == 0)
     for (int b = b0; b < b1 && b < b0 + NST; ++b) issue_load(b);
 
+  // X and y are model data, not produced by the predecessor kernel: the ring is already filling while we wait for Theta
+  if (pdl_pending) { pdl_wait(); pdl_pending = false; }
+  if (warp < nvw) {
   // ---- consumers: warp w owns chains tile*CB + 8w .. +7; thread (gid, tig) owns dims 8J+2tig+{0,1} of chain gid
   const int gid = lane >> 2, tig = lane & 3;
   const uint32_t chain = (uint32_t)tile * CB + warp * 8 + gid;
@@ -430,10 +451,11 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
     lpacc += __shfl_xor_sync(0xffffffffu, lpacc, 2);
     if (valid && tig == 0) P.partLp[(size_t)split * P.C + chain] = lpacc;
   }
+  }   // warp < nvw
   if (!SK) break;
   __syncthreads();                       // next segment of this CTA's run: the ring starts over
   const int su_next = tile * P.nblocks + b1;
-  if (su_next >= min(((int)blockIdx.x + 1) * P.sk_U, P.ntiles * P.nblocks)) break;
+  if (su_next >= P.sk_start[blockIdx.x + 1]) break;
   if (threadIdx.x == 0) {
     sk_su = su_next;
     for (int s = 0; s < NST; ++s) { mbar_inval(&full[s]); mbar_inval(&empty[s]); }
@@ -449,7 +471,8 @@ enum { V_INIT_SAMPLE = 0, V_FINISH_EVAL = 1, V_TRANS_FIRST = 2, V_TRANS_MID = 3,
 
 struct VecParams {
   RngKey key; uint32_t chain_begin, C; int d, Dp, ksplit;
-  int sk_U, sk_nblocks, sk_CB;   // stream-K decomposition of the gradient kernel (sk_U > 0): partial-sum slots per chain tile vary
+  int sk_U, sk_nblocks, sk_CB;   // balanced decomposition of the gradient kernel (sk_U > 0): partial-sum slots per chain tile vary
+  const int* sk_np;              // [ntiles] number of partial sums of every chain tile
   double prior_sigma;
   double *x, *g, *xs, *gs, *p;                 // [C][Dp]
   const double* partG; const double* partLp;
@@ -477,10 +500,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // number of partial sums the stream-K gradient kernel left for chain c (its tile's segments)
-__device__ __forceinline__ int n_partials_sk(const VecParams& P, uint32_t c) {
-  const long t0 = (long)(c / (uint32_t)P.sk_CB) * P.sk_nblocks;
-  return (int)((t0 + P.sk_nblocks - 1) / P.sk_U - t0 / P.sk_U) + 1;
-}
+__device__ __forceinline__ int n_partials_sk(const VecParams& P, uint32_t c) { return P.sk_np[c / (uint32_t)P.sk_CB]; }
 // gradient and (optionally) log-density of the chain at xs from the partial sums of the GEMM kernel
 __device__ __forceinline__ double finish_grad(const VecParams& P, uint32_t c, int i, double th) {
   double gl = 0.0;
@@ -510,6 +530,8 @@ __device__ __forceinline__ double finish_lp(const VecParams& P, uint32_t c, int 
 template <int MODE>
 __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ VecParams P) {
   const uint32_t c = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  pdl_trigger();
+  pdl_wait();
   if (c >= P.C) return;
   const int lane = threadIdx.x & 31;
   const uint32_t gc = P.chain_begin + c;
@@ -767,6 +789,7 @@ struct GlmSampler {
   uint64_t iter = 0, burnin = 0, lag = 1, max_samples = 0, rec_iters = 0;
   uint64_t iter_base = 0;   // iterations of earlier runs on this chain state (the Philox iteration word keeps counting across begins)
   uint64_t grad_evals = 0, leapfrogs = 0, launches = 0;
+  bool advanced = false;   // ev0 / ev1 recorded at least once
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int nj_inst = 0;
   size_t smem = 0;
@@ -792,6 +815,18 @@ static int pick_ksplit(int ntiles, int nblocks, int nsm) {
   return best;
 }
 
+static bool pdl_enabled() { static const bool on = !getenv("QSB_NO_PDL"); return on; }
+template <class... KArgs, class... Args>
+static cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int NJ, bool FULL, bool LP, bool TRIM = false, bool SK = false> static cudaError_t launch_grad_tf(const GradParams& P, size_t smem, cudaStream_t st) {
   if constexpr (!SK) { if (P.sk_U) return launch_grad_tf<NJ, FULL, LP, TRIM, true>(P, smem, st); }
   static bool attr_set[64] = {};   // per device
@@ -802,9 +837,8 @@ template <int NJ, bool FULL, bool LP, bool TRIM = false, bool SK = false> static
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
-  const int grid = P.sk_U ? (int)(((long)P.ntiles * P.nblocks + P.sk_U - 1) / P.sk_U) : P.ntiles * P.ksplit;
-  glm_grad_kernel<NJ, FULL, LP, TRIM, SK><<<grid, GRAD_THREADS, smem, st>>>(P);
-  return cudaGetLastError();
+  const int grid = P.sk_U ? P.sk_U : P.ntiles * P.ksplit;
+  return launch_ex(glm_grad_kernel<NJ, FULL, LP, TRIM, SK>, (unsigned)grid, GRAD_THREADS, smem, st, pdl_enabled(), P);
 }
 template <int NJ> static cudaError_t launch_grad_t(const GradParams& P, size_t smem, cudaStream_t st) {
   if constexpr (NJ == 13) {   // config c3's shape (d = 100): last tile half empty
@@ -824,6 +858,46 @@ static cudaError_t launch_grad(int nj_inst, const GradParams& P, size_t smem, cu
   return cudaErrorInvalidValue;
 }
 static int pick_nj_inst(int nj) { for (int c : {2, 4, 13, 16}) if (nj <= c) return c; return 0; }
+
+// Balanced decomposition of one gradient launch (see glm_grad_kernel): the ntiles x nblocks row-block units, tile-major, are
+// cut into one run per CTA such that every run costs the same.  A unit of a full chain tile costs CW/4 (warps per SM
+// sub-partition); the last tile may hold fewer chains and its units cost ceil(live warps / 4).  Cuts closer than 3 row
+// blocks to a tile boundary snap to it (a 1-2 block segment is all prologue).  Output: start[ncta+1], first[ntiles] (first
+// CTA touching a tile), np[ntiles] (partial sums of a tile = CTAs touching it); returns ncta.
+int glm_layout(int ntiles, int nblocks, uint32_t C, int nsm, std::vector<int>& start, std::vector<int>& first, std::vector<int>& np) {
+  const long total = (long)ntiles * nblocks;
+  const int WF = CW / 4;
+  const int live_last = std::min<int>(CW, (int)((C - (uint32_t)(ntiles - 1) * CB + 7u) / 8u));
+  const int w_last = (live_last + 3) / 4;
+  const long Ufull = (long)(ntiles - 1) * nblocks;
+  const double Cfull = (double)Ufull * WF, T = Cfull + (double)nblocks * w_last;
+  int ncta = (int)std::min<long>(nsm, std::max<long>(1, total / 12));
+  std::vector<long> cut(ncta + 1, 0);
+  for (int i = 1; i < ncta; ++i) {
+    const double target = T * i / ncta;
+    long u = target <= Cfull ? llround(target / WF) : Ufull + llround((target - Cfull) / w_last);
+    const long r = u % nblocks;
+    if (r && r < 3) u -= r; else if (r && nblocks - r < 3) u += nblocks - r;
+    cut[i] = std::min(std::max(u, cut[i - 1]), total);
+  }
+  cut[ncta] = total;
+  start.clear();
+  for (int i = 0; i < ncta; ++i) if (cut[i + 1] > cut[i]) start.push_back((int)cut[i]);   // CTAs with an empty run are dropped
+  ncta = (int)start.size();
+  start.push_back((int)total);
+  first.assign(ntiles, 0); np.assign(ntiles, 0);
+  for (int t = 0, i = 0; t < ntiles; ++t) {
+    const long lo = (long)t * nblocks, hi = lo + nblocks;
+    while (start[i + 1] <= lo) ++i;           // first run that reaches into the tile
+    int j = i;
+    while (j + 1 < ncta && start[j + 1] < hi) ++j;
+    first[t] = i; np[t] = j - i + 1;
+  }
+  return ncta;
+}
+
+int glm_chains_per_tile() { return CB; }
+int glm_rows_per_block() { return MB; }
 
 int glm_model_create(GlmModel* m, const double* X, const uint8_t* y, int N, int d, double prior_sigma, std::string& why) {
   if (d > 128) { why = "dim <= 128 supported by the tensor-core GLM path"; return 1; }
@@ -899,13 +973,18 @@ GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t 
   G.ntiles = (int)((C + CB - 1) / CB); G.ksplit = pick_ksplit(G.ntiles, G.nblocks, nsm);
   G.C = numchains; G.Dp = m->Dp;
   G.sk_U = 0;
-  const char* env_sk = getenv("QSB_GLM_STREAMK");   // tuning override of QSB_FLAG_BALANCED (0 / 1)
-  if (env_sk ? atoi(env_sk) > 0 : (flags & QSB_FLAG_BALANCED) != 0) {
-    const long total = (long)G.ntiles * G.nblocks;
-    if (total < (1L << 30)) {   // one run of row-block units per SM, at least 12 row blocks per run (prologue/epilogue cost ~0.75 of one)
-      G.sk_U = (int)std::max(12L, (total + nsm - 1) / nsm);
-      G.ksplit = (G.nblocks + G.sk_U - 1) / G.sk_U + 1;   // most partial-sum slots a tile can have
-    }
+  // Default: the balanced decomposition (one equal-cost run of row blocks per SM).  QSB_FLAG_INVARIANT: the (chain tile x
+  // 12 row splits) grid, whose grouping of a chain's row blocks into partial sums depends on nothing but the data shape, so
+  // that a chain's draws are bit-identical for ANY partition of the chains over samplers / GPUs.
+  const char* env_sk = getenv("QSB_GLM_STREAMK");   // tuning override (0 / 1)
+  const bool invariant = env_sk ? atoi(env_sk) == 0 : (flags & QSB_FLAG_INVARIANT) != 0;
+  int* sk_tab = nullptr;
+  std::vector<int> sk_start, sk_first, sk_np;
+  if (invariant) {
+    if (!getenv("QSB_GLM_KSPLIT")) G.ksplit = std::max(1, std::min(12, G.nblocks / 12));
+  } else if ((long)G.ntiles * G.nblocks < (1L << 30)) {
+    G.sk_U = glm_layout(G.ntiles, G.nblocks, numchains, nsm, sk_start, sk_first, sk_np);
+    G.ksplit = *std::max_element(sk_np.begin(), sk_np.end());   // most partial-sum slots a tile has
   }
   s->nj_inst = pick_nj_inst(G.nj);
   G.stages = STAGES;
@@ -916,6 +995,15 @@ GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t 
   V.key = RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)}; V.chain_begin = chain_begin; V.C = numchains; V.d = m->d; V.Dp = m->Dp;
   V.T = 1.0; V.invT = 1.0;
   V.sk_U = G.sk_U; V.sk_nblocks = G.nblocks; V.sk_CB = CB;
+  if (G.sk_U) {
+    std::vector<int> tab(sk_start);
+    tab.insert(tab.end(), sk_first.begin(), sk_first.end());
+    tab.insert(tab.end(), sk_np.begin(), sk_np.end());
+    if (!dalloc(s, &sk_tab, tab.size()) || cudaMemcpy(sk_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+      why = "cudaMalloc failed"; glm_sampler_destroy(s); return nullptr;
+    }
+    G.sk_start = sk_tab; G.sk_first = sk_tab + sk_start.size(); V.sk_np = sk_tab + sk_start.size() + sk_first.size();
+  }
   V.ksplit = G.ksplit; V.prior_sigma = m->prior_sigma; V.L = numSteps; V.adapting = adapt ? 1 : 0; V.stepSize0 = stepSize; V.SC = sample_chains;
   bool ok = dalloc(s, &V.x, C * Dp) && dalloc(s, &V.g, C * Dp) && dalloc(s, &V.xs, C * Dp) && dalloc(s, &V.gs, C * Dp) && dalloc(s, &V.p, C * Dp);
   double *partG = nullptr, *partLp = nullptr;
@@ -952,14 +1040,14 @@ static void glm_collect_times(GlmSampler* s) {
   for (size_t i = 0; i + 1 < s->tev_used; i += 2) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s->tev[i], s->tev[i + 1]) == cudaSuccess) { s->t_accum += ms * 1e-3; ++s->t_launches; }
+    else (void)cudaGetLastError();
   }
   s->tev_used = 0;
 }
 
 template <int MODE> static cudaError_t launch_vec(GlmSampler* s, const VecParams& V) {
-  glm_vec_kernel<MODE><<<(unsigned)(((size_t)V.C * 32 + 255) / 256), 256, 0, s->stream>>>(V);
   ++s->launches;
-  return cudaGetLastError();
+  return launch_ex(glm_vec_kernel<MODE>, (unsigned)(((size_t)V.C * 32 + 255) / 256), 256u, 0, s->stream, pdl_enabled(), V);
 }
 static cudaError_t run_grad(GlmSampler* s, const double* theta, int want_lp, int want_grad = 1) {
   GradParams G = s->Gp;
@@ -1116,7 +1204,7 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
       GCU(launch_vec<V_MH_ACCEPT>(s, V));
     }
     GCU(cudaEventRecord(s->ev1, s->stream));
-    s->iter += iters;
+    s->iter += iters; s->advanced = true;
     return 0;
   }
   if (!s->searched) {
@@ -1151,7 +1239,7 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
     s->leapfrogs += s->L;
   }
   GCU(cudaEventRecord(s->ev1, s->stream));
-  s->iter += iters;
+  s->iter += iters; s->advanced = true;
   return 0;
 }
 
@@ -1170,7 +1258,8 @@ int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* gr
   for (size_t c = 0; c < V.C; ++c) { *made += m[c]; *acc += a[c]; }
   *grad_evals = s->grad_evals * V.C; *leapfrogs = s->leapfrogs * V.C; *launches = s->launches;
   float ms = 0.f;
-  *seconds = (s->iter && cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) ? ms * 1e-3 : 0.0;
+  *seconds = 0.0;
+  if (s->advanced) { if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) *seconds = ms * 1e-3; else (void)cudaGetLastError(); }
   return 0;
 }
 
@@ -1185,6 +1274,10 @@ int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, doub
   if (step) GCU(cudaMemcpy(step, V.rec_step, 8 * C * T, cudaMemcpyDeviceToHost));
   if (leap) { if (!V.rec_leap) { why = "leapfrog positions need QSB_FLAG_RECORD_LEAP"; return 2; } GCU(cudaMemcpy(leap, V.rec_leap, 8 * C * T * s->L * d, cudaMemcpyDeviceToHost)); }
   return 0;
+}
+
+void glm_sampler_set_timing(GlmSampler* s, bool on) {
+  if (on) s->flags |= QSB_FLAG_TIME_KERNEL; else s->flags &= ~(uint32_t)QSB_FLAG_TIME_KERNEL;
 }
 
 int glm_sampler_kernel_time(GlmSampler* s, double* seconds, uint64_t* launches, std::string& why) {

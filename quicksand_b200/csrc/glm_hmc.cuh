@@ -38,7 +38,11 @@ void glm_sampler_sample_view(GlmSampler* s, const double** samples, const double
 int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* grad_evals, uint64_t* leapfrogs, uint64_t* launches,
                       double* seconds, std::string& why);
 int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, double* dh, double* step, double* leap, std::string& why);
+void glm_sampler_set_timing(GlmSampler* s, bool on);
 int glm_sampler_kernel_time(GlmSampler* s, double* seconds, uint64_t* launches, std::string& why);
+int glm_layout(int ntiles, int nblocks, uint32_t C, int nsm, std::vector<int>& start, std::vector<int>& first, std::vector<int>& np);
+int glm_chains_per_tile();
+int glm_rows_per_block();
 int glm_debug_leapfrog(GlmModel* m, int n, const double* x, const double* p, const double* g, const double* eps, int last,
                        double* x_out, double* p_out, double* g_out, double* lp_out, std::string& why);
 int glm_logp_grad(GlmModel* m, const double* x, int n, double* lp_dual, double* grad, double* lp_float, std::string& why);

@@ -164,7 +164,12 @@ def teacher_forced_hmc(program, kernel, chains, iters, seed=1234, chain_begin=0,
     pin = np.concatenate([p0[:, :, None, :], mom[:, :, :-1, :]], axis=2)
     gin = np.concatenate([g0[:, :, None, :], grd[:, :, :-1, :]], axis=2)
     ein = np.broadcast_to(eps[:, :, None], (C, T, Ls))
-    fin = np.isfinite(xin).all(axis=3) & np.isfinite(pin).all(axis=3) & np.isfinite(gin).all(axis=3)   # a diverged trajectory may overflow
+    # A diverged trajectory of the adaptation transient may overflow.  A step is replayed when its oracle INPUT and OUTPUT are
+    # finite; steps past an overflow have no numbers to compare (both sides carry inf / NaN, and the trajectory is rejected on
+    # both -- the accept decisions below are still checked for EVERY trajectory).
+    fin = np.isfinite(xin).all(axis=3) & np.isfinite(pin).all(axis=3) & np.isfinite(gin).all(axis=3)
+    fin &= np.isfinite(pos).all(axis=3) & np.isfinite(mom).all(axis=3) & np.isfinite(grd).all(axis=3)
+    fin_in_last = np.isfinite(xin[:, :, Ls - 1]).all(axis=2) & np.isfinite(pin[:, :, Ls - 1]).all(axis=2) & np.isfinite(gin[:, :, Ls - 1]).all(axis=2)
     res = {}
     worst = dict(x=0.0, p=0.0, g=0.0, lp=0.0)
     nsteps = 0
@@ -175,15 +180,26 @@ def teacher_forced_hmc(program, kernel, chains, iters, seed=1234, chain_begin=0,
         else:
             sel[:, :, :Ls - 1] = True
         sel &= fin
+        if last:
+            sel[:, :, Ls - 1] |= fin_in_last      # the last step is replayed whenever it can be injected: it carries the accept decision
         if not sel.any():
             continue
         r = program.debug_leapfrog(xin[sel], pin[sel], ein[sel], g=gin[sel], last=last)
         nsteps += int(sel.sum())
+        cmp = fin[sel]                               # rows of this batch whose oracle output is finite
         for key, ref in (("x", pos), ("p", mom), ("g", grd)):
-            e = relerr(r[key], ref[sel], vector_floor(ref[sel]))
-            worst[key] = max(worst[key], float(e.max()))
+            e = relerr(r[key][cmp], ref[sel][cmp], vector_floor(ref[sel][cmp]))
+            if e.size:
+                worst[key] = max(worst[key], float(e.max()))
+                if float(e.max()) > tol:
+                    bad = np.argwhere(sel)[cmp][np.argmax(e.max(axis=1))]
+                    print("   worst %s at (chain, iter, step) = %s: eps %.3g |x| %.3g |p| %.3g |g| %.3g err %.3g" % (
+                        key, tuple(bad), eps[bad[0], bad[1]], np.abs(pos[tuple(bad)]).max(), np.abs(mom[tuple(bad)]).max(), np.abs(grd[tuple(bad)]).max(), e.max()))
         if last:
-            worst["lp"] = float(relerr(r["lp"], lps[sel]).max())
+            with np.errstate(invalid="ignore"):
+                okl = cmp & np.isfinite(lps[sel])
+            if okl.any():
+                worst["lp"] = float(relerr(r["lp"][okl], lps[sel][okl]).max())
             res["last_sel"] = sel[:, :, Ls - 1]
             res["p_last"], res["lp_last"] = r["p"], r["lp"]
     # accept decisions from the device's own final momentum and log-density, the oracle's H0 and the injected uniform
@@ -193,14 +209,15 @@ def teacher_forced_hmc(program, kernel, chains, iters, seed=1234, chain_begin=0,
     if "last_sel" in res:
         ls = res["last_sel"]
         H0 = -0.5 * (p0 * p0).sum(axis=2) + lp0
-        dH_dev = (-0.5 * (res["p_last"] ** 2).sum(axis=1) + res["lp_last"]) - H0[ls]
+        with np.errstate(invalid="ignore", over="ignore"):
+            dH_dev = (-0.5 * (res["p_last"] ** 2).sum(axis=1) + res["lp_last"]) - H0[ls]
         u = np.empty((C, T))
         one_u = np.empty(1)
         for c in range(C):
             for t in range(T):
                 L.check(L.lib().qsb_uniforms(seed, chain_begin + c, t, n, 1, one_u.ctypes.data_as(L.dp)))
                 u[c, t] = one_u[0]
-        with np.errstate(invalid="ignore", divide="ignore"):
+        with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
             acc_dev = np.log(u[ls]) < dH_dev
         flips = int((acc_dev != (acc[ls] != 0)).sum())
         ntraj = int(ls.sum())
@@ -211,7 +228,9 @@ def teacher_forced_hmc(program, kernel, chains, iters, seed=1234, chain_begin=0,
     msg = "%s teacher-forced: %d leapfrog steps (of %d), x %.2e p %.2e g %.2e lp %.2e; %d trajectories, dH %.2e (rel. to H), accept flips %d; accept rate %.2f, eps range [%.3g, %.3g]" % (
         what, nsteps, C * T * Ls, worst["x"], worst["p"], worst["g"], worst["lp"], ntraj, e_dh, flips, acc.mean(), eps.min(), eps.max())
     print(msg)
-    assert nsteps >= 0.98 * C * T * Ls, msg          # (steps whose INPUT already overflowed in the oracle cannot be injected)
+    msg += "; %d steps not comparable (oracle state overflowed)" % (C * T * Ls - int(fin.sum()))
+    print(msg)
+    assert int(fin.sum()) >= 0.9 * C * T * Ls, msg    # overflowed steps are the exception, not a way out
     assert worst["x"] <= tol and worst["p"] <= tol, msg
     assert worst["g"] <= 10 * tol and worst["lp"] <= tol, msg
     assert flips == 0, msg

@@ -122,7 +122,7 @@ HMC_FIXED = [
     ("factor1", dict(numSteps=10, stepSize=0.05), 0, 1.0), ("factor6", dict(numSteps=5, stepSize=0.05), 0, 1.0), ("factor6", dict(numSteps=5, stepSize=0.05), 32, 1.0),
     ("mixed10", dict(numSteps=5, stepSize=0.1), 32, 1.0),
     ("hier4", dict(numSteps=10, stepSize=0.05), 0, 1.0), ("hier12", dict(numSteps=5, stepSize=0.02), 0, 0.9), ("hierdir9", dict(numSteps=5, stepSize=0.03), 0, 0.9),
-    ("c2", dict(numSteps=16, stepSize=0.15), 0, 1.0),
+    ("c2", dict(numSteps=16, stepSize=0.15), 0, 1.0), ("c2", dict(numSteps=16, stepSize=0.15), 4, 1.0),   # 4: four lanes per chain
     ("schools13", dict(numSteps=8, stepSize=0.02), 1, 0.95), ("schools13", dict(numSteps=8, stepSize=0.02), 32, 0.95),
     ("schools62", dict(numSteps=8, stepSize=0.02), 0, 0.95),
     ("funnel12", dict(numSteps=16, stepSize=0.01), 1, 0.9), ("funnel12", dict(numSteps=16, stepSize=0.01), 32, 0.9),
@@ -154,7 +154,7 @@ def test_hmc_fixed_step_per_leapfrog_parity(qs, oracle, name, kp, mapping, min_c
 # between two CPU builds of the oracle that differ only in FMA contraction.
 HMC_ADAPT = [
     ("gaussian1", 1, 0, 0.9), ("gaussian1", 10, 0, 0.5), ("gamma1", 10, 0, 0.5), ("beta1", 1, 0, 0.9), ("uniform1", 10, 0, 0.8),
-    ("gauss10", 10, 0, 0.4), ("mixed10", 5, 32, 0.8), ("c2", 16, 0, 0.4), ("dirichlet4", 10, 0, 0.4), ("dirmix9", 1, 0, 0.8),
+    ("gauss10", 10, 0, 0.4), ("mixed10", 5, 32, 0.8), ("c2", 16, 0, 0.4), ("c2", 16, 4, 0.4), ("dirichlet4", 10, 0, 0.4), ("dirmix9", 1, 0, 0.8),
     ("schools13", 1, 32, 0.9), ("schools13", 2, 1, 0.8), ("schools62", 1, 0, 0.9), ("funnel12", 1, 1, 0.9), ("funnel12", 2, 32, 0.8),
     ("funnel70", 1, 0, 0.9), ("logistic20", 1, 0, 0.9), ("logistic20", 2, 0, 0.05), ("hier4", 1, 0, 0.8), ("hier12", 2, 0, 0.3),
     ("schools13", 8, 32, 0.05), ("funnel12", 16, 1, 0.03), ("logistic20", 20, 0, 0.01),
@@ -176,7 +176,7 @@ def test_hmc_adaptive_search_and_dual_averaging(qs, oracle, name, L, mapping, mi
     assert gpu["stats"]["grad_evals"] > 0
 
 
-@pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0),
+@pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("c2", 4), ("schools13", 1), ("schools13", 32), ("schools62", 0),
                                           ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0), ("logistic20", 0), ("factor6", 0), ("factor6", 32),
                                           ("hier4", 0), ("hier12", 0), ("hierdir9", 0)])
 def test_drift_per_step_parity(qs, oracle, name, mapping):
@@ -203,7 +203,7 @@ def test_drift_lexical_scale_sharing_parity(qs, oracle, name, mapping):
         assert not np.array_equal(plain["state"], gpu["state"][:8])
 
 
-@pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("gaussian1", 0), ("c2", 0), ("schools13", 32), ("schools62", 0),
+@pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("gaussian1", 0), ("c2", 0), ("c2", 4), ("schools13", 32), ("schools62", 0),
                                           ("funnel12", 1), ("funnel70", 0), ("dirichlet4", 0), ("logistic20", 0), ("hier4", 0), ("hier12", 0)])
 def test_harm_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
@@ -213,7 +213,7 @@ def test_harm_per_step_parity(qs, oracle, name, mapping):
 
 
 TRACEMH = [("hier4", 0), ("hier12", 0), ("hierdir9", 0), ("factor1", 0), ("factor6", 0), ("factor6", 32), ("gaussian1", 0), ("gamma1", 0), ("beta1", 0), ("uniform1", 0), ("gauss10", 0), ("mixed10", 0), ("mixed10", 32), ("dirichlet4", 0),
-           ("dirmix9", 0), ("wide24", 0), ("c2", 0), ("schools13", 1), ("schools13", 32), ("schools62", 0), ("funnel12", 1), ("funnel12", 32),
+           ("dirmix9", 0), ("wide24", 0), ("c2", 0), ("c2", 4), ("schools13", 1), ("schools13", 32), ("schools62", 0), ("funnel12", 1), ("funnel12", 32),
            ("funnel70", 0)]
 
 
@@ -258,7 +258,7 @@ def test_tracemh_in_mixtures_and_truth(qs, oracle):
         qs.Sampler(_programs(qs)["logistic20"], qs.TraceMHKernel(doStruct=False), numchains=4)
 
 
-@pytest.mark.parametrize("name,mapping,eps", [("funnel12", 1, 0.01), ("funnel70", 0, 0.01), ("gauss10", 0, 0.2), ("schools13", 32, 0.02)])
+@pytest.mark.parametrize("name,mapping,eps", [("funnel12", 1, 0.01), ("funnel70", 0, 0.01), ("gauss10", 0, 0.2), ("schools13", 32, 0.02), ("c2", 4, 0.15)])
 def test_mixture_harm_hmc_parity(qs, oracle, name, mapping, eps):
     """config c5's kernel: MixtureKernel({HARMKernel{}, HMCKernel{numSteps=L}}, {0.5, 0.5}) (mcmc.t:199-291)."""
     prog = _programs(qs)[name]
@@ -295,7 +295,7 @@ def _cooling(i, n):
 
 ANNEAL = [
     ("logistic20", "drift", 0), ("logistic20", "harm", 0),
-    ("c2", "hmc", 0), ("gauss10", "mix3", 0), ("schools13", "drift", 32), ("schools13", "hmc", 32), ("schools13", "hmc", 1),
+    ("c2", "hmc", 0), ("c2", "hmc", 4), ("c2", "mix3", 4), ("gauss10", "mix3", 0), ("schools13", "drift", 32), ("schools13", "hmc", 32), ("schools13", "hmc", 1),
     ("funnel12", "mix", 32), ("funnel12", "mix", 1), ("funnel70", "harm", 0), ("logistic20", "hmc", 0), ("mixed10", "hmc", 32),
 ]
 
@@ -378,11 +378,19 @@ def test_c3_full_shape_gradient_kernel_against_oracle(qs, oracle):
     k = qs.HMCKernel(numSteps=4, stepSize=0.015, doStepSizeAdapt=False)
     gpu, cpu = P.run_both(prog, k, chains=6, iters=4, seed=20261019, leap=True)
     P.compare(gpu, cpu, TOL, leap=True, what="c3 full shape HMC")
-    # a chain's result does not depend on the tile it sits in: 200 chains (2 full tiles + a partial one) vs the same ids in shards
-    full = qs.Sampler(prog, k, numchains=200, seed=5); full.init(); full.run(3)
-    tail = qs.Sampler(prog, k, numchains=10, seed=5, chain_begin=190); tail.init(); tail.run(3)
-    assert np.array_equal(full.fetch_values()[190:], tail.fetch_values())
-    full.close(); tail.close()
+    # QSB_FLAG_INVARIANT: a chain's result depends neither on the tile it sits in nor on how many chains its sampler holds --
+    # 200 chains (2 full tiles + a partial one) vs the same ids in shards of 10 and of 150 chains, bit for bit
+    from quicksand_b200 import _lib as L
+    full = qs.Sampler(prog, k, numchains=200, seed=5, flags=L.FLAG_INVARIANT); full.init(); full.run(3)
+    tail = qs.Sampler(prog, k, numchains=10, seed=5, chain_begin=190, flags=L.FLAG_INVARIANT); tail.init(); tail.run(3)
+    head = qs.Sampler(prog, k, numchains=150, seed=5, chain_begin=0, flags=L.FLAG_INVARIANT); head.init(); head.run(3)
+    fv = full.fetch_values()
+    assert np.array_equal(fv[190:], tail.fetch_values()) and np.array_equal(fv[:150], head.fetch_values())
+    # the default (balanced) decomposition groups the row blocks by the sampler's chain count: equal to rounding only
+    dflt = qs.Sampler(prog, k, numchains=200, seed=5); dflt.init(); dflt.run(3)
+    dv = dflt.fetch_values()
+    assert P.relerr(dv, fv, P.vector_floor(fv)).max() <= 1e-10
+    full.close(); tail.close(); head.close(); dflt.close()
 
 
 def test_shared_and_per_lane_gaussian_fill_agree(qs, oracle):
@@ -710,17 +718,18 @@ def test_latent_parameter_descriptor_errors(qs):
 
 
 def test_glm_stream_k_decomposition_parity(qs, oracle, monkeypatch):
-    """QSB_GLM_STREAMK=1: the gradient kernel's balanced decomposition (equal runs of row-block units per SM, runs crossing
-    chain-tile boundaries, a varying number of partial sums per tile) against the oracle and against the default
-    (chain tile x row split) grid.  The two group a chain's row blocks differently: equal to rounding, not bit for bit --
-    which is why the default keeps the grid whose grouping does not depend on the tile a chain sits in."""
+    """The gradient kernel's balanced decomposition (the default: equal-cost runs of row-block units per SM, runs crossing
+    chain-tile boundaries, a varying number of partial sums per tile, idle tail warps skipped) against the oracle and against
+    the (chain tile x row split) grid of QSB_FLAG_INVARIANT.  The two group a chain's row blocks differently: equal to
+    rounding, not bit for bit."""
+    from quicksand_b200 import _lib as L
     rng = np.random.default_rng(7)
     N, d = 10000, 100
     X = rng.standard_normal((N, d)) / np.sqrt(d)
     y = (rng.random(N) < 1.0 / (1.0 + np.exp(-X @ rng.normal(0, 1, d)))).astype(np.uint8)
     big = qs.programs.logistic(X, y, 2.5)
     k = qs.HMCKernel(numSteps=4, stepSize=0.015, doStepSizeAdapt=False)
-    ref = qs.Sampler(big, k, numchains=300, seed=5); ref.init(); ref.run(3)
+    ref = qs.Sampler(big, k, numchains=300, seed=5, flags=L.FLAG_INVARIANT); ref.init(); ref.run(3)
     ref_vals = ref.fetch_values(); ref.close()
     monkeypatch.setenv("QSB_GLM_STREAMK", "1")
     gpu, cpu = P.run_both(big, k, chains=6, iters=4, seed=20261019, leap=True)
@@ -729,10 +738,13 @@ def test_glm_stream_k_decomposition_parity(qs, oracle, monkeypatch):
     sk_vals = sk.fetch_values(); sk.close()
     assert P.relerr(sk_vals, ref_vals, P.vector_floor(ref_vals)).max() <= 1e-10
     monkeypatch.delenv("QSB_GLM_STREAMK")
-    from quicksand_b200 import _lib as L
-    fl = qs.Sampler(big, k, numchains=300, seed=5, flags=L.FLAG_BALANCED); fl.init(); fl.run(3)       # the public switch: QSB_FLAG_BALANCED
+    fl = qs.Sampler(big, k, numchains=300, seed=5); fl.init(); fl.run(3)       # no flag: the balanced decomposition is the default
     assert np.array_equal(fl.fetch_values(), sk_vals) and not np.array_equal(sk_vals, ref_vals)
     fl.close()
+    monkeypatch.setenv("QSB_GLM_STREAMK", "0")      # the tuning override selects the grid as well
+    g0 = qs.Sampler(big, k, numchains=300, seed=5); g0.init(); g0.run(3)
+    assert np.array_equal(g0.fetch_values(), ref_vals)
+    g0.close()
     monkeypatch.setenv("QSB_GLM_STREAMK", "1")
     small = _programs(qs)["logistic20"]
     for kern, iters, minc in [(qs.HMCKernel(numSteps=7, stepSize=0.1, doStepSizeAdapt=False), 20, 1.0), (qs.DriftKernel(scale=0.3), 100, 1.0),
