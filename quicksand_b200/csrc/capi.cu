@@ -594,7 +594,7 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   std::string why;
   int mapping = m->dev.has_vector ? 1 : cfg->reserved;
   // c2-like shapes: four lanes per chain when the chains fill whole warps (8 per warp) and there are enough of them to matter
-  if (mapping == 0 && m->desc.family == QSB_FAM_GAUSS_PREC && cfg->numchains % 8 == 0 && cfg->numchains >= 2048 && !getenv("QSB_NO_G4")) mapping = 4;
+  if (mapping == 0 && m->desc.family == QSB_FAM_GAUSS_PREC && cfg->numchains % 8 == 0 && getenv("QSB_G4")) mapping = 4;   // (measured 2 x slower than thread per chain at c2's shape: not the default)
   if (mapping > 1 && mapping < 32 && cfg->numchains % (32 / mapping) != 0) return bail(2, "a mapping of " + std::to_string(mapping) + " lanes per chain needs a chain count that fills whole warps");
   s->var = pick_variant(m->desc.family, P.d, mapping, why);
   if (!s->var) return bail(2, m->dev.has_vector ? "dirichlet choices and latent parameters run in the thread-per-chain mapping only (" + why + ")" : why);
@@ -762,10 +762,14 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
     for (int k = 0; k < R.nsub; ++k) has_hmc |= R.kind[k] == K_HMC;
     bool has_mh = false;
     for (int k = 0; k < R.nsub; ++k) has_mh |= R.kind[k] == K_TRACEMH;
+    // warp-per-chain variants run warp-specialised (sampler warps + trajectory warps, engine.cuh: advance_ws_kernel);
+    // QSB_NO_WS=1 selects the fused kernels (every warp samples and integrates) for A/B measurements
+    static const bool ws = !getenv("QSB_NO_WS");
+    const bool use_ws = ws && s->var->advance_ws != nullptr;
     if (R.dr_lexical || has_mh) s->var->advance_lex(R, s->stream);   // the general kernel
-    else if (R.nsub == 1 && R.kind[0] == K_DRIFT) s->var->advance_drift(R, s->stream);
-    else if (has_hmc) s->var->advance(R, s->stream);
-    else s->var->advance_nohmc(R, s->stream);
+    else if (R.nsub == 1 && R.kind[0] == K_DRIFT) (use_ws ? s->var->advance_drift_ws : s->var->advance_drift)(R, s->stream);
+    else if (has_hmc) (use_ws ? s->var->advance_ws : s->var->advance)(R, s->stream);
+    else (use_ws ? s->var->advance_nohmc_ws : s->var->advance_nohmc)(R, s->stream);
   }
   ++s->launches;
   if (timed) { CU(cudaEventRecord(s->tev[s->tev_used + 1], s->stream)); s->tev_used += 2; }

@@ -21,6 +21,7 @@
 #pragma once
 #include <cstdint>
 #include "distrib.cuh"
+#include "mbar.cuh"
 #include "philox.cuh"
 
 namespace qsb {
@@ -99,18 +100,25 @@ struct EngineParams {
 
 // ---------------------------------------------------------------------------------------------
 // G lanes per chain, G a power of two in 1..32: a warp holds 32/G chains side by side.  Reductions are xor butterflies over
-// the low log2(G) lane bits, broadcasts are shuffles of width G.  Every lane of the warp must be at the call (kernels only
-// pick 1 < G < 32 when the chain count fills whole warps).
+// the low log2(G) lane bits, broadcasts are shuffles of width G; both name only the G lanes of the chain in their mask, so
+// the chains of a warp may sit in different branches (mixture kernels, step-size search loops of different length).
 template <int G> struct Grp {
   static_assert(G >= 1 && G <= 32 && (G & (G - 1)) == 0, "lanes per chain: a power of two up to 32");
   static __device__ __forceinline__ int lane() { return G == 1 ? 0 : (int)(threadIdx.x & (unsigned)(G - 1)); }
+  static __device__ __forceinline__ unsigned mask() {
+    if (G == 32) return 0xffffffffu;
+    return ((1u << (G & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
+  }
   static __device__ __forceinline__ double sum(double v) {
+    if (G > 1) {
+      const unsigned m = mask();
 #pragma unroll
-    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    }
     return v;
   }
   static __device__ __forceinline__ double bcast(double v, int src) {
-    if (G > 1) return __shfl_sync(0xffffffffu, v, src, G);
+    if (G > 1) return __shfl_sync(mask(), v, src, G);
     return v;
   }
 };
@@ -120,6 +128,11 @@ template <int G> __device__ __forceinline__ size_t vidx(const EngineParams& P, i
 }
 
 #define QSB_FOR_E _Pragma("unroll") for (int e = 0; e < NPL; ++e)
+// GAUSS_PREC: where the transition kernels read S = A + A^T from: 1 = the copy staged in shared memory (broadcast LDS),
+// 0 = the kernel parameter itself (constant-bank operands of the DFMAs, no load instructions)
+#ifndef QSB_GP_SMEM
+#define QSB_GP_SMEM 1
+#endif
 
 // One ERP site of a dual trace: prior logprob of the constrained value, log-Jacobian, and
 // d(logprob + logJ)/dx  (erp.t:623-640).  Not inlined: the INDEP family is not a throughput path
@@ -488,12 +501,10 @@ template <int FAM> struct ModelStream {
 // j is component row_begin + (j >> 5) of chain gc + (j & 31) and lands in the same place of the staging array, so the warp
 // shares the attempts of its 32 chains the same way.  Needs all 32 lanes of the warp at the call.
 template <int G>
-static __device__ __noinline__ void gaussian_fill_warp(uint32_t k0, uint32_t k1, uint32_t gc, uint32_t iter, int row_begin, int n, int rstride) {
+static __device__ __forceinline__ void gaussian_fill_body(uint32_t k0, uint32_t k1, uint32_t gc, uint32_t iter, int row_begin, int n, double* zw, int rstride) {
   // work item j: chain q = j % CPW of the warp's CPW = 32/G chains (gc = the chain of lane 0), component row_begin*G + j / CPW;
-  // it belongs to lane q*G + (component % G), row component / G - row_begin.  n = number of work items.
+  // it belongs to lane q*G + (component % G), row component / G - row_begin of the staging rows at zw.  n = number of work items.
   constexpr int CPW = 32 / G;
-  extern __shared__ double qsb_zbuf[];
-  double* zw = qsb_zbuf + (threadIdx.x & ~31u);
   const int lane = (int)(threadIdx.x & 31u);
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t comp0 = (uint32_t)row_begin * (uint32_t)G;
@@ -523,21 +534,40 @@ static __device__ __noinline__ void gaussian_fill_warp(uint32_t k0, uint32_t k1,
   }
   __syncwarp();
 }
+// One out-of-line copy per kernel for the fused (every warp samples and integrates) kernels.
+template <int G>
+static __device__ __noinline__ void gaussian_fill_warp(uint32_t k0, uint32_t k1, uint32_t gc, uint32_t iter, int row_begin, int n, double* zw, int rstride) {
+  gaussian_fill_body<G>(k0, k1, gc, iter, row_begin, n, zw, rstride);
+}
+
+// Hand-off between the sampler warps and the trajectory warp of one chain slot in the warp-specialised kernel
+// (advance_ws_kernel): two staging buffers of NPL x 32 standard normals alternate, full[b] / empty[b] are mbarriers.
+struct WsLink {
+  double* zbuf;        // this slot's two buffers (2 x NPL x 32 doubles: row r of buffer b at zbuf + (b * NPL + r) * 32)
+  double* zsearch;     // a third buffer for the trajectory warp's own draws (step-size search probes), or nullptr
+  uint64_t* full; uint64_t* empty;
+  uint32_t k;          // hand-offs consumed so far: buffer k & 1, phase (k >> 1) & 1
+  bool held;           // the trajectory warp currently reads buffer k & 1
+};
 
 // ---------------------------------------------------------------------------------------------
-template <int FAM, int G, int NPL> struct Chain {
+// WS: the chain runs on a trajectory warp of the warp-specialised kernel -- the standard normals of an iteration arrive
+// from the sampler warps through `link` instead of being drawn in place.
+template <int FAM, int G, int NPL, bool WS = false> struct Chain {
   const EngineParams& P;
   const uint32_t c;       // local chain index
   const uint32_t gc;      // global chain id (Philox counter word)
   const int lane;
   const int d;
+  WsLink* const link;
+  mutable const double* zptr = nullptr;   // WS: this lane's column of the staging rows currently being read
   mutable unsigned long long cnt[2] = {0, 0};  // gradient evaluations / leapfrog steps of this group, flushed once per launch
   // currTrace.temperature of this iteration (trace.t:652-655): every log-density evaluated during the iteration is
   // divided by it (trace.t:737-741) and its gradient multiplied by 1/T (the adjoint of that division, ad.t:405-412);
   // values cached from earlier iterations (lp, gradient) keep the temperature they were computed under, as in the reference
   mutable double T = 1.0, invT = 1.0;
-  __device__ __forceinline__ Chain(const EngineParams& P_, uint32_t c_)
-      : P(P_), c(c_), gc(P_.chain_begin + c_), lane(Grp<G>::lane()), d(P_.d) {}
+  __device__ __forceinline__ Chain(const EngineParams& P_, uint32_t c_, WsLink* link_ = nullptr)
+      : P(P_), c(c_), gc(P_.chain_begin + c_), lane(Grp<G>::lane()), d(P_.d), link(link_) {}
 
   __device__ __forceinline__ void load(const double* base, double (&v)[NPL]) const {
     QSB_FOR_E { int i = e * G + lane; v[e] = i < d ? base[vidx<G>(P, i, c)] : 0.0; }
@@ -568,26 +598,57 @@ template <int FAM, int G, int NPL> struct Chain {
   // consumer then reads the rows with compile-time indices.  Warp trips ~ max over lanes of the lane's total attempts.
   static constexpr int HALF = (NPL + 1) / 2;
   static constexpr int NB = 2 * HALF;                 // shared-memory rows per thread
-  __device__ __forceinline__ double* zcol() const {
+  __device__ __forceinline__ const double* zcol() const {
+    if (WS) return zptr;
     extern __shared__ double qsb_zbuf[];
     return qsb_zbuf + threadIdx.x;
+  }
+  __device__ __forceinline__ double* zcol_w() const {
+    extern __shared__ double qsb_zbuf[];
+    return qsb_zbuf + threadIdx.x;
+  }
+  __device__ __forceinline__ int zstride() const { return WS ? 32 : (int)blockDim.x; }
+  // WS: take / give back the staging buffer the sampler warps filled for this iteration
+  __device__ __forceinline__ void ws_acquire() const {
+    const uint32_t b = link->k & 1u;
+    mbar_wait(&link->full[b], (link->k >> 1) & 1u);
+    zptr = link->zbuf + (size_t)b * (NPL * 32) + (threadIdx.x & 31u);
+    link->held = true;
+  }
+  __device__ __forceinline__ void ws_release() const {
+    if (!link->held) return;
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0) mbar_arrive(&link->empty[link->k & 1u]);
+    ++link->k;
+    link->held = false;
   }
   // VU = false: row r (component e_begin + r) <- v/u;  VU = true: row r <- v, row HALF + r <- u
   template <bool VU>
   __device__ __forceinline__ void gaussian_fill(uint32_t iter, int e_begin, int e_end) const {
+    if constexpr (WS) {
+      const int hi = e_end * 32 < d ? e_end * 32 : d;
+      if (iter < QSB_ITER_SEARCH) { ws_acquire(); return; }      // drawn ahead of time by the sampler warps
+      // the probes of the step-size search: drawn in place, into the slot's third buffer
+      gaussian_fill_warp<32>(P.key.k0, P.key.k1, gc, iter, e_begin, hi - e_begin * 32, link->zsearch + e_begin * 32, 32);
+      zptr = link->zsearch + (threadIdx.x & 31u);
+      return;
+    }
     if (G == 32 && !VU) {   // warp per chain: the lanes share the attempts of all components of these rows
       const int hi = e_end * 32 < d ? e_end * 32 : d;
-      gaussian_fill_warp<32>(P.key.k0, P.key.k1, gc, iter, e_begin, hi - e_begin * 32, (int)blockDim.x);
+      extern __shared__ double qsb_zbuf[];
+      gaussian_fill_warp<32>(P.key.k0, P.key.k1, gc, iter, e_begin, hi - e_begin * 32, qsb_zbuf + (threadIdx.x & ~31u), (int)blockDim.x);
       return;
     }
     if (G < 32 && !VU && P.nsub == 1 && __activemask() == 0xffffffffu) {
       // several chains per warp, a single kernel (every lane of the warp is at this call) and a full warp: the 32/G chains
       // share their attempts.  Partial tail warps and mixtures (lanes in different sub-kernels) take the per-lane loop below.
       const int hi = e_end * G < d ? e_end * G : d;
-      gaussian_fill_warp<G>(P.key.k0, P.key.k1, gc - (uint32_t)((threadIdx.x & 31u) / (unsigned)G), iter, e_begin, (hi - e_begin * G) * (32 / G), (int)blockDim.x);
+      extern __shared__ double qsb_zbuf[];
+      gaussian_fill_warp<G>(P.key.k0, P.key.k1, gc - (uint32_t)((threadIdx.x & 31u) / (unsigned)G), iter, e_begin, (hi - e_begin * G) * (32 / G),
+                            qsb_zbuf + (threadIdx.x & ~31u), (int)blockDim.x);
       return;
     }
-    double* z = zcol();
+    double* z = zcol_w();
     const int stride = blockDim.x;
     int e = e_begin;
     uint32_t blk = 0;
@@ -599,18 +660,19 @@ template <int FAM, int G, int NPL> struct Chain {
         ++e; blk = 0;
       } else ++blk;
     }
-    if (G > 1) __syncwarp();
+    if (G == 32) __syncwarp();
   }
 
   // ---- sampleMomenta + kinetic energy (hmc.t:289-305), invMasses == 1
   __device__ __forceinline__ void sample_momenta(uint32_t iter, double (&p)[NPL]) const {
     gaussian_fill<false>(iter, 0, NPL);
     const double* z = zcol();
-    const int stride = blockDim.x;
+    const int stride = zstride();
     QSB_FOR_E {
       int i = e * G + lane;
       p[e] = i < d ? z[e * stride] * 1.0 : 0.0;
     }
+    if constexpr (WS) { if (iter < QSB_ITER_SEARCH) ws_release(); }   // the momenta are in registers: the sampler warps may refill
   }
   __device__ __forceinline__ double kinetic(const double (&p)[NPL]) const {
     double k = 0.0;
@@ -626,7 +688,7 @@ template <int FAM, int G, int NPL> struct Chain {
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     QSB_FOR_E xs[e] = xs[e] + eps * p[e] * 1.0;
     double lpf;
-    double lp = model_eval<FAM, G, NPL, true, LPW, FAM == FAM_GAUSS_PREC>(P, lane, xs, gs, lpf);
+    double lp = model_eval<FAM, G, NPL, true, LPW, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xs, gs, lpf);
     if (T != 1.0) { lp = lp / T; QSB_FOR_E gs[e] = gs[e] * invT; }
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     return lp;
@@ -690,7 +752,7 @@ template <int FAM, int G, int NPL> struct Chain {
     if (!(fl & FLAG_GRAD_VALID)) {
       load(P.x, xs);
       double lpf;
-      double dual_lp = model_eval<FAM, G, NPL, true, true, FAM == FAM_GAUSS_PREC>(P, lane, xs, gs, lpf);
+      double dual_lp = model_eval<FAM, G, NPL, true, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xs, gs, lpf);
       if (P.temps) {
         // hmc.t:254 runs before hmc.t:266: the re-gathered gradient is taken under the temperature the dual trace was
         // left with by the previous HMC call (first call: the copy of currTrace's, hmc.t:218 / trace.t:167-173)
@@ -867,7 +929,7 @@ template <int FAM, int G, int NPL> struct Chain {
     // proposal x'_i = gaussian.sample(x_i, scale_i) = x_i + scale_i*v/u (distrib.t:73), in two passes of HALF components
     {
       const double* z = zcol();
-      const int stride = blockDim.x;
+      const int stride = zstride();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         gaussian_fill<true>(iter, h * HALF, h * HALF + HALF < NPL ? h * HALF + HALF : NPL);
@@ -886,12 +948,12 @@ template <int FAM, int G, int NPL> struct Chain {
             } else xp[e] = 0.0;
           }
         }
-        if (G > 1) __syncwarp();
+        if (G == 32) __syncwarp();
       }
     }
     rec_step = s0;
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false, true, FAM == FAM_GAUSS_PREC>(P, lane, xp, gdummy, lpf);
+    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf);
     if (T != 1.0) lpf = lpf / T;
     const double lp_cur = P.lp[c];
     const double thresh = lpf - lp_cur;
@@ -960,7 +1022,7 @@ template <int FAM, int G, int NPL> struct Chain {
     load(P.x, x);
     {
       const double* z = zcol();
-      const int stride = blockDim.x;
+      const int stride = zstride();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         gaussian_fill<true>(iter, h * HALF, h * HALF + HALF < NPL ? h * HALF + HALF : NPL);
@@ -975,12 +1037,12 @@ template <int FAM, int G, int NPL> struct Chain {
             } else xp[e] = 0.0;
           }
         }
-        if (G > 1) __syncwarp();
+        if (G == 32) __syncwarp();
       }
     }
     rec_step = P.ls_scale[c];
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false, true, FAM == FAM_GAUSS_PREC>(P, lane, xp, gdummy, lpf);
+    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf);
     if (T != 1.0) lpf = lpf / T;
     const double thresh = lpf - P.lp[c];
     rec_dh = thresh;
@@ -1025,7 +1087,7 @@ template <int FAM, int G, int NPL> struct Chain {
     const size_t kc = (size_t)k * P.C + c;
     unsigned long long made = P.made[kc] + 1, acc = P.acc[kc];
     const double* z = zcol();
-    const int stride = blockDim.x;
+    const int stride = zstride();
     const int ne = (d + G - 1) / G;
     const size_t base = (size_t)c * d;
     double* __restrict__ xw = P.x + base;
@@ -1255,7 +1317,7 @@ template <int FAM, int G, int NPL> struct Chain {
     gaussian_fill<false>(iter, 0, NPL);
     {
       const double* z = zcol();
-      const int stride = blockDim.x;
+      const int stride = zstride();
       QSB_FOR_E {
         int i = e * G + lane;
         xp[e] = i < d ? z[e * stride] : 0.0;
@@ -1271,7 +1333,7 @@ template <int FAM, int G, int NPL> struct Chain {
       xp[e] = i < d ? x[e] + (step * (xp[e] / nrm)) : 0.0;
     }
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false, true, FAM == FAM_GAUSS_PREC>(P, lane, xp, gdummy, lpf);
+    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf);
     if (T != 1.0) lpf = lpf / T;
     double t = 0.234;
     if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
@@ -1429,7 +1491,7 @@ template <int FAM, int G, int NPL> struct Chain {
     const bool adapting = P.doAdapt[k] != 0;
     const size_t kc = (size_t)k * P.C + c;
     const double* z = zcol();
-    const int stride = blockDim.x;
+    const int stride = zstride();
     const int ne = (d + G - 1) / G;
     const size_t base = (size_t)c * d;
     double* __restrict__ xw = P.x + base;
@@ -1519,11 +1581,12 @@ template <int FAM, int G, int NPL> struct Chain {
         if constexpr (STREAM) accept = drift_next_stream_lex(k, iter, rdh, rstep);
         else accept = drift_next_lex(k, iter, rdh, rstep);
       } else {
-        if constexpr (STREAM) accept = drift_next_stream<(G == 1 || HAS_HMC) ? 128 : 256>(k, iter, rdh, rstep);
+        if constexpr (STREAM) accept = drift_next_stream<WS ? 32 : ((G == 1 || HAS_HMC) ? 128 : 256)>(k, iter, rdh, rstep);
         else accept = drift_next(k, iter, rdh, rstep);
       }
     }
     else accept = STREAM ? harm_next_stream(k, iter, rdh, rstep) : harm_next(k, iter, rdh, rstep);
+    if constexpr (WS) ws_release();
     if (G == 32) __syncwarp();
     const bool keep = lit >= P.burnin && (lit % P.lag) == 0 && c < P.sample_chains && P.samples != nullptr;
     if (keep || P.rec_state) {
@@ -1594,6 +1657,67 @@ advance_kernel(const __grid_constant__ EngineParams P) {
   if (active)
     for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC, LEX, DRIFT_ONLY>(it);
   ch.flush_counts();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised form of advance_kernel for the warp-per-chain mapping (G = 32): the Gaussian sampling (Philox + Leva:
+// half of the fused kernels' instructions, ~40 registers) and the transition itself (the trajectory state: 2 x NPL doubles per
+// lane) run on DIFFERENT warps of one CTA with different register budgets (setmaxnreg) and meet in shared memory.
+//   warpgroup 0   (warps 0..3)          4 trajectory warps, one chain slot each
+//   warpgroups 1..NPROD (4 NPROD warps)  sampler warps: warp j of warpgroup 1+p fills rows [p RP, (p+1) RP) of slot j's buffer
+// Every iteration of every chain needs exactly the standard normals z_i(chain, iteration), i < n, whatever kernel the
+// mixture picks (HMC momenta, HARM direction, drift proposal: slots 0..n-1 of the iteration's sub-streams), so the sampler
+// warps run ahead through the same (chain, iteration) sequence as their trajectory warp, two staging buffers per slot
+// alternating under a full / empty mbarrier pair.  Only the probes of the step-size search (once per chain) are drawn by the
+// trajectory warp itself.  The kernel is persistent: gridDim = CTAs that fit the device, slot s works off chains s, s + S, ...
+static constexpr int WS_CONSUMER_REGS = 160, WS_PRODUCER_REGS = 40;
+template <int FAM, int NPL, bool HAS_HMC, bool DRIFT_ONLY, int NPROD>
+__global__ void __launch_bounds__(128 * (1 + NPROD), 2)
+advance_ws_kernel(const __grid_constant__ EngineParams P) {
+  extern __shared__ double qsb_zbuf[];
+  constexpr int BUF = NPL * 32;                      // doubles per staging buffer
+  constexpr int SLOT = (HAS_HMC ? 3 : 2) * BUF;      // two hand-off buffers (+ the trajectory warp's own)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qsb_zbuf + 4 * SLOT);    // per slot: full[2], empty[2]
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+  const int slot = warp & 3, role = warp >> 2;       // role 0: trajectory; 1..NPROD: sampler
+  if (threadIdx.x < 4) {
+    uint64_t* b = bars + 4 * threadIdx.x;
+    mbar_init(&b[0], NPROD); mbar_init(&b[1], NPROD); mbar_init(&b[2], 1); mbar_init(&b[3], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double* zslot = qsb_zbuf + (size_t)slot * SLOT;
+  uint64_t* full = bars + 4 * slot;
+  uint64_t* empty = full + 2;
+  const uint32_t nslots = gridDim.x * 4u, s0 = blockIdx.x * 4u + (uint32_t)slot;
+  if (role == 0) {
+    reg_alloc<WS_CONSUMER_REGS>();
+    WsLink link{zslot, HAS_HMC ? zslot + 2 * BUF : nullptr, full, empty, 0u, false};
+    unsigned long long tot[2] = {0ull, 0ull};
+    for (uint32_t c = s0; c < P.C; c += nslots) {
+      Chain<FAM, 32, NPL, true> ch(P, c, &link);
+      for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC, false, DRIFT_ONLY>(it);
+      tot[0] += ch.cnt[0]; tot[1] += ch.cnt[1];
+    }
+    if (lane == 0) { if (tot[0]) atomicAdd(&P.counters[0], tot[0]); if (tot[1]) atomicAdd(&P.counters[1], tot[1]); }
+  } else {
+    reg_dealloc<WS_PRODUCER_REGS>();
+    constexpr int RP = (NPL + NPROD - 1) / NPROD;    // rows per sampler warp
+    const int row0 = (role - 1) * RP;
+    const int d = P.d;
+    const int n = min(d, (row0 + RP) * 32) - row0 * 32;   // components this warp draws (may be <= 0 past the last row)
+    uint32_t k = 0;
+    for (uint32_t c = s0; c < P.C; c += nslots) {
+      const uint32_t gc = P.chain_begin + c;
+      for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it, ++k) {
+        const uint32_t b = k & 1u;
+        mbar_wait(&empty[b], ((k >> 1) & 1u) ^ 1u);      // (a fresh barrier passes the wait on the preceding phase)
+        if (n > 0) gaussian_fill_body<32>(P.key.k0, P.key.k1, gc, (uint32_t)it, row0, n, zslot + (size_t)b * BUF + row0 * 32, 32);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[b]);
+      }
+    }
+  }
 }
 
 // Forward-sampling initialisation (trace.t:592-624: update(true) creates every choice by sampling it,
@@ -1748,7 +1872,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) debug_leap_kernel(const __
     if (D.last) lp = ch.lp_only(x);
   } else {
     if (D.g) ch.load(D.g, g);
-    else { double lpf; model_eval<FAM, G, NPL, true, true, FAM == FAM_GAUSS_PREC>(P, lane, x, g, lpf); }
+    else { double lpf; model_eval<FAM, G, NPL, true, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, x, g, lpf); }
     if (D.last) lp = ch.template leapfrog<true>(eps, x, g, p);
     else ch.template leapfrog<false>(eps, x, g, p);
   }
@@ -1767,6 +1891,10 @@ struct EngineVariant {
   void (*rescore)(const EngineParams&, void* stream);
   void (*logp_grad)(const EngineParams&, void* stream);
   void (*debug_leap)(const EngineParams&, const DebugLeap&, void* stream);
+  // warp-specialised forms (G == 32 only, otherwise nullptr): same semantics as advance / advance_nohmc / advance_drift
+  void (*advance_ws)(const EngineParams&, void* stream);
+  void (*advance_nohmc_ws)(const EngineParams&, void* stream);
+  void (*advance_drift_ws)(const EngineParams&, void* stream);
 };
 
 }  // namespace qsb

@@ -1,6 +1,7 @@
 // Instantiation helper: one EngineVariant per (family, lanes per chain, elements per lane).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include "engine.cuh"
 
 namespace qsb {
@@ -27,11 +28,37 @@ template <int FAM, int G, int NPL> struct VariantImpl {
   static void init(const EngineParams& P, void* st) { init_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void rescore(const EngineParams& P, void* st) { rescore_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   static void logp_grad(const EngineParams& P, void* st) { logp_grad_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
+  // warp-specialised kernel: persistent grid of CTAs of 4 trajectory warps + 4 * NPROD sampler warps
+  template <bool HAS_HMC, bool DRIFT_ONLY> static void advance_ws_t(const EngineParams& P, void* st) {
+    if constexpr (G == 32) {
+      constexpr int NPROD = 2;
+      constexpr int THREADS = 128 * (1 + NPROD);
+      constexpr size_t SMEM = (size_t)4 * (HAS_HMC ? 3 : 2) * NPL * 32 * sizeof(double) + 16 * sizeof(uint64_t);
+      auto kern = advance_ws_kernel<FAM, NPL, HAS_HMC, DRIFT_ONLY, NPROD>;
+      static int ctas_per_sm[64] = {};   // per device
+      int dev = 0, nsm = 148;
+      cudaGetDevice(&dev);
+      if (!ctas_per_sm[dev & 63]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS, SMEM);
+        ctas_per_sm[dev & 63] = n > 0 ? n : 1;
+      }
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+      const unsigned want = (unsigned)((P.C + 3) / 4);
+      const unsigned grid = std::min<unsigned>(want, (unsigned)(nsm * ctas_per_sm[dev & 63]));
+      kern<<<grid, THREADS, SMEM, (cudaStream_t)st>>>(P);
+    }
+  }
+  static void advance_ws(const EngineParams& P, void* st) { advance_ws_t<true, false>(P, st); }
+  static void advance_nohmc_ws(const EngineParams& P, void* st) { advance_ws_t<false, false>(P, st); }
+  static void advance_drift_ws(const EngineParams& P, void* st) { advance_ws_t<false, true>(P, st); }
   static void debug_leap(const EngineParams& P, const DebugLeap& D, void* st) {
     constexpr size_t SMEM = FAM == FAM_GAUSS_PREC ? ((size_t)Chain<FAM, G, NPL>::NB * TPB + G * NPL * G * NPL) * sizeof(double) : 0;
     debug_leap_kernel<FAM, G, NPL><<<grid(P), TPB, SMEM, (cudaStream_t)st>>>(P, D);
   }
-  static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &advance_nohmc, &advance_lex, &advance_drift, &init, &rescore, &logp_grad, &debug_leap}; }
+  static EngineVariant make() { return EngineVariant{FAM, G, NPL, &advance, &advance_nohmc, &advance_lex, &advance_drift, &init, &rescore, &logp_grad, &debug_leap,
+                                                   G == 32 ? &advance_ws : nullptr, G == 32 ? &advance_nohmc_ws : nullptr, G == 32 ? &advance_drift_ws : nullptr}; }
 };
 
 }  // namespace qsb

@@ -31,6 +31,7 @@
 #include "../../include/qsb200.h"
 #include "distrib.cuh"
 #include "glm_hmc.cuh"
+#include "mbar.cuh"
 #include "philox.cuh"
 
 namespace qsb {
@@ -71,37 +72,6 @@ struct GradParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
-  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// arrive; true iff this arrival was the last one pending, i.e. it completed the phase
-__device__ __forceinline__ bool mbar_arrive_last(uint64_t* bar) {
-  uint32_t pending;
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%1];\n mbarrier.pending_count.b64 %0, st;\n}"
-               : "=r"(pending) : "r"(smem_u32(bar)) : "memory");
-  return pending == 1u;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 // Programmatic dependent launch (PDL): every kernel of a transition is launched with programmatic stream serialization, lets
 // its successor start launching at once (pdl_trigger) and touches nothing its predecessor produces before pdl_wait, which
 // returns when the predecessor grid has completed and its writes are visible.  The ~2-3 us launch gap per kernel boundary
@@ -241,7 +211,7 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   const int nvw = min(CW, (int)((P.C - (uint32_t)tile * CB + 7u) / 8u));
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nvw); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   if ((int)threadIdx.x < NST * 8) sm[SD * (threadIdx.x >> 3) + (size_t)MB * P.S + (threadIdx.x & 7)] = 0.0;   // over-read pads
   if (THETA_SMEM) {   // the chain tile's Theta, [CB][theta_stride]; rows of chains past the end are zero
@@ -860,15 +830,19 @@ static cudaError_t launch_grad(int nj_inst, const GradParams& P, size_t smem, cu
 static int pick_nj_inst(int nj) { for (int c : {2, 4, 13, 16}) if (nj <= c) return c; return 0; }
 
 // Balanced decomposition of one gradient launch (see glm_grad_kernel): the ntiles x nblocks row-block units, tile-major, are
-// cut into one run per CTA such that every run costs the same.  A unit of a full chain tile costs CW/4 (warps per SM
-// sub-partition); the last tile may hold fewer chains and its units cost ceil(live warps / 4).  Cuts closer than 3 row
-// blocks to a tile boundary snap to it (a 1-2 block segment is all prologue).  Output: start[ncta+1], first[ntiles] (first
-// CTA touching a tile), np[ntiles] (partial sums of a tile = CTAs touching it); returns ncta.
+// cut into one run per CTA such that every run costs the same.  The last tile may hold fewer chains than a full one; its
+// idle warps are skipped, but a row block then does not cost in proportion to the live warps: measured on B200 (c3 shape,
+// r02b) a row block takes 6.3 us with 12 live warps, 4.85 us with 8 and 3.56 us with 4 -- about 2.2 us of per-block latency
+// that only thread-level parallelism hides -- hence the cost table 100 / 78 / 57 per warps-per-sub-partition 3 / 2 / 1.
+// A cut one row block away from a tile boundary snaps to it (a single-block segment is all prologue).
+// Output: start[ncta+1], first[ntiles] (first CTA touching a tile), np[ntiles] (partial sums of a tile = CTAs touching it);
+// returns ncta.
+int glm_unit_cost(int live_warps) { const int per_sp = (live_warps + 3) / 4; return per_sp >= 3 ? 100 : (per_sp == 2 ? 78 : 57); }
 int glm_layout(int ntiles, int nblocks, uint32_t C, int nsm, std::vector<int>& start, std::vector<int>& first, std::vector<int>& np) {
   const long total = (long)ntiles * nblocks;
-  const int WF = CW / 4;
+  const int WF = glm_unit_cost(CW);
   const int live_last = std::min<int>(CW, (int)((C - (uint32_t)(ntiles - 1) * CB + 7u) / 8u));
-  const int w_last = (live_last + 3) / 4;
+  const int w_last = glm_unit_cost(live_last);
   const long Ufull = (long)(ntiles - 1) * nblocks;
   const double Cfull = (double)Ufull * WF, T = Cfull + (double)nblocks * w_last;
   int ncta = (int)std::min<long>(nsm, std::max<long>(1, total / 12));
@@ -877,7 +851,7 @@ int glm_layout(int ntiles, int nblocks, uint32_t C, int nsm, std::vector<int>& s
     const double target = T * i / ncta;
     long u = target <= Cfull ? llround(target / WF) : Ufull + llround((target - Cfull) / w_last);
     const long r = u % nblocks;
-    if (r && r < 3) u -= r; else if (r && nblocks - r < 3) u += nblocks - r;
+    if (r == 1) u -= 1; else if (nblocks - r == 1) u += 1;     // no single-block segments
     cut[i] = std::min(std::max(u, cut[i - 1]), total);
   }
   cut[ncta] = total;

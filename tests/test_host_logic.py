@@ -50,16 +50,17 @@ def test_balanced_layout_covers_every_tile_exactly_once():
 
 def test_balanced_layout_equalises_cost():
     """BASELINE config c3 (N = 10 000 -> 313 row blocks) at its strong-scaling shard sizes: one run per SM, and the costliest
-    run is within 2 % of the mean (a unit of the partially filled last tile costs ceil(live warps / 4) / 3 of a full one)."""
+    run is within 2 % of the mean (a unit of the partially filled last tile costs 78 % / 57 % of a full one with 2 / 1 live warps
+    per SM sub-partition: the measured table of glm_unit_cost)."""
     for chains in (8192, 4096, 2048, 1024):
         nt, nb, nc, start, first, np_ = _layout(chains, 10000, 148)
         assert nc == 148 and nb == 313
         live_last = min(12, (chains - (nt - 1) * 96 + 7) // 8)
-        w_last = (live_last + 3) // 4
+        w_last = {3: 100, 2: 78, 1: 57}[(live_last + 3) // 4]
         cost = []
         for c in range(nc):
             full_units = max(0, min(start[c + 1], (nt - 1) * nb) - start[c])
             last_units = (start[c + 1] - start[c]) - full_units
-            cost.append(3 * full_units + w_last * last_units)
-        assert max(cost) <= 1.02 * (sum(cost) / nc) + 3, (chains, max(cost), sum(cost) / nc)
+            cost.append(100 * full_units + w_last * last_units)
+        assert max(cost) <= 1.02 * (sum(cost) / nc) + 100, (chains, max(cost), sum(cost) / nc)
         assert max(np_) <= 16
