@@ -51,7 +51,10 @@ enum { QSB_ERP_GAUSSIAN = 0, QSB_ERP_GAMMA = 1, QSB_ERP_BETA = 2, QSB_ERP_UNIFOR
         * components of this kind with erp_p0 = alpha_k and erp_p1 = k (index inside the choice, 0..K-1); component K-1
         * of the unconstrained vector is the reference's unused stick coordinate.  gammamv / betamv (erpdefs.t:72-88,
         * 103-125) are host-side reparametrisations of gamma / beta. */
-       QSB_ERP_DIRICHLET = 4 };
+       QSB_ERP_DIRICHLET = 4,
+       /* Bounds.Upper (erp.t:158-173), which the reference offers to user-defined ERPs (makeRandomChoice) and binds to none of
+        * its own: value = -gamma(shape = erp_p0, scale = erp_p1) < 0, upper bound 0. */
+       QSB_ERP_NEGGAMMA = 5 };
 
 /* transition kernels: qs/hmc.t:57-66, qs/drift.t:63-73, qs/harm.t:16-22; TRACEMH = TraceMHKernel{doStruct=false}
  * (qs/mcmc.t:134-193): one random choice per iteration, gaussian ERPs drift with their own sigma (erpdefs.t:46-57), the
@@ -94,6 +97,12 @@ typedef struct {
   const int32_t* erp_pref;  /* [2*dim] */
   const double* erp_pcoef;  /* [2*dim] */
   const int32_t* erp_ptf;   /* [2*dim] or NULL (all identity) */
+  /* Hard constraints (INDEP, both NULL = none): the statement  qs.condition(value_i > erp_cond_lo[i] and value_i <
+   * erp_cond_hi[i])  right after scalar choice i (trace.t:794-796, 1103-1107; -inf / +inf = no bound on that side).  The trace
+   * is initialised by rejection (trace.t:612-623: the program is re-run from scratch until every condition holds) and every
+   * kernel's accept test is `conditionsSatisfied and log(random()) < ...` (hmc.t:164, drift.t:158, harm.t:93, mcmc.t:181). */
+  const double* erp_cond_lo; /* [dim] */
+  const double* erp_cond_hi; /* [dim] */
 } qsb_model_desc;
 
 /* One transition kernel; nspecs > 1 means MixtureKernel(kernels, weights) (qs/mcmc.t:199-291). */

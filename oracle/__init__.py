@@ -33,7 +33,7 @@ def use(variant):
     _ACTIVE = variant
 
 HMC, DRIFT, HARM, TRACEMH = 1, 2, 3, 4
-ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
+ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET, ERP_NEGGAMMA = 0, 1, 2, 3, 4, 5
 ITER_INIT = 0xFFFFFFFF
 ITER_SEARCH = 0xF0000000
 SLOT_MIXTURE = 0xFFFFFFFF
@@ -82,6 +82,7 @@ def lib(variant=None):
         L.qso_program_indep_lexids.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.qso_program_indep_factors.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.qso_program_indep_latent.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), dp, C.POINTER(C.c_int)]
+        L.qso_program_indep_conditions.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.qso_program_gauss_prec.argtypes = [C.c_int, dp]
         L.qso_program_logistic.argtypes = [C.c_int, C.c_int, dp, C.POINTER(C.c_ubyte), C.c_double]
         L.qso_program_eight_schools.argtypes = [C.c_int, dp, dp]
@@ -158,7 +159,7 @@ class Program:
             pass
 
     @staticmethod
-    def indep(kinds, p0, p1, ret_mode=0, ret_div=1.0, lexids=None, fmu=None, fsigma=None, pref=None, pcoef=None, ptf=None):
+    def indep(kinds, p0, p1, ret_mode=0, ret_div=1.0, lexids=None, fmu=None, fsigma=None, pref=None, pcoef=None, ptf=None, cond_lo=None, cond_hi=None):
         k = np.ascontiguousarray(kinds, dtype=np.int32)
         a = np.ascontiguousarray(p0, dtype=np.float64)
         b = np.ascontiguousarray(p1, dtype=np.float64)
@@ -169,6 +170,9 @@ class Program:
         if fsigma is not None:
             fm = np.ascontiguousarray(fmu, dtype=np.float64); fs = np.ascontiguousarray(fsigma, dtype=np.float64)
             lib().qso_program_indep_factors(C.c_void_p(h), len(fs), _dp(fm), _dp(fs))
+        if cond_lo is not None:
+            lo = np.ascontiguousarray(cond_lo, dtype=np.float64); hi = np.ascontiguousarray(cond_hi, dtype=np.float64)
+            lib().qso_program_indep_conditions(C.c_void_p(h), len(lo), _dp(lo), _dp(hi))
         if pref is not None:
             r = np.ascontiguousarray(pref, dtype=np.int32).ravel(); cb = np.ascontiguousarray(pcoef, dtype=np.float64).ravel()
             tf = np.ascontiguousarray(ptf if ptf is not None else np.zeros(len(r)), dtype=np.int32).ravel()

@@ -99,6 +99,10 @@ void qso_program_indep_latent(void* prog, int K, const int* ref, const double* b
   IndepErps* p = (IndepErps*)prog;
   p->lat_ref.assign(ref, ref + 2 * K); p->lat_b.assign(b, b + 2 * K); p->lat_tf.assign(tf, tf + 2 * K);
 }
+void qso_program_indep_conditions(void* prog, int K, const double* lo, const double* hi) {
+  IndepErps* p = (IndepErps*)prog;
+  p->cond_lo.assign(lo, lo + K); p->cond_hi.assign(hi, hi + K);
+}
 void* qso_program_gauss_prec(int d, const double* A) {
   GaussPrecision* p = new GaussPrecision();
   p->d = d; p->A.assign(A, A + (size_t)d * d); p->retdim = d;

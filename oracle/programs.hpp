@@ -34,6 +34,9 @@ struct IndepErps : Program {
   // a dual trace the tape differentiates the log-density with respect to it.
   std::vector<int> lat_ref, lat_tf;
   std::vector<double> lat_b;
+  // optional hard constraint after scalar choice i: qs.condition(value_i > cond_lo[i] and value_i < cond_hi[i])
+  // (trace.t:794-796, 1103-1107; +-inf = no bound).  Empty: none.
+  std::vector<double> cond_lo, cond_hi;
   int ret_mode = 0;
   double ret_div = 1.0;
   // Entries are per real component.  A dirichlet choice of K components is K consecutive entries of kind
@@ -62,6 +65,7 @@ struct IndepErps : Program {
         real x = t.erp(kind[i], par(0, i), par(1, i));
         vals[i] = x;
         if (!fsigma.empty() && fsigma[i] > 0.0) t.factor(D::gaussian_logprob<real>(x, real(fmu[i]), real(fsigma[i])));   // testsuite.t:394-442
+        if (!cond_lo.empty() && (cond_lo[i] > -HUGE_VAL || cond_hi[i] < HUGE_VAL)) t.condition(val(x) > cond_lo[i] && val(x) < cond_hi[i]);
         if (ret_mode == 0) sum = sum + x; else t.returnValue.push_back(x);
         ++i;
       }

@@ -28,7 +28,9 @@
 
 namespace qso {
 
-enum ErpKind { ERP_GAUSSIAN = 0, ERP_GAMMA = 1, ERP_BETA = 2, ERP_UNIFORM = 3, ERP_DIRICHLET = 4 };
+// ERP_NEGGAMMA: a user-defined ERP built with makeRandomChoice over Bounds.Upper (erp.t:158-173) -- the reference binds Upper
+// to none of its own ERPs: value = -gamma(shape, scale) < 0, upper bound 0.
+enum ErpKind { ERP_GAUSSIAN = 0, ERP_GAMMA = 1, ERP_BETA = 2, ERP_UNIFORM = 3, ERP_DIRICHLET = 4, ERP_NEGGAMMA = 5 };
 
 template <class real> struct is_dual : std::false_type {};
 template <> struct is_dual<ad::num> : std::true_type {};
@@ -43,6 +45,10 @@ static const double POS_INF = std::numeric_limits<double>::infinity();
 template <class real> inline real lower_fwd(real x, double lo) { return tmath::fmax(tmath::exp(x) + lo, lo + 1e-15); }
 template <class real> inline real lower_inv(real y, double lo) { real z = tmath::fmax(y, lo + 1e-15); return tmath::log(z - lo); }
 template <class real> inline real lower_lpincr(real x, double) { return x; }
+// ---- Bounds.Upper (erp.t:158-173)
+template <class real> inline real upper_fwd(real x, double hi) { return tmath::fmin(hi - tmath::exp(x), hi - 1e-15); }
+template <class real> inline real upper_inv(real y, double hi) { real z = tmath::fmin(y, hi - 1e-15); return tmath::log(hi - z); }
+template <class real> inline real upper_lpincr(real x, double) { return x; }
 // ---- Bounds.LowerUpper (erp.t:175-198); LO/HI are double (beta) or real (uniform)
 template <class real, class BT> inline real lowerupper_fwd(real x, BT lo, BT hi) {
   real logit = logistic(x);
@@ -145,6 +151,7 @@ template <class real> struct RandomChoice {   // RandomChoiceT, erp.t:286-311
   real fwd(real x) {
     switch (kind) {
       case ERP_GAMMA: return lower_fwd<real>(x, 0.0);
+      case ERP_NEGGAMMA: return upper_fwd<real>(x, 0.0);
       case ERP_BETA: return lowerupper_fwd<real, double>(x, 0.0, 1.0);
       case ERP_UNIFORM: return lowerupper_fwd<real, real>(x, param0, param1);
       default: return x;
@@ -153,6 +160,7 @@ template <class real> struct RandomChoice {   // RandomChoiceT, erp.t:286-311
   real inv(real y) {
     switch (kind) {
       case ERP_GAMMA: return lower_inv<real>(y, 0.0);
+      case ERP_NEGGAMMA: return upper_inv<real>(y, 0.0);
       case ERP_BETA: return lowerupper_inv<real, double>(y, 0.0, 1.0);
       case ERP_UNIFORM: return lowerupper_inv<real, real>(y, param0, param1);
       default: return y;
@@ -161,6 +169,7 @@ template <class real> struct RandomChoice {   // RandomChoiceT, erp.t:286-311
   real lpincr(real x) {
     switch (kind) {
       case ERP_GAMMA: return lower_lpincr<real>(x, 0.0);
+      case ERP_NEGGAMMA: return upper_lpincr<real>(x, 0.0);
       case ERP_BETA: return lowerupper_lpincr<real, double>(x, 0.0, 1.0);
       case ERP_UNIFORM: return lowerupper_lpincr<real, real>(x, param0, param1);
       default: return real(0.0);
@@ -169,6 +178,7 @@ template <class real> struct RandomChoice {   // RandomChoiceT, erp.t:286-311
   real prior_logprob(real val) {
     switch (kind) {
       case ERP_GAMMA: return D::gamma_logprob<real>(val, param0, param1);
+      case ERP_NEGGAMMA: return D::gamma_logprob<real>(-val, param0, param1);
       case ERP_BETA: return D::beta_logprob<real>(val, param0, param1);
       case ERP_UNIFORM: return D::uniform_logprob<real>(val, param0, param1);
       default: return D::gaussian_logprob<real>(val, param0, param1);
@@ -177,6 +187,7 @@ template <class real> struct RandomChoice {   // RandomChoiceT, erp.t:286-311
   double sample(double p0, double p1) {
     switch (kind) {
       case ERP_GAMMA: return D::gamma_sample(p0, p1);
+      case ERP_NEGGAMMA: return -D::gamma_sample(p0, p1);
       case ERP_BETA: return D::beta_sample(p0, p1);
       case ERP_UNIFORM: return D::uniform_sample(p0, p1);
       default: return D::gaussian_sample(p0, p1);
@@ -293,8 +304,12 @@ template <class real> struct Trace {   // RandExecTraceT, trace.t:523-540
     canStructureChange = true; doEvalLikelihoodsAndConditions = true; numUpdates = 0;
     choices.clear();
     if (doRejectionInit) {
+      // every rejection-init attempt reads fresh sub-streams: attempt a samples under iteration code ITER_INIT - a
+      // (the reference's rand() stream simply continues, trace.t:612-623)
+      uint32_t attempt = 0;
       while (!conditionsSatisfied) {
         choices.clear();
+        rng().iter = ITER_INIT - attempt; ++attempt;
         update(true);
       }
     }

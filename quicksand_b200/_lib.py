@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QSB200_LIB") or os.path.join(HERE, "libqsb200.so")   # QSB200_LIB: another build of the same ABI (A/B measurements)
 
 FAM_INDEP, FAM_GAUSS_PREC, FAM_LOGISTIC, FAM_EIGHT_SCHOOLS, FAM_FUNNEL = 1, 2, 3, 4, 5
-ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET = 0, 1, 2, 3, 4
+ERP_GAUSSIAN, ERP_GAMMA, ERP_BETA, ERP_UNIFORM, ERP_DIRICHLET, ERP_NEGGAMMA = 0, 1, 2, 3, 4, 5
 KERNEL_HMC, KERNEL_DRIFT, KERNEL_HARM, KERNEL_TRACEMH = 1, 2, 3, 4
 FLAG_MOMENTS, FLAG_RECORD, FLAG_RECORD_LEAP, FLAG_TIME_KERNEL, FLAG_BALANCED, FLAG_INVARIANT = 1, 2, 4, 8, 16, 32
 
@@ -24,7 +24,7 @@ class ModelDesc(C.Structure):
                 ("ret_div", C.c_double), ("prior_sigma", C.c_double),
                 ("erp_kind", ip), ("erp_p0", dp), ("erp_p1", dp), ("A", dp), ("X", dp),
                 ("ybin", C.POINTER(C.c_uint8)), ("y", dp), ("sigma", dp), ("erp_lexid", ip), ("erp_fmu", dp), ("erp_fsigma", dp),
-                ("erp_pref", ip), ("erp_pcoef", dp), ("erp_ptf", ip)]
+                ("erp_pref", ip), ("erp_pcoef", dp), ("erp_ptf", ip), ("erp_cond_lo", dp), ("erp_cond_hi", dp)]
 
 
 class KernelSpec(C.Structure):

@@ -320,7 +320,7 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
   switch (d->family) {
     case QSB_FAM_INDEP: {
       if (!d->erp_kind || !d->erp_p0 || !d->erp_p1) return bail(3, "INDEP: erp_kind/erp_p0/erp_p1 required");
-      for (int i = 0; i < d->dim; ++i) if (d->erp_kind[i] < 0 || d->erp_kind[i] > 4) return bail(3, "INDEP: unsupported ERP kind (continuous gaussian/gamma/beta/uniform/dirichlet only)");
+      for (int i = 0; i < d->dim; ++i) if (d->erp_kind[i] < 0 || d->erp_kind[i] > 5) return bail(3, "INDEP: unsupported ERP kind (continuous gaussian/gamma/beta/uniform/dirichlet/neggamma only)");
       // vector choices: K consecutive components of kind DIRICHLET with erp_p1 = 0, 1, .., K-1
       std::vector<int> len(d->dim, 1), slot(d->dim, 0);
       std::vector<double> asum(d->dim, 0.0);
@@ -384,6 +384,23 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
         cudaMemcpy(fm, d->erp_fmu, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
         cudaMemcpy(fs, d->erp_fsigma, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
         m->dev.fmu = fm; m->dev.fsigma = fs;
+      }
+      if (d->erp_cond_lo || d->erp_cond_hi) {
+        if (!d->erp_cond_lo || !d->erp_cond_hi) return bail(3, "INDEP: erp_cond_lo and erp_cond_hi come together");
+        bool any = false;
+        for (int i = 0; i < d->dim; ++i) {
+          const bool has = d->erp_cond_lo[i] > -INFINITY || d->erp_cond_hi[i] < INFINITY;
+          if (has && d->erp_kind[i] == QSB_ERP_DIRICHLET) return bail(3, "INDEP: conditions on the components of a dirichlet choice are not supported");
+          if (has && !(d->erp_cond_lo[i] < d->erp_cond_hi[i])) return bail(3, "INDEP: an empty condition interval can never be satisfied");
+          any |= has;
+        }
+        if (any) {
+          double *cl, *chh;
+          if (m->arena.alloc(&cl, d->dim) || m->arena.alloc(&chh, d->dim)) return bail(4, "cudaMalloc failed");
+          cudaMemcpy(cl, d->erp_cond_lo, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
+          cudaMemcpy(chh, d->erp_cond_hi, sizeof(double) * d->dim, cudaMemcpyHostToDevice);
+          m->dev.cond_lo = cl; m->dev.cond_hi = chh;
+        }
       }
       if (d->erp_pref) {
         if (!d->erp_pcoef) return bail(3, "INDEP: erp_pcoef is required with erp_pref");
@@ -762,9 +779,9 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
     for (int k = 0; k < R.nsub; ++k) has_hmc |= R.kind[k] == K_HMC;
     bool has_mh = false;
     for (int k = 0; k < R.nsub; ++k) has_mh |= R.kind[k] == K_TRACEMH;
-    // warp-per-chain variants run warp-specialised (sampler warps + trajectory warps, engine.cuh: advance_ws_kernel);
-    // QSB_NO_WS=1 selects the fused kernels (every warp samples and integrates) for A/B measurements
-    static const bool ws = !getenv("QSB_NO_WS");
+    // QSB_WS=1: the warp-per-chain variants run warp-specialised (sampler warps + trajectory warps, engine.cuh:
+    // advance_ws_kernel) instead of fused (every warp samples and integrates)
+    static const bool ws = getenv("QSB_WS") && atoi(getenv("QSB_WS")) != 0;   // (not the default yet: see profiles/README.md)
     const bool use_ws = ws && s->var->advance_ws != nullptr;
     if (R.dr_lexical || has_mh) s->var->advance_lex(R, s->stream);   // the general kernel
     else if (R.nsub == 1 && R.kind[0] == K_DRIFT) (use_ws ? s->var->advance_drift_ws : s->var->advance_drift)(R, s->stream);

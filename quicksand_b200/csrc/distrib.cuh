@@ -79,7 +79,9 @@ QSB_D double bernoulli_lp(bool val, double p) { return log(val ? p : 1.0 - p); }
 QSB_D double logistic_(double x) { return 1.0 / (1.0 + exp(-x)); }
 QSB_D double invlogistic_(double y) { return -log(1.0 / y - 1.0); }
 
-enum { ERP_GAUSSIAN = 0, ERP_GAMMA = 1, ERP_BETA = 2, ERP_UNIFORM = 3, ERP_DIRICHLET = 4 };
+// ERP_NEGGAMMA: value = -gamma(shape, scale) < 0 under Bounds.Upper(0) (erp.t:158-173): the transform the reference offers
+// to user-defined ERPs (makeRandomChoice) but binds to none of its own.
+enum { ERP_GAUSSIAN = 0, ERP_GAMMA = 1, ERP_BETA = 2, ERP_UNIFORM = 3, ERP_DIRICHLET = 4, ERP_NEGGAMMA = 5 };
 
 // ---- dirichlet (distrib.t:336-362) under Bounds.UnitSimplex (erp.t:200-254), one component at a time.
 // A K-vector dirichlet choice occupies K consecutive real components; component K-1 of the unconstrained vector is
@@ -116,6 +118,13 @@ QSB_D double erp_fwd(int kind, double x, double p0, double p1, double* dydx) {
       if (dydx) *dydx = 0.0;
       return 0.0 + 1e-15;
     }
+    case ERP_NEGGAMMA: {                               // Upper(0): fmin(hi - exp(x), hi - 1e-15); zero gradient on the clamp
+      double ex = exp(x);
+      double v = 0.0 - ex;
+      if (v <= 0.0 - 1e-15) { if (dydx) *dydx = -ex; return v; }
+      if (dydx) *dydx = 0.0;
+      return 0.0 - 1e-15;
+    }
     case ERP_BETA:
     case ERP_UNIFORM: {                                // LowerUpper(lo,hi)
       double lo = kind == ERP_BETA ? 0.0 : p0, hi = kind == ERP_BETA ? 1.0 : p1;
@@ -136,6 +145,7 @@ QSB_D double erp_fwd(int kind, double x, double p0, double p1, double* dydx) {
 QSB_D double erp_inv(int kind, double y, double p0, double p1) {
   switch (kind) {
     case ERP_GAMMA: { double z = fmax(y, 0.0 + 1e-15); return log(z - 0.0); }
+    case ERP_NEGGAMMA: { double z = fmin(y, 0.0 - 1e-15); return log(0.0 - z); }
     case ERP_BETA:
     case ERP_UNIFORM: {
       double lo = kind == ERP_BETA ? 0.0 : p0, hi = kind == ERP_BETA ? 1.0 : p1;
@@ -149,7 +159,8 @@ QSB_D double erp_inv(int kind, double y, double p0, double p1) {
 // logprobIncrement (log-Jacobian) and its derivative
 QSB_D double erp_logjac(int kind, double x, double p0, double p1, double* dldx) {
   switch (kind) {
-    case ERP_GAMMA: if (dldx) *dldx = 1.0; return x;
+    case ERP_GAMMA:
+    case ERP_NEGGAMMA: if (dldx) *dldx = 1.0; return x;
     case ERP_BETA:
     case ERP_UNIFORM: {
       double lo = kind == ERP_BETA ? 0.0 : p0, hi = kind == ERP_BETA ? 1.0 : p1;
@@ -164,6 +175,7 @@ QSB_D double erp_logjac(int kind, double x, double p0, double p1, double* dldx) 
 QSB_D double erp_prior_lp(int kind, double y, double p0, double p1, double* dlpdy) {
   switch (kind) {
     case ERP_GAMMA: if (dlpdy) *dlpdy = gamma_dlp_dx(y, p0, p1); return gamma_lp(y, p0, p1);
+    case ERP_NEGGAMMA: if (dlpdy) *dlpdy = -gamma_dlp_dx(-y, p0, p1); return gamma_lp(-y, p0, p1);
     case ERP_BETA: if (dlpdy) *dlpdy = beta_dlp_dx(y, p0, p1); return beta_lp(y, p0, p1);
     case ERP_UNIFORM: if (dlpdy) *dlpdy = 0.0; return uniform_lp(y, p0, p1);
     default: if (dlpdy) *dlpdy = gaussian_dlp_dx(y, p0, p1); return gaussian_lp(y, p0, p1);
@@ -174,6 +186,7 @@ QSB_D double erp_prior_lp(int kind, double y, double p0, double p1, double* dlpd
 // a choice whose parameters depend on earlier choices
 QSB_D void erp_dlp_dparams(int kind, double y, double p0, double p1, double& d0, double& d1) {
   switch (kind) {
+    case ERP_NEGGAMMA: y = -y;   // the gamma density of -y; fall through
     case ERP_GAMMA:    // (k-1) ln y - y/theta - lg5(k) - k ln theta
       d0 = log(y) - digamma5(p0) - log(p1);
       d1 = y / (p1 * p1) - p0 / p1;
@@ -225,6 +238,7 @@ QSB_D double beta_sample_seq(SubStream& s, double a, double b) {   // distrib.t:
 QSB_D double erp_sample_seq(int kind, SubStream& s, double p0, double p1) {
   switch (kind) {
     case ERP_GAMMA: return gamma_sample_seq(s, p0, p1);
+    case ERP_NEGGAMMA: return -gamma_sample_seq(s, p0, p1);
     case ERP_BETA: return beta_sample_seq(s, p0, p1);
     case ERP_UNIFORM: return uniform_sample_seq(s, p0, p1);
     default: return gaussian_sample_seq(s, p0, p1);

@@ -39,6 +39,9 @@ struct ModelDev {
   // INDEP: optional Gaussian factor on the value of a scalar choice, qs.factor(gaussian.logprob(value, fmu, fsigma)) ==
   // qs.gaussian.observe(value, fmu, fsigma) (trace.t:1099-1107; erp.t:687-696; testsuite.t:394-442); fsigma <= 0: none
   const double* fmu; const double* fsigma;
+  // INDEP: optional hard constraint after scalar choice i, qs.condition(value_i > cond_lo[i] and value_i < cond_hi[i])
+  // (trace.t:794-796, 1103-1107); nullptr: the program has none
+  const double* cond_lo; const double* cond_hi;
   // INDEP, dirichlet components (thread-per-chain mapping only): choice length K, sum of the later alphas of the choice,
   // and the ERP index of every component (= the Philox slot of its forward sample; equals the component index without vector choices)
   const int* erp_len; const double* erp_asum; const int* erp_slot;
@@ -137,9 +140,10 @@ template <int G> __device__ __forceinline__ size_t vidx(const EngineParams& P, i
 // One ERP site of a dual trace: prior logprob of the constrained value, log-Jacobian, and
 // d(logprob + logJ)/dx  (erp.t:623-640).  Not inlined: the INDEP family is not a throughput path
 // and the four-way kind switch would otherwise be replicated at every unrolled component.
-static __device__ __noinline__ void erp_eval(int kind, double x, double p0, double p1, double fmu, double fsigma, double& lpy, double& lj, double& g) {
+static __device__ __noinline__ void erp_eval(int kind, double x, double p0, double p1, double fmu, double fsigma, double& lpy, double& lj, double& g, double& yout) {
   double dydx, dlpdy, dlj;
   double y = erp_fwd(kind, x, p0, p1, &dydx);
+  yout = y;
   lpy = erp_prior_lp(kind, y, p0, p1, &dlpdy);
   if (fsigma > 0.0) {   // the factor statement that follows the choice: likelihood term on the constrained value
     lpy = lpy + gaussian_lp(y, fmu, fsigma);
@@ -163,8 +167,9 @@ static __device__ __noinline__ double dirichlet_component_noinline(SimplexCarry&
 // Forward in program order: value, resolved parameters, log-density terms and the adjoint each term sends to the values
 // its parameters were computed from; then g_i = (dlp_i/dy_i + adjoint_i) dy_i/dx_i + dlogJ_i/dx_i  -- the reverse sweep of
 // the reference's tape (ad.t) over  sum_i [lp_i(y_i; p(y_parents)) + logJ_i(x_i)]  (erp.t:623-640).
-static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const double* x, double* g, double* lp_float, bool grad) {
+static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const double* x, double* g, double* lp_float, bool grad, double* cond_bad) {
   const int d = m.dim;
+  double bad = 0.0;
   double yv[32], yb[32], A[32], B[32];
   double lpd = 0.0, lpf = 0.0;
   SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
@@ -186,6 +191,7 @@ static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const
     double dydx, dlpdy, dlj;
     const double y = erp_fwd(kind, x[i], p0, p1, &dydx);
     yv[i] = y;
+    if (m.cond_lo && !(y > m.cond_lo[i] && y < m.cond_hi[i])) bad += 1.0;
     double lpy = erp_prior_lp(kind, y, p0, p1, &dlpdy);
     if (grad && (r0 >= 0 || r1 >= 0)) {
       double d0, d1;
@@ -200,6 +206,7 @@ static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const
   }
   if (grad) for (int i = 0; i < d; ++i) g[i] = (A[i] + yb[i]) * B[i] + g[i];
   *lp_float = lpf;
+  if (cond_bad) *cond_bad = bad;
   return lpd;
 }
 
@@ -211,18 +218,21 @@ static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const
 // SSM: GAUSS_PREC reads A + A^T from the copy advance_kernel staged in shared memory behind the Gaussian columns
 // (the pointer is formed here from the shared array itself so that the loads compile to LDS, not generic LD).
 template <int FAM, int G, int NPL, bool GRAD, bool LP = true, bool SSM = false>
-__device__ __forceinline__ double model_eval(const EngineParams& P, int lane, const double (&x)[NPL], double (&g)[NPL], double& lp_float) {
+__device__ __forceinline__ double model_eval(const EngineParams& P, int lane, const double (&x)[NPL], double (&g)[NPL], double& lp_float,
+                                             double* cond_bad = nullptr) {
+  // cond_bad (INDEP): receives the number of qs.condition statements the evaluated point violates (0 = conditionsSatisfied)
   const ModelDev& m = P.m;
   const int d = m.dim;
+  if (cond_bad) *cond_bad = 0.0;
   if (FAM == FAM_INDEP) {
     if (G == 1 && NPL <= 32 && m.lat_ref) {   // latent parameters: the general (slow) evaluator on local copies
       double xl[NPL], gl[NPL];
       QSB_FOR_E { xl[e] = x[e]; gl[e] = 0.0; }
-      const double lpd = indep_latent_eval(m, xl, gl, &lp_float, GRAD);
+      const double lpd = indep_latent_eval(m, xl, gl, &lp_float, GRAD, cond_bad);
       if (GRAD) { QSB_FOR_E g[e] = e < d ? gl[e] : 0.0; }
       return lpd;
     }
-    double lpd = 0.0, lpf = 0.0;
+    double lpd = 0.0, lpf = 0.0, bad = 0.0;
     SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
@@ -235,14 +245,16 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
           if (k == K - 1) { lpf += sc.lp; lpd += sc.lp + sc.lj; }
           if (GRAD) g[e] = gi;
         } else {
-          double lpy, lj, gi;
-          erp_eval(kind, x[e], m.p0[i], m.p1[i], m.fsigma ? m.fmu[i] : 0.0, m.fsigma ? m.fsigma[i] : 0.0, lpy, lj, gi);
+          double lpy, lj, gi, y;
+          erp_eval(kind, x[e], m.p0[i], m.p1[i], m.fsigma ? m.fmu[i] : 0.0, m.fsigma ? m.fsigma[i] : 0.0, lpy, lj, gi, y);
+          if (m.cond_lo && !(y > m.cond_lo[i] && y < m.cond_hi[i])) bad += 1.0;
           lpf += lpy;
           lpd += lpy + lj;
           if (GRAD) g[e] = gi;
         }
       } else if (GRAD) g[e] = 0.0;
     }
+    if (cond_bad && m.cond_lo) *cond_bad = Grp<G>::sum(bad);
     lp_float = Grp<G>::sum(lpf);
     return Grp<G>::sum(lpd);
   } else if (FAM == FAM_GAUSS_PREC) {
@@ -454,6 +466,7 @@ template <int FAM> struct GradScalars {
 // model_eval's (components ascending, then the warp butterfly), so both forms give bit-identical sums.
 template <int FAM> struct ModelStream {
   double g0, g1, a, b;   // component 0 and 1 of the proposal and two derived scalars (a is a reciprocal)
+  mutable double bad = 0.0;   // INDEP: qs.condition statements violated by the components this lane scored
   struct Obs { double y, cy, is2; };   // per-component observation data, fetched ahead of use
   __device__ __forceinline__ void prep(const EngineParams& P, double x0, double x1) {
     g0 = x0; g1 = x1; a = 0.0; b = 0.0;
@@ -468,8 +481,9 @@ template <int FAM> struct ModelStream {
   // products with their reciprocals here (<= 1 ulp per term from the reference's divisions).
   __device__ __forceinline__ void term(const EngineParams& P, int i, double xi, const Obs& o, double& lp) const {
     if (FAM == FAM_INDEP) {
-      double lpy, lj, gi;
-      erp_eval(P.m.erp_kind[i], xi, P.m.p0[i], P.m.p1[i], P.m.fsigma ? P.m.fmu[i] : 0.0, P.m.fsigma ? P.m.fsigma[i] : 0.0, lpy, lj, gi);
+      double lpy, lj, gi, y;
+      erp_eval(P.m.erp_kind[i], xi, P.m.p0[i], P.m.p1[i], P.m.fsigma ? P.m.fmu[i] : 0.0, P.m.fsigma ? P.m.fsigma[i] : 0.0, lpy, lj, gi, y);
+      if (P.m.cond_lo && !(y > P.m.cond_lo[i] && y < P.m.cond_hi[i])) bad += 1.0;
       lp += lpy;
     } else if (FAM == FAM_EIGHT_SCHOOLS) {
       if (i >= 2) {
@@ -566,6 +580,9 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
   // divided by it (trace.t:737-741) and its gradient multiplied by 1/T (the adjoint of that division, ad.t:405-412);
   // values cached from earlier iterations (lp, gradient) keep the temperature they were computed under, as in the reference
   mutable double T = 1.0, invT = 1.0;
+  // conditionsSatisfied of the trace evaluated last (trace.t:723, 794-796), as a count of violated qs.condition statements;
+  // the accept tests read it: `conditionsSatisfied and log(random()) < ...` (hmc.t:164, drift.t:158, harm.t:93, mcmc.t:181)
+  mutable double cond_bad = 0.0;
   __device__ __forceinline__ Chain(const EngineParams& P_, uint32_t c_, WsLink* link_ = nullptr)
       : P(P_), c(c_), gc(P_.chain_begin + c_), lane(Grp<G>::lane()), d(P_.d), link(link_) {}
 
@@ -688,7 +705,7 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     QSB_FOR_E xs[e] = xs[e] + eps * p[e] * 1.0;
     double lpf;
-    double lp = model_eval<FAM, G, NPL, true, LPW, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xs, gs, lpf);
+    double lp = model_eval<FAM, G, NPL, true, LPW, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xs, gs, lpf, &cond_bad);
     if (T != 1.0) { lp = lp / T; QSB_FOR_E gs[e] = gs[e] * invT; }
     QSB_FOR_E p[e] = p[e] + he * gs[e];
     return lp;
@@ -798,7 +815,7 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     rec_dh = dH;
     if (adapting) eps = adapt_step_size(dH, target);
     const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
-    const bool accept = log(u) < dH;
+    const bool accept = cond_bad == 0.0 && log(u) < dH;      // dualTrace.conditionsSatisfied after the last step (hmc.t:164)
     if (accept) {
       store(P.x, xs); store(P.g, gs);
       if (leader()) { P.acc[(size_t)k * P.C + c] += 1; P.lp[c] = newlp; }
@@ -953,13 +970,13 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     }
     rec_step = s0;
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf);
+    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf, &cond_bad);
     if (T != 1.0) lpf = lpf / T;
     const double lp_cur = P.lp[c];
     const double thresh = lpf - lp_cur;
     rec_dh = thresh;
     const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
-    const bool accept = log(u) < thresh;
+    const bool accept = cond_bad == 0.0 && log(u) < thresh;   // `conditionsSatisfied and log(random()) < ...`
     if (accept) {
       acc += 1;
       store(P.x, xp);
@@ -1042,12 +1059,12 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     }
     rec_step = P.ls_scale[c];
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf);
+    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf, &cond_bad);
     if (T != 1.0) lpf = lpf / T;
     const double thresh = lpf - P.lp[c];
     rec_dh = thresh;
     const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
-    const bool accept = log(u) < thresh;
+    const bool accept = cond_bad == 0.0 && log(u) < thresh;   // `conditionsSatisfied and log(random()) < ...`
     if (accept) {
       acc += 1;
       store(P.x, xp);
@@ -1120,11 +1137,12 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     }
     rec_step = FEW ? s3[0] : P.ls_scale[c];
     double lpf = ms.finish(Grp<G>::sum(lp));
+    if (FAM == FAM_INDEP && P.m.cond_lo) cond_bad = Grp<G>::sum(ms.bad); else cond_bad = 0.0;
     if (T != 1.0) lpf = lpf / T;
     const double thresh = lpf - P.lp[c];
     rec_dh = thresh;
     const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
-    const bool accept = log(u) < thresh;
+    const bool accept = cond_bad == 0.0 && log(u) < thresh;   // `conditionsSatisfied and log(random()) < ...`
     if (accept) acc += 1;
     const double ratio = (double)acc / (double)made;
     const bool upd = adapting && ratio >= 0.05 && acc > 5;
@@ -1292,12 +1310,12 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
       QSB_FOR_E { if (e * G + lane == j0) x[e] = new_x; }
     }
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false, true, false>(P, lane, x, gdummy, lpf);
+    model_eval<FAM, G, NPL, false, true, false>(P, lane, x, gdummy, lpf, &cond_bad);
     if (T != 1.0) lpf = lpf / T;
     const double thresh = (lpf - P.lp[c]) + rvslp - fwdlp;
     rec_dh = thresh;
     const double u = uniform_at(P.key, gc, iter, QSB_SLOT_MH_ACCEPT);
-    const bool accept = log(u) < thresh;
+    const bool accept = cond_bad == 0.0 && log(u) < thresh;   // `conditionsSatisfied and log(random()) < ...`
     if (accept) store(P.x, x);
     if (G == 32) __syncwarp();
     if (leader()) {
@@ -1333,14 +1351,14 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
       xp[e] = i < d ? x[e] + (step * (xp[e] / nrm)) : 0.0;
     }
     double lpf, gdummy[NPL];
-    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf);
+    model_eval<FAM, G, NPL, false, true, (FAM == FAM_GAUSS_PREC && QSB_GP_SMEM)>(P, lane, xp, gdummy, lpf, &cond_bad);
     if (T != 1.0) lpf = lpf / T;
     double t = 0.234;
     if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
     const double thresh = lpf - P.lp[c];
     rec_dh = thresh;
     const double u = uniform_at(P.key, gc, iter, (uint32_t)d + 1u);
-    const bool accept = log(u) < thresh;
+    const bool accept = cond_bad == 0.0 && log(u) < thresh;   // `conditionsSatisfied and log(random()) < ...`
     double ns = hscale;
     if (accept) {
       store(P.x, xp);
@@ -1423,11 +1441,12 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     }
     rec_step = s0;
     double lpf = ms.finish(Grp<G>::sum(lp));
+    if (FAM == FAM_INDEP && P.m.cond_lo) cond_bad = Grp<G>::sum(ms.bad); else cond_bad = 0.0;
     if (T != 1.0) lpf = lpf / T;
     const double thresh = lpf - P.lp[c];
     rec_dh = thresh;
     const double u = uniform_at(P.key, gc, iter, (uint32_t)d);
-    const bool accept = log(u) < thresh;
+    const bool accept = cond_bad == 0.0 && log(u) < thresh;   // `conditionsSatisfied and log(random()) < ...`
     if (accept) acc += 1;
     const double ratio = (double)acc / (double)made;
     const bool upd = adapting && ratio >= 0.05 && acc > 5;   // RunningVar:update with the current state (drift.t:26-37, 279-284)
@@ -1490,12 +1509,12 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
   __device__ __forceinline__ bool harm_next_stream(int k, uint32_t iter, double& rec_dh, double& rec_step) const {
     const bool adapting = P.doAdapt[k] != 0;
     const size_t kc = (size_t)k * P.C + c;
-    const double* z = zcol();
     const int stride = zstride();
     const int ne = (d + G - 1) / G;
     const size_t base = (size_t)c * d;
     double* __restrict__ xw = P.x + base;
     gaussian_fill<false>(iter, 0, ne);
+    const double* z = zcol();       // (after the fill: the warp-specialised kernel hands the buffer over in it)
     double nrm = 0.0;
     for (int e = 0; e < ne; ++e) { if (e * G + lane < d) { const double zi = z[e * stride]; nrm += zi * zi; } }
     nrm = sqrt(Grp<G>::sum(nrm));
@@ -1522,13 +1541,14 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
       }
     }
     double lpf = ms.finish(Grp<G>::sum(lp));
+    if (FAM == FAM_INDEP && P.m.cond_lo) cond_bad = Grp<G>::sum(ms.bad); else cond_bad = 0.0;
     if (T != 1.0) lpf = lpf / T;
     double t = 0.234;
     if (d < 5) { double tt = (d - 1) / 4.0; t = (1.0 - tt) * 0.44 + tt * 0.234; }
     const double thresh = lpf - P.lp[c];
     rec_dh = thresh;
     const double u = uniform_at(P.key, gc, iter, (uint32_t)d + 1u);
-    const bool accept = log(u) < thresh;
+    const bool accept = cond_bad == 0.0 && log(u) < thresh;   // `conditionsSatisfied and log(random()) < ...`
     double ns = hscale;
     if (accept) {
       for (int e0 = 0; e0 < ne; e0 += RB) {
@@ -1734,6 +1754,12 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_c
   if (FAM == FAM_INDEP) {
     double lp = 0.0;
     double yv[G == 1 ? NPL : 1];   // sampled values (programs with latent parameters: later choices read them)
+    // rejection initialisation (trace.t:612-623): re-run the program from scratch until every qs.condition holds; attempt a
+    // reads the sub-streams of iteration code QSB_ITER_INIT - a
+    for (uint32_t attempt = 0;; ++attempt) {
+    const uint32_t it_init = QSB_ITER_INIT - attempt;
+    double bad = 0.0;
+    lp = 0.0;
     QSB_FOR_E x[e] = 0.0;
     QSB_FOR_E {
       int i = e * G + lane;
@@ -1752,7 +1778,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_c
             // dirichlet.sample (distrib.t:339-350): K gammas from the choice's sub-stream, normalised; logprob of the
             // sampled vector (distrib.t:352-362); inverse stick breaking (erp.t:219-233), x[K-1] = 0
             const int K = P.m.erp_len[i], Km1 = K - 1;
-            SubStream s(P.key, ch.gc, QSB_ITER_INIT, slot);
+            SubStream s(P.key, ch.gc, it_init, slot);
             double t[32];
             double ssum = 0.0, asum = 0.0;
             for (int k = 0; k < K; ++k) { t[k] = gamma_sample_seq(s, P.m.p0[i + k], 1.0); ssum = ssum + t[k]; asum = asum + P.m.p0[i + k]; }
@@ -1768,14 +1794,17 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_c
             }
           }
         } else {
-          SubStream s(P.key, ch.gc, QSB_ITER_INIT, slot);
+          SubStream s(P.key, ch.gc, it_init, slot);
           double y = erp_sample_seq(kind, s, p0, p1);
           lp += erp_prior_lp(kind, y, p0, p1, nullptr);   // float trace: logprob of the sampled value itself
           if (P.m.fsigma && P.m.fsigma[i] > 0.0) lp += gaussian_lp(y, P.m.fmu[i], P.m.fsigma[i]);   // and the factor that follows it
           x[e] = erp_inv(kind, y, p0, p1);
+          if (P.m.cond_lo && !(y > P.m.cond_lo[i] && y < P.m.cond_hi[i])) bad += 1.0;
           if (G == 1) yv[e] = y;
         }
       }
+    }
+    if (!P.m.cond_lo || Grp<G>::sum(bad) == 0.0 || attempt >= 100000u) break;
     }
     lp0 = Grp<G>::sum(lp);
   } else {

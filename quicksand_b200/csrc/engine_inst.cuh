@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include "engine.cuh"
 
 namespace qsb {
@@ -30,8 +31,11 @@ template <int FAM, int G, int NPL> struct VariantImpl {
   static void logp_grad(const EngineParams& P, void* st) { logp_grad_kernel<FAM, G, NPL><<<grid(P), TPB, 0, (cudaStream_t)st>>>(P); }
   // warp-specialised kernel: persistent grid of CTAs of 4 trajectory warps + 4 * NPROD sampler warps
   template <bool HAS_HMC, bool DRIFT_ONLY> static void advance_ws_t(const EngineParams& P, void* st) {
+    static const int nprod = getenv("QSB_WS_NPROD") ? atoi(getenv("QSB_WS_NPROD")) : 2;   // sampler warpgroups per trajectory warpgroup
+    if (nprod == 1) advance_ws_n<HAS_HMC, DRIFT_ONLY, 1>(P, st); else advance_ws_n<HAS_HMC, DRIFT_ONLY, 2>(P, st);
+  }
+  template <bool HAS_HMC, bool DRIFT_ONLY, int NPROD> static void advance_ws_n(const EngineParams& P, void* st) {
     if constexpr (G == 32) {
-      constexpr int NPROD = 2;
       constexpr int THREADS = 128 * (1 + NPROD);
       constexpr size_t SMEM = (size_t)4 * (HAS_HMC ? 3 : 2) * NPL * 32 * sizeof(double) + 16 * sizeof(uint64_t);
       auto kern = advance_ws_kernel<FAM, NPL, HAS_HMC, DRIFT_ONLY, NPROD>;

@@ -46,6 +46,8 @@ class Program:
             d.erp_lexid = a["erp_lexid"].ctypes.data_as(L.ip)
         if "erp_fsigma" in a:
             d.erp_fmu = _dp(a["erp_fmu"]); d.erp_fsigma = _dp(a["erp_fsigma"])
+        if "erp_cond_lo" in a:
+            d.erp_cond_lo = _dp(a["erp_cond_lo"]); d.erp_cond_hi = _dp(a["erp_cond_hi"])
         if "erp_pref" in a:
             d.erp_pref = a["erp_pref"].ctypes.data_as(L.ip); d.erp_pcoef = _dp(a["erp_pcoef"]); d.erp_ptf = a["erp_ptf"].ctypes.data_as(L.ip)
         return d
@@ -107,7 +109,7 @@ class Program:
         return dict(x=xo, p=po, g=go, lp=lpo)
 
 
-_KIND = {"gaussian": L.ERP_GAUSSIAN, "gamma": L.ERP_GAMMA, "beta": L.ERP_BETA, "uniform": L.ERP_UNIFORM}
+_KIND = {"gaussian": L.ERP_GAUSSIAN, "gamma": L.ERP_GAMMA, "beta": L.ERP_BETA, "uniform": L.ERP_UNIFORM, "neggamma": L.ERP_NEGGAMMA}
 
 
 class latent:
@@ -119,7 +121,7 @@ class latent:
         self.entry, self.a, self.b, self.exp = int(entry), float(a), float(b), bool(exp)
 
 
-def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
+def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None, conditions=None):
     """ERPs in program order with constant parameters (or ``latent`` ones, see above), e.g. ``[("gamma", 2.0, 2.0)]`` with ret_div=10 for
     ``return qs.gamma(2.0, 2.0, {struc=false})/10.0`` (test/testsuite.t:657-673).  Entries:
 
@@ -131,9 +133,13 @@ def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
     ``factors[i]``: ``None`` or ``(mu, sigma)``: the statement ``qs.factor(gaussian.logprob(value_i, mu, sigma))`` (equally
     ``qs.gaussian.observe(value_i, mu, sigma)``) right after scalar choice i (test/testsuite.t:394-442).
 
+    ``conditions[i]``: ``None`` or ``(lo, hi)``: the statement ``qs.condition(value_i > lo and value_i < hi)`` right after scalar
+    choice i (``None`` / +-inf on a side = no bound): hard constraint, rejection initialisation, accept tests that require it
+    (trace.t:612-623, 794-796).  ("neggamma", shape, scale): value = -gamma(shape, scale) under Bounds.Upper(0) (erp.t:158-173).
+
     ``lexids[i]``: call-site id of entry i (entries produced by one ERP call inside a loop share an id); only
     DriftKernel{lexicalScaleSharing=true} looks at it (drift.t:208-235).  Default: every entry is its own call site."""
-    kinds, p0, p1, lex, fmu, fsig = [], [], [], [], [], []
+    kinds, p0, p1, lex, fmu, fsig, clo, chi = [], [], [], [], [], [], [], []
     pref, pcoef, ptf, comp_of_entry = [], [], [], []
     for n_e, e in enumerate(erps):
         k = e[0]
@@ -143,15 +149,19 @@ def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
         if k == "dirichlet":
             assert fac is None, "factors on a dirichlet choice are not supported"
             alphas = [float(a) for a in e[1]]
+            assert conditions is None or conditions[n_e] is None, "conditions on a dirichlet choice are not supported"
             for j, a in enumerate(alphas):
                 kinds.append(L.ERP_DIRICHLET); p0.append(a); p1.append(float(j)); lex.append(site); fmu.append(0.0); fsig.append(0.0)
+                clo.append(-np.inf); chi.append(np.inf)
                 pref += [-1, -1]; pcoef += [0.0, 0.0]; ptf += [0, 0]
             continue
         lex.append(site)
         fmu.append(0.0 if fac is None else float(fac[0])); fsig.append(0.0 if fac is None else float(fac[1]))
+        cnd = None if conditions is None else conditions[n_e]
+        clo.append(-np.inf if cnd is None or cnd[0] is None else float(cnd[0])); chi.append(np.inf if cnd is None or cnd[1] is None else float(cnd[1]))
         for q in (1, 2):
             if isinstance(e[q], latent):
-                assert k in ("gaussian", "gamma", "beta"), "latent parameters: gaussian, gamma and beta choices"
+                assert k in ("gaussian", "gamma", "beta", "neggamma"), "latent parameters: gaussian, gamma, beta and neggamma choices"
                 assert 0 <= e[q].entry < n_e and erps[e[q].entry][0] != "dirichlet", "a latent parameter refers to an earlier scalar entry"
                 pref.append(comp_of_entry[e[q].entry]); pcoef.append(e[q].b); ptf.append(1 if e[q].exp else 0)
             else:
@@ -167,6 +177,8 @@ def indep(erps, ret="sum", ret_div=1.0, lexids=None, factors=None):
     extra = {} if lexids is None else {"erp_lexid": np.array(lex, dtype=np.int32)}
     if factors is not None:
         extra.update(erp_fmu=np.array(fmu, dtype=np.float64), erp_fsigma=np.array(fsig, dtype=np.float64))
+    if conditions is not None:
+        extra.update(erp_cond_lo=np.array(clo, dtype=np.float64), erp_cond_hi=np.array(chi, dtype=np.float64))
     if any(r >= 0 for r in pref):
         extra.update(erp_pref=np.array(pref, dtype=np.int32), erp_pcoef=np.array(pcoef, dtype=np.float64), erp_ptf=np.array(ptf, dtype=np.int32))
     return Program(L.FAM_INDEP, len(kinds), erp_kind=np.array(kinds, dtype=np.int32), erp_p0=np.array(p0, dtype=np.float64),

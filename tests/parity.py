@@ -17,7 +17,8 @@ def oracle_program(p):
     if p.family == L.FAM_INDEP:
         return O.Program.indep(a["erp_kind"], a["erp_p0"], a["erp_p1"], p.ret_mode, p.ret_div, lexids=a.get("erp_lexid"),
                                fmu=a.get("erp_fmu"), fsigma=a.get("erp_fsigma"),
-                               pref=a.get("erp_pref"), pcoef=a.get("erp_pcoef"), ptf=a.get("erp_ptf"))
+                               pref=a.get("erp_pref"), pcoef=a.get("erp_pcoef"), ptf=a.get("erp_ptf"),
+                               cond_lo=a.get("erp_cond_lo"), cond_hi=a.get("erp_cond_hi"))
     if p.family == L.FAM_GAUSS_PREC:
         return O.Program.gauss_prec(a["A"])
     if p.family == L.FAM_LOGISTIC:

@@ -82,6 +82,16 @@ def _programs(qs):
                                          factors=[None] * 9 + [(0.4, 0.2), None, (0.5, 1.0)])
     progs["hierdir9"] = qs.programs.indep([("gamma", 3.0, 1.0), ("dirichlet", [2.0, 3.0, 5.0]), ("gamma", lat(0), 2.0), ("gaussian", 0.0, 1.0),
                                             ("dirichlet", [0.7, 1.5, 1.0]), ("gaussian", lat(3), lat(2, a=0.1))], ret="vector")
+    # Bounds.Upper (erp.t:158-173) through a user-defined ERP, and qs.condition statements (trace.t:794-796): hard constraints with
+    # rejection initialisation and `conditionsSatisfied and ...` accept tests
+    progs["neggamma1"] = qs.programs.indep([("neggamma", 2.0, 2.0)], ret_div=10.0)
+    progs["upper5"] = qs.programs.indep([("neggamma", 2.0, 2.0), ("gaussian", 0.1, 0.5), ("neggamma", 0.7, 1.5), ("gamma", 2.0, 2.0), ("neggamma", 3.0, 0.5)], ret="vector")
+    progs["cond5"] = qs.programs.indep([("gaussian", 0.0, 1.0), ("neggamma", 2.0, 1.5), ("gamma", 2.0, 2.0), ("uniform", -1.0, 1.0), ("gaussian", 1.0, 2.0)], ret="vector",
+                                        conditions=[(-0.5, None), (None, -0.1), (0.2, 9.0), None, (-1.0, 3.0)])
+    progs["cond5w"] = qs.programs.indep([("gaussian", 0.0, 1.0), ("neggamma", 2.0, 1.5), ("gamma", 2.0, 2.0), ("uniform", -1.0, 1.0), ("gaussian", 1.0, 2.0)] * 8, ret="vector",
+                                         conditions=[(-1.5, None), (None, -0.01), (0.02, 30.0), None, (-5.0, 7.0)] * 8)          # 40 components: warp per chain
+    progs["condhier4"] = qs.programs.indep([("gaussian", 1.0, 0.5), ("gaussian", 0.0, 0.5), ("gaussian", lat(0), lat(1, b=0.5, exp=True)),
+                                             ("gaussian", lat(2, a=0.5, b=2.0), 1.0)], ret="vector", conditions=[(0.0, None), None, (-1.0, 4.0), None])
     progs["c2"] = qs.programs.c2_correlated_gaussian()[0]
     J = 11
     progs["schools13"] = qs.programs.eight_schools(rng.normal(4, 10, J), rng.uniform(8, 18, J))
@@ -96,7 +106,7 @@ def _programs(qs):
 
 
 @pytest.mark.parametrize("name", ["gaussian1", "gamma1", "beta1", "uniform1", "gauss10", "mixed10", "dirichlet4", "dirmix9", "wide24", "factor1", "factor6", "hier4", "hier12", "hierdir9", "c2",
-                                  "schools13", "schools62", "funnel12", "funnel70", "logistic20"])
+                                  "schools13", "schools62", "funnel12", "funnel70", "logistic20", "neggamma1", "upper5", "cond5", "cond5w", "condhier4"])
 def test_logp_and_gradient_match_tape_ad(qs, oracle, name):
     """Closed-form device gradients vs the oracle's tape AD (qs/lib/ad.t) on random unconstrained points."""
     prog = _programs(qs)[name]
@@ -123,6 +133,9 @@ HMC_FIXED = [
     ("mixed10", dict(numSteps=5, stepSize=0.1), 32, 1.0),
     ("hier4", dict(numSteps=10, stepSize=0.05), 0, 1.0), ("hier12", dict(numSteps=5, stepSize=0.02), 0, 0.9), ("hierdir9", dict(numSteps=5, stepSize=0.03), 0, 0.9),
     ("c2", dict(numSteps=16, stepSize=0.15), 0, 1.0), ("c2", dict(numSteps=16, stepSize=0.15), 4, 1.0),   # 4: four lanes per chain
+    ("neggamma1", dict(numSteps=10, stepSize=0.2), 0, 1.0), ("upper5", dict(numSteps=5, stepSize=0.1), 0, 1.0), ("upper5", dict(numSteps=5, stepSize=0.1), 32, 1.0),
+    ("cond5", dict(numSteps=5, stepSize=0.15), 0, 1.0), ("cond5", dict(numSteps=5, stepSize=0.15), 32, 1.0), ("cond5w", dict(numSteps=4, stepSize=0.05), 0, 1.0),
+    ("condhier4", dict(numSteps=6, stepSize=0.05), 0, 1.0),
     ("schools13", dict(numSteps=8, stepSize=0.02), 1, 0.95), ("schools13", dict(numSteps=8, stepSize=0.02), 32, 0.95),
     ("schools62", dict(numSteps=8, stepSize=0.02), 0, 0.95),
     ("funnel12", dict(numSteps=16, stepSize=0.01), 1, 0.9), ("funnel12", dict(numSteps=16, stepSize=0.01), 32, 0.9),
@@ -178,7 +191,7 @@ def test_hmc_adaptive_search_and_dual_averaging(qs, oracle, name, L, mapping, mi
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("c2", 0), ("c2", 4), ("schools13", 1), ("schools13", 32), ("schools62", 0),
                                           ("funnel12", 1), ("funnel70", 0), ("mixed10", 0), ("dirichlet4", 0), ("dirmix9", 0), ("wide24", 0), ("logistic20", 0), ("factor6", 0), ("factor6", 32),
-                                          ("hier4", 0), ("hier12", 0), ("hierdir9", 0)])
+                                          ("hier4", 0), ("hier12", 0), ("hierdir9", 0), ("upper5", 0), ("upper5", 32), ("cond5", 0), ("cond5", 32), ("cond5w", 0), ("condhier4", 0)])
 def test_drift_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.DriftKernel(scale=0.3), chains=64, iters=400, seed=99, mapping=mapping)
@@ -204,7 +217,8 @@ def test_drift_lexical_scale_sharing_parity(qs, oracle, name, mapping):
 
 
 @pytest.mark.parametrize("name,mapping", [("gauss10", 0), ("gaussian1", 0), ("c2", 0), ("c2", 4), ("schools13", 32), ("schools62", 0),
-                                          ("funnel12", 1), ("funnel70", 0), ("dirichlet4", 0), ("logistic20", 0), ("hier4", 0), ("hier12", 0)])
+                                          ("funnel12", 1), ("funnel70", 0), ("dirichlet4", 0), ("logistic20", 0), ("hier4", 0), ("hier12", 0),
+                                          ("upper5", 0), ("cond5", 0), ("cond5", 32), ("cond5w", 0), ("condhier4", 0)])
 def test_harm_per_step_parity(qs, oracle, name, mapping):
     prog = _programs(qs)[name]
     gpu, cpu = P.run_both(prog, qs.HARMKernel(), chains=64, iters=300, seed=5, mapping=mapping)
@@ -214,7 +228,7 @@ def test_harm_per_step_parity(qs, oracle, name, mapping):
 
 TRACEMH = [("hier4", 0), ("hier12", 0), ("hierdir9", 0), ("factor1", 0), ("factor6", 0), ("factor6", 32), ("gaussian1", 0), ("gamma1", 0), ("beta1", 0), ("uniform1", 0), ("gauss10", 0), ("mixed10", 0), ("mixed10", 32), ("dirichlet4", 0),
            ("dirmix9", 0), ("wide24", 0), ("c2", 0), ("c2", 4), ("schools13", 1), ("schools13", 32), ("schools62", 0), ("funnel12", 1), ("funnel12", 32),
-           ("funnel70", 0)]
+           ("funnel70", 0), ("neggamma1", 0), ("upper5", 0), ("cond5", 0), ("cond5", 32), ("condhier4", 0)]
 
 
 @pytest.mark.parametrize("name,mapping", TRACEMH)
@@ -751,6 +765,27 @@ def test_glm_stream_k_decomposition_parity(qs, oracle, monkeypatch):
                               (qs.HARMKernel(), 60, 1.0), (qs.HMCKernel(numSteps=1), 15, 0.8)]:
         gpu, cpu = P.run_both(small, kern, chains=200, iters=iters, seed=3)      # 200 chains of 333 rows: 3 tiles x 11 row blocks in runs of 12
         P.compare(gpu, cpu, TOL, what="logistic20 stream-K %d" % kern.specs[0].kind, min_compared=minc)
+
+
+def test_conditions_hold_and_reject(qs, oracle):
+    """qs.condition (trace.t:794-796): every chain starts inside the constraints (rejection initialisation, trace.t:612-623,
+    bit-equal to the oracle's retries), never leaves them under any kernel, and proposals that violate them are rejected
+    whatever their density (the accept decisions equal the oracle's, which evaluates `conditionsSatisfied and ...`)."""
+    prog = _programs(qs)["cond5"]
+    lo = np.array([-0.5, -np.inf, 0.2, -np.inf, -1.0]); hi = np.array([np.inf, -0.1, 9.0, np.inf, 3.0])
+    for kern, mapping in [(qs.HMCKernel(numSteps=5, stepSize=0.4, doStepSizeAdapt=False), 0), (qs.DriftKernel(scale=1.5), 0), (qs.DriftKernel(scale=1.5), 32),
+                          (qs.HARMKernel(scale=3.0, doScaleAdapt=False), 32), (qs.TraceMHKernel(doStruct=False), 0),
+                          (qs.MixtureKernel([qs.HARMKernel(), qs.HMCKernel(numSteps=4, stepSize=0.3, doStepSizeAdapt=False), qs.DriftKernel()], [0.3, 0.4, 0.3]), 0)]:
+        gpu, cpu = P.run_both(prog, kern, chains=96, iters=150, seed=8, mapping=mapping)
+        P.compare(gpu, cpu, TOL, what="conditions %s map%d" % ([s.kind for s in kern.specs], mapping))
+        v = gpu["samples"]
+        assert (v > lo).all() and (v < hi).all()
+        assert 0.05 < gpu["accept"].mean() < 0.98
+    # without the conditions the same kernel wanders outside: the constraint is what keeps it in
+    free = qs.programs.indep([("gaussian", 0.0, 1.0), ("neggamma", 2.0, 1.5), ("gamma", 2.0, 2.0), ("uniform", -1.0, 1.0), ("gaussian", 1.0, 2.0)], ret="vector")
+    s = qs.Sampler(free, qs.DriftKernel(scale=1.5), numchains=96, seed=8); s.init(); s.run(150)
+    fv = s.fetch_values(); s.close()
+    assert not ((fv > lo).all() and (fv < hi).all())
 
 
 def test_single_chain_reference_protocol(qs, oracle):

@@ -47,7 +47,7 @@ def test_c2_adaptive_L16_every_leapfrog_step(qs, oracle):
 
 SMALL = [("gaussian1", 10, 0), ("gamma1", 10, 0), ("beta1", 10, 0), ("uniform1", 10, 0), ("gauss10", 10, 0), ("mixed10", 5, 32), ("mixed10", 5, 1),
          ("dirichlet4", 10, 0), ("schools13", 8, 32), ("schools13", 8, 1), ("funnel12", 16, 1), ("funnel12", 16, 32), ("logistic20", 20, 0),
-         ("hier12", 2, 0), ("c2", 16, 4)]
+         ("hier12", 2, 0), ("c2", 16, 4), ("upper5", 5, 0), ("upper5", 5, 32)]
 
 
 @pytest.mark.parametrize("name,L,mapping", SMALL)
