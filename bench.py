@@ -478,13 +478,13 @@ def main():
                   "timing_pass": "%d extra steps after the timed region with a CUDA-event pair around every launch of the kernel "
                                  "(%.3f ms per step in that pass vs %.3f ms in the timed region)" % (Kr, 1e3 * t_roof / max(Kr, 1), 1e3 * t / K)}
         if wl["bound"] == "hbm":
-            achieved = wl["bytes_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e9
+            achieved = wl["bytes_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e9 if klaunch else float("nan")
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
             peak = float(mp.get("hbm_gbs", 6650.0))
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if mp else "fallback 6.65 TB/s"}
         else:
-            achieved = wl["flops_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e12
+            achieved = wl["flops_per_unit"] * per_launch_units / (ktime / max(klaunch, 1)) / 1e12 if klaunch else float("nan")
             peak = peaks[wl["peak_kind"]]
             roof = {"bound": wl["bound"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "measured in this run on this GPU by qsb_measure_fp64_peak (%s: %s), best launch over ~0.3 s; "

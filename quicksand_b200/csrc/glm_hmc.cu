@@ -173,8 +173,10 @@ template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps(SigState
 // contraction the k <-> dimension map of that tile becomes k-step 0 = dims 8(NJ-1) + tig and its all-padding second
 // k-step is not issued (100 instead of 104 DMMAs per row block); the second contraction is unchanged.
 // SK: the balanced decomposition below (GradParams::sk_U > 0) instead of the (chain tile, row split) grid.
-template <int NJ, bool FULL, bool LP, bool TRIM = false, bool SK = false>
-__global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_constant__ GradParams P) {
+// COH: Theta was written by OTHER SMs earlier in this same launch (glm_traj_kernel: the leapfrog update between two gradient
+// evaluations runs inside the kernel): read it past the non-coherent L1.
+template <int NJ, bool FULL, bool LP, bool TRIM, bool SK, bool COH>
+__device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pending) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   const size_t SD = stage_doubles(P.S);
@@ -182,8 +184,6 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + SD * NST);
   uint64_t* empty = full + STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  pdl_trigger();
-  bool pdl_pending = true;      // Theta (and the partial-sum buffers this kernel overwrites) belong to the predecessor until pdl_wait
   // Work decomposition.  sk_U == 0: CTA = (chain tile, row split), grid = ntiles x ksplit.  sk_U > 0: the ntiles x nblocks
   // row-block units, tile-major, are cut into sk_U runs of equal COST, one run per CTA (grid = number of SMs: one full
   // wave for any chain count; a unit of the partially filled last tile costs what its live warps cost -- glm_layout()); a
@@ -262,13 +262,14 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
     if (!THETA_SMEM) {
       th[J % (THETA_SMEM ? 1 : NJ)][0] = th[J % (THETA_SMEM ? 1 : NJ)][1] = 0.0;
       if ((FULL || J < nj) && valid) {
-        double2 v = *reinterpret_cast<const double2*>(P.theta + (size_t)chain * P.Dp + 8 * J + 2 * tig);
+        const double2* tp = reinterpret_cast<const double2*>(P.theta + (size_t)chain * P.Dp + 8 * J + 2 * tig);
+        double2 v = COH ? __ldcg(tp) : *tp;
         th[J % (THETA_SMEM ? 1 : NJ)][0] = v.x; th[J % (THETA_SMEM ? 1 : NJ)][1] = v.y;
       }
     }
   }
   double thL = 0.0;                                     // TRIM: theta[8(NJ-1) + tig]
-  if (TRIM && valid) thL = P.theta[(size_t)chain * P.Dp + 8 * (NJ - 1) + tig];
+  if (TRIM && valid) thL = COH ? __ldcg(P.theta + (size_t)chain * P.Dp + 8 * (NJ - 1) + tig) : P.theta[(size_t)chain * P.Dp + 8 * (NJ - 1) + tig];
   double lpacc = 0.0;
   const int offA = rho_g * S + 2 * tig;                 // phase 1 B fragment: X[rho(gid)][8J + 2tig .. +1]
   const int offL = rho_g * S + 8 * (NJ - 1) + tig;      // TRIM: X[rho(gid)][8(NJ-1) + tig]
@@ -434,6 +435,13 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_
   }
 }
 
+template <int NJ, bool FULL, bool LP, bool TRIM = false, bool SK = false>
+__global__ void __launch_bounds__(GRAD_THREADS, 1) glm_grad_kernel(const __grid_constant__ GradParams P) {
+  pdl_trigger();
+  bool pdl_pending = true;      // Theta (and the partial-sum buffers this kernel overwrites) belong to the predecessor until pdl_wait
+  glm_grad_body<NJ, FULL, LP, TRIM, SK, false>(P, pdl_pending);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Vector kernels: one warp per chain, lanes over dimensions.
 enum { V_INIT_SAMPLE = 0, V_FINISH_EVAL = 1, V_TRANS_FIRST = 2, V_TRANS_MID = 3, V_TRANS_LAST = 4, V_PROBE_FIRST = 5, V_PROBE_LAST = 6,
@@ -472,13 +480,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 // number of partial sums the stream-K gradient kernel left for chain c (its tile's segments)
 __device__ __forceinline__ int n_partials_sk(const VecParams& P, uint32_t c) { return P.sk_np[c / (uint32_t)P.sk_CB]; }
 // gradient and (optionally) log-density of the chain at xs from the partial sums of the GEMM kernel
+template <bool COH = false>
 __device__ __forceinline__ double finish_grad(const VecParams& P, uint32_t c, int i, double th) {
   double gl = 0.0;
   if (!P.sk_U) {
     for (int r = 0; r < P.ksplit; ++r) gl += P.partG[((size_t)r * P.C + c) * P.Dp + i];
   } else {
     const int np = n_partials_sk(P, c);
-    for (int r = 0; r < np; ++r) gl += P.partG[((size_t)r * P.C + c) * P.Dp + i];
+    if (COH) { for (int r = 0; r < np; ++r) gl += __ldcg(P.partG + ((size_t)r * P.C + c) * P.Dp + i); }   // written by other SMs in this launch
+    else for (int r = 0; r < np; ++r) gl += P.partG[((size_t)r * P.C + c) * P.Dp + i];
   }
   const double g = gaussian_dlp_dx(th, 0.0, P.prior_sigma) + gl;
   return P.T != 1.0 ? g * P.invT : g;
@@ -495,6 +505,24 @@ __device__ __forceinline__ double finish_lp(const VecParams& P, uint32_t c, int 
     for (int r = 0; r < np; ++r) ll += P.partLp[(size_t)r * P.C + c];
   }
   return lpp + ll;   // at temperature 1; callers divide
+}
+
+// finish leapfrog step `step` of chain c (second half-kick), start the next one (hmc.t:307-323); one warp
+template <bool COH>
+__device__ __forceinline__ void trans_mid_chain(const VecParams& P, uint32_t c, int lane, uint32_t step) {
+  const int d = P.d;
+  const size_t base = (size_t)c * P.Dp;
+  double* xs = P.xs + base; double* p = P.p + base;
+  const double eps = P.eps[c];
+  const double he = 0.5 * eps;
+  for (int i = lane; i < d; i += 32) {
+    double pos = xs[i];
+    double gn = finish_grad<COH>(P, c, i, pos);
+    double m = p[i] + he * gn;
+    if (P.rec_leap) P.rec_leap[(((size_t)c * P.rec_iters + P.rec_row) * P.L + step) * d + i] = pos;
+    m = m + he * gn;
+    p[i] = m; xs[i] = pos + eps * m * 1.0;
+  }
 }
 
 template <int MODE>
@@ -651,18 +679,7 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
     }
     return;
   }
-  if (MODE == V_TRANS_MID) {
-    // finish leapfrog step `step` (second half-kick), start the next one (hmc.t:307-323)
-    for (int i = lane; i < d; i += 32) {
-      double pos = xs[i];
-      double gn = finish_grad(P, c, i, pos);
-      double m = p[i] + he * gn;
-      if (P.rec_leap) P.rec_leap[(((size_t)c * P.rec_iters + P.rec_row) * P.L + P.step) * d + i] = pos;
-      m = m + he * gn;
-      p[i] = m; xs[i] = pos + eps * m * 1.0;
-    }
-    return;
-  }
+  if (MODE == V_TRANS_MID) { trans_mid_chain<false>(P, c, lane, P.step); return; }
   if (MODE == V_PROBE_LAST) {
     if (P.done[c]) return;
     // searchForInitialStepSize bookkeeping (hmc.t:345-391); the momentum half-kick is irrelevant to it
@@ -746,6 +763,43 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
 }
 
 // ---------------------------------------------------------------------------------------------
+// The interior of a trajectory in ONE launch: `nsteps` gradient evaluations, each followed by the leapfrog update that
+// produces the next Theta (V_TRANS_MID), with grid-wide barriers in place of the 2 x nsteps kernel boundaries.  Balanced
+// decomposition only (one CTA per SM, all co-resident: cooperative launch).  What it saves is the ~13 us per leapfrog step
+// that sit outside the gradient kernel at small chain counts (launch gaps + the vector kernel's own launch): at 1 024 chains
+// per GPU -- BASELINE's c3 on 8 GPUs -- that is 8 % of the step.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+  }
+  __syncthreads();
+}
+template <int NJ, bool FULL, bool TRIM>
+__global__ void __launch_bounds__(GRAD_THREADS, 1) glm_traj_kernel(const __grid_constant__ GradParams P, const __grid_constant__ VecParams V,
+                                                                   int nsteps, unsigned step0, unsigned* counter) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + stage_doubles(P.S) * P.stages);
+  uint64_t* empty = full + STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned target = 0;
+  bool no_pdl = false;
+  for (int s = 0; s < nsteps; ++s) {
+    glm_grad_body<NJ, FULL, false, TRIM, true, true>(P, no_pdl);
+    __syncthreads();
+    if (threadIdx.x == 0) for (int q = 0; q < P.stages; ++q) { mbar_inval(&full[q]); mbar_inval(&empty[q]); }
+    grid_barrier(counter, target);             // every partial sum of this evaluation is in L2
+    for (uint32_t c = blockIdx.x * CW + warp; c < V.C; c += gridDim.x * CW) trans_mid_chain<true>(V, c, lane, step0 + (unsigned)s);
+    grid_barrier(counter, target);             // the next Theta is complete
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct GlmSampler {
   GlmModel* m = nullptr;
   cudaStream_t stream = nullptr;
@@ -768,6 +822,8 @@ struct GlmSampler {
   size_t tev_used = 0;
   double t_accum = 0.0; uint64_t t_launches = 0;
   std::vector<double> temps;   // AnnealingKernel schedule (host: the launches of an iteration carry its temperature)
+  unsigned* traj_counter = nullptr;   // grid-barrier counter of glm_traj_kernel
+  bool fused_traj = false;            // the interior of a trajectory runs as one cooperative launch
 };
 
 static int pick_ksplit(int ntiles, int nblocks, int nsm) {
@@ -824,6 +880,33 @@ static cudaError_t launch_grad(int nj_inst, const GradParams& P, size_t smem, cu
     case 4: return launch_grad_t<4>(P, smem, st);
     case 13: return launch_grad_t<13>(P, smem, st);
     case 16: return launch_grad_t<16>(P, smem, st);
+  }
+  return cudaErrorInvalidValue;
+}
+template <int NJ> static cudaError_t launch_traj_t(const GradParams& P, const VecParams& V, int nsteps, unsigned* counter, size_t smem, cudaStream_t st) {
+  auto go = [&](auto kern) -> cudaError_t {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set[dev & 63] = true;
+    }
+    unsigned step0 = 0;
+    void* args[] = {(void*)&P, (void*)&V, (void*)&nsteps, (void*)&step0, (void*)&counter};
+    return cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)P.sk_U), dim3(GRAD_THREADS), args, smem, st);
+  };
+  if constexpr (NJ == 13) { if (P.nj == NJ && P.d <= 8 * (NJ - 1) + 4) return go(glm_traj_kernel<NJ, true, true>); }
+  if (P.nj == NJ) return go(glm_traj_kernel<NJ, true, false>);
+  return go(glm_traj_kernel<NJ, false, false>);
+}
+static cudaError_t launch_traj(int nj_inst, const GradParams& P, const VecParams& V, int nsteps, unsigned* counter, size_t smem, cudaStream_t st) {
+  switch (nj_inst) {
+    case 2: return launch_traj_t<2>(P, V, nsteps, counter, smem, st);
+    case 4: return launch_traj_t<4>(P, V, nsteps, counter, smem, st);
+    case 13: return launch_traj_t<13>(P, V, nsteps, counter, smem, st);
+    case 16: return launch_traj_t<16>(P, V, nsteps, counter, smem, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -992,6 +1075,11 @@ GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t 
   if (!ok || !s->nj_inst) { why = !s->nj_inst ? "unsupported dim" : "cudaMalloc failed"; glm_sampler_destroy(s); return nullptr; }
   G.partG = partG; G.partLp = partLp; V.partG = partG; V.partLp = partLp;
   G.theta = V.xs;
+  if (G.sk_U && kind == 1 && numSteps >= 2 && !getenv("QSB_NO_FUSED_TRAJ")) {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (coop && G.sk_U <= nsm && dalloc(s, &s->traj_counter, 1)) s->fused_traj = true;
+  }
   return s;
 }
 
@@ -1198,7 +1286,19 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
     V.iter = (uint32_t)(s->iter_base + it); V.rec_row = it;
     V.T = temp_at(s, it); V.invT = 1.0 / V.T;
     GCU(launch_vec<V_TRANS_FIRST>(s, V));
-    for (uint32_t st = 0; st < s->L; ++st) {
+    uint32_t st_begin = 0;
+    if (s->fused_traj && !(s->flags & QSB_FLAG_TIME_KERNEL)) {
+      // leapfrog steps 0 .. L-2 (gradient + update) as one cooperative launch; the last gradient (which also evaluates the
+      // log-likelihood) and the accept step follow as before.  With QSB_FLAG_TIME_KERNEL the launches stay separate so that
+      // the event pairs bracket the gradient contraction alone.
+      GradParams Gp = s->Gp;
+      Gp.theta = V.xs; Gp.want_lp = 0; Gp.want_grad = 1;
+      GCU(cudaMemsetAsync(s->traj_counter, 0, sizeof(unsigned), s->stream));
+      GCU(launch_traj(s->nj_inst, Gp, V, (int)s->L - 1, s->traj_counter, s->smem, s->stream));
+      ++s->launches; s->grad_evals += s->L - 1;
+      st_begin = s->L - 1;
+    }
+    for (uint32_t st = st_begin; st < s->L; ++st) {
       const bool last = st + 1 == s->L;
       V.step = st;
       GCU(run_grad(s, V.xs, last ? 1 : 0));
