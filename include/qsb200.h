@@ -151,6 +151,10 @@ typedef struct {
   uint64_t iterations;                    /* MCMC iterations done so far (per chain) */
   uint64_t kernel_launches;               /* CUDA kernels launched by this sampler so far */
   double seconds;                         /* device time of the last qsb_sampler_run / advance (CUDA events) */
+  /* chain health, summed over chains since the last init / set_state: transitions whose accept threshold was not finite (a NaN
+   * or infinite log-density: the proposal left the support or overflowed; always rejected), and HMC transitions whose energy
+   * error exceeded 1000 in magnitude (divergent trajectories: the step size is too large for the local curvature) */
+  uint64_t nonfinite, divergent;
 } qsb_stats;
 
 int qsb_version(void);

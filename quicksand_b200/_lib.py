@@ -43,7 +43,7 @@ class Stats(C.Structure):
     _fields_ = [("props_made", C.c_uint64), ("props_accepted", C.c_uint64),
                 ("sub_made", C.c_uint64 * 8), ("sub_accepted", C.c_uint64 * 8),
                 ("grad_evals", C.c_uint64), ("leapfrog_steps", C.c_uint64), ("iterations", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("seconds", C.c_double)]
+                ("kernel_launches", C.c_uint64), ("seconds", C.c_double), ("nonfinite", C.c_uint64), ("divergent", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/qsb200.h declares

@@ -213,7 +213,7 @@ class Sampler:
         n = len(self.kernel.specs)
         return dict(props_made=st.props_made, props_accepted=st.props_accepted, sub_made=list(st.sub_made)[:n],
                     sub_accepted=list(st.sub_accepted)[:n], grad_evals=st.grad_evals, leapfrog_steps=st.leapfrog_steps,
-                    iterations=st.iterations, kernel_launches=st.kernel_launches, seconds=st.seconds)
+                    iterations=st.iterations, kernel_launches=st.kernel_launches, seconds=st.seconds, nonfinite=st.nonfinite, divergent=st.divergent)
 
     def set_kernel_timing(self, on):
         L.check(L.lib().qsb_sampler_set_kernel_timing(self.h, int(bool(on))))
@@ -330,7 +330,7 @@ class Group:
         n = len(self.kernel.specs)
         return dict(props_made=st.props_made, props_accepted=st.props_accepted, sub_made=list(st.sub_made)[:n],
                     sub_accepted=list(st.sub_accepted)[:n], grad_evals=st.grad_evals, leapfrog_steps=st.leapfrog_steps,
-                    iterations=st.iterations, kernel_launches=st.kernel_launches, seconds=st.seconds)
+                    iterations=st.iterations, kernel_launches=st.kernel_launches, seconds=st.seconds, nonfinite=st.nonfinite, divergent=st.divergent)
 
     def diagnostics_raw(self, maxlag=0):
         """The sufficient statistics of qsb_sampler_diagnostics summed over the shards (NCCL all-reduce inside the library)."""

@@ -932,6 +932,7 @@ int qsb_sampler_stats(qsb_sampler* s, qsb_stats* out) {
   if (s->glm) {
     std::string why;
     if (glm_sampler_stats(s->glm, &out->props_made, &out->props_accepted, &out->grad_evals, &out->leapfrog_steps, &out->kernel_launches, &out->seconds, why)) return fail(5, why);
+    glm_sampler_health(s->glm, &out->nonfinite, &out->divergent);
     out->sub_made[0] = out->props_made; out->sub_accepted[0] = out->props_accepted;
     out->iterations = s->iter;
     return 0;
@@ -948,6 +949,7 @@ int qsb_sampler_stats(qsb_sampler* s, qsb_stats* out) {
   }
   for (int k = 0; k < P.nsub; ++k) { out->props_made += out->sub_made[k]; out->props_accepted += out->sub_accepted[k]; }
   out->grad_evals = counters[0]; out->leapfrog_steps = counters[1];
+  out->nonfinite = counters[2]; out->divergent = counters[3];
   out->iterations = s->iter; out->kernel_launches = s->launches;
   float ms = 0.f;
   // (events that were never recorded make cudaEventElapsedTime fail AND leave that error pending for the next

@@ -538,7 +538,17 @@ static __device__ __forceinline__ void gaussian_fill_body(uint32_t k0, uint32_t 
       const double qq = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, __dsub_rn(__dmul_rn(0.196, y), __dmul_rn(0.25472, x))));
       if (!(qq >= 0.27597)) ok = true;
       else if (qq > 0.27846) ok = false;
-      else ok = !(__dmul_rn(v, v) > __dmul_rn(__dmul_rn(__dmul_rn(-4.0, u), u), log(u)));
+      else {
+        // The exact test v^2 > -4 u^2 log(u) (distrib.t:71) is reached by 0.85 % of the attempts, i.e. by some lane of a warp in
+        // 23 % of the trips, and the double-precision log() then costs every lane ~90 instructions.  A single-precision log
+        // decides it first: |__logf(u) - log(u)| < 1e-5 for every u in [2^-53, 1], so outside the band |v^2 - R_f| <= 4 u^2 * 2e-5
+        // the decision equals the exact one; inside it (~1e-6 of the attempts) the exact expression is evaluated.
+        const double u2x4 = __dmul_rn(__dmul_rn(4.0, u), u), vv = __dmul_rn(v, v);
+        const double rf = u2x4 * (double)(-__logf((float)u)), band = u2x4 * 2e-5;
+        if (vv > rf + band) ok = false;
+        else if (vv < rf - band) ok = true;
+        else ok = !(vv > __dmul_rn(__dmul_rn(__dmul_rn(-4.0, u), u), log(u)));
+      }
       if (ok) zw[(ci / (uint32_t)G) * rstride + q * (uint32_t)G + (ci % (uint32_t)G)] = v / u;
     }
     const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -575,7 +585,9 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
   const int d;
   WsLink* const link;
   mutable const double* zptr = nullptr;   // WS: this lane's column of the staging rows currently being read
-  mutable unsigned long long cnt[2] = {0, 0};  // gradient evaluations / leapfrog steps of this group, flushed once per launch
+  // gradient evaluations / leapfrog steps / transitions whose accept threshold was not finite (NaN or +-inf log-density: the
+  // chain left the support or overflowed) / HMC transitions with |dH| > 1000 (divergent); of this group, flushed once per launch
+  mutable unsigned long long cnt[4] = {0, 0, 0, 0};
   // currTrace.temperature of this iteration (trace.t:652-655): every log-density evaluated during the iteration is
   // divided by it (trace.t:737-741) and its gradient multiplied by 1/T (the adjoint of that division, ad.t:405-412);
   // values cached from earlier iterations (lp, gradient) keep the temperature they were computed under, as in the reference
@@ -599,7 +611,7 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
   // one atomic per warp and counter per launch (a per-chain atomic on one address serialised 9 % of the c2 kernel)
   __device__ __forceinline__ void flush_counts() const {
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < 4; ++w) {
       unsigned long long v = cnt[w];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1607,6 +1619,9 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     }
     else accept = STREAM ? harm_next_stream(k, iter, rdh, rstep) : harm_next(k, iter, rdh, rstep);
     if constexpr (WS) ws_release();
+    // health counters: a non-finite accept threshold, an HMC energy error beyond 1000
+    if (!(fabs(rdh) <= 1.7976931348623157e308)) count(2, 1);
+    else if (HAS_HMC && kind == K_HMC && fabs(rdh) > 1000.0) count(3, 1);
     if (G == 32) __syncwarp();
     const bool keep = lit >= P.burnin && (lit % P.lag) == 0 && c < P.sample_chains && P.samples != nullptr;
     if (keep || P.rec_state) {
@@ -1713,13 +1728,13 @@ advance_ws_kernel(const __grid_constant__ EngineParams P) {
   if (role == 0) {
     reg_alloc<WS_CONSUMER_REGS>();
     WsLink link{zslot, HAS_HMC ? zslot + 2 * BUF : nullptr, full, empty, 0u, false};
-    unsigned long long tot[2] = {0ull, 0ull};
+    unsigned long long tot[4] = {0ull, 0ull, 0ull, 0ull};
     for (uint32_t c = s0; c < P.C; c += nslots) {
       Chain<FAM, 32, NPL, true> ch(P, c, &link);
       for (uint64_t it = P.it_begin; it < P.it_begin + P.n_iters; ++it) ch.template iterate<HAS_HMC, false, DRIFT_ONLY>(it);
-      tot[0] += ch.cnt[0]; tot[1] += ch.cnt[1];
+      for (int w = 0; w < 4; ++w) tot[w] += ch.cnt[w];
     }
-    if (lane == 0) { if (tot[0]) atomicAdd(&P.counters[0], tot[0]); if (tot[1]) atomicAdd(&P.counters[1], tot[1]); }
+    if (lane == 0) for (int w = 0; w < 4; ++w) if (tot[w]) atomicAdd(&P.counters[w], tot[w]);
   } else {
     reg_dealloc<WS_PRODUCER_REGS>();
     constexpr int RP = (NPL + NPROD - 1) / NPROD;    // rows per sampler warp

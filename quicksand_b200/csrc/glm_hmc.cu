@@ -459,6 +459,7 @@ struct VecParams {
   int *direction, *done; int* n_active;
   unsigned long long *made, *acc;
   int* status;
+  unsigned long long* health;   // [0] transitions with a non-finite accept threshold, [1] HMC transitions with |dH| > 1000
   uint32_t iter, L, step, probe;
   double T, invT;   // trace temperature of this iteration (AnnealingKernel, mcmc.t:297-319; trace.t:737-741)
   int kind;         // 1 HMC, 2 Drift, 3 HARM
@@ -583,6 +584,7 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
     double lpn = finish_lp(P, c, lane, xs);
     if (P.T != 1.0) lpn = lpn / P.T;
     const double thresh = lpn - P.lp[c];
+    if (lane == 0 && !(fabs(thresh) <= 1.7976931348623157e308)) atomicAdd(&P.health[0], 1ull);
     const double u = uniform_at(P.key, gc, P.iter, (uint32_t)d + (P.kind == 3 ? 1u : 0u));
     const bool accept = log(u) < thresh;
     double step_rec = 0.0;
@@ -725,6 +727,7 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
   if (P.T != 1.0) newlp = newlp / P.T;
   const double H_new = -0.5 * warp_sum(kin) + newlp;
   const double dH = H_new - P.H0[c];
+  if (lane == 0) { if (!(fabs(dH) <= 1.7976931348623157e308)) atomicAdd(&P.health[0], 1ull); else if (fabs(dH) > 1000.0) atomicAdd(&P.health[1], 1ull); }
   double eps_new = eps;
   if (P.adapting) {   // adaptStepSize + DualAverage:update (hmc.t:38-48, 394-402)
     double EdH = exp(dH);
@@ -765,9 +768,10 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
 // ---------------------------------------------------------------------------------------------
 // The interior of a trajectory in ONE launch: `nsteps` gradient evaluations, each followed by the leapfrog update that
 // produces the next Theta (V_TRANS_MID), with grid-wide barriers in place of the 2 x nsteps kernel boundaries.  Balanced
-// decomposition only (one CTA per SM, all co-resident: cooperative launch).  What it saves is the ~13 us per leapfrog step
-// that sit outside the gradient kernel at small chain counts (launch gaps + the vector kernel's own launch): at 1 024 chains
-// per GPU -- BASELINE's c3 on 8 GPUs -- that is 8 % of the step.
+// decomposition only (one CTA per SM, all co-resident: cooperative launch).  The idea was to save the ~13 us per leapfrog step
+// that sit outside the gradient kernel at small chain counts; measured, the two grid barriers per step cost MORE than the two
+// kernel boundaries they replace once those overlap through programmatic dependent launch (see glm_sampler_create): an
+// experiment kept behind QSB_FUSED_TRAJ=1, not the default path.
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1067,6 +1071,7 @@ GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t 
   ok = ok && dalloc(s, &partG, (size_t)G.ksplit * C * Dp) && dalloc(s, &partLp, (size_t)G.ksplit * C);
   ok = ok && dalloc(s, &V.lp, C) && dalloc(s, &V.H0, C) && dalloc(s, &V.eps, C) && dalloc(s, &V.prevlp, C);
   ok = ok && dalloc(s, &V.da_gbar, C) && dalloc(s, &V.da_xbar, C) && dalloc(s, &V.da_x0, C) && dalloc(s, &V.da_lastx, C) && dalloc(s, &V.da_gamma, C) && dalloc(s, &V.da_k, C);
+  ok = ok && dalloc(s, &V.health, 2);
   ok = ok && dalloc(s, &V.direction, C) && dalloc(s, &V.done, C) && dalloc(s, &V.n_active, 1) && dalloc(s, &V.made, C) && dalloc(s, &V.acc, C) && dalloc(s, &V.status, 1);
   V.kind = kind;
   if (kind == 2) ok = ok && dalloc(s, &V.dr_mean, C * Dp) && dalloc(s, &V.dr_m2, C * Dp) && dalloc(s, &V.dr_s0, C) && dalloc(s, &V.dr_mult, C) && dalloc(s, &V.dr_n, C);
@@ -1075,10 +1080,15 @@ GlmSampler* glm_sampler_create(GlmModel* m, int kind, double stepSize, uint32_t 
   if (!ok || !s->nj_inst) { why = !s->nj_inst ? "unsupported dim" : "cudaMalloc failed"; glm_sampler_destroy(s); return nullptr; }
   G.partG = partG; G.partLp = partLp; V.partG = partG; V.partLp = partLp;
   G.theta = V.xs;
-  if (G.sk_U && kind == 1 && numSteps >= 2 && !getenv("QSB_NO_FUSED_TRAJ")) {
-    int coop = 0;
+  // QSB_FUSED_TRAJ=1: the interior of a trajectory as ONE cooperative launch (glm_traj_kernel).  Measured SLOWER than the
+  // separate launches with programmatic dependent launch (r02e, same box: 6.81 vs 7.01 M leapfrog steps/s at 8 192 chains,
+  // 6.13 vs 6.28 M at 1 024): two grid-wide barriers per step cost more than two PDL-overlapped kernel boundaries.  Kept
+  // selectable, off by default.
+  if (G.sk_U && kind == 1 && numSteps >= 2 && getenv("QSB_FUSED_TRAJ") && atoi(getenv("QSB_FUSED_TRAJ")) != 0) {
+    int coop = 0, occ = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (coop && G.sk_U <= nsm && dalloc(s, &s->traj_counter, 1)) s->fused_traj = true;
+    (void)occ;
   }
   return s;
 }
@@ -1138,6 +1148,7 @@ static int reset_chain_state(GlmSampler* s, std::string& why) {
   GCU(cudaMemsetAsync(V.done, 0, 4 * C, s->stream)); GCU(cudaMemsetAsync(V.direction, 0, 4 * C, s->stream));
   GCU(cudaMemsetAsync(V.made, 0, 8 * C, s->stream)); GCU(cudaMemsetAsync(V.acc, 0, 8 * C, s->stream));
   GCU(cudaMemsetAsync(V.status, 0, 4, s->stream));
+  GCU(cudaMemsetAsync(V.health, 0, 16, s->stream));
   if (s->kind == 2) {
     std::vector<double> sc(C, s->scale0), one(C, 1.0);
     GCU(cudaMemcpyAsync(V.dr_s0, sc.data(), 8 * C, cudaMemcpyHostToDevice, s->stream));
@@ -1335,6 +1346,13 @@ int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* gr
   *seconds = 0.0;
   if (s->advanced) { if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) *seconds = ms * 1e-3; else (void)cudaGetLastError(); }
   return 0;
+}
+
+void glm_sampler_health(GlmSampler* s, uint64_t* nonfinite, uint64_t* divergent) {
+  unsigned long long h[2] = {0, 0};
+  cudaStreamSynchronize(s->stream);
+  if (cudaMemcpy(h, s->V.health, 16, cudaMemcpyDeviceToHost) != cudaSuccess) (void)cudaGetLastError();
+  *nonfinite = h[0]; *divergent = h[1];
 }
 
 int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, double* dh, double* step, double* leap, std::string& why) {

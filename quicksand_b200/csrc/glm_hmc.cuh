@@ -37,6 +37,7 @@ int glm_sampler_set_temperatures(GlmSampler* s, const double* temps, uint64_t n,
 void glm_sampler_sample_view(GlmSampler* s, const double** samples, const double** samp_lp, int* G, uint32_t* SC, int* retdim);
 int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* grad_evals, uint64_t* leapfrogs, uint64_t* launches,
                       double* seconds, std::string& why);
+void glm_sampler_health(GlmSampler* s, uint64_t* nonfinite, uint64_t* divergent);
 int glm_sampler_fetch_record(GlmSampler* s, double* state, int32_t* accept, double* dh, double* step, double* leap, std::string& why);
 void glm_sampler_set_timing(GlmSampler* s, bool on);
 int glm_sampler_kernel_time(GlmSampler* s, double* seconds, uint64_t* launches, std::string& why);

@@ -203,6 +203,7 @@ int qsb_group_stats(qsb_group* g, qsb_stats* out) {
     out->props_made += st.props_made; out->props_accepted += st.props_accepted;
     for (int k = 0; k < 8; ++k) { out->sub_made[k] += st.sub_made[k]; out->sub_accepted[k] += st.sub_accepted[k]; }
     out->grad_evals += st.grad_evals; out->leapfrog_steps += st.leapfrog_steps; out->kernel_launches += st.kernel_launches;
+    out->nonfinite += st.nonfinite; out->divergent += st.divergent;
     out->iterations = st.iterations;
     out->seconds = std::max(out->seconds, st.seconds);
   }

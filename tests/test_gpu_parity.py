@@ -788,6 +788,24 @@ def test_conditions_hold_and_reject(qs, oracle):
     assert not ((fv > lo).all() and (fv < hi).all())
 
 
+def test_chain_health_counters(qs):
+    """qsb_stats.nonfinite / divergent: a stable run reports none; a funnel driven with a step size far beyond
+    its stability limit reports divergent (|dH| > 1000) and non-finite transitions, on the engine and on the tensor-core path."""
+    s = qs.Sampler(_programs(qs)["gauss10"], qs.HMCKernel(numSteps=10, stepSize=0.2, doStepSizeAdapt=False), numchains=256, seed=1)
+    s.init(); s.run(50)
+    st = s.stats(); s.close()
+    assert st["nonfinite"] == 0 and st["divergent"] == 0
+    for mapping in (1, 32):
+        s = qs.Sampler(_programs(qs)["funnel12"], qs.HMCKernel(numSteps=16, stepSize=3.0, doStepSizeAdapt=False), numchains=256, seed=1, mapping=mapping)
+        s.init(); s.run(50)
+        st = s.stats(); s.close()
+        assert st["divergent"] + st["nonfinite"] > 1000 and st["props_accepted"] < st["props_made"]
+    s = qs.Sampler(_programs(qs)["logistic20"], qs.HMCKernel(numSteps=20, stepSize=5.0, doStepSizeAdapt=False), numchains=192, seed=1)
+    s.init(); s.run(30)
+    st = s.stats(); s.close()
+    assert st["divergent"] + st["nonfinite"] > 100
+
+
 def test_single_chain_reference_protocol(qs, oracle):
     """Config c1: with numchains = 1 (the default) qs.MCMC is the reference's single chain.  The reference's own protocol --
     150 samples x lag 20, 5 runs, mean absolute error <= 0.07 (testsuite.t:84-141) -- on its HMC programs (testsuite.t:621-691,
