@@ -118,7 +118,10 @@ typedef struct {
 } qsb_kernel_spec;
 
 enum {
-  QSB_FLAG_MOMENTS = 1u,     /* accumulate per-chain running moments of the kept samples (for split-Rhat) */
+  QSB_FLAG_MOMENTS = 1u,     /* keep running statistics of the kept samples INSTEAD of the samples: per chain and return-value
+                              * dimension Welford moments of the two halves of the run (split-Rhat) and of sqrt(max_samples)-long
+                              * batch means (ESS), 56 bytes in all, updated in the transition kernels.  qsb_sampler_diagnostics then
+                              * works without stored draws (fetch / queries have nothing to read); see its layout note. */
   QSB_FLAG_RECORD = 2u,      /* keep a per-iteration record (state, accept, dH, step, kernel index) -- parity tests */
   QSB_FLAG_RECORD_LEAP = 4u, /* additionally record the position after every leapfrog step (single HMC kernel) */
   QSB_FLAG_TIME_KERNEL = 8u, /* bracket every launch of the dominant kernel with CUDA events (roofline measurement) */
@@ -239,7 +242,12 @@ int qsb_sampler_set_kernel_timing(qsb_sampler* s, int32_t on);
  * numerators sum_i (x_i - m_c)(x_{i+t} - m_c), t = 0..maxlag, m_c = the chain's mean.
  * These are plain sums, so shards on different GPUs combine with one all-reduce(sum).
  * If dst_is_device != 0, dst is a device pointer on the sampler's device (e.g. a torch tensor
- * handed to NCCL); otherwise a host pointer. */
+ * handed to NCCL); otherwise a host pointer.
+ * With QSB_FLAG_MOMENTS the same 12 sums per dimension are formed from the running statistics (the halves are the
+ * kept-sample ranges [0, max_samples/2) and [max_samples/2, n): run the sampler to max_samples for equal halves), maxlag is
+ * ignored and 3 doubles per dimension follow instead of the autocovariances: [0] sum over chains of the sample variance of
+ * the chain's completed batch means, [1] the batch size b, [2] completed batches per chain -- ESS = M N s^2 / (b * mean
+ * batch-mean variance).  Total retdim * 15 doubles; [1], [2] are constants like header entries [1], [8]. */
 int qsb_sampler_diagnostics(qsb_sampler* s, int32_t maxlag, double* dst, int32_t dst_is_device);
 
 /* ---- queries (qs/infer.t:128-264) evaluated on the device, per chain, over the kept samples of a sampler (no host
@@ -301,7 +309,9 @@ int qsb_group_sync(qsb_group* g);                                  /* wait for e
 int qsb_group_fetch_samples(qsb_group* g, uint32_t chain_begin, uint32_t chain_end, uint64_t sample_begin, uint64_t sample_end,
                             void* dst, size_t stride_bytes);
 int qsb_group_stats(qsb_group* g, qsb_stats* out);                 /* counters summed over shards, seconds = max */
-/* qsb_sampler_diagnostics of every shard, all-reduced (NCCL ncclSum over the group's communicator): dst is HOST */
+/* qsb_sampler_diagnostics of every shard, all-reduced (NCCL ncclSum over the group's communicator): dst is HOST.
+ * (Here and in qsb_sampler_diagnostics_allreduce pass maxlag = -1 for samplers created with QSB_FLAG_MOMENTS: the
+ * 15-doubles-per-dimension layout.) */
 int qsb_group_diagnostics(qsb_group* g, int32_t maxlag, double* dst);
 
 int qsb_comm_unique_id(uint8_t id[QSB_COMM_ID_BYTES]);            /* rank 0; hand the bytes to the other ranks */

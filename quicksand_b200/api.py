@@ -227,7 +227,10 @@ class Sampler:
     def diagnostics_raw(self, maxlag=0, out_ptr=None):
         """Sufficient statistics (see qsb_sampler_diagnostics).  ``out_ptr``: device pointer (e.g. a torch
         tensor's data_ptr()) to write into for a following NCCL all-reduce; otherwise a numpy array."""
-        n = self.retdim * 12 + (self.retdim * (maxlag + 1) if maxlag > 0 else 0)
+        if self.flags & L.FLAG_MOMENTS:     # running statistics instead of stored draws: 12 + 3 doubles per dimension
+            maxlag, n = -1, self.retdim * 15
+        else:
+            n = self.retdim * 12 + (self.retdim * (maxlag + 1) if maxlag > 0 else 0)
         if out_ptr is not None:
             L.check(L.lib().qsb_sampler_diagnostics(self.h, maxlag, C.c_void_p(out_ptr), 1))
             return None
@@ -263,6 +266,7 @@ class Group:
         cfg = L.RunConfig(int(seed), int(chain_begin), self.numchains, int(sample_chains), int(flags), -1, 0, None)
         dev = (C.c_int32 * len(self.devices))(*self.devices)
         self.h = C.c_void_p()
+        self.flags = flags
         desc = program.desc()
         L.check(L.lib().qsb_group_create(C.byref(desc), arr, len(kernel.specs), C.byref(cfg), dev, len(self.devices), C.byref(self.h)))
         self._numiters = 0
@@ -334,7 +338,9 @@ class Group:
 
     def diagnostics_raw(self, maxlag=0):
         """The sufficient statistics of qsb_sampler_diagnostics summed over the shards (NCCL all-reduce inside the library)."""
-        out = np.empty(self.retdim * 12 + (self.retdim * (maxlag + 1) if maxlag > 0 else 0))
+        if self.flags & L.FLAG_MOMENTS:
+            maxlag = -1
+        out = np.empty(self.retdim * 15 if maxlag < 0 else self.retdim * 12 + (self.retdim * (maxlag + 1) if maxlag > 0 else 0))
         L.check(L.lib().qsb_group_diagnostics(self.h, maxlag, out.ctypes.data_as(L.dp)))
         return out
 
@@ -364,7 +370,9 @@ class Comm:
         L.check(L.lib().qsb_comm_allreduce_sum(self.h, C.c_void_p(dev_ptr), n, C.c_void_p(stream) if stream else None))
 
     def diagnostics_raw(self, sampler, maxlag=0):
-        out = np.empty(sampler.retdim * 12 + (sampler.retdim * (maxlag + 1) if maxlag > 0 else 0))
+        if sampler.flags & L.FLAG_MOMENTS:
+            maxlag = -1
+        out = np.empty(sampler.retdim * 15 if maxlag < 0 else sampler.retdim * 12 + (sampler.retdim * (maxlag + 1) if maxlag > 0 else 0))
         L.check(L.lib().qsb_sampler_diagnostics_allreduce(sampler.h, self.h, maxlag, out.ctypes.data_as(L.dp)))
         return out
 

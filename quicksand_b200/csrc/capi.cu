@@ -142,6 +142,33 @@ __global__ void diagnostics_kernel(const double* samples, int G, uint32_t SC, in
     }
   }
 }
+// The same per-dimension sums from the running statistics of QSB_FLAG_MOMENTS (moments.cuh) instead of stored draws: the two
+// halves are the kept-sample ranges [0, half) and [half, n); a chain's moments are their Chan combination.  Behind the 12 sums
+// per dimension: [0] sum over chains of the sample variance of the completed batch means, [1] the batch size, [2] the number
+// of completed batches (per chain): asymptotic variance ~ batch * var(batch means), ESS = chains * n * s^2 / that.
+__global__ void diagnostics_moments_kernel(const double* mom, int layout1, uint32_t SC, int retdim, uint64_t n, uint64_t half, uint32_t batch, double* out) {
+  size_t total = (size_t)SC * retdim;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t c; int j;
+  if (layout1) { c = (uint32_t)(t % SC); j = (int)(t / SC); } else { j = (int)(t % retdim); c = (uint32_t)(t / retdim); }
+  const size_t plane = (size_t)SC * retdim;
+  const double* b = mom + (layout1 ? (size_t)j * SC + c : (size_t)c * retdim + j);
+  const double n0 = (double)(n < half ? n : half), n1 = (double)(n > half ? n - half : 0);
+  const double m0 = b[0], q0 = b[plane], m1 = b[2 * plane], q1 = b[3 * plane];
+  double* o = out + (size_t)j * 12;
+  if (n0 >= 2.0 && n1 >= 2.0) {
+    atomicAdd(&o[2], m0 + m1); atomicAdd(&o[3], m0 * m0 + m1 * m1); atomicAdd(&o[4], q0 / (n0 - 1.0) + q1 / (n1 - 1.0));
+  }
+  const double nn = n0 + n1;
+  const double mean = (n0 * m0 + n1 * m1) / nn;
+  const double M2 = q0 + q1 + (n1 > 0.0 ? (m1 - m0) * (m1 - m0) * n0 * n1 / nn : 0.0);
+  atomicAdd(&o[5], nn * mean); atomicAdd(&o[6], M2 + nn * mean * mean);
+  atomicAdd(&o[9], mean); atomicAdd(&o[10], mean * mean); atomicAdd(&o[11], M2 / (nn - 1.0));
+  const uint64_t nb = n / batch;
+  if (nb >= 2) atomicAdd(&out[(size_t)retdim * 12 + (size_t)j * 3], b[6 * plane] / (double)(nb - 1));
+  if (c == 0) { out[(size_t)retdim * 12 + (size_t)j * 3 + 1] = (double)batch; out[(size_t)retdim * 12 + (size_t)j * 3 + 2] = (double)nb; }
+}
 __global__ void diagnostics_header_kernel(double* out, int retdim, double mh, double nh, double M, double N) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < retdim) { double* o = out + (size_t)j * 12; o[0] = mh; o[1] = nh; o[7] = M; o[8] = N; }
@@ -499,7 +526,7 @@ int qsb_model_retdim(const qsb_model* m) { return m ? m->retdim : -1; }
 
 static void free_run_buffers(qsb_sampler* s) {
   EngineParams& P = s->P;
-  for (double** p : {&P.samples, &P.samp_lp, &P.rec_state, &P.rec_dh, &P.rec_step, &P.rec_leap}) if (*p) { cudaFree(*p); *p = nullptr; }
+  for (double** p : {&P.samples, &P.samp_lp, &P.rec_state, &P.rec_dh, &P.rec_step, &P.rec_leap, &P.mom}) if (*p) { cudaFree(*p); *p = nullptr; }
   for (int** p : {&P.rec_accept, &P.rec_kidx}) if (*p) { cudaFree(*p); *p = nullptr; }
   s->rec_iters = 0; P.rec_iters = 0;
 }
@@ -709,7 +736,13 @@ int qsb_sampler_begin(qsb_sampler* s, uint64_t max_samples, uint64_t burnin, uin
   // (re)allocate the sample and record buffers of this run; the chain state persists
   free_run_buffers(s);
   P.max_samples = max_samples; P.burnin = burnin; P.lag = lag;
-  if (max_samples > 0) {
+  if (max_samples > 0 && (s->cfg.flags & QSB_FLAG_MOMENTS)) {   // running statistics of the kept draws instead of the draws
+    const size_t bytes = sizeof(double) * MOM_STATS * P.sample_chains * P.retdim;
+    CU(cudaMalloc((void**)&P.mom, bytes));
+    CU(cudaMemsetAsync(P.mom, 0, bytes, s->stream));
+    P.mom_half = max_samples / 2;
+    P.mom_batch = (uint32_t)std::max<uint64_t>(1, (uint64_t)std::floor(std::sqrt((double)max_samples)));
+  } else if (max_samples > 0) {
     CU(cudaMalloc((void**)&P.samples, sizeof(double) * max_samples * P.sample_chains * P.retdim));
     CU(cudaMalloc((void**)&P.samp_lp, sizeof(double) * max_samples * P.sample_chains));
   }
@@ -978,8 +1011,32 @@ int qsb_sampler_kernel_time(qsb_sampler* s, double* seconds, uint64_t* launches)
 
 int qsb_sampler_diagnostics(qsb_sampler* s, int32_t maxlag, double* dst, int32_t dst_is_device) {
   if (!s || !dst) return fail(1, "null argument");
-  if (maxlag < 0) return fail(2, "maxlag must be >= 0");
   CU(cudaSetDevice(s->m->device));
+  if (s->cfg.flags & QSB_FLAG_MOMENTS) {   // from the running statistics: 12 + 3 doubles per dimension, whatever maxlag says
+    const double* mom = nullptr; uint64_t half = 0; uint32_t batch = 1; int G; uint32_t SC; int retdim;
+    const double *sm_, *sl_;
+    if (s->glm) { glm_sampler_sample_view(s->glm, &sm_, &sl_, &G, &SC, &retdim); glm_sampler_moments_view(s->glm, &mom, &half, &batch); }
+    else { mom = s->P.mom; half = s->P.mom_half; batch = s->P.mom_batch; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }
+    const uint64_t n = qsb_sampler_num_samples(s);
+    const size_t len = (size_t)retdim * 15;
+    double* out = dst;
+    if (!dst_is_device) CU(cudaMalloc((void**)&out, len * 8));
+    CU(cudaMemsetAsync(out, 0, len * 8, s->stream));
+    if (n >= 2 && mom) {
+      const size_t total = (size_t)SC * retdim;
+      diagnostics_moments_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s->stream>>>(mom, G == 1 ? 1 : 0, SC, retdim, n, half, batch, out);
+      const double nh = (n > half && half >= 2 && n - half >= 2) ? 0.5 * (double)n : 0.0;
+      diagnostics_header_kernel<<<(retdim + 127) / 128, 128, 0, s->stream>>>(out, retdim, nh > 0.0 ? 2.0 * SC : 0.0, nh, (double)SC, (double)n);
+      s->launches += 2;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !dst_is_device) e = cudaMemcpyAsync(dst, out, len * 8, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (!dst_is_device) cudaFree(out);
+    if (e != cudaSuccess) return fail(100 + (int)e, std::string("diagnostics: ") + cudaGetErrorString(e));
+    return 0;
+  }
+  if (maxlag < 0) return fail(2, "maxlag must be >= 0");
   const double *samples, *samp_lp; int G; uint32_t SC; int retdim;
   if (s->glm) glm_sampler_sample_view(s->glm, &samples, &samp_lp, &G, &SC, &retdim);
   else { samples = s->P.samples; samp_lp = s->P.samp_lp; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }

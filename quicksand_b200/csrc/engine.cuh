@@ -22,6 +22,7 @@
 #include <cstdint>
 #include "distrib.cuh"
 #include "mbar.cuh"
+#include "moments.cuh"
 #include "philox.cuh"
 
 namespace qsb {
@@ -95,6 +96,8 @@ struct EngineParams {
   double *samples, *samp_lp;
   uint32_t sample_chains;
   uint64_t max_samples;
+  // QSB_FLAG_MOMENTS: streaming statistics of the kept draws instead of the draws (see mom_update); nullptr = off
+  double* mom; uint64_t mom_half; uint32_t mom_batch;
   // per-iteration record (parity tests)
   double *rec_state, *rec_dh, *rec_step, *rec_leap;
   int *rec_accept, *rec_kidx;
@@ -1623,7 +1626,7 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     if (!(fabs(rdh) <= 1.7976931348623157e308)) count(2, 1);
     else if (HAS_HMC && kind == K_HMC && fabs(rdh) > 1000.0) count(3, 1);
     if (G == 32) __syncwarp();
-    const bool keep = lit >= P.burnin && (lit % P.lag) == 0 && c < P.sample_chains && P.samples != nullptr;
+    const bool keep = lit >= P.burnin && (lit % P.lag) == 0 && c < P.sample_chains && (P.samples != nullptr || P.mom != nullptr);
     if (keep || P.rec_state) {
       double x[NPL];
       load(P.x, x);
@@ -1639,6 +1642,14 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
         const uint64_t sidx = lit / P.lag - (P.burnin + P.lag - 1) / P.lag;
         if (sidx < P.max_samples) {
           const uint32_t SC = P.sample_chains;
+          // where kept value j of this chain goes: the sample array, or (QSB_FLAG_MOMENTS) the running statistics
+          auto put = [&](int j, double v) {
+            if (P.mom) {
+              const size_t plane = (size_t)SC * P.retdim;
+              double* base = P.mom + (G == 1 ? (size_t)j * SC + c : (size_t)c * P.retdim + j);
+              mom_update([&](int st) { return base + (size_t)st * plane; }, sidx, P.mom_half, P.mom_batch, v);
+            } else P.samples[G == 1 ? ((size_t)sidx * P.retdim + j) * SC + c : ((size_t)sidx * SC + c) * P.retdim + j] = v;
+          };
           if (FAM == FAM_INDEP) {
             double sum = 0.0;
             SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
@@ -1650,20 +1661,20 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
                   y = dirichlet_component_noinline(sc, (int)P.m.p1[i], P.m.erp_len[i], x[e], P.m.p0[i], P.m.erp_asum[i], gdummy);
                 else y = erp_fwd_noinline(P.m.erp_kind[i], x[e], P.m.p0[i], P.m.p1[i]);
                 if (P.m.ret_mode == 0) sum += y;
-                else P.samples[G == 1 ? ((size_t)sidx * P.retdim + i) * SC + c : ((size_t)sidx * SC + c) * P.retdim + i] = y;
+                else put(i, y);
               }
             }
             if (P.m.ret_mode == 0) {
               sum = Grp<G>::sum(sum);
-              if (leader()) P.samples[(size_t)sidx * SC + c] = sum / P.m.ret_div;
+              if (leader()) put(0, sum / P.m.ret_div);
             }
           } else {
             QSB_FOR_E {
               int i = e * G + lane;
-              if (i < d) P.samples[G == 1 ? ((size_t)sidx * P.retdim + i) * SC + c : ((size_t)sidx * SC + c) * P.retdim + i] = x[e];
+              if (i < d) put(i, x[e]);
             }
           }
-          if (leader()) P.samp_lp[(size_t)sidx * SC + c] = P.lp[c] * T;   // mcmc.t:69
+          if (leader() && P.samp_lp) P.samp_lp[(size_t)sidx * SC + c] = P.lp[c] * T;   // mcmc.t:69
         }
       }
     }

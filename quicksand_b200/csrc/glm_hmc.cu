@@ -31,6 +31,7 @@
 #include "../../include/qsb200.h"
 #include "distrib.cuh"
 #include "glm_hmc.cuh"
+#include "moments.cuh"
 #include "mbar.cuh"
 #include "philox.cuh"
 
@@ -469,6 +470,7 @@ struct VecParams {
   double stepSize0;
   // samples / record
   double *samples, *samp_lp; uint32_t SC; uint64_t sidx; int keep;
+  double* mom; uint64_t mom_half; uint32_t mom_batch;   // QSB_FLAG_MOMENTS (engine.cuh: mom_update), layout [stat][chain][dim]
   double *rec_state, *rec_dh, *rec_step, *rec_leap; int* rec_accept; uint64_t rec_iters, rec_row;
 };
 
@@ -640,8 +642,16 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
       if (lane == 0) { P.rec_accept[r] = accept ? 1 : 0; P.rec_dh[r] = thresh; P.rec_step[r] = step_rec; }
     }
     if (P.keep && c < P.SC) {
-      for (int i = lane; i < d; i += 32) P.samples[((size_t)P.sidx * P.SC + c) * d + i] = x[i];
-      if (lane == 0) P.samp_lp[(size_t)P.sidx * P.SC + c] = lp_keep * P.T;   // mcmc.t:69
+      if (P.mom) {
+        const size_t plane = (size_t)P.SC * d;
+        for (int i = lane; i < d; i += 32) {
+          double* b0 = P.mom + (size_t)c * d + i;
+          mom_update([&](int st) { return b0 + (size_t)st * plane; }, P.sidx, P.mom_half, P.mom_batch, x[i]);
+        }
+      } else {
+        for (int i = lane; i < d; i += 32) P.samples[((size_t)P.sidx * P.SC + c) * d + i] = x[i];
+        if (lane == 0) P.samp_lp[(size_t)P.sidx * P.SC + c] = lp_keep * P.T;   // mcmc.t:69
+      }
     }
     return;
   }
@@ -760,8 +770,16 @@ __global__ void __launch_bounds__(256) glm_vec_kernel(const __grid_constant__ Ve
     if (lane == 0) { P.rec_accept[r] = accept ? 1 : 0; P.rec_dh[r] = dH; P.rec_step[r] = eps; }
   }
   if (P.keep && c < P.SC) {
-    for (int i = lane; i < d; i += 32) P.samples[((size_t)P.sidx * P.SC + c) * d + i] = x[i];
-    if (lane == 0) P.samp_lp[(size_t)P.sidx * P.SC + c] = (accept ? newlp : P.lp[c]) * P.T;   // mcmc.t:69
+    if (P.mom) {
+      const size_t plane = (size_t)P.SC * d;
+      for (int i = lane; i < d; i += 32) {
+        double* b0 = P.mom + (size_t)c * d + i;
+        mom_update([&](int st) { return b0 + (size_t)st * plane; }, P.sidx, P.mom_half, P.mom_batch, x[i]);
+      }
+    } else {
+      for (int i = lane; i < d; i += 32) P.samples[((size_t)P.sidx * P.SC + c) * d + i] = x[i];
+      if (lane == 0) P.samp_lp[(size_t)P.sidx * P.SC + c] = (accept ? newlp : P.lp[c]) * P.T;   // mcmc.t:69
+    }
   }
 }
 
@@ -1014,7 +1032,7 @@ template <class T> static bool dalloc(GlmSampler* s, T** p, size_t n) {
 
 static void glm_free_run_buffers(GlmSampler* s) {
   VecParams& V = s->V;
-  for (double** p : {&V.samples, &V.samp_lp, &V.rec_state, &V.rec_dh, &V.rec_step, &V.rec_leap}) if (*p) { cudaFree(*p); *p = nullptr; }
+  for (double** p : {&V.samples, &V.samp_lp, &V.rec_state, &V.rec_dh, &V.rec_step, &V.rec_leap, &V.mom}) if (*p) { cudaFree(*p); *p = nullptr; }
   if (V.rec_accept) { cudaFree(V.rec_accept); V.rec_accept = nullptr; }
   s->rec_iters = 0; V.rec_iters = 0;
 }
@@ -1204,7 +1222,12 @@ int glm_sampler_begin(GlmSampler* s, uint64_t max_samples, uint64_t burnin, uint
   glm_free_run_buffers(s);
   s->iter_base += s->iter;
   s->iter = 0; s->burnin = burnin; s->lag = lag; s->max_samples = max_samples;
-  if (max_samples > 0) {
+  if (max_samples > 0 && (s->flags & QSB_FLAG_MOMENTS)) {
+    const size_t bytes = 8 * (size_t)MOM_STATS * V.SC * V.d;
+    GCU(cudaMalloc((void**)&V.mom, bytes));
+    GCU(cudaMemsetAsync(V.mom, 0, bytes, s->stream));
+    V.mom_half = max_samples / 2; V.mom_batch = (uint32_t)std::max<uint64_t>(1, (uint64_t)std::floor(std::sqrt((double)max_samples)));
+  } else if (max_samples > 0) {
     GCU(cudaMalloc((void**)&V.samples, 8 * max_samples * V.SC * V.d));
     GCU(cudaMalloc((void**)&V.samp_lp, 8 * max_samples * V.SC));
   }
@@ -1271,7 +1294,7 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
       GCU(launch_vec<V_MH_PROPOSE>(s, V));
       GCU(run_grad(s, V.xs, 1, 0));
       --s->grad_evals;   // a log-density evaluation, not a gradient
-      V.keep = (it >= s->burnin && it % s->lag == 0 && V.samples) ? 1 : 0;
+      V.keep = (it >= s->burnin && it % s->lag == 0 && (V.samples || V.mom)) ? 1 : 0;
       V.sidx = it / s->lag - (s->burnin + s->lag - 1) / s->lag;
       if (V.sidx >= s->max_samples) V.keep = 0;
       GCU(launch_vec<V_MH_ACCEPT>(s, V));
@@ -1315,7 +1338,7 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
       GCU(run_grad(s, V.xs, last ? 1 : 0));
       if (!last) GCU(launch_vec<V_TRANS_MID>(s, V));
       else {
-        V.keep = (it >= s->burnin && it % s->lag == 0 && V.samples) ? 1 : 0;
+        V.keep = (it >= s->burnin && it % s->lag == 0 && (V.samples || V.mom)) ? 1 : 0;
         V.sidx = it / s->lag - (s->burnin + s->lag - 1) / s->lag;
         if (V.sidx >= s->max_samples) V.keep = 0;
         GCU(launch_vec<V_TRANS_LAST>(s, V));
@@ -1328,6 +1351,7 @@ int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why) {
   return 0;
 }
 
+void glm_sampler_moments_view(GlmSampler* s, const double** mom, uint64_t* half, uint32_t* batch) { *mom = s->V.mom; *half = s->V.mom_half; *batch = s->V.mom_batch; }
 void glm_sampler_sample_view(GlmSampler* s, const double** samples, const double** samp_lp, int* G, uint32_t* SC, int* retdim) {
   *samples = s->V.samples; *samp_lp = s->V.samp_lp; *G = 32; *SC = s->V.SC; *retdim = s->V.d;
 }

@@ -34,6 +34,7 @@ int glm_sampler_get_state(GlmSampler* s, double* x, std::string& why);
 int glm_sampler_begin(GlmSampler* s, uint64_t max_samples, uint64_t burnin, uint64_t lag, uint64_t numiters, std::string& why);
 int glm_sampler_advance(GlmSampler* s, uint64_t iters, std::string& why);
 int glm_sampler_set_temperatures(GlmSampler* s, const double* temps, uint64_t n, std::string& why);
+void glm_sampler_moments_view(GlmSampler* s, const double** mom, uint64_t* half, uint32_t* batch);
 void glm_sampler_sample_view(GlmSampler* s, const double** samples, const double** samp_lp, int* G, uint32_t* SC, int* retdim);
 int glm_sampler_stats(GlmSampler* s, uint64_t* made, uint64_t* acc, uint64_t* grad_evals, uint64_t* leapfrogs, uint64_t* launches,
                       double* seconds, std::string& why);

@@ -60,12 +60,14 @@ __global__ void sum_into_kernel(double* dst, const double* src, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
 }
 
-size_t diag_len(int retdim, int maxlag) { return (size_t)retdim * 12 + (maxlag > 0 ? (size_t)retdim * (maxlag + 1) : 0); }
+// maxlag < 0: the QSB_FLAG_MOMENTS layout (12 + 3 doubles per dimension)
+size_t diag_len(int retdim, int maxlag) { return maxlag < 0 ? (size_t)retdim * 15 : (size_t)retdim * 12 + (maxlag > 0 ? (size_t)retdim * (maxlag + 1) : 0); }
 
 // The header entries [0] half-chains, [1] draws per half-chain, [7] chains, [8] draws per chain of every dimension are
 // written identically by every shard: after a sum over shards [1] and [8] must be divided back.
-void fix_header_after_sum(double* h, int retdim, int nshards) {
+void fix_header_after_sum(double* h, int retdim, int nshards, int maxlag) {
   for (int j = 0; j < retdim; ++j) { h[(size_t)j * 12 + 1] /= nshards; h[(size_t)j * 12 + 8] /= nshards; }
+  if (maxlag < 0) for (int j = 0; j < retdim; ++j) { h[(size_t)retdim * 12 + 3 * j + 1] /= nshards; h[(size_t)retdim * 12 + 3 * j + 2] /= nshards; }
 }
 
 }  // namespace
@@ -212,7 +214,6 @@ int qsb_group_stats(qsb_group* g, qsb_stats* out) {
 
 int qsb_group_diagnostics(qsb_group* g, int32_t maxlag, double* dst) {
   if (!g || !dst) return fail(1, "null argument");
-  if (maxlag < 0) return fail(2, "maxlag must be >= 0");
   const size_t len = diag_len(g->retdim, maxlag);
   const int n = (int)g->samplers.size();
   if (g->dbuf_len < len) {
@@ -245,7 +246,7 @@ int qsb_group_diagnostics(qsb_group* g, int32_t maxlag, double* dst) {
   CU(cudaSetDevice(g->devices[0]));
   CU(cudaMemcpyAsync(dst, g->dbuf[0], len * 8, cudaMemcpyDeviceToHost, g->streams[0]));
   CU(cudaStreamSynchronize(g->streams[0]));
-  if (n > 1) fix_header_after_sum(dst, g->retdim, n);
+  if (n > 1) fix_header_after_sum(dst, g->retdim, n, maxlag);
   if (!g->comms.empty()) return qsb_group_sync(g);
   return 0;
 }
@@ -290,7 +291,6 @@ int qsb_comm_allreduce_sum(qsb_comm* c, double* buf, size_t n, void* stream) {
 }
 int qsb_sampler_diagnostics_allreduce(qsb_sampler* s, qsb_comm* c, int32_t maxlag, double* dst) {
   if (!s || !c || !dst) return fail(1, "null argument");
-  if (maxlag < 0) return fail(2, "maxlag must be >= 0");
   CU(cudaSetDevice(c->device));
   // retdim from a zero-lag probe of the layout is not available here: ask the sampler through the public entry
   int retdim = qsb_sampler_retdim_(s);
@@ -306,7 +306,7 @@ int qsb_sampler_diagnostics_allreduce(qsb_sampler* s, qsb_comm* c, int32_t maxla
     if (e != cudaSuccess) rc = fail(100 + (int)e, cudaGetErrorString(e));
   }
   cudaFree(d);
-  if (!rc && c->nranks > 1) fix_header_after_sum(dst, retdim, c->nranks);
+  if (!rc && c->nranks > 1) fix_header_after_sum(dst, retdim, c->nranks, maxlag);
   return rc;
 }
 

@@ -51,6 +51,26 @@ def summarize(raw, retdim, maxlag=0, nshards=1):
     return out
 
 
+def summarize_moments(raw, retdim, nshards=1):
+    """The same summary from the QSB_FLAG_MOMENTS layout (15 doubles per dimension: the 12 sums + [sum over chains of the
+    batch-mean variance, batch size, batches per chain]); the ESS is the batch-means estimate
+    M N s^2 / (b * mean batch-mean variance), s^2 the mean within-chain variance."""
+    raw = np.asarray(raw, dtype=np.float64)
+    out = summarize(raw[:retdim * HDR], retdim, 0, nshards)
+    bm = raw[retdim * HDR:].reshape(retdim, 3).copy()
+    bm[:, 1] /= nshards; bm[:, 2] /= nshards
+    hdr, _ = unpack(raw[:retdim * HDR], retdim, 0, nshards)
+    M, N = hdr[:, 7], hdr[:, 8]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        W = hdr[:, 11] / M
+        sigma2 = bm[:, 1] * bm[:, 0] / M              # asymptotic variance of the chain mean times N
+        tau = np.where(bm[:, 2] >= 2, sigma2 / W, np.nan)
+        out["tau"] = tau
+        out["ess"] = M * N / np.maximum(tau, 1e-3)
+    out["batch"] = bm[:, 1]; out["batches"] = bm[:, 2]
+    return out
+
+
 def _geyer_tau(rho, with_flag=False):
     """tau = -1 + 2 * sum of the initial positive, monotone sequence of pair sums P_k = rho_2k + rho_2k+1.
     with_flag: also return whether the sequence ran into the end of rho (maxlag) before a non-positive pair sum."""
