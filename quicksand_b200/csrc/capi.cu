@@ -873,6 +873,8 @@ static int fetch_common(qsb_sampler* s, uint32_t c0, uint32_t c1, uint64_t s0, u
   if (s->glm) glm_sampler_sample_view(s->glm, &samples, &samp_lp, &G, &SC, &retdim);
   else { samples = s->P.samples; samp_lp = s->P.samp_lp; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }
   const uint64_t have = qsb_sampler_num_samples(s);
+  if (s->cfg.flags & QSB_FLAG_MOMENTS) return fail(2, "fetch: QSB_FLAG_MOMENTS keeps running statistics, no draws are stored");
+  if (have > 0 && !samples) return fail(2, "fetch: the sampler holds no stored draws");
   if (c1 > SC || c0 > c1 || s1 > have || s0 > s1) return fail(2, "fetch: chain/sample range out of bounds (chains stored: " + std::to_string(SC) + ", samples kept: " + std::to_string(have) + ")");
   const int w = retdim + (with_lp ? 2 : 0);
   if (stride_bytes < (size_t)w * 8 || stride_bytes % 8) return fail(2, "fetch: stride must be a multiple of 8 and >= element size");
@@ -914,6 +916,8 @@ int qsb_sampler_fetch_samples_async(qsb_sampler* s, uint32_t c0, uint32_t c1, ui
   if (s->glm) glm_sampler_sample_view(s->glm, &samples, &samp_lp, &G, &SC, &retdim);
   else { samples = s->P.samples; samp_lp = s->P.samp_lp; G = s->var->G; SC = s->P.sample_chains; retdim = s->P.retdim; }
   const uint64_t have = qsb_sampler_num_samples(s);
+  if (s->cfg.flags & QSB_FLAG_MOMENTS) return fail(2, "fetch: QSB_FLAG_MOMENTS keeps running statistics, no draws are stored");
+  if (have > 0 && !samples) return fail(2, "fetch: the sampler holds no stored draws");
   if (c1 > SC || c0 > c1 || s1 > have || s0 > s1) return fail(2, "fetch: chain/sample range out of bounds (chains stored: " + std::to_string(SC) + ", samples kept: " + std::to_string(have) + ")");
   const int w = retdim + 2;
   if (stride_bytes < (size_t)w * 8 || stride_bytes % 8) return fail(2, "fetch: stride must be a multiple of 8 and >= element size");

@@ -68,6 +68,11 @@ def summarize_moments(raw, retdim, nshards=1):
         out["tau"] = tau
         out["ess"] = M * N / np.maximum(tau, 1e-3)
     out["batch"] = bm[:, 1]; out["batches"] = bm[:, 2]
+    # batch means need batches much longer than the autocorrelation time; when the estimate itself says they are not
+    # (tau > batch / 4) it is biased low and the ESS is an upper bound, not an estimate (the counterpart of Geyer's
+    # `truncated_at_maxlag`)
+    with np.errstate(invalid="ignore"):
+        out["batch_too_short"] = ~(tau <= bm[:, 1] / 4.0)
     return out
 
 

@@ -98,8 +98,14 @@ def test_streaming_moments_match_stored_draws(qs):
         b.close()
         assert np.allclose(got["mean"], ref["mean"], rtol=1e-9, atol=1e-12) and np.allclose(got["var"], ref["var"], rtol=1e-9)
         assert np.allclose(got["rhat"], ref["rhat"], rtol=1e-9)
+        # batch means (batch = 20 draws here) estimate the asymptotic variance when the autocorrelation time is well below the
+        # batch length: there the two ESS estimates agree within a factor of two; on slowly mixing dimensions (the funnel
+        # under a small fixed step) batch means are biased low, the ESS is an upper bound and is flagged as such
         ratio = got["ess"] / ref["ess"]
-        assert (ratio > 0.4).all() and (ratio < 2.5).all(), ratio
+        fast = ref["tau"] <= got["batch"] / 4.0
+        assert (ratio[fast] > 0.4).all() and (ratio[fast] < 2.5).all(), ratio
+        assert (ratio[~fast] > 0.4).all(), (ratio, ref["tau"])
+        assert got["batch_too_short"].dtype == bool and not got["batch_too_short"][ref["tau"] < 1.5].any()
         g = qs.Group(prog, kern, [0, 0], numchains=256, seed=9, flags=L.FLAG_MOMENTS); g.init(); g.run(400, 50, 1)
         gg = D.summarize_moments(g.diagnostics_raw(), prog.retdim); g.close()
         if mapping == 0:      # (the group picks its own mapping)
