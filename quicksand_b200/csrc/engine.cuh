@@ -517,7 +517,15 @@ template <int FAM> struct ModelStream {
 // LANE_CHAINS (thread per chain): the 32 lanes of the warp own 32 consecutive chains (gc = the chain of lane 0); work item
 // j is component row_begin + (j >> 5) of chain gc + (j & 31) and lands in the same place of the staging array, so the warp
 // shares the attempts of its 32 chains the same way.  Needs all 32 lanes of the warp at the call.
-template <int G>
+// QSB_FILL_U work items can be in flight per lane (U independent attempts per trip as straight-line code, the votes / cursor /
+// loop branch paid once per U attempts).  Measured on B200 (gpurun r02k, same box, c5 / c4 / c2): U = 1 1.095 / 2.061 / 0.0402 ms
+// per step, U = 2 1.124 / 2.090 / 0.0432, U = 4 1.364 / 2.356 / 0.0475 -- the interleaving buys nothing (a warp inside the fill
+// already issues at the rate its IMAD.WIDE / FP64 mix allows; the kernels lack WARPS, not ILP) and the tail of the fill, where
+// most slots idle but every trip still costs U attempts, grows with U.  U = 1 is the default.
+#ifndef QSB_FILL_U
+#define QSB_FILL_U 1
+#endif
+template <int G, int U = QSB_FILL_U>
 static __device__ __forceinline__ void gaussian_fill_body(uint32_t k0, uint32_t k1, uint32_t gc, uint32_t iter, int row_begin, int n, double* zw, int rstride) {
   // work item j: chain q = j % CPW of the warp's CPW = 32/G chains (gc = the chain of lane 0), component row_begin*G + j / CPW;
   // it belongs to lane q*G + (component % G), row component / G - row_begin of the staging rows at zw.  n = number of work items.
@@ -525,39 +533,59 @@ static __device__ __forceinline__ void gaussian_fill_body(uint32_t k0, uint32_t 
   const int lane = (int)(threadIdx.x & 31u);
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t comp0 = (uint32_t)row_begin * (uint32_t)G;
-  int j = lane, next = 32;
-  uint32_t blk = 0;
-  bool active = j < n;
-  while (__any_sync(0xffffffffu, active)) {
-    bool ok = false;
-    if (active) {
+  int j[U], next = 32 * U;
+  uint32_t blk[U];
+  bool active[U];
+#pragma unroll
+  for (int t = 0; t < U; ++t) { j[t] = lane + 32 * t; blk[t] = 0; active[t] = j[t] < n; }
+  for (;;) {
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < U; ++t) any = any || active[t];
+    if (!__any_sync(0xffffffffu, any)) break;
+    double u[U], v[U], qq[U];
+    uint32_t q[U], ci[U];
+    // the U attempts, unconditionally (an idle slot recomputes its last item: no branch separates the chains)
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
       uint32_t w[4];
-      const uint32_t q = (uint32_t)j % (uint32_t)CPW, ci = (uint32_t)j / (uint32_t)CPW;     // chain in the warp, component - comp0
-      philox4x32_10(blk, comp0 + ci, iter, gc + q, k0, k1, w);
-      const double u = __dsub_rn(1.0, u53(w[0], w[1]));
-      const double v = __dmul_rn(1.7156, __dsub_rn(u53(w[2], w[3]), 0.5));
-      const double x = __dsub_rn(u, 0.449871);
-      const double y = __dadd_rn(fabs(v), 0.386595);
-      const double qq = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, __dsub_rn(__dmul_rn(0.196, y), __dmul_rn(0.25472, x))));
-      if (!(qq >= 0.27597)) ok = true;
-      else if (qq > 0.27846) ok = false;
-      else {
+      q[t] = (uint32_t)j[t] % (uint32_t)CPW; ci[t] = (uint32_t)j[t] / (uint32_t)CPW;     // chain in the warp, component - comp0
+      philox4x32_10(blk[t], comp0 + ci[t], iter, gc + q[t], k0, k1, w);
+      u[t] = __dsub_rn(1.0, u53(w[0], w[1]));
+      v[t] = __dmul_rn(1.7156, __dsub_rn(u53(w[2], w[3]), 0.5));
+      const double x = __dsub_rn(u[t], 0.449871);
+      const double y = __dadd_rn(fabs(v[t]), 0.386595);
+      qq[t] = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, __dsub_rn(__dmul_rn(0.196, y), __dmul_rn(0.25472, x))));
+    }
+    bool ok[U];
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      ok[t] = !(qq[t] >= 0.27597);
+      if (!ok[t] && !(qq[t] > 0.27846)) {
         // The exact test v^2 > -4 u^2 log(u) (distrib.t:71) is reached by 0.85 % of the attempts, i.e. by some lane of a warp in
         // 23 % of the trips, and the double-precision log() then costs every lane ~90 instructions.  A single-precision log
         // decides it first: |__logf(u) - log(u)| < 1e-5 for every u in [2^-53, 1], so outside the band |v^2 - R_f| <= 4 u^2 * 2e-5
         // the decision equals the exact one; inside it (~1e-6 of the attempts) the exact expression is evaluated.
-        const double u2x4 = __dmul_rn(__dmul_rn(4.0, u), u), vv = __dmul_rn(v, v);
-        const double rf = u2x4 * (double)(-__logf((float)u)), band = u2x4 * 2e-5;
-        if (vv > rf + band) ok = false;
-        else if (vv < rf - band) ok = true;
-        else ok = !(vv > __dmul_rn(__dmul_rn(__dmul_rn(-4.0, u), u), log(u)));
+        const double u2x4 = __dmul_rn(__dmul_rn(4.0, u[t]), u[t]), vv = __dmul_rn(v[t], v[t]);
+        const double rf = u2x4 * (double)(-__logf((float)u[t])), band = u2x4 * 2e-5;
+        if (vv > rf + band) ok[t] = false;
+        else if (vv < rf - band) ok[t] = true;
+        else ok[t] = !(vv > __dmul_rn(__dmul_rn(__dmul_rn(-4.0, u[t]), u[t]), log(u[t])));
       }
-      if (ok) zw[(ci / (uint32_t)G) * rstride + q * (uint32_t)G + (ci % (uint32_t)G)] = v / u;
+      ok[t] = ok[t] && active[t];
     }
-    const unsigned m = __ballot_sync(0xffffffffu, ok);
-    if (ok) { j = next + __popc(m & lt); blk = 0; active = j < n; }
-    else ++blk;
-    next += __popc(m);
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const double z = v[t] / u[t];          // u in (0, 1]: finite for idle slots too
+      if (ok[t]) zw[(ci[t] / (uint32_t)G) * rstride + q[t] * (uint32_t)G + (ci[t] % (uint32_t)G)] = z;
+    }
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const unsigned m = __ballot_sync(0xffffffffu, ok[t]);
+      if (ok[t]) { j[t] = next + __popc(m & lt); blk[t] = 0; active[t] = j[t] < n; }
+      else if (active[t]) ++blk[t];
+      next += __popc(m);
+    }
   }
   __syncwarp();
 }
@@ -752,8 +780,8 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     int direction = 0;
     unsigned long long evals = 0;
     for (uint32_t probe = 0;; ++probe) {     // one leapfrog call site for the first probe and the doubling/halving loop
-      load(P.x, xs); load(P.g, gs);
       sample_momenta(QSB_ITER_SEARCH + probe, p);
+      load(P.x, xs); load(P.g, gs);
       const double lp = leapfrog(eps, xs, gs, p);
       ++evals;
       const double H = lp - prevlp;      // hmc.t:349-351, 357: dualTrace.logprob is the previous probe's value
@@ -804,8 +832,8 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
       fl |= FLAG_HMC_INIT | FLAG_GRAD_VALID;
     }
     if (P.temps && leader()) P.hmc_dualT[c] = T;   // hmc.t:266
-    load(P.x, xs); load(P.g, gs);
     sample_momenta(iter, p);
+    load(P.x, xs); load(P.g, gs);
     const double lp_cur = P.lp[c];
     const double H = kinetic(p) + lp_cur;
     double newlp = 0.0;
@@ -865,8 +893,8 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     unsigned long long evals = 0;
     GradScalars<FAM> gs;
     for (uint32_t probe = 0;; ++probe) {
+      sample_momenta(QSB_ITER_SEARCH + probe, p);     // (before the positions are loaded: the fill runs with few live registers)
       load(P.x, x);
-      sample_momenta(QSB_ITER_SEARCH + probe, p);
       gs.template reduce<G, NPL>(P, lane, x);
       kick(0.5 * eps, gs, x, p, false, invT);
       QSB_FOR_E x[e] = x[e] + eps * p[e] * 1.0;
@@ -914,8 +942,8 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
       }
       fl |= FLAG_HMC_INIT | FLAG_GRAD_VALID;
     }
-    load(P.x, x);
     sample_momenta(iter, p);
+    load(P.x, x);
     const double H = kinetic(p) + P.lp[c];
     rec_step = eps;
     const double he = 0.5 * eps;
