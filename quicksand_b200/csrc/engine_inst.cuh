@@ -20,7 +20,21 @@ template <int FAM, int G, int NPL> struct VariantImpl {
       cudaFuncSetAttribute(advance_kernel<FAM, G, NPL, HAS_HMC, LEX, DRIFT_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
       attr[dev & 63] = true;
     }
-    advance_kernel<FAM, G, NPL, HAS_HMC, LEX, DRIFT_ONLY><<<(unsigned)(((size_t)P.C * G + TPBA - 1) / TPBA), TPBA, SMEM, (cudaStream_t)st>>>(P);
+    // Thread per chain with less than one wave of blocks (config c2: 65 536 chains = 512 blocks of 128 on 148 SMs x 4 slots): the
+    // launch takes as long as the SM with the most warps, 4 blocks = 16 warps where the mean is 13.8.  Smaller blocks spread the
+    // same warps evenly (14 on the fullest SM with blocks of 64); every shared-memory offset in the kernel is relative to blockDim.
+    int tpb = TPBA;
+    if (G == 1 && !LEX) {
+      int nsm = 148;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+      size_t best = ~(size_t)0;
+      for (int b : {128, 64, 32}) {
+        const size_t blocks = ((size_t)P.C + b - 1) / b, worst = ((blocks + nsm - 1) / nsm) * (size_t)(b / 32);
+        if (worst < best && blocks <= (size_t)nsm * 16) { best = worst; tpb = b; }
+      }
+    }
+    const size_t smem = SMEM - (size_t)Chain<FAM, G, NPL>::NB * (TPBA - tpb) * sizeof(double);
+    advance_kernel<FAM, G, NPL, HAS_HMC, LEX, DRIFT_ONLY><<<(unsigned)(((size_t)P.C * G + tpb - 1) / tpb), tpb, smem, (cudaStream_t)st>>>(P);
   }
   static void advance(const EngineParams& P, void* st) { advance_t<true>(P, st); }
   static void advance_nohmc(const EngineParams& P, void* st) { advance_t<false>(P, st); }
