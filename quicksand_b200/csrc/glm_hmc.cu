@@ -12,12 +12,15 @@
 // second are chosen so that every thread only ever touches the 2*NJ dimensions it owns
 // (dims 8J+2t, 8J+2t+1 of chain g) and all shared-memory fragment loads are bank-conflict free.
 //
-// X (N x d, row stride S) is streamed from L2 through shared memory by one producer thread with TMA
-// bulk copies (cp.async.bulk + mbarrier complete_tx) into a ring of 2..4 stages; the 16 consumer warps of a
-// CTA (128 chains) all read the same staged rows, so each row block is fetched once per 128 chains; the chain tile's Theta
-// sits in shared memory next to the ring (conflict-free LDS.128 rows), not in registers.
-// The grid is (chain tiles) x (row splits): row splits give full waves on 148 SMs for any chain
-// count; their partial gradients are summed in a fixed order by the vector kernel (deterministic).
+// X (N x d, row stride S) is streamed from L2 through shared memory with TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx) into a ring of 2..4 stages.  There is no producer warp: the warp whose release of a stage is the last one
+// pending re-arms it.  The default build runs 12 warps x 8 chains per CTA (96 chains read the same staged rows, so a row
+// block is fetched once per 96 chains) with the Theta of a warp's 8 chains in registers (168 registers); QSB_GLM_CW = 16 /
+// QSB_GLM_THETA_SMEM select the measured-slower variants with the chain tile's Theta in shared memory.
+// Work decomposition: by default the (chain tile, row block) units are cut into one cost-balanced run per SM (grid = 148,
+// one wave for any chain count, host-computed run table); QSB_FLAG_INVARIANT selects the fixed grid (chain tiles) x (row
+// splits) whose grouping of row blocks into partial sums does not depend on the chain tile, so that a chain's draws are
+// bit-identical for any partition of the chains.  Partial gradients are summed in a fixed order by the vector kernel.
 //
 // The leapfrog updates, momenta, Hamiltonians, accept/reject, dual averaging and sample collection
 // are the warp-per-chain vector kernels below (qs/hmc.t:134-186, 289-323, 394-402).
