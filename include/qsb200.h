@@ -93,7 +93,8 @@ typedef struct {
    * -- the parameter expressions of a program such as  mu = gaussian(0,1); x = gaussian(mu, exp(logtau)).  The reference
    * re-evaluates them on every run and hands them to RandomChoiceT:update (trace.t:948-994, erp.t:576-610); in a dual trace the
    * tape differentiates the log-density with respect to them, including d/dk of the 5-coefficient log-gamma (distrib.t:84-106).
-   * gaussian, gamma and beta choices only (a uniform's parameters are its bounds); thread-per-chain mapping (dim <= 32). */
+   * gaussian, gamma and beta choices only (a uniform's parameters are its bounds); thread per chain up to 32 components, warp per
+   * chain (general evaluator on scratch memory) up to the INDEP family's 128. */
   const int32_t* erp_pref;  /* [2*dim] */
   const double* erp_pcoef;  /* [2*dim] */
   const int32_t* erp_ptf;   /* [2*dim] or NULL (all identity) */

@@ -444,7 +444,7 @@ int qsb_model_create(const qsb_model_desc* d, int32_t device, qsb_model** out) {
             if (d->erp_kind[i] == QSB_ERP_UNIFORM || d->erp_kind[i] == QSB_ERP_DIRICHLET)
               return bail(3, "INDEP: latent parameters are supported on gaussian, gamma and beta choices");
           }
-        if (any && d->dim > 32) return bail(3, "INDEP: latent parameters run in the thread-per-chain mapping (dim <= 32)");
+        // (dim <= 32: thread per chain; beyond that the warp-per-chain mapping with the sequential evaluator on scratch memory)
         if (any) {
           int *lr, *lt; double* lb;
           if (m->arena.alloc(&lr, 2 * (size_t)d->dim) || m->arena.alloc(&lt, 2 * (size_t)d->dim) || m->arena.alloc(&lb, 2 * (size_t)d->dim)) return bail(4, "cudaMalloc failed");
@@ -540,6 +540,7 @@ static int alloc_engine_state(qsb_sampler* s) {
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
   A(a.alloc(&P.x, C * d)); A(a.alloc(&P.lp, C)); A(a.alloc(&P.flags, C));
+  if (P.vs_dpad > 0) A(a.alloc(&P.vscratch, ((C + 7) / 8) * 8 * (size_t)VS_ARRAYS * P.vs_dpad));   // one slice per warp of the grid (blocks of 8 warps)
   A(a.alloc(&P.eps, C));   // also the lp_float output of the logp_grad test hook
   A(a.alloc(&P.g, C * d));
   if (has_hmc) {
@@ -636,13 +637,22 @@ int qsb_sampler_create(qsb_model* m, const qsb_kernel_spec* specs, int32_t nspec
   P.sample_chains = s->cfg.sample_chains;
   P.lag = 1;
   std::string why;
-  int mapping = m->dev.has_vector ? 1 : cfg->reserved;
+  // vector (dirichlet) choices and latent parameters: thread per chain up to 32 components (every component of the chain in
+  // one thread's registers), warp per chain with the general evaluator on scratch memory beyond that or when asked for
+  int mapping = cfg->reserved;
+  if (m->dev.has_vector) {
+    if (mapping != 0 && mapping != 1 && mapping != 32) return bail(2, "dirichlet choices and latent parameters run in the thread-per-chain (<= 32 components) or the warp-per-chain mapping");
+    if (mapping == 0) mapping = P.d <= 32 ? 1 : 32;
+    // the per-adapter running variances of lexicalScaleSharing are updated component by component in program order by the
+    // non-streaming drift kernel: one thread per chain
+    if (P.dr_lexical && mapping == 32) return bail(2, "DriftKernel{lexicalScaleSharing} over dirichlet choices / latent parameters runs in the thread-per-chain mapping (<= 32 components)");
+  }
   // c2-like shapes: four lanes per chain when the chains fill whole warps (8 per warp) and there are enough of them to matter
   if (mapping == 0 && m->desc.family == QSB_FAM_GAUSS_PREC && cfg->numchains % 8 == 0 && getenv("QSB_G4")) mapping = 4;   // (measured 2 x slower than thread per chain at c2's shape: not the default)
   if (mapping > 1 && mapping < 32 && cfg->numchains % (32 / mapping) != 0) return bail(2, "a mapping of " + std::to_string(mapping) + " lanes per chain needs a chain count that fills whole warps");
   s->var = pick_variant(m->desc.family, P.d, mapping, why);
-  if (!s->var) return bail(2, m->dev.has_vector ? "dirichlet choices and latent parameters run in the thread-per-chain mapping only (" + why + ")" : why);
-  if (m->dev.has_vector && cfg->reserved != 0 && cfg->reserved != 1) return bail(2, "dirichlet choices and latent parameters run in the thread-per-chain mapping only");
+  if (!s->var) return bail(2, why);
+  if (m->dev.has_vector && s->var->G == 32) P.vs_dpad = 32 * s->var->npl;   // scratch of the general evaluator (alloc_engine_state)
   if (m->desc.family == QSB_FAM_GAUSS_PREC) {
     const int d = P.d, npl = s->var->npl * s->var->G;   // row stride of the staged S = padded dimension
     for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) P.Sc[i * npl + j] = m->A[(size_t)i * d + j] + m->A[(size_t)j * d + i];
@@ -815,7 +825,7 @@ int qsb_sampler_advance(qsb_sampler* s, uint64_t iters) {
     // QSB_WS=1: the warp-per-chain variants run warp-specialised (sampler warps + trajectory warps, engine.cuh:
     // advance_ws_kernel) instead of fused (every warp samples and integrates)
     static const bool ws = getenv("QSB_WS") && atoi(getenv("QSB_WS")) != 0;   // (not the default yet: see profiles/README.md)
-    const bool use_ws = ws && s->var->advance_ws != nullptr;
+    const bool use_ws = ws && s->var->advance_ws != nullptr && !R.vscratch;   // (the scratch slices are indexed by the fused kernels' warp number)
     if (R.dr_lexical || has_mh) s->var->advance_lex(R, s->stream);   // the general kernel
     else if (R.nsub == 1 && R.kind[0] == K_DRIFT) (use_ws ? s->var->advance_drift_ws : s->var->advance_drift)(R, s->stream);
     else if (has_hmc) (use_ws ? s->var->advance_ws : s->var->advance)(R, s->stream);

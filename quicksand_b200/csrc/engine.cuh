@@ -43,11 +43,11 @@ struct ModelDev {
   // INDEP: optional hard constraint after scalar choice i, qs.condition(value_i > cond_lo[i] and value_i < cond_hi[i])
   // (trace.t:794-796, 1103-1107); nullptr: the program has none
   const double* cond_lo; const double* cond_hi;
-  // INDEP, dirichlet components (thread-per-chain mapping only): choice length K, sum of the later alphas of the choice,
+  // INDEP, dirichlet components (thread per chain; warp per chain through the scratch evaluator): choice length K, sum of the later alphas of the choice,
   // and the ERP index of every component (= the Philox slot of its forward sample; equals the component index without vector choices)
   const int* erp_len; const double* erp_asum; const int* erp_slot;
   int has_vector;
-  // INDEP, latent parameters (thread-per-chain mapping only): parameter q of choice i = f(p_q[i] + lat_b[2i+q] * value of
+  // INDEP, latent parameters (thread per chain; warp per chain through the scratch evaluator): parameter q of choice i = f(p_q[i] + lat_b[2i+q] * value of
   // choice lat_ref[2i+q]) with f = identity / exp (lat_tf); lat_ref < 0: constant; lat_ref == nullptr: none in the program
   const int* lat_ref; const double* lat_b; const int* lat_tf;
   // DriftKernel{lexicalScaleSharing} (drift.t:101-115, 208-235): scale adapter of every component.  INDEP: lex_map;
@@ -102,7 +102,11 @@ struct EngineParams {
   double *rec_state, *rec_dh, *rec_step, *rec_leap;
   int *rec_accept, *rec_kidx;
   uint64_t rec_iters;
+  // INDEP programs with vector (dirichlet) choices or latent parameters in the warp-per-chain mapping: VS_ARRAYS arrays of
+  // vs_dpad doubles per warp of the grid (see indep_general_warp); nullptr otherwise
+  double* vscratch; int vs_dpad;
 };
+static constexpr int VS_ARRAYS = 6;   // x, g, and the evaluator's four work arrays
 
 // ---------------------------------------------------------------------------------------------
 // G lanes per chain, G a power of two in 1..32: a warp holds 32/G chains side by side.  Reductions are xor butterflies over
@@ -170,10 +174,12 @@ static __device__ __noinline__ double dirichlet_component_noinline(SimplexCarry&
 // Forward in program order: value, resolved parameters, log-density terms and the adjoint each term sends to the values
 // its parameters were computed from; then g_i = (dlp_i/dy_i + adjoint_i) dy_i/dx_i + dlogJ_i/dx_i  -- the reverse sweep of
 // the reference's tape (ad.t) over  sum_i [lp_i(y_i; p(y_parents)) + logJ_i(x_i)]  (erp.t:623-640).
-static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const double* x, double* g, double* lp_float, bool grad, double* cond_bad) {
+// work: 4 * dim doubles (values, value adjoints, dlp/dy, dy/dx) -- a local array in the thread-per-chain mapping, this warp's
+// slice of EngineParams::vscratch in the warp-per-chain mapping (where lane 0 runs this function for its chain).
+static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const double* x, double* g, double* lp_float, bool grad, double* cond_bad, double* work) {
   const int d = m.dim;
   double bad = 0.0;
-  double yv[32], yb[32], A[32], B[32];
+  double* yv = work; double* yb = work + d; double* A = work + 2 * d; double* B = work + 3 * d;
   double lpd = 0.0, lpf = 0.0;
   SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
   for (int i = 0; i < d; ++i) { yb[i] = 0.0; yv[i] = 0.0; }
@@ -188,7 +194,7 @@ static __device__ __noinline__ double indep_latent_eval(const ModelDev& m, const
       continue;
     }
     double p0 = m.p0[i], p1 = m.p1[i], dp0 = 0.0, dp1 = 0.0;
-    const int r0 = m.lat_ref[2 * i], r1 = m.lat_ref[2 * i + 1];
+    const int r0 = m.lat_ref ? m.lat_ref[2 * i] : -1, r1 = m.lat_ref ? m.lat_ref[2 * i + 1] : -1;
     if (r0 >= 0) latent_param(m, i, 0, yv[r0], p0, dp0);
     if (r1 >= 0) latent_param(m, i, 1, yv[r1], p1, dp1);
     double dydx, dlpdy, dlj;
@@ -229,10 +235,29 @@ __device__ __forceinline__ double model_eval(const EngineParams& P, int lane, co
   if (cond_bad) *cond_bad = 0.0;
   if (FAM == FAM_INDEP) {
     if (G == 1 && NPL <= 32 && m.lat_ref) {   // latent parameters: the general (slow) evaluator on local copies
-      double xl[NPL], gl[NPL];
+      double xl[NPL], gl[NPL], work[4 * NPL];
       QSB_FOR_E { xl[e] = x[e]; gl[e] = 0.0; }
-      const double lpd = indep_latent_eval(m, xl, gl, &lp_float, GRAD, cond_bad);
+      const double lpd = indep_latent_eval(m, xl, gl, &lp_float, GRAD, cond_bad, work);
       if (GRAD) { QSB_FOR_E g[e] = e < d ? gl[e] : 0.0; }
+      return lpd;
+    }
+    if (G == 32 && P.vscratch) {
+      // Vector choices / latent parameters with a warp per chain (n up to 32 NPL): the stick-breaking recurrence and the
+      // parameter links run through the program in order, so lane 0 evaluates the chain with the same sequential evaluator
+      // the thread-per-chain mapping uses (same arithmetic, same order: the same numbers), on this warp's scratch slice;
+      // the lanes hand their components in and take their gradient components out.  Not a throughput path.
+      double* w = P.vscratch + (size_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) * VS_ARRAYS * P.vs_dpad;
+      double* xs = w; double* gsx = w + P.vs_dpad;
+      QSB_FOR_E { const int i = e * G + lane; if (i < d) xs[i] = x[e]; }
+      __syncwarp();
+      double lpd = 0.0, lpf = 0.0, bad = 0.0;
+      if (lane == 0) lpd = indep_latent_eval(m, xs, gsx, &lpf, GRAD, &bad, w + 2 * P.vs_dpad);
+      __syncwarp();
+      lpd = __shfl_sync(0xffffffffu, lpd, 0); lpf = __shfl_sync(0xffffffffu, lpf, 0); bad = __shfl_sync(0xffffffffu, bad, 0);
+      if (GRAD) { QSB_FOR_E { const int i = e * G + lane; g[e] = i < d ? gsx[i] : 0.0; } }
+      __syncwarp();
+      lp_float = lpf;
+      if (cond_bad) *cond_bad = bad;
       return lpd;
     }
     double lpd = 0.0, lpf = 0.0, bad = 0.0;
@@ -1275,7 +1300,7 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     kind = ERP_GAUSSIAN; p0 = 0.0; p1 = 1.0;
     if (FAM == FAM_INDEP) {
       kind = P.m.erp_kind[j]; p0 = P.m.p0[j]; p1 = P.m.p1[j];
-      if (G == 1 && P.m.lat_ref) {   // current parameters from the current values of the choices they depend on
+      if (P.m.lat_ref) {   // current parameters from the current values of the choices they depend on
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
           const int r = P.m.lat_ref[2 * j + q];
@@ -1310,7 +1335,7 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
     double fwdlp, rvslp;
     int kind; double p0, p1;
     choice_params(j0, x, kind, p0, p1);
-    if (G == 1 && FAM == FAM_INDEP && kind == ERP_DIRICHLET) {
+    if (FAM == FAM_INDEP && kind == ERP_DIRICHLET) {   // (every lane of the chain's group computes the chain-uniform proposal)
       // vector choice: K gammas from the proposal sub-stream, normalised (distrib.t:339-350); current value by stick
       // breaking, new unconstrained coordinates by its inverse (erp.t:205-233)
       const int K = P.m.erp_len[j0], Km1 = K - 1;
@@ -1329,11 +1354,11 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
         rvslp = rvslp + (alpha[q] - 1.0) * log(cur[q]); rvslp = rvslp - log_gamma5(alpha[q]);
       }
       double sticklen = t[Km1];
-      QSB_FOR_E { if (e == j0 + Km1) x[e] = 0.0; }
+      QSB_FOR_E { if (e * G + lane == j0 + Km1) x[e] = 0.0; }
       for (int q = Km1 - 1; q >= 0; --q) {
         sticklen = sticklen + t[q];
         const double xn = invlogistic_(t[q] / sticklen) + log((double)(Km1 - q));
-        QSB_FOR_E { if (e == j0 + q) x[e] = xn; }
+        QSB_FOR_E { if (e * G + lane == j0 + q) x[e] = xn; }
       }
     } else {
       const double cur_x = component(x, j0);
@@ -1639,16 +1664,23 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
       else accept = hmc_next(k, iter, rdh, rstep);
     }
     else if (LEX && kind == K_TRACEMH) accept = tracemh_next(k, iter, rdh, rstep);
+    // the streaming Drift / HARM scorers take a program term by term; INDEP programs with vector choices or latent parameters
+    // (vscratch set) are scored by the general evaluator through the non-streaming forms
     else if (DRIFT_ONLY || kind == K_DRIFT) {
       if (LEX && P.dr_lexical) {
-        if constexpr (STREAM) accept = drift_next_stream_lex(k, iter, rdh, rstep);
+        if constexpr (STREAM && FAM != FAM_INDEP) accept = drift_next_stream_lex(k, iter, rdh, rstep);
+        else if constexpr (STREAM) accept = P.vscratch ? drift_next_lex(k, iter, rdh, rstep) : drift_next_stream_lex(k, iter, rdh, rstep);
         else accept = drift_next_lex(k, iter, rdh, rstep);
       } else {
-        if constexpr (STREAM) accept = drift_next_stream<WS ? 32 : ((G == 1 || HAS_HMC) ? 128 : 256)>(k, iter, rdh, rstep);
+        constexpr int ZS = WS ? 32 : ((G == 1 || HAS_HMC) ? 128 : 256);
+        if constexpr (STREAM && FAM != FAM_INDEP) accept = drift_next_stream<ZS>(k, iter, rdh, rstep);
+        else if constexpr (STREAM) accept = P.vscratch ? drift_next(k, iter, rdh, rstep) : drift_next_stream<ZS>(k, iter, rdh, rstep);
         else accept = drift_next(k, iter, rdh, rstep);
       }
     }
-    else accept = STREAM ? harm_next_stream(k, iter, rdh, rstep) : harm_next(k, iter, rdh, rstep);
+    else if constexpr (STREAM && FAM != FAM_INDEP) accept = harm_next_stream(k, iter, rdh, rstep);
+    else if constexpr (STREAM) accept = P.vscratch ? harm_next(k, iter, rdh, rstep) : harm_next_stream(k, iter, rdh, rstep);
+    else accept = harm_next(k, iter, rdh, rstep);
     if constexpr (WS) ws_release();
     // health counters: a non-finite accept threshold, an HMC energy error beyond 1000
     if (!(fabs(rdh) <= 1.7976931348623157e308)) count(2, 1);
@@ -1678,7 +1710,29 @@ template <int FAM, int G, int NPL, bool WS = false> struct Chain {
               mom_update([&](int st) { return base + (size_t)st * plane; }, sidx, P.mom_half, P.mom_batch, v);
             } else P.samples[G == 1 ? ((size_t)sidx * P.retdim + j) * SC + c : ((size_t)sidx * SC + c) * P.retdim + j] = v;
           };
-          if (FAM == FAM_INDEP) {
+          if (FAM == FAM_INDEP && G == 32 && P.vscratch && P.m.has_vector) {
+            // the values of a dirichlet choice come out of the stick-breaking recurrence in component order: lane 0 walks
+            // the chain's components through the scratch slice, the lanes then store (or sum) their own
+            double* w = P.vscratch + (size_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) * VS_ARRAYS * P.vs_dpad;
+            QSB_FOR_E { const int i = e * G + lane; if (i < d) w[i] = x[e]; }
+            __syncwarp();
+            if (lane == 0) {
+              SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
+              double* ys = w + P.vs_dpad;
+              for (int i = 0; i < d; ++i) {
+                double gdummy;
+                if (P.m.erp_kind[i] == ERP_DIRICHLET) ys[i] = dirichlet_component_noinline(sc, (int)P.m.p1[i], P.m.erp_len[i], w[i], P.m.p0[i], P.m.erp_asum[i], gdummy);
+                else ys[i] = erp_fwd_noinline(P.m.erp_kind[i], w[i], P.m.p0[i], P.m.p1[i]);
+              }
+            }
+            __syncwarp();
+            if (P.m.ret_mode == 0) {
+              if (lane == 0) { double sum = 0.0; for (int i = 0; i < d; ++i) sum += w[P.vs_dpad + i]; put(0, sum / P.m.ret_div); }
+            } else {
+              QSB_FOR_E { const int i = e * G + lane; if (i < d) put(i, w[P.vs_dpad + i]); }
+            }
+            __syncwarp();
+          } else if (FAM == FAM_INDEP) {
             double sum = 0.0;
             SimplexCarry sc; sc.stick = 1.0; sc.lp = 0.0; sc.lj = 0.0;
             QSB_FOR_E {
@@ -1794,6 +1848,56 @@ advance_ws_kernel(const __grid_constant__ EngineParams P) {
   }
 }
 
+// The forward sample of a whole INDEP chain in program order by ONE lane (warp-per-chain mapping with vector choices or latent
+// parameters: a later choice reads the sampled values of earlier ones, a dirichlet choice is one draw of K components).  The
+// statements are those of the thread-per-chain branch of init_kernel below, over arrays in the warp's scratch slice.
+static __device__ __noinline__ void indep_init_seq(const EngineParams& P, uint32_t gc, uint32_t it_init, double* xs, double* yv, double& lp_out, double& bad_out) {
+  const ModelDev& m = P.m;
+  const int d = m.dim;
+  double lp = 0.0, bad = 0.0;
+  for (int i = 0; i < d; ++i) xs[i] = 0.0;
+  for (int i = 0; i < d; ++i) {
+    const int kind = m.erp_kind[i];
+    double p0 = m.p0[i], p1 = m.p1[i];
+    if (m.lat_ref) {
+      double dp;
+      const int r0 = m.lat_ref[2 * i], r1 = m.lat_ref[2 * i + 1];
+      if (r0 >= 0) latent_param(m, i, 0, yv[r0], p0, dp);
+      if (r1 >= 0) latent_param(m, i, 1, yv[r1], p1, dp);
+    }
+    const uint32_t slot = m.erp_slot ? (uint32_t)m.erp_slot[i] : (uint32_t)i;
+    if (kind == ERP_DIRICHLET) {
+      if ((int)p1 == 0) {
+        const int K = m.erp_len[i], Km1 = K - 1;
+        SubStream s(P.key, gc, it_init, slot);
+        double t[32];
+        double ssum = 0.0, asum = 0.0;
+        for (int k = 0; k < K; ++k) { t[k] = gamma_sample_seq(s, m.p0[i + k], 1.0); ssum = ssum + t[k]; asum = asum + m.p0[i + k]; }
+        for (int k = 0; k < K; ++k) t[k] = t[k] / ssum;
+        double lpv = log_gamma5(asum);
+        for (int k = 0; k < K; ++k) { const double a = m.p0[i + k]; lpv = lpv + (a - 1.0) * log(t[k]); lpv = lpv - log_gamma5(a); }
+        lp += lpv;
+        double sticklen = t[Km1];
+        for (int k = Km1 - 1; k >= 0; --k) {
+          sticklen = sticklen + t[k];
+          const double z = t[k] / sticklen;
+          xs[i + k] = invlogistic_(z) + log((double)(Km1 - k));
+        }
+      }
+      yv[i] = 0.0;
+    } else {
+      SubStream s(P.key, gc, it_init, slot);
+      const double y = erp_sample_seq(kind, s, p0, p1);
+      lp += erp_prior_lp(kind, y, p0, p1, nullptr);
+      if (m.fsigma && m.fsigma[i] > 0.0) lp += gaussian_lp(y, m.fmu[i], m.fsigma[i]);
+      xs[i] = erp_inv(kind, y, p0, p1);
+      if (m.cond_lo && !(y > m.cond_lo[i] && y < m.cond_hi[i])) bad += 1.0;
+      yv[i] = y;
+    }
+  }
+  lp_out = lp; bad_out = bad;
+}
+
 // Forward-sampling initialisation (trace.t:592-624: update(true) creates every choice by sampling it,
 // erp.t:567-572) followed by the kernels' first gather of unconstrained components (erp.t:519-522).
 // The ERPs of a chain are sampled in program order; ERP i reads sub-stream (chain, ITER_INIT, i).
@@ -1805,7 +1909,20 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256) init_kernel(const __grid_c
   const int lane = ch.lane, d = P.d;
   double x[NPL];
   double lp0 = 0.0;
-  if (FAM == FAM_INDEP) {
+  if (FAM == FAM_INDEP && G == 32 && P.vscratch) {
+    double* w = P.vscratch + (size_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) * VS_ARRAYS * P.vs_dpad;
+    double lp = 0.0;
+    for (uint32_t attempt = 0;; ++attempt) {     // rejection initialisation as below
+      double bad = 0.0;
+      if (lane == 0) indep_init_seq(P, ch.gc, QSB_ITER_INIT - attempt, w, w + 2 * P.vs_dpad, lp, bad);
+      __syncwarp();
+      bad = __shfl_sync(0xffffffffu, bad, 0);
+      if (!P.m.cond_lo || bad == 0.0 || attempt >= 100000u) break;
+    }
+    lp0 = __shfl_sync(0xffffffffu, lp, 0);
+    QSB_FOR_E { const int i = e * G + lane; x[e] = i < d ? w[i] : 0.0; }
+    __syncwarp();
+  } else if (FAM == FAM_INDEP) {
     double lp = 0.0;
     double yv[G == 1 ? NPL : 1];   // sampled values (programs with latent parameters: later choices read them)
     // rejection initialisation (trace.t:612-623): re-run the program from scratch until every qs.condition holds; attempt a

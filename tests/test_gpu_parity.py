@@ -92,6 +92,13 @@ def _programs(qs):
                                          conditions=[(-1.5, None), (None, -0.01), (0.02, 30.0), None, (-5.0, 7.0)] * 8)          # 40 components: warp per chain
     progs["condhier4"] = qs.programs.indep([("gaussian", 1.0, 0.5), ("gaussian", 0.0, 0.5), ("gaussian", lat(0), lat(1, b=0.5, exp=True)),
                                              ("gaussian", lat(2, a=0.5, b=2.0), 1.0)], ret="vector", conditions=[(0.0, None), None, (-1.0, 4.0), None])
+    # vector choices and latent parameters beyond 32 components: warp per chain, the general evaluator on scratch memory
+    progs["hier70"] = qs.programs.indep([("gaussian", 1.0, 0.5), ("gaussian", 0.0, 0.5)] + [("gaussian", lat(0), lat(1, b=0.5, exp=True))] * 60
+                                         + [("gamma", 3.0, 1.0), ("gamma", lat(62), 2.0), ("dirichlet", [2.0, 3.0, 5.0, 1.5, 2.5, 4.0])], ret="vector",
+                                         factors=[None] * 2 + [(1.2, 0.8)] * 30 + [None] * 32 + [None])
+    progs["hier64"] = qs.programs.indep([("gaussian", 1.0, 0.5), ("gaussian", 0.0, 0.5)] + [("gaussian", lat(0), lat(1, b=0.5, exp=True))] * 60
+                                         + [("gamma", 3.0, 1.0), ("gamma", lat(62), 2.0)], ret="vector", factors=[None] * 2 + [(1.2, 0.8)] * 30 + [None] * 32)
+    progs["dirwide40"] = qs.programs.indep([("dirichlet", [1.5, 0.8, 2.0, 3.0, 1.2, 0.9, 1.0, 2.5])] * 5, ret="vector")
     progs["c2"] = qs.programs.c2_correlated_gaussian()[0]
     J = 11
     progs["schools13"] = qs.programs.eight_schools(rng.normal(4, 10, J), rng.uniform(8, 18, J))
