@@ -59,3 +59,82 @@ def test_small_programs_adaptive_every_leapfrog_step(qs, oracle, monkeypatch, na
         monkeypatch.setenv("QSB_TEST_MAPPING", str(mapping))
     prog = _programs(qs)[name]
     P.teacher_forced_hmc(prog, qs.HMCKernel(numSteps=L), chains=48, iters=25, seed=7, what="%s adaptive L=%d map%d" % (name, L, mapping))
+
+
+def test_c3_full_shape_working_regime_ties_the_device_run_to_the_oracle(qs, oracle):
+    """The headline configuration where it spends its time: AFTER the adaptation transient.  A free-running device run of c3
+    (full shape, adaptive, L = 20, the bench's 150 burn-in transitions) is recorded; for each of its next transitions the
+    oracle side re-computes the whole trajectory from the DEVICE's own state and step size -- momenta from the shared Philox
+    stream, `HMCKernel:step` (hmc.t:307-323) in the reference's operation order on the oracle's tape-AD gradient -- and
+
+    * every one of the 20 leapfrog steps is replayed on the device from the oracle's input (qsb_debug_leapfrog: the tensor-core
+      gradient kernel) and agrees within 1e-10 (positions, momenta, log-density; gradient 1e-9): no trajectory is exempt;
+    * the accept decision the device run actually took, its energy error and the state it moved to equal the oracle's.
+
+    Nothing here depends on a prefix or on a divergence filter: in the working regime |dH| is of order one."""
+    from concurrent.futures import ThreadPoolExecutor
+    from quicksand_b200 import _lib as L
+    X, y, _ = qs.programs.c3_logistic_data(10000, 100)
+    prog = qs.programs.logistic(X, y, 2.5)
+    C, B, T, Ls, seed, d = 16, 150, 4, 20, 20261019, 100
+    s = qs.Sampler(prog, qs.HMCKernel(numSteps=Ls), numchains=C, seed=seed, flags=L.FLAG_RECORD)
+    s.init(); s.run(T, B, 1)
+    rec = s.fetch_record(); s.close()
+    state, step, acc, dH = rec["state"], rec["step"], rec["accept"], rec["dH"]
+
+    def seqsum(v):
+        t = 0.0
+        for a in v:
+            t = t + a
+        return t
+
+    def one(c):
+        op = P.oracle_program(prog)          # (the oracle's tape is thread-local)
+        out = []
+        for t in range(B, B + T):
+            x, eps = state[c, t - 1].copy(), float(step[c, t])
+            p = oracle.gaussians(seed, c, t, 0, d)
+            lp, g, _ = op.logp_grad(x)
+            H0 = -0.5 * seqsum(p * p * 1.0) + lp
+            xin, pin, gin, xo, po, go = [], [], [], [], [], []
+            for _ in range(Ls):
+                xin.append(x.copy()); pin.append(p.copy()); gin.append(g.copy())
+                p = p + (0.5 * eps) * g
+                x = x + (eps * p) * 1.0
+                lp, g, _ = op.logp_grad(x)
+                p = p + (0.5 * eps) * g
+                xo.append(x.copy()); po.append(p.copy()); go.append(g.copy())
+            dh = (-0.5 * seqsum(p * p * 1.0) + lp) - H0
+            u = oracle.uniforms(seed, c, t, d, 1)[0]
+            out.append(dict(c=c, t=t, eps=eps, xin=np.array(xin), pin=np.array(pin), gin=np.array(gin), xo=np.array(xo), po=np.array(po), go=np.array(go),
+                            lp=lp, dH=dh, accept=bool(np.log(u) < dh), x_start=state[c, t - 1]))
+        return out
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        trajs = [tr for chain in ex.map(one, range(C)) for tr in chain]
+    worst = dict(x=0.0, p=0.0, g=0.0, lp=0.0, dH=0.0, state=0.0)
+    flips = 0
+    for last in (False, True):
+        sl = slice(Ls - 1, Ls) if last else slice(0, Ls - 1)
+        xin = np.concatenate([tr["xin"][sl] for tr in trajs]); pin = np.concatenate([tr["pin"][sl] for tr in trajs]); gin = np.concatenate([tr["gin"][sl] for tr in trajs])
+        eps = np.concatenate([np.full(xin.shape[0] // len(trajs), tr["eps"]) for tr in trajs])
+        r = prog.debug_leapfrog(xin, pin, eps, g=gin, last=last)
+        for key, ref in (("x", "xo"), ("p", "po"), ("g", "go")):
+            want = np.concatenate([tr[ref][sl] for tr in trajs])
+            worst[key] = max(worst[key], float(P.relerr(r[key], want, P.vector_floor(want)).max()))
+        if last:
+            worst["lp"] = float(P.relerr(r["lp"], np.array([tr["lp"] for tr in trajs])).max())
+    for tr in trajs:
+        c, t = tr["c"], tr["t"]
+        flips += int(bool(acc[c, t]) != tr["accept"])
+        worst["dH"] = max(worst["dH"], abs(dH[c, t] - tr["dH"]) / max(1.0, abs(tr["lp"])))        # a difference of two Hamiltonians of size |lp|
+        want = tr["xo"][-1] if tr["accept"] else tr["x_start"]
+        worst["state"] = max(worst["state"], float(P.relerr(state[c, t], want, P.vector_floor(want)).max()))
+    dhs = np.array([tr["dH"] for tr in trajs])
+    msg = ("c3 full shape, working regime: %d trajectories x %d steps, x %.2e p %.2e g %.2e lp %.2e; device run vs oracle: dH %.2e (rel. to H) state %.2e "
+           "accept flips %d; accept rate %.2f, |dH| max %.2f, eps range [%.3g, %.3g]" % (
+               len(trajs), Ls, worst["x"], worst["p"], worst["g"], worst["lp"], worst["dH"], worst["state"], flips, float(np.mean([tr["accept"] for tr in trajs])),
+               float(np.abs(dhs).max()), min(tr["eps"] for tr in trajs), max(tr["eps"] for tr in trajs)))
+    print(msg)
+    assert np.abs(dhs).max() < 30.0, msg                      # the working regime: no divergent trajectory among them
+    assert worst["x"] <= 1e-10 and worst["p"] <= 1e-10 and worst["lp"] <= 1e-10 and worst["g"] <= 1e-9, msg
+    assert flips == 0 and worst["dH"] <= 1e-10 and worst["state"] <= 1e-10, msg
