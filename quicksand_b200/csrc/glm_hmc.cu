@@ -58,6 +58,16 @@ static constexpr int CW = QSB_GLM_CW;
 static constexpr bool THETA_SMEM = QSB_GLM_THETA_SMEM;
 static constexpr int CB = CW * 8;      // chains per CTA
 static constexpr int GRAD_THREADS = CW * 32;
+// Column-permuted X for config c3's shape (the TRIM instantiation: 13 dimension tiles, d <= 100).  Logical dimension 8J + n sits
+// in physical column n * PERM_PJ + J, so the dimensions a thread needs from consecutive tiles J, J+1 are adjacent in shared
+// memory: the B fragments of BOTH contractions come in as LDS.128 (two tiles per load) -- the second contraction had one
+// LDS.64 per DMMA (104 per row block) in the natural layout.  Row stride PERM_S = 114 doubles and the identity row map make
+// both load patterns conflict-free per quarter warp (checked exhaustively: tools in DESIGN.md 5.2).  0 = natural layout.
+#ifndef QSB_GLM_PERM
+#define QSB_GLM_PERM 1
+#endif
+static constexpr bool PERMX = QSB_GLM_PERM != 0 && !THETA_SMEM;   // (the Theta-in-shared-memory builds keep the natural layout)
+static constexpr int PERM_PJ = 14, PERM_S = 114;
 
 struct GradParams {
   const double* Xp; const double* yv;
@@ -253,8 +263,9 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
   const bool valid = chain < P.C;
   const int S = P.S;
   const int nj = FULL ? NJ : P.nj;
-  // row permutation inside an 8-row tile (see header): rho = [0,2,1,3,6,4,7,5]
-  const uint32_t RHO = 0x57463120u;
+  // row permutation inside an 8-row tile (see header): rho = [0,2,1,3,6,4,7,5]; identity with the column-permuted X
+  constexpr bool PERM = TRIM && PERMX;
+  const uint32_t RHO = PERM ? 0x76543210u : 0x57463120u;
   const int rho_g = (RHO >> (4 * gid)) & 7, rho_t0 = (RHO >> (8 * tig)) & 7, rho_t1 = (RHO >> (8 * tig + 4)) & 7;
 
   double th[THETA_SMEM ? 1 : NJ][2], G[NJ][2];
@@ -276,8 +287,9 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
   if (TRIM && valid) thL = COH ? __ldcg(P.theta + (size_t)chain * P.Dp + 8 * (NJ - 1) + tig) : P.theta[(size_t)chain * P.Dp + 8 * (NJ - 1) + tig];
   double lpacc = 0.0;
   const int offA = rho_g * S + 2 * tig;                 // phase 1 B fragment: X[rho(gid)][8J + 2tig .. +1]
-  const int offL = rho_g * S + 8 * (NJ - 1) + tig;      // TRIM: X[rho(gid)][8(NJ-1) + tig]
-  const int offB0 = rho_t0 * S + gid, offB1 = rho_t1 * S + gid;   // phase 2 B fragment: X[rho(2tig+e)][8J + gid]
+  const int offL = PERM ? rho_g * S + tig * PERM_PJ + (NJ - 1) : rho_g * S + 8 * (NJ - 1) + tig;      // TRIM: X[rho(gid)][8(NJ-1) + tig]
+  const int offB0 = rho_t0 * S + (PERM ? gid * PERM_PJ : gid), offB1 = rho_t1 * S + (PERM ? gid * PERM_PJ : gid);   // phase 2 B fragment: X[rho(2tig+e)][8J + gid]
+  const int offP = rho_g * S + 2 * tig * PERM_PJ;       // PERM, phase 1: X[rho(gid)][(2tig + s) PJ + J]
   constexpr bool want_lp = LP;
 
   // Software pipeline over row blocks: while the sigmoid epilogue of block b runs on the FP64 ALU path, the first
@@ -304,6 +316,22 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
 #pragma unroll
     for (int T = 0; T < NT; ++T) dmma(a[T], t1, xv[T].y);   // then the dependent second k-step of each
   };
+  // PERM: half of a tile pair.  slot k = 2 Jp + s: k-step s of tiles J = 2 Jp and J + 1 from one LDS.128 per n-tile
+  // (4 loads, 8 DMMAs: the granularity of phase1_tile, so the lock-step sigmoid schedule below is unchanged)
+  auto phase1_half = [&](const double* Xs, int k, double (&a)[NT][2]) {
+    const int J = k & ~1, sidx = k & 1;
+    double2 xv[NT];
+#pragma unroll
+    for (int T = 0; T < NT; ++T) xv[T] = *reinterpret_cast<const double2*>(Xs + T * 8 * S + offP + sidx * PERM_PJ + J);
+    const double t0 = th[J % (THETA_SMEM ? 1 : NJ)][sidx], t1 = th[(J + 1) % (THETA_SMEM ? 1 : NJ)][sidx];
+#pragma unroll
+    for (int T = 0; T < NT; ++T) dmma(a[T], t0, xv[T].x);
+#pragma unroll
+    for (int T = 0; T < NT; ++T) dmma(a[T], t1, xv[T].y);
+  };
+  auto phase1_slot = [&](const double* Xs, int k, double (&a)[NT][2]) {
+    if constexpr (PERM) phase1_half(Xs, k, a); else phase1_tile(Xs, k, a);
+  };
   // Log-likelihood of a row block: sum_i log w_i with w_i = (y_i ? p_i : 1 - p_i) (distrib.t:17-25 on the naive sigmoid) is
   // taken as ONE log of the product of the block's eight w_i per thread -- seven library logs fewer per block, and the
   // product's rounding (8 ulp) is smaller than that of a sum of eight logs.  Factors below 1e-30 (a hopelessly misfit
@@ -328,8 +356,14 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
     mbar_wait(&full[0], 0u);
 #pragma unroll
     for (int T = 0; T < NT; ++T) acc[T][0] = acc[T][1] = 0.0;
+    if constexpr (PERM) {
 #pragma unroll
-    for (int J = 0; J < NJ; ++J) if (FULL || J < nj) phase1_tile(sm, J, acc);
+      for (int k = 0; k < NJ - 1; ++k) phase1_half(sm, k, acc);
+      phase1_tile(sm, NJ - 1, acc);
+    } else {
+#pragma unroll
+      for (int J = 0; J < NJ; ++J) if (FULL || J < nj) phase1_tile(sm, J, acc);
+    }
   }
   for (int b = b0; b < b1; ++b) {
     const int it = b - b0, st = it % NST;
@@ -351,18 +385,18 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
           sa[i].zr = acc[i >> 1][i & 1]; sa[i].q = 0.0; sa[i].k = 0; ya[i] = ys[(i >> 1) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
           sb[i].zr = acc[2 + (i >> 1)][i & 1]; sb[i].q = 0.0; sb[i].k = 0; yb[i] = ys[(2 + (i >> 1)) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
         }
-        if (FULL || 0 < nj) phase1_tile(Xn, 0, nxt);  sigmoid_steps<0, 4>(sa, ya);
-        if (FULL || 1 < nj) phase1_tile(Xn, 1, nxt);  sigmoid_steps<4, 8>(sa, ya);
-        if (FULL || 2 < nj) phase1_tile(Xn, 2, nxt);  sigmoid_steps<8, 12>(sa, ya);
-        if (FULL || 3 < nj) phase1_tile(Xn, 3, nxt);  sigmoid_steps<12, 16>(sa, ya);
-        if (FULL || 4 < nj) phase1_tile(Xn, 4, nxt);  sigmoid_steps<16, 20>(sa, ya);
-        if (FULL || 5 < nj) phase1_tile(Xn, 5, nxt);  sigmoid_steps<20, 22>(sa, ya);
-        if (FULL || 6 < nj) phase1_tile(Xn, 6, nxt);  sigmoid_steps<0, 4>(sb, yb);
-        if (FULL || 7 < nj) phase1_tile(Xn, 7, nxt);  sigmoid_steps<4, 8>(sb, yb);
-        if (FULL || 8 < nj) phase1_tile(Xn, 8, nxt);  sigmoid_steps<8, 12>(sb, yb);
-        if (FULL || 9 < nj) phase1_tile(Xn, 9, nxt);  sigmoid_steps<12, 16>(sb, yb);
-        if (FULL || 10 < nj) phase1_tile(Xn, 10, nxt); sigmoid_steps<16, 20>(sb, yb);
-        if (FULL || 11 < nj) phase1_tile(Xn, 11, nxt); sigmoid_steps<20, 22>(sb, yb);
+        if (FULL || 0 < nj) phase1_slot(Xn, 0, nxt);  sigmoid_steps<0, 4>(sa, ya);
+        if (FULL || 1 < nj) phase1_slot(Xn, 1, nxt);  sigmoid_steps<4, 8>(sa, ya);
+        if (FULL || 2 < nj) phase1_slot(Xn, 2, nxt);  sigmoid_steps<8, 12>(sa, ya);
+        if (FULL || 3 < nj) phase1_slot(Xn, 3, nxt);  sigmoid_steps<12, 16>(sa, ya);
+        if (FULL || 4 < nj) phase1_slot(Xn, 4, nxt);  sigmoid_steps<16, 20>(sa, ya);
+        if (FULL || 5 < nj) phase1_slot(Xn, 5, nxt);  sigmoid_steps<20, 22>(sa, ya);
+        if (FULL || 6 < nj) phase1_slot(Xn, 6, nxt);  sigmoid_steps<0, 4>(sb, yb);
+        if (FULL || 7 < nj) phase1_slot(Xn, 7, nxt);  sigmoid_steps<4, 8>(sb, yb);
+        if (FULL || 8 < nj) phase1_slot(Xn, 8, nxt);  sigmoid_steps<8, 12>(sb, yb);
+        if (FULL || 9 < nj) phase1_slot(Xn, 9, nxt);  sigmoid_steps<12, 16>(sb, yb);
+        if (FULL || 10 < nj) phase1_slot(Xn, 10, nxt); sigmoid_steps<16, 20>(sb, yb);
+        if (FULL || 11 < nj) phase1_slot(Xn, 11, nxt); sigmoid_steps<20, 22>(sb, yb);
 #pragma unroll
         for (int J = 12; J < NJ; ++J) if (FULL || J < nj) phase1_tile(Xn, J, nxt);
 #pragma unroll
@@ -399,9 +433,18 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const double* xb = Xs + T * 8 * S + (e ? offB1 : offB0);
+        if constexpr (PERM) {
+#pragma unroll
+          for (int J = 0; J < NJ; J += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(xb + J);
+            dmma(G[J], acc[T][e], v.x);
+            if (J + 1 < NJ) dmma(G[J + 1], acc[T][e], v.y);
+          }
+        } else {
 #pragma unroll
         for (int J = 0; J < NJ; ++J)
           if (FULL || J < nj) dmma(G[J], acc[T][e], xb[8 * J]);
+        }
       }
     }
     __syncwarp();
@@ -986,17 +1029,27 @@ int glm_model_create(GlmModel* m, const double* X, const uint8_t* y, int N, int 
   m->N = N; m->d = d; m->prior_sigma = prior_sigma;
   m->Dp = 8 * ((d + 7) / 8);
   int S = d; while (S % 8 != 4) ++S;
+  m->perm = PERMX && m->Dp / 8 == 13 && d <= 8 * 12 + 4;     // the shape launch_grad_t runs with the TRIM instantiation
+  if (m->perm) S = PERM_S;
   m->S = S;
   m->Npad = MB * ((N + MB - 1) / MB);
   std::vector<double> Xp((size_t)m->Npad * S, 0.0), yv(m->Npad, 2.0);
   for (int i = 0; i < N; ++i) {
-    memcpy(&Xp[(size_t)i * S], X + (size_t)i * d, sizeof(double) * d);
+    if (m->perm) { for (int j = 0; j < d; ++j) Xp[(size_t)i * S + (j & 7) * PERM_PJ + (j >> 3)] = X[(size_t)i * d + j]; }
+    else memcpy(&Xp[(size_t)i * S], X + (size_t)i * d, sizeof(double) * d);
     yv[i] = y[i] ? 1.0 : 0.0;
   }
   if (cudaMalloc((void**)&m->Xp, Xp.size() * 8) != cudaSuccess || cudaMalloc((void**)&m->yv, yv.size() * 8) != cudaSuccess) { why = "cudaMalloc failed"; return 2; }
   cudaMemcpy(m->Xp, Xp.data(), Xp.size() * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(m->yv, yv.data(), yv.size() * 8, cudaMemcpyHostToDevice);
   return 0;
+}
+// column-permuted copy of freshly uploaded rows (glm_model_update): logical dimension j of row i -> column (j % 8) PJ + j / 8
+__global__ void permute_x_kernel(const double* __restrict__ Xraw, double* __restrict__ Xp, int N, int d, int S) {
+  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * d) return;
+  const int i = (int)(idx / d), j = (int)(idx - (size_t)i * d);
+  Xp[(size_t)i * S + (j & 7) * PERM_PJ + (j >> 3)] = Xraw[idx];
 }
 __global__ void ybin_to_double_kernel(const uint8_t* yb, double* yv, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1007,7 +1060,16 @@ __global__ void ybin_to_double_kernel(const uint8_t* yb, double* yv, int n) {
 int glm_model_update(GlmModel* m, const double* X, const uint8_t* y, void* stream, std::string& why) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  if (m->S == m->d) e = cudaMemcpyAsync(m->Xp, X, (size_t)m->N * m->d * 8, cudaMemcpyHostToDevice, st);
+  if (m->perm) {
+    if (!m->Xraw && cudaMalloc((void**)&m->Xraw, (size_t)m->N * m->d * 8) != cudaSuccess) { why = "cudaMalloc failed"; return 2; }
+    e = cudaMemcpyAsync(m->Xraw, X, (size_t)m->N * m->d * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+      const size_t n = (size_t)m->N * m->d;
+      permute_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->Xraw, m->Xp, m->N, m->d, m->S);
+      e = cudaGetLastError();
+    }
+  }
+  else if (m->S == m->d) e = cudaMemcpyAsync(m->Xp, X, (size_t)m->N * m->d * 8, cudaMemcpyHostToDevice, st);
   else e = cudaMemcpy2DAsync(m->Xp, (size_t)m->S * 8, X, (size_t)m->d * 8, (size_t)m->d * 8, m->N, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) { why = cudaGetErrorString(e); return 100 + (int)e; }
   if (!m->ybin_dev && cudaMalloc((void**)&m->ybin_dev, m->N) != cudaSuccess) { why = "cudaMalloc failed"; return 2; }
@@ -1020,6 +1082,8 @@ int glm_model_update(GlmModel* m, const double* X, const uint8_t* y, void* strea
 }
 void glm_model_destroy(GlmModel* m) {
   if (m->Xp) cudaFree(m->Xp);
+  if (m->Xraw) cudaFree(m->Xraw);
+  m->Xraw = nullptr;
   if (m->yv) cudaFree(m->yv);
   if (m->ybin_dev) cudaFree(m->ybin_dev);
   m->Xp = m->yv = nullptr; m->ybin_dev = nullptr;

@@ -10,10 +10,12 @@ namespace qsb {
 struct GlmModel {
   int N = 0, d = 0;        // observations, regression dimension
   int Npad = 0;            // rows padded to a whole number of row blocks
-  int S = 0;               // row stride of the staged X in doubles (>= d, S % 8 == 4: conflict-free fragment loads)
+  int S = 0;               // row stride of the staged X in doubles (>= d, S % 8 == 4: conflict-free fragment loads; 114 when perm)
   int Dp = 0;              // d padded to a multiple of 8 (DMMA n-tiles)
   double prior_sigma = 0;
+  bool perm = false;       // c3's shape (13 dimension tiles, d <= 100): columns of Xp permuted, dimension 8J + n in column 14 n + J (glm_hmc.cu: PERMX)
   double* Xp = nullptr;    // HBM [Npad][S], zero padded
+  double* Xraw = nullptr;  // HBM [N][d] staging of qsb_model_update_data when Xp is column-permuted
   double* yv = nullptr;    // HBM [Npad]: 0.0 / 1.0, 2.0 marks a padding row
   uint8_t* ybin_dev = nullptr;  // HBM [N] raw labels, staging of qsb_model_update_data
 };
