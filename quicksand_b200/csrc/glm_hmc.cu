@@ -110,8 +110,20 @@ __host__ __device__ inline int theta_stride(int Dp) { return ((Dp / 8) & 1) ? Dp
 // issue slots and reconvergence stalls inside the MMA pipeline (ncu: profiles/r01_c3_grad_v1).  Accurate to
 // ~2 ulp (range reduction with a split ln2, degree-13 polynomial, exponent scaling, reciprocal by MUFU seed
 // + two Newton steps); saturates exactly like the naive form for |z| > 708.
+// -z clamped to [-708, 708] on the high word alone (|z| >= 708 <=> (hi & 0x7fffffff) >= 0x40862000: the same values as
+// fmin(fmax(-z, -708), 708), which compiles to two DSETP on the FP64 pipe plus six select / logic instructions per element)
+__device__ __forceinline__ double neg_clamp708(double z) {
+#ifdef QSB_GLM_FPCLAMP      // A/B: the previous form
+  return fmin(fmax(-z, -708.0), 708.0);
+#else
+  const int hi = __double2hiint(z);
+  const bool big = (unsigned)(hi & 0x7fffffff) >= 0x40862000u;
+  const int nhi = hi ^ (int)0x80000000;                                 // high word of -z
+  return __hiloint2double(big ? ((nhi & (int)0x80000000) | 0x40862000) : nhi, big ? 0 : __double2loint(z));
+#endif
+}
 __device__ __forceinline__ double sigmoid_fast(double z) {
-  double t = fmin(fmax(-z, -708.0), 708.0);
+  double t = neg_clamp708(z);
   const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest-integer by addition
   double kd = fma(t, 1.4426950408889634, SHIFT);
   int k = __double2loint(kd);
@@ -149,7 +161,7 @@ __device__ __forceinline__ double sigmoid_fast(double z) {
 struct SigState { double zr, q; int k; };
 template <int STEP> __device__ __forceinline__ void sigmoid_step(SigState& s, double yv) {
   constexpr double SHIFT = 6755399441055744.0;
-  if (STEP == 0) s.zr = fmin(fmax(-s.zr, -708.0), 708.0);
+  if (STEP == 0) s.zr = neg_clamp708(s.zr);
   else if (STEP == 1) s.q = fma(s.zr, 1.4426950408889634, SHIFT);
   else if (STEP == 2) { s.k = __double2loint(s.q); s.q -= SHIFT; }
   else if (STEP == 3) s.zr = fma(s.q, -6.93147180369123816490e-01, s.zr);
@@ -173,6 +185,57 @@ template <int STEP> __device__ __forceinline__ void sigmoid_step(SigState& s, do
   else if (STEP == 21) s.zr = yv - s.zr;
 }
 static constexpr int SIG_STEPS = 22;
+// The gradient-only launches (19 of the 20 evaluations of a trajectory; the log-likelihood is not taken from them) run a
+// lighter form of the same steps: after the round-2 layout changes the kernel is bound by the FP64 datapath the DMMAs and the
+// sigmoid's DFMAs share, so every DFMA moved off it counts.  (i) the terms r^7/7! .. r^13/13! of the exponential series are
+// below 1.2e-7 for |r| <= ln2/2, so their bracket is evaluated in SINGLE precision (6 FFMA on the otherwise idle FP32 pipe;
+// error 1e-14 relative to e^r) and only the seven leading terms in double; (ii) k as a double comes from I2F (XU pipe)
+// instead of a DADD; (iii) the reciprocal takes one Newton step on the 23-bit seed (2^-46) instead of the cubic one.
+// 14 instead of 22 FP64-pipe operations per element; p is accurate to 6e-15 relative (numpy model against 200-bit
+// arithmetic), i.e. the gradient to ~1e-13 -- the parity gates are 1e-9 (gradient) and 1e-10 (positions).  The launches that
+// also produce the log-likelihood keep the 2-ulp form above: 1 - p must match the reference's own rounding there.
+struct SigStateF { double zr, q; float rf, pf; int k; };
+template <int STEP> __device__ __forceinline__ void sigmoid_step_f(SigStateF& s, double yv) {
+  constexpr double SHIFT = 6755399441055744.0;
+  if (STEP == 0) s.zr = neg_clamp708(s.zr);
+  else if (STEP == 1) s.q = fma(s.zr, 1.4426950408889634, SHIFT);
+  else if (STEP == 2) { s.k = __double2loint(s.q); s.q = (double)s.k; }
+  else if (STEP == 3) s.zr = fma(s.q, -6.93147180369123816490e-01, s.zr);
+  else if (STEP == 4) { s.zr = fma(s.q, -1.90821492927058770002e-10, s.zr); s.rf = (float)s.zr; s.pf = 1.6059043836821613e-10f; }
+  else if (STEP == 5) s.pf = fmaf(s.pf, s.rf, 2.08767569878681e-09f);
+  else if (STEP == 6) s.pf = fmaf(s.pf, s.rf, 2.505210838544172e-08f);
+  else if (STEP == 7) s.pf = fmaf(s.pf, s.rf, 2.755731922398589e-07f);
+  else if (STEP == 8) s.pf = fmaf(s.pf, s.rf, 2.7557319223985893e-06f);
+  else if (STEP == 9) s.pf = fmaf(s.pf, s.rf, 2.48015873015873e-05f);
+  else if (STEP == 10) s.pf = fmaf(s.pf, s.rf, 1.984126984126984e-04f);
+  else if (STEP == 11) s.q = (double)s.pf;
+  else if (STEP == 12) s.q = fma(s.q, s.zr, 1.388888888888889e-03);
+  else if (STEP == 13) s.q = fma(s.q, s.zr, 8.333333333333333e-03);
+  else if (STEP == 14) s.q = fma(s.q, s.zr, 4.1666666666666664e-02);
+  else if (STEP == 15) s.q = fma(s.q, s.zr, 1.6666666666666666e-01);
+  else if (STEP == 16) s.q = fma(s.q, s.zr, 0.5);
+  else if (STEP == 17) s.q = fma(s.q, s.zr, 1.0);
+  else if (STEP == 18) s.q = fma(s.q, s.zr, 1.0);
+  else if (STEP == 19) s.q = 1.0 + __hiloint2double(__double2hiint(s.q) + (s.k << 20), __double2loint(s.q));
+  else if (STEP == 20) { asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s.zr) : "d"(s.q)); }
+  else if (STEP == 21) { const double err = fma(-s.q, s.zr, 1.0); s.zr = fma(s.zr, err, s.zr); }   // Newton step
+  else if (STEP == 22) s.zr = yv - s.zr;
+}
+static constexpr int SIG_STEPS_F = 23;
+template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps_f(SigStateF (&st)[4], const double (&yv)[4]) {
+  if constexpr (S0 < S1 && S0 < SIG_STEPS_F) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sigmoid_step_f<S0>(st[i], yv[i]);
+    sigmoid_steps_f<S0 + 1, S1>(st, yv);
+  }
+}
+// Measured (gpurun r02w, same box, alternating): 22.26 / 22.12 against 22.32 / 22.33 ms per transition at 8 192 chains, 3.117
+// against 3.145 at 1 024 (-0.3 .. -0.9 %) -- and the teacher-forced parity of the ADAPTATION TRANSIENT (gradients of order 1e3
+// with heavy cancellation) slips to 2.4e-10 on momenta / 3.8e-10 on the gradient, past the 1e-10 / 1e-9 gates.  Off: the gain
+// does not pay for the margin.  -DQSB_GLM_SIG32=1 builds it.
+#ifndef QSB_GLM_SIG32
+#define QSB_GLM_SIG32 0
+#endif
 template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps(SigState (&st)[4], const double (&yv)[4]) {
   if constexpr (S0 < S1 && S0 < SIG_STEPS) {
 #pragma unroll
@@ -244,15 +307,14 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
   // the ring; afterwards the warp whose release of a stage is the LAST one pending re-arms it with the next row
   // block (TMA bulk copies of whole row blocks: contiguous in HBM because Xp is stored with stride S)
   const uint32_t bytesX = (uint32_t)(MB * P.S * sizeof(double)), bytesY = (uint32_t)(MB * sizeof(double));
-  auto issue_load = [&](int b) {
-    const int st = (b - b0) % NST;
+  auto issue_load = [&](int b, int st) {      // st = (b - b0) % NST, carried by the callers (no runtime division in the loop)
     mbar_expect_tx(&full[st], bytesX + bytesY);
     double* dst = sm + SD * st;
     bulk_g2s(dst, P.Xp + (size_t)b * MB * P.S, bytesX, &full[st]);
     bulk_g2s(dst + (size_t)MB * P.S + 8, P.yv + (size_t)b * MB, bytesY, &full[st]);
   };
   if (threadIdx.x == 0)
-    for (int b = b0; b < b1 && b < b0 + NST; ++b) issue_load(b);
+    for (int b = b0; b < b1 && b < b0 + NST; ++b) issue_load(b, b - b0);
 
   // X and y are model data, not produced by the predecessor kernel: the ring is already filling while we wait for Theta
   if (pdl_pending) { pdl_wait(); pdl_pending = false; }
@@ -365,18 +427,50 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
       for (int J = 0; J < NJ; ++J) if (FULL || J < nj) phase1_tile(sm, J, acc);
     }
   }
+  // ring position of the row block being worked on: stage st = (b - b0) % NST and the parity ph = ((b - b0) / NST) & 1 of its
+  // use, advanced by increment-and-wrap (NST is a run-time value: `%` and `/` by it cost ~55 integer / MUFU instructions per
+  // row block and sat in front of the wait for the next stage)
+  int st = 0; uint32_t ph = 0u;
   for (int b = b0; b < b1; ++b) {
-    const int it = b - b0, st = it % NST;
     const double* Xs = sm + SD * st;
     const double* ys = Xs + (size_t)MB * S + 8;
     const bool has_next = b + 1 < b1;
+    int st2 = st + 1; uint32_t ph2 = ph;
+    if (st2 == NST) { st2 = 0; ph2 ^= 1u; }
+#ifdef QSB_GLM_RINGDIV       // A/B: the previous form
+    { const int it2 = b - b0 + 1; st2 = it2 % NST; ph2 = (uint32_t)((it2 / NST) & 1); }
+#endif
     if (has_next) {
-      const int it2 = it + 1, st2 = it2 % NST;
-      mbar_wait(&full[st2], (uint32_t)((it2 / NST) & 1));
+      mbar_wait(&full[st2], ph2);
       const double* Xn = sm + SD * st2;
 #pragma unroll
       for (int T = 0; T < NT; ++T) nxt[T][0] = nxt[T][1] = 0.0;
-      if constexpr (NT == 4 && NJ >= 12) {
+      if constexpr (NT == 4 && NJ >= 12 && !LP && QSB_GLM_SIG32) {
+        // gradient-only launch: the lighter lock-step sigmoid (SigStateF), same slots
+        SigStateF sa[4], sb[4];
+        double ya[4], yb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          sa[i].zr = acc[i >> 1][i & 1]; sa[i].q = 0.0; sa[i].k = 0; sa[i].rf = 0.f; sa[i].pf = 0.f; ya[i] = ys[(i >> 1) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
+          sb[i].zr = acc[2 + (i >> 1)][i & 1]; sb[i].q = 0.0; sb[i].k = 0; sb[i].rf = 0.f; sb[i].pf = 0.f; yb[i] = ys[(2 + (i >> 1)) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
+        }
+        if (FULL || 0 < nj) phase1_slot(Xn, 0, nxt);  sigmoid_steps_f<0, 4>(sa, ya);
+        if (FULL || 1 < nj) phase1_slot(Xn, 1, nxt);  sigmoid_steps_f<4, 8>(sa, ya);
+        if (FULL || 2 < nj) phase1_slot(Xn, 2, nxt);  sigmoid_steps_f<8, 12>(sa, ya);
+        if (FULL || 3 < nj) phase1_slot(Xn, 3, nxt);  sigmoid_steps_f<12, 16>(sa, ya);
+        if (FULL || 4 < nj) phase1_slot(Xn, 4, nxt);  sigmoid_steps_f<16, 20>(sa, ya);
+        if (FULL || 5 < nj) phase1_slot(Xn, 5, nxt);  sigmoid_steps_f<20, 23>(sa, ya);
+        if (FULL || 6 < nj) phase1_slot(Xn, 6, nxt);  sigmoid_steps_f<0, 4>(sb, yb);
+        if (FULL || 7 < nj) phase1_slot(Xn, 7, nxt);  sigmoid_steps_f<4, 8>(sb, yb);
+        if (FULL || 8 < nj) phase1_slot(Xn, 8, nxt);  sigmoid_steps_f<8, 12>(sb, yb);
+        if (FULL || 9 < nj) phase1_slot(Xn, 9, nxt);  sigmoid_steps_f<12, 16>(sb, yb);
+        if (FULL || 10 < nj) phase1_slot(Xn, 10, nxt); sigmoid_steps_f<16, 20>(sb, yb);
+        if (FULL || 11 < nj) phase1_slot(Xn, 11, nxt); sigmoid_steps_f<20, 23>(sb, yb);
+#pragma unroll
+        for (int J = 12; J < NJ; ++J) if (FULL || J < nj) phase1_tile(Xn, J, nxt);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i >> 1][i & 1] = sa[i].zr; acc[2 + (i >> 1)][i & 1] = sb[i].zr; }
+      } else if constexpr (NT == 4 && NJ >= 12) {
         // lock-step sigmoid: elements (T=0,1) advance 4 steps per dimension tile J = 0..5, elements (T=2,3) during J = 6..11
         SigState sa[4], sb[4];
         double ya[4], yb[4];
@@ -450,12 +544,13 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
     __syncwarp();
     if (lane == 0) {
       if (mbar_arrive_last(&empty[st])) {           // every warp is done with this stage: refill it
-        mbar_wait(&empty[st], (uint32_t)((it / NST) & 1));   // acquire the other warps' releases (already complete)
-        if (b + NST < b1) issue_load(b + NST);
+        mbar_wait(&empty[st], ph);                  // acquire the other warps' releases (already complete)
+        if (b + NST < b1) issue_load(b + NST, st);
       }
     }
 #pragma unroll
     for (int T = 0; T < NT; ++T) { acc[T][0] = nxt[T][0]; acc[T][1] = nxt[T][1]; }
+    st = st2; ph = ph2;
   }
 
   if (valid && P.want_grad) {
