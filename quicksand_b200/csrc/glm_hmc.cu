@@ -42,8 +42,55 @@ namespace qsb {
 
 static constexpr int MB = 32;          // observation rows per pipeline stage
 static constexpr int NT = MB / 8;      // 8-row n-tiles per stage
-static constexpr int BAR_DOUBLES = 2 * 4 + 2;   // behind the ring: full[STAGES], empty[STAGES] mbarriers and the stream-K cursor
+static constexpr int TAB_OFF = 2 * 4 + 2;       // behind the ring: full[STAGES], empty[STAGES] mbarriers and the stream-K cursor ...
 static constexpr int STAGES = 4;        // deepest ring; a sampler uses 2..4 stages (GradParams::stages), whatever fits 227 KB
+static constexpr int TAB_N = 256;                // entries of the table 2^(j/256) of the sigmoid's exponential (2 KB) ...
+static constexpr int BAR_DOUBLES = TAB_OFF + TAB_N;   // ... which sits behind them
+// 2^(j/256), j = 0..255, correctly rounded (generated with 200-bit arithmetic)
+__constant__ double c_exp2_tab[TAB_N] = {
+    0x1.0000000000000p+0, 0x1.00b1afa5abcbfp+0, 0x1.0163da9fb3335p+0, 0x1.02168143b0281p+0, 0x1.02c9a3e778061p+0, 0x1.037d42e11bbccp+0,
+    0x1.04315e86e7f85p+0, 0x1.04e5f72f654b1p+0, 0x1.059b0d3158574p+0, 0x1.0650a0e3c1f89p+0, 0x1.0706b29ddf6dep+0, 0x1.07bd42b72a836p+0,
+    0x1.0874518759bc8p+0, 0x1.092bdf66607e0p+0, 0x1.09e3ecac6f383p+0, 0x1.0a9c79b1f3919p+0, 0x1.0b5586cf9890fp+0, 0x1.0c0f145e46c85p+0,
+    0x1.0cc922b7247f7p+0, 0x1.0d83b23395decp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.0efa55fdfa9c5p+0, 0x1.0fb66affed31bp+0, 0x1.1073028d7233ep+0,
+    0x1.11301d0125b51p+0, 0x1.11edbab5e2ab6p+0, 0x1.12abdc06c31ccp+0, 0x1.136a814f204abp+0, 0x1.1429aaea92de0p+0, 0x1.14e95934f312ep+0,
+    0x1.15a98c8a58e51p+0, 0x1.166a45471c3c2p+0, 0x1.172b83c7d517bp+0, 0x1.17ed48695bbc0p+0, 0x1.18af9388c8deap+0, 0x1.1972658375d2fp+0,
+    0x1.1a35beb6fcb75p+0, 0x1.1af99f8138a1cp+0, 0x1.1bbe084045cd4p+0, 0x1.1c82f95281c6bp+0, 0x1.1d4873168b9aap+0, 0x1.1e0e75eb44027p+0,
+    0x1.1ed5022fcd91dp+0, 0x1.1f9c18438ce4dp+0, 0x1.2063b88628cd6p+0, 0x1.212be3578a819p+0, 0x1.21f49917ddc96p+0, 0x1.22bdda27912d1p+0,
+    0x1.2387a6e756238p+0, 0x1.2451ffb82140ap+0, 0x1.251ce4fb2a63fp+0, 0x1.25e85711ece75p+0, 0x1.26b4565e27cddp+0, 0x1.2780e341ddf29p+0,
+    0x1.284dfe1f56381p+0, 0x1.291ba7591bb70p+0, 0x1.29e9df51fdee1p+0, 0x1.2ab8a66d10f13p+0, 0x1.2b87fd0dad990p+0, 0x1.2c57e39771b2fp+0,
+    0x1.2d285a6e4030bp+0, 0x1.2df961f641589p+0, 0x1.2ecafa93e2f56p+0, 0x1.2f9d24abd886bp+0, 0x1.306fe0a31b715p+0, 0x1.31432edeeb2fdp+0,
+    0x1.32170fc4cd831p+0, 0x1.32eb83ba8ea32p+0, 0x1.33c08b26416ffp+0, 0x1.3496266e3fa2dp+0, 0x1.356c55f929ff1p+0, 0x1.36431a2de883bp+0,
+    0x1.371a7373aa9cbp+0, 0x1.37f26231e754ap+0, 0x1.38cae6d05d866p+0, 0x1.39a401b7140efp+0, 0x1.3a7db34e59ff7p+0, 0x1.3b57fbfec6cf4p+0,
+    0x1.3c32dc313a8e5p+0, 0x1.3d0e544ede173p+0, 0x1.3dea64c123422p+0, 0x1.3ec70df1c5175p+0, 0x1.3fa4504ac801cp+0, 0x1.40822c367a024p+0,
+    0x1.4160a21f72e2ap+0, 0x1.423fb2709468ap+0, 0x1.431f5d950a897p+0, 0x1.43ffa3f84b9d4p+0, 0x1.44e086061892dp+0, 0x1.45c2042a7d232p+0,
+    0x1.46a41ed1d0057p+0, 0x1.4786d668b3237p+0, 0x1.486a2b5c13cd0p+0, 0x1.494e1e192aed2p+0, 0x1.4a32af0d7d3dep+0, 0x1.4b17dea6db7d7p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4ce41b817c114p+0, 0x1.4dcb299fddd0dp+0, 0x1.4eb2d81d8abffp+0, 0x1.4f9b2769d2ca7p+0, 0x1.508417f4531eep+0,
+    0x1.516daa2cf6642p+0, 0x1.5257de83f4eefp+0, 0x1.5342b569d4f82p+0, 0x1.542e2f4f6ad27p+0, 0x1.551a4ca5d920fp+0, 0x1.56070dde910d2p+0,
+    0x1.56f4736b527dap+0, 0x1.57e27dbe2c4cfp+0, 0x1.58d12d497c7fdp+0, 0x1.59c0827ff07ccp+0, 0x1.5ab07dd485429p+0, 0x1.5ba11fba87a03p+0,
+    0x1.5c9268a5946b7p+0, 0x1.5d84590998b93p+0, 0x1.5e76f15ad2148p+0, 0x1.5f6a320dceb71p+0, 0x1.605e1b976dc09p+0, 0x1.6152ae6cdf6f4p+0,
+    0x1.6247eb03a5585p+0, 0x1.633dd1d1929fdp+0, 0x1.6434634ccc320p+0, 0x1.652b9febc8fb7p+0, 0x1.6623882552225p+0, 0x1.671c1c70833f6p+0,
+    0x1.68155d44ca973p+0, 0x1.690f4b19e9538p+0, 0x1.6a09e667f3bcdp+0, 0x1.6b052fa75173ep+0, 0x1.6c012750bdabfp+0, 0x1.6cfdcddd47645p+0,
+    0x1.6dfb23c651a2fp+0, 0x1.6ef9298593ae5p+0, 0x1.6ff7df9519484p+0, 0x1.70f7466f42e87p+0, 0x1.71f75e8ec5f74p+0, 0x1.72f8286ead08ap+0,
+    0x1.73f9a48a58174p+0, 0x1.74fbd35d7cbfdp+0, 0x1.75feb564267c9p+0, 0x1.77024b1ab6e09p+0, 0x1.780694fde5d3fp+0, 0x1.790b938ac1cf6p+0,
+    0x1.7a11473eb0187p+0, 0x1.7b17b0976cfdbp+0, 0x1.7c1ed0130c132p+0, 0x1.7d26a62ff86f0p+0, 0x1.7e2f336cf4e62p+0, 0x1.7f3878491c491p+0,
+    0x1.80427543e1a12p+0, 0x1.814d2add106d9p+0, 0x1.82589994cce13p+0, 0x1.8364c1eb941f7p+0, 0x1.8471a4623c7adp+0, 0x1.857f4179f5b21p+0,
+    0x1.868d99b4492edp+0, 0x1.879cad931a436p+0, 0x1.88ac7d98a6699p+0, 0x1.89bd0a478580fp+0, 0x1.8ace5422aa0dbp+0, 0x1.8be05bad61778p+0,
+    0x1.8cf3216b5448cp+0, 0x1.8e06a5e0866d9p+0, 0x1.8f1ae99157736p+0, 0x1.902fed0282c8ap+0, 0x1.9145b0b91ffc6p+0, 0x1.925c353aa2fe2p+0,
+    0x1.93737b0cdc5e5p+0, 0x1.948b82b5f98e5p+0, 0x1.95a44cbc8520fp+0, 0x1.96bdd9a7670b3p+0, 0x1.97d829fde4e50p+0, 0x1.98f33e47a22a2p+0,
+    0x1.9a0f170ca07bap+0, 0x1.9b2bb4d53fe0dp+0, 0x1.9c49182a3f090p+0, 0x1.9d674194bb8d5p+0, 0x1.9e86319e32323p+0, 0x1.9fa5e8d07f29ep+0,
+    0x1.a0c667b5de565p+0, 0x1.a1e7aed8eb8bbp+0, 0x1.a309bec4a2d33p+0, 0x1.a42c980460ad8p+0, 0x1.a5503b23e255dp+0, 0x1.a674a8af46052p+0,
+    0x1.a799e1330b358p+0, 0x1.a8bfe53c12e59p+0, 0x1.a9e6b5579fdbfp+0, 0x1.ab0e521356ebap+0, 0x1.ac36bbfd3f37ap+0, 0x1.ad5ff3a3c2774p+0,
+    0x1.ae89f995ad3adp+0, 0x1.afb4ce622f2ffp+0, 0x1.b0e07298db666p+0, 0x1.b20ce6c9a8952p+0, 0x1.b33a2b84f15fbp+0, 0x1.b468415b749b1p+0,
+    0x1.b59728de5593ap+0, 0x1.b6c6e29f1c52ap+0, 0x1.b7f76f2fb5e47p+0, 0x1.b928cf22749e4p+0, 0x1.ba5b030a1064ap+0, 0x1.bb8e0b79a6f1fp+0,
+    0x1.bcc1e904bc1d2p+0, 0x1.bdf69c3f3a207p+0, 0x1.bf2c25bd71e09p+0, 0x1.c06286141b33dp+0, 0x1.c199bdd85529cp+0, 0x1.c2d1cd9fa652cp+0,
+    0x1.c40ab5fffd07ap+0, 0x1.c544778fafb22p+0, 0x1.c67f12e57d14bp+0, 0x1.c7ba88988c933p+0, 0x1.c8f6d9406e7b5p+0, 0x1.ca3405751c4dbp+0,
+    0x1.cb720dcef9069p+0, 0x1.ccb0f2e6d1675p+0, 0x1.cdf0b555dc3fap+0, 0x1.cf3155b5bab74p+0, 0x1.d072d4a07897cp+0, 0x1.d1b532b08c968p+0,
+    0x1.d2f87080d89f2p+0, 0x1.d43c8eacaa1d6p+0, 0x1.d5818dcfba487p+0, 0x1.d6c76e862e6d3p+0, 0x1.d80e316c98398p+0, 0x1.d955d71ff6075p+0,
+    0x1.da9e603db3285p+0, 0x1.dbe7cd63a8315p+0, 0x1.dd321f301b460p+0, 0x1.de7d5641c0658p+0, 0x1.dfc97337b9b5fp+0, 0x1.e11676b197d17p+0,
+    0x1.e264614f5a129p+0, 0x1.e3b333b16ee12p+0, 0x1.e502ee78b3ff6p+0, 0x1.e653924676d76p+0, 0x1.e7a51fbc74c83p+0, 0x1.e8f7977cdb740p+0,
+    0x1.ea4afa2a490dap+0, 0x1.eb9f4867cca6ep+0, 0x1.ecf482d8e67f1p+0, 0x1.ee4aaa2188510p+0, 0x1.efa1bee615a27p+0, 0x1.f0f9c1cb6412ap+0,
+    0x1.f252b376bba97p+0, 0x1.f3ac948dd7274p+0, 0x1.f50765b6e4540p+0, 0x1.f6632798844f8p+0, 0x1.f7bfdad9cbe14p+0, 0x1.f91d802243c89p+0,
+    0x1.fa7c1819e90d8p+0, 0x1.fbdba3692d514p+0, 0x1.fd3c22b8f71f1p+0, 0x1.fe9d96b2a23d9p+0};
 #ifndef QSB_GLM_CW
 #define QSB_GLM_CW 12
 #endif
@@ -122,29 +169,25 @@ __device__ __forceinline__ double neg_clamp708(double z) {
   return __hiloint2double(big ? ((nhi & (int)0x80000000) | 0x40862000) : nhi, big ? 0 : __double2loint(z));
 #endif
 }
-__device__ __forceinline__ double sigmoid_fast(double z) {
+// exp(t) = 2^k 2^(j/256) e^r with n = 256 k + j = round(256 t / ln 2) and |r| <= ln2/512: a degree-4 series (truncation
+// r^5/120 < 4e-17) and one table value from shared memory replace the degree-13 series on |r| <= ln2/2 -- 9 instead of 17
+// FP64-datapath operations up to e^t (the kernel is bound by the datapath the DMMAs and these DFMAs share), ~1.5 ulp on p as
+// before (numpy model against 200-bit arithmetic).  n as a double comes from I2F (XU pipe) instead of subtracting the
+// rounding shift again.  Measured: profiles/README.md (r02x, r02y).
+__device__ __forceinline__ double sigmoid_fast(double z, const double* tab) {
   double t = neg_clamp708(z);
   const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52: round-to-nearest-integer by addition
-  double kd = fma(t, 1.4426950408889634, SHIFT);
-  int k = __double2loint(kd);
-  kd -= SHIFT;
-  double r = fma(kd, -6.93147180369123816490e-01, t);
-  r = fma(kd, -1.90821492927058770002e-10, r);
-  double q = 1.6059043836821613e-10;           // 1/13!
-  q = fma(q, r, 2.08767569878681e-09);         // 1/12!
-  q = fma(q, r, 2.505210838544172e-08);        // 1/11!
-  q = fma(q, r, 2.755731922398589e-07);        // 1/10!
-  q = fma(q, r, 2.7557319223985893e-06);       // 1/9!
-  q = fma(q, r, 2.48015873015873e-05);         // 1/8!
-  q = fma(q, r, 1.984126984126984e-04);        // 1/7!
-  q = fma(q, r, 1.388888888888889e-03);        // 1/6!
-  q = fma(q, r, 8.333333333333333e-03);        // 1/5!
-  q = fma(q, r, 4.1666666666666664e-02);       // 1/4!
+  const int n = __double2loint(fma(t, 369.3299304675746, SHIFT));
+  const double nd = (double)n;
+  double r = fma(nd, -0x1.62e42fee00000p-9, t);
+  r = fma(nd, -7.453964567463233e-13, r);
+  double q = 4.1666666666666664e-02;           // 1/4!
   q = fma(q, r, 1.6666666666666666e-01);       // 1/3!
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
-  double e = __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));   // q * 2^k, result stays normal
+  q = q * tab[n & (TAB_N - 1)];
+  double e = __hiloint2double(__double2hiint(q) + ((n >> 8) << 20), __double2loint(q));   // q * 2^k, result stays normal
   double d = 1.0 + e;
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
@@ -154,93 +197,35 @@ __device__ __forceinline__ double sigmoid_fast(double z) {
   return y;
 }
 
-// The same computation cut into 22 single-latency steps on a (zr, q, k) state, so that the steps of several
+// The same computation cut into 14 single-latency steps on a (zr, q, k) state, so that the steps of several
 // elements can be issued round-robin between the tensor-core instructions of the next row block: no step waits on
-// its predecessor and the MMA stream of the warp never stalls behind a 25-deep dependent DFMA chain
+// its predecessor and the MMA stream of the warp never stalls behind a long dependent DFMA chain
 // (ncu profiles/r01_c3_grad_v2: stall_wait 33 % of samples before this change).
 struct SigState { double zr, q; int k; };
-template <int STEP> __device__ __forceinline__ void sigmoid_step(SigState& s, double yv) {
+template <int STEP> __device__ __forceinline__ void sigmoid_step(SigState& s, double yv, const double* tab) {
   constexpr double SHIFT = 6755399441055744.0;
+  static_assert(TAB_N == 256, "the constants below are for 256 table entries");
   if (STEP == 0) s.zr = neg_clamp708(s.zr);
-  else if (STEP == 1) s.q = fma(s.zr, 1.4426950408889634, SHIFT);
-  else if (STEP == 2) { s.k = __double2loint(s.q); s.q -= SHIFT; }
-  else if (STEP == 3) s.zr = fma(s.q, -6.93147180369123816490e-01, s.zr);
-  else if (STEP == 4) { s.zr = fma(s.q, -1.90821492927058770002e-10, s.zr); s.q = 1.6059043836821613e-10; }
-  else if (STEP == 5) s.q = fma(s.q, s.zr, 2.08767569878681e-09);
-  else if (STEP == 6) s.q = fma(s.q, s.zr, 2.505210838544172e-08);
-  else if (STEP == 7) s.q = fma(s.q, s.zr, 2.755731922398589e-07);
-  else if (STEP == 8) s.q = fma(s.q, s.zr, 2.7557319223985893e-06);
-  else if (STEP == 9) s.q = fma(s.q, s.zr, 2.48015873015873e-05);
-  else if (STEP == 10) s.q = fma(s.q, s.zr, 1.984126984126984e-04);
-  else if (STEP == 11) s.q = fma(s.q, s.zr, 1.388888888888889e-03);
-  else if (STEP == 12) s.q = fma(s.q, s.zr, 8.333333333333333e-03);
-  else if (STEP == 13) s.q = fma(s.q, s.zr, 4.1666666666666664e-02);
-  else if (STEP == 14) s.q = fma(s.q, s.zr, 1.6666666666666666e-01);
-  else if (STEP == 15) s.q = fma(s.q, s.zr, 0.5);
-  else if (STEP == 16) s.q = fma(s.q, s.zr, 1.0);
-  else if (STEP == 17) s.q = fma(s.q, s.zr, 1.0);
-  else if (STEP == 18) s.q = 1.0 + __hiloint2double(__double2hiint(s.q) + (s.k << 20), __double2loint(s.q));
-  else if (STEP == 19) { asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s.zr) : "d"(s.q)); }
-  else if (STEP == 20) { double err = fma(-s.q, s.zr, 1.0); err = fma(err, err, err); s.zr = fma(s.zr, err, s.zr); }   // cubic step
-  else if (STEP == 21) s.zr = yv - s.zr;
-}
-static constexpr int SIG_STEPS = 22;
-// The gradient-only launches (19 of the 20 evaluations of a trajectory; the log-likelihood is not taken from them) run a
-// lighter form of the same steps: after the round-2 layout changes the kernel is bound by the FP64 datapath the DMMAs and the
-// sigmoid's DFMAs share, so every DFMA moved off it counts.  (i) the terms r^7/7! .. r^13/13! of the exponential series are
-// below 1.2e-7 for |r| <= ln2/2, so their bracket is evaluated in SINGLE precision (6 FFMA on the otherwise idle FP32 pipe;
-// error 1e-14 relative to e^r) and only the seven leading terms in double; (ii) k as a double comes from I2F (XU pipe)
-// instead of a DADD; (iii) the reciprocal takes one Newton step on the 23-bit seed (2^-46) instead of the cubic one.
-// 14 instead of 22 FP64-pipe operations per element; p is accurate to 6e-15 relative (numpy model against 200-bit
-// arithmetic), i.e. the gradient to ~1e-13 -- the parity gates are 1e-9 (gradient) and 1e-10 (positions).  The launches that
-// also produce the log-likelihood keep the 2-ulp form above: 1 - p must match the reference's own rounding there.
-struct SigStateF { double zr, q; float rf, pf; int k; };
-template <int STEP> __device__ __forceinline__ void sigmoid_step_f(SigStateF& s, double yv) {
-  constexpr double SHIFT = 6755399441055744.0;
-  if (STEP == 0) s.zr = neg_clamp708(s.zr);
-  else if (STEP == 1) s.q = fma(s.zr, 1.4426950408889634, SHIFT);
+  else if (STEP == 1) s.q = fma(s.zr, 369.3299304675746, SHIFT);
   else if (STEP == 2) { s.k = __double2loint(s.q); s.q = (double)s.k; }
-  else if (STEP == 3) s.zr = fma(s.q, -6.93147180369123816490e-01, s.zr);
-  else if (STEP == 4) { s.zr = fma(s.q, -1.90821492927058770002e-10, s.zr); s.rf = (float)s.zr; s.pf = 1.6059043836821613e-10f; }
-  else if (STEP == 5) s.pf = fmaf(s.pf, s.rf, 2.08767569878681e-09f);
-  else if (STEP == 6) s.pf = fmaf(s.pf, s.rf, 2.505210838544172e-08f);
-  else if (STEP == 7) s.pf = fmaf(s.pf, s.rf, 2.755731922398589e-07f);
-  else if (STEP == 8) s.pf = fmaf(s.pf, s.rf, 2.7557319223985893e-06f);
-  else if (STEP == 9) s.pf = fmaf(s.pf, s.rf, 2.48015873015873e-05f);
-  else if (STEP == 10) s.pf = fmaf(s.pf, s.rf, 1.984126984126984e-04f);
-  else if (STEP == 11) s.q = (double)s.pf;
-  else if (STEP == 12) s.q = fma(s.q, s.zr, 1.388888888888889e-03);
-  else if (STEP == 13) s.q = fma(s.q, s.zr, 8.333333333333333e-03);
-  else if (STEP == 14) s.q = fma(s.q, s.zr, 4.1666666666666664e-02);
-  else if (STEP == 15) s.q = fma(s.q, s.zr, 1.6666666666666666e-01);
-  else if (STEP == 16) s.q = fma(s.q, s.zr, 0.5);
-  else if (STEP == 17) s.q = fma(s.q, s.zr, 1.0);
-  else if (STEP == 18) s.q = fma(s.q, s.zr, 1.0);
-  else if (STEP == 19) s.q = 1.0 + __hiloint2double(__double2hiint(s.q) + (s.k << 20), __double2loint(s.q));
-  else if (STEP == 20) { asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s.zr) : "d"(s.q)); }
-  else if (STEP == 21) { const double err = fma(-s.q, s.zr, 1.0); s.zr = fma(s.zr, err, s.zr); }   // Newton step
-  else if (STEP == 22) s.zr = yv - s.zr;
+  else if (STEP == 3) s.zr = fma(s.q, -0x1.62e42fee00000p-9, s.zr);
+  else if (STEP == 4) { s.zr = fma(s.q, -7.453964567463233e-13, s.zr); s.q = 4.1666666666666664e-02; }
+  else if (STEP == 5) s.q = fma(s.q, s.zr, 1.6666666666666666e-01);
+  else if (STEP == 6) s.q = fma(s.q, s.zr, 0.5);
+  else if (STEP == 7) s.q = fma(s.q, s.zr, 1.0);
+  else if (STEP == 8) s.q = fma(s.q, s.zr, 1.0);
+  else if (STEP == 9) s.q = s.q * tab[s.k & (TAB_N - 1)];
+  else if (STEP == 10) s.q = 1.0 + __hiloint2double(__double2hiint(s.q) + ((s.k >> 8) << 20), __double2loint(s.q));
+  else if (STEP == 11) { asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s.zr) : "d"(s.q)); }
+  else if (STEP == 12) { double err = fma(-s.q, s.zr, 1.0); err = fma(err, err, err); s.zr = fma(s.zr, err, s.zr); }   // cubic step
+  else if (STEP == 13) s.zr = yv - s.zr;
 }
-static constexpr int SIG_STEPS_F = 23;
-template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps_f(SigStateF (&st)[4], const double (&yv)[4]) {
-  if constexpr (S0 < S1 && S0 < SIG_STEPS_F) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sigmoid_step_f<S0>(st[i], yv[i]);
-    sigmoid_steps_f<S0 + 1, S1>(st, yv);
-  }
-}
-// Measured (gpurun r02w, same box, alternating): 22.26 / 22.12 against 22.32 / 22.33 ms per transition at 8 192 chains, 3.117
-// against 3.145 at 1 024 (-0.3 .. -0.9 %) -- and the teacher-forced parity of the ADAPTATION TRANSIENT (gradients of order 1e3
-// with heavy cancellation) slips to 2.4e-10 on momenta / 3.8e-10 on the gradient, past the 1e-10 / 1e-9 gates.  Off: the gain
-// does not pay for the margin.  -DQSB_GLM_SIG32=1 builds it.
-#ifndef QSB_GLM_SIG32
-#define QSB_GLM_SIG32 0
-#endif
-template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps(SigState (&st)[4], const double (&yv)[4]) {
+static constexpr int SIG_STEPS = 14;
+template <int S0, int S1> __device__ __forceinline__ void sigmoid_steps(SigState (&st)[4], const double (&yv)[4], const double* tab) {
   if constexpr (S0 < S1 && S0 < SIG_STEPS) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sigmoid_step<S0>(st[i], yv[i]);
-    sigmoid_steps<S0 + 1, S1>(st, yv);
+    for (int i = 0; i < 4; ++i) sigmoid_step<S0>(st[i], yv[i], tab);
+    sigmoid_steps<S0 + 1, S1>(st, yv, tab);
   }
 }
 
@@ -291,6 +276,7 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
     mbar_fence_init();
   }
   if ((int)threadIdx.x < NST * 8) sm[SD * (threadIdx.x >> 3) + (size_t)MB * P.S + (threadIdx.x & 7)] = 0.0;   // over-read pads
+  for (int j = threadIdx.x; j < TAB_N; j += GRAD_THREADS) sm[SD * NST + TAB_OFF + j] = c_exp2_tab[j];   // 2^(j/256) for the sigmoid
   if (THETA_SMEM) {   // the chain tile's Theta, [CB][theta_stride]; rows of chains past the end are zero
     if (pdl_pending) { pdl_wait(); pdl_pending = false; }
     double* sT = sm + SD * NST + BAR_DOUBLES;
@@ -321,6 +307,7 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
   if (warp < nvw) {
   // ---- consumers: warp w owns chains tile*CB + 8w .. +7; thread (gid, tig) owns dims 8J+2tig+{0,1} of chain gid
   const int gid = lane >> 2, tig = lane & 3;
+  const double* tab = sm + SD * NST + TAB_OFF;
   const uint32_t chain = (uint32_t)tile * CB + warp * 8 + gid;
   const bool valid = chain < P.C;
   const int S = P.S;
@@ -410,7 +397,7 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
       if (y <= 1.0) lik_factor(y != 0.0 ? pr : 1.0 - pr);
       acc[T][e] = y - pr;
     } else {
-      acc[T][e] = y - sigmoid_fast(acc[T][e]);
+      acc[T][e] = y - sigmoid_fast(acc[T][e], tab);
     }
   };
 
@@ -445,32 +432,7 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
       const double* Xn = sm + SD * st2;
 #pragma unroll
       for (int T = 0; T < NT; ++T) nxt[T][0] = nxt[T][1] = 0.0;
-      if constexpr (NT == 4 && NJ >= 12 && !LP && QSB_GLM_SIG32) {
-        // gradient-only launch: the lighter lock-step sigmoid (SigStateF), same slots
-        SigStateF sa[4], sb[4];
-        double ya[4], yb[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          sa[i].zr = acc[i >> 1][i & 1]; sa[i].q = 0.0; sa[i].k = 0; sa[i].rf = 0.f; sa[i].pf = 0.f; ya[i] = ys[(i >> 1) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
-          sb[i].zr = acc[2 + (i >> 1)][i & 1]; sb[i].q = 0.0; sb[i].k = 0; sb[i].rf = 0.f; sb[i].pf = 0.f; yb[i] = ys[(2 + (i >> 1)) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
-        }
-        if (FULL || 0 < nj) phase1_slot(Xn, 0, nxt);  sigmoid_steps_f<0, 4>(sa, ya);
-        if (FULL || 1 < nj) phase1_slot(Xn, 1, nxt);  sigmoid_steps_f<4, 8>(sa, ya);
-        if (FULL || 2 < nj) phase1_slot(Xn, 2, nxt);  sigmoid_steps_f<8, 12>(sa, ya);
-        if (FULL || 3 < nj) phase1_slot(Xn, 3, nxt);  sigmoid_steps_f<12, 16>(sa, ya);
-        if (FULL || 4 < nj) phase1_slot(Xn, 4, nxt);  sigmoid_steps_f<16, 20>(sa, ya);
-        if (FULL || 5 < nj) phase1_slot(Xn, 5, nxt);  sigmoid_steps_f<20, 23>(sa, ya);
-        if (FULL || 6 < nj) phase1_slot(Xn, 6, nxt);  sigmoid_steps_f<0, 4>(sb, yb);
-        if (FULL || 7 < nj) phase1_slot(Xn, 7, nxt);  sigmoid_steps_f<4, 8>(sb, yb);
-        if (FULL || 8 < nj) phase1_slot(Xn, 8, nxt);  sigmoid_steps_f<8, 12>(sb, yb);
-        if (FULL || 9 < nj) phase1_slot(Xn, 9, nxt);  sigmoid_steps_f<12, 16>(sb, yb);
-        if (FULL || 10 < nj) phase1_slot(Xn, 10, nxt); sigmoid_steps_f<16, 20>(sb, yb);
-        if (FULL || 11 < nj) phase1_slot(Xn, 11, nxt); sigmoid_steps_f<20, 23>(sb, yb);
-#pragma unroll
-        for (int J = 12; J < NJ; ++J) if (FULL || J < nj) phase1_tile(Xn, J, nxt);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i >> 1][i & 1] = sa[i].zr; acc[2 + (i >> 1)][i & 1] = sb[i].zr; }
-      } else if constexpr (NT == 4 && NJ >= 12) {
+      if constexpr (NT == 4 && NJ >= 12) {
         // lock-step sigmoid: elements (T=0,1) advance 4 steps per dimension tile J = 0..5, elements (T=2,3) during J = 6..11
         SigState sa[4], sb[4];
         double ya[4], yb[4];
@@ -479,18 +441,18 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
           sa[i].zr = acc[i >> 1][i & 1]; sa[i].q = 0.0; sa[i].k = 0; ya[i] = ys[(i >> 1) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
           sb[i].zr = acc[2 + (i >> 1)][i & 1]; sb[i].q = 0.0; sb[i].k = 0; yb[i] = ys[(2 + (i >> 1)) * 8 + ((i & 1) ? rho_t1 : rho_t0)];
         }
-        if (FULL || 0 < nj) phase1_slot(Xn, 0, nxt);  sigmoid_steps<0, 4>(sa, ya);
-        if (FULL || 1 < nj) phase1_slot(Xn, 1, nxt);  sigmoid_steps<4, 8>(sa, ya);
-        if (FULL || 2 < nj) phase1_slot(Xn, 2, nxt);  sigmoid_steps<8, 12>(sa, ya);
-        if (FULL || 3 < nj) phase1_slot(Xn, 3, nxt);  sigmoid_steps<12, 16>(sa, ya);
-        if (FULL || 4 < nj) phase1_slot(Xn, 4, nxt);  sigmoid_steps<16, 20>(sa, ya);
-        if (FULL || 5 < nj) phase1_slot(Xn, 5, nxt);  sigmoid_steps<20, 22>(sa, ya);
-        if (FULL || 6 < nj) phase1_slot(Xn, 6, nxt);  sigmoid_steps<0, 4>(sb, yb);
-        if (FULL || 7 < nj) phase1_slot(Xn, 7, nxt);  sigmoid_steps<4, 8>(sb, yb);
-        if (FULL || 8 < nj) phase1_slot(Xn, 8, nxt);  sigmoid_steps<8, 12>(sb, yb);
-        if (FULL || 9 < nj) phase1_slot(Xn, 9, nxt);  sigmoid_steps<12, 16>(sb, yb);
-        if (FULL || 10 < nj) phase1_slot(Xn, 10, nxt); sigmoid_steps<16, 20>(sb, yb);
-        if (FULL || 11 < nj) phase1_slot(Xn, 11, nxt); sigmoid_steps<20, 22>(sb, yb);
+        if (FULL || 0 < nj) phase1_slot(Xn, 0, nxt);  sigmoid_steps<0, 3>(sa, ya, tab);
+        if (FULL || 1 < nj) phase1_slot(Xn, 1, nxt);  sigmoid_steps<3, 5>(sa, ya, tab);
+        if (FULL || 2 < nj) phase1_slot(Xn, 2, nxt);  sigmoid_steps<5, 7>(sa, ya, tab);
+        if (FULL || 3 < nj) phase1_slot(Xn, 3, nxt);  sigmoid_steps<7, 10>(sa, ya, tab);
+        if (FULL || 4 < nj) phase1_slot(Xn, 4, nxt);  sigmoid_steps<10, 12>(sa, ya, tab);
+        if (FULL || 5 < nj) phase1_slot(Xn, 5, nxt);  sigmoid_steps<12, 14>(sa, ya, tab);
+        if (FULL || 6 < nj) phase1_slot(Xn, 6, nxt);  sigmoid_steps<0, 3>(sb, yb, tab);
+        if (FULL || 7 < nj) phase1_slot(Xn, 7, nxt);  sigmoid_steps<3, 5>(sb, yb, tab);
+        if (FULL || 8 < nj) phase1_slot(Xn, 8, nxt);  sigmoid_steps<5, 7>(sb, yb, tab);
+        if (FULL || 9 < nj) phase1_slot(Xn, 9, nxt);  sigmoid_steps<7, 10>(sb, yb, tab);
+        if (FULL || 10 < nj) phase1_slot(Xn, 10, nxt); sigmoid_steps<10, 12>(sb, yb, tab);
+        if (FULL || 11 < nj) phase1_slot(Xn, 11, nxt); sigmoid_steps<12, 14>(sb, yb, tab);
 #pragma unroll
         for (int J = 12; J < NJ; ++J) if (FULL || J < nj) phase1_tile(Xn, J, nxt);
 #pragma unroll
