@@ -170,8 +170,8 @@ __device__ __forceinline__ double neg_clamp708(double z) {
 #endif
 }
 // exp(t) = 2^k 2^(j/256) e^r with n = 256 k + j = round(256 t / ln 2) and |r| <= ln2/512: a degree-4 series (truncation
-// r^5/120 < 4e-17) and one table value from shared memory replace the degree-13 series on |r| <= ln2/2 -- 9 instead of 17
-// FP64-datapath operations up to e^t (the kernel is bound by the datapath the DMMAs and these DFMAs share), ~1.5 ulp on p as
+// r^5/120 < 4e-17) and one table value from shared memory replace the degree-13 series on |r| <= ln2/2 -- 8 instead of 17
+// FP64-datapath operations up to 1 + e^t (the kernel is bound by the datapath the DMMAs and these DFMAs share), ~1.5 ulp on p as
 // before (numpy model against 200-bit arithmetic).  n as a double comes from I2F (XU pipe) instead of subtracting the
 // rounding shift again.  Measured: profiles/README.md (r02x, r02y).
 __device__ __forceinline__ double sigmoid_fast(double z, const double* tab) {
@@ -186,9 +186,9 @@ __device__ __forceinline__ double sigmoid_fast(double z, const double* tab) {
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
-  q = q * tab[n & (TAB_N - 1)];
-  double e = __hiloint2double(__double2hiint(q) + ((n >> 8) << 20), __double2loint(q));   // q * 2^k, result stays normal
-  double d = 1.0 + e;
+  const double tj = tab[n & (TAB_N - 1)];
+  const double ts = __hiloint2double(__double2hiint(tj) + ((n >> 8) << 20), __double2loint(tj));   // 2^k 2^(j/256): stays normal (|k| <= 1022)
+  double d = fma(q, ts, 1.0);                  // 1 + e^t in one rounding
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   double err = fma(-d, y, 1.0);          // one cubic step: y (1 + e + e^2), 3 x the seed's ~23 bits
@@ -214,8 +214,8 @@ template <int STEP> __device__ __forceinline__ void sigmoid_step(SigState& s, do
   else if (STEP == 6) s.q = fma(s.q, s.zr, 0.5);
   else if (STEP == 7) s.q = fma(s.q, s.zr, 1.0);
   else if (STEP == 8) s.q = fma(s.q, s.zr, 1.0);
-  else if (STEP == 9) s.q = s.q * tab[s.k & (TAB_N - 1)];
-  else if (STEP == 10) s.q = 1.0 + __hiloint2double(__double2hiint(s.q) + ((s.k >> 8) << 20), __double2loint(s.q));
+  else if (STEP == 9) s.zr = tab[s.k & (TAB_N - 1)];                    // (zr is free from here to the reciprocal)
+  else if (STEP == 10) s.q = fma(s.q, __hiloint2double(__double2hiint(s.zr) + ((s.k >> 8) << 20), __double2loint(s.zr)), 1.0);
   else if (STEP == 11) { asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s.zr) : "d"(s.q)); }
   else if (STEP == 12) { double err = fma(-s.q, s.zr, 1.0); err = fma(err, err, err); s.zr = fma(s.zr, err, s.zr); }   // cubic step
   else if (STEP == 13) s.zr = yv - s.zr;
