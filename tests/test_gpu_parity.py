@@ -558,8 +558,11 @@ def test_dirichlet_samples_live_on_the_simplex(qs):
     s.close()
     assert np.abs(v.sum(axis=2) - 1.0).max() < 1e-12 and v.min() > 0.0
     assert np.abs(v.mean(axis=(0, 1)) - np.array([0.2, 0.3, 0.5])).max() < 0.01
-    with pytest.raises(L.QsbError):   # vector choices need the thread-per-chain mapping
-        qs.Sampler(prog, qs.HMCKernel(), numchains=4, mapping=32)
+    # the warp-per-chain mapping takes vector choices too (tests/test_gpu_vector_warp.py): same simplex, same chains
+    s = qs.Sampler(prog, qs.HMCKernel(), numchains=4, mapping=32)
+    s.init(); s.run(20, 5, 1)
+    v = s.fetch_values(); s.close()
+    assert np.abs(v.sum(axis=2) - 1.0).max() < 1e-12 and (v >= 0).all()
 
 
 def test_reference_compile_and_run_programs(qs, oracle):
@@ -733,7 +736,11 @@ def test_latent_parameter_descriptor_errors(qs):
     p.arrays["erp_kind"][1] = L.ERP_UNIFORM          # a uniform's parameters are its bounds: not supported as latent
     with pytest.raises(L.QsbError):
         p.model()
-    p = qs.programs.indep([("gaussian", 0.0, 1.0)] + [("gaussian", lat(0), 1.0)] * 40, ret="vector")   # 41 components: no thread-per-chain variant
+    p = qs.programs.indep([("gaussian", 0.0, 1.0)] + [("gaussian", lat(0), 1.0)] * 40, ret="vector")   # 41 components: warp per chain
+    qs.Sampler(p, qs.HMCKernel(), numchains=4).close()
+    with pytest.raises(L.QsbError):                   # ... but thread per chain holds at most 32
+        qs.Sampler(p, qs.HMCKernel(), numchains=4, mapping=1)
+    p = qs.programs.indep([("gaussian", 0.0, 1.0)] + [("gaussian", lat(0), 1.0)] * 140, ret="vector")  # 141 components: beyond the INDEP family
     with pytest.raises(L.QsbError):
         qs.Sampler(p, qs.HMCKernel(), numchains=4)
 
