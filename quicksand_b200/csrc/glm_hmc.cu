@@ -113,7 +113,7 @@ static constexpr int GRAD_THREADS = CW * 32;
 #ifndef QSB_GLM_PERM
 #define QSB_GLM_PERM 1
 #endif
-static constexpr bool PERMX = QSB_GLM_PERM != 0 && !THETA_SMEM;   // (the Theta-in-shared-memory builds keep the natural layout)
+static constexpr bool PERMX = QSB_GLM_PERM != 0;
 static constexpr int PERM_PJ = 14, PERM_S = 114;
 
 struct GradParams {
@@ -372,7 +372,11 @@ __device__ __forceinline__ void glm_grad_body(const GradParams& P, bool& pdl_pen
     double2 xv[NT];
 #pragma unroll
     for (int T = 0; T < NT; ++T) xv[T] = *reinterpret_cast<const double2*>(Xs + T * 8 * S + offP + sidx * PERM_PJ + J);
-    const double t0 = th[J % (THETA_SMEM ? 1 : NJ)][sidx], t1 = th[(J + 1) % (THETA_SMEM ? 1 : NJ)][sidx];
+    double t0, t1;
+    if (THETA_SMEM) {      // (conflict-free as LDS.128 of the dimension pair; the k-step picks its half)
+      const double2 v0 = *reinterpret_cast<const double2*>(sTh + 8 * J), v1 = *reinterpret_cast<const double2*>(sTh + 8 * (J + 1));
+      t0 = sidx ? v0.y : v0.x; t1 = sidx ? v1.y : v1.x;
+    } else { t0 = th[J % (THETA_SMEM ? 1 : NJ)][sidx]; t1 = th[(J + 1) % (THETA_SMEM ? 1 : NJ)][sidx]; }
 #pragma unroll
     for (int T = 0; T < NT; ++T) dmma(a[T], t0, xv[T].x);
 #pragma unroll
